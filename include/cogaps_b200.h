@@ -1,0 +1,292 @@
+/*
+ * cogaps_b200.h — C ABI of the B200-native CoGAPS hot path.
+ *
+ * This is the drop-in boundary for ONE path of FertigLab/CoGAPS: the atomic-domain Gibbs
+ * sampler that alternately updates the A and P factor matrices.  Every entry point below
+ * replaces one member of the reference's implicit "Sampler concept" (what
+ * runCoGAPSAlgorithm<Sampler> and GapsStatistics call) or the run loop itself; the
+ * reference interface each one stands in for is cited as file:line relative to the
+ * reference tree.  INTEGRATION.md shows the C++ adapter a maintainer would add next to
+ * chooseSampler (src/GapsRunner.cpp:65-78) to bind these.
+ *
+ * Conventions
+ *   - extern "C", plain pointers and sizes, opaque handles, no C++/torch types.
+ *   - Every call returns an int status: CGB_OK (0) or a negative CGB_E* code;
+ *     cgb_last_error() returns a thread-local message for the last failure.
+ *     (The reference prints and calls Rcpp::stop / exit — utils/GapsAssert.h:18-25; the
+ *     C++ adapter turns a non-zero status back into GAPS_ERROR.)
+ *   - Host pointers are borrowed for the duration of the call only; the library owns all
+ *     device memory.  Matrices cross the boundary as fp32 row-major (element (i,j) at
+ *     ptr[i*ncol + j]) unless a `colmajor` flag says otherwise.
+ *   - A handle is not thread-safe; one host thread drives one handle (the reference calls
+ *     the sampler from one thread and fans out with OpenMP inside — here the fan-out is
+ *     the GPU).
+ *   - There is no CPU fallback: if no sm_100-class device is usable the calls that need
+ *     one fail with CGB_ENODEVICE.
+ */
+#ifndef COGAPS_B200_H
+#define COGAPS_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define CGB_OK            0
+#define CGB_EINVAL       -1   /* bad argument */
+#define CGB_ENODEVICE    -2   /* no usable CUDA device */
+#define CGB_ECUDA        -3   /* CUDA runtime / kernel failure */
+#define CGB_ENOMEM       -4
+#define CGB_EUNSUPPORTED -5   /* feature of the reference not on this path yet */
+#define CGB_EINTERNAL    -6
+
+#define CGB_ERF_TABLE_SIZE     3001  /* math/Random.h:13 */
+#define CGB_ERFINV_TABLE_SIZE  5001  /* math/Random.h:14 */
+#define CGB_QGAMMA_TABLE_SIZE  5001  /* math/Random.h:15 */
+
+#define CGB_PHASE_EQUILIBRATION 1    /* GapsParameters.h:19-24 */
+#define CGB_PHASE_SAMPLING      2
+#define CGB_PHASE_ALL           3
+
+const char *cgb_last_error(void);
+/* library / kernel build facts: "sm_100a;threads=256;..." (utils/GlobalConfig.h:26-54 buildReport) */
+const char *cgb_build_report(void);
+/* select the CUDA device used by handles created afterwards (default: COGAPS_DEVICE env or 0) */
+int cgb_set_device(int device);
+/* number of kernel launches issued by this library since process start (bench.py gpu_launches) */
+uint64_t cgb_kernel_launch_count(void);
+
+/* ------------------------------------------------------------------------------------------
+ * Run parameters — mirrors struct GapsParameters (src/GapsParameters.h:25-70, defaults :79-114)
+ * ---------------------------------------------------------------------------------------- */
+typedef struct cgb_params
+{
+    uint32_t struct_size;          /* = sizeof(cgb_params); ABI guard */
+    uint32_t seed;
+    uint32_t nPatterns;            /* default 3 */
+    uint32_t nIterations;          /* per phase, default 1000 */
+    uint32_t maxThreads;           /* accepted, unused on the device path */
+    uint32_t outputFrequency;      /* default 500; 0 = never */
+    uint32_t snapshotFrequency;    /* default 0 */
+    uint32_t snapshotPhase;        /* CGB_PHASE_* ; default ALL */
+    float alphaA;                  /* 0.01 */
+    float alphaP;                  /* 0.01 */
+    float maxGibbsMassA;           /* 100 */
+    float maxGibbsMassP;           /* 100 */
+    int32_t transposeData;
+    int32_t useSparseOptimization; /* SparseNormalModel — CGB_EUNSUPPORTED for now */
+    int32_t asynchronousUpdates;   /* must be 1: the device path is the asynchronous sampler */
+    int32_t takePumpSamples;
+    int32_t printMessages;
+    int32_t whichMatrixFixed;      /* 'N', 'A' or 'P' */
+    int32_t subsetGenes;           /* meaning of subsetIndices: 1 = genes, 0 = samples */
+    uint32_t nSubsetIndices;       /* 0 = no subsetting */
+    const uint32_t *subsetIndices; /* 1-based, like R (data_structures/Matrix.cpp:30-69) */
+    const float *fixedPatterns;    /* rows(of the fixed matrix) x nPatterns row-major, or NULL */
+    uint32_t workerID;             /* default 1 */
+    int32_t runningDistributed;
+} cgb_params;
+
+/* fill *p with the reference defaults (GapsParameters.h:79-114) */
+void cgb_params_default(cgb_params *p);
+
+/* ------------------------------------------------------------------------------------------
+ * Run result — mirrors struct GapsResult (src/GapsResult.h:11-36).  All arrays are
+ * caller-allocated; capacities are given, counts are written back.
+ * ---------------------------------------------------------------------------------------- */
+typedef struct cgb_result
+{
+    uint32_t struct_size;
+    uint32_t historyCapacity;      /* in: room in the three history arrays */
+    float *Amean;                  /* nGenes   x nPatterns row-major */
+    float *Asd;
+    float *Pmean;                  /* nSamples x nPatterns row-major */
+    float *Psd;
+    float *chisqHistory;           /* one entry per outputFrequency iterations, both phases */
+    uint32_t *atomHistoryA;
+    uint32_t *atomHistoryP;
+    float *pumpMatrix;             /* optional (NULL ok): nGenes x nPatterns */
+    float *meanPatternAssignment;  /* optional */
+    float *snapshotsA;             /* optional: snapshotCapacity x nGenes x nPatterns, equilibration then sampling */
+    float *snapshotsP;             /* optional: snapshotCapacity x nSamples x nPatterns */
+    uint32_t snapshotCapacity;
+    uint32_t nSnapshotsEquilibration; /* out */
+    uint32_t nSnapshotsSampling;      /* out */
+    uint32_t nHistory;             /* out */
+    uint32_t seed;                 /* out */
+    uint64_t totalUpdates;         /* out */
+    double totalRunningTime;       /* out, seconds in the sampler loop (reference: whole seconds) */
+    float meanChiSq;               /* out */
+    float averageQueueLengthA;     /* out */
+    float averageQueueLengthP;     /* out */
+    /* extras the reference does not report; used by bench.py */
+    uint64_t nBatchesA;            /* out: proposal batches evaluated (= eval-kernel launches) */
+    uint64_t nBatchesP;
+    double secondsUpdateA;         /* out: host wall time inside A.update / P.update */
+    double secondsUpdateP;
+    double secondsDevice;          /* out: CUDA-event time of all eval kernels */
+    double algorithmicBytes;       /* out: SURVEY 8(d) reference-formulation bytes of all evaluated proposals */
+} cgb_result;
+
+/* ------------------------------------------------------------------------------------------
+ * gaps::run (src/GapsRunner.h:14-24, src/GapsRunner.cpp:113-117,381-503)
+ * data: nrow x ncol fp32 (row-major unless colmajor != 0); uncertainty: same shape or NULL.
+ * ---------------------------------------------------------------------------------------- */
+int cgb_run(const float *data, uint32_t nrow, uint32_t ncol, int32_t colmajor,
+            const float *uncertainty, const cgb_params *params, cgb_result *result);
+
+/* ------------------------------------------------------------------------------------------
+ * GapsRandomState (src/math/Random.h:79-98): the xoroshiro128+ seeder every sampler and every
+ * proposal pulls its PCG seed from, plus the three lookup tables.
+ * ---------------------------------------------------------------------------------------- */
+typedef struct cgb_randstate cgb_randstate;
+int cgb_randstate_create(uint32_t seed, cgb_randstate **out);          /* Random.cpp:264-267 */
+/* Replace the built-in tables (a host that links Boost passes the reference's own:
+ * Random.cpp:269-295).  Must be called before samplers are created. */
+int cgb_randstate_set_tables(cgb_randstate *rs, const float *erf, const float *erfinv,
+                             const float *qgamma);
+int cgb_randstate_get_tables(const cgb_randstate *rs, float *erf, float *erfinv, float *qgamma);
+int cgb_randstate_next_seed(cgb_randstate *rs, uint64_t *out);         /* Random.cpp:297-300 */
+void cgb_randstate_destroy(cgb_randstate *rs);
+
+/* A GapsRng stream (Random.cpp:32-200), host side; used by the run loop for the Poisson
+ * update counts (GapsRunner.cpp:294-295) and exposed for known-answer tests. */
+typedef struct cgb_rng cgb_rng;
+int cgb_rng_create(cgb_randstate *rs, cgb_rng **out);
+int cgb_rng_uniform32(cgb_rng *r, uint32_t *out);
+int cgb_rng_uniform32_range(cgb_rng *r, uint32_t a, uint32_t b, uint32_t *out);
+int cgb_rng_uniform64_range(cgb_rng *r, uint64_t a, uint64_t b, uint64_t *out);
+int cgb_rng_uniform(cgb_rng *r, float *out);
+int cgb_rng_poisson(cgb_rng *r, double lambda, int32_t *out);
+int cgb_rng_exponential(cgb_rng *r, float lambda, float *out);
+int cgb_rng_trunc_normal(cgb_rng *r, float a, float b, float mean, float sd, float *out,
+                         int32_t *has_value);
+int cgb_rng_trunc_gamma_upper(cgb_rng *r, float b, float scale, float *out);
+void cgb_rng_destroy(cgb_rng *r);
+
+/* ------------------------------------------------------------------------------------------
+ * The Sampler concept: AsynchronousGibbsSampler<DenseNormalModel>
+ * (src/gibbs_sampler/AsynchronousGibbsSampler.h:31-56, DenseNormalModel.h:15-64).
+ * One handle per factor matrix, exactly as the reference builds ASampler and PSampler
+ * (GapsRunner.cpp:402-406).
+ * ---------------------------------------------------------------------------------------- */
+typedef struct cgb_sampler cgb_sampler;
+
+/* ctor (AsynchronousGibbsSampler.h:63-76 + DenseNormalModel.h:66-88).  `transpose` and
+ * `subsetRows` have the reference's meaning (Matrix.cpp:30-69: genesInCols / subsetGenes);
+ * the A sampler is created with transpose = !transposeData, the P sampler with transposeData. */
+int cgb_sampler_create(const float *data, uint32_t nrow, uint32_t ncol, int32_t colmajor,
+                       int32_t transpose, int32_t subsetRows, float alpha, float maxGibbsMass,
+                       const cgb_params *params, cgb_randstate *rs, cgb_sampler **out);
+void cgb_sampler_destroy(cgb_sampler *s);
+/* setUncertainty (DenseNormalModel.h:90-95) */
+int cgb_sampler_set_uncertainty(cgb_sampler *s, const float *unc, uint32_t nrow, uint32_t ncol,
+                                int32_t colmajor, int32_t transpose, int32_t subsetRows,
+                                const cgb_params *params);
+/* setMatrix (DenseNormalModel.cpp:9-12): rows x nPatterns row-major */
+int cgb_sampler_set_matrix(cgb_sampler *s, const float *mat);
+/* setAnnealingTemp (DenseNormalModel.cpp:14-17) */
+int cgb_sampler_set_annealing_temp(cgb_sampler *s, float temp);
+/* sync (DenseNormalModel.cpp:20-36): AP <- transpose(other.AP), repoint the other factor */
+int cgb_sampler_sync(cgb_sampler *s, const cgb_sampler *other);
+/* extraInitialization (DenseNormalModel.cpp:38-54): AP <- Other * Matrix^T */
+int cgb_sampler_extra_initialization(cgb_sampler *s);
+/* update (AsynchronousGibbsSampler.h:88-122): nSteps birth/death/move/exchange proposals */
+int cgb_sampler_update(cgb_sampler *s, uint32_t nSteps, uint32_t nThreads);
+/* chiSq (DenseNormalModel.cpp:56-68) */
+int cgb_sampler_chisq(const cgb_sampler *s, float *out);
+/* nAtoms (AsynchronousGibbsSampler.h:78-82) */
+int cgb_sampler_n_atoms(const cgb_sampler *s, uint64_t *out);
+/* dataSparsity (DenseNormalModel.cpp:70-73) */
+int cgb_sampler_data_sparsity(const cgb_sampler *s, float *out);
+/* getAverageQueueLength (AsynchronousGibbsSampler.h:84-88) */
+int cgb_sampler_average_queue_length(const cgb_sampler *s, float *out);
+/* mMatrix.getMatrix() (read by GapsStatistics.h:129-202): rows x nPatterns row-major */
+int cgb_sampler_get_matrix(const cgb_sampler *s, float *out);
+/* shape of the factor matrix this sampler owns */
+int cgb_sampler_shape(const cgb_sampler *s, uint32_t *rows, uint32_t *nPatterns, uint32_t *rowLength);
+/* lambda / maxGibbsMass after the ctor's rescaling (DenseNormalModel.h:79-81) */
+int cgb_sampler_lambda(const cgb_sampler *s, float *lambda, float *maxGibbsMass);
+/* atomic domain contents (operator<< of ConcurrentAtomicDomain, ConcurrentAtomicDomain.cpp:133-141):
+ * atoms in the reference's vector order; pass NULLs to query the count */
+int cgb_sampler_get_atoms(const cgb_sampler *s, uint64_t *pos, float *mass, uint64_t capacity,
+                          uint64_t *count);
+/* cached AP row (debug / tests): row of the sampler's AP matrix, rowLength floats */
+int cgb_sampler_get_ap_row(const cgb_sampler *s, uint32_t row, float *out);
+
+/* Lock-step probes of the three scan variants (DenseNormalModel.cpp:162-240), evaluated by the
+ * same device code the update uses.  n queries; r2/c2 may equal r1/c1.  variant: 0 =
+ * alphaParameters(r1,c1); 1 = alphaParameters(r1,c1,r2,c2); 2 = alphaParametersWithChange(r1,c1,ch). */
+int cgb_sampler_alpha_parameters(cgb_sampler *s, uint32_t n, const int32_t *variant,
+                                 const uint32_t *r1, const uint32_t *c1, const uint32_t *r2,
+                                 const uint32_t *c2, const float *ch, float *s_out, float *smu_out);
+
+/* Per-sampler counters accumulated over update() calls (bench.py). */
+typedef struct cgb_sampler_counters
+{
+    uint64_t nBatches;          /* eval-kernel launches */
+    uint64_t nProposalsQueued;  /* proposals evaluated on the device */
+    uint64_t nProposalsTotal;   /* nSteps processed (includes same-bin moves/exchanges) */
+    double algorithmicBytes;    /* SURVEY 8(d) bytes of the queued proposals */
+    double secondsHostGenerate; /* wall time in proposal generation + bookkeeping */
+    double secondsDeviceWait;   /* wall time launching + waiting for the device */
+    double secondsKernel;       /* CUDA-event time of eval kernels (only when timing enabled) */
+} cgb_sampler_counters;
+int cgb_sampler_get_counters(const cgb_sampler *s, cgb_sampler_counters *out);
+int cgb_sampler_reset_counters(cgb_sampler *s);
+/* enable CUDA-event timing of every eval-kernel launch (costs a sync each; bench roofline leg) */
+int cgb_sampler_set_kernel_timing(cgb_sampler *s, int32_t enabled);
+
+/* The device reduction order of the scan, so a checker can reproduce it bit-for-bit:
+ * a row of length L is cut into `nSegments` contiguous segments of `segmentLength` floats;
+ * within a segment element e belongs to lane ((e / vectorWidth) % threadsPerSegment); lanes
+ * sum their elements in increasing index order; 32 consecutive lanes combine by an xor
+ * butterfly (offsets 16,8,4,2,1); warp totals, then segment totals, add in increasing order. */
+typedef struct cgb_reduction_order
+{
+    uint32_t threadsPerSegment;
+    uint32_t vectorWidth;
+    uint32_t nSegments;
+    uint32_t segmentLength;
+} cgb_reduction_order;
+int cgb_sampler_reduction_order(const cgb_sampler *s, cgb_reduction_order *out);
+
+/* ------------------------------------------------------------------------------------------
+ * GapsStatistics (src/GapsStatistics.h:17-64): running sums for Amean/Asd/Pmean/Psd kept on
+ * the device next to the factor matrices.
+ * ---------------------------------------------------------------------------------------- */
+typedef struct cgb_stats cgb_stats;
+int cgb_stats_create(uint32_t nGenes, uint32_t nSamples, uint32_t nPatterns, cgb_stats **out);
+void cgb_stats_destroy(cgb_stats *st);
+int cgb_stats_update(cgb_stats *st, const cgb_sampler *A, const cgb_sampler *P);   /* GapsStatistics.h:129-149 */
+int cgb_stats_update_a(cgb_stats *st, const cgb_sampler *A, const cgb_sampler *P); /* :151-167 */
+int cgb_stats_update_p(cgb_stats *st, const cgb_sampler *A, const cgb_sampler *P); /* :169-185 */
+int cgb_stats_update_pump(cgb_stats *st, const cgb_sampler *A);                    /* :119-127 */
+int cgb_stats_amean(const cgb_stats *st, float *out);   /* GapsStatistics.cpp:13-21 */
+int cgb_stats_asd(const cgb_stats *st, float *out);     /* :23-36 */
+int cgb_stats_pmean(const cgb_stats *st, float *out);   /* :38-46 */
+int cgb_stats_psd(const cgb_stats *st, float *out);     /* :48-61 */
+int cgb_stats_pump_matrix(const cgb_stats *st, float *out);          /* :113-117 */
+int cgb_stats_mean_pattern(const cgb_stats *st, float *out);         /* :119-131 */
+/* meanChiSq (GapsStatistics.cpp:63-87) against the P sampler's D and S */
+int cgb_stats_mean_chisq(const cgb_stats *st, const cgb_sampler *P, float *out);
+
+/* ------------------------------------------------------------------------------------------
+ * Multi-GPU: one process per GPU, each running an independent chain on its own
+ * subset (R/DistributedCogaps.R:48-119).  The only exchange is the concatenation of per-shard
+ * factor rows (stitchTogether, R/DistributedCogaps.R:226-278), done by the caller with NCCL on
+ * device buffers obtained here.
+ * ---------------------------------------------------------------------------------------- */
+/* device pointer + stride of the sampler's factor matrix, column (pattern) major:
+ * element (row r, pattern p) at dev[p * ld + r] */
+int cgb_sampler_device_matrix(const cgb_sampler *s, void **dev, uint64_t *ld);
+/* device pointers of the statistics sums (same layout) */
+int cgb_stats_device_sums(const cgb_stats *st, void **AmeanSum, void **AsqSum, void **PmeanSum,
+                          void **PsqSum, uint64_t *ldA, uint64_t *ldP, uint32_t *nUpdates);
+
+#ifdef __cplusplus
+}
+#endif
+
+#endif /* COGAPS_B200_H */

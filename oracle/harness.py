@@ -1,0 +1,97 @@
+"""ctypes loaders for the two CPU checkers.  TEST INFRASTRUCTURE ONLY.
+
+  RefLib(variant)  -> oracle/_ref/libcogaps_ref_<variant>.so  (the unmodified reference, compiled in place)
+  OracleLib()      -> oracle/libcogaps_oracle.so              (our C restatement)
+
+Only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline / --impl reference legs import this.
+"""
+import ctypes as C
+import os
+import numpy as np
+
+from cogaps_b200._abi import (CgbParams, CgbResult, c_float_p, c_u32_p, c_u64_p, c_i32_p,
+                              ERF_TABLE_SIZE, ERFINV_TABLE_SIZE, QGAMMA_TABLE_SIZE)
+from cogaps_b200._runhelp import make_params, ResultArrays, fptr
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+
+
+def _f32(a):
+    return np.ascontiguousarray(a, dtype=np.float32)
+
+
+def _u32(a):
+    return np.ascontiguousarray(a, dtype=np.uint32)
+
+
+class RefLib(object):
+    """The reference C++ core behind oracle/ref_driver.cpp."""
+
+    def __init__(self, variant="scalar"):
+        path = os.path.join(HERE, "_ref", "libcogaps_ref_%s.so" % variant)
+        if not os.path.exists(path):
+            raise OSError("reference build %s missing - run `make -C oracle ref` where /root/reference exists" % path)
+        self.variant = variant
+        self.lib = C.CDLL(path)
+        self.lib.cogaps_ref_build_report.restype = C.c_char_p
+        self.lib.cogaps_ref_rng_stream.argtypes = [C.c_uint32, C.c_int, C.c_uint32, C.c_uint64, C.c_uint64,
+                                                   C.c_double, C.c_float, C.c_float, C.c_float, C.c_float, c_u64_p]
+
+    @staticmethod
+    def available(variant="scalar"):
+        return os.path.exists(os.path.join(HERE, "_ref", "libcogaps_ref_%s.so" % variant))
+
+    def build_report(self):
+        return self.lib.cogaps_ref_build_report().decode()
+
+    def max_threads(self):
+        return self.lib.cogaps_ref_max_threads()
+
+    def run(self, data, uncertainty=None, snapshots=False, **kw):
+        data = _f32(data)
+        unc = _f32(uncertainty) if uncertainty is not None else None
+        p = make_params(**kw)
+        res = ResultArrays(p, data.shape[0], data.shape[1], snapshots=snapshots)
+        rc = self.lib.cogaps_ref_run(fptr(data), C.c_uint32(data.shape[0]), C.c_uint32(data.shape[1]),
+                                     fptr(unc), C.byref(p), C.byref(res.c))
+        if rc != 0:
+            raise RuntimeError("cogaps_ref_run failed: %d" % rc)
+        return res.finish()
+
+    def tables(self):
+        erf = np.zeros(ERF_TABLE_SIZE, np.float32)
+        erfinv = np.zeros(ERFINV_TABLE_SIZE, np.float32)
+        qgamma = np.zeros(QGAMMA_TABLE_SIZE, np.float32)
+        self.lib.cogaps_ref_tables(fptr(erf), fptr(erfinv), fptr(qgamma))
+        return erf, erfinv, qgamma
+
+    def rng_stream(self, seed, kind, n, a=0, b=0, lam=0.0, f=(0.0, 0.0, 0.0, 0.0)):
+        out = np.zeros(n, np.uint64)
+        rc = self.lib.cogaps_ref_rng_stream(seed, kind, n, a, b, lam, f[0], f[1], f[2], f[3],
+                                            out.ctypes.data_as(c_u64_p))
+        if rc != 0:
+            raise RuntimeError("cogaps_ref_rng_stream failed")
+        return out
+
+    def alpha_parameters(self, data, A, P, queries, uncertainty=None, want_ap=False):
+        """queries: list of (variant, r1, c1, r2, c2, ch)."""
+        data, A, P = _f32(data), _f32(A), _f32(P)
+        g, s = data.shape
+        k = A.shape[1]
+        q = np.asarray(queries, dtype=np.float64).reshape(-1, 6)
+        n = q.shape[0]
+        variant = np.ascontiguousarray(q[:, 0], dtype=np.int32)
+        r1, c1, r2, c2 = (_u32(q[:, i]) for i in (1, 2, 3, 4))
+        ch = _f32(q[:, 5])
+        s_out = np.zeros(n, np.float32)
+        smu_out = np.zeros(n, np.float32)
+        ap = np.zeros((g, s), np.float32) if want_ap else None
+        unc = _f32(uncertainty) if uncertainty is not None else None
+        rc = self.lib.cogaps_ref_alpha_parameters(
+            fptr(data), C.c_uint32(g), C.c_uint32(s), C.c_uint32(k), fptr(A), fptr(P), fptr(unc),
+            C.c_uint32(n), variant.ctypes.data_as(c_i32_p), r1.ctypes.data_as(c_u32_p),
+            c1.ctypes.data_as(c_u32_p), r2.ctypes.data_as(c_u32_p), c2.ctypes.data_as(c_u32_p),
+            fptr(ch), fptr(s_out), fptr(smu_out), fptr(ap))
+        if rc != 0:
+            raise RuntimeError("cogaps_ref_alpha_parameters failed")
+        return (s_out, smu_out, ap) if want_ap else (s_out, smu_out)
