@@ -1794,7 +1794,7 @@ int cogaps_oracle_run_trace(const float *data, uint32_t nrow, uint32_t ncol, con
         {
             /* meanPattern, GapsStatistics.cpp:119-131 on Amean() */
             size_t n = (size_t)nGenes * p->nPatterns;
-            float *am = (float*)malloc(sizeof(float) * n);
+            float *am = (float*)calloc(n, sizeof(float));
             float *mp = (float*)calloc(n, sizeof(float));
             for (size_t i = 0; i < n; ++i) { am[i] = st.Amean[i] / (float)st.statUpdates; }
             pump_threshold(am, nGenes, p->nPatterns, mp);
@@ -1913,4 +1913,34 @@ int cogaps_oracle_alpha_parameters(const float *data, uint32_t nGenes, uint32_t 
     model_free(&A);
     model_free(&P);
     return rc;
+}
+
+int cogaps_oracle_chisq(const float *data, uint32_t nGenes, uint32_t nSamples, uint32_t k,
+                        const float *Amat, const float *Pmat, const float *uncertainty, float *out)
+{
+    cgb_params p;
+    memset(&p, 0, sizeof(p));
+    p.nPatterns = k;
+    p.alphaA = p.alphaP = 0.01f;
+    p.maxGibbsMassA = p.maxGibbsMassP = 100.f;
+    model_t A, P;
+    model_init(&A, data, nGenes, nSamples, 1, 1, &p, p.alphaA, p.maxGibbsMassA, NULL, 1);
+    model_init(&P, data, nGenes, nSamples, 0, 0, &p, p.alphaP, p.maxGibbsMassP, NULL, 0);
+    if (uncertainty)
+    {
+        model_set_uncertainty(&A, uncertainty, nGenes, nSamples, 1, 1, &p);
+        model_set_uncertainty(&P, uncertainty, nGenes, nSamples, 0, 0, &p);
+    }
+    model_set_matrix(&A, Amat);
+    model_set_matrix(&P, Pmat);
+    model_sync(&A, &P);
+    model_sync(&P, &A);
+    model_extra_initialization(&A);
+    model_extra_initialization(&P);
+    out[0] = model_chisq(&A);
+    out[1] = model_chisq(&P);
+    out[2] = model_data_sparsity(&P);
+    model_free(&A);
+    model_free(&P);
+    return 0;
 }

@@ -82,6 +82,10 @@ int cogaps_oracle_alpha_parameters(const float *data, uint32_t nGenes, uint32_t 
                                    const float *ch, float *s_out, float *smu_out, float *ap_out,
                                    const oracle_options *opt);
 
+/* chiSq of the A-side (out[0]) and P-side (out[1]) models for given factors; out[2] = dataSparsity */
+int cogaps_oracle_chisq(const float *data, uint32_t nGenes, uint32_t nSamples, uint32_t k,
+                        const float *A, const float *P, const float *uncertainty, float *out);
+
 float cogaps_oracle_portable_logf(float x);
 
 #ifdef __cplusplus

@@ -96,6 +96,16 @@ class RefLib(object):
             raise RuntimeError("cogaps_ref_alpha_parameters failed")
         return (s_out, smu_out, ap) if want_ap else (s_out, smu_out)
 
+    def chisq(self, data, A, P, uncertainty=None):
+        data, A, P = _f32(data), _f32(A), _f32(P)
+        unc = _f32(uncertainty) if uncertainty is not None else None
+        out = np.zeros(3, np.float32)
+        rc = self.lib.cogaps_ref_chisq(fptr(data), C.c_uint32(data.shape[0]), C.c_uint32(data.shape[1]),
+                         C.c_uint32(A.shape[1]), fptr(A), fptr(P), fptr(unc), fptr(out))
+        if rc != 0:
+            raise RuntimeError("chisq probe failed")
+        return out
+
 
 class OracleOptions(C.Structure):
     _fields_ = [
@@ -218,3 +228,13 @@ class OracleLib(object):
         if rc != 0:
             raise RuntimeError("cogaps_oracle_alpha_parameters failed")
         return (s_out, smu_out, ap) if want_ap else (s_out, smu_out)
+
+    def chisq(self, data, A, P, uncertainty=None):
+        data, A, P = _f32(data), _f32(A), _f32(P)
+        unc = _f32(uncertainty) if uncertainty is not None else None
+        out = np.zeros(3, np.float32)
+        rc = self.lib.cogaps_oracle_chisq(fptr(data), C.c_uint32(data.shape[0]), C.c_uint32(data.shape[1]),
+                         C.c_uint32(A.shape[1]), fptr(A), fptr(P), fptr(unc), fptr(out))
+        if rc != 0:
+            raise RuntimeError("chisq probe failed")
+        return out

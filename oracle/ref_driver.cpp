@@ -274,4 +274,32 @@ int cogaps_ref_alpha_parameters(const float *data, uint32_t nGenes, uint32_t nSa
     return 0;
 }
 
+// DenseNormalModel::chiSq (src/gibbs_sampler/DenseNormalModel.cpp:56-68) of both models for given
+// factor matrices; out[0] = A-side model, out[1] = P-side model.
+int cogaps_ref_chisq(const float *data, uint32_t nGenes, uint32_t nSamples, uint32_t k,
+                     const float *A, const float *P, const float *uncertainty, float *out)
+{
+    Matrix D = toMatrix(data, nGenes, nSamples);
+    GapsParameters params(D);
+    params.nPatterns = k;
+    params.printMessages = false;
+    DenseNormalModel AModel(D, true, true, params, params.alphaA, params.maxGibbsMassA);
+    DenseNormalModel PModel(D, false, false, params, params.alphaP, params.maxGibbsMassP);
+    if (uncertainty != NULL)
+    {
+        Matrix U = toMatrix(uncertainty, nGenes, nSamples);
+        AModel.setUncertainty(U, true, true, params);
+        PModel.setUncertainty(U, false, false, params);
+    }
+    AModel.setMatrix(toMatrix(A, nGenes, k));
+    PModel.setMatrix(toMatrix(P, nSamples, k));
+    AModel.sync(PModel);
+    PModel.sync(AModel);
+    AModel.extraInitialization();
+    PModel.extraInitialization();
+    out[0] = AModel.chiSq();
+    out[1] = PModel.chiSq();
+    return 0;
+}
+
 } // extern "C"
