@@ -1,0 +1,223 @@
+"""The user-facing surface of the reference, kept name for name so a CoGAPS user can switch:
+
+    R: CoGAPS(data, params, nPatterns, nThreads, messages, outputFrequency, uncertainty, ..., ...)   R/CoGAPS.R:90-156
+    R: new("CogapsParams", ...), setParam, getParam                                                 R/class-CogapsParams.R:44-193
+    R: CogapsResult (featureLoadings, sampleFactors, loadingStdDev, factorStdDev, metadata)         R/class-CogapsResult.R:9-51
+    C++: gaps::run(data, params, uncertainty, randState)                                            src/GapsRunner.h:14-24
+
+R itself is not installed in this image, so this Python layer stands where R/CoGAPS.R stands: it validates
+and packs parameters exactly like getGapsParameters (src/Cogaps.cpp:63-139) and calls the C ABI's cgb_run.
+All computation happens in libcogaps_b200.so on the GPU.
+"""
+import ctypes as C
+import time
+
+import numpy as np
+
+from ._abi import PHASE_ALL, PHASE_EQUILIBRATION, PHASE_SAMPLING
+from ._lib import lib, check
+from ._runhelp import make_params, ResultArrays, fptr
+
+_PARAM_DEFAULTS = dict(
+    nPatterns=None, nIterations=50000, alphaA=0.01, alphaP=0.01, maxGibbsMassA=100.0, maxGibbsMassP=100.0,
+    seed=None, sparseOptimization=False, distributed=None, nSets=4, cut=None, minNS=None, maxNS=None,
+    explicitSets=None, samplingAnnotation=None, samplingWeight=None, subsetIndices=None, subsetDim=0,
+    geneNames=None, sampleNames=None, checkpointInterval=0, checkpointInFile=None, checkpointOutFile=None,
+    fixedPatterns=None, whichMatrixFixed="N", takePumpSamples=False,
+)
+
+
+class CogapsParams(object):
+    """S4 class CogapsParams (R/class-CogapsParams.R:44-123): same slots, same defaults, same validity rules."""
+
+    def __init__(self, nPatterns=7, distributed=None, **kw):
+        for bad in ("nSets", "cut", "minNS", "maxNS"):
+            if bad in kw:
+                raise ValueError("%s must be set after CogapsParams are intialized" % bad)
+        self.__dict__.update(_PARAM_DEFAULTS)
+        if distributed == "none":
+            distributed = None
+        self.distributed = distributed
+        self.nPatterns = nPatterns
+        self.seed = int((time.time() % 1) * 1000) or 1
+        self.cut = nPatterns
+        self.minNS = int(np.ceil(self.nSets / 2.0))
+        self.maxNS = self.minNS + self.nSets
+        for k, v in kw.items():
+            if k not in _PARAM_DEFAULTS:
+                raise ValueError("invalid slot name %r for CogapsParams" % k)
+            setattr(self, k, v)
+        self.validate()
+
+    def validate(self):
+        """setValidity("CogapsParams"), R/class-CogapsParams.R:126-193"""
+        def is_int(x):
+            return float(x) == int(x)
+        if self.nPatterns <= 0 or not is_int(self.nPatterns):
+            raise ValueError("number of patterns must be an integer greater than zero")
+        if self.nIterations <= 0 or not is_int(self.nIterations):
+            raise ValueError("number of iterations must be an integer greater than zero")
+        if self.alphaA <= 0 or self.alphaP <= 0:
+            raise ValueError("alpha parameter must be greater than zero")
+        if self.maxGibbsMassA <= 0 or self.maxGibbsMassP <= 0:
+            raise ValueError("maxGibbsMass must be greater than zero")
+        if self.seed <= 0 or not is_int(self.seed):
+            raise ValueError("random seed must be an integer greater than zero")
+        if self.whichMatrixFixed not in ("A", "P", "N"):
+            raise ValueError("Invalid choice of fixed matrix, must be 'A' or 'P'")
+        if self.fixedPatterns is not None and self.whichMatrixFixed == "N":
+            raise ValueError("fixedPatterns passed without setting whichMatrixFixed")
+        if self.whichMatrixFixed in ("A", "P") and self.fixedPatterns is None:
+            raise ValueError("whichMatrixFixed is set without passing fixedPatterns")
+        if self.subsetDim not in (0, 1, 2):
+            raise ValueError("invalid subset dimension")
+        if self.subsetDim > 0 and self.subsetIndices is None:
+            raise ValueError("subsetDim provided without subsetIndices")
+        if self.distributed is not None:
+            if self.distributed not in ("genome-wide", "single-cell"):
+                raise ValueError("distributed method must be either 'genome-wide' or 'single-cell'")
+            if self.distributed == "single-cell" and self.whichMatrixFixed == "P":
+                raise ValueError("can't fix P matrix when running single-cell CoGAPS")
+            if self.distributed == "genome-wide" and self.whichMatrixFixed == "A":
+                raise ValueError("can't fix A matrix when running genome-wide CoGAPS")
+            if self.cut > self.nPatterns:
+                raise ValueError("cut must be less than or equal to nPatterns")
+        return True
+
+    def setParam(self, name, value):
+        """setParam, R/methods-CogapsParams.R — nSets/nPatterns re-derive their dependents"""
+        if name not in _PARAM_DEFAULTS:
+            raise ValueError("invalid slot name %r for CogapsParams" % name)
+        setattr(self, name, value)
+        if name == "nSets":
+            self.minNS = int(np.ceil(value / 2.0))
+            self.maxNS = self.minNS + value
+        if name == "nPatterns":
+            self.cut = min(self.cut, value)
+        self.validate()
+        return self
+
+    def getParam(self, name):
+        return getattr(self, name)
+
+    def setFixedPatterns(self, fixedPatterns, whichMatrixFixed):
+        self.fixedPatterns = np.asarray(fixedPatterns, dtype=np.float32)
+        self.whichMatrixFixed = whichMatrixFixed
+        self.validate()
+        return self
+
+
+class CogapsResult(object):
+    """CogapsResult (R/class-CogapsResult.R:9-51, built by createCogapsResult, R/methods-CogapsResult.R:8-51)"""
+
+    def __init__(self, res, params, extras):
+        self.featureLoadings = res.Amean      # Amean, nGenes x nPatterns
+        self.sampleFactors = res.Pmean        # Pmean, nSamples x nPatterns
+        self.loadingStdDev = res.Asd
+        self.factorStdDev = res.Psd
+        self.metadata = dict(
+            meanChiSq=float(res.meanChiSq), chisq=res.chisqHistory, atomsA=res.atomHistoryA, atomsP=res.atomHistoryP,
+            totalUpdates=int(res.totalUpdates), totalRunningTime=float(res.totalRunningTime),
+            averageQueueLengthA=float(res.averageQueueLengthA), averageQueueLengthP=float(res.averageQueueLengthP),
+            seed=int(res.seed), params=params, firstPassResults=None, unmatchedPatterns=None, clusteredPatterns=None,
+            CorrToMeanPattern=None, subsets=None, version="cogaps_b200 (B200 device path)",
+            pumpStat=res.pumpMatrix if params.takePumpSamples else None,
+            meanPatternAssignment=res.meanPatternAssignment if params.takePumpSamples else None,
+            equilibrationSnapshotsA=res.snapshotsA[:res.nSnapshotsEquilibration],
+            equilibrationSnapshotsP=res.snapshotsP[:res.nSnapshotsEquilibration],
+            samplingSnapshotsA=res.snapshotsA[res.nSnapshotsEquilibration:],
+            samplingSnapshotsP=res.snapshotsP[res.nSnapshotsEquilibration:],
+        )
+        self.metadata.update(extras)
+
+    # accessors named like the R generics
+    def getFeatureLoadings(self):
+        return self.featureLoadings
+
+    def getAmplitudeMatrix(self):
+        return self.featureLoadings
+
+    def getSampleFactors(self):
+        return self.sampleFactors
+
+    def getPatternMatrix(self):
+        return self.sampleFactors
+
+    def getMeanChiSq(self):
+        return self.metadata["meanChiSq"]
+
+
+def gaps_run(data, uncertainty=None, snapshots=False, **kw):
+    """gaps::run (src/GapsRunner.h:14-24) through the C ABI: data nrow x ncol fp32 host array -> result arrays.
+    Keyword arguments are the fields of cgb_params / GapsParameters."""
+    data = np.ascontiguousarray(data, dtype=np.float32)
+    unc = np.ascontiguousarray(uncertainty, dtype=np.float32) if uncertainty is not None else None
+    if unc is not None and unc.shape != data.shape:
+        raise ValueError("uncertainty must have the same dimensions as the data")
+    p = make_params(**kw)
+    res = ResultArrays(p, data.shape[0], data.shape[1], snapshots=snapshots)
+    check(lib().cgb_run(fptr(data), data.shape[0], data.shape[1], 0, fptr(unc), C.byref(p), C.byref(res.c)))
+    return res.finish()
+
+
+_SNAPSHOT_PHASE = {"equilibration": PHASE_EQUILIBRATION, "sampling": PHASE_SAMPLING, "all": PHASE_ALL}
+
+
+def CoGAPS(data, params=None, nPatterns=None, nThreads=1, messages=True, outputFrequency=1000, uncertainty=None,
+           checkpointOutFile="gaps_checkpoint.out", checkpointInterval=0, checkpointInFile=None,
+           transposeData=False, BPPARAM=None, workerID=1, asynchronousUpdates=True, nSnapshots=0,
+           snapshotPhase="sampling", **kwargs):
+    """CoGAPS() — R/CoGAPS.R:90-156.  `data` is a genes x samples array (or samples x genes with
+    transposeData=True).  Extra keyword arguments overwrite slots of `params` (parseExtraParams,
+    R/HelperFunctions.R:165-183: unknown names are an error)."""
+    if params is None:
+        params = CogapsParams(nPatterns=nPatterns if nPatterns is not None else 7)
+    elif nPatterns is not None:
+        params.setParam("nPatterns", nPatterns)
+    for k, v in kwargs.items():
+        if k not in _PARAM_DEFAULTS:
+            raise ValueError("unrecognized argument: %s" % k)
+        params.setParam(k, v)
+    params.validate()
+    data = np.asarray(data)
+    # checkInputs, R/HelperFunctions.R:203-260
+    if data.ndim != 2:
+        raise ValueError("data must be a matrix")
+    if np.isnan(data).any():
+        raise ValueError("NA values in data")
+    if (data < 0).any():
+        raise ValueError("negative values in data matrix")
+    if uncertainty is not None:
+        uncertainty = np.asarray(uncertainty)
+        if (uncertainty < 0).any():
+            raise ValueError("negative values in uncertainty matrix")
+        if params.sparseOptimization:
+            raise ValueError("must use default uncertainty when enabling sparseOptimization")
+    if checkpointInFile is not None or checkpointInterval:
+        raise ValueError("checkpoints not supported in this build")  # R/HelperFunctions.R:225-226
+    if params.distributed is not None:
+        from .distributed import distributedCogaps
+        return distributedCogaps(data, params, uncertainty, nThreads=nThreads, messages=messages,
+                                 outputFrequency=outputFrequency, transposeData=transposeData)
+    nGenes, nSamples = (data.shape[1], data.shape[0]) if transposeData else data.shape
+    if params.nPatterns >= min(nGenes, nSamples) and params.subsetDim == 0:
+        pass  # R only warns here
+    kw = dict(seed=int(params.seed), nPatterns=int(params.nPatterns), nIterations=int(params.nIterations),
+              maxThreads=int(nThreads), outputFrequency=int(outputFrequency), alphaA=params.alphaA,
+              alphaP=params.alphaP, maxGibbsMassA=params.maxGibbsMassA, maxGibbsMassP=params.maxGibbsMassP,
+              transposeData=int(bool(transposeData)), useSparseOptimization=int(bool(params.sparseOptimization)),
+              asynchronousUpdates=int(bool(asynchronousUpdates)), takePumpSamples=int(bool(params.takePumpSamples)),
+              printMessages=int(bool(messages) and workerID == 1), whichMatrixFixed=params.whichMatrixFixed,
+              workerID=int(workerID))
+    if nSnapshots:
+        kw["snapshotFrequency"] = max(1, int(params.nIterations) // int(nSnapshots))  # Cogaps.cpp:95-99
+        kw["snapshotPhase"] = _SNAPSHOT_PHASE[snapshotPhase]
+    if params.subsetDim:
+        kw["subsetGenes"] = 1 if params.subsetDim == 1 else 0                          # Cogaps.cpp:120-126
+        kw["subsetIndices"] = np.asarray(params.subsetIndices, dtype=np.uint32)
+    if params.fixedPatterns is not None:
+        kw["fixedPatterns"] = np.asarray(params.fixedPatterns, dtype=np.float32)
+    res = gaps_run(data, uncertainty=uncertainty, snapshots=bool(nSnapshots), **kw)
+    extras = dict(nBatchesA=res.nBatchesA, nBatchesP=res.nBatchesP, secondsUpdateA=res.secondsUpdateA,
+                  secondsUpdateP=res.secondsUpdateP, algorithmicBytes=res.algorithmicBytes)
+    return CogapsResult(res, params, extras)

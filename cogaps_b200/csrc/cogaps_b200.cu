@@ -1,0 +1,1251 @@
+// cogaps_b200.cu — the C ABI (include/cogaps_b200.h): device-resident sampler state, kernel launches,
+// statistics and the gaps::run loop.  There is no CPU fallback anywhere in this file: every entry
+// point that computes needs an sm_100-class device and fails with CGB_ENODEVICE / CGB_ECUDA otherwise.
+#include "../../include/cogaps_b200.h"
+#include "kernels.cuh"
+#include "sampler.h"
+
+#include <chrono>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <new>
+#include <string>
+
+using namespace cgb;
+
+// ------------------------------------------------------------------------------------------------
+// error plumbing
+// ------------------------------------------------------------------------------------------------
+static thread_local std::string g_lastError;
+static uint64_t g_kernelLaunches = 0;
+static int g_device = -1;
+
+static int fail(int code, const std::string &msg)
+{
+    g_lastError = msg;
+    return code;
+}
+
+#define CGB_CUDA(call)                                                                                  \
+    do                                                                                                  \
+    {                                                                                                   \
+        cudaError_t e__ = (call);                                                                       \
+        if (e__ != cudaSuccess)                                                                         \
+        {                                                                                               \
+            const int code__ = (e__ == cudaErrorNoDevice || e__ == cudaErrorInsufficientDriver)         \
+                ? CGB_ENODEVICE : (e__ == cudaErrorMemoryAllocation ? CGB_ENOMEM : CGB_ECUDA);          \
+            return fail(code__, std::string(#call) + ": " + cudaGetErrorString(e__));                   \
+        }                                                                                               \
+    } while (0)
+
+#define CGB_CHECK(cond, msg)                                       \
+    do                                                             \
+    {                                                              \
+        if (!(cond)) { return fail(CGB_EINVAL, msg); }             \
+    } while (0)
+
+#define CGB_TRY(expr)                      \
+    do                                     \
+    {                                      \
+        int rc__ = (expr);                 \
+        if (rc__ != CGB_OK) { return rc__; } \
+    } while (0)
+
+static inline double nowSeconds()
+{
+    return std::chrono::duration<double>(std::chrono::steady_clock::now().time_since_epoch()).count();
+}
+
+static int envInt(const char *name, int dflt)
+{
+    const char *v = std::getenv(name);
+    return (v && *v) ? std::atoi(v) : dflt;
+}
+
+static int ensureDevice()
+{
+    if (g_device < 0) { g_device = envInt("COGAPS_DEVICE", 0); }
+    int n = 0;
+    cudaError_t e = cudaGetDeviceCount(&n);
+    if (e != cudaSuccess || n == 0)
+    {
+        return fail(CGB_ENODEVICE, std::string("no CUDA device: ") + (e != cudaSuccess ? cudaGetErrorString(e) : "count is 0"));
+    }
+    if (g_device >= n) { return fail(CGB_EINVAL, "COGAPS_DEVICE / cgb_set_device out of range"); }
+    CGB_CUDA(cudaSetDevice(g_device));
+    cudaDeviceProp prop;
+    CGB_CUDA(cudaGetDeviceProperties(&prop, g_device));
+    if (prop.major < 10)
+    {
+        return fail(CGB_ENODEVICE, std::string("device is sm_") + std::to_string(prop.major * 10 + prop.minor)
+            + "; this library is built for sm_100a only");
+    }
+    return CGB_OK;
+}
+
+extern "C" const char *cgb_last_error(void) { return g_lastError.c_str(); }
+
+extern "C" const char *cgb_build_report(void)
+{
+    static std::string s;
+    s = "cogaps_b200: sm_100a; eval kernel: " + std::to_string(kThreads) + " threads/CTA, "
+        + std::to_string(kVec) + "-float vectors, clusters <= " + std::to_string(kMaxCluster)
+        + ", <= " + std::to_string(kMaxBatch) + " proposals/launch; TMA bulk staging; no CPU fallback";
+    return s.c_str();
+}
+
+extern "C" int cgb_set_device(int device)
+{
+    g_device = device;
+    return ensureDevice();
+}
+
+extern "C" uint64_t cgb_kernel_launch_count(void) { return g_kernelLaunches; }
+
+extern "C" void cgb_params_default(cgb_params *p)
+{
+    std::memset(p, 0, sizeof(*p));
+    p->struct_size = sizeof(cgb_params);
+    p->nPatterns = 3;
+    p->nIterations = 1000;
+    p->maxThreads = 1;
+    p->outputFrequency = 500;
+    p->snapshotPhase = CGB_PHASE_ALL;
+    p->alphaA = 0.01f;
+    p->alphaP = 0.01f;
+    p->maxGibbsMassA = 100.f;
+    p->maxGibbsMassP = 100.f;
+    p->asynchronousUpdates = 1;
+    p->whichMatrixFixed = 'N';
+    p->workerID = 1;
+}
+
+// ------------------------------------------------------------------------------------------------
+// GapsRandomState / GapsRng
+// ------------------------------------------------------------------------------------------------
+extern "C" int cgb_randstate_create(uint32_t seed, cgb_randstate **out)
+{
+    CGB_CHECK(out != nullptr, "cgb_randstate_create: out is NULL");
+    *out = new (std::nothrow) cgb_randstate(seed);
+    return *out ? CGB_OK : fail(CGB_ENOMEM, "cgb_randstate_create: out of memory");
+}
+
+extern "C" int cgb_randstate_set_tables(cgb_randstate *rs, const float *erf, const float *erfinv, const float *qgamma)
+{
+    CGB_CHECK(rs && erf && erfinv && qgamma, "cgb_randstate_set_tables: NULL argument");
+    CGB_CHECK(rs->dErf == nullptr, "cgb_randstate_set_tables: tables already uploaded; set them before creating samplers");
+    std::memcpy(rs->tables.erf, erf, sizeof(rs->tables.erf));
+    std::memcpy(rs->tables.erfinv, erfinv, sizeof(rs->tables.erfinv));
+    std::memcpy(rs->tables.qgamma, qgamma, sizeof(rs->tables.qgamma));
+    return CGB_OK;
+}
+
+extern "C" int cgb_randstate_get_tables(const cgb_randstate *rs, float *erf, float *erfinv, float *qgamma)
+{
+    CGB_CHECK(rs && erf && erfinv && qgamma, "cgb_randstate_get_tables: NULL argument");
+    std::memcpy(erf, rs->tables.erf, sizeof(rs->tables.erf));
+    std::memcpy(erfinv, rs->tables.erfinv, sizeof(rs->tables.erfinv));
+    std::memcpy(qgamma, rs->tables.qgamma, sizeof(rs->tables.qgamma));
+    return CGB_OK;
+}
+
+extern "C" int cgb_randstate_next_seed(cgb_randstate *rs, uint64_t *out)
+{
+    CGB_CHECK(rs && out, "cgb_randstate_next_seed: NULL argument");
+    *out = rs->seeder.next();
+    return CGB_OK;
+}
+
+extern "C" void cgb_randstate_destroy(cgb_randstate *rs)
+{
+    if (!rs) { return; }
+    if (rs->dErf) { cudaFree(rs->dErf); }
+    if (rs->dErfinv) { cudaFree(rs->dErfinv); }
+    delete rs;
+}
+
+static int uploadTables(cgb_randstate *rs)
+{
+    if (rs->dErf) { return CGB_OK; }
+    CGB_CUDA(cudaMalloc(&rs->dErf, sizeof(rs->tables.erf)));
+    CGB_CUDA(cudaMalloc(&rs->dErfinv, sizeof(rs->tables.erfinv)));
+    CGB_CUDA(cudaMemcpy(rs->dErf, rs->tables.erf, sizeof(rs->tables.erf), cudaMemcpyHostToDevice));
+    CGB_CUDA(cudaMemcpy(rs->dErfinv, rs->tables.erfinv, sizeof(rs->tables.erfinv), cudaMemcpyHostToDevice));
+    return CGB_OK;
+}
+
+extern "C" int cgb_rng_create(cgb_randstate *rs, cgb_rng **out)
+{
+    CGB_CHECK(rs && out, "cgb_rng_create: NULL argument");
+    cgb_rng *r = new (std::nothrow) cgb_rng();
+    if (!r) { return fail(CGB_ENOMEM, "cgb_rng_create: out of memory"); }
+    r->rs = rs;
+    r->rng = HostRng(rs->seeder);
+    *out = r;
+    return CGB_OK;
+}
+extern "C" int cgb_rng_uniform32(cgb_rng *r, uint32_t *out) { *out = r->rng.next(); return CGB_OK; }
+extern "C" int cgb_rng_uniform32_range(cgb_rng *r, uint32_t a, uint32_t b, uint32_t *out) { *out = r->rng.uniform32(a, b); return CGB_OK; }
+extern "C" int cgb_rng_uniform64_range(cgb_rng *r, uint64_t a, uint64_t b, uint64_t *out) { *out = r->rng.uniform64(a, b); return CGB_OK; }
+extern "C" int cgb_rng_uniform(cgb_rng *r, float *out) { *out = r->rng.uniform(); return CGB_OK; }
+extern "C" int cgb_rng_poisson(cgb_rng *r, double lambda, int32_t *out) { *out = r->rng.poisson(lambda); return CGB_OK; }
+extern "C" int cgb_rng_exponential(cgb_rng *r, float lambda, float *out) { *out = r->rng.exponential(lambda); return CGB_OK; }
+extern "C" int cgb_rng_trunc_normal(cgb_rng *r, float a, float b, float mean, float sd, float *out, int32_t *has)
+{
+    *has = trunc_normal(r->rng, r->rs->tables.erf, r->rs->tables.erfinv, a, b, mean, sd, out) ? 1 : 0;
+    return CGB_OK;
+}
+extern "C" int cgb_rng_trunc_gamma_upper(cgb_rng *r, float b, float scale, float *out)
+{
+    *out = r->rng.truncGammaUpper(r->rs->tables.qgamma, b, scale);
+    return CGB_OK;
+}
+extern "C" void cgb_rng_destroy(cgb_rng *r) { delete r; }
+
+// ------------------------------------------------------------------------------------------------
+// sampler construction
+// ------------------------------------------------------------------------------------------------
+static uint32_t roundUp(uint32_t x, uint32_t m) { return (x + m - 1) / m * m; }
+
+// Matrix(const Matrix&, genesInCols, subsetGenes, indices) (data_structures/Matrix.cpp:30-69), written
+// straight into the padded one-sampler-row-per-line layout: out[j * ld + i] = result(i, j)
+static void orientData(const float *data, uint32_t nrow, uint32_t ncol, bool colmajor, bool genesInCols,
+                       bool subsetGenes, const uint32_t *indices, uint32_t nIdx, uint32_t &nRows,
+                       uint32_t &L, uint32_t &ld, std::vector<float> &out, float padValue)
+{
+    const bool subsetData = nIdx > 0;
+    const uint32_t nGenes = (subsetData && subsetGenes) ? nIdx : (genesInCols ? ncol : nrow);
+    const uint32_t nSamples = (subsetData && !subsetGenes) ? nIdx : (genesInCols ? nrow : ncol);
+    L = nGenes;
+    nRows = nSamples;
+    ld = roundUp(L, 32);
+    out.assign(static_cast<size_t>(nRows) * ld, padValue);
+    for (uint32_t j = 0; j < nSamples; ++j)
+    {
+        for (uint32_t i = 0; i < nGenes; ++i)
+        {
+            const uint32_t dataRow = (subsetData && (subsetGenes != genesInCols))
+                ? indices[genesInCols ? j : i] - 1 : (genesInCols ? j : i);
+            const uint32_t dataCol = (subsetData && (subsetGenes == genesInCols))
+                ? indices[genesInCols ? i : j] - 1 : (genesInCols ? i : j);
+            const size_t src = colmajor ? static_cast<size_t>(dataCol) * nrow + dataRow
+                                        : static_cast<size_t>(dataRow) * ncol + dataCol;
+            out[static_cast<size_t>(j) * ld + i] = data[src];
+        }
+    }
+}
+
+static int checkSubset(const cgb_params *p, uint32_t nrow, uint32_t ncol)
+{
+    for (uint32_t i = 0; i < p->nSubsetIndices; ++i)
+    {
+        CGB_CHECK(p->subsetIndices && p->subsetIndices[i] >= 1, "subset indices are 1-based (R convention)");
+    }
+    (void)nrow; (void)ncol;
+    return CGB_OK;
+}
+
+// one cluster per row scan: nSeg CTAs of kThreads threads, each staging `seg` floats per stream
+static void segmentsForLength(uint32_t L, uint32_t &nSeg, uint32_t &seg)
+{
+    const uint32_t target = static_cast<uint32_t>(envInt("COGAPS_SEG_FLOATS", 2560));
+    const uint32_t maxCluster = static_cast<uint32_t>(envInt("COGAPS_MAX_CLUSTER", 4));
+    uint32_t n = 1;
+    while (n < maxCluster && n < static_cast<uint32_t>(kMaxCluster) && (L + n - 1) / n > target) { n *= 2; }
+    nSeg = n;
+    seg = roundUp((L + n - 1) / n, 4);
+}
+
+static void chooseSegments(cgb_sampler *s)
+{
+    segmentsForLength(s->L, s->nSeg, s->seg);
+    s->segPad = roundUp(s->seg, 32);
+    s->smemBytes = 256 + static_cast<size_t>(5) * s->segPad * sizeof(float);
+}
+
+extern "C" int cgb_reduction_order_for_length(uint32_t rowLength, cgb_reduction_order *out)
+{
+    CGB_CHECK(out && rowLength, "cgb_reduction_order_for_length: bad argument");
+    out->threadsPerSegment = kThreads;
+    out->vectorWidth = kVec;
+    segmentsForLength(rowLength, out->nSegments, out->segmentLength);
+    return CGB_OK;
+}
+
+extern "C" void cgb_sampler_destroy(cgb_sampler *s)
+{
+    if (!s) { return; }
+    cudaSetDevice(s->device);
+    cudaFree(s->dD); cudaFree(s->dS); cudaFree(s->dAP); cudaFree(s->dM); cudaFree(s->dColNonzero);
+    cudaFree(s->dPartials); cudaFree(s->dTickets); cudaFree(s->dReducePartials);
+    if (s->hOutcomes) { cudaFreeHost(s->hOutcomes); }
+    if (s->hReducePartials) { cudaFreeHost(s->hReducePartials); }
+    if (s->evStart) { cudaEventDestroy(s->evStart); }
+    if (s->evStop) { cudaEventDestroy(s->evStop); }
+    if (s->stream) { cudaStreamDestroy(s->stream); }
+    delete s;
+}
+
+static const int kReduceBlocks = 592; // 148 SMs x 4
+
+extern "C" int cgb_sampler_create(const float *data, uint32_t nrow, uint32_t ncol, int32_t colmajor,
+                                  int32_t transpose, int32_t subsetRows, float alpha, float maxGibbsMass,
+                                  const cgb_params *params, cgb_randstate *rs, cgb_sampler **out)
+{
+    CGB_CHECK(data && params && rs && out, "cgb_sampler_create: NULL argument");
+    CGB_CHECK(params->struct_size == sizeof(cgb_params), "cgb_sampler_create: cgb_params ABI mismatch");
+    CGB_CHECK(params->nPatterns >= 1, "cgb_sampler_create: nPatterns must be >= 1");
+    if (params->useSparseOptimization) { return fail(CGB_EUNSUPPORTED, "SparseNormalModel is not on the device path yet"); }
+    if (!params->asynchronousUpdates) { return fail(CGB_EUNSUPPORTED, "the device path is the asynchronous sampler; asynchronousUpdates must be true"); }
+    CGB_TRY(checkSubset(params, nrow, ncol));
+    CGB_TRY(ensureDevice());
+
+    cgb_sampler *s = new (std::nothrow) cgb_sampler();
+    if (!s) { return fail(CGB_ENOMEM, "cgb_sampler_create: out of memory"); }
+    std::memset(static_cast<void*>(&s->counters), 0, sizeof(s->counters));
+    s->dD = s->dS = s->dAP = s->dM = nullptr;
+    s->dColNonzero = nullptr; s->dPartials = nullptr; s->dTickets = nullptr; s->dReducePartials = nullptr;
+    s->hOutcomes = nullptr; s->hReducePartials = nullptr; s->stream = nullptr; s->evStart = s->evStop = nullptr;
+    s->other = nullptr;
+    s->rs = rs;
+    s->device = g_device;
+    s->hasS = false;
+    s->timeKernels = false;
+    s->avgQueueLength = s->numQueueSamples = 0.f;
+    s->k = params->nPatterns;
+    s->alpha = alpha;
+    s->annealingTemp = 1.f;
+
+    // DenseNormalModel ctor, DenseNormalModel.h:66-88
+    std::vector<float> host;
+    orientData(data, nrow, ncol, colmajor != 0, transpose != 0, subsetRows != 0, params->subsetIndices,
+        params->nSubsetIndices, s->nRows, s->L, s->ld, host, 0.f);
+    CGB_CHECK(s->nRows >= 1 && s->L >= 1, "cgb_sampler_create: empty data");
+    s->ldM = roundUp(s->nRows, 32);
+    {
+        // gaps::nonZeroMean (MatrixMath.cpp:39-55): fp32 running sum over everything / count of positives
+        float sum = 0.f;
+        unsigned nnz = 0;
+        for (uint32_t r = 0; r < s->nRows; ++r)
+        {
+            const float *row = host.data() + static_cast<size_t>(r) * s->ld;
+            for (uint32_t l = 0; l < s->L; ++l)
+            {
+                sum += row[l];
+                if (row[l] > 0.f) { ++nnz; }
+            }
+        }
+        const float meanD = sum / static_cast<float>(nnz);
+        s->lambda = alpha * std::sqrt(static_cast<float>(static_cast<uint64_t>(s->k)) / meanD);
+        s->maxGibbsMass = maxGibbsMass / s->lambda;
+        const float size = static_cast<float>(s->nRows * s->L);                 // gaps::sparsity, MatrixMath.cpp:6-21
+        s->dataSparsity = 1.f - static_cast<float>(nnz) / size;
+    }
+    chooseSegments(s);
+
+    int rc = CGB_OK;
+    do
+    {
+        const size_t matBytes = static_cast<size_t>(s->nRows) * s->ld * sizeof(float);
+        const size_t facBytes = static_cast<size_t>(s->k) * s->ldM * sizeof(float);
+#define CGB_CUDA_BREAK(call) { cudaError_t e__ = (call); if (e__ != cudaSuccess) { rc = fail(e__ == cudaErrorMemoryAllocation ? CGB_ENOMEM : CGB_ECUDA, std::string(#call) + ": " + cudaGetErrorString(e__)); break; } }
+        CGB_CUDA_BREAK(cudaStreamCreateWithFlags(&s->stream, cudaStreamNonBlocking));
+        CGB_CUDA_BREAK(cudaMalloc(&s->dD, matBytes));
+        CGB_CUDA_BREAK(cudaMalloc(&s->dAP, matBytes));
+        CGB_CUDA_BREAK(cudaMalloc(&s->dM, facBytes));
+        CGB_CUDA_BREAK(cudaMalloc(&s->dColNonzero, sizeof(int) * s->k));
+        CGB_CUDA_BREAK(cudaMalloc(&s->dPartials, sizeof(AlphaPair) * 2 * kMaxBatch));
+        CGB_CUDA_BREAK(cudaMalloc(&s->dTickets, sizeof(uint32_t) * kMaxBatch));
+        CGB_CUDA_BREAK(cudaMalloc(&s->dReducePartials, sizeof(double) * kReduceBlocks));
+        CGB_CUDA_BREAK(cudaHostAlloc(&s->hOutcomes, sizeof(DevOutcome) * kMaxBatch, cudaHostAllocMapped));
+        CGB_CUDA_BREAK(cudaHostAlloc(&s->hReducePartials, sizeof(double) * kReduceBlocks, cudaHostAllocDefault));
+        CGB_CUDA_BREAK(cudaEventCreate(&s->evStart));
+        CGB_CUDA_BREAK(cudaEventCreate(&s->evStop));
+        CGB_CUDA_BREAK(cudaMemcpy(s->dD, host.data(), matBytes, cudaMemcpyHostToDevice));
+        CGB_CUDA_BREAK(cudaMemset(s->dAP, 0, matBytes));
+        CGB_CUDA_BREAK(cudaMemset(s->dM, 0, facBytes));
+        CGB_CUDA_BREAK(cudaMemset(s->dColNonzero, 0, sizeof(int) * s->k));
+        CGB_CUDA_BREAK(cudaMemset(s->dTickets, 0, sizeof(uint32_t) * kMaxBatch));
+        CGB_CUDA_BREAK(cudaFuncSetAttribute(eval_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+        CGB_CUDA_BREAK(cudaFuncSetAttribute(eval_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+        if (s->smemBytes > 227u * 1024u)
+        {
+            rc = fail(CGB_EUNSUPPORTED, "row length too large for one cluster of staged segments (raise COGAPS_MAX_CLUSTER)");
+            break;
+        }
+        rc = uploadTables(rs);
+    } while (0);
+    if (rc != CGB_OK)
+    {
+        cgb_sampler_destroy(s);
+        return rc;
+    }
+
+    // AsynchronousGibbsSampler ctor, AsynchronousGibbsSampler.h:63-76: domain over nRows*k bins, queue
+    // rng seeded from the shared state (this is where the seed consumption order is fixed)
+    const uint64_t nElements = static_cast<uint64_t>(s->nRows) * s->k;
+    s->domain.init(nElements);
+    s->queue.init(nElements, s->k, rs, alpha, s->lambda);
+    *out = s;
+    return CGB_OK;
+}
+
+extern "C" int cgb_sampler_set_uncertainty(cgb_sampler *s, const float *unc, uint32_t nrow, uint32_t ncol,
+                                           int32_t colmajor, int32_t transpose, int32_t subsetRows,
+                                           const cgb_params *params)
+{
+    CGB_CHECK(s && unc && params, "cgb_sampler_set_uncertainty: NULL argument");
+    CGB_CUDA(cudaSetDevice(s->device));
+    std::vector<float> host;
+    uint32_t nRows, L, ld;
+    // pads are 1 like mSMatrix.pad(1.f) (DenseNormalModel.h:87,94); the kernels never read them as data
+    orientData(unc, nrow, ncol, colmajor != 0, transpose != 0, subsetRows != 0, params->subsetIndices,
+        params->nSubsetIndices, nRows, L, ld, host, 1.f);
+    CGB_CHECK(nRows == s->nRows && L == s->L, "cgb_sampler_set_uncertainty: shape differs from the data");
+    const size_t matBytes = static_cast<size_t>(s->nRows) * s->ld * sizeof(float);
+    if (!s->dS) { CGB_CUDA(cudaMalloc(&s->dS, matBytes)); }
+    CGB_CUDA(cudaMemcpy(s->dS, host.data(), matBytes, cudaMemcpyHostToDevice));
+    s->hasS = true;
+    return CGB_OK;
+}
+
+static int refreshColNonzero(cgb_sampler *s)
+{
+    col_nonzero_kernel<<<s->k, 256, 0, s->stream>>>(s->dM, s->nRows, s->ldM, s->dColNonzero);
+    ++g_kernelLaunches;
+    CGB_CUDA(cudaGetLastError());
+    return CGB_OK;
+}
+
+extern "C" int cgb_sampler_set_matrix(cgb_sampler *s, const float *mat)
+{
+    CGB_CHECK(s && mat, "cgb_sampler_set_matrix: NULL argument");
+    CGB_CUDA(cudaSetDevice(s->device));
+    std::vector<float> host(static_cast<size_t>(s->k) * s->ldM, 0.f);
+    for (uint32_t r = 0; r < s->nRows; ++r)
+    {
+        for (uint32_t c = 0; c < s->k; ++c) { host[static_cast<size_t>(c) * s->ldM + r] = mat[static_cast<size_t>(r) * s->k + c]; }
+    }
+    CGB_CUDA(cudaMemcpyAsync(s->dM, host.data(), host.size() * sizeof(float), cudaMemcpyHostToDevice, s->stream));
+    CGB_CUDA(cudaStreamSynchronize(s->stream));
+    return refreshColNonzero(s);
+}
+
+extern "C" int cgb_sampler_set_annealing_temp(cgb_sampler *s, float temp)
+{
+    CGB_CHECK(s != nullptr, "cgb_sampler_set_annealing_temp: NULL sampler");
+    s->annealingTemp = temp;
+    return CGB_OK;
+}
+
+extern "C" int cgb_sampler_sync(cgb_sampler *s, const cgb_sampler *other)
+{
+    CGB_CHECK(s && other, "cgb_sampler_sync: NULL argument");
+    CGB_CHECK(other->nRows == s->L && other->L == s->nRows && other->k == s->k, "cgb_sampler_sync: shapes do not transpose");
+    CGB_CUDA(cudaSetDevice(s->device));
+    // the other sampler's stream may still hold its last commit
+    CGB_CUDA(cudaStreamSynchronize(other->stream));
+    dim3 grid((s->L + 31) / 32, (s->nRows + 31) / 32);
+    transpose_kernel<<<grid, 256, 0, s->stream>>>(s->dAP, other->dAP, s->nRows, s->L, s->ld, other->ld);
+    ++g_kernelLaunches;
+    CGB_CUDA(cudaGetLastError());
+    // canUseGibbs flags of the other factor, constant for the whole of our next update()
+    col_nonzero_kernel<<<other->k, 256, 0, s->stream>>>(other->dM, other->nRows, other->ldM, other->dColNonzero);
+    ++g_kernelLaunches;
+    CGB_CUDA(cudaGetLastError());
+    s->other = other;
+    return CGB_OK;
+}
+
+extern "C" int cgb_sampler_extra_initialization(cgb_sampler *s)
+{
+    CGB_CHECK(s && s->other, "cgb_sampler_extra_initialization: sync() has not been called");
+    CGB_CUDA(cudaSetDevice(s->device));
+    CGB_CUDA(cudaStreamSynchronize(s->other->stream));
+    dim3 grid((s->L + 255) / 256, s->nRows);
+    rebuild_ap_kernel<<<grid, 256, 0, s->stream>>>(s->dAP, s->dM, s->other->dM, s->nRows, s->L, s->k, s->ld, s->ldM, s->other->ldM);
+    ++g_kernelLaunches;
+    CGB_CUDA(cudaGetLastError());
+    return CGB_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
+// evaluation of one conflict-free batch on the device
+// ------------------------------------------------------------------------------------------------
+static void fillModelView(const cgb_sampler *s, ModelView &mv)
+{
+    mv.D = s->dD;
+    mv.S = s->hasS ? s->dS : nullptr;
+    mv.AP = s->dAP;
+    mv.M = s->dM;
+    mv.otherM = s->other->dM;
+    mv.otherColNonzero = s->other->dColNonzero;
+    mv.erf = s->rs->dErf;
+    mv.erfinv = s->rs->dErfinv;
+    mv.outcomes = s->hOutcomes;
+    mv.partials = s->dPartials;
+    mv.tickets = s->dTickets;
+    mv.nRows = s->nRows;
+    mv.L = s->L;
+    mv.k = s->k;
+    mv.ld = s->ld;
+    mv.ldM = s->ldM;
+    mv.ldOther = s->other->ldM;
+    mv.seg = s->seg;
+    mv.nSeg = s->nSeg;
+    mv.segPad = s->segPad;
+    mv.lambda = s->lambda;
+    mv.maxGibbsMass = s->maxGibbsMass;
+    mv.annealingTemp = s->annealingTemp;
+}
+
+// launches the eval kernel for params.nProps proposals already written to params.props; blocks until
+// the outcomes are visible in s->hOutcomes
+static int launchEval(cgb_sampler *s, EvalParams &params)
+{
+    uint32_t nExtra = 0;
+    for (uint32_t i = 0; i < params.nProps; ++i)
+    {
+        const DevProposal &p = params.props[i];
+        const bool pairType = p.type == 'M' || p.type == 'E' || (p.type == kProbe && p.variant == 1);
+        if (pairType && p.r1 != p.r2) { params.extra[nExtra++] = static_cast<uint16_t>(i); }
+    }
+    params.nTasks = params.nProps + nExtra;
+
+    cudaLaunchConfig_t cfg;
+    cfg = cudaLaunchConfig_t();
+    cfg.gridDim = dim3(s->nSeg, params.nTasks, 1);
+    cfg.blockDim = dim3(kThreads, 1, 1);
+    cfg.dynamicSmemBytes = s->smemBytes;
+    cfg.stream = s->stream;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = s->nSeg;
+    attr[0].val.clusterDim.y = 1;
+    attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+
+    const double t0 = nowSeconds();
+    if (s->timeKernels) { CGB_CUDA(cudaEventRecord(s->evStart, s->stream)); }
+    if (s->hasS) { CGB_CUDA(cudaLaunchKernelEx(&cfg, eval_kernel<true>, params)); }
+    else { CGB_CUDA(cudaLaunchKernelEx(&cfg, eval_kernel<false>, params)); }
+    ++g_kernelLaunches;
+    if (s->timeKernels) { CGB_CUDA(cudaEventRecord(s->evStop, s->stream)); }
+    CGB_CUDA(cudaStreamSynchronize(s->stream));
+    if (s->timeKernels)
+    {
+        float ms = 0.f;
+        CGB_CUDA(cudaEventElapsedTime(&ms, s->evStart, s->evStop));
+        s->counters.secondsKernel += static_cast<double>(ms) * 1e-3;
+    }
+    s->counters.secondsDeviceWait += nowSeconds() - t0;
+    s->counters.nBatches += 1;
+    return CGB_OK;
+}
+
+// reference-formulation bytes of one evaluated proposal (fp32, L = scanned length)
+static double algorithmicBytes(const DevProposal &p, const DevOutcome &o, uint32_t L)
+{
+    const double l = static_cast<double>(L);
+    if (p.type == 'B') { return 16.0 * l + (o.accepted ? 4.0 * l : 0.0); }
+    if (p.type == 'D') { return 16.0 * l + ((!o.accepted || o.mass1 != p.m1) ? 4.0 * l : 0.0); }
+    const bool changed = o.accepted != 0;
+    if (p.r1 == p.r2) { return 20.0 * l + (changed ? 4.0 * l : 0.0); }
+    return (p.c1 == p.c2 ? 28.0 : 32.0) * l + (changed ? 8.0 * l : 0.0);
+}
+
+static int evaluateQueue(cgb_sampler *s)
+{
+    std::vector<HostProposal> &q = s->queue.entries();
+    static thread_local EvalParams params; // ~20 KB of kernel parameters, reused
+    fillModelView(s, params.mv);
+    size_t done = 0;
+    while (done < q.size())
+    {
+        const uint32_t n = static_cast<uint32_t>(std::min<size_t>(kMaxBatch, q.size() - done));
+        for (uint32_t i = 0; i < n; ++i)
+        {
+            const HostProposal &hp = q[done + i];
+            DevProposal &dp = params.props[i];
+            dp.rng = hp.rng.state;
+            dp.r1 = hp.r1; dp.c1 = hp.c1; dp.r2 = hp.r2; dp.c2 = hp.c2;
+            dp.m1 = s->domain.atom(hp.atom1).mass;
+            dp.m2 = (hp.atom2 != kNoAtom) ? s->domain.atom(hp.atom2).mass : 0.f;
+            dp.type = static_cast<uint32_t>(hp.type);
+            dp.variant = 0;
+            dp.ch = 0.f;
+            dp.pad = 0;
+        }
+        params.nProps = n;
+        CGB_TRY(launchEval(s, params));
+        // apply the outcomes (AsynchronousGibbsSampler.h:126-219, the host-visible half)
+        for (uint32_t i = 0; i < n; ++i)
+        {
+            const HostProposal &hp = q[done + i];
+            const DevOutcome &o = s->hOutcomes[i];
+            s->counters.algorithmicBytes += algorithmicBytes(params.props[i], o, s->L);
+            switch (hp.type)
+            {
+                case 'B':
+                    if (o.accepted)
+                    {
+                        s->queue.acceptBirth();
+                        s->domain.atom(hp.atom1).mass = o.mass1;
+                    }
+                    else
+                    {
+                        s->queue.rejectBirth();
+                        s->domain.cacheErase(hp.atom1);
+                    }
+                    break;
+                case 'D':
+                    if (o.accepted)
+                    {
+                        s->queue.rejectDeath();
+                        s->domain.atom(hp.atom1).mass = o.mass1;
+                    }
+                    else
+                    {
+                        s->queue.acceptDeath();
+                        s->domain.cacheErase(hp.atom1);
+                    }
+                    break;
+                case 'M':
+                    if (o.accepted) { s->domain.move(hp.atom1, hp.pos); }
+                    break;
+                case 'E':
+                    if (o.accepted)
+                    {
+                        s->domain.atom(hp.atom1).mass = o.mass1;
+                        s->domain.atom(hp.atom2).mass = o.mass2;
+                    }
+                    break;
+                default: return fail(CGB_EINTERNAL, "evaluateQueue: corrupt proposal type");
+            }
+        }
+        s->counters.nProposalsQueued += n;
+        done += n;
+    }
+    return CGB_OK;
+}
+
+// AsynchronousGibbsSampler::update, AsynchronousGibbsSampler.h:88-122
+extern "C" int cgb_sampler_update(cgb_sampler *s, uint32_t nSteps, uint32_t nThreads)
+{
+    (void)nThreads;
+    CGB_CHECK(s && s->other, "cgb_sampler_update: sync() has not been called");
+    CGB_CUDA(cudaSetDevice(s->device));
+    uint32_t n = 0;
+    while (n < nSteps)
+    {
+        const double t0 = nowSeconds();
+        s->queue.populate(s->domain, nSteps - n);
+        n += s->queue.nProcessed();
+        if (n < nSteps)
+        {
+            s->numQueueSamples += 1.f;
+            s->avgQueueLength *= (s->numQueueSamples - 1.f) / s->numQueueSamples;
+            s->avgQueueLength += static_cast<float>(s->queue.entries().size()) / s->numQueueSamples;
+        }
+        const double t1 = nowSeconds();
+        s->counters.secondsHostGenerate += t1 - t0;
+        const double waitBefore = s->counters.secondsDeviceWait;
+        if (!s->queue.entries().empty()) { CGB_TRY(evaluateQueue(s)); }
+        s->queue.clear();
+        s->domain.flushEraseCache();
+        s->counters.secondsHostGenerate += (nowSeconds() - t1) - (s->counters.secondsDeviceWait - waitBefore);
+    }
+    s->counters.nProposalsTotal += nSteps;
+    if (s->queue.minAtoms() != s->queue.maxAtoms() || s->queue.maxAtoms() != s->domain.size())
+    {
+        return fail(CGB_EINTERNAL, "cgb_sampler_update: atom bookkeeping out of step with the domain");
+    }
+    return CGB_OK;
+}
+
+extern "C" int cgb_sampler_alpha_parameters(cgb_sampler *s, uint32_t n, const int32_t *variant,
+                                            const uint32_t *r1, const uint32_t *c1, const uint32_t *r2,
+                                            const uint32_t *c2, const float *ch, float *s_out, float *smu_out)
+{
+    CGB_CHECK(s && s->other && variant && r1 && c1 && r2 && c2 && ch && s_out && smu_out, "cgb_sampler_alpha_parameters: NULL argument or no sync()");
+    CGB_CUDA(cudaSetDevice(s->device));
+    static thread_local EvalParams params;
+    fillModelView(s, params.mv);
+    uint32_t done = 0;
+    while (done < n)
+    {
+        const uint32_t m = std::min<uint32_t>(kMaxBatch, n - done);
+        for (uint32_t i = 0; i < m; ++i)
+        {
+            const uint32_t j = done + i;
+            CGB_CHECK(variant[j] >= 0 && variant[j] <= 2, "cgb_sampler_alpha_parameters: bad variant");
+            CGB_CHECK(r1[j] < s->nRows && r2[j] < s->nRows && c1[j] < s->k && c2[j] < s->k, "cgb_sampler_alpha_parameters: index out of range");
+            DevProposal &dp = params.props[i];
+            std::memset(&dp, 0, sizeof(dp));
+            dp.type = kProbe;
+            dp.variant = static_cast<uint32_t>(variant[j]);
+            dp.r1 = r1[j]; dp.c1 = c1[j];
+            dp.r2 = (variant[j] == 1) ? r2[j] : r1[j];
+            dp.c2 = (variant[j] == 1) ? c2[j] : c1[j];
+            dp.ch = ch[j];
+        }
+        params.nProps = m;
+        CGB_TRY(launchEval(s, params));
+        for (uint32_t i = 0; i < m; ++i)
+        {
+            s_out[done + i] = s->hOutcomes[i].s;
+            smu_out[done + i] = s->hOutcomes[i].s_mu;
+        }
+        done += m;
+    }
+    return CGB_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
+// reductions and accessors
+// ------------------------------------------------------------------------------------------------
+static int sumPartials(cgb_sampler *s, int nBlocks, double *out)
+{
+    CGB_CUDA(cudaMemcpyAsync(s->hReducePartials, s->dReducePartials, sizeof(double) * nBlocks, cudaMemcpyDeviceToHost, s->stream));
+    CGB_CUDA(cudaStreamSynchronize(s->stream));
+    double t = 0.0;
+    for (int i = 0; i < nBlocks; ++i) { t += s->hReducePartials[i]; }
+    *out = t;
+    return CGB_OK;
+}
+
+extern "C" int cgb_sampler_chisq(const cgb_sampler *cs, float *out)
+{
+    CGB_CHECK(cs && out, "cgb_sampler_chisq: NULL argument");
+    cgb_sampler *s = const_cast<cgb_sampler*>(cs);
+    CGB_CUDA(cudaSetDevice(s->device));
+    const int blocks = static_cast<int>(std::min<uint32_t>(kReduceBlocks, s->nRows));
+    chisq_kernel<<<blocks, 256, 0, s->stream>>>(s->dD, s->hasS ? s->dS : nullptr, s->dAP, s->nRows, s->L, s->ld, s->dReducePartials);
+    ++g_kernelLaunches;
+    CGB_CUDA(cudaGetLastError());
+    double t = 0.0;
+    CGB_TRY(sumPartials(s, blocks, &t));
+    *out = static_cast<float>(t);
+    return CGB_OK;
+}
+
+extern "C" int cgb_sampler_n_atoms(const cgb_sampler *s, uint64_t *out)
+{
+    CGB_CHECK(s && out, "cgb_sampler_n_atoms: NULL argument");
+    *out = s->domain.size();
+    return CGB_OK;
+}
+
+extern "C" int cgb_sampler_data_sparsity(const cgb_sampler *s, float *out)
+{
+    CGB_CHECK(s && out, "cgb_sampler_data_sparsity: NULL argument");
+    *out = s->dataSparsity;
+    return CGB_OK;
+}
+
+extern "C" int cgb_sampler_average_queue_length(const cgb_sampler *s, float *out)
+{
+    CGB_CHECK(s && out, "cgb_sampler_average_queue_length: NULL argument");
+    *out = s->avgQueueLength;
+    return CGB_OK;
+}
+
+extern "C" int cgb_sampler_get_matrix(const cgb_sampler *s, float *out)
+{
+    CGB_CHECK(s && out, "cgb_sampler_get_matrix: NULL argument");
+    CGB_CUDA(cudaSetDevice(s->device));
+    std::vector<float> host(static_cast<size_t>(s->k) * s->ldM);
+    CGB_CUDA(cudaStreamSynchronize(s->stream));
+    CGB_CUDA(cudaMemcpy(host.data(), s->dM, host.size() * sizeof(float), cudaMemcpyDeviceToHost));
+    for (uint32_t r = 0; r < s->nRows; ++r)
+    {
+        for (uint32_t c = 0; c < s->k; ++c) { out[static_cast<size_t>(r) * s->k + c] = host[static_cast<size_t>(c) * s->ldM + r]; }
+    }
+    return CGB_OK;
+}
+
+extern "C" int cgb_sampler_shape(const cgb_sampler *s, uint32_t *rows, uint32_t *nPatterns, uint32_t *rowLength)
+{
+    CGB_CHECK(s != nullptr, "cgb_sampler_shape: NULL sampler");
+    if (rows) { *rows = s->nRows; }
+    if (nPatterns) { *nPatterns = s->k; }
+    if (rowLength) { *rowLength = s->L; }
+    return CGB_OK;
+}
+
+extern "C" int cgb_sampler_lambda(const cgb_sampler *s, float *lambda, float *maxGibbsMass)
+{
+    CGB_CHECK(s != nullptr, "cgb_sampler_lambda: NULL sampler");
+    if (lambda) { *lambda = s->lambda; }
+    if (maxGibbsMass) { *maxGibbsMass = s->maxGibbsMass; }
+    return CGB_OK;
+}
+
+extern "C" int cgb_sampler_get_atoms(const cgb_sampler *s, uint64_t *pos, float *mass, uint64_t capacity, uint64_t *count)
+{
+    CGB_CHECK(s && count, "cgb_sampler_get_atoms: NULL argument");
+    *count = s->domain.size();
+    if (pos && mass)
+    {
+        const uint64_t n = std::min<uint64_t>(capacity, s->domain.size());
+        for (uint64_t i = 0; i < n; ++i)
+        {
+            const Atom &a = s->domain.atom(s->domain.atIndex(static_cast<uint32_t>(i)));
+            pos[i] = a.pos;
+            mass[i] = a.mass;
+        }
+    }
+    return CGB_OK;
+}
+
+extern "C" int cgb_sampler_get_ap_row(const cgb_sampler *s, uint32_t row, float *out)
+{
+    CGB_CHECK(s && out && row < s->nRows, "cgb_sampler_get_ap_row: bad argument");
+    CGB_CUDA(cudaSetDevice(s->device));
+    CGB_CUDA(cudaStreamSynchronize(s->stream));
+    CGB_CUDA(cudaMemcpy(out, s->dAP + static_cast<size_t>(row) * s->ld, sizeof(float) * s->L, cudaMemcpyDeviceToHost));
+    return CGB_OK;
+}
+
+extern "C" int cgb_sampler_get_counters(const cgb_sampler *s, cgb_sampler_counters *out)
+{
+    CGB_CHECK(s && out, "cgb_sampler_get_counters: NULL argument");
+    *out = s->counters;
+    return CGB_OK;
+}
+
+extern "C" int cgb_sampler_reset_counters(cgb_sampler *s)
+{
+    CGB_CHECK(s != nullptr, "cgb_sampler_reset_counters: NULL sampler");
+    std::memset(static_cast<void*>(&s->counters), 0, sizeof(s->counters));
+    return CGB_OK;
+}
+
+extern "C" int cgb_sampler_set_kernel_timing(cgb_sampler *s, int32_t enabled)
+{
+    CGB_CHECK(s != nullptr, "cgb_sampler_set_kernel_timing: NULL sampler");
+    s->timeKernels = enabled != 0;
+    return CGB_OK;
+}
+
+extern "C" int cgb_sampler_reduction_order(const cgb_sampler *s, cgb_reduction_order *out)
+{
+    CGB_CHECK(s && out, "cgb_sampler_reduction_order: NULL argument");
+    out->threadsPerSegment = kThreads;
+    out->vectorWidth = kVec;
+    out->nSegments = s->nSeg;
+    out->segmentLength = s->seg;
+    return CGB_OK;
+}
+
+extern "C" int cgb_sampler_device_matrix(const cgb_sampler *s, void **dev, uint64_t *ld)
+{
+    CGB_CHECK(s && dev && ld, "cgb_sampler_device_matrix: NULL argument");
+    *dev = s->dM;
+    *ld = s->ldM;
+    return CGB_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
+// GapsStatistics on the device
+// ------------------------------------------------------------------------------------------------
+struct cgb_stats
+{
+    uint32_t nGenes, nSamples, k, ldA, ldP;
+    float *dAmean, *dAsq, *dPmean, *dPsq, *dPump, *dNorms, *dScratch;
+    unsigned statUpdates, pumpUpdates;
+    int device;
+};
+
+extern "C" void cgb_stats_destroy(cgb_stats *st)
+{
+    if (!st) { return; }
+    cudaSetDevice(st->device);
+    cudaFree(st->dAmean); cudaFree(st->dAsq); cudaFree(st->dPmean); cudaFree(st->dPsq);
+    cudaFree(st->dPump); cudaFree(st->dNorms); cudaFree(st->dScratch);
+    delete st;
+}
+
+extern "C" int cgb_stats_create(uint32_t nGenes, uint32_t nSamples, uint32_t nPatterns, cgb_stats **out)
+{
+    CGB_CHECK(out && nGenes && nSamples && nPatterns, "cgb_stats_create: bad argument");
+    CGB_TRY(ensureDevice());
+    cgb_stats *st = new (std::nothrow) cgb_stats();
+    if (!st) { return fail(CGB_ENOMEM, "cgb_stats_create: out of memory"); }
+    std::memset(static_cast<void*>(st), 0, sizeof(*st));
+    st->nGenes = nGenes; st->nSamples = nSamples; st->k = nPatterns;
+    st->ldA = roundUp(nGenes, 32);
+    st->ldP = roundUp(nSamples, 32);
+    st->device = g_device;
+    const size_t aBytes = static_cast<size_t>(nPatterns) * st->ldA * sizeof(float);
+    const size_t pBytes = static_cast<size_t>(nPatterns) * st->ldP * sizeof(float);
+    cudaError_t e = cudaSuccess;
+    if (e == cudaSuccess) { e = cudaMalloc(&st->dAmean, aBytes); }
+    if (e == cudaSuccess) { e = cudaMalloc(&st->dAsq, aBytes); }
+    if (e == cudaSuccess) { e = cudaMalloc(&st->dPump, aBytes); }
+    if (e == cudaSuccess) { e = cudaMalloc(&st->dScratch, aBytes); }
+    if (e == cudaSuccess) { e = cudaMalloc(&st->dPmean, pBytes); }
+    if (e == cudaSuccess) { e = cudaMalloc(&st->dPsq, pBytes); }
+    if (e == cudaSuccess) { e = cudaMalloc(&st->dNorms, sizeof(float) * nPatterns); }
+    if (e == cudaSuccess) { e = cudaMemset(st->dAmean, 0, aBytes); }
+    if (e == cudaSuccess) { e = cudaMemset(st->dAsq, 0, aBytes); }
+    if (e == cudaSuccess) { e = cudaMemset(st->dPump, 0, aBytes); }
+    if (e == cudaSuccess) { e = cudaMemset(st->dPmean, 0, pBytes); }
+    if (e == cudaSuccess) { e = cudaMemset(st->dPsq, 0, pBytes); }
+    if (e != cudaSuccess)
+    {
+        cgb_stats_destroy(st);
+        return fail(e == cudaErrorMemoryAllocation ? CGB_ENOMEM : CGB_ECUDA, std::string("cgb_stats_create: ") + cudaGetErrorString(e));
+    }
+    *out = st;
+    return CGB_OK;
+}
+
+// mode 0: update (both, P normalised by its column max); 1: updateA; 2: updateP (norm forced to 1)
+static int statsUpdate(cgb_stats *st, const cgb_sampler *A, const cgb_sampler *P, int mode)
+{
+    CGB_CHECK(st && A && P, "cgb_stats_update: NULL argument");
+    CGB_CHECK(A->nRows == st->nGenes && P->nRows == st->nSamples && A->k == st->k && P->k == st->k, "cgb_stats_update: shape mismatch");
+    CGB_CUDA(cudaSetDevice(st->device));
+    cudaStream_t stream = P->stream;
+    CGB_CUDA(cudaStreamSynchronize(A->stream));
+    ++st->statUpdates;
+    col_max_kernel<<<st->k, 256, 0, stream>>>(P->dM, P->nRows, P->ldM, st->dNorms, mode != 0 ? 1 : 0);
+    ++g_kernelLaunches;
+    if (mode == 0 || mode == 2)
+    {
+        dim3 grid((P->nRows + 255) / 256, st->k);
+        stats_accumulate_kernel<<<grid, 256, 0, stream>>>(P->dM, P->nRows, P->ldM, st->dNorms, 1, st->dPmean, st->dPsq);
+        ++g_kernelLaunches;
+    }
+    if (mode == 0 || mode == 1)
+    {
+        dim3 grid((A->nRows + 255) / 256, st->k);
+        stats_accumulate_kernel<<<grid, 256, 0, stream>>>(A->dM, A->nRows, A->ldM, st->dNorms, 0, st->dAmean, st->dAsq);
+        ++g_kernelLaunches;
+    }
+    CGB_CUDA(cudaGetLastError());
+    CGB_CUDA(cudaStreamSynchronize(stream));
+    return CGB_OK;
+}
+
+extern "C" int cgb_stats_update(cgb_stats *st, const cgb_sampler *A, const cgb_sampler *P) { return statsUpdate(st, A, P, 0); }
+extern "C" int cgb_stats_update_a(cgb_stats *st, const cgb_sampler *A, const cgb_sampler *P) { return statsUpdate(st, A, P, 1); }
+extern "C" int cgb_stats_update_p(cgb_stats *st, const cgb_sampler *A, const cgb_sampler *P) { return statsUpdate(st, A, P, 2); }
+
+extern "C" int cgb_stats_update_pump(cgb_stats *st, const cgb_sampler *A)
+{
+    CGB_CHECK(st && A && A->nRows == st->nGenes, "cgb_stats_update_pump: bad argument");
+    CGB_CUDA(cudaSetDevice(st->device));
+    ++st->pumpUpdates;
+    pump_kernel<<<(A->nRows + 255) / 256, 256, 0, A->stream>>>(A->dM, A->nRows, A->ldM, st->k, 1.f, st->dPump);
+    ++g_kernelLaunches;
+    CGB_CUDA(cudaGetLastError());
+    CGB_CUDA(cudaStreamSynchronize(A->stream));
+    return CGB_OK;
+}
+
+static int downloadFactor(const float *dev, uint32_t rows, uint32_t k, uint32_t ld, std::vector<float> &host)
+{
+    host.resize(static_cast<size_t>(k) * ld);
+    CGB_CUDA(cudaMemcpy(host.data(), dev, host.size() * sizeof(float), cudaMemcpyDeviceToHost));
+    (void)rows;
+    return CGB_OK;
+}
+
+// Amean / Pmean: sums / nUpdates (GapsStatistics.cpp:13-21,38-46)
+static int statsMean(const cgb_stats *st, const float *dev, uint32_t rows, uint32_t ld, float div, float *out)
+{
+    CGB_CHECK(st && out, "cgb_stats: NULL argument");
+    CGB_CUDA(cudaSetDevice(st->device));
+    std::vector<float> host;
+    CGB_TRY(downloadFactor(dev, rows, st->k, ld, host));
+    for (uint32_t i = 0; i < rows; ++i)
+    {
+        for (uint32_t c = 0; c < st->k; ++c) { out[static_cast<size_t>(i) * st->k + c] = host[static_cast<size_t>(c) * ld + i] / div; }
+    }
+    return CGB_OK;
+}
+
+// Asd / Psd (GapsStatistics.cpp:23-36,48-61)
+static int statsSd(const cgb_stats *st, const float *devMean, const float *devSq, uint32_t rows, uint32_t ld, float *out)
+{
+    CGB_CHECK(st && out, "cgb_stats: NULL argument");
+    CGB_CUDA(cudaSetDevice(st->device));
+    std::vector<float> mean, sq;
+    CGB_TRY(downloadFactor(devMean, rows, st->k, ld, mean));
+    CGB_TRY(downloadFactor(devSq, rows, st->k, ld, sq));
+    const float n = static_cast<float>(st->statUpdates);
+    for (uint32_t i = 0; i < rows; ++i)
+    {
+        for (uint32_t c = 0; c < st->k; ++c)
+        {
+            const size_t idx = static_cast<size_t>(c) * ld + i;
+            const float meanTerm = (mean[idx] * mean[idx]) / n;
+            const float numer = gmax(0.f, sq[idx] - meanTerm);
+            out[static_cast<size_t>(i) * st->k + c] = std::sqrt(numer / (n - 1.f));
+        }
+    }
+    return CGB_OK;
+}
+
+extern "C" int cgb_stats_amean(const cgb_stats *st, float *out) { return statsMean(st, st ? st->dAmean : nullptr, st ? st->nGenes : 0, st ? st->ldA : 0, st ? static_cast<float>(st->statUpdates) : 1.f, out); }
+extern "C" int cgb_stats_pmean(const cgb_stats *st, float *out) { return statsMean(st, st ? st->dPmean : nullptr, st ? st->nSamples : 0, st ? st->ldP : 0, st ? static_cast<float>(st->statUpdates) : 1.f, out); }
+extern "C" int cgb_stats_asd(const cgb_stats *st, float *out) { return statsSd(st, st ? st->dAmean : nullptr, st ? st->dAsq : nullptr, st ? st->nGenes : 0, st ? st->ldA : 0, out); }
+extern "C" int cgb_stats_psd(const cgb_stats *st, float *out) { return statsSd(st, st ? st->dPmean : nullptr, st ? st->dPsq : nullptr, st ? st->nSamples : 0, st ? st->ldP : 0, out); }
+
+extern "C" int cgb_stats_pump_matrix(const cgb_stats *st, float *out)
+{
+    const float denom = (st && st->pumpUpdates != 0) ? static_cast<float>(st->pumpUpdates) : 1.f;
+    return statsMean(st, st ? st->dPump : nullptr, st ? st->nGenes : 0, st ? st->ldA : 0, denom, out);
+}
+
+extern "C" int cgb_stats_mean_pattern(const cgb_stats *cst, float *out)
+{
+    CGB_CHECK(cst && out, "cgb_stats_mean_pattern: NULL argument");
+    cgb_stats *st = const_cast<cgb_stats*>(cst);
+    CGB_CUDA(cudaSetDevice(st->device));
+    const size_t aBytes = static_cast<size_t>(st->k) * st->ldA * sizeof(float);
+    CGB_CUDA(cudaMemset(st->dScratch, 0, aBytes));
+    pump_kernel<<<(st->nGenes + 255) / 256, 256>>>(st->dAmean, st->nGenes, st->ldA, st->k, static_cast<float>(st->statUpdates), st->dScratch);
+    ++g_kernelLaunches;
+    CGB_CUDA(cudaGetLastError());
+    CGB_CUDA(cudaDeviceSynchronize());
+    return statsMean(st, st->dScratch, st->nGenes, st->ldA, 1.f, out);
+}
+
+extern "C" int cgb_stats_mean_chisq(const cgb_stats *st, const cgb_sampler *cP, float *out)
+{
+    CGB_CHECK(st && cP && out, "cgb_stats_mean_chisq: NULL argument");
+    cgb_sampler *P = const_cast<cgb_sampler*>(cP);
+    CGB_CHECK(P->nRows == st->nSamples && P->L == st->nGenes, "cgb_stats_mean_chisq: expects the P sampler");
+    CGB_CUDA(cudaSetDevice(st->device));
+    const float n = static_cast<float>(st->statUpdates);
+    const int blocks = static_cast<int>(std::min<uint32_t>(kReduceBlocks, P->nRows));
+    mean_chisq_kernel<<<blocks, 256, 0, P->stream>>>(P->dD, P->hasS ? P->dS : nullptr, P->nRows, P->L, P->ld,
+        st->dAmean, st->ldA, st->dPmean, st->ldP, st->k, n * n, P->dReducePartials);
+    ++g_kernelLaunches;
+    CGB_CUDA(cudaGetLastError());
+    double t = 0.0;
+    CGB_TRY(sumPartials(P, blocks, &t));
+    *out = static_cast<float>(t);
+    return CGB_OK;
+}
+
+extern "C" int cgb_stats_device_sums(const cgb_stats *st, void **AmeanSum, void **AsqSum, void **PmeanSum,
+                                     void **PsqSum, uint64_t *ldA, uint64_t *ldP, uint32_t *nUpdates)
+{
+    CGB_CHECK(st != nullptr, "cgb_stats_device_sums: NULL stats");
+    if (AmeanSum) { *AmeanSum = st->dAmean; }
+    if (AsqSum) { *AsqSum = st->dAsq; }
+    if (PmeanSum) { *PmeanSum = st->dPmean; }
+    if (PsqSum) { *PsqSum = st->dPsq; }
+    if (ldA) { *ldA = st->ldA; }
+    if (ldP) { *ldP = st->ldP; }
+    if (nUpdates) { *nUpdates = st->statUpdates; }
+    return CGB_OK;
+}
+
+// device portable-log probe (tests)
+extern "C" int cgb_debug_logf(const float *in, float *out, uint32_t n)
+{
+    CGB_CHECK(in && out, "cgb_debug_logf: NULL argument");
+    CGB_TRY(ensureDevice());
+    float *dIn = nullptr, *dOut = nullptr;
+    CGB_CUDA(cudaMalloc(&dIn, sizeof(float) * n));
+    CGB_CUDA(cudaMalloc(&dOut, sizeof(float) * n));
+    CGB_CUDA(cudaMemcpy(dIn, in, sizeof(float) * n, cudaMemcpyHostToDevice));
+    logf_probe_kernel<<<(n + 255) / 256, 256>>>(dIn, dOut, n);
+    ++g_kernelLaunches;
+    CGB_CUDA(cudaGetLastError());
+    CGB_CUDA(cudaMemcpy(out, dOut, sizeof(float) * n, cudaMemcpyDeviceToHost));
+    cudaFree(dIn);
+    cudaFree(dOut);
+    return CGB_OK;
+}
+
+// host portable-log probe: the same header compiled for the host (tests compare both with the oracle)
+extern "C" float cgb_debug_host_logf(float x) { return portable_logf(x); }
+
+// ------------------------------------------------------------------------------------------------
+// gaps::run — runCoGAPSAlgorithm / runOnePhase / updateSampler / displayStatus
+// (src/GapsRunner.cpp:161-222, 272-327, 381-503)
+// ------------------------------------------------------------------------------------------------
+struct RunGuard
+{
+    cgb_randstate *rs;
+    cgb_sampler *A, *P;
+    cgb_stats *st;
+    cgb_rng *rng;
+    RunGuard() : rs(nullptr), A(nullptr), P(nullptr), st(nullptr), rng(nullptr) {}
+    ~RunGuard()
+    {
+        cgb_rng_destroy(rng);
+        cgb_stats_destroy(st);
+        cgb_sampler_destroy(A);
+        cgb_sampler_destroy(P);
+        cgb_randstate_destroy(rs);
+    }
+};
+
+static const float *g_tableOverride[3] = {nullptr, nullptr, nullptr};
+// tables used by cgb_run for the GapsRandomState it creates internally (NULLs restore the built-ins)
+extern "C" int cgb_run_set_tables(const float *erf, const float *erfinv, const float *qgamma)
+{
+    g_tableOverride[0] = erf;
+    g_tableOverride[1] = erfinv;
+    g_tableOverride[2] = qgamma;
+    return CGB_OK;
+}
+
+extern "C" int cgb_run(const float *data, uint32_t nrow, uint32_t ncol, int32_t colmajor,
+                       const float *uncertainty, const cgb_params *p, cgb_result *r)
+{
+    CGB_CHECK(data && p && r, "cgb_run: NULL argument");
+    CGB_CHECK(p->struct_size == sizeof(cgb_params), "cgb_run: cgb_params ABI mismatch");
+    CGB_CHECK(r->struct_size == sizeof(cgb_result), "cgb_run: cgb_result ABI mismatch");
+    const int fixed = p->whichMatrixFixed ? p->whichMatrixFixed : 'N';
+    CGB_CHECK(fixed == 'N' || fixed == 'A' || fixed == 'P', "cgb_run: whichMatrixFixed must be 'N', 'A' or 'P'");
+    const bool useFixed = p->fixedPatterns != nullptr && fixed != 'N';
+
+    uint32_t nGenes = p->transposeData ? ncol : nrow;
+    uint32_t nSamples = p->transposeData ? nrow : ncol;
+    if (p->nSubsetIndices && p->subsetGenes) { nGenes = p->nSubsetIndices; }
+    if (p->nSubsetIndices && !p->subsetGenes) { nSamples = p->nSubsetIndices; }
+
+    RunGuard g;
+    CGB_TRY(cgb_randstate_create(p->seed, &g.rs));
+    if (g_tableOverride[0]) { CGB_TRY(cgb_randstate_set_tables(g.rs, g_tableOverride[0], g_tableOverride[1], g_tableOverride[2])); }
+    // GapsRunner.cpp:402-406: A first, then P — this fixes which seeds the two queue rngs get
+    CGB_TRY(cgb_sampler_create(data, nrow, ncol, colmajor, !p->transposeData, !p->subsetGenes, p->alphaA, p->maxGibbsMassA, p, g.rs, &g.A));
+    CGB_TRY(cgb_sampler_create(data, nrow, ncol, colmajor, p->transposeData, p->subsetGenes, p->alphaP, p->maxGibbsMassP, p, g.rs, &g.P));
+    if (uncertainty)
+    {
+        CGB_TRY(cgb_sampler_set_uncertainty(g.A, uncertainty, nrow, ncol, colmajor, !p->transposeData, !p->subsetGenes, p));
+        CGB_TRY(cgb_sampler_set_uncertainty(g.P, uncertainty, nrow, ncol, colmajor, p->transposeData, p->subsetGenes, p));
+    }
+    if (useFixed)
+    {
+        if (fixed == 'A') { CGB_TRY(cgb_sampler_set_matrix(g.A, p->fixedPatterns)); }
+        if (fixed == 'P') { CGB_TRY(cgb_sampler_set_matrix(g.P, p->fixedPatterns)); }
+    }
+    CGB_TRY(cgb_stats_create(nGenes, nSamples, p->nPatterns, &g.st));
+    CGB_TRY(cgb_rng_create(g.rs, &g.rng)); // GapsRunner.cpp:437
+
+    CGB_TRY(cgb_sampler_sync(g.A, g.P));
+    CGB_TRY(cgb_sampler_sync(g.P, g.A));
+    CGB_TRY(cgb_sampler_extra_initialization(g.A));
+    CGB_TRY(cgb_sampler_extra_initialization(g.P));
+
+    const double tStart = nowSeconds();
+    uint64_t totalUpdates = 0;
+    uint32_t nHist = 0, nSnapEq = 0, nSnapSamp = 0;
+    double secondsA = 0.0, secondsP = 0.0;
+    for (int phase = CGB_PHASE_EQUILIBRATION; phase <= CGB_PHASE_SAMPLING; ++phase)
+    {
+        if (p->printMessages) { std::printf(phase == CGB_PHASE_EQUILIBRATION ? "-- Equilibration Phase --\n" : "-- Sampling Phase --\n"); }
+        for (uint32_t iter = 0; iter < p->nIterations; ++iter)
+        {
+            if (phase == CGB_PHASE_EQUILIBRATION)
+            {
+                const float temp = static_cast<float>(2 * iter) / static_cast<float>(p->nIterations);
+                g.A->annealingTemp = gmin(1.f, temp);
+                g.P->annealingTemp = gmin(1.f, temp);
+            }
+            const unsigned atomsA = static_cast<unsigned>(g.A->domain.size());
+            const unsigned atomsP = static_cast<unsigned>(g.P->domain.size());
+            const unsigned nA = static_cast<unsigned>(g.rng->rng.poisson(static_cast<double>(atomsA < 10u ? 10u : atomsA)));
+            const unsigned nP = static_cast<unsigned>(g.rng->rng.poisson(static_cast<double>(atomsP < 10u ? 10u : atomsP)));
+            // updateSampler, GapsRunner.cpp:201-222
+            if (fixed != 'A')
+            {
+                const double t0 = nowSeconds();
+                CGB_TRY(cgb_sampler_update(g.A, nA, p->maxThreads));
+                secondsA += nowSeconds() - t0;
+                if (fixed != 'P') { CGB_TRY(cgb_sampler_sync(g.P, g.A)); }
+            }
+            if (fixed != 'P')
+            {
+                const double t0 = nowSeconds();
+                CGB_TRY(cgb_sampler_update(g.P, nP, p->maxThreads));
+                secondsP += nowSeconds() - t0;
+                if (fixed != 'A') { CGB_TRY(cgb_sampler_sync(g.A, g.P)); }
+            }
+            totalUpdates += nA + nP;
+            if (phase == CGB_PHASE_SAMPLING)
+            {
+                if (useFixed)
+                {
+                    if (fixed == 'A') { CGB_TRY(cgb_stats_update_p(g.st, g.A, g.P)); }
+                    else { CGB_TRY(cgb_stats_update_a(g.st, g.A, g.P)); }
+                }
+                else
+                {
+                    CGB_TRY(cgb_stats_update(g.st, g.A, g.P));
+                    if (p->takePumpSamples) { CGB_TRY(cgb_stats_update_pump(g.st, g.A)); }
+                }
+            }
+            if (static_cast<int>(p->snapshotPhase) == phase || p->snapshotPhase == CGB_PHASE_ALL)
+            {
+                if (p->snapshotFrequency > 0 && ((iter + 1) % p->snapshotFrequency) == 0)
+                {
+                    const uint32_t slot = nSnapEq + nSnapSamp;
+                    if (slot < r->snapshotCapacity)
+                    {
+                        if (r->snapshotsA) { CGB_TRY(cgb_sampler_get_matrix(g.A, r->snapshotsA + static_cast<size_t>(slot) * nGenes * p->nPatterns)); }
+                        if (r->snapshotsP) { CGB_TRY(cgb_sampler_get_matrix(g.P, r->snapshotsP + static_cast<size_t>(slot) * nSamples * p->nPatterns)); }
+                    }
+                    if (phase == CGB_PHASE_EQUILIBRATION) { ++nSnapEq; } else { ++nSnapSamp; }
+                }
+            }
+            // displayStatus, GapsRunner.cpp:161-199
+            if (p->outputFrequency > 0 && ((iter + 1) % p->outputFrequency) == 0)
+            {
+                float cs = 0.f;
+                CGB_TRY(cgb_sampler_chisq(fixed == 'P' ? g.A : g.P, &cs));
+                const unsigned a = static_cast<unsigned>(g.A->domain.size()), b = static_cast<unsigned>(g.P->domain.size());
+                if (nHist < r->historyCapacity)
+                {
+                    if (r->chisqHistory) { r->chisqHistory[nHist] = cs; }
+                    if (r->atomHistoryA) { r->atomHistoryA[nHist] = a; }
+                    if (r->atomHistoryP) { r->atomHistoryP[nHist] = b; }
+                    ++nHist;
+                }
+                if (p->printMessages)
+                {
+                    std::printf("%d of %d, Atoms: %d(A), %d(P), ChiSq: %.0f, elapsed %.1f s\n", iter + 1, p->nIterations, a, b, cs, nowSeconds() - tStart);
+                    std::fflush(stdout);
+                }
+            }
+        }
+    }
+    r->totalRunningTime = nowSeconds() - tStart;
+
+    if (r->Amean) { CGB_TRY(cgb_stats_amean(g.st, r->Amean)); }
+    if (r->Asd) { CGB_TRY(cgb_stats_asd(g.st, r->Asd)); }
+    if (r->Pmean) { CGB_TRY(cgb_stats_pmean(g.st, r->Pmean)); }
+    if (r->Psd) { CGB_TRY(cgb_stats_psd(g.st, r->Psd)); }
+    r->nHistory = nHist;
+    r->nSnapshotsEquilibration = nSnapEq;
+    r->nSnapshotsSampling = nSnapSamp;
+    r->seed = p->seed;
+    r->totalUpdates = totalUpdates;
+    r->averageQueueLengthA = g.A->avgQueueLength;
+    r->averageQueueLengthP = g.P->avgQueueLength;
+    r->meanChiSq = 0.f; // GapsRunner.cpp:478-485: zero whenever a matrix is fixed
+    if (fixed == 'N') { CGB_TRY(cgb_stats_mean_chisq(g.st, g.P, &r->meanChiSq)); }
+    if (p->takePumpSamples)
+    {
+        if (r->pumpMatrix) { CGB_TRY(cgb_stats_pump_matrix(g.st, r->pumpMatrix)); }
+        if (r->meanPatternAssignment) { CGB_TRY(cgb_stats_mean_pattern(g.st, r->meanPatternAssignment)); }
+    }
+    r->nBatchesA = g.A->counters.nBatches;
+    r->nBatchesP = g.P->counters.nBatches;
+    r->secondsUpdateA = secondsA;
+    r->secondsUpdateP = secondsP;
+    r->secondsDevice = g.A->counters.secondsKernel + g.P->counters.secondsKernel;
+    r->algorithmicBytes = g.A->counters.algorithmicBytes + g.P->counters.algorithmicBytes;
+    return CGB_OK;
+}

@@ -1,0 +1,676 @@
+// kernels.cuh — sm_100a kernels of the Gibbs-sampler hot path.
+//
+//   eval_kernel        one cluster per (proposal, row): TMA bulk-stage the touched D/S/AP row segment
+//                      and the 1-2 factor columns into shared memory, the alphaParameters scan
+//                      (DenseNormalModel.cpp:162-240), gibbsMass / accept epilogue on one lane
+//                      (AsynchronousGibbsSampler.h:126-219), AP commit from shared memory
+//                      (DenseNormalModel.cpp:243-258).  HBM-bound: 12-20 B per row element.
+//   transpose_kernel   DenseNormalModel::sync (DenseNormalModel.cpp:20-36)
+//   rebuild_ap_kernel  extraInitialization (:38-54)
+//   chisq_kernel       chiSq (:56-68)
+//   col_nonzero_kernel canUseGibbs precompute (:100-108)
+//   stats kernels      GapsStatistics::update/updateA/updateP, meanChiSq (GapsStatistics.h:129-185, .cpp:63-87)
+#ifndef CGB_KERNELS_CUH
+#define CGB_KERNELS_CUH
+
+#include <cooperative_groups.h>
+#include <cuda_runtime.h>
+
+#include "device_types.h"
+#include "gaps_math.h"
+
+namespace cgb {
+
+namespace cg = cooperative_groups;
+
+// ------------------------------------------------------------------------------------------------
+// PTX helpers: mbarrier + 1-D bulk async copy (TMA without a tensor map; SASS: UBLKCP / SYNCS)
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void *p)
+{
+    return static_cast<uint32_t>(__cvta_generic_to_shared(p));
+}
+
+__device__ __forceinline__ void mbar_init(uint64_t *bar, uint32_t count)
+{
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+
+__device__ __forceinline__ void fence_mbar_init()
+{
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+
+__device__ __forceinline__ void mbar_expect_tx(uint64_t *bar, uint32_t bytes)
+{
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+
+__device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity)
+{
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "WAIT_LOOP:\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+        "@p bra WAIT_DONE;\n"
+        "bra WAIT_LOOP;\n"
+        "WAIT_DONE:\n"
+        "}\n" ::"r"(smem_u32(bar)), "r"(parity) : "memory");
+}
+
+// global -> this CTA's shared memory, completion counted in bytes on `bar`
+__device__ __forceinline__ void bulk_g2s(void *dstSmem, const void *srcGmem, uint32_t bytes, uint64_t *bar)
+{
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 ::"r"(smem_u32(dstSmem)), "l"(srcGmem), "r"(bytes), "r"(smem_u32(bar)) : "memory");
+}
+
+// ------------------------------------------------------------------------------------------------
+// eval kernel
+// ------------------------------------------------------------------------------------------------
+struct Decision
+{
+    float dOwn1;        // delta applied to the own row with stream V1
+    float dOwn2;        // delta applied afterwards with stream V2 (same-row move / exchange)
+    float dOther;       // delta for the other row of a two-row proposal
+    uint32_t otherRow;
+    uint32_t otherCol;
+    uint32_t flags;     // bit0 own1, bit1 own2, bit2 other
+};
+
+struct EvalSmem
+{
+    uint64_t bar;
+    float warpS[kThreads / 32];
+    float warpMu[kThreads / 32];
+    float segS[kMaxCluster];
+    float segMu[kMaxCluster];
+    Decision dec;
+    uint32_t pad[2];
+};
+
+__device__ __forceinline__ float derive_s(float d)
+{
+    // gaps::pmax(D, 0.1f): max(D * 0.1, 0.1) (MatrixMath.cpp:74-84, DenseNormalModel.h:73)
+    const float a = fmul(d, 0.1f);
+    return a < 0.1f ? 0.1f : a;
+}
+
+template <bool HAS_S, bool USE_V2, bool WITH_CHANGE>
+__device__ __forceinline__ void scan_segment(const float *bufD, const float *bufS, const float *bufAP,
+                                             const float *bufV1, const float *bufV2, uint32_t len, float ch,
+                                             float &accS, float &accMu)
+{
+    const uint32_t tid = threadIdx.x;
+    const uint32_t nVec = (len + kVec - 1) / kVec;
+    for (uint32_t j = tid; j < nVec; j += kThreads)
+    {
+        const float4 d4 = reinterpret_cast<const float4*>(bufD)[j];
+        const float4 a4 = reinterpret_cast<const float4*>(bufAP)[j];
+        const float4 v4 = reinterpret_cast<const float4*>(bufV1)[j];
+        float4 w4 = make_float4(0.f, 0.f, 0.f, 0.f);
+        float4 s4 = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (USE_V2) { w4 = reinterpret_cast<const float4*>(bufV2)[j]; }
+        if (HAS_S) { s4 = reinterpret_cast<const float4*>(bufS)[j]; }
+        const float d[4] = {d4.x, d4.y, d4.z, d4.w};
+        const float a[4] = {a4.x, a4.y, a4.z, a4.w};
+        const float v[4] = {v4.x, v4.y, v4.z, v4.w};
+        const float w[4] = {w4.x, w4.y, w4.z, w4.w};
+        const float su[4] = {s4.x, s4.y, s4.z, s4.w};
+        const uint32_t base = j * kVec;
+#pragma unroll
+        for (int c = 0; c < kVec; ++c)
+        {
+            if (base + c < len)
+            {
+                const float sd = HAS_S ? su[c] : derive_s(d[c]);
+                const float mat = USE_V2 ? fsub(v[c], w[c]) : v[c];
+                const float ratio = fdiv(mat, fmul(sd, sd));
+                accS = fadd(accS, fmul(mat, ratio));
+                const float resid = WITH_CHANGE ? fsub(d[c], fadd(a[c], fmul(ch, v[c]))) : fsub(d[c], a[c]);
+                accMu = fadd(accMu, fmul(ratio, resid));
+            }
+        }
+    }
+}
+
+template <bool HAS_S>
+__global__ void __launch_bounds__(kThreads) eval_kernel(const __grid_constant__ EvalParams P)
+{
+    extern __shared__ __align__(128) unsigned char smemRaw[];
+    EvalSmem *hdr = reinterpret_cast<EvalSmem*>(smemRaw);
+    const ModelView &mv = P.mv;
+    float *bufD = reinterpret_cast<float*>(smemRaw + 256);
+    float *bufAP = bufD + mv.segPad;
+    float *bufV1 = bufAP + mv.segPad;
+    float *bufV2 = bufV1 + mv.segPad;
+    float *bufS = bufV2 + mv.segPad;
+
+    cg::cluster_group cluster = cg::this_cluster();
+    const uint32_t rank = cluster.block_rank();
+    const uint32_t nSeg = mv.nSeg;
+    const uint32_t tid = threadIdx.x;
+    const uint32_t task = blockIdx.y;
+    const uint32_t pi = task < P.nProps ? task : static_cast<uint32_t>(P.extra[task - P.nProps]);
+    const uint32_t part = task < P.nProps ? 0u : 1u;
+
+    const uint32_t type = P.props[pi].type;
+    const uint32_t r1 = P.props[pi].r1, c1 = P.props[pi].c1, r2 = P.props[pi].r2, c2 = P.props[pi].c2;
+    const uint32_t variant = P.props[pi].variant;
+    const bool pairType = (type == 'M') || (type == 'E') || (type == kProbe && variant == 1);
+    const bool twoRow = pairType && (r1 != r2);
+    const bool useV2 = pairType && (r1 == r2);
+    const bool withChange = (type == 'D') || (type == kProbe && variant == 2);
+    const float m1 = P.props[pi].m1, m2 = P.props[pi].m2;
+    const float ch = (type == 'D') ? -m1 : P.props[pi].ch;
+    const uint32_t row = part ? r2 : r1;
+    const uint32_t colA = part ? c2 : c1;
+
+    const uint32_t segStart = rank * mv.seg;
+    const uint32_t len = segStart >= mv.L ? 0u : min(mv.seg, mv.L - segStart);
+    const uint32_t lenPad = (len + 3u) & ~3u;
+
+    // ---- stage the touched row segment and factor columns with bulk async copies ----
+    if (tid == 0)
+    {
+        mbar_init(&hdr->bar, 1);
+        fence_mbar_init();
+    }
+    __syncthreads();
+    float M1 = 0.f, M2 = 0.f;
+    if (tid == 0)
+    {
+        if (len > 0)
+        {
+            const uint32_t bytes = lenPad * 4u;
+            const uint32_t nStreams = 3u + (useV2 ? 1u : 0u) + (HAS_S ? 1u : 0u);
+            mbar_expect_tx(&hdr->bar, bytes * nStreams);
+            const size_t rowOff = static_cast<size_t>(row) * mv.ld + segStart;
+            bulk_g2s(bufD, mv.D + rowOff, bytes, &hdr->bar);
+            bulk_g2s(bufAP, mv.AP + rowOff, bytes, &hdr->bar);
+            bulk_g2s(bufV1, mv.otherM + static_cast<size_t>(colA) * mv.ldOther + segStart, bytes, &hdr->bar);
+            if (useV2) { bulk_g2s(bufV2, mv.otherM + static_cast<size_t>(c2) * mv.ldOther + segStart, bytes, &hdr->bar); }
+            if (HAS_S) { bulk_g2s(bufS, mv.S + rowOff, bytes, &hdr->bar); }
+        }
+        if (rank == 0 && type != kProbe)
+        {
+            // current factor-matrix elements, needed by safelyChangeMatrix; latency hides under the copies
+            M1 = mv.M[static_cast<size_t>(c1) * mv.ldM + r1];
+            if (pairType) { M2 = mv.M[static_cast<size_t>(c2) * mv.ldM + r2]; }
+        }
+    }
+
+    // ---- the scan ----
+    float accS = 0.f, accMu = 0.f;
+    if (len > 0)
+    {
+        mbar_wait(&hdr->bar, 0);
+        if (useV2)
+        {
+            scan_segment<HAS_S, true, false>(bufD, bufS, bufAP, bufV1, bufV2, len, 0.f, accS, accMu);
+        }
+        else if (withChange)
+        {
+            scan_segment<HAS_S, false, true>(bufD, bufS, bufAP, bufV1, bufV2, len, ch, accS, accMu);
+        }
+        else
+        {
+            scan_segment<HAS_S, false, false>(bufD, bufS, bufAP, bufV1, bufV2, len, 0.f, accS, accMu);
+        }
+    }
+    // lanes -> warp: xor butterfly, offsets 16,8,4,2,1 (the order the oracle reproduces)
+#pragma unroll
+    for (int off = 16; off >= 1; off >>= 1)
+    {
+        accS = fadd(accS, __shfl_xor_sync(0xffffffffu, accS, off));
+        accMu = fadd(accMu, __shfl_xor_sync(0xffffffffu, accMu, off));
+    }
+    if ((tid & 31) == 0)
+    {
+        hdr->warpS[tid >> 5] = accS;
+        hdr->warpMu[tid >> 5] = accMu;
+    }
+    __syncthreads();
+    // warps -> segment, in warp order; segment totals go to the cluster leader
+    if (tid == 0)
+    {
+        float sS = hdr->warpS[0], sMu = hdr->warpMu[0];
+#pragma unroll
+        for (int w = 1; w < kThreads / 32; ++w)
+        {
+            sS = fadd(sS, hdr->warpS[w]);
+            sMu = fadd(sMu, hdr->warpMu[w]);
+        }
+        EvalSmem *lead = cluster.map_shared_rank(hdr, 0);
+        lead->segS[rank] = sS;
+        lead->segMu[rank] = sMu;
+    }
+    cluster.sync();
+
+    // ---- decision: one lane of the leader CTA ----
+    if (rank == 0 && tid == 0)
+    {
+        float s = hdr->segS[0], mu = hdr->segMu[0];
+        for (uint32_t q = 1; q < nSeg; ++q)
+        {
+            s = fadd(s, hdr->segS[q]);
+            mu = fadd(mu, hdr->segMu[q]);
+        }
+        bool decide = true;
+        if (twoRow)
+        {
+            // the cluster that arrives second owns the decision; sums combine in (row1,row2) order
+            // whatever the arrival order: s = s1 + s2, s_mu = s_mu1 - s_mu2 (AlphaParameters.cpp:11-14)
+            AlphaPair mine;
+            mine.s = s;
+            mine.s_mu = mu;
+            mv.partials[pi * 2 + part] = mine;
+            __threadfence();
+            const uint32_t ticket = atomicAdd(&mv.tickets[pi], 1u);
+            decide = (ticket == 1u);
+            if (decide)
+            {
+                __threadfence();
+                const volatile AlphaPair *o = &mv.partials[pi * 2 + (1u - part)];
+                const float os = o->s, omu = o->s_mu;
+                mv.tickets[pi] = 0u;
+                const float s1 = part ? os : s, s2 = part ? s : os;
+                const float mu1 = part ? omu : mu, mu2 = part ? mu : omu;
+                s = fadd(s1, s2);
+                mu = fsub(mu1, mu2);
+            }
+        }
+        Decision dec;
+        dec.dOwn1 = dec.dOwn2 = dec.dOther = 0.f;
+        dec.otherRow = dec.otherCol = 0u;
+        dec.flags = 0u;
+        if (decide)
+        {
+            DevOutcome out;
+            out.mass1 = 0.f;
+            out.mass2 = 0.f;
+            out.accepted = 0u;
+            out.pad[0] = out.pad[1] = out.pad[2] = 0u;
+            const float T = mv.annealingTemp;
+            const float as = fmul(s, T), amu = fmul(mu, T);
+            out.s = as;
+            out.s_mu = amu;
+            Pcg rng;
+            rng.state = P.props[pi].rng;
+            float d1 = 0.f, d2 = 0.f;   // deltas of element (r1,c1) and (r2,c2)
+            bool ch1 = false, ch2 = false;
+            if (type == kProbe)
+            {
+                out.s = s;
+                out.s_mu = mu;
+            }
+            else if (type == 'B')
+            {
+                // AsynchronousGibbsSampler::birth, AsynchronousGibbsSampler.h:126-144
+                float mass = 0.f;
+                bool has;
+                if (mv.otherColNonzero[c1] != 0)
+                {
+                    has = gibbs_mass(rng, mv.erf, mv.erfinv, as, amu, 0.f, mv.maxGibbsMass, true, mv.lambda, &mass);
+                }
+                else
+                {
+                    mass = fdiv(fmul(-1.f, portable_logf(rng.uniform())), mv.lambda);
+                    has = true;
+                }
+                if (has && mass >= kEpsilon)
+                {
+                    out.accepted = 1u;
+                    out.mass1 = mass;
+                    d1 = mass;                      // changeMatrix: no clamp
+                    M1 = fadd(M1, mass);
+                    ch1 = true;
+                }
+            }
+            else if (type == 'D')
+            {
+                // AsynchronousGibbsSampler::death, :147-180
+                float rebirth = m1;
+                if (mv.otherColNonzero[c1] != 0)
+                {
+                    float g;
+                    if (gibbs_mass(rng, mv.erf, mv.erfinv, as, amu, 0.f, mv.maxGibbsMass, true, mv.lambda, &g)) { rebirth = g; }
+                }
+                const float dLL = fmul(rebirth, fsub(amu, fdiv(fmul(as, rebirth), 2.f)));
+                if (portable_logf(rng.uniform()) < dLL)
+                {
+                    out.accepted = 1u;
+                    out.mass1 = rebirth;
+                    if (rebirth != m1)
+                    {
+                        const float nv = gmax(fadd(M1, fsub(rebirth, m1)), 0.f); // safelyChangeMatrix
+                        d1 = fsub(nv, M1);
+                        M1 = nv;
+                        ch1 = true;
+                    }
+                }
+                else
+                {
+                    const float nv = gmax(fadd(M1, fmul(-1.f, m1)), 0.f);
+                    d1 = fsub(nv, M1);
+                    M1 = nv;
+                    ch1 = true;
+                }
+            }
+            else if (type == 'M')
+            {
+                // AsynchronousGibbsSampler::move, :183-196; deltaLogLikelihood DenseNormalModel.cpp:125-130
+                const float dLL = fmul(fmul(-1.f, m1), fadd(amu, fdiv(fmul(as, m1), 2.f)));
+                if (portable_logf(rng.uniform()) < dLL)
+                {
+                    out.accepted = 1u;
+                    out.mass1 = m1;
+                    const float nv = gmax(fadd(M1, -m1), 0.f);
+                    d1 = fsub(nv, M1);
+                    M1 = nv;
+                    ch1 = true;
+                    d2 = m1;                        // changeMatrix(r2, c2, mass)
+                    M2 = fadd(M2, m1);
+                    ch2 = true;
+                }
+            }
+            else if (type == 'E')
+            {
+                // AsynchronousGibbsSampler::exchange, :200-219; sampleExchange DenseNormalModel.cpp:154-159
+                if (mv.otherColNonzero[c1] != 0 || mv.otherColNonzero[c2] != 0)
+                {
+                    float g;
+                    const bool has = gibbs_mass(rng, mv.erf, mv.erfinv, as, amu, -m1, m2, false, 0.f, &g);
+                    const float n1 = fadd(m1, g), n2 = fsub(m2, g);
+                    if (has && n1 > kEpsilon && n2 > kEpsilon)
+                    {
+                        out.accepted = 1u;
+                        out.mass1 = n1;
+                        out.mass2 = n2;
+                        const float nv1 = gmax(fadd(M1, fsub(n1, m1)), 0.f);
+                        d1 = fsub(nv1, M1);
+                        M1 = nv1;
+                        ch1 = true;
+                        const float nv2 = gmax(fadd(M2, fsub(n2, m2)), 0.f);
+                        d2 = fsub(nv2, M2);
+                        M2 = nv2;
+                        ch2 = true;
+                    }
+                }
+            }
+            if (ch1) { mv.M[static_cast<size_t>(c1) * mv.ldM + r1] = M1; }
+            if (ch2) { mv.M[static_cast<size_t>(c2) * mv.ldM + r2] = M2; }
+            if (twoRow)
+            {
+                // own row is row `part`; the other row is committed through global memory
+                const float dOwn = part ? d2 : d1, dOth = part ? d1 : d2;
+                const bool cOwn = part ? ch2 : ch1, cOth = part ? ch1 : ch2;
+                dec.dOwn1 = dOwn;
+                dec.dOther = dOth;
+                dec.otherRow = part ? r1 : r2;
+                dec.otherCol = part ? c1 : c2;
+                dec.flags = (cOwn ? 1u : 0u) | (cOth ? 4u : 0u);
+            }
+            else
+            {
+                dec.dOwn1 = d1;
+                dec.dOwn2 = d2;
+                dec.flags = (ch1 ? 1u : 0u) | (ch2 ? 2u : 0u);
+            }
+            mv.outcomes[pi] = out;
+        }
+        hdr->dec = dec;
+    }
+    cluster.sync();
+
+    // ---- commit: AP[row,:] += delta * other[:,col] (updateAPMatrix, DenseNormalModel.cpp:243-258) ----
+    const Decision dec = *cluster.map_shared_rank(&hdr->dec, 0);
+    if ((dec.flags & 3u) != 0u && len > 0)
+    {
+        float *apRow = mv.AP + static_cast<size_t>(row) * mv.ld + segStart;
+        const uint32_t nVec = lenPad / kVec;
+        const bool own1 = (dec.flags & 1u) != 0u, own2 = (dec.flags & 2u) != 0u;
+        for (uint32_t j = tid; j < nVec; j += kThreads)
+        {
+            float4 a = reinterpret_cast<const float4*>(bufAP)[j];
+            if (own1)
+            {
+                const float4 v = reinterpret_cast<const float4*>(bufV1)[j];
+                a.x = fadd(a.x, fmul(dec.dOwn1, v.x));
+                a.y = fadd(a.y, fmul(dec.dOwn1, v.y));
+                a.z = fadd(a.z, fmul(dec.dOwn1, v.z));
+                a.w = fadd(a.w, fmul(dec.dOwn1, v.w));
+            }
+            if (own2)
+            {
+                const float4 v = reinterpret_cast<const float4*>(bufV2)[j];
+                a.x = fadd(a.x, fmul(dec.dOwn2, v.x));
+                a.y = fadd(a.y, fmul(dec.dOwn2, v.y));
+                a.z = fadd(a.z, fmul(dec.dOwn2, v.z));
+                a.w = fadd(a.w, fmul(dec.dOwn2, v.w));
+            }
+            reinterpret_cast<float4*>(apRow)[j] = a;
+        }
+    }
+    if ((dec.flags & 4u) != 0u && len > 0)
+    {
+        float *apRow = mv.AP + static_cast<size_t>(dec.otherRow) * mv.ld + segStart;
+        const float *vCol = mv.otherM + static_cast<size_t>(dec.otherCol) * mv.ldOther + segStart;
+        const uint32_t nVec = lenPad / kVec;
+        for (uint32_t j = tid; j < nVec; j += kThreads)
+        {
+            float4 a = reinterpret_cast<const float4*>(apRow)[j];
+            const float4 v = __ldg(reinterpret_cast<const float4*>(vCol) + j);
+            a.x = fadd(a.x, fmul(dec.dOther, v.x));
+            a.y = fadd(a.y, fmul(dec.dOther, v.y));
+            a.z = fadd(a.z, fmul(dec.dOther, v.z));
+            a.w = fadd(a.w, fmul(dec.dOther, v.w));
+            reinterpret_cast<float4*>(apRow)[j] = a;
+        }
+    }
+    // keep the leader's shared memory alive until every CTA has read the decision
+    cluster.sync();
+}
+
+// ------------------------------------------------------------------------------------------------
+// sync: dst[r][l] = src[l][r]  (DenseNormalModel::sync, DenseNormalModel.cpp:20-36)
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) transpose_kernel(float *__restrict__ dst, const float *__restrict__ src,
+                                                        uint32_t dstRows, uint32_t dstCols, uint32_t ldDst,
+                                                        uint32_t ldSrc)
+{
+    __shared__ float tile[32][33];
+    const uint32_t bx = blockIdx.x * 32, by = blockIdx.y * 32; // bx: dst col block, by: dst row block
+    const uint32_t tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+#pragma unroll
+    for (int i = 0; i < 32; i += 8)
+    {
+        const uint32_t srcRow = bx + ty + i, srcCol = by + tx; // src is [dstCols][dstRows]
+        tile[ty + i][tx] = (srcRow < dstCols && srcCol < dstRows) ? src[static_cast<size_t>(srcRow) * ldSrc + srcCol] : 0.f;
+    }
+    __syncthreads();
+#pragma unroll
+    for (int i = 0; i < 32; i += 8)
+    {
+        const uint32_t dRow = by + ty + i, dCol = bx + tx;
+        if (dRow < dstRows && dCol < dstCols) { dst[static_cast<size_t>(dRow) * ldDst + dCol] = tile[tx][ty + i]; }
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// extraInitialization: AP[r][l] = sum_c other[c][l] * M[c][r], c ascending, mul and add rounded
+// separately exactly like the reference's scalar triple loop (DenseNormalModel.cpp:38-54)
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) rebuild_ap_kernel(float *__restrict__ AP, const float *__restrict__ M,
+                                                         const float *__restrict__ otherM, uint32_t nRows,
+                                                         uint32_t L, uint32_t k, uint32_t ld, uint32_t ldM,
+                                                         uint32_t ldOther)
+{
+    const uint32_t r = blockIdx.y;
+    const uint32_t l = blockIdx.x * blockDim.x + threadIdx.x;
+    if (r >= nRows || l >= L) { return; }
+    float acc = 0.f;
+    for (uint32_t c = 0; c < k; ++c)
+    {
+        acc = fadd(acc, fmul(otherM[static_cast<size_t>(c) * ldOther + l], M[static_cast<size_t>(c) * ldM + r]));
+    }
+    AP[static_cast<size_t>(r) * ld + l] = acc;
+}
+
+// ------------------------------------------------------------------------------------------------
+// chiSq = sum ((D - AP) / S)^2 (DenseNormalModel.cpp:56-68).  Terms in fp32 exactly as the reference
+// forms them; accumulation in f64 in a fixed order (per-thread, warp tree, block, then the host adds
+// the per-block partials in index order) — deterministic and more accurate than the reference's
+// single fp32 running sum.
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) chisq_kernel(const float *__restrict__ D, const float *__restrict__ S,
+                                                    const float *__restrict__ AP, uint32_t nRows, uint32_t L,
+                                                    uint32_t ld, double *__restrict__ partials)
+{
+    __shared__ double warpSum[8];
+    double acc = 0.0;
+    for (uint32_t r = blockIdx.x; r < nRows; r += gridDim.x)
+    {
+        const float *d = D + static_cast<size_t>(r) * ld;
+        const float *a = AP + static_cast<size_t>(r) * ld;
+        const float *s = S ? S + static_cast<size_t>(r) * ld : nullptr;
+        for (uint32_t l = threadIdx.x; l < L; l += blockDim.x)
+        {
+            const float dv = d[l];
+            const float sv = s ? s[l] : derive_s(dv);
+            const float t = fdiv(fsub(dv, a[l]), sv);
+            acc += static_cast<double>(fmul(t, t));
+        }
+    }
+    for (int off = 16; off >= 1; off >>= 1) { acc += __shfl_xor_sync(0xffffffffu, acc, off); }
+    if ((threadIdx.x & 31) == 0) { warpSum[threadIdx.x >> 5] = acc; }
+    __syncthreads();
+    if (threadIdx.x == 0)
+    {
+        double t = 0.0;
+        for (int w = 0; w < 8; ++w) { t += warpSum[w]; }
+        partials[blockIdx.x] = t;
+    }
+}
+
+// canUseGibbs(col) == "column col of the factor matrix has a positive entry" (DenseNormalModel.cpp:100-108)
+__global__ void __launch_bounds__(256) col_nonzero_kernel(const float *__restrict__ M, uint32_t nRows, uint32_t ldM,
+                                                          int *__restrict__ flags)
+{
+    const float *col = M + static_cast<size_t>(blockIdx.x) * ldM;
+    int any = 0;
+    for (uint32_t i = threadIdx.x; i < nRows; i += blockDim.x) { any |= (col[i] > 0.f) ? 1 : 0; }
+    any = __syncthreads_or(any);
+    if (threadIdx.x == 0) { flags[blockIdx.x] = any; }
+}
+
+// gaps::max(Vector) per pattern (VectorMath.cpp; starts from 0), then norm = (max == 0) ? 1 : max
+__global__ void __launch_bounds__(256) col_max_kernel(const float *__restrict__ M, uint32_t nRows, uint32_t ldM,
+                                                      float *__restrict__ norms, int forceOne)
+{
+    __shared__ float warpMax[8];
+    const float *col = M + static_cast<size_t>(blockIdx.x) * ldM;
+    float mx = 0.f;
+    for (uint32_t i = threadIdx.x; i < nRows; i += blockDim.x) { mx = (col[i] > mx) ? col[i] : mx; }
+    for (int off = 16; off >= 1; off >>= 1)
+    {
+        const float o = __shfl_xor_sync(0xffffffffu, mx, off);
+        mx = (o > mx) ? o : mx;
+    }
+    if ((threadIdx.x & 31) == 0) { warpMax[threadIdx.x >> 5] = mx; }
+    __syncthreads();
+    if (threadIdx.x == 0)
+    {
+        for (int w = 0; w < 8; ++w) { mx = (warpMax[w] > mx) ? warpMax[w] : mx; }
+        mx = (mx == 0.f) ? 1.f : mx;
+        norms[blockIdx.x] = forceOne ? 1.f : mx;
+    }
+}
+
+// GapsStatistics::update (GapsStatistics.h:129-149): mean += x, sq += x*x with x = M/norm (divide != 0)
+// or x = M*norm
+__global__ void __launch_bounds__(256) stats_accumulate_kernel(const float *__restrict__ M, uint32_t nRows,
+                                                               uint32_t ldM, const float *__restrict__ norms,
+                                                               int divide, float *__restrict__ meanSum,
+                                                               float *__restrict__ sqSum)
+{
+    const uint32_t c = blockIdx.y;
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= nRows) { return; }
+    const size_t idx = static_cast<size_t>(c) * ldM + i;
+    const float nrm = norms[c];
+    const float x = divide ? fdiv(M[idx], nrm) : fmul(M[idx], nrm);
+    meanSum[idx] = fadd(meanSum[idx], x);
+    sqSum[idx] = fadd(sqSum[idx], fmul(x, x));
+}
+
+// pumpMatrix*Threshold (GapsStatistics.h:66-117): per row, the first pattern holding the maximum
+__global__ void __launch_bounds__(256) pump_kernel(const float *__restrict__ M, uint32_t nRows, uint32_t ldM,
+                                                   uint32_t k, float divisor, float *__restrict__ pump)
+{
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= nRows) { return; }
+    float mx = 0.f;
+    uint32_t arg = 0;
+    for (uint32_t c = 0; c < k; ++c)
+    {
+        const float v = fdiv(M[static_cast<size_t>(c) * ldM + i], divisor);
+        if (mx < v)
+        {
+            mx = v;
+            arg = c;
+        }
+    }
+    pump[static_cast<size_t>(arg) * ldM + i] += 1.f;
+}
+
+// meanChiSq (GapsStatistics.cpp:63-87): m = (sum_c Asum[i,c] Psum[j,c]) / n^2 in fp32, c ascending;
+// terms (d-m)^2 / s^2 in fp32; f64 accumulation as in chisq_kernel.  D is the P sampler's copy: [S][ld].
+__global__ void __launch_bounds__(256) mean_chisq_kernel(const float *__restrict__ D, const float *__restrict__ S,
+                                                         uint32_t nSamples, uint32_t nGenes, uint32_t ld,
+                                                         const float *__restrict__ Asum, uint32_t ldA,
+                                                         const float *__restrict__ Psum, uint32_t ldP, uint32_t k,
+                                                         float nSq, double *__restrict__ partials)
+{
+    __shared__ double warpSum[8];
+    double acc = 0.0;
+    for (uint32_t j = blockIdx.x; j < nSamples; j += gridDim.x)
+    {
+        const float *d = D + static_cast<size_t>(j) * ld;
+        const float *s = S ? S + static_cast<size_t>(j) * ld : nullptr;
+        for (uint32_t i = threadIdx.x; i < nGenes; i += blockDim.x)
+        {
+            float m = 0.f;
+            for (uint32_t c = 0; c < k; ++c)
+            {
+                m = fadd(m, fmul(Asum[static_cast<size_t>(c) * ldA + i], Psum[static_cast<size_t>(c) * ldP + j]));
+            }
+            m = fdiv(m, nSq);
+            const float dv = d[i];
+            const float sv = s ? s[i] : derive_s(dv);
+            const float diff = fsub(dv, m);
+            acc += static_cast<double>(fdiv(fmul(diff, diff), fmul(sv, sv)));
+        }
+    }
+    for (int off = 16; off >= 1; off >>= 1) { acc += __shfl_xor_sync(0xffffffffu, acc, off); }
+    if ((threadIdx.x & 31) == 0) { warpSum[threadIdx.x >> 5] = acc; }
+    __syncthreads();
+    if (threadIdx.x == 0)
+    {
+        double t = 0.0;
+        for (int w = 0; w < 8; ++w) { t += warpSum[w]; }
+        partials[blockIdx.x] = t;
+    }
+}
+
+// known-answer probe of the device portable log
+__global__ void logf_probe_kernel(const float *__restrict__ in, float *__restrict__ out, uint32_t n)
+{
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) { out[i] = portable_logf(in[i]); }
+}
+
+} // namespace cgb
+
+#endif // CGB_KERNELS_CUH

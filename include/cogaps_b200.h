@@ -251,6 +251,8 @@ typedef struct cgb_reduction_order
     uint32_t segmentLength;
 } cgb_reduction_order;
 int cgb_sampler_reduction_order(const cgb_sampler *s, cgb_reduction_order *out);
+/* the same, for any sampler whose rows have this length (no device needed) */
+int cgb_reduction_order_for_length(uint32_t rowLength, cgb_reduction_order *out);
 
 /* ------------------------------------------------------------------------------------------
  * GapsStatistics (src/GapsStatistics.h:17-64): running sums for Amean/Asd/Pmean/Psd kept on
@@ -284,6 +286,15 @@ int cgb_sampler_device_matrix(const cgb_sampler *s, void **dev, uint64_t *ld);
 /* device pointers of the statistics sums (same layout) */
 int cgb_stats_device_sums(const cgb_stats *st, void **AmeanSum, void **AsqSum, void **PmeanSum,
                           void **PsqSum, uint64_t *ldA, uint64_t *ldP, uint32_t *nUpdates);
+
+/* ------------------------------------------------------------------------------------------
+ * Test hooks (no reference counterpart)
+ * ---------------------------------------------------------------------------------------- */
+/* lookup tables cgb_run hands to the GapsRandomState it creates (NULLs restore the built-ins) */
+int cgb_run_set_tables(const float *erf, const float *erfinv, const float *qgamma);
+/* the portable log of csrc/gaps_math.h evaluated on the device / on the host */
+int cgb_debug_logf(const float *in, float *out, uint32_t n);
+float cgb_debug_host_logf(float x);
 
 #ifdef __cplusplus
 }
