@@ -1,0 +1,344 @@
+#!/usr/bin/env python
+"""bench.py — atom-updates/s of the Gibbs-sampler hot path on the BASELINE.json workload.
+
+Workload (config.workload): synthetic dense 20000x5000, nPatterns=20 (BASELINE.json configs[2], the
+configuration the metric is quoted on; recipe SURVEY.md 8(d)).  A "step" is one MCMC iteration of the
+hot path exactly as GapsRunner.cpp:294-296 drives it: nA ~ Poisson(atomsA), nP ~ Poisson(atomsP),
+A.update(nA) -> P.sync(A) -> P.update(nP) -> A.sync(P).
+
+  value  : atom-updates/s over K timed steps with D/S/AP/factors resident in HBM, after a ramp that grows
+           the chain from zero atoms (untimed) and W warm-up steps.  Host generator + device evaluator:
+           every batch's proposals go H2D as kernel parameters and its outcomes come back D2H, inside the
+           timed region, because that is what the path is.
+  e2e    : the same metric through the reference-facing entry point cgb_run (= gaps::run) on HOST buffers:
+           upload of both data orientations, the whole two-phase run from zero atoms, statistics, download
+           of Amean/Asd/Pmean/Psd — wall clock of the call.  `--impl reference` times the reference's own
+           gaps::run on the identical call (same matrix, seed, iterations) on the host cores.
+  roofline: eval kernel, algorithmic bytes (16L/20L/32L read + 4L per changed AP row) over
+           CUDA-event time of every launch, from a separate pass with per-launch events enabled.
+  cpu_baseline: oracle/_ref (the unmodified reference, OpenMP, all host threads) on a bounded sample.
+
+Multi-GPU (--gpus N under torchrun): the path does not shard inside one chain ("replicas only");
+each rank runs an independent chain on its own shard-sized matrix (what distributed CoGAPS does per set),
+no data-path collective, scaling = weak; time is the max over ranks.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+G, S, K = 20000, 5000, 20
+DATA_SEED = 20260117
+CHAIN_SEED = 42
+RAMP_ITERS = 50          # untimed iterations growing the chain from zero atoms before warm-up
+E2E_ITERS = 20           # iterations per phase of the end-to-end / reference gaps::run call
+
+
+def make_data(g=G, s=S, k=K, seed=DATA_SEED):
+    """SURVEY 8(d) C3 recipe: noisy non-negative rank-k matrix, max < 50, fp32."""
+    rng = np.random.default_rng(seed)
+    a0 = (rng.gamma(2.0, 0.5, (g, k)) * (rng.random((g, k)) < 0.3)).astype(np.float32)
+    p0 = (rng.gamma(2.0, 0.5, (s, k)) * (rng.random((s, k)) < 0.3)).astype(np.float32)
+    m = a0 @ p0.T
+    noise = rng.standard_normal(m.shape, dtype=np.float32)
+    d = np.maximum(m * (1.0 + 0.1 * noise), 0.0)
+    d *= np.float32(40.0 / max(float(d.max()), 1e-9))
+    return np.ascontiguousarray(d, dtype=np.float32)
+
+
+def load_peaks():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(path):
+        with open(path) as f:
+            return float(json.load(f)["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+    return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
+
+
+class ClockSampler(object):
+    """nvidia-smi clocks / throttle reasons sampled during the timed region."""
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.rows = []
+        self.proc = None
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(index), "--query-gpu=" + self.Q,
+                                          "--format=csv,noheader,nounits", "-lms", "200"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.thread = threading.Thread(target=self._read, daemon=True)
+            self.thread.start()
+        except OSError:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append(line.strip())
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except subprocess.TimeoutExpired:
+            self.proc.kill()
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for row in self.rows:
+            parts = [p.strip() for p in row.split(",")]
+            if len(parts) < 7:
+                continue
+            try:
+                sm.append(float(parts[0]))
+                mx.append(float(parts[1]))
+            except ValueError:
+                continue
+            for name, val in zip(names, parts[3:7]):
+                if val.lower().startswith("active"):
+                    reasons.add(name)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+class Chain(object):
+    """Both samplers of one factorisation, driven like runOnePhase (GapsRunner.cpp:272-327)."""
+
+    def __init__(self, data, k, seed):
+        import cogaps_b200 as cg
+        from cogaps_b200._runhelp import make_params
+        self.cg = cg
+        self.params = make_params(nPatterns=k, seed=seed)
+        self.rs = cg.GapsRandomState(seed)
+        # GapsRunner.cpp:402-406: A sampler sees the data transposed, P sampler as given
+        self.A = cg.GibbsSampler(data, True, True, 0.01, 100.0, self.params, self.rs)
+        self.P = cg.GibbsSampler(data, False, False, 0.01, 100.0, self.params, self.rs)
+        self.rng = cg.GapsRng(self.rs)
+        self.A.sync(self.P)
+        self.P.sync(self.A)
+        self.A.extraInitialization()
+        self.P.extraInitialization()
+
+    def step(self):
+        nA = self.rng.poisson(float(max(self.A.nAtoms(), 10)))
+        nP = self.rng.poisson(float(max(self.P.nAtoms(), 10)))
+        self.A.update(nA)
+        self.P.sync(self.A)
+        self.P.update(nP)
+        self.A.sync(self.P)
+        return nA + nP
+
+    def ramp(self, iters):
+        for i in range(iters):
+            temp = min(1.0, 2.0 * i / iters)      # annealing as in the equilibration phase
+            self.A.setAnnealingTemp(temp)
+            self.P.setAnnealingTemp(temp)
+            self.step()
+        self.A.setAnnealingTemp(1.0)
+        self.P.setAnnealingTemp(1.0)
+
+
+def run_reference(args, data):
+    """The reference's own gaps::run (oracle/_ref, unmodified sources, OpenMP over all host threads)."""
+    from oracle.harness import RefLib
+    variant = "fast" if RefLib.available("fast") else "scalar"
+    ref = RefLib(variant)
+    threads = ref.max_threads()
+    t0 = time.time()
+    res = ref.run(data, seed=CHAIN_SEED, nPatterns=K, nIterations=args.e2e_iters, outputFrequency=0,
+                  maxThreads=threads)
+    wall = res.totalRunningTime
+    value = res.totalUpdates / wall
+    sample = ("one gaps::run call, %d iterations/phase from zero atoms, %d atom updates, %.1f s in gaps::run "
+              "(%.1f s incl. host matrix conversion); build: oracle/_ref %s, %d OpenMP threads"
+              % (args.e2e_iters, res.totalUpdates, wall, time.time() - t0, variant, threads))
+    return value, wall, int(res.totalUpdates), threads, sample
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--ramp", type=int, default=RAMP_ITERS)
+    ap.add_argument("--e2e-iters", type=int, default=E2E_ITERS)
+    ap.add_argument("--rows", type=int, default=G)
+    ap.add_argument("--cols", type=int, default=S)
+    ap.add_argument("--patterns", type=int, default=K)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-e2e", action="store_true")
+    args = ap.parse_args()
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    workload = "synthetic dense %dx%d nPatterns=%d" % (args.rows, args.cols, args.patterns)
+    config = {"workload": workload, "data_seed": DATA_SEED, "chain_seed": CHAIN_SEED,
+              "sampler": "asynchronous, dense normal model, default uncertainty",
+              "step": "one MCMC iteration: A.update(Poisson(atomsA)) + P.sync + P.update(Poisson(atomsP)) + A.sync",
+              "ramp_iterations": args.ramp,
+              "l2": "inputs larger than L2: 1.6 GB of resident D/AP streamed ~40 GB per step, no flush needed",
+              "parallelism": "replicas x%d (one independent chain per GPU, no data-path collective)" % world
+              if world > 1 else "single chain"}
+
+    if args.impl == "reference":
+        if rank != 0:
+            return 0
+        data = make_data(args.rows, args.cols, args.patterns)
+        value, wall, updates, threads, sample = run_reference(args, data)
+        line = {"impl": "reference", "metric": "atom_updates_per_s", "value": value, "unit": "atom-updates/s",
+                "n_gpus": args.gpus, "steps": 1, "warmup": 0, "ms_per_step": wall * 1e3,
+                "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
+                "data": "synthetic", "config": config,
+                "cpu_baseline": {"value": value, "unit": "atom-updates/s", "cores": threads, "kind": "reference",
+                                 "sample": sample},
+                "e2e": {"value": value, "unit": "atom-updates/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+        print(json.dumps(line))
+        return 0
+
+    import torch
+    import torch.distributed as dist
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device: the hot path has no CPU fallback")
+    torch.cuda.set_device(local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    import cogaps_b200 as cg
+    from cogaps_b200._lib import check
+    check(cg.lib().cgb_set_device(local_rank))
+
+    data = make_data(args.rows, args.cols, args.patterns, DATA_SEED + rank)
+    t_setup = time.time()
+    chain = Chain(data, args.patterns, CHAIN_SEED + rank)
+    chain.ramp(args.ramp)
+    for _ in range(args.warmup):
+        chain.step()
+    setup_s = time.time() - t_setup
+
+    def barrier():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    # ---- timed region: exactly K steps ----
+    chain.A.resetCounters()
+    chain.P.resetCounters()
+    launches0 = cg.lib().cgb_kernel_launch_count()
+    clocks = ClockSampler(local_rank)
+    barrier()
+    t0 = time.perf_counter()
+    updates = 0
+    for _ in range(args.steps):
+        updates += chain.step()
+    barrier()
+    elapsed = time.perf_counter() - t0
+    clock_info = clocks.stop()
+    launches = cg.lib().cgb_kernel_launch_count() - launches0
+    cA, cP = chain.A.counters(), chain.P.counters()
+    queued = cA.nProposalsQueued + cP.nProposalsQueued
+    batches = cA.nBatches + cP.nBatches
+    h2d_step = queued * 48.0 / args.steps
+    d2h_step = queued * 32.0 / args.steps
+
+    if world > 1:
+        t = torch.tensor([elapsed], dtype=torch.float64, device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        elapsed_max = float(t.item())
+        u = torch.tensor([float(updates), float(launches)], dtype=torch.float64, device="cuda")
+        dist.all_reduce(u, op=dist.ReduceOp.SUM)
+        total_updates, total_launches = float(u[0].item()), int(u[1].item())
+    else:
+        elapsed_max, total_updates, total_launches = elapsed, float(updates), int(launches)
+    value = total_updates / elapsed_max
+
+    # ---- roofline pass: per-launch CUDA events on the launching stream (separate from the timed region) ----
+    roofline = None
+    if rank == 0:
+        chain.A.setKernelTiming(True)
+        chain.P.setKernelTiming(True)
+        chain.A.resetCounters()
+        chain.P.resetCounters()
+        for _ in range(2):
+            chain.step()
+        rA, rP = chain.A.counters(), chain.P.counters()
+        chain.A.setKernelTiming(False)
+        chain.P.setKernelTiming(False)
+        peak, peak_src = load_peaks()
+        bytes_total = rA.algorithmicBytes + rP.algorithmicBytes
+        ktime = rA.secondsKernel + rP.secondsKernel
+        achieved = bytes_total / ktime / 1e9
+        traffic = None
+        tpath = os.path.join(ROOT, "profiles", "eval_kernel_traffic.json")
+        if os.path.exists(tpath):
+            with open(tpath) as f:
+                traffic = json.load(f).get("dram_bytes_per_launch")
+        roofline = {"bound": "hbm", "kernel": "eval_kernel (alphaParameters scan + epilogue + AP commit)",
+                    "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                    "peak_source": peak_src, "traffic": traffic,
+                    "algorithmic_bytes_per_launch": bytes_total / max(rA.nBatches + rP.nBatches, 1),
+                    "avg_launch_us": ktime / max(rA.nBatches + rP.nBatches, 1) * 1e6,
+                    "A_side": {"GBps": rA.algorithmicBytes / max(rA.secondsKernel, 1e-12) / 1e9,
+                               "avg_launch_us": rA.secondsKernel / max(rA.nBatches, 1) * 1e6,
+                               "proposals_per_launch": rA.nProposalsQueued / max(rA.nBatches, 1)},
+                    "P_side": {"GBps": rP.algorithmicBytes / max(rP.secondsKernel, 1e-12) / 1e9,
+                               "avg_launch_us": rP.secondsKernel / max(rP.nBatches, 1) * 1e6,
+                               "proposals_per_launch": rP.nProposalsQueued / max(rP.nBatches, 1)}}
+        # chi-sq wall time (second half of BASELINE.json's metric)
+        tcs = time.perf_counter()
+        for _ in range(5):
+            chain.P.chiSq()
+        chisq_ms = (time.perf_counter() - tcs) / 5 * 1e3
+    atomsA, atomsP = chain.A.nAtoms(), chain.P.nAtoms()
+    del chain
+
+    # ---- end to end: cgb_run (= gaps::run) on host buffers ----
+    e2e = None
+    if rank == 0 and not args.no_e2e:
+        t0 = time.perf_counter()
+        res = cg.gaps_run(data, seed=CHAIN_SEED, nPatterns=args.patterns, nIterations=args.e2e_iters,
+                          outputFrequency=0, maxThreads=1)
+        wall = time.perf_counter() - t0
+        n_it = 2 * args.e2e_iters
+        upload = 2.0 * data.nbytes
+        results = 4.0 * 2 * (args.rows + args.cols) * args.patterns
+        e2e = {"value": res.totalUpdates / wall, "unit": "atom-updates/s",
+               "h2d_bytes_per_step": (upload + 48.0 * res.totalUpdates) / n_it,
+               "d2h_bytes_per_step": (results + 32.0 * res.totalUpdates) / n_it,
+               "call": "cgb_run (gaps::run): host fp32 matrix in, Amean/Asd/Pmean/Psd out",
+               "iterations_per_phase": args.e2e_iters, "atom_updates": int(res.totalUpdates), "wall_s": wall}
+
+    cpu_baseline = None
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        v, wall, upd, threads, sample = run_reference(args, data)
+        cpu_baseline = {"value": v, "unit": "atom-updates/s", "cores": threads, "kind": "reference", "sample": sample}
+
+    if rank == 0:
+        line = {"metric": "atom_updates_per_s", "value": value, "unit": "atom-updates/s", "n_gpus": args.gpus,
+                "steps": args.steps, "warmup": args.warmup, "ms_per_step": elapsed_max / args.steps * 1e3,
+                "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
+                "data": "synthetic", "config": config, "clocks": clock_info, "e2e": e2e,
+                "gpu_launches": total_launches, "roofline": roofline, "cpu_baseline": cpu_baseline,
+                "chisq_ms": chisq_ms, "atoms": {"A": int(atomsA), "P": int(atomsP)},
+                "batches_per_step": batches / args.steps, "proposals_per_batch": queued / max(batches, 1),
+                "host_generate_s_per_step": (cA.secondsHostGenerate + cP.secondsHostGenerate) / args.steps,
+                "device_wait_s_per_step": (cA.secondsDeviceWait + cP.secondsDeviceWait) / args.steps,
+                "h2d_bytes_per_step": h2d_step, "d2h_bytes_per_step": d2h_step, "setup_s": setup_s}
+        print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+    return 0
+
+
+if __name__ == "__main__":
+    sys.exit(main())

@@ -249,7 +249,7 @@ static int checkSubset(const cgb_params *p, uint32_t nrow, uint32_t ncol)
 // one cluster per row scan: nSeg CTAs of kThreads threads, each staging `seg` floats per stream
 static void segmentsForLength(uint32_t L, uint32_t &nSeg, uint32_t &seg)
 {
-    const uint32_t target = static_cast<uint32_t>(envInt("COGAPS_SEG_FLOATS", 2560));
+    const uint32_t target = static_cast<uint32_t>(envInt("COGAPS_SEG_FLOATS", 5120));
     const uint32_t maxCluster = static_cast<uint32_t>(envInt("COGAPS_MAX_CLUSTER", 4));
     uint32_t n = 1;
     while (n < maxCluster && n < static_cast<uint32_t>(kMaxCluster) && (L + n - 1) / n > target) { n *= 2; }
@@ -278,7 +278,7 @@ extern "C" void cgb_sampler_destroy(cgb_sampler *s)
     if (!s) { return; }
     cudaSetDevice(s->device);
     cudaFree(s->dD); cudaFree(s->dS); cudaFree(s->dAP); cudaFree(s->dM); cudaFree(s->dColNonzero);
-    cudaFree(s->dPartials); cudaFree(s->dTickets); cudaFree(s->dReducePartials);
+    cudaFree(s->dPartials); cudaFree(s->dTickets); cudaFree(s->dReducePartials); cudaFree(s->dPhaseClocks);
     if (s->hOutcomes) { cudaFreeHost(s->hOutcomes); }
     if (s->hReducePartials) { cudaFreeHost(s->hReducePartials); }
     if (s->evStart) { cudaEventDestroy(s->evStart); }
@@ -306,6 +306,8 @@ extern "C" int cgb_sampler_create(const float *data, uint32_t nrow, uint32_t nco
     std::memset(static_cast<void*>(&s->counters), 0, sizeof(s->counters));
     s->dD = s->dS = s->dAP = s->dM = nullptr;
     s->dColNonzero = nullptr; s->dPartials = nullptr; s->dTickets = nullptr; s->dReducePartials = nullptr;
+    s->dPhaseClocks = nullptr; s->phaseTasks = 0;
+    for (int i = 0; i < kPhaseSlots; ++i) { s->phaseSum[i] = 0.0; }
     s->hOutcomes = nullptr; s->hReducePartials = nullptr; s->stream = nullptr; s->evStart = s->evStop = nullptr;
     s->other = nullptr;
     s->rs = rs;
@@ -486,6 +488,7 @@ static void fillModelView(const cgb_sampler *s, ModelView &mv)
     mv.outcomes = s->hOutcomes;
     mv.partials = s->dPartials;
     mv.tickets = s->dTickets;
+    mv.phaseClocks = s->dPhaseClocks;
     mv.nRows = s->nRows;
     mv.L = s->L;
     mv.k = s->k;
@@ -517,7 +520,7 @@ static int launchEval(cgb_sampler *s, EvalParams &params)
     cfg = cudaLaunchConfig_t();
     cfg.gridDim = dim3(s->nSeg, params.nTasks, 1);
     cfg.blockDim = dim3(kThreads, 1, 1);
-    cfg.dynamicSmemBytes = s->smemBytes;
+    cfg.dynamicSmemBytes = 256 + static_cast<size_t>(s->hasS ? 5 : 4) * s->segPad * sizeof(float);
     cfg.stream = s->stream;
     cudaLaunchAttribute attr[1];
     attr[0].id = cudaLaunchAttributeClusterDimension;
@@ -542,6 +545,47 @@ static int launchEval(cgb_sampler *s, EvalParams &params)
     }
     s->counters.secondsDeviceWait += nowSeconds() - t0;
     s->counters.nBatches += 1;
+    if (s->dPhaseClocks)
+    {
+        std::vector<unsigned long long> h(static_cast<size_t>(params.nTasks) * kPhaseSlots);
+        CGB_CUDA(cudaMemcpy(h.data(), s->dPhaseClocks, h.size() * sizeof(unsigned long long), cudaMemcpyDeviceToHost));
+        unsigned long long firstStart = ~0ull, lastStart = 0;
+        for (uint32_t t = 0; t < params.nTasks; ++t)
+        {
+            const unsigned long long *p = h.data() + static_cast<size_t>(t) * kPhaseSlots;
+            firstStart = std::min(firstStart, p[0]);
+            lastStart = std::max(lastStart, p[0]);
+            for (int i = 2; i < 9; ++i) { s->phaseSum[i] += static_cast<double>(p[i] - p[1]); }
+        }
+        s->phaseSum[0] += static_cast<double>(lastStart - firstStart); // ns between first and last CTA start
+        s->phaseSum[1] += 1.0;                                          // launches
+        s->phaseTasks += params.nTasks;
+    }
+    return CGB_OK;
+}
+
+// debug: per-phase SM-clock offsets of the leader CTA of every task, averaged (COGAPS phase profile)
+extern "C" int cgb_sampler_debug_phase_clocks(cgb_sampler *s, int32_t enable, double *out, uint64_t *nTasks)
+{
+    CGB_CHECK(s != nullptr, "cgb_sampler_debug_phase_clocks: NULL sampler");
+    CGB_CUDA(cudaSetDevice(s->device));
+    if (out)
+    {
+        for (int i = 0; i < kPhaseSlots; ++i) { out[i] = s->phaseSum[i]; }
+    }
+    if (nTasks) { *nTasks = s->phaseTasks; }
+    if (enable && !s->dPhaseClocks)
+    {
+        CGB_CUDA(cudaMalloc(&s->dPhaseClocks, sizeof(unsigned long long) * kPhaseSlots * 2 * kMaxBatch));
+        CGB_CUDA(cudaMemset(s->dPhaseClocks, 0, sizeof(unsigned long long) * kPhaseSlots * 2 * kMaxBatch));
+    }
+    if (!enable && s->dPhaseClocks)
+    {
+        cudaFree(s->dPhaseClocks);
+        s->dPhaseClocks = nullptr;
+    }
+    for (int i = 0; i < kPhaseSlots; ++i) { s->phaseSum[i] = 0.0; }
+    s->phaseTasks = 0;
     return CGB_OK;
 }
 

@@ -10,6 +10,7 @@ static const int kThreads = 256;      // threads per CTA of the eval kernel (8 w
 static const int kVec = 4;            // floats per vector access (16 B)
 static const int kMaxBatch = 384;     // proposals per launch carried in kernel-parameter space
 static const int kMaxCluster = 8;     // portable cluster limit
+static const int kPhaseSlots = 12;    // debug phase timestamps per task
 static const uint32_t kProbe = 'P';   // lock-step probe pseudo-proposal
 
 struct AlphaPair { float s, s_mu; };
@@ -52,6 +53,7 @@ struct ModelView
     DevOutcome *outcomes;    // [kMaxBatch] pinned host memory, written by the kernel
     AlphaPair *partials;     // [kMaxBatch][2] cross-cluster (s, s_mu) of two-row proposals
     uint32_t *tickets;       // [kMaxBatch]
+    unsigned long long *phaseClocks; // debug: [kMaxBatch][kPhaseSlots] SM clock at each phase, or nullptr
     uint32_t nRows, L, k;
     uint32_t ld, ldM, ldOther;
     uint32_t seg;            // floats per segment (multiple of 4)

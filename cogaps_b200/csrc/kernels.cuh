@@ -104,13 +104,14 @@ __device__ __forceinline__ void scan_segment(const float *bufD, const float *buf
 {
     const uint32_t tid = threadIdx.x;
     const uint32_t nVec = (len + kVec - 1) / kVec;
+#pragma unroll 2
     for (uint32_t j = tid; j < nVec; j += kThreads)
     {
         const float4 d4 = reinterpret_cast<const float4*>(bufD)[j];
         const float4 a4 = reinterpret_cast<const float4*>(bufAP)[j];
         const float4 v4 = reinterpret_cast<const float4*>(bufV1)[j];
         float4 w4 = make_float4(0.f, 0.f, 0.f, 0.f);
-        float4 s4 = make_float4(0.f, 0.f, 0.f, 0.f);
+        float4 s4 = make_float4(1.f, 1.f, 1.f, 1.f);
         if (USE_V2) { w4 = reinterpret_cast<const float4*>(bufV2)[j]; }
         if (HAS_S) { s4 = reinterpret_cast<const float4*>(bufS)[j]; }
         const float d[4] = {d4.x, d4.y, d4.z, d4.w};
@@ -119,19 +120,40 @@ __device__ __forceinline__ void scan_segment(const float *bufD, const float *buf
         const float w[4] = {w4.x, w4.y, w4.z, w4.w};
         const float su[4] = {s4.x, s4.y, s4.z, s4.w};
         const uint32_t base = j * kVec;
+        float ts[4], tmu[4];
+        // Four independent element pipelines, no branches: an element with mat == 0 (or past the end of
+        // the row) contributes exactly +0 to both sums, so it is replaced by a select instead of being
+        // computed — which also keeps the IEEE division off the slow path a zero numerator would take.
 #pragma unroll
         for (int c = 0; c < kVec; ++c)
         {
-            if (base + c < len)
-            {
-                const float sd = HAS_S ? su[c] : derive_s(d[c]);
-                const float mat = USE_V2 ? fsub(v[c], w[c]) : v[c];
-                const float ratio = fdiv(mat, fmul(sd, sd));
-                accS = fadd(accS, fmul(mat, ratio));
-                const float resid = WITH_CHANGE ? fsub(d[c], fadd(a[c], fmul(ch, v[c]))) : fsub(d[c], a[c]);
-                accMu = fadd(accMu, fmul(ratio, resid));
-            }
+            const float mat = USE_V2 ? fsub(v[c], w[c]) : v[c];
+            const bool live = (base + c < len) && (mat != 0.f);
+            const float sd = HAS_S ? su[c] : derive_s(d[c]);
+            const float ratio = fdiv(live ? mat : 1.f, fmul(sd, sd));
+            const float resid = WITH_CHANGE ? fsub(d[c], fadd(a[c], fmul(ch, v[c]))) : fsub(d[c], a[c]);
+            ts[c] = live ? fmul(mat, ratio) : 0.f;
+            tmu[c] = live ? fmul(ratio, resid) : 0.f;
         }
+        // the lane's running sums take the elements in increasing index order
+#pragma unroll
+        for (int c = 0; c < kVec; ++c)
+        {
+            accS = fadd(accS, ts[c]);
+            accMu = fadd(accMu, tmu[c]);
+        }
+    }
+}
+
+// debug phase profile: SM clock of the leader CTA's lane 0 at each phase boundary (off unless requested)
+__device__ __forceinline__ void stamp(const ModelView &mv, uint32_t task, uint32_t rank, int slot)
+{
+    if (mv.phaseClocks != nullptr && rank == 0 && threadIdx.x == 0)
+    {
+        unsigned long long t;
+        asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+        mv.phaseClocks[static_cast<size_t>(task) * kPhaseSlots + slot] = (slot == 0) ? t : static_cast<unsigned long long>(clock64());
+        if (slot == 0) { mv.phaseClocks[static_cast<size_t>(task) * kPhaseSlots + 1] = static_cast<unsigned long long>(clock64()); }
     }
 }
 
@@ -171,6 +193,7 @@ __global__ void __launch_bounds__(kThreads) eval_kernel(const __grid_constant__ 
     const uint32_t len = segStart >= mv.L ? 0u : min(mv.seg, mv.L - segStart);
     const uint32_t lenPad = (len + 3u) & ~3u;
 
+    stamp(mv, task, rank, 0); // slots 0 (globaltimer), 1 (clock)
     // ---- stage the touched row segment and factor columns with bulk async copies ----
     if (tid == 0)
     {
@@ -179,6 +202,7 @@ __global__ void __launch_bounds__(kThreads) eval_kernel(const __grid_constant__ 
     }
     __syncthreads();
     float M1 = 0.f, M2 = 0.f;
+    int can1 = 0, can2 = 0;
     if (tid == 0)
     {
         if (len > 0)
@@ -197,15 +221,22 @@ __global__ void __launch_bounds__(kThreads) eval_kernel(const __grid_constant__ 
         {
             // current factor-matrix elements, needed by safelyChangeMatrix; latency hides under the copies
             M1 = mv.M[static_cast<size_t>(c1) * mv.ldM + r1];
-            if (pairType) { M2 = mv.M[static_cast<size_t>(c2) * mv.ldM + r2]; }
+            can1 = mv.otherColNonzero[c1];
+            if (pairType)
+            {
+                M2 = mv.M[static_cast<size_t>(c2) * mv.ldM + r2];
+                can2 = mv.otherColNonzero[c2];
+            }
         }
     }
 
+    stamp(mv, task, rank, 2); // copies issued
     // ---- the scan ----
     float accS = 0.f, accMu = 0.f;
     if (len > 0)
     {
         mbar_wait(&hdr->bar, 0);
+        stamp(mv, task, rank, 3); // data landed
         if (useV2)
         {
             scan_segment<HAS_S, true, false>(bufD, bufS, bufAP, bufV1, bufV2, len, 0.f, accS, accMu);
@@ -219,6 +250,7 @@ __global__ void __launch_bounds__(kThreads) eval_kernel(const __grid_constant__ 
             scan_segment<HAS_S, false, false>(bufD, bufS, bufAP, bufV1, bufV2, len, 0.f, accS, accMu);
         }
     }
+    stamp(mv, task, rank, 4); // scan done
     // lanes -> warp: xor butterfly, offsets 16,8,4,2,1 (the order the oracle reproduces)
 #pragma unroll
     for (int off = 16; off >= 1; off >>= 1)
@@ -232,21 +264,27 @@ __global__ void __launch_bounds__(kThreads) eval_kernel(const __grid_constant__ 
         hdr->warpMu[tid >> 5] = accMu;
     }
     __syncthreads();
-    // warps -> segment, in warp order; segment totals go to the cluster leader
-    if (tid == 0)
+    // warps -> segment: the warp totals sit in the low lanes of warp 0 (zeros above) and combine by
+    // the same xor butterfly; segment totals go to the cluster leader
+    if (tid < 32)
     {
-        float sS = hdr->warpS[0], sMu = hdr->warpMu[0];
+        float sS = (tid < kThreads / 32) ? hdr->warpS[tid] : 0.f;
+        float sMu = (tid < kThreads / 32) ? hdr->warpMu[tid] : 0.f;
 #pragma unroll
-        for (int w = 1; w < kThreads / 32; ++w)
+        for (int off = 16; off >= 1; off >>= 1)
         {
-            sS = fadd(sS, hdr->warpS[w]);
-            sMu = fadd(sMu, hdr->warpMu[w]);
+            sS = fadd(sS, __shfl_xor_sync(0xffffffffu, sS, off));
+            sMu = fadd(sMu, __shfl_xor_sync(0xffffffffu, sMu, off));
         }
-        EvalSmem *lead = cluster.map_shared_rank(hdr, 0);
-        lead->segS[rank] = sS;
-        lead->segMu[rank] = sMu;
+        if (tid == 0)
+        {
+            EvalSmem *lead = (nSeg > 1) ? cluster.map_shared_rank(hdr, 0) : hdr;
+            lead->segS[rank] = sS;
+            lead->segMu[rank] = sMu;
+        }
     }
-    cluster.sync();
+    if (nSeg > 1) { cluster.sync(); } // single-CTA rows: the same lane wrote and reads the totals
+    stamp(mv, task, rank, 5); // cluster reduce done
 
     // ---- decision: one lane of the leader CTA ----
     if (rank == 0 && tid == 0)
@@ -310,7 +348,7 @@ __global__ void __launch_bounds__(kThreads) eval_kernel(const __grid_constant__ 
                 // AsynchronousGibbsSampler::birth, AsynchronousGibbsSampler.h:126-144
                 float mass = 0.f;
                 bool has;
-                if (mv.otherColNonzero[c1] != 0)
+                if (can1 != 0)
                 {
                     has = gibbs_mass(rng, mv.erf, mv.erfinv, as, amu, 0.f, mv.maxGibbsMass, true, mv.lambda, &mass);
                 }
@@ -332,7 +370,7 @@ __global__ void __launch_bounds__(kThreads) eval_kernel(const __grid_constant__ 
             {
                 // AsynchronousGibbsSampler::death, :147-180
                 float rebirth = m1;
-                if (mv.otherColNonzero[c1] != 0)
+                if (can1 != 0)
                 {
                     float g;
                     if (gibbs_mass(rng, mv.erf, mv.erfinv, as, amu, 0.f, mv.maxGibbsMass, true, mv.lambda, &g)) { rebirth = g; }
@@ -378,7 +416,7 @@ __global__ void __launch_bounds__(kThreads) eval_kernel(const __grid_constant__ 
             else if (type == 'E')
             {
                 // AsynchronousGibbsSampler::exchange, :200-219; sampleExchange DenseNormalModel.cpp:154-159
-                if (mv.otherColNonzero[c1] != 0 || mv.otherColNonzero[c2] != 0)
+                if (can1 != 0 || can2 != 0)
                 {
                     float g;
                     const bool has = gibbs_mass(rng, mv.erf, mv.erfinv, as, amu, -m1, m2, false, 0.f, &g);
@@ -420,12 +458,17 @@ __global__ void __launch_bounds__(kThreads) eval_kernel(const __grid_constant__ 
             }
             mv.outcomes[pi] = out;
         }
+        // push the decision into every CTA of the cluster (DSMEM stores), so nobody reads our shared
+        // memory after the barrier and no third cluster barrier is needed before exit
         hdr->dec = dec;
+        for (uint32_t q = 1; q < nSeg; ++q) { cluster.map_shared_rank(hdr, q)->dec = dec; }
+        stamp(mv, task, rank, 6); // decision made
     }
-    cluster.sync();
+    if (nSeg > 1) { cluster.sync(); } else { __syncthreads(); }
+    stamp(mv, task, rank, 7); // decision broadcast
 
     // ---- commit: AP[row,:] += delta * other[:,col] (updateAPMatrix, DenseNormalModel.cpp:243-258) ----
-    const Decision dec = *cluster.map_shared_rank(&hdr->dec, 0);
+    const Decision dec = hdr->dec;
     if ((dec.flags & 3u) != 0u && len > 0)
     {
         float *apRow = mv.AP + static_cast<size_t>(row) * mv.ld + segStart;
@@ -469,8 +512,7 @@ __global__ void __launch_bounds__(kThreads) eval_kernel(const __grid_constant__ 
             reinterpret_cast<float4*>(apRow)[j] = a;
         }
     }
-    // keep the leader's shared memory alive until every CTA has read the decision
-    cluster.sync();
+    stamp(mv, task, rank, 8); // commit done
 }
 
 // ------------------------------------------------------------------------------------------------

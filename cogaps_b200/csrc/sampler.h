@@ -101,6 +101,9 @@ struct cgb_sampler
     // bench counters
     cgb_sampler_counters counters;
     bool timeKernels;
+    unsigned long long *dPhaseClocks; // debug phase profile
+    double phaseSum[cgb::kPhaseSlots];
+    uint64_t phaseTasks;
     cudaEvent_t evStart, evStop;
 };
 

@@ -241,8 +241,9 @@ int cgb_sampler_set_kernel_timing(cgb_sampler *s, int32_t enabled);
 /* The device reduction order of the scan, so a checker can reproduce it bit-for-bit:
  * a row of length L is cut into `nSegments` contiguous segments of `segmentLength` floats;
  * within a segment element e belongs to lane ((e / vectorWidth) % threadsPerSegment); lanes
- * sum their elements in increasing index order; 32 consecutive lanes combine by an xor
- * butterfly (offsets 16,8,4,2,1); warp totals, then segment totals, add in increasing order. */
+ * sum their elements in increasing index order; 32 consecutive lanes (a warp) combine by an xor
+ * butterfly (offsets 16,8,4,2,1); the threadsPerSegment/32 warp totals, zero-padded to 32 lanes,
+ * combine by the same butterfly; segment totals add in increasing order. */
 typedef struct cgb_reduction_order
 {
     uint32_t threadsPerSegment;

@@ -754,7 +754,8 @@ static float reduce_terms(const model_t *m, const float *t, uint32_t L, float *s
         float *lanes = scratch;
         for (uint32_t i = 0; i < T; ++i) { lanes[i] = 0.f; }
         for (uint32_t e = 0; e < len; ++e) { lanes[(e / V) % T] += t[base + e]; }
-        float segTotal = 0.f;
+        float wt[32];
+        for (uint32_t i = 0; i < 32; ++i) { wt[i] = 0.f; }
         for (uint32_t w = 0; w < T / 32; ++w)
         {
             float v[32], nv[32];
@@ -764,8 +765,18 @@ static float reduce_terms(const model_t *m, const float *t, uint32_t L, float *s
                 for (uint32_t i = 0; i < 32; ++i) { nv[i] = v[i] + v[i ^ off]; }
                 memcpy(v, nv, sizeof(v));
             }
-            segTotal = (w == 0) ? v[0] : segTotal + v[0];
+            wt[w] = v[0];
         }
+        /* warp totals in the low lanes of one warp (zeros above), same butterfly again */
+        {
+            float nv[32];
+            for (uint32_t off = 16; off >= 1; off >>= 1)
+            {
+                for (uint32_t i = 0; i < 32; ++i) { nv[i] = wt[i] + wt[i ^ off]; }
+                memcpy(wt, nv, sizeof(wt));
+            }
+        }
+        float segTotal = wt[0];
         total = (q == 0) ? segTotal : total + segTotal;
     }
     return total;
