@@ -187,6 +187,8 @@ def main():
               "sampler": "asynchronous, dense normal model, default uncertainty",
               "step": "one MCMC iteration: A.update(Poisson(atomsA)) + P.sync + P.update(Poisson(atomsP)) + A.sync",
               "ramp_iterations": args.ramp,
+              "device_mode": "persistent grid per update(), batches through a pinned-memory mailbox"
+              if os.environ.get("COGAPS_PERSISTENT", "1") != "0" else "one eval-kernel launch per batch",
               "l2": "inputs larger than L2: 1.6 GB of resident D/AP streamed ~40 GB per step, no flush needed",
               "parallelism": "replicas x%d (one independent chain per GPU, no data-path collective)" % world
               if world > 1 else "single chain"}
@@ -265,15 +267,26 @@ def main():
     # ---- roofline pass: per-launch CUDA events on the launching stream (separate from the timed region) ----
     roofline = None
     if rank == 0:
-        chain.A.setKernelTiming(True)
-        chain.P.setKernelTiming(True)
+        # (a) the resident grid's own clock: bytes over the time the device spent on each batch
         chain.A.resetCounters()
         chain.P.resetCounters()
         for _ in range(2):
             chain.step()
+        bA, bP = chain.A.counters(), chain.P.counters()
+        busy = {"GBps": (bA.algorithmicBytes + bP.algorithmicBytes) / max(bA.secondsKernel + bP.secondsKernel, 1e-12) / 1e9,
+                "avg_batch_us": (bA.secondsKernel + bP.secondsKernel) / max(bA.nBatches + bP.nBatches, 1) * 1e6,
+                "how": "globaltimer inside the persistent kernel: batch seen by CTA 0 -> last CTA done"}
+        # (b) the same device code launched once per batch, each launch bracketed by CUDA events on its stream
+        for smp in (chain.A, chain.P):
+            smp.setPersistent(False)
+            smp.setKernelTiming(True)
+            smp.resetCounters()
+        for _ in range(2):
+            chain.step()
         rA, rP = chain.A.counters(), chain.P.counters()
-        chain.A.setKernelTiming(False)
-        chain.P.setKernelTiming(False)
+        for smp in (chain.A, chain.P):
+            smp.setKernelTiming(False)
+            smp.setPersistent(True)
         peak, peak_src = load_peaks()
         bytes_total = rA.algorithmicBytes + rP.algorithmicBytes
         ktime = rA.secondsKernel + rP.secondsKernel
@@ -286,6 +299,8 @@ def main():
         roofline = {"bound": "hbm", "kernel": "eval_kernel (alphaParameters scan + epilogue + AP commit)",
                     "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                     "peak_source": peak_src, "traffic": traffic,
+                    "how": "per-batch launches of eval_kernel, cudaEvent pairs on the launching stream, 2 steps",
+                    "persistent_grid": busy,
                     "algorithmic_bytes_per_launch": bytes_total / max(rA.nBatches + rP.nBatches, 1),
                     "avg_launch_us": ktime / max(rA.nBatches + rP.nBatches, 1) * 1e6,
                     "A_side": {"GBps": rA.algorithmicBytes / max(rA.secondsKernel, 1e-12) / 1e9,

@@ -24,7 +24,7 @@ EXPORTS = [
     "cgb_sampler_update", "cgb_sampler_chisq", "cgb_sampler_n_atoms", "cgb_sampler_data_sparsity",
     "cgb_sampler_average_queue_length", "cgb_sampler_get_matrix", "cgb_sampler_shape", "cgb_sampler_lambda",
     "cgb_sampler_get_atoms", "cgb_sampler_get_ap_row", "cgb_sampler_alpha_parameters",
-    "cgb_sampler_get_counters", "cgb_sampler_reset_counters", "cgb_sampler_set_kernel_timing",
+    "cgb_sampler_get_counters", "cgb_sampler_reset_counters", "cgb_sampler_set_kernel_timing", "cgb_sampler_set_persistent",
     "cgb_sampler_reduction_order", "cgb_reduction_order_for_length", "cgb_stats_create", "cgb_stats_destroy", "cgb_stats_update",
     "cgb_stats_update_a", "cgb_stats_update_p", "cgb_stats_update_pump", "cgb_stats_amean", "cgb_stats_asd",
     "cgb_stats_pmean", "cgb_stats_psd", "cgb_stats_pump_matrix", "cgb_stats_mean_pattern",
@@ -99,6 +99,7 @@ def lib():
     L.cgb_sampler_get_counters.argtypes = [vp, C.POINTER(CgbSamplerCounters)]
     L.cgb_sampler_reset_counters.argtypes = [vp]
     L.cgb_sampler_set_kernel_timing.argtypes = [vp, C.c_int32]
+    L.cgb_sampler_set_persistent.argtypes = [vp, C.c_int32]
     L.cgb_sampler_reduction_order.argtypes = [vp, C.POINTER(CgbReductionOrder)]
     L.cgb_reduction_order_for_length.argtypes = [C.c_uint32, C.POINTER(CgbReductionOrder)]
     L.cgb_stats_create.argtypes = [C.c_uint32, C.c_uint32, C.c_uint32, C.POINTER(vp)]

@@ -279,6 +279,8 @@ extern "C" void cgb_sampler_destroy(cgb_sampler *s)
     cudaSetDevice(s->device);
     cudaFree(s->dD); cudaFree(s->dS); cudaFree(s->dAP); cudaFree(s->dM); cudaFree(s->dColNonzero);
     cudaFree(s->dPartials); cudaFree(s->dTickets); cudaFree(s->dReducePartials); cudaFree(s->dPhaseClocks);
+    if (s->hMailbox) { cudaFreeHost(s->hMailbox); }
+    cudaFree(s->dMailbox);
     if (s->hOutcomes) { cudaFreeHost(s->hOutcomes); }
     if (s->hReducePartials) { cudaFreeHost(s->hReducePartials); }
     if (s->evStart) { cudaEventDestroy(s->evStart); }
@@ -306,6 +308,8 @@ extern "C" int cgb_sampler_create(const float *data, uint32_t nrow, uint32_t nco
     std::memset(static_cast<void*>(&s->counters), 0, sizeof(s->counters));
     s->dD = s->dS = s->dAP = s->dM = nullptr;
     s->dColNonzero = nullptr; s->dPartials = nullptr; s->dTickets = nullptr; s->dReducePartials = nullptr;
+    s->usePersistent = envInt("COGAPS_PERSISTENT", 1) != 0; s->persistentRunning = false;
+    s->hMailbox = nullptr; s->dMailbox = nullptr; s->mailSeq = 0; s->persistentGrid = 0; s->lastPostTime = 0.0;
     s->dPhaseClocks = nullptr; s->phaseTasks = 0;
     for (int i = 0; i < kPhaseSlots; ++i) { s->phaseSum[i] = 0.0; }
     s->hOutcomes = nullptr; s->hReducePartials = nullptr; s->stream = nullptr; s->evStart = s->evStop = nullptr;
@@ -357,21 +361,27 @@ extern "C" int cgb_sampler_create(const float *data, uint32_t nrow, uint32_t nco
         CGB_CUDA_BREAK(cudaMalloc(&s->dAP, matBytes));
         CGB_CUDA_BREAK(cudaMalloc(&s->dM, facBytes));
         CGB_CUDA_BREAK(cudaMalloc(&s->dColNonzero, sizeof(int) * s->k));
-        CGB_CUDA_BREAK(cudaMalloc(&s->dPartials, sizeof(AlphaPair) * 2 * kMaxBatch));
-        CGB_CUDA_BREAK(cudaMalloc(&s->dTickets, sizeof(uint32_t) * kMaxBatch));
+        CGB_CUDA_BREAK(cudaMalloc(&s->dPartials, sizeof(AlphaPair) * 2 * kMaxPersistentBatch));
+        CGB_CUDA_BREAK(cudaMalloc(&s->dTickets, sizeof(uint32_t) * kMaxPersistentBatch));
         CGB_CUDA_BREAK(cudaMalloc(&s->dReducePartials, sizeof(double) * kReduceBlocks));
         CGB_CUDA_BREAK(cudaHostAlloc(&s->hOutcomes, sizeof(DevOutcome) * kMaxBatch, cudaHostAllocMapped));
         CGB_CUDA_BREAK(cudaHostAlloc(&s->hReducePartials, sizeof(double) * kReduceBlocks, cudaHostAllocDefault));
+        CGB_CUDA_BREAK(cudaHostAlloc(&s->hMailbox, sizeof(HostMailbox), cudaHostAllocMapped));
+        CGB_CUDA_BREAK(cudaMalloc(&s->dMailbox, sizeof(DeviceMailbox)));
+        CGB_CUDA_BREAK(cudaMemset(s->dMailbox, 0, sizeof(DeviceMailbox)));
+        std::memset(s->hMailbox, 0, sizeof(HostMailbox));
         CGB_CUDA_BREAK(cudaEventCreate(&s->evStart));
         CGB_CUDA_BREAK(cudaEventCreate(&s->evStop));
         CGB_CUDA_BREAK(cudaMemcpy(s->dD, host.data(), matBytes, cudaMemcpyHostToDevice));
         CGB_CUDA_BREAK(cudaMemset(s->dAP, 0, matBytes));
         CGB_CUDA_BREAK(cudaMemset(s->dM, 0, facBytes));
         CGB_CUDA_BREAK(cudaMemset(s->dColNonzero, 0, sizeof(int) * s->k));
-        CGB_CUDA_BREAK(cudaMemset(s->dTickets, 0, sizeof(uint32_t) * kMaxBatch));
+        CGB_CUDA_BREAK(cudaMemset(s->dTickets, 0, sizeof(uint32_t) * kMaxPersistentBatch));
         CGB_CUDA_BREAK(cudaFuncSetAttribute(eval_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
         CGB_CUDA_BREAK(cudaFuncSetAttribute(eval_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
-        if (s->smemBytes > 227u * 1024u)
+        CGB_CUDA_BREAK(cudaFuncSetAttribute(eval_persistent_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024 - 1024));
+        CGB_CUDA_BREAK(cudaFuncSetAttribute(eval_persistent_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024 - 1024));
+        if (s->smemBytes > 226u * 1024u)
         {
             rc = fail(CGB_EUNSUPPORTED, "row length too large for one cluster of staged segments (raise COGAPS_MAX_CLUSTER)");
             break;
@@ -503,6 +513,11 @@ static void fillModelView(const cgb_sampler *s, ModelView &mv)
     mv.annealingTemp = s->annealingTemp;
 }
 
+static size_t evalSmemBytes(const cgb_sampler *s)
+{
+    return 256 + static_cast<size_t>(s->hasS ? 5 : 4) * s->segPad * sizeof(float);
+}
+
 // launches the eval kernel for params.nProps proposals already written to params.props; blocks until
 // the outcomes are visible in s->hOutcomes
 static int launchEval(cgb_sampler *s, EvalParams &params)
@@ -520,7 +535,7 @@ static int launchEval(cgb_sampler *s, EvalParams &params)
     cfg = cudaLaunchConfig_t();
     cfg.gridDim = dim3(s->nSeg, params.nTasks, 1);
     cfg.blockDim = dim3(kThreads, 1, 1);
-    cfg.dynamicSmemBytes = 256 + static_cast<size_t>(s->hasS ? 5 : 4) * s->segPad * sizeof(float);
+    cfg.dynamicSmemBytes = evalSmemBytes(s);
     cfg.stream = s->stream;
     cudaLaunchAttribute attr[1];
     attr[0].id = cudaLaunchAttributeClusterDimension;
@@ -600,74 +615,270 @@ static double algorithmicBytes(const DevProposal &p, const DevOutcome &o, uint32
     return (p.c1 == p.c2 ? 28.0 : 32.0) * l + (changed ? 8.0 * l : 0.0);
 }
 
+// ------------------------------------------------------------------------------------------------
+// persistent mode: one resident grid per update(), batches through a pinned-memory mailbox
+// ------------------------------------------------------------------------------------------------
+static int startPersistent(cgb_sampler *s)
+{
+    cudaLaunchConfig_t cfg = cudaLaunchConfig_t();
+    cfg.blockDim = dim3(kThreads, 1, 1);
+    cfg.dynamicSmemBytes = evalSmemBytes(s);
+    cfg.stream = s->stream;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = s->nSeg;
+    attr[0].val.clusterDim.y = 1;
+    attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    if (s->persistentGrid == 0)
+    {
+        // every CTA spins on a flag another CTA sets, so the whole grid must be resident at once
+        cfg.gridDim = dim3(s->nSeg, 1, 1);
+        int maxClusters = 0;
+        if (s->hasS) { CGB_CUDA(cudaOccupancyMaxActiveClusters(&maxClusters, eval_persistent_kernel<true>, &cfg)); }
+        else { CGB_CUDA(cudaOccupancyMaxActiveClusters(&maxClusters, eval_persistent_kernel<false>, &cfg)); }
+        if (maxClusters < 1) { return fail(CGB_ECUDA, "persistent kernel: no cluster fits on the device"); }
+        const int cap = envInt("COGAPS_PERSISTENT_CLUSTERS", 0);
+        if (cap > 0 && cap < maxClusters) { maxClusters = cap; }
+        s->persistentGrid = maxClusters * static_cast<int>(s->nSeg);
+    }
+    cfg.gridDim = dim3(s->persistentGrid, 1, 1);
+    HostMailbox *hb = static_cast<HostMailbox*>(s->hMailbox);
+    hb->seq = pack_seq(s->mailSeq, 0, 0); // anything but the next id or the exit code
+    __sync_synchronize();
+    ModelView mv;
+    fillModelView(s, mv);
+    const unsigned long long firstSeq = s->mailSeq + 1;
+    mv.annealingTemp = s->annealingTemp; // constant for the whole update() this grid serves
+    const unsigned long long idleNs = static_cast<unsigned long long>(envInt("COGAPS_PERSISTENT_IDLE_MS", 2000)) * 1000000ull;
+    DeviceMailbox *db = static_cast<DeviceMailbox*>(s->dMailbox);
+    CGB_CUDA(cudaMemsetAsync(db, 0, sizeof(DeviceMailbox), s->stream));
+    if (s->hasS) { CGB_CUDA(cudaLaunchKernelEx(&cfg, eval_persistent_kernel<true>, mv, hb, db, firstSeq, idleNs)); }
+    else { CGB_CUDA(cudaLaunchKernelEx(&cfg, eval_persistent_kernel<false>, mv, hb, db, firstSeq, idleNs)); }
+    ++g_kernelLaunches;
+    s->persistentRunning = true;
+    s->lastPostTime = nowSeconds();
+    return CGB_OK;
+}
+
+static int stopPersistent(cgb_sampler *s)
+{
+    if (!s->persistentRunning) { return CGB_OK; }
+    HostMailbox *hb = static_cast<HostMailbox*>(s->hMailbox);
+    __sync_synchronize();
+    hb->seq = kExitSeq;
+    __sync_synchronize();
+    CGB_CUDA(cudaStreamSynchronize(s->stream));
+    s->persistentRunning = false;
+    unsigned long long busy = 0;
+    CGB_CUDA(cudaMemcpy(&busy, &static_cast<DeviceMailbox*>(s->dMailbox)->busyNs, sizeof(busy), cudaMemcpyDeviceToHost));
+    s->counters.secondsKernel += static_cast<double>(busy) * 1e-9;
+    if (s->dPhaseClocks)
+    {
+        // phase profile of the tasks of the last batch (each task slot holds its latest stamps)
+        std::vector<unsigned long long> h(static_cast<size_t>(2 * kMaxBatch) * kPhaseSlots);
+        CGB_CUDA(cudaMemcpy(h.data(), s->dPhaseClocks, h.size() * sizeof(unsigned long long), cudaMemcpyDeviceToHost));
+        const uint32_t nLast = s->lastPostedTasks;
+        for (uint32_t t = 0; t < nLast && t < 2u * kMaxBatch; ++t)
+        {
+            const unsigned long long *p = h.data() + static_cast<size_t>(t) * kPhaseSlots;
+            if (p[8] <= p[1]) { continue; }
+            for (int i = 2; i < 9; ++i) { s->phaseSum[i] += static_cast<double>(p[i] - p[1]); }
+            s->phaseTasks += 1;
+        }
+    }
+    if (envInt("COGAPS_PERSISTENT_DEBUG", 0))
+    {
+        unsigned long long d[8];
+        CGB_CUDA(cudaMemcpy(d, static_cast<DeviceMailbox*>(s->dMailbox)->dbg, sizeof(d), cudaMemcpyDeviceToHost));
+        const double nb = static_cast<double>(d[4] ? d[4] : 1), nt = static_cast<double>(d[3] ? d[3] : 1);
+        std::printf("[persistent nSeg=%u grid=%d] batches %llu tasks %llu | release->task start %.2f us | task %.2f us = pull %.2f + process %.2f | "
+                    "max release->task end (any batch) %.2f us | busy %.2f us per batch\n",
+                    s->nSeg, s->persistentGrid, d[4], d[3], d[1] / nt * 1e-3, d[2] / nt * 1e-3, d[0] / nt * 1e-3, d[5] / nt * 1e-3,
+                    d[6] * 1e-3, busy / nb * 1e-3);
+    }
+    return CGB_OK;
+}
+
+// posts the batch whose task records 0..n-1 (first rows) are already in the mailbox and waits for the n outcomes
+static int persistentBatch(cgb_sampler *s, uint32_t n)
+{
+    HostMailbox *hb = static_cast<HostMailbox*>(s->hMailbox);
+    const double t0 = nowSeconds();
+    if (s->persistentRunning && t0 - s->lastPostTime > 1.0 && cudaStreamQuery(s->stream) == cudaSuccess)
+    {
+        s->persistentRunning = false; // the grid gave up waiting for us (idle timeout)
+    }
+    if (!s->persistentRunning) { CGB_TRY(startPersistent(s)); }
+    // second rows of two-row moves / exchanges become tasks of their own, after the first rows;
+    // every CTA of a task's cluster reads its own copy of the record (slot task * nSeg + rank)
+    const uint32_t nSeg = s->nSeg;
+    uint32_t nTasks = n;
+    for (uint32_t i = 0; i < n; ++i)
+    {
+        const DevProposal &p = hb->tasks[static_cast<size_t>(i) * nSeg].pr;
+        if ((p.type == 'M' || p.type == 'E') && p.r1 != p.r2)
+        {
+            TaskRecord &t = hb->tasks[static_cast<size_t>(nTasks++) * nSeg];
+            t.pr = p;
+            t.pi = i;
+            t.part = 1;
+        }
+    }
+    if (nSeg > 1)
+    {
+        for (uint32_t t = 0; t < nTasks; ++t)
+        {
+            const TaskRecord &src = hb->tasks[static_cast<size_t>(t) * nSeg];
+            for (uint32_t q = 1; q < nSeg; ++q) { hb->tasks[static_cast<size_t>(t) * nSeg + q] = src; }
+        }
+    }
+    const unsigned long long seq = ++s->mailSeq;
+    __sync_synchronize();
+    hb->seq = pack_seq(seq, n, nTasks);
+    s->lastPostedTasks = nTasks;
+    __sync_synchronize();
+    s->lastPostTime = t0;
+    // spin on the self-validating outcome records
+    const uint32_t want = static_cast<uint32_t>(seq);
+    for (uint32_t i = 0; i < n; ++i)
+    {
+        volatile HostOutcome *o = &hb->outcomes[i];
+        uint64_t spins = 0;
+        for (;;)
+        {
+            const uint32_t w2 = o->seqAndAccepted;
+            if ((w2 >> 1) == (want & 0x7fffffffu))
+            {
+                const uint32_t w0 = o->mass1Bits, w1 = o->mass2Bits, w3 = o->check;
+                if (o->seqAndAccepted == w2 && w3 == outcome_check(w0, w1, w2)) { break; }
+            }
+            __builtin_ia32_pause();
+            if ((++spins & 0xfffff) == 0 && nowSeconds() - t0 > 20.0)
+            {
+                cudaError_t e = cudaStreamQuery(s->stream);
+                s->persistentRunning = false;
+                unsigned long long d[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+                if (e == cudaSuccess) { cudaMemcpy(d, s->dMailbox, sizeof(d), cudaMemcpyDeviceToHost); }
+                const uint32_t *dw = reinterpret_cast<const uint32_t*>(d);
+                return fail(CGB_ECUDA, std::string("persistent eval kernel did not answer within 20 s (stream state: ")
+                    + cudaGetErrorString(e) + "; waiting for outcome " + std::to_string(i) + " of " + std::to_string(n)
+                    + " of batch " + std::to_string(seq) + "; host word " + std::to_string(hb->seq) + "; device word "
+                    + std::to_string(d[0]) + " doneCtas " + std::to_string(dw[2]) + " exitFlag " + std::to_string(dw[3]) + " grid "
+                    + std::to_string(s->persistentGrid) + " nSeg " + std::to_string(s->nSeg) + ")");
+            }
+        }
+    }
+    s->counters.secondsDeviceWait += nowSeconds() - t0;
+    s->counters.nBatches += 1;
+    return CGB_OK;
+}
+
+static void fillProposal(const cgb_sampler *s, const HostProposal &hp, DevProposal &dp)
+{
+    dp.rng = hp.rng.state;
+    dp.r1 = hp.r1; dp.c1 = hp.c1; dp.r2 = hp.r2; dp.c2 = hp.c2;
+    dp.m1 = s->domain.atom(hp.atom1).mass;
+    dp.m2 = (hp.atom2 != kNoAtom) ? s->domain.atom(hp.atom2).mass : 0.f;
+    dp.type = static_cast<uint32_t>(hp.type);
+    dp.variant = 0;
+    dp.ch = 0.f;
+    dp.pad = 0;
+}
+
+// the host-visible half of AsynchronousGibbsSampler::birth/death/move/exchange (:126-219)
+static int applyOutcome(cgb_sampler *s, const HostProposal &hp, const DevProposal &dp, bool accepted, float mass1, float mass2)
+{
+    DevOutcome o;
+    o.accepted = accepted ? 1u : 0u;
+    o.mass1 = mass1;
+    o.mass2 = mass2;
+    s->counters.algorithmicBytes += algorithmicBytes(dp, o, s->L);
+    switch (hp.type)
+    {
+        case 'B':
+            if (accepted)
+            {
+                s->queue.acceptBirth();
+                s->domain.atom(hp.atom1).mass = mass1;
+            }
+            else
+            {
+                s->queue.rejectBirth();
+                s->domain.cacheErase(hp.atom1);
+            }
+            break;
+        case 'D':
+            if (accepted)
+            {
+                s->queue.rejectDeath();
+                s->domain.atom(hp.atom1).mass = mass1;
+            }
+            else
+            {
+                s->queue.acceptDeath();
+                s->domain.cacheErase(hp.atom1);
+            }
+            break;
+        case 'M':
+            if (accepted) { s->domain.move(hp.atom1, hp.pos); }
+            break;
+        case 'E':
+            if (accepted)
+            {
+                s->domain.atom(hp.atom1).mass = mass1;
+                s->domain.atom(hp.atom2).mass = mass2;
+            }
+            break;
+        default: return fail(CGB_EINTERNAL, "applyOutcome: corrupt proposal type");
+    }
+    return CGB_OK;
+}
+
 static int evaluateQueue(cgb_sampler *s)
 {
     std::vector<HostProposal> &q = s->queue.entries();
+    size_t done = 0;
+    if (s->usePersistent)
+    {
+        HostMailbox *hb = static_cast<HostMailbox*>(s->hMailbox);
+        while (done < q.size())
+        {
+            const uint32_t n = static_cast<uint32_t>(std::min<size_t>(kMaxPersistentBatch, q.size() - done));
+            for (uint32_t i = 0; i < n; ++i)
+            {
+                TaskRecord &t = hb->tasks[static_cast<size_t>(i) * s->nSeg];
+                fillProposal(s, q[done + i], t.pr);
+                t.pi = i;
+                t.part = 0;
+            }
+            CGB_TRY(persistentBatch(s, n));
+            for (uint32_t i = 0; i < n; ++i)
+            {
+                const HostOutcome &o = hb->outcomes[i];
+                float m1, m2;
+                std::memcpy(&m1, &o.mass1Bits, 4);
+                std::memcpy(&m2, &o.mass2Bits, 4);
+                CGB_TRY(applyOutcome(s, q[done + i], hb->tasks[static_cast<size_t>(i) * s->nSeg].pr, (o.seqAndAccepted & 1u) != 0u, m1, m2));
+            }
+            s->counters.nProposalsQueued += n;
+            done += n;
+        }
+        return CGB_OK;
+    }
     static thread_local EvalParams params; // ~20 KB of kernel parameters, reused
     fillModelView(s, params.mv);
-    size_t done = 0;
     while (done < q.size())
     {
         const uint32_t n = static_cast<uint32_t>(std::min<size_t>(kMaxBatch, q.size() - done));
-        for (uint32_t i = 0; i < n; ++i)
-        {
-            const HostProposal &hp = q[done + i];
-            DevProposal &dp = params.props[i];
-            dp.rng = hp.rng.state;
-            dp.r1 = hp.r1; dp.c1 = hp.c1; dp.r2 = hp.r2; dp.c2 = hp.c2;
-            dp.m1 = s->domain.atom(hp.atom1).mass;
-            dp.m2 = (hp.atom2 != kNoAtom) ? s->domain.atom(hp.atom2).mass : 0.f;
-            dp.type = static_cast<uint32_t>(hp.type);
-            dp.variant = 0;
-            dp.ch = 0.f;
-            dp.pad = 0;
-        }
+        for (uint32_t i = 0; i < n; ++i) { fillProposal(s, q[done + i], params.props[i]); }
         params.nProps = n;
         CGB_TRY(launchEval(s, params));
-        // apply the outcomes (AsynchronousGibbsSampler.h:126-219, the host-visible half)
         for (uint32_t i = 0; i < n; ++i)
         {
-            const HostProposal &hp = q[done + i];
             const DevOutcome &o = s->hOutcomes[i];
-            s->counters.algorithmicBytes += algorithmicBytes(params.props[i], o, s->L);
-            switch (hp.type)
-            {
-                case 'B':
-                    if (o.accepted)
-                    {
-                        s->queue.acceptBirth();
-                        s->domain.atom(hp.atom1).mass = o.mass1;
-                    }
-                    else
-                    {
-                        s->queue.rejectBirth();
-                        s->domain.cacheErase(hp.atom1);
-                    }
-                    break;
-                case 'D':
-                    if (o.accepted)
-                    {
-                        s->queue.rejectDeath();
-                        s->domain.atom(hp.atom1).mass = o.mass1;
-                    }
-                    else
-                    {
-                        s->queue.acceptDeath();
-                        s->domain.cacheErase(hp.atom1);
-                    }
-                    break;
-                case 'M':
-                    if (o.accepted) { s->domain.move(hp.atom1, hp.pos); }
-                    break;
-                case 'E':
-                    if (o.accepted)
-                    {
-                        s->domain.atom(hp.atom1).mass = o.mass1;
-                        s->domain.atom(hp.atom2).mass = o.mass2;
-                    }
-                    break;
-                default: return fail(CGB_EINTERNAL, "evaluateQueue: corrupt proposal type");
-            }
+            CGB_TRY(applyOutcome(s, q[done + i], params.props[i], o.accepted != 0u, o.mass1, o.mass2));
         }
         s->counters.nProposalsQueued += n;
         done += n;
@@ -696,11 +907,20 @@ extern "C" int cgb_sampler_update(cgb_sampler *s, uint32_t nSteps, uint32_t nThr
         const double t1 = nowSeconds();
         s->counters.secondsHostGenerate += t1 - t0;
         const double waitBefore = s->counters.secondsDeviceWait;
-        if (!s->queue.entries().empty()) { CGB_TRY(evaluateQueue(s)); }
+        if (!s->queue.entries().empty())
+        {
+            const int rcEval = evaluateQueue(s);
+            if (rcEval != CGB_OK)
+            {
+                stopPersistent(s);
+                return rcEval;
+            }
+        }
         s->queue.clear();
         s->domain.flushEraseCache();
         s->counters.secondsHostGenerate += (nowSeconds() - t1) - (s->counters.secondsDeviceWait - waitBefore);
     }
+    CGB_TRY(stopPersistent(s));
     s->counters.nProposalsTotal += nSteps;
     if (s->queue.minAtoms() != s->queue.maxAtoms() || s->queue.maxAtoms() != s->domain.size())
     {
@@ -871,6 +1091,14 @@ extern "C" int cgb_sampler_set_kernel_timing(cgb_sampler *s, int32_t enabled)
 {
     CGB_CHECK(s != nullptr, "cgb_sampler_set_kernel_timing: NULL sampler");
     s->timeKernels = enabled != 0;
+    return CGB_OK;
+}
+
+extern "C" int cgb_sampler_set_persistent(cgb_sampler *s, int32_t enabled)
+{
+    CGB_CHECK(s != nullptr, "cgb_sampler_set_persistent: NULL sampler");
+    CGB_CHECK(!s->persistentRunning, "cgb_sampler_set_persistent: called in the middle of an update");
+    s->usePersistent = enabled != 0;
     return CGB_OK;
 }
 

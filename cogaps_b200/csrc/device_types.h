@@ -10,6 +10,8 @@ static const int kThreads = 256;      // threads per CTA of the eval kernel (8 w
 static const int kVec = 4;            // floats per vector access (16 B)
 static const int kMaxBatch = 384;     // proposals per launch carried in kernel-parameter space
 static const int kMaxCluster = 8;     // portable cluster limit
+static const int kMaxPersistentBatch = 1024; // proposals per batch through the persistent kernel's mailbox
+static const unsigned long long kExitSeq = ~0ull;
 static const int kPhaseSlots = 12;    // debug phase timestamps per task
 static const uint32_t kProbe = 'P';   // lock-step probe pseudo-proposal
 
@@ -51,8 +53,8 @@ struct ModelView
     const float *erf;        // lookup tables
     const float *erfinv;
     DevOutcome *outcomes;    // [kMaxBatch] pinned host memory, written by the kernel
-    AlphaPair *partials;     // [kMaxBatch][2] cross-cluster (s, s_mu) of two-row proposals
-    uint32_t *tickets;       // [kMaxBatch]
+    AlphaPair *partials;     // [kMaxPersistentBatch][2] cross-cluster (s, s_mu) of two-row proposals
+    uint32_t *tickets;       // [kMaxPersistentBatch]
     unsigned long long *phaseClocks; // debug: [kMaxBatch][kPhaseSlots] SM clock at each phase, or nullptr
     uint32_t nRows, L, k;
     uint32_t ld, ldM, ldOther;

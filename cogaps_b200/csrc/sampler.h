@@ -105,6 +105,16 @@ struct cgb_sampler
     double phaseSum[cgb::kPhaseSlots];
     uint64_t phaseTasks;
     cudaEvent_t evStart, evStop;
+
+    // persistent-kernel mode: mailbox between the host generator and the resident grid
+    bool usePersistent;
+    bool persistentRunning;
+    void *hMailbox;               // cgb::HostMailbox, pinned + mapped
+    void *dMailbox;               // cgb::DeviceMailbox
+    unsigned long long mailSeq;   // id of the last batch posted
+    int persistentGrid;
+    double lastPostTime;
+    uint32_t lastPostedTasks;
 };
 
 #endif // CGB_SAMPLER_H

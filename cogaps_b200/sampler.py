@@ -204,6 +204,9 @@ class GibbsSampler(object):
     def setKernelTiming(self, enabled):
         check(lib().cgb_sampler_set_kernel_timing(self._h, int(bool(enabled))))
 
+    def setPersistent(self, enabled):
+        check(lib().cgb_sampler_set_persistent(self._h, int(bool(enabled))))
+
     def reductionOrder(self):
         o = CgbReductionOrder()
         check(lib().cgb_sampler_reduction_order(self._h, C.byref(o)))

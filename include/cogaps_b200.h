@@ -237,6 +237,10 @@ int cgb_sampler_get_counters(const cgb_sampler *s, cgb_sampler_counters *out);
 int cgb_sampler_reset_counters(cgb_sampler *s);
 /* enable CUDA-event timing of every eval-kernel launch (costs a sync each; bench roofline leg) */
 int cgb_sampler_set_kernel_timing(cgb_sampler *s, int32_t enabled);
+/* How update() reaches the device.  1 (default, or COGAPS_PERSISTENT=1): one resident grid per update(),
+ * batches posted through a pinned-memory mailbox (no per-batch launch).  0: one eval-kernel launch per
+ * conflict-free batch.  Both run the same device code and give bit-identical chains. */
+int cgb_sampler_set_persistent(cgb_sampler *s, int32_t enabled);
 
 /* The device reduction order of the scan, so a checker can reproduce it bit-for-bit:
  * a row of length L is cut into `nSegments` contiguous segments of `segmentLength` floats;
