@@ -39,7 +39,7 @@ G, S, K = 20000, 5000, 20
 DATA_SEED = 20260117
 CHAIN_SEED = 42
 RAMP_ITERS = 50          # untimed iterations growing the chain from zero atoms before warm-up
-E2E_ITERS = 20           # iterations per phase of the end-to-end / reference gaps::run call
+E2E_ITERS = 30           # iterations per phase of the end-to-end / reference gaps::run call
 
 
 def make_data(g=G, s=S, k=K, seed=DATA_SEED):

@@ -244,3 +244,21 @@ def test_user_api_mirrors_reference():
         cg.CoGAPS(data, params, notAParameter=1)
     with pytest.raises(ValueError):
         cg.CoGAPS(-data, params)
+
+
+def test_distributed_modes_single_process():
+    """test_top_level.R:84-118 — genome-wide and single-cell distributed CoGAPS return full-size matrices with no
+    NA; here every subset runs on this process's GPU (the multi-rank plumbing is covered over gloo on CPU)."""
+    import cogaps_b200 as cg
+    data = load_data("gist")
+    gw = cg.CogapsParams(nPatterns=3, nIterations=60, seed=42, distributed="genome-wide")
+    res = cg.CoGAPS(data, gw, messages=False, outputFrequency=30)
+    assert res.featureLoadings.shape[0] == 1363 and res.sampleFactors.shape[0] == 9
+    assert res.featureLoadings.shape[1] == res.sampleFactors.shape[1] >= 1
+    assert not np.isnan(res.featureLoadings).any() and not np.isnan(res.sampleFactors).any()
+    assert len(res.metadata["subsets"]) == 4 and res.metadata["meanChiSq"] == 0.0   # fixed-matrix runs report 0
+    sc = cg.CogapsParams(nPatterns=2, nIterations=60, seed=42, distributed="single-cell")
+    sc.setParam("nSets", 2)
+    res = cg.CoGAPS(data, sc, messages=False, outputFrequency=30)
+    assert res.featureLoadings.shape[0] == 1363 and res.sampleFactors.shape[0] == 9
+    assert not np.isnan(res.sampleFactors).any()

@@ -1,0 +1,250 @@
+"""CPU-side tests (no GPU): the C ABI loads and exports what include/cogaps_b200.h declares, the host halves of
+the path (RNG streams, lookup tables, parameter validation) agree with the oracle, compute entry points fail
+loudly without a device, and the multi-process distributed driver works over gloo with world_size 2."""
+import ctypes as C
+import os
+import re
+import socket
+import sys
+
+import numpy as np
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def bits(a):
+    return np.ascontiguousarray(a, dtype=np.float32).view(np.uint32)
+
+
+def has_gpu():
+    try:
+        import torch
+        return torch.cuda.is_available()
+    except Exception:
+        return False
+
+
+def test_library_exports_every_declared_symbol():
+    import cogaps_b200 as cg
+    from cogaps_b200._lib import EXPORTS
+    header = open(os.path.join(ROOT, "include", "cogaps_b200.h")).read()
+    declared = set(re.findall(r"\b(cgb_[a-z0-9_]+)\s*\(", header))
+    assert len(declared) > 50
+    lib = cg.lib()
+    missing = [n for n in sorted(declared) if not hasattr(lib, n)]
+    assert not missing, missing
+    assert declared == set(EXPORTS), declared.symmetric_difference(set(EXPORTS))
+    assert b"sm_100a" in lib.cgb_build_report()
+
+
+def test_struct_layouts_match_the_header():
+    """cgb_params_default fills the ctypes mirror exactly like CgbParams.defaults() (layout + defaults)."""
+    import cogaps_b200 as cg
+    from cogaps_b200._abi import CgbParams
+    p = CgbParams()
+    cg.lib().cgb_params_default(C.byref(p))
+    d = CgbParams.defaults()
+    assert p.struct_size == C.sizeof(CgbParams)
+    for name, _ in CgbParams._fields_:
+        if name in ("subsetIndices", "fixedPatterns"):
+            continue
+        assert getattr(p, name) == getattr(d, name), name
+    # reference defaults, GapsParameters.h:79-114
+    assert (p.nPatterns, p.nIterations, p.outputFrequency, p.asynchronousUpdates) == (3, 1000, 500, 1)
+    assert p.alphaA == pytest.approx(0.01) and p.maxGibbsMassP == 100.0 and p.whichMatrixFixed == ord("N")
+
+
+@pytest.mark.skipif(has_gpu(), reason="checks the no-device error path")
+def test_compute_calls_fail_loudly_without_a_device():
+    import cogaps_b200 as cg
+    with pytest.raises(cg.CogapsError) as e:
+        cg.gaps_run(np.ones((6, 5), np.float32), nPatterns=2, nIterations=2)
+    assert e.value.code == -2          # CGB_ENODEVICE: no silent CPU fallback exists
+    with pytest.raises(cg.CogapsError):
+        cg.GapsStatistics(4, 3, 2)
+
+
+def test_lookup_tables_match_oracle(oracle):
+    """Random.cpp:269-295 — the library's built-in tables are the oracle's, bit for bit."""
+    import cogaps_b200 as cg
+    rs = cg.GapsRandomState(7)
+    for a, b in zip(rs.tables(), oracle.tables()):
+        assert np.array_equal(bits(a), bits(b))
+
+
+@pytest.mark.parametrize("seed", [1, 42, 969, 4294967295])
+def test_host_rng_streams_match_oracle(oracle, seed):
+    """math/Random.cpp:32-200 through cgb_rng_*: seeder, PCG32, inclusive ranges, Poisson, truncated draws."""
+    import cogaps_b200 as cg
+    n = 300
+    rs = cg.GapsRandomState(seed)
+    assert [rs.nextSeed() for _ in range(5)] == oracle.rng_stream(seed, 0, 5).tolist()
+
+    def stream(fn):
+        r = cg.GapsRng(cg.GapsRandomState(seed))
+        return [fn(r) for _ in range(n)]
+    assert stream(lambda r: r.uniform32()) == oracle.rng_stream(seed, 1, n).tolist()
+    assert stream(lambda r: r.uniform32(0, 9)) == oracle.rng_stream(seed, 2, n, a=0, b=9).tolist()
+    assert stream(lambda r: r.uniform32(0, 4000000000)) == oracle.rng_stream(seed, 2, n, a=0, b=4000000000).tolist()
+    big = 18446744073709551600
+    assert stream(lambda r: r.uniform64(1, big)) == oracle.rng_stream(seed, 3, n, a=1, b=big).tolist()
+    u = np.array(stream(lambda r: r.uniform()), np.float32)
+    assert np.array_equal(bits(u), oracle.rng_stream(seed, 4, n).astype(np.uint32))
+    for lam in (0.5, 4.9, 10.0, 3400.0, 215000.0):
+        got = stream(lambda r: r.poisson(lam))
+        assert got == oracle.rng_stream(seed, 5, n, lam=lam).astype(np.int64).tolist()
+    for f in ((0.0, 5.0, 1.2, 0.7), (0.0, 50.0, -3.0, 0.5), (-1.5, 2.5, 0.2, 3.0), (0.0, 50.0, 80.0, 1.0)):
+        got = stream(lambda r: r.truncNormal(*f))
+        want = oracle.rng_stream(seed, 7, n, f=f)
+        for g, w in zip(got, want):
+            if w == 0xFFFFFFFFFFFFFFFF:
+                assert g is None
+            else:
+                assert np.float32(g).view(np.uint32) == np.uint32(w)
+    for f in ((3.0, 1.7), (0.02, 0.4)):
+        got = np.array(stream(lambda r: r.truncGammaUpper(*f)), np.float32)
+        assert np.array_equal(bits(got), oracle.rng_stream(seed, 8, n, f=f + (0, 0)).astype(np.uint32))
+    # exponential uses the portable log: within 1 ulp of the libm-based reference stream
+    got = np.array(stream(lambda r: r.exponential(0.37)), np.float32)
+    want = oracle.rng_stream(seed, 6, n, f=(0.37, 0, 0, 0)).astype(np.uint32).view(np.float32)
+    assert np.all(np.abs(got - want) <= np.abs(want) * 2.0 ** -22)
+
+
+def test_host_portable_log_is_the_oracle_log(oracle):
+    import cogaps_b200 as cg
+    rng = np.random.default_rng(3)
+    for x in np.concatenate([rng.random(3000), [0.0, 1.0, 2.0 ** -149, 0.5]]).astype(np.float32):
+        a, b = cg.lib().cgb_debug_host_logf(float(x)), oracle.portable_logf(x)
+        assert np.float32(a).view(np.uint32) == np.float32(b).view(np.uint32)
+
+
+def test_reduction_order_is_a_function_of_row_length():
+    from cogaps_b200.sampler import reduction_order_for_length
+    t, v, nseg, seg = reduction_order_for_length(5000)
+    assert t % 32 == 0 and v == 4 and seg % 4 == 0 and nseg * seg >= 5000
+    for length in (1, 9, 1363, 5000, 20000, 30000):
+        t, v, nseg, seg = reduction_order_for_length(length)
+        assert nseg * seg >= length and (nseg - 1) * seg < length
+
+
+def test_params_validation_mirrors_reference():
+    """setValidity("CogapsParams"), R/class-CogapsParams.R:126-193"""
+    import cogaps_b200 as cg
+    p = cg.CogapsParams(nPatterns=3)
+    assert (p.nIterations, p.alphaA, p.maxGibbsMassA, p.nSets, p.cut, p.minNS, p.maxNS) == (50000, 0.01, 100.0, 4, 3, 2, 6)
+    for bad in (dict(nPatterns=0), dict(nPatterns=2.5), dict(nPatterns=3, nIterations=0), dict(nPatterns=3, alphaA=0),
+                dict(nPatterns=3, seed=0), dict(nPatterns=3, whichMatrixFixed="Q"),
+                dict(nPatterns=3, whichMatrixFixed="A"), dict(nPatterns=3, subsetDim=1)):
+        with pytest.raises(ValueError):
+            cg.CogapsParams(**bad)
+    with pytest.raises(ValueError):
+        cg.CogapsParams(nPatterns=3, nSets=5)         # "nSets must be set after CogapsParams are intialized"
+    p.setParam("nSets", 6)
+    assert (p.minNS, p.maxNS) == (3, 9)
+    with pytest.raises(ValueError):
+        cg.CogapsParams(nPatterns=3, distributed="single-cell", fixedPatterns=np.ones((4, 3)), whichMatrixFixed="P")
+
+
+# ---------------------------------------------------------------------------------------------
+# distributed driver
+# ---------------------------------------------------------------------------------------------
+def test_create_sets_partitions_like_reference():
+    """R/SubsetData.R:63-75: floor(total/nSets) per set, remainder to the last, sorted, disjoint, complete."""
+    from cogaps_b200.distributed import createSets
+    sets = createSets(103, 4, seed=42)
+    assert [len(s) for s in sets] == [25, 25, 25, 28]
+    allidx = np.concatenate(sets)
+    assert np.array_equal(np.sort(allidx), np.arange(1, 104))
+    assert all(np.all(np.diff(s) > 0) for s in sets)
+    again = createSets(103, 4, seed=42)
+    assert all(np.array_equal(a, b) for a, b in zip(sets, again))
+    with pytest.raises(ValueError):
+        createSets(10, 3, 1, explicitSets=[[1, 2], [3]])
+
+
+def _synthetic_patterns(nSets=4, k=3, length=60, seed=0):
+    rng = np.random.default_rng(seed)
+    base = rng.gamma(2.0, 1.0, (length, k))
+    out = []
+    for _ in range(nSets):
+        perm = rng.permutation(k)
+        out.append((base[:, perm] * rng.uniform(0.5, 2.0, k) + 0.05 * rng.random((length, k))).astype(np.float32))
+    return base, out
+
+
+def test_consensus_recovers_shared_patterns():
+    """patternMatch, R/DistributedCogaps.R:143-177: permuted, rescaled, noisy copies cluster back together."""
+    import cogaps_b200 as cg
+    from cogaps_b200.distributed import findConsensusMatrix
+    base, unmatched = _synthetic_patterns()
+    params = cg.CogapsParams(nPatterns=3, distributed="single-cell")
+    consensus, clusters = findConsensusMatrix(unmatched, params)
+    assert consensus.shape == (60, 3) and len(clusters) == 3 and all(c.shape[1] == 4 for c in clusters)
+    assert np.allclose(consensus.max(axis=0), 1.0)
+    cor = np.abs(np.corrcoef(consensus.T, base.T)[:3, 3:])
+    assert np.all(cor.max(axis=1) > 0.99) and sorted(cor.argmax(axis=1).tolist()) == [0, 1, 2]
+
+
+class _FakeResult(object):
+    def __init__(self, A, P):
+        self.featureLoadings, self.sampleFactors = A, P
+        self.loadingStdDev, self.factorStdDev = 0.1 * A, 0.1 * P
+        self.metadata = dict(meanChiSq=1.5, totalUpdates=10)
+
+
+def _fake_runner(data, params, uncertainty, subset, subsetDim, runKw):
+    """Stands in for a GPU run: the 'factorisation' of a subset is a deterministic function of its indices."""
+    base, _ = _synthetic_patterns(k=params.nPatterns, length=data.shape[0])
+    idx = np.asarray(subset, dtype=np.int64)
+    if params.fixedPatterns is None:
+        A = base[:, ::-1] if int(idx[0]) % 2 else base
+        P = np.outer(idx, np.arange(1, params.nPatterns + 1))
+    else:
+        A = np.asarray(params.fixedPatterns)
+        P = np.outer(idx, np.arange(1, A.shape[1] + 1))
+    return _FakeResult(A.astype(np.float32), P.astype(np.float32))
+
+
+def _run_distributed(world, rank, port, out):
+    import torch.distributed as dist
+    if world > 1:
+        os.environ["MASTER_ADDR"] = "127.0.0.1"
+        os.environ["MASTER_PORT"] = str(port)
+        dist.init_process_group("gloo", rank=rank, world_size=world)
+    sys.path.insert(0, ROOT)
+    import cogaps_b200 as cg
+    from cogaps_b200.distributed import distributedCogaps
+    data = np.ones((60, 103), np.float32)
+    params = cg.CogapsParams(nPatterns=3, distributed="single-cell", seed=42)
+    res = distributedCogaps(data, params, runner=_fake_runner)
+    if rank == 0:
+        np.savez(out, P=res.sampleFactors, Psd=res.factorStdDev, A=res.featureLoadings, chisq=res.metadata["meanChiSq"],
+                 updates=res.metadata["totalUpdates"])
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def _spawn_entry(rank, world, port, out):
+    _run_distributed(world, rank, port, out)
+
+
+def test_distributed_single_cell_world_size_2_gloo(tmp_path):
+    """subsets round-robin over ranks, all-gather of unequal row blocks, rows restored to data
+    order (stitchTogether).  Two gloo processes must reproduce the single-process result exactly."""
+    import torch.multiprocessing as mp
+    single = str(tmp_path / "single.npz")
+    _run_distributed(1, 0, 0, single)
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    port = s.getsockname()[1]
+    s.close()
+    multi = str(tmp_path / "multi.npz")
+    mp.spawn(_spawn_entry, args=(2, port, multi), nprocs=2, join=True)
+    a, b = np.load(single), np.load(multi)
+    for k in ("P", "Psd", "A", "chisq", "updates"):
+        assert np.array_equal(a[k], b[k]), k
+    # every sample's row is the one computed from its own (1-based) index: the partition was undone
+    assert np.array_equal(a["P"][:, 0], np.arange(1, 104, dtype=np.float32))
+    assert a["P"].shape == (103, 3) and a["A"].shape == (60, 3)
+    assert float(a["chisq"]) == pytest.approx(4 * 1.5) and int(a["updates"]) == 40
