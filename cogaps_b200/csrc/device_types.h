@@ -6,7 +6,7 @@
 
 namespace cgb {
 
-static const int kThreads = 256;      // threads per CTA of the eval kernel (8 warps)
+static const int kThreads = 512;      // threads per CTA of the eval kernel (16 warps)
 static const int kVec = 4;            // floats per vector access (16 B)
 static const int kMaxBatch = 384;     // proposals per launch carried in kernel-parameter space
 static const int kMaxCluster = 8;     // portable cluster limit

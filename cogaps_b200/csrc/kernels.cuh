@@ -16,6 +16,7 @@
 #include <cooperative_groups.h>
 #include <cuda_runtime.h>
 
+#include "../../include/cogaps_b200.h"
 #include "device_types.h"
 #include "gaps_math.h"
 
@@ -174,7 +175,7 @@ struct Verdict
 // The serial tail of one proposal: alpha parameters -> gibbsMass / accept test -> deltas
 // (AsynchronousGibbsSampler.h:126-219).  One lane runs it; kept out of line so its registers (f64 log,
 // divisions) do not inflate the allocation of the 255 lanes that only scan.
-__device__ __noinline__ void decide(const ModelView &mv, float T, const DevProposal &pr, uint32_t part, bool twoRow,
+__device__ __noinline__ void decide(const ModelView &mv, const float *erfT, const float *erfinvT, float T, const DevProposal &pr, uint32_t part, bool twoRow,
                                     float s, float mu, float M1, float M2, int can1, int can2, Verdict *v)
 {
     const uint32_t type = pr.type;
@@ -208,7 +209,7 @@ __device__ __noinline__ void decide(const ModelView &mv, float T, const DevPropo
         bool has;
         if (can1 != 0)
         {
-            has = gibbs_mass(rng, mv.erf, mv.erfinv, as, amu, 0.f, mv.maxGibbsMass, true, mv.lambda, &mass);
+            has = gibbs_mass(rng, erfT, erfinvT, as, amu, 0.f, mv.maxGibbsMass, true, mv.lambda, &mass);
         }
         else
         {
@@ -231,7 +232,7 @@ __device__ __noinline__ void decide(const ModelView &mv, float T, const DevPropo
         if (can1 != 0)
         {
             float g;
-            if (gibbs_mass(rng, mv.erf, mv.erfinv, as, amu, 0.f, mv.maxGibbsMass, true, mv.lambda, &g)) { rebirth = g; }
+            if (gibbs_mass(rng, erfT, erfinvT, as, amu, 0.f, mv.maxGibbsMass, true, mv.lambda, &g)) { rebirth = g; }
         }
         const float dLL = fmul(rebirth, fsub(amu, fdiv(fmul(as, rebirth), 2.f)));
         if (portable_logf(rng.uniform()) < dLL)
@@ -277,7 +278,7 @@ __device__ __noinline__ void decide(const ModelView &mv, float T, const DevPropo
         if (can1 != 0 || can2 != 0)
         {
             float g;
-            const bool has = gibbs_mass(rng, mv.erf, mv.erfinv, as, amu, -m1, m2, false, 0.f, &g);
+            const bool has = gibbs_mass(rng, erfT, erfinvT, as, amu, -m1, m2, false, 0.f, &g);
             const float n1 = fadd(m1, g), n2 = fsub(m2, g);
             if (has && n1 > kEpsilon && n2 > kEpsilon)
             {
@@ -322,7 +323,7 @@ __device__ __noinline__ void decide(const ModelView &mv, float T, const DevPropo
 // staging mbarrier (flips every task in the persistent kernel).  Returns true on the lane that owns the
 // proposal's outcome (leader CTA, lane 0, deciding cluster), with the outcome in *outp.
 template <bool HAS_S, bool PERSISTENT>
-__device__ __forceinline__ bool process_task(const ModelView &mv, float annealingTemp, const DevProposal pr, uint32_t pi, uint32_t part,
+__device__ __forceinline__ bool process_task(const ModelView &mv, const float *erfT, const float *erfinvT, float annealingTemp, const DevProposal pr, uint32_t pi, uint32_t part,
                                              uint32_t task, unsigned char *smemRaw, uint32_t parity,
                                              cg::cluster_group &cluster, uint32_t rank, DevOutcome *outp)
 {
@@ -478,7 +479,7 @@ __device__ __forceinline__ bool process_task(const ModelView &mv, float annealin
         v.dec.flags = 0u;
         if (decideHere)
         {
-            decide(mv, annealingTemp, pr, part, twoRow, s, mu, M1, M2, can1, can2, &v);
+            decide(mv, erfT, erfinvT, annealingTemp, pr, part, twoRow, s, mu, M1, M2, can1, can2, &v);
             *outp = v.out;
             owner = true;
         }
@@ -542,7 +543,7 @@ __device__ __forceinline__ bool process_task(const ModelView &mv, float annealin
 
 // One launch per conflict-free batch; proposals travel in kernel-parameter space.
 template <bool HAS_S>
-__global__ void __launch_bounds__(kThreads) eval_kernel(const __grid_constant__ EvalParams P)
+__global__ void __launch_bounds__(kThreads, 2) eval_kernel(const __grid_constant__ EvalParams P)
 {
     extern __shared__ __align__(128) unsigned char smemRaw[];
     EvalSmem *hdr = reinterpret_cast<EvalSmem*>(smemRaw);
@@ -559,7 +560,7 @@ __global__ void __launch_bounds__(kThreads) eval_kernel(const __grid_constant__ 
     __syncthreads();
     DevOutcome out;
     const DevProposal pr = P.props[pi];
-    if (process_task<HAS_S, false>(P.mv, P.mv.annealingTemp, pr, pi, part, task, smemRaw, 0u, cluster, rank, &out))
+    if (process_task<HAS_S, false>(P.mv, P.mv.erf, P.mv.erfinv, P.mv.annealingTemp, pr, pi, part, task, smemRaw, 0u, cluster, rank, &out))
     {
         P.mv.outcomes[pi] = out;
     }
@@ -661,7 +662,7 @@ __device__ __forceinline__ unsigned long long global_timer_ns()
 }
 
 template <bool HAS_S>
-__global__ void __launch_bounds__(kThreads) eval_persistent_kernel(const __grid_constant__ ModelView mv,
+__global__ void __launch_bounds__(kThreads, 2) eval_persistent_kernel(const __grid_constant__ ModelView mv,
                                                                    HostMailbox *hbox, DeviceMailbox *dbox,
                                                                    unsigned long long firstBatch,
                                                                    unsigned long long idleTimeoutNs)
@@ -744,7 +745,7 @@ __global__ void __launch_bounds__(kThreads) eval_persistent_kernel(const __grid_
             const DevProposal pr = sTask.pr;
             const uint32_t pi = sTask.pi, part = sTask.part;
             DevOutcome out;
-            if (process_task<HAS_S, true>(mv, mv.annealingTemp, pr, pi, part, task, smemRaw, parity, cluster, rank, &out))
+            if (process_task<HAS_S, true>(mv, mv.erf, mv.erfinv, mv.annealingTemp, pr, pi, part, task, smemRaw, parity, cluster, rank, &out))
             {
                 // one 16-byte store across PCIe; word 2 carries the batch id, word 3 a checksum of the
                 // other three, so the polling host can tell a complete record from a stale or torn one
