@@ -567,6 +567,12 @@ typedef struct model_s
     float maxGibbsMass, annealingTemp, lambda;
     int reduceMode;
     cgb_reduction_order order;
+    /* SparseNormalModel (gibbs_sampler/SparseNormalModel.h:16-66) */
+    int sparse;
+    float *Mrows;       /* HybridMatrix::mRows: nRows x k row-major, never zeroed below epsilon          */
+                        /* (M above is HybridMatrix::mCols: values below epsilon stored as 0, flag off) */
+    float *Z1, *Z2;     /* k and k x k lookup tables of the other factor (generateLookupTables)        */
+    float beta;
 } model_t;
 
 /* Matrix(const Matrix&, genesInCols, subsetGenes, indices), data_structures/Matrix.cpp:30-69.
@@ -625,11 +631,16 @@ static void model_init(model_t *m, const float *data, uint32_t nrow, uint32_t nc
     m->maxGibbsMass = m->maxGibbsMass / m->lambda;
     m->reduceMode = opt ? opt->reduceMode : ORACLE_REDUCE_SCALAR;
     if (opt) { m->order = isA ? opt->orderA : opt->orderP; }
+    m->sparse = p->useSparseOptimization != 0;
+    m->beta = 100.f;                                         /* SparseNormalModel.h:77 */
+    m->Mrows = (float*)calloc((size_t)m->nRows * m->k, sizeof(float));
+    m->Z1 = (float*)calloc(m->k, sizeof(float));
+    m->Z2 = (float*)calloc((size_t)m->k * m->k, sizeof(float));
 }
 
 static void model_free(model_t *m)
 {
-    free(m->D); free(m->S); free(m->AP); free(m->M);
+    free(m->D); free(m->S); free(m->AP); free(m->M); free(m->Mrows); free(m->Z1); free(m->Z2);
     memset(m, 0, sizeof(*m));
 }
 
@@ -638,6 +649,7 @@ static void model_set_uncertainty(model_t *m, const float *unc, uint32_t nrow, u
                                   int subsetRows, const cgb_params *p)
 {
     uint32_t R, Cc;
+    if (m->sparse) { return; } /* SparseNormalModel::setUncertainty is a nop (SparseNormalModel.h:92-98) */
     free(m->S);
     m->S = load_matrix(unc, nrow, ncol, transpose, subsetRows, p->subsetIndices, p->nSubsetIndices, &R, &Cc);
 }
@@ -647,13 +659,27 @@ static void model_set_matrix(model_t *m, const float *mat)
 {
     for (uint32_t r = 0; r < m->nRows; ++r)
     {
-        for (uint32_t c = 0; c < m->k; ++c) { m->M[(size_t)c * m->nRows + r] = mat[(size_t)r * m->k + c]; }
+        for (uint32_t c = 0; c < m->k; ++c)
+        {
+            float v = mat[(size_t)r * m->k + c];
+            m->Mrows[(size_t)r * m->k + c] = v;
+            /* HybridMatrix::operator=(Matrix): add(-old) then add(new) on the column copy */
+            m->M[(size_t)c * m->nRows + r] = (m->sparse && v < EPSILON) ? 0.f : v;
+        }
     }
 }
 
 /* sync, DenseNormalModel.cpp:20-36: AP <- transpose(other.AP) */
+static void sparse_generate_tables(model_t *m);
+
 static void model_sync(model_t *m, const model_t *o)
 {
+    if (m->sparse)
+    {
+        m->other = o; /* SparseNormalModel::sync, SparseNormalModel.cpp:27-31 */
+        sparse_generate_tables(m);
+        return;
+    }
     for (uint32_t r = 0; r < m->nRows; ++r)
     {
         for (uint32_t l = 0; l < m->L; ++l) { m->AP[(size_t)r * m->L + l] = o->AP[(size_t)l * o->L + r]; }
@@ -664,6 +690,7 @@ static void model_sync(model_t *m, const model_t *o)
 /* extraInitialization, DenseNormalModel.cpp:38-54 */
 static void model_extra_initialization(model_t *m)
 {
+    if (m->sparse) { return; } /* SparseNormalModel.cpp:33-37 */
     const model_t *o = m->other;
     for (uint32_t r = 0; r < m->nRows; ++r)
     {
@@ -680,8 +707,11 @@ static void model_extra_initialization(model_t *m)
 }
 
 /* chiSq, DenseNormalModel.cpp:56-68: outer loop over mDMatrix rows (= scan index), inner over columns */
+static float sparse_chisq(const model_t *m);
+
 static float model_chisq(const model_t *m)
 {
+    if (m->sparse) { return sparse_chisq(m); }
     float chisq = 0.f;
     for (uint32_t l = 0; l < m->L; ++l)
     {
@@ -715,16 +745,16 @@ static int model_can_use_gibbs(const model_t *m, uint32_t col)
 }
 
 /* ---- the association order of the two scan sums ---- */
-static float reduce_terms(const model_t *m, const float *t, uint32_t L, float *scratch)
+static float reduce_terms_mode(int reduceMode, const cgb_reduction_order *o, const float *t, uint32_t L, float *scratch)
 {
-    if (m->reduceMode == ORACLE_REDUCE_SCALAR)
+    if (reduceMode == ORACLE_REDUCE_SCALAR)
     {
         /* math/SIMD.h scalar path: PackedFloat is one float, one running sum from 0 */
         float acc = 0.f;
         for (uint32_t i = 0; i < L; ++i) { acc += t[i]; }
         return acc;
     }
-    if (m->reduceMode == ORACLE_REDUCE_AVX8)
+    if (reduceMode == ORACLE_REDUCE_AVX8)
     {
         /* math/SIMD.h:8-19: 8 lanes, chunk c feeds lane j with element 8c+j; the loop runs over
          * ceil(L/8) chunks and reads the pads (data 0, S 1 -> term +0); scalar() = two hadds then
@@ -744,7 +774,6 @@ static float reduce_terms(const model_t *m, const float *t, uint32_t L, float *s
         return lo + hi;
     }
     /* ORACLE_REDUCE_DEVICE: see cgb_reduction_order in include/cogaps_b200.h */
-    const cgb_reduction_order *o = &m->order;
     uint32_t T = o->threadsPerSegment, V = o->vectorWidth;
     float total = 0.f;
     for (uint32_t q = 0; q < o->nSegments; ++q)
@@ -780,6 +809,11 @@ static float reduce_terms(const model_t *m, const float *t, uint32_t L, float *s
         total = (q == 0) ? segTotal : total + segTotal;
     }
     return total;
+}
+
+static float reduce_terms(const model_t *m, const float *t, uint32_t L, float *scratch)
+{
+    return reduce_terms_mode(m->reduceMode, &m->order, t, L, scratch);
 }
 
 typedef struct { float s, s_mu; } alpha_t;
@@ -820,14 +854,21 @@ static alpha_t model_scan(const model_t *m, uint32_t row, const float *v1, const
 static const float *other_col(const model_t *m, uint32_t c) { return m->other->M + (size_t)c * m->other->nRows; }
 
 /* alphaParameters(row, col), DenseNormalModel.cpp:162-183 */
+static alpha_t sparse_alpha(const model_t *m, uint32_t row, uint32_t col, int withChange, float ch);
+static alpha_t sparse_alpha2(const model_t *m, uint32_t r1, uint32_t c1, uint32_t r2, uint32_t c2);
+static void sparse_change_matrix(model_t *m, uint32_t row, uint32_t col, float delta);
+static void sparse_safely_change_matrix(model_t *m, uint32_t row, uint32_t col, float delta);
+
 static alpha_t model_alpha(const model_t *m, uint32_t row, uint32_t col)
 {
+    if (m->sparse) { return sparse_alpha(m, row, col, 0, 0.f); }
     return model_scan(m, row, other_col(m, col), NULL, 0, 0.f);
 }
 
 /* alphaParameters(r1,c1,r2,c2), DenseNormalModel.cpp:186-214; operator+ AlphaParameters.cpp:11-14 */
 static alpha_t model_alpha2(const model_t *m, uint32_t r1, uint32_t c1, uint32_t r2, uint32_t c2)
 {
+    if (m->sparse) { return sparse_alpha2(m, r1, c1, r2, c2); }
     if (r1 == r2) { return model_scan(m, r1, other_col(m, c1), other_col(m, c2), 0, 0.f); }
     alpha_t a = model_alpha(m, r1, c1);
     alpha_t b = model_alpha(m, r2, c2);
@@ -840,6 +881,7 @@ static alpha_t model_alpha2(const model_t *m, uint32_t r1, uint32_t c1, uint32_t
 /* alphaParametersWithChange, DenseNormalModel.cpp:217-240 */
 static alpha_t model_alpha_with_change(const model_t *m, uint32_t row, uint32_t col, float ch)
 {
+    if (m->sparse) { return sparse_alpha(m, row, col, 1, ch); }
     return model_scan(m, row, other_col(m, col), NULL, 1, ch);
 }
 
@@ -854,16 +896,293 @@ static void model_update_ap(model_t *m, uint32_t row, uint32_t col, float delta)
 /* changeMatrix / safelyChangeMatrix, DenseNormalModel.cpp:110-123 */
 static void model_change_matrix(model_t *m, uint32_t row, uint32_t col, float delta)
 {
+    if (m->sparse) { sparse_change_matrix(m, row, col, delta); return; }
     m->M[(size_t)col * m->nRows + row] += delta;
     model_update_ap(m, row, col, delta);
 }
 
 static void model_safely_change_matrix(model_t *m, uint32_t row, uint32_t col, float delta)
 {
+    if (m->sparse) { sparse_safely_change_matrix(m, row, col, delta); return; }
     float *el = &m->M[(size_t)col * m->nRows + row];
     float newVal = fmaxr(*el + delta, 0.f);
     model_update_ap(m, row, col, newVal - *el);
     *el = newVal;
+}
+
+
+/* ============================ sparse normal model ================================== */
+/* SparseNormalModel (gibbs_sampler/SparseNormalModel.cpp).  The reference walks 64-bit index flags
+ * of the data column and of the factor column (common = d_flags & v_flags) and a packed value
+ * array; here the same elements are visited in the same ascending order by testing D > 0 and the
+ * factor's column copy != 0 (its flag is set exactly when the stored value is non-zero,
+ * data_structures/HybridVector.cpp:55-86). */
+
+/* gaps::dot (math/VectorMath.h:40-98): the 25-case fall-through switch accumulates the chunks in
+ * DESCENDING order when there are at most 25 of them, ascending otherwise */
+static float ref_dot(const float *a, const float *b, uint32_t n, int mode)
+{
+    if (mode == ORACLE_REDUCE_AVX8)
+    {
+        float lane[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+        uint32_t nChunks = 1 + (n - 1) / 8;
+        for (uint32_t q = 0; q < nChunks; ++q)
+        {
+            uint32_t c = (nChunks <= 25) ? nChunks - 1 - q : q;
+            for (uint32_t j = 0; j < 8; ++j)
+            {
+                uint32_t i = c * 8 + j;
+                lane[j] = lane[j] + ((i < n) ? a[i] * b[i] : 0.f);
+            }
+        }
+        float lo = (lane[0] + lane[1]) + (lane[2] + lane[3]);
+        float hi = (lane[4] + lane[5]) + (lane[6] + lane[7]);
+        return lo + hi;
+    }
+    float acc = 0.f;
+    if (mode == ORACLE_REDUCE_SCALAR && n <= 25)
+    {
+        for (uint32_t q = 0; q < n; ++q) { uint32_t i = n - 1 - q; acc = acc + a[i] * b[i]; }
+        return acc;
+    }
+    for (uint32_t i = 0; i < n; ++i) { acc = acc + a[i] * b[i]; }
+    return acc;
+}
+
+/* gaps::dot_diff (math/VectorMath.h:136-154): always ascending */
+static float ref_dot_diff(const float *a, const float *b, const float *c, uint32_t n, int mode)
+{
+    if (mode == ORACLE_REDUCE_AVX8)
+    {
+        float lane[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+        for (uint32_t i0 = 0; i0 < n; i0 += 8)
+        {
+            for (uint32_t j = 0; j < 8; ++j)
+            {
+                uint32_t i = i0 + j;
+                lane[j] += (i < n) ? a[i] * (b[i] - c[i]) : 0.f;
+            }
+        }
+        float lo = (lane[0] + lane[1]) + (lane[2] + lane[3]);
+        float hi = (lane[4] + lane[5]) + (lane[6] + lane[7]);
+        return lo + hi;
+    }
+    float acc = 0.f;
+    for (uint32_t i = 0; i < n; ++i) { acc += a[i] * (b[i] - c[i]); }
+    return acc;
+}
+
+/* the device's association order for the sparse sums: element e of the visited list goes to lane
+ * e % 256, lanes and warps combine by the usual butterflies (one segment) */
+static const cgb_reduction_order SPARSE_ORDER = {256u, 1u, 1u, 0x7fffffffu};
+
+static float sparse_reduce(const model_t *m, const float *t, uint32_t n)
+{
+    float scratch[256];
+    return reduce_terms_mode(ORACLE_REDUCE_DEVICE, &SPARSE_ORDER, t, n, scratch);
+}
+
+static const float *mrow(const model_t *m, uint32_t r) { return m->Mrows + (size_t)r * m->k; }
+
+/* generateLookupTables, SparseNormalModel.cpp:294-311 */
+static void sparse_generate_tables(model_t *m)
+{
+    const model_t *o = m->other;
+    uint32_t k = m->k, n = o->nRows;
+    float *t = (float*)malloc(sizeof(float) * (n + 1));
+    for (uint32_t i = 0; i < k; ++i)
+    {
+        if (m->reduceMode == ORACLE_REDUCE_DEVICE)
+        {
+            for (uint32_t r = 0; r < n; ++r) { float v = mrow(o, r)[i]; t[r] = v * v; }
+            m->Z1[i] = sparse_reduce(m, t, n);
+        }
+        else
+        {
+            m->Z1[i] = 0.f;
+            for (uint32_t r = 0; r < n; ++r) { float v = mrow(o, r)[i]; m->Z1[i] += v * v; }
+        }
+        for (uint32_t j = i; j < k; ++j)
+        {
+            const float *a = o->M + (size_t)i * n, *b = o->M + (size_t)j * n;
+            float d;
+            if (m->reduceMode == ORACLE_REDUCE_DEVICE)
+            {
+                for (uint32_t r = 0; r < n; ++r) { t[r] = a[r] * b[r]; }
+                d = sparse_reduce(m, t, n);
+            }
+            else
+            {
+                d = ref_dot(a, b, n, m->reduceMode);
+            }
+            m->Z2[(size_t)j * k + i] = d;
+            m->Z2[(size_t)i * k + j] = d;
+        }
+    }
+    free(t);
+}
+
+/* alphaParameters(row,col) / alphaParametersWithChange, SparseNormalModel.cpp:153-236 */
+static alpha_t sparse_alpha(const model_t *m, uint32_t row, uint32_t col, int withChange, float ch)
+{
+    const model_t *o = m->other;
+    uint32_t L = m->L, k = m->k;
+    const float *D = m->D + (size_t)row * L;
+    const float *V = o->M + (size_t)col * o->nRows;
+    const float *Z2col = m->Z2 + (size_t)col * k;
+    int dev = m->reduceMode == ORACLE_REDUCE_DEVICE;
+    float s = m->Z1[col];
+    float s_mu = -1.f * ref_dot(mrow(m, row), Z2col, k, m->reduceMode);
+    if (withChange) { s_mu -= ch * m->Z2[(size_t)col * k + col]; }
+    float *ts = NULL, *tm = NULL, *tm2 = NULL;
+    uint32_t n = 0;
+    if (dev)
+    {
+        ts = (float*)malloc(sizeof(float) * 3 * (L + 1));
+        tm = ts + L + 1;
+        tm2 = tm + L + 1;
+    }
+    for (uint32_t l = 0; l < L; ++l)
+    {
+        if (D[l] > 0.f && V[l] != 0.f)
+        {
+            float v_val = V[l], d_val = D[l];
+            float term1 = v_val / d_val;
+            float term2 = v_val - term1 / d_val;
+            float dotv = ref_dot(mrow(m, row), mrow(o, l), k, m->reduceMode);
+            float es = term1 * term1 - v_val * v_val;
+            float em = term1 + term2 * dotv;
+            float em2 = withChange ? term2 * mrow(o, l)[col] * ch : 0.f;
+            if (dev)
+            {
+                ts[n] = es; tm[n] = em; tm2[n] = em2; ++n;
+            }
+            else
+            {
+                s += es;
+                s_mu += em;
+                if (withChange) { s_mu += em2; }
+            }
+        }
+    }
+    if (dev)
+    {
+        /* lane e % 256 adds its elements in order (both s_mu contributions of an element back to back) */
+        float lanesS[256], lanesM[256];
+        for (int i = 0; i < 256; ++i) { lanesS[i] = 0.f; lanesM[i] = 0.f; }
+        for (uint32_t e = 0; e < n; ++e)
+        {
+            lanesS[e % 256] += ts[e];
+            lanesM[e % 256] += tm[e];
+            if (withChange) { lanesM[e % 256] += tm2[e]; }
+        }
+        /* feed the lane totals to the generic butterfly (one element per lane) */
+        s = s + sparse_reduce(m, lanesS, 256);
+        s_mu = s_mu + sparse_reduce(m, lanesM, 256);
+        free(ts);
+    }
+    alpha_t a;
+    a.s = s * m->beta;
+    a.s_mu = s_mu * m->beta;
+    return a;
+}
+
+/* alphaParameters(r1,c1,r2,c2), SparseNormalModel.cpp:239-292 */
+static alpha_t sparse_alpha2(const model_t *m, uint32_t r1, uint32_t c1, uint32_t r2, uint32_t c2)
+{
+    if (r1 != r2)
+    {
+        alpha_t a = sparse_alpha(m, r1, c1, 0, 0.f);
+        alpha_t b = sparse_alpha(m, r2, c2, 0, 0.f);
+        alpha_t r;
+        r.s = a.s + b.s;
+        r.s_mu = a.s_mu - b.s_mu;
+        return r;
+    }
+    const model_t *o = m->other;
+    uint32_t L = m->L, k = m->k;
+    const float *D = m->D + (size_t)r1 * L;
+    const float *V1 = o->M + (size_t)c1 * o->nRows;
+    const float *V2 = o->M + (size_t)c2 * o->nRows;
+    int dev = m->reduceMode == ORACLE_REDUCE_DEVICE;
+    float s = m->Z1[c1] - 2.f * m->Z2[(size_t)c2 * k + c1] + m->Z1[c2];
+    float s_mu = -1.f * ref_dot_diff(mrow(m, r1), m->Z2 + (size_t)c1 * k, m->Z2 + (size_t)c2 * k, k, m->reduceMode);
+    float lanesS[256], lanesM[256];
+    for (int i = 0; i < 256; ++i) { lanesS[i] = 0.f; lanesM[i] = 0.f; }
+    uint32_t n = 0;
+    for (uint32_t l = 0; l < L; ++l)
+    {
+        if (D[l] > 0.f && (V1[l] != 0.f || V2[l] != 0.f))
+        {
+            float d_recip = 1.f / D[l];
+            float term1 = 1.f - d_recip * d_recip;
+            float v_diff = V1[l] - V2[l];
+            float ap = ref_dot(mrow(m, r1), mrow(o, l), k, m->reduceMode);
+            float es = v_diff * v_diff * term1;
+            float em = v_diff * (ap * term1 + d_recip);
+            if (dev)
+            {
+                lanesS[n % 256] += es;
+                lanesM[n % 256] += em;
+                ++n;
+            }
+            else
+            {
+                s -= es;
+                s_mu += em;
+            }
+        }
+    }
+    if (dev)
+    {
+        s = s - sparse_reduce(m, lanesS, 256);
+        s_mu = s_mu + sparse_reduce(m, lanesM, 256);
+    }
+    alpha_t a;
+    a.s = s * m->beta;
+    a.s_mu = s_mu * m->beta;
+    return a;
+}
+
+/* HybridMatrix::add / set (data_structures/HybridMatrix.cpp:25-39, HybridVector.cpp:55-86) */
+static void sparse_change_matrix(model_t *m, uint32_t row, uint32_t col, float delta)
+{
+    m->Mrows[(size_t)row * m->k + col] += delta;
+    float *c = &m->M[(size_t)col * m->nRows + row];
+    if (*c + delta < EPSILON) { *c = 0.f; } else { *c += delta; }
+}
+
+static void sparse_safely_change_matrix(model_t *m, uint32_t row, uint32_t col, float delta)
+{
+    float newVal = fmaxr(m->Mrows[(size_t)row * m->k + col] + delta, 0.f);
+    m->Mrows[(size_t)row * m->k + col] = newVal;
+    m->M[(size_t)col * m->nRows + row] = (newVal < EPSILON) ? 0.f : newVal;
+}
+
+/* chiSq, SparseNormalModel.cpp:39-60 */
+static float sparse_chisq(const model_t *m)
+{
+    const model_t *o = m->other;
+    float chisq = 0.f;
+    for (uint32_t j = 0; j < m->nRows; ++j)
+    {
+        for (uint32_t i = 0; i < m->L; ++i)
+        {
+            float dotv = ref_dot(mrow(m, j), mrow(o, i), m->k, m->reduceMode);
+            chisq += dotv * dotv;
+        }
+        for (uint32_t i = 0; i < m->L; ++i)
+        {
+            float d = m->D[(size_t)j * m->L + i];
+            if (d > 0.f)
+            {
+                float dotv = ref_dot(mrow(m, j), mrow(o, i), m->k, m->reduceMode);
+                float dsq = d * d;
+                chisq += 1 + dotv * (dotv - 2 * d - dsq * dotv) / dsq;
+            }
+        }
+    }
+    return chisq * m->beta;
 }
 
 /* gibbsMass, gibbs_sampler/AlphaParameters.cpp:27-48 */
@@ -1664,7 +1983,7 @@ static void snapshot(const model_t *m, float *dst)
     if (!dst) { return; }
     for (uint32_t r = 0; r < m->nRows; ++r)
     {
-        for (uint32_t c = 0; c < m->k; ++c) { dst[(size_t)r * m->k + c] = m->M[(size_t)c * m->nRows + r]; }
+        for (uint32_t c = 0; c < m->k; ++c) { dst[(size_t)r * m->k + c] = m->sparse ? m->Mrows[(size_t)r * m->k + c] : m->M[(size_t)c * m->nRows + r]; }
     }
 }
 
@@ -1673,7 +1992,6 @@ int cogaps_oracle_run_trace(const float *data, uint32_t nrow, uint32_t ncol, con
                             const cgb_params *p, cgb_result *r, const oracle_options *opt,
                             oracle_trace_record *traceBuf, uint64_t capacity, uint64_t *count)
 {
-    if (p->useSparseOptimization) { return CGB_EUNSUPPORTED; }
     randstate_t *rs = (randstate_t*)malloc(sizeof(randstate_t));
     randstate_init(rs, p->seed, opt);
     trace_t trace;

@@ -20,7 +20,19 @@ def synthetic(spec):
     return d.astype(np.float32)
 
 
+def synthetic_sparse(spec):
+    """'spz:G:S:k:seed:zeroPercent' -> the synthetic recipe with a fraction of entries zeroed uniformly at
+    random (single-cell-like matrices for the sparse model)."""
+    _, g, s, k, seed, z = spec.split(":")
+    d = synthetic("syn:%s:%s:%s:%s" % (g, s, k, seed))
+    rng = np.random.default_rng(int(seed) + 1)
+    d[rng.random(d.shape) < int(z) / 100.0] = 0
+    return d
+
+
 def load_data(name):
+    if name.startswith("spz:"):
+        return synthetic_sparse(name)
     if name.startswith("syn:"):
         return synthetic(name)
     return np.load(os.path.join(GOLDEN, name + ".npy"))
@@ -53,6 +65,17 @@ RUN_CASES = {
                                                       subsetIndices=[9, 2, 4, 5, 7])),
     # a shape where both row lengths exceed one SIMD/warp width and are not multiples of 8
     "syn_203x117": dict(data="syn:203:117:5:11", params=P(nPatterns=5, nIterations=60, seed=123)),
+    # SparseNormalModel (sparseOptimization=TRUE; test_seed_consistency.R:55-69 runs the same checks on it)
+    "sparse_gist": dict(data="gist", params=P(nPatterns=7, nIterations=100, outputFrequency=10, useSparseOptimization=1)),
+    "sparse_modsim": dict(data="modsim", params=P(nIterations=300, outputFrequency=50, useSparseOptimization=1,
+                                                   snapshotFrequency=100)),
+    "sparse_120x90": dict(data="spz:120:90:4:3:80", params=P(nPatterns=4, nIterations=80, seed=7, useSparseOptimization=1)),
+    # k > 25: gaps::dot leaves its fall-through switch and accumulates forwards (VectorMath.h:40-98)
+    "sparse_k30": dict(data="spz:60:200:5:9:90", params=P(nPatterns=30, nIterations=40, seed=9, useSparseOptimization=1)),
+    "sparse_gist_seq": dict(data="gist", params=P(nPatterns=5, nIterations=50, useSparseOptimization=1,
+                                                  asynchronousUpdates=0)),
+    "sparse_gist_fixedP": dict(data="gist", params=P(nPatterns=3, nIterations=60, whichMatrixFixed="P",
+                                                     useSparseOptimization=1), fixed=True),
     "syn_sparse": dict(data="syn:90:70:4:5", params=P(nPatterns=4, nIterations=80, seed=9, alphaA=0.05, alphaP=0.02,
                                                       maxGibbsMassA=50.0, maxGibbsMassP=75.0)),
 }

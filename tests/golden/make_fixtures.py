@@ -19,7 +19,7 @@ ROOT = os.path.dirname(os.path.dirname(HERE))
 sys.path.insert(0, ROOT)
 REF = os.environ.get("COGAPS_REFERENCE", "/root/reference")
 
-from tests.cases import RUN_CASES, synthetic  # noqa: E402
+from tests.cases import RUN_CASES, load_data  # noqa: E402
 
 
 def read_modsim():
@@ -58,7 +58,7 @@ def main():
         out["%s/tables/erfinv" % variant] = erfinv
         out["%s/tables/qgamma" % variant] = qgamma
         for name, case in RUN_CASES.items():
-            data = datasets[case["data"]] if case["data"] in datasets else synthetic(case["data"])
+            data = datasets[case["data"]] if case["data"] in datasets else load_data(case["data"])
             kw = dict(case["params"])
             unc = None
             if case.get("uncertainty"):
