@@ -187,7 +187,7 @@ def main():
               "sampler": "asynchronous, dense normal model, default uncertainty",
               "step": "one MCMC iteration: A.update(Poisson(atomsA)) + P.sync + P.update(Poisson(atomsP)) + A.sync",
               "ramp_iterations": args.ramp,
-              "device_mode": "persistent grid per update(), batches through a pinned-memory mailbox"
+              "device_mode": "resident grid per update(); each proposal streamed to its cluster through pinned host memory as it is generated; per-row commit versions instead of grid barriers"
               if os.environ.get("COGAPS_PERSISTENT", "1") != "0" else "one eval-kernel launch per batch",
               "l2": "inputs larger than L2: 1.6 GB of resident D/AP streamed ~40 GB per step, no flush needed",
               "parallelism": "replicas x%d (one independent chain per GPU, no data-path collective)" % world
@@ -275,7 +275,7 @@ def main():
         bA, bP = chain.A.counters(), chain.P.counters()
         busy = {"GBps": (bA.algorithmicBytes + bP.algorithmicBytes) / max(bA.secondsKernel + bP.secondsKernel, 1e-12) / 1e9,
                 "avg_batch_us": (bA.secondsKernel + bP.secondsKernel) / max(bA.nBatches + bP.nBatches, 1) * 1e6,
-                "how": "globaltimer inside the persistent kernel: batch seen by CTA 0 -> last CTA done"}
+                "how": "resident kernel, whole launch (one per update()) timed with CUDA events on its stream: includes the time the grid waits for the host generator"}
         # (b) the same device code launched once per batch, each launch bracketed by CUDA events on its stream
         for smp in (chain.A, chain.P):
             smp.setPersistent(False)

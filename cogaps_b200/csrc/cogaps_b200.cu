@@ -6,6 +6,7 @@
 #include "sampler.h"
 
 #include <chrono>
+#include <emmintrin.h>
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
@@ -51,6 +52,13 @@ static int fail(int code, const std::string &msg)
         int rc__ = (expr);                 \
         if (rc__ != CGB_OK) { return rc__; } \
     } while (0)
+
+// optional host-side split of update() (COGAPS_HOST_PROFILE=1): TSC ticks in posting, applying, flushing
+static int g_hostProfile = -1;   // env value; g_prof is set for the sampled batches only (every 16th)
+static bool g_prof = false;
+static unsigned long long g_profBatches = 0, g_profCounter = 0, g_tscWaitTail = 0;
+static unsigned long long g_tscPost = 0, g_tscApply = 0, g_tscFlush = 0, g_tscPopulate = 0, g_nPosts = 0;
+static inline unsigned long long tsc() { return __builtin_ia32_rdtsc(); }
 
 static inline double nowSeconds()
 {
@@ -279,8 +287,10 @@ extern "C" void cgb_sampler_destroy(cgb_sampler *s)
     cudaSetDevice(s->device);
     cudaFree(s->dD); cudaFree(s->dS); cudaFree(s->dAP); cudaFree(s->dM); cudaFree(s->dColNonzero);
     cudaFree(s->dPartials); cudaFree(s->dTickets); cudaFree(s->dReducePartials); cudaFree(s->dPhaseClocks);
-    if (s->hMailbox) { cudaFreeHost(s->hMailbox); }
-    cudaFree(s->dMailbox);
+    cudaFree(s->dRowVersion); cudaFree(s->dStreamStats);
+    if (s->hCommitsMirror) { cudaFreeHost(const_cast<unsigned long long*>(s->hCommitsMirror)); }
+    if (s->hSlots) { cudaFreeHost(s->hSlots); }
+    if (s->hStreamOutcomes) { cudaFreeHost(s->hStreamOutcomes); }
     if (s->hOutcomes) { cudaFreeHost(s->hOutcomes); }
     if (s->hReducePartials) { cudaFreeHost(s->hReducePartials); }
     if (s->evStart) { cudaEventDestroy(s->evStart); }
@@ -290,6 +300,8 @@ extern "C" void cgb_sampler_destroy(cgb_sampler *s)
 }
 
 static const int kReduceBlocks = 592; // 148 SMs x 4
+// erf + erfinv tables the resident kernel keeps in shared memory behind the staging buffers
+static const size_t kStreamTableBytes = (((CGB_ERF_TABLE_SIZE + 3) & ~3) + ((CGB_ERFINV_TABLE_SIZE + 3) & ~3)) * sizeof(float);
 
 extern "C" int cgb_sampler_create(const float *data, uint32_t nrow, uint32_t ncol, int32_t colmajor,
                                   int32_t transpose, int32_t subsetRows, float alpha, float maxGibbsMass,
@@ -309,7 +321,10 @@ extern "C" int cgb_sampler_create(const float *data, uint32_t nrow, uint32_t nco
     s->dD = s->dS = s->dAP = s->dM = nullptr;
     s->dColNonzero = nullptr; s->dPartials = nullptr; s->dTickets = nullptr; s->dReducePartials = nullptr;
     s->usePersistent = envInt("COGAPS_PERSISTENT", 1) != 0; s->persistentRunning = false;
-    s->hMailbox = nullptr; s->dMailbox = nullptr; s->mailSeq = 0; s->persistentGrid = 0; s->lastPostTime = 0.0;
+    s->hSlots = nullptr; s->nSlotRecords = 0; s->hStreamOutcomes = nullptr; s->dStreamStats = nullptr; s->dRowVersion = nullptr;
+    s->mailSeq = 0; s->streamSerial = 0; s->persistentGrid = 0; s->nClusters = 0; s->lastPostTime = 0.0;
+    s->chunkTag = 0; s->chunkPosted = 0; s->chunkBase = 0;
+    s->hCommitsMirror = nullptr; s->commitsExpected = 0; s->commitsProven = 0;
     s->dPhaseClocks = nullptr; s->phaseTasks = 0;
     for (int i = 0; i < kPhaseSlots; ++i) { s->phaseSum[i] = 0.0; }
     s->hOutcomes = nullptr; s->hReducePartials = nullptr; s->stream = nullptr; s->evStart = s->evStop = nullptr;
@@ -366,10 +381,19 @@ extern "C" int cgb_sampler_create(const float *data, uint32_t nrow, uint32_t nco
         CGB_CUDA_BREAK(cudaMalloc(&s->dReducePartials, sizeof(double) * kReduceBlocks));
         CGB_CUDA_BREAK(cudaHostAlloc(&s->hOutcomes, sizeof(DevOutcome) * kMaxBatch, cudaHostAllocMapped));
         CGB_CUDA_BREAK(cudaHostAlloc(&s->hReducePartials, sizeof(double) * kReduceBlocks, cudaHostAllocDefault));
-        CGB_CUDA_BREAK(cudaHostAlloc(&s->hMailbox, sizeof(HostMailbox), cudaHostAllocMapped));
-        CGB_CUDA_BREAK(cudaMalloc(&s->dMailbox, sizeof(DeviceMailbox)));
-        CGB_CUDA_BREAK(cudaMemset(s->dMailbox, 0, sizeof(DeviceMailbox)));
-        std::memset(s->hMailbox, 0, sizeof(HostMailbox));
+        CGB_CUDA_BREAK(cudaHostAlloc(&s->hStreamOutcomes, sizeof(HostOutcome) * kMaxPersistentBatch, cudaHostAllocMapped));
+        std::memset(s->hStreamOutcomes, 0, sizeof(HostOutcome) * kMaxPersistentBatch);
+        CGB_CUDA_BREAK(cudaMalloc(&s->dStreamStats, sizeof(StreamStats)));
+        CGB_CUDA_BREAK(cudaMalloc(&s->dRowVersion, sizeof(uint32_t) * s->nRows));
+        CGB_CUDA_BREAK(cudaMemset(s->dRowVersion, 0, sizeof(uint32_t) * s->nRows));
+        s->rowVersion.assign(s->nRows, 0u);
+        s->rowPending.assign(s->nRows, 0ull);
+        {
+            void *mirror = nullptr;
+            CGB_CUDA_BREAK(cudaHostAlloc(&mirror, 64, cudaHostAllocMapped));
+            std::memset(mirror, 0, 64);
+            s->hCommitsMirror = static_cast<volatile unsigned long long*>(mirror);
+        }
         CGB_CUDA_BREAK(cudaEventCreate(&s->evStart));
         CGB_CUDA_BREAK(cudaEventCreate(&s->evStop));
         CGB_CUDA_BREAK(cudaMemcpy(s->dD, host.data(), matBytes, cudaMemcpyHostToDevice));
@@ -379,9 +403,9 @@ extern "C" int cgb_sampler_create(const float *data, uint32_t nrow, uint32_t nco
         CGB_CUDA_BREAK(cudaMemset(s->dTickets, 0, sizeof(uint32_t) * kMaxPersistentBatch));
         CGB_CUDA_BREAK(cudaFuncSetAttribute(eval_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
         CGB_CUDA_BREAK(cudaFuncSetAttribute(eval_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
-        CGB_CUDA_BREAK(cudaFuncSetAttribute(eval_persistent_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024 - 1024));
-        CGB_CUDA_BREAK(cudaFuncSetAttribute(eval_persistent_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024 - 1024));
-        if (s->smemBytes > 226u * 1024u)
+        CGB_CUDA_BREAK(cudaFuncSetAttribute(eval_stream_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024 - 1024));
+        CGB_CUDA_BREAK(cudaFuncSetAttribute(eval_stream_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024 - 1024));
+        if (s->smemBytes + kStreamTableBytes > 226u * 1024u)
         {
             rc = fail(CGB_EUNSUPPORTED, "row length too large for one cluster of staged segments (raise COGAPS_MAX_CLUSTER)");
             break;
@@ -499,6 +523,7 @@ static void fillModelView(const cgb_sampler *s, ModelView &mv)
     mv.partials = s->dPartials;
     mv.tickets = s->dTickets;
     mv.phaseClocks = s->dPhaseClocks;
+    mv.rowVersion = s->dRowVersion;
     mv.nRows = s->nRows;
     mv.L = s->L;
     mv.k = s->k;
@@ -616,165 +641,8 @@ static double algorithmicBytes(const DevProposal &p, const DevOutcome &o, uint32
 }
 
 // ------------------------------------------------------------------------------------------------
-// persistent mode: one resident grid per update(), batches through a pinned-memory mailbox
+// host <-> device proposal traffic
 // ------------------------------------------------------------------------------------------------
-static int startPersistent(cgb_sampler *s)
-{
-    cudaLaunchConfig_t cfg = cudaLaunchConfig_t();
-    cfg.blockDim = dim3(kThreads, 1, 1);
-    cfg.dynamicSmemBytes = evalSmemBytes(s);
-    cfg.stream = s->stream;
-    cudaLaunchAttribute attr[1];
-    attr[0].id = cudaLaunchAttributeClusterDimension;
-    attr[0].val.clusterDim.x = s->nSeg;
-    attr[0].val.clusterDim.y = 1;
-    attr[0].val.clusterDim.z = 1;
-    cfg.attrs = attr;
-    cfg.numAttrs = 1;
-    if (s->persistentGrid == 0)
-    {
-        // every CTA spins on a flag another CTA sets, so the whole grid must be resident at once
-        cfg.gridDim = dim3(s->nSeg, 1, 1);
-        int maxClusters = 0;
-        if (s->hasS) { CGB_CUDA(cudaOccupancyMaxActiveClusters(&maxClusters, eval_persistent_kernel<true>, &cfg)); }
-        else { CGB_CUDA(cudaOccupancyMaxActiveClusters(&maxClusters, eval_persistent_kernel<false>, &cfg)); }
-        if (maxClusters < 1) { return fail(CGB_ECUDA, "persistent kernel: no cluster fits on the device"); }
-        const int cap = envInt("COGAPS_PERSISTENT_CLUSTERS", 0);
-        if (cap > 0 && cap < maxClusters) { maxClusters = cap; }
-        s->persistentGrid = maxClusters * static_cast<int>(s->nSeg);
-    }
-    cfg.gridDim = dim3(s->persistentGrid, 1, 1);
-    HostMailbox *hb = static_cast<HostMailbox*>(s->hMailbox);
-    hb->seq = pack_seq(s->mailSeq, 0, 0); // anything but the next id or the exit code
-    __sync_synchronize();
-    ModelView mv;
-    fillModelView(s, mv);
-    const unsigned long long firstSeq = s->mailSeq + 1;
-    mv.annealingTemp = s->annealingTemp; // constant for the whole update() this grid serves
-    const unsigned long long idleNs = static_cast<unsigned long long>(envInt("COGAPS_PERSISTENT_IDLE_MS", 2000)) * 1000000ull;
-    DeviceMailbox *db = static_cast<DeviceMailbox*>(s->dMailbox);
-    CGB_CUDA(cudaMemsetAsync(db, 0, sizeof(DeviceMailbox), s->stream));
-    if (s->hasS) { CGB_CUDA(cudaLaunchKernelEx(&cfg, eval_persistent_kernel<true>, mv, hb, db, firstSeq, idleNs)); }
-    else { CGB_CUDA(cudaLaunchKernelEx(&cfg, eval_persistent_kernel<false>, mv, hb, db, firstSeq, idleNs)); }
-    ++g_kernelLaunches;
-    s->persistentRunning = true;
-    s->lastPostTime = nowSeconds();
-    return CGB_OK;
-}
-
-static int stopPersistent(cgb_sampler *s)
-{
-    if (!s->persistentRunning) { return CGB_OK; }
-    HostMailbox *hb = static_cast<HostMailbox*>(s->hMailbox);
-    __sync_synchronize();
-    hb->seq = kExitSeq;
-    __sync_synchronize();
-    CGB_CUDA(cudaStreamSynchronize(s->stream));
-    s->persistentRunning = false;
-    unsigned long long busy = 0;
-    CGB_CUDA(cudaMemcpy(&busy, &static_cast<DeviceMailbox*>(s->dMailbox)->busyNs, sizeof(busy), cudaMemcpyDeviceToHost));
-    s->counters.secondsKernel += static_cast<double>(busy) * 1e-9;
-    if (s->dPhaseClocks)
-    {
-        // phase profile of the tasks of the last batch (each task slot holds its latest stamps)
-        std::vector<unsigned long long> h(static_cast<size_t>(2 * kMaxBatch) * kPhaseSlots);
-        CGB_CUDA(cudaMemcpy(h.data(), s->dPhaseClocks, h.size() * sizeof(unsigned long long), cudaMemcpyDeviceToHost));
-        const uint32_t nLast = s->lastPostedTasks;
-        for (uint32_t t = 0; t < nLast && t < 2u * kMaxBatch; ++t)
-        {
-            const unsigned long long *p = h.data() + static_cast<size_t>(t) * kPhaseSlots;
-            if (p[8] <= p[1]) { continue; }
-            for (int i = 2; i < 9; ++i) { s->phaseSum[i] += static_cast<double>(p[i] - p[1]); }
-            s->phaseTasks += 1;
-        }
-    }
-    if (envInt("COGAPS_PERSISTENT_DEBUG", 0))
-    {
-        unsigned long long d[8];
-        CGB_CUDA(cudaMemcpy(d, static_cast<DeviceMailbox*>(s->dMailbox)->dbg, sizeof(d), cudaMemcpyDeviceToHost));
-        const double nb = static_cast<double>(d[4] ? d[4] : 1), nt = static_cast<double>(d[3] ? d[3] : 1);
-        std::printf("[persistent nSeg=%u grid=%d] batches %llu tasks %llu | release->task start %.2f us | task %.2f us = pull %.2f + process %.2f | "
-                    "max release->task end (any batch) %.2f us | busy %.2f us per batch\n",
-                    s->nSeg, s->persistentGrid, d[4], d[3], d[1] / nt * 1e-3, d[2] / nt * 1e-3, d[0] / nt * 1e-3, d[5] / nt * 1e-3,
-                    d[6] * 1e-3, busy / nb * 1e-3);
-    }
-    return CGB_OK;
-}
-
-// posts the batch whose task records 0..n-1 (first rows) are already in the mailbox and waits for the n outcomes
-static int persistentBatch(cgb_sampler *s, uint32_t n)
-{
-    HostMailbox *hb = static_cast<HostMailbox*>(s->hMailbox);
-    const double t0 = nowSeconds();
-    if (s->persistentRunning && t0 - s->lastPostTime > 1.0 && cudaStreamQuery(s->stream) == cudaSuccess)
-    {
-        s->persistentRunning = false; // the grid gave up waiting for us (idle timeout)
-    }
-    if (!s->persistentRunning) { CGB_TRY(startPersistent(s)); }
-    // second rows of two-row moves / exchanges become tasks of their own, after the first rows;
-    // every CTA of a task's cluster reads its own copy of the record (slot task * nSeg + rank)
-    const uint32_t nSeg = s->nSeg;
-    uint32_t nTasks = n;
-    for (uint32_t i = 0; i < n; ++i)
-    {
-        const DevProposal &p = hb->tasks[static_cast<size_t>(i) * nSeg].pr;
-        if ((p.type == 'M' || p.type == 'E') && p.r1 != p.r2)
-        {
-            TaskRecord &t = hb->tasks[static_cast<size_t>(nTasks++) * nSeg];
-            t.pr = p;
-            t.pi = i;
-            t.part = 1;
-        }
-    }
-    if (nSeg > 1)
-    {
-        for (uint32_t t = 0; t < nTasks; ++t)
-        {
-            const TaskRecord &src = hb->tasks[static_cast<size_t>(t) * nSeg];
-            for (uint32_t q = 1; q < nSeg; ++q) { hb->tasks[static_cast<size_t>(t) * nSeg + q] = src; }
-        }
-    }
-    const unsigned long long seq = ++s->mailSeq;
-    __sync_synchronize();
-    hb->seq = pack_seq(seq, n, nTasks);
-    s->lastPostedTasks = nTasks;
-    __sync_synchronize();
-    s->lastPostTime = t0;
-    // spin on the self-validating outcome records
-    const uint32_t want = static_cast<uint32_t>(seq);
-    for (uint32_t i = 0; i < n; ++i)
-    {
-        volatile HostOutcome *o = &hb->outcomes[i];
-        uint64_t spins = 0;
-        for (;;)
-        {
-            const uint32_t w2 = o->seqAndAccepted;
-            if ((w2 >> 1) == (want & 0x7fffffffu))
-            {
-                const uint32_t w0 = o->mass1Bits, w1 = o->mass2Bits, w3 = o->check;
-                if (o->seqAndAccepted == w2 && w3 == outcome_check(w0, w1, w2)) { break; }
-            }
-            __builtin_ia32_pause();
-            if ((++spins & 0xfffff) == 0 && nowSeconds() - t0 > 20.0)
-            {
-                cudaError_t e = cudaStreamQuery(s->stream);
-                s->persistentRunning = false;
-                unsigned long long d[8] = {0, 0, 0, 0, 0, 0, 0, 0};
-                if (e == cudaSuccess) { cudaMemcpy(d, s->dMailbox, sizeof(d), cudaMemcpyDeviceToHost); }
-                const uint32_t *dw = reinterpret_cast<const uint32_t*>(d);
-                return fail(CGB_ECUDA, std::string("persistent eval kernel did not answer within 20 s (stream state: ")
-                    + cudaGetErrorString(e) + "; waiting for outcome " + std::to_string(i) + " of " + std::to_string(n)
-                    + " of batch " + std::to_string(seq) + "; host word " + std::to_string(hb->seq) + "; device word "
-                    + std::to_string(d[0]) + " doneCtas " + std::to_string(dw[2]) + " exitFlag " + std::to_string(dw[3]) + " grid "
-                    + std::to_string(s->persistentGrid) + " nSeg " + std::to_string(s->nSeg) + ")");
-            }
-        }
-    }
-    s->counters.secondsDeviceWait += nowSeconds() - t0;
-    s->counters.nBatches += 1;
-    return CGB_OK;
-}
-
 static void fillProposal(const cgb_sampler *s, const HostProposal &hp, DevProposal &dp)
 {
     dp.rng = hp.rng.state;
@@ -787,14 +655,23 @@ static void fillProposal(const cgb_sampler *s, const HostProposal &hp, DevPropos
     dp.pad = 0;
 }
 
+static inline bool isTwoRow(const DevProposal &p)
+{
+    return (p.type == 'M' || p.type == 'E') && p.r1 != p.r2;
+}
+
 // the host-visible half of AsynchronousGibbsSampler::birth/death/move/exchange (:126-219)
-static int applyOutcome(cgb_sampler *s, const HostProposal &hp, const DevProposal &dp, bool accepted, float mass1, float mass2)
+// `resident`: the commit is made by the resident grid (no kernel boundary orders it before the next batch)
+static int applyOutcome(cgb_sampler *s, const HostProposal &hp, const DevProposal &dp, bool resident, bool accepted, float mass1, float mass2)
 {
     DevOutcome o;
     o.accepted = accepted ? 1u : 0u;
     o.mass1 = mass1;
     o.mass2 = mass2;
     s->counters.algorithmicBytes += algorithmicBytes(dp, o, s->L);
+    // rows whose AP line / factor element the device rewrites for this outcome: every CTA of the
+    // committing cluster bumps the row's version once (kernels.cuh commit_task)
+    bool commit = false;
     switch (hp.type)
     {
         case 'B':
@@ -802,6 +679,7 @@ static int applyOutcome(cgb_sampler *s, const HostProposal &hp, const DevProposa
             {
                 s->queue.acceptBirth();
                 s->domain.atom(hp.atom1).mass = mass1;
+                commit = true;
             }
             else
             {
@@ -814,15 +692,18 @@ static int applyOutcome(cgb_sampler *s, const HostProposal &hp, const DevProposa
             {
                 s->queue.rejectDeath();
                 s->domain.atom(hp.atom1).mass = mass1;
+                commit = (mass1 != dp.m1);
             }
             else
             {
                 s->queue.acceptDeath();
                 s->domain.cacheErase(hp.atom1);
+                commit = true;
             }
             break;
         case 'M':
             if (accepted) { s->domain.move(hp.atom1, hp.pos); }
+            commit = accepted;
             break;
         case 'E':
             if (accepted)
@@ -830,10 +711,319 @@ static int applyOutcome(cgb_sampler *s, const HostProposal &hp, const DevProposa
                 s->domain.atom(hp.atom1).mass = mass1;
                 s->domain.atom(hp.atom2).mass = mass2;
             }
+            commit = accepted;
             break;
         default: return fail(CGB_EINTERNAL, "applyOutcome: corrupt proposal type");
     }
+    if (commit)
+    {
+        s->rowVersion[dp.r1] += s->nSeg;
+        if (isTwoRow(dp)) { s->rowVersion[dp.r2] += s->nSeg; }
+        if (resident)
+        {
+            s->commitsExpected += s->nSeg; // every CTA of the committing cluster counts itself done once
+            s->rowPending[dp.r1] = s->commitsExpected;
+            if (isTwoRow(dp)) { s->rowPending[dp.r2] = s->commitsExpected; }
+        }
+    }
     return CGB_OK;
+}
+
+// true when the last commit to `row` is known to have landed, i.e. no rowVersion check is needed
+static inline bool rowSettled(cgb_sampler *s, uint32_t row)
+{
+    const uint64_t pend = s->rowPending[row];
+    if (pend <= s->commitsProven) { return true; }
+    // commits finish out of order, so only "all of them" proves anything: the mirror equals what the
+    // host expects (no outcome is applied while a batch is being generated, so the target stands still)
+    if (*s->hCommitsMirror == s->commitsExpected)
+    {
+        s->commitsProven = s->commitsExpected;
+        return true;
+    }
+    return false;
+}
+
+// ------------------------------------------------------------------------------------------------
+// resident mode: one grid per update(); every proposal is posted to its cluster's record ring the moment
+// the generator queues it, outcomes come back as self-validating 16-byte records
+// ------------------------------------------------------------------------------------------------
+static size_t streamSmemBytes(const cgb_sampler *s) { return evalSmemBytes(s) + kStreamTableBytes; }
+
+static int startPersistent(cgb_sampler *s)
+{
+    cudaLaunchConfig_t cfg = cudaLaunchConfig_t();
+    cfg.blockDim = dim3(kThreads, 1, 1);
+    cfg.dynamicSmemBytes = streamSmemBytes(s);
+    cfg.stream = s->stream;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = s->nSeg;
+    attr[0].val.clusterDim.y = 1;
+    attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    if (s->persistentGrid == 0)
+    {
+        // every CTA polls for work until told to leave, so the whole grid must be resident at once;
+        // the last cluster only mirrors the commit count, the others are workers
+        cfg.gridDim = dim3(s->nSeg, 1, 1);
+        int maxClusters = 0;
+        if (s->hasS) { CGB_CUDA(cudaOccupancyMaxActiveClusters(&maxClusters, eval_stream_kernel<true>, &cfg)); }
+        else { CGB_CUDA(cudaOccupancyMaxActiveClusters(&maxClusters, eval_stream_kernel<false>, &cfg)); }
+        const int cap = envInt("COGAPS_PERSISTENT_CLUSTERS", 0);
+        if (cap > 1 && cap < maxClusters) { maxClusters = cap; }
+        if (maxClusters < 2) { return fail(CGB_ECUDA, "resident kernel: fewer than two clusters fit on the device"); }
+        s->persistentGrid = maxClusters * static_cast<int>(s->nSeg);
+        s->nClusters = static_cast<uint32_t>(maxClusters - 1);
+        s->nSlotRecords = static_cast<size_t>(s->nClusters) * kStreamRing * s->nSeg;
+        CGB_CUDA(cudaHostAlloc(&s->hSlots, sizeof(StreamRecord) * (s->nSlotRecords + 1), cudaHostAllocMapped));
+        std::memset(s->hSlots, 0, sizeof(StreamRecord) * (s->nSlotRecords + 1));
+        s->slotOwner.assign(static_cast<size_t>(s->nClusters) * kStreamRing, ~0ull);
+    }
+    cfg.gridDim = dim3(s->persistentGrid, 1, 1);
+    ModelView mv;
+    fillModelView(s, mv);
+    mv.annealingTemp = s->annealingTemp; // constant for the whole update() this grid serves
+    // cluster c serves serials c, c + nWorkers, ...; its tickets continue where the last grid stopped
+    s->streamSerial = (s->streamSerial + s->nClusters - 1) / s->nClusters * s->nClusters;
+    volatile unsigned long long *doorbell = reinterpret_cast<volatile unsigned long long*>(static_cast<StreamRecord*>(s->hSlots) + s->nSlotRecords);
+    *doorbell = 0ull;
+    __sync_synchronize();
+    StreamParams sp;
+    sp.slots = static_cast<const StreamRecord*>(s->hSlots);
+    sp.doorbell = doorbell;
+    sp.outcomes = static_cast<HostOutcome*>(s->hStreamOutcomes);
+    sp.commitsMirror = s->hCommitsMirror;
+    sp.stats = static_cast<StreamStats*>(s->dStreamStats);
+    sp.serial0 = s->streamSerial;
+    sp.idleTimeoutNs = static_cast<unsigned long long>(envInt("COGAPS_PERSISTENT_IDLE_MS", 2000)) * 1000000ull;
+    sp.nWorkers = s->nClusters;
+    sp.pollSleepNs = static_cast<uint32_t>(envInt("COGAPS_POLL_SLEEP_NS", 0));
+    CGB_CUDA(cudaMemsetAsync(sp.stats, 0, sizeof(StreamStats), s->stream));
+    // the device counter restarts with the grid; nothing is pending across a kernel boundary
+    *s->hCommitsMirror = 0ull;
+    std::fill(s->rowPending.begin(), s->rowPending.end(), 0ull);
+    s->commitsExpected = s->commitsProven = 0;
+    CGB_CUDA(cudaEventRecord(s->evStart, s->stream));
+    if (s->hasS) { CGB_CUDA(cudaLaunchKernelEx(&cfg, eval_stream_kernel<true>, mv, sp)); }
+    else { CGB_CUDA(cudaLaunchKernelEx(&cfg, eval_stream_kernel<false>, mv, sp)); }
+    CGB_CUDA(cudaEventRecord(s->evStop, s->stream));
+    ++g_kernelLaunches;
+    s->persistentRunning = true;
+    s->lastPostTime = nowSeconds();
+    return CGB_OK;
+}
+
+// writes the record of serial T into its cluster's ring (one copy per CTA of the cluster); a torn read
+// fails the checksum and is simply polled again
+static void writeRecord(cgb_sampler *s, uint64_t T, const StreamRecord &rec)
+{
+    StreamRecord r = rec;
+    r.ticket = static_cast<uint32_t>(T / s->nClusters) + 1u;
+    r.check = stream_check(reinterpret_cast<const uint32_t*>(&r));
+    StreamRecord *dst = static_cast<StreamRecord*>(s->hSlots)
+        + (static_cast<size_t>(T % s->nClusters) * kStreamRing + ((T / s->nClusters) % kStreamRing)) * s->nSeg;
+    static const int mode = envInt("COGAPS_RECORD_STORES", 0);
+    if (mode == 1)
+    {
+        // non-temporal: no read-for-ownership of a line the device keeps pulling across PCIe
+        const __m128i *src = reinterpret_cast<const __m128i*>(&r);
+        const __m128i w0 = _mm_loadu_si128(src), w1 = _mm_loadu_si128(src + 1), w2 = _mm_loadu_si128(src + 2), w3 = _mm_loadu_si128(src + 3);
+        for (uint32_t q = 0; q < s->nSeg; ++q)
+        {
+            __m128i *d = reinterpret_cast<__m128i*>(dst + q);
+            _mm_stream_si128(d, w0);
+            _mm_stream_si128(d + 1, w1);
+            _mm_stream_si128(d + 2, w2);
+            _mm_stream_si128(d + 3, w3);
+        }
+        return;
+    }
+    for (uint32_t q = 0; q < s->nSeg; ++q) { std::memcpy(static_cast<void*>(dst + q), &r, sizeof(r)); }
+    if (mode == 2)
+    {
+        // ask for ownership of the lines the next few serials will land in while we generate them
+        for (uint64_t U = T + 6; U < T + 8; ++U)
+        {
+            const StreamRecord *nx = static_cast<StreamRecord*>(s->hSlots)
+                + (static_cast<size_t>(U % s->nClusters) * kStreamRing + ((U / s->nClusters) % kStreamRing)) * s->nSeg;
+            for (uint32_t q = 0; q < s->nSeg; ++q) { __builtin_prefetch(nx + q, 1, 3); }
+        }
+    }
+}
+
+static int stopPersistent(cgb_sampler *s)
+{
+    if (!s->persistentRunning) { return CGB_OK; }
+    // an exit record in every worker cluster's next slot (all earlier records have been consumed: their
+    // outcomes are in), and the exit bit for the mirror CTA
+    StreamRecord rec;
+    std::memset(&rec, 0, sizeof(rec));
+    rec.type = kStreamExit;
+    for (uint64_t T = s->streamSerial; T < s->streamSerial + s->nClusters; ++T) { writeRecord(s, T, rec); }
+    volatile unsigned long long *doorbell = reinterpret_cast<volatile unsigned long long*>(static_cast<StreamRecord*>(s->hSlots) + s->nSlotRecords);
+    *doorbell = kDoorbellExit;
+    __sync_synchronize();
+    s->streamSerial = (s->streamSerial + s->nClusters + s->nClusters - 1) / s->nClusters * s->nClusters;
+    CGB_CUDA(cudaStreamSynchronize(s->stream));
+    s->persistentRunning = false;
+    s->commitsProven = s->commitsExpected; // the grid has drained: every commit it made is complete
+    float ms = 0.f;
+    CGB_CUDA(cudaEventElapsedTime(&ms, s->evStart, s->evStop));
+    s->counters.secondsKernel += static_cast<double>(ms) * 1e-3;
+    if (s->dPhaseClocks)
+    {
+        // phase profile: every task slot holds the stamps of the last task that used it
+        std::vector<unsigned long long> h(static_cast<size_t>(2 * kMaxBatch) * kPhaseSlots);
+        CGB_CUDA(cudaMemcpy(h.data(), s->dPhaseClocks, h.size() * sizeof(unsigned long long), cudaMemcpyDeviceToHost));
+        for (uint32_t t = 0; t < 2u * kMaxBatch; ++t)
+        {
+            const unsigned long long *p = h.data() + static_cast<size_t>(t) * kPhaseSlots;
+            if (p[1] == 0 || p[8] <= p[1]) { continue; }
+            for (int i = 2; i < 9; ++i) { s->phaseSum[i] += static_cast<double>(p[i] - p[1]); }
+            s->phaseTasks += 1;
+        }
+        CGB_CUDA(cudaMemset(s->dPhaseClocks, 0, h.size() * sizeof(unsigned long long)));
+    }
+    if (envInt("COGAPS_PERSISTENT_DEBUG", 0))
+    {
+        StreamStats st;
+        CGB_CUDA(cudaMemcpy(&st, s->dStreamStats, sizeof(st), cudaMemcpyDeviceToHost));
+        const double nt = static_cast<double>(st.tasks ? st.tasks : 1), no = static_cast<double>(st.outcomes ? st.outcomes : 1);
+        std::printf("[resident nSeg=%u grid=%d] kernel %.3f ms, tasks %llu | record seen -> commit done %.2f us (max %.2f) | "
+                    "record seen -> outcome posted %.2f us | row-version wait %.3f us\n",
+                    s->nSeg, s->persistentGrid, ms, st.tasks, st.taskNs / nt * 1e-3, st.maxTaskNs * 1e-3,
+                    st.decideNs / no * 1e-3, st.verWaitNs / nt * 1e-3);
+    }
+    return CGB_OK;
+}
+
+// spins until the outcome of proposal `pi` of the current chunk is in host memory, then files it
+static int waitOutcome(cgb_sampler *s, uint32_t pi)
+{
+    const size_t idx = s->chunkBase + pi;
+    if (s->arrived[idx]) { return CGB_OK; }
+    volatile HostOutcome *o = static_cast<HostOutcome*>(s->hStreamOutcomes) + pi;
+    const uint32_t want = s->chunkTag;
+    double t0 = 0.0; // the clock is only read when we actually have to wait
+    uint64_t spins = 0;
+    for (;;)
+    {
+        const uint32_t w2 = o->seqAndAccepted;
+        if ((w2 >> 1) == want)
+        {
+            const uint32_t w0 = o->mass1Bits, w1 = o->mass2Bits, w3 = o->check;
+            if (o->seqAndAccepted == w2 && w3 == outcome_check(w0, w1, w2))
+            {
+                DevOutcome &d = s->collected[idx];
+                std::memcpy(&d.mass1, &w0, 4);
+                std::memcpy(&d.mass2, &w1, 4);
+                d.accepted = w2 & 1u;
+                s->arrived[idx] = 1;
+                break;
+            }
+        }
+        if (spins == 0) { t0 = nowSeconds(); }
+        __builtin_ia32_pause();
+        if ((++spins & 0xfffff) == 0 && nowSeconds() - t0 > 20.0)
+        {
+            cudaError_t e = cudaStreamQuery(s->stream);
+            s->persistentRunning = false;
+            return fail(CGB_ECUDA, std::string("resident eval kernel did not answer within 20 s (stream state: ")
+                + cudaGetErrorString(e) + "; waiting for outcome " + std::to_string(pi) + " of chunk " + std::to_string(s->mailSeq)
+                + ", " + std::to_string(s->chunkPosted) + " posted; grid " + std::to_string(s->persistentGrid) + " nSeg "
+                + std::to_string(s->nSeg) + ")");
+        }
+    }
+    if (spins != 0) { s->counters.secondsDeviceWait += nowSeconds() - t0; }
+    return CGB_OK;
+}
+
+// opens a chunk of at most kMaxPersistentBatch proposals whose outcomes share one tag
+static int beginChunk(cgb_sampler *s, size_t chunkBase)
+{
+    const double t0 = nowSeconds();
+    if (s->persistentRunning && t0 - s->lastPostTime > 1.0)
+    {
+        CGB_TRY(stopPersistent(s)); // the grid may be about to give up waiting (idle timeout): restart it
+    }
+    if (!s->persistentRunning) { CGB_TRY(startPersistent(s)); }
+    s->lastPostTime = t0;
+    ++s->mailSeq;
+    s->chunkTag = static_cast<uint32_t>(s->mailSeq) & 0x7fffffffu;
+    s->chunkPosted = 0;
+    s->chunkBase = chunkBase;
+    return CGB_OK;
+}
+
+// posts proposal `index` of the batch (ProposalQueue sink, or the chunk loop for very long batches)
+static int postProposal(cgb_sampler *s, const HostProposal &hp, size_t index)
+{
+    if (index < s->chunkBase || index - s->chunkBase >= static_cast<size_t>(kMaxPersistentBatch)) { return CGB_OK; }
+    if (s->posted.size() <= index)
+    {
+        const size_t n = std::max<size_t>(index + 1, s->posted.size() * 2 + 256);
+        s->posted.resize(n);
+        s->collected.resize(n);
+        s->arrived.resize(n, 0);
+    }
+    DevProposal &dp = s->posted[index];
+    fillProposal(s, hp, dp);
+    s->arrived[index] = 0;
+    const uint32_t pi = static_cast<uint32_t>(index - s->chunkBase);
+    StreamRecord rec;
+    rec.rng = dp.rng;
+    rec.r1 = dp.r1; rec.c1 = dp.c1; rec.r2 = dp.r2; rec.c2 = dp.c2;
+    rec.m1 = dp.m1; rec.m2 = dp.m2;
+    rec.type = dp.type;
+    rec.ver1 = s->rowVersion[dp.r1];
+    rec.ver2 = 0u;
+    if (!rowSettled(s, dp.r1)) { rec.type |= kStreamWait1; }
+    if (dp.type == 'M' || dp.type == 'E')
+    {
+        rec.ver2 = s->rowVersion[dp.r2];
+        if (!rowSettled(s, dp.r2)) { rec.type |= kStreamWait2; }
+    }
+    rec.pad = 0u;
+    rec.batch = s->chunkTag;
+    const uint32_t nParts = isTwoRow(dp) ? 2u : 1u;
+    for (uint32_t part = 0; part < nParts; ++part)
+    {
+        const uint64_t T = s->streamSerial++;
+        const uint32_t cluster = static_cast<uint32_t>(T % s->nClusters);
+        uint64_t &owner = s->slotOwner[static_cast<size_t>(cluster) * kStreamRing + ((T / s->nClusters) % kStreamRing)];
+        if ((owner >> 32) == (s->mailSeq & 0xffffffffull))
+        {
+            // the ring slot still holds a record of this chunk: its outcome proves it has been consumed
+            CGB_TRY(waitOutcome(s, static_cast<uint32_t>(owner & 0xffffffffull)));
+        }
+        owner = ((s->mailSeq & 0xffffffffull) << 32) | pi;
+        rec.piPart = pi | (part << 31);
+        writeRecord(s, T, rec);
+    }
+    s->chunkPosted += 1;
+    return CGB_OK;
+}
+
+struct SinkCtx
+{
+    cgb_sampler *s;
+    int rc;
+};
+
+static void proposalSink(void *ctx, const HostProposal &hp, size_t index)
+{
+    SinkCtx *c = static_cast<SinkCtx*>(ctx);
+    if (g_prof)
+    {
+        const unsigned long long t0 = tsc();
+        if (c->rc == CGB_OK) { c->rc = postProposal(c->s, hp, index); }
+        g_tscPost += tsc() - t0;
+        ++g_nPosts;
+        return;
+    }
+    if (c->rc == CGB_OK) { c->rc = postProposal(c->s, hp, index); }
 }
 
 static int evaluateQueue(cgb_sampler *s)
@@ -842,29 +1032,31 @@ static int evaluateQueue(cgb_sampler *s)
     size_t done = 0;
     if (s->usePersistent)
     {
-        HostMailbox *hb = static_cast<HostMailbox*>(s->hMailbox);
+        // the first chunk was streamed while the generator ran; longer batches continue in chunks
         while (done < q.size())
         {
-            const uint32_t n = static_cast<uint32_t>(std::min<size_t>(kMaxPersistentBatch, q.size() - done));
-            for (uint32_t i = 0; i < n; ++i)
+            const size_t n = std::min<size_t>(kMaxPersistentBatch, q.size() - done);
+            if (done > 0)
             {
-                TaskRecord &t = hb->tasks[static_cast<size_t>(i) * s->nSeg];
-                fillProposal(s, q[done + i], t.pr);
-                t.pi = i;
-                t.part = 0;
+                CGB_TRY(beginChunk(s, done));
+                for (size_t i = 0; i < n; ++i) { CGB_TRY(postProposal(s, q[done + i], done + i)); }
             }
-            CGB_TRY(persistentBatch(s, n));
-            for (uint32_t i = 0; i < n; ++i)
+            // outcomes are applied in queue order as they arrive (generation is over, so the domain and
+            // the atom-count window may change now); the early ones are long in, the tail hides the rest
+            for (size_t i = 0; i < n; ++i)
             {
-                const HostOutcome &o = hb->outcomes[i];
-                float m1, m2;
-                std::memcpy(&m1, &o.mass1Bits, 4);
-                std::memcpy(&m2, &o.mass2Bits, 4);
-                CGB_TRY(applyOutcome(s, q[done + i], hb->tasks[static_cast<size_t>(i) * s->nSeg].pr, (o.seqAndAccepted & 1u) != 0u, m1, m2));
+                const unsigned long long tw = g_prof ? tsc() : 0ull;
+                CGB_TRY(waitOutcome(s, static_cast<uint32_t>(i)));
+                if (g_prof) { g_tscWaitTail += tsc() - tw; }
+                const DevOutcome &o = s->collected[done + i];
+                const unsigned long long ta = g_prof ? tsc() : 0ull;
+                CGB_TRY(applyOutcome(s, q[done + i], s->posted[done + i], true, o.accepted != 0u, o.mass1, o.mass2));
+                if (g_prof) { g_tscApply += tsc() - ta; }
             }
-            s->counters.nProposalsQueued += n;
+            s->counters.nBatches += 1;
             done += n;
         }
+        s->counters.nProposalsQueued += q.size();
         return CGB_OK;
     }
     static thread_local EvalParams params; // ~20 KB of kernel parameters, reused
@@ -878,7 +1070,7 @@ static int evaluateQueue(cgb_sampler *s)
         for (uint32_t i = 0; i < n; ++i)
         {
             const DevOutcome &o = s->hOutcomes[i];
-            CGB_TRY(applyOutcome(s, q[done + i], params.props[i], o.accepted != 0u, o.mass1, o.mass2));
+            CGB_TRY(applyOutcome(s, q[done + i], params.props[i], false, o.accepted != 0u, o.mass1, o.mass2));
         }
         s->counters.nProposalsQueued += n;
         done += n;
@@ -892,11 +1084,29 @@ extern "C" int cgb_sampler_update(cgb_sampler *s, uint32_t nSteps, uint32_t nThr
     (void)nThreads;
     CGB_CHECK(s && s->other, "cgb_sampler_update: sync() has not been called");
     CGB_CUDA(cudaSetDevice(s->device));
+    if (g_hostProfile < 0) { g_hostProfile = envInt("COGAPS_HOST_PROFILE", 0); }
     uint32_t n = 0;
     while (n < nSteps)
     {
         const double t0 = nowSeconds();
-        s->queue.populate(s->domain, nSteps - n);
+        const double waitBefore = s->counters.secondsDeviceWait;
+        SinkCtx sink;
+        sink.s = s;
+        sink.rc = CGB_OK;
+        if (s->usePersistent)
+        {
+            const int rcBegin = beginChunk(s, 0);
+            if (rcBegin != CGB_OK) { return rcBegin; }
+            g_prof = g_hostProfile > 0 && ((g_profCounter++ & 15ull) == 0ull);
+            if (g_prof) { ++g_profBatches; }
+            const unsigned long long tp = g_prof ? tsc() : 0ull;
+            s->queue.populate(s->domain, nSteps - n, proposalSink, &sink);
+            if (g_prof) { g_tscPopulate += tsc() - tp; }
+        }
+        else
+        {
+            s->queue.populate(s->domain, nSteps - n);
+        }
         n += s->queue.nProcessed();
         if (n < nSteps)
         {
@@ -904,23 +1114,30 @@ extern "C" int cgb_sampler_update(cgb_sampler *s, uint32_t nSteps, uint32_t nThr
             s->avgQueueLength *= (s->numQueueSamples - 1.f) / s->numQueueSamples;
             s->avgQueueLength += static_cast<float>(s->queue.entries().size()) / s->numQueueSamples;
         }
-        const double t1 = nowSeconds();
-        s->counters.secondsHostGenerate += t1 - t0;
-        const double waitBefore = s->counters.secondsDeviceWait;
-        if (!s->queue.entries().empty())
+        int rcEval = sink.rc;
+        if (rcEval == CGB_OK && !s->queue.entries().empty()) { rcEval = evaluateQueue(s); }
+        if (rcEval != CGB_OK)
         {
-            const int rcEval = evaluateQueue(s);
-            if (rcEval != CGB_OK)
-            {
-                stopPersistent(s);
-                return rcEval;
-            }
+            stopPersistent(s);
+            return rcEval;
         }
+        const unsigned long long tf = g_prof ? tsc() : 0ull;
         s->queue.clear();
         s->domain.flushEraseCache();
-        s->counters.secondsHostGenerate += (nowSeconds() - t1) - (s->counters.secondsDeviceWait - waitBefore);
+        if (g_prof) { g_tscFlush += tsc() - tf; }
+        g_prof = false;
+        s->counters.secondsHostGenerate += (nowSeconds() - t0) - (s->counters.secondsDeviceWait - waitBefore);
     }
     CGB_TRY(stopPersistent(s));
+    if (g_hostProfile > 0)
+    {
+        const double nb = static_cast<double>(g_profBatches ? g_profBatches : 1);
+        std::printf("[host profile nSeg=%u] kticks per sampled batch (%llu batches, %.1f posts each): populate incl. posting %.2f, posting %.2f, "
+                    "outcome wait %.2f, apply %.2f, flush+clear %.2f\n",
+                    s->nSeg, g_profBatches, g_nPosts / nb, g_tscPopulate / nb * 1e-3, g_tscPost / nb * 1e-3, g_tscWaitTail / nb * 1e-3,
+                    g_tscApply / nb * 1e-3, g_tscFlush / nb * 1e-3);
+        g_tscPost = g_tscApply = g_tscFlush = g_tscPopulate = g_nPosts = g_profBatches = g_tscWaitTail = 0;
+    }
     s->counters.nProposalsTotal += nSteps;
     if (s->queue.minAtoms() != s->queue.maxAtoms() || s->queue.maxAtoms() != s->domain.size())
     {

@@ -10,8 +10,11 @@ static const int kThreads = 512;      // threads per CTA of the eval kernel (16 
 static const int kVec = 4;            // floats per vector access (16 B)
 static const int kMaxBatch = 384;     // proposals per launch carried in kernel-parameter space
 static const int kMaxCluster = 8;     // portable cluster limit
-static const int kMaxPersistentBatch = 1024; // proposals per batch through the persistent kernel's mailbox
-static const unsigned long long kExitSeq = ~0ull;
+static const int kMaxPersistentBatch = 1024; // proposals per chunk through the resident kernel's mailbox
+static const int kStreamRing = 8;     // task-record slots per resident cluster (ring, host pinned memory)
+static const uint32_t kStreamExit = 0xFFFFFFFFu; // record type that retires a resident CTA
+static const uint32_t kStreamWait1 = 0x100u;     // record type bits: the host has no proof yet that the last commit
+static const uint32_t kStreamWait2 = 0x200u;     //   to row r1 / r2 has landed, so the task must check rowVersion
 static const int kPhaseSlots = 12;    // debug phase timestamps per task
 static const uint32_t kProbe = 'P';   // lock-step probe pseudo-proposal
 
@@ -56,12 +59,43 @@ struct ModelView
     AlphaPair *partials;     // [kMaxPersistentBatch][2] cross-cluster (s, s_mu) of two-row proposals
     uint32_t *tickets;       // [kMaxPersistentBatch]
     unsigned long long *phaseClocks; // debug: [kMaxBatch][kPhaseSlots] SM clock at each phase, or nullptr
+    uint32_t *rowVersion;    // [nRows] CTA-commits applied to each row (AP row + its factor elements)
     uint32_t nRows, L, k;
     uint32_t ld, ldM, ldOther;
     uint32_t seg;            // floats per segment (multiple of 4)
     uint32_t nSeg;           // segments per row = cluster size
     uint32_t segPad;         // floats reserved per stream in shared memory
     float lambda, maxGibbsMass, annealingTemp;
+};
+
+// One (proposal, row) work item as the host streams it to the resident grid: 64 bytes = one PCIe read.
+// Word layout matters (the poller validates 16-byte chunks): w12..w15 = batch, ticket, check, pad.
+struct StreamRecord
+{
+    uint64_t rng;         // PCG state after the generator's own draws
+    uint32_t r1, c1;
+    uint32_t r2, c2;
+    float m1, m2;
+    uint32_t type;        // 'B','D','M','E' (| kStreamWait1/2) or kStreamExit
+    uint32_t piPart;      // index of the proposal in its chunk | (which of its rows this task is) << 31
+    uint32_t ver1, ver2;  // rowVersion[r1] / rowVersion[r2] this task must see before it reads those rows
+    uint32_t batch;       // chunk tag, echoed in the outcome record
+    uint32_t ticket;      // 1-based serial of this record in its cluster's stream: what the poller waits for
+    uint32_t check;       // stream_check of the other 15 words: tells a complete record from a torn one
+    uint32_t pad;
+};
+
+// device-side diagnostics of the resident grid
+struct StreamStats
+{
+    unsigned long long taskNs;     // sum over tasks: record seen -> commit done (leader CTA, globaltimer)
+    unsigned long long tasks;
+    unsigned long long maxTaskNs;
+    unsigned long long verWaitNs;  // sum over tasks: time spent waiting for a row version
+    unsigned long long decideNs;   // sum over tasks: record seen -> outcome posted (deciding CTA)
+    unsigned long long outcomes;
+    unsigned long long commitsDone; // CTA-commits completed (AP row written, fenced); the mirror CTA copies it to the host
+    unsigned long long pad;
 };
 
 struct EvalParams

@@ -197,9 +197,9 @@ struct Pcg
     CGB_HD float uniform()
     {
 #if defined(__CUDA_ARCH__)
-        return fdiv(__uint2float_rn(next()), 4294967296.0f);
+        return fmul(__uint2float_rn(next()), 2.3283064365386963e-10f); // x / 2^32, exact scaling
 #else
-        return static_cast<float>(next()) / 4294967296.0f;
+        return static_cast<float>(next()) * 2.3283064365386963e-10f;
 #endif
     }
     CGB_HD float uniform(float a, float b) { return fadd(fmul(uniform(), fsub(b, a)), a); } // :68-71

@@ -88,7 +88,7 @@ struct EvalSmem
     float segS[kMaxCluster];
     float segMu[kMaxCluster];
     Decision dec;
-    uint32_t pad[2];
+    float preLog[2];    // log of the proposal stream's next and next-but-one uniform (see PreLog)
 };
 
 __device__ __forceinline__ float derive_s(float d)
@@ -172,11 +172,28 @@ struct Verdict
     DevOutcome out;
 };
 
+// The accept tests take log(uniform()) of the proposal's own PCG stream, as its first draw (move, death
+// without a Gibbs draw) or its second (death after gibbsMass drew).  Both candidates depend only on the
+// stream state the host sent, so another warp computes them while the scan runs and the f64 log is off
+// the serial tail; which one applies is known once gibbsMass has or has not advanced the stream.
+struct PreLog
+{
+    uint64_t state0;   // stream state as posted
+    float logFirst;    // portable_logf(uniform()) of the first draw
+    float logSecond;   // ... of the second draw
+    __device__ __forceinline__ float take(Pcg &rng) const
+    {
+        const bool first = (rng.state == state0);
+        rng.advance();
+        return first ? logFirst : logSecond;
+    }
+};
+
 // The serial tail of one proposal: alpha parameters -> gibbsMass / accept test -> deltas
 // (AsynchronousGibbsSampler.h:126-219).  One lane runs it; kept out of line so its registers (f64 log,
 // divisions) do not inflate the allocation of the 255 lanes that only scan.
 __device__ __noinline__ void decide(const ModelView &mv, const float *erfT, const float *erfinvT, float T, const DevProposal &pr, uint32_t part, bool twoRow,
-                                    float s, float mu, float M1, float M2, int can1, int can2, Verdict *v)
+                                    float s, float mu, float M1, float M2, int can1, int can2, const PreLog &pre, Verdict *v)
 {
     const uint32_t type = pr.type;
     const uint32_t r1 = pr.r1, c1 = pr.c1, r2 = pr.r2, c2 = pr.c2;
@@ -213,7 +230,7 @@ __device__ __noinline__ void decide(const ModelView &mv, const float *erfT, cons
         }
         else
         {
-            mass = fdiv(fmul(-1.f, portable_logf(rng.uniform())), mv.lambda);
+            mass = fdiv(fmul(-1.f, pre.take(rng)), mv.lambda);
             has = true;
         }
         if (has && mass >= kEpsilon)
@@ -234,8 +251,8 @@ __device__ __noinline__ void decide(const ModelView &mv, const float *erfT, cons
             float g;
             if (gibbs_mass(rng, erfT, erfinvT, as, amu, 0.f, mv.maxGibbsMass, true, mv.lambda, &g)) { rebirth = g; }
         }
-        const float dLL = fmul(rebirth, fsub(amu, fdiv(fmul(as, rebirth), 2.f)));
-        if (portable_logf(rng.uniform()) < dLL)
+        const float dLL = fmul(rebirth, fsub(amu, fmul(fmul(as, rebirth), 0.5f)));
+        if (pre.take(rng) < dLL)
         {
             out.accepted = 1u;
             out.mass1 = rebirth;
@@ -258,8 +275,8 @@ __device__ __noinline__ void decide(const ModelView &mv, const float *erfT, cons
     else if (type == 'M')
     {
         // AsynchronousGibbsSampler::move, :183-196; deltaLogLikelihood DenseNormalModel.cpp:125-130
-        const float dLL = fmul(fmul(-1.f, m1), fadd(amu, fdiv(fmul(as, m1), 2.f)));
-        if (portable_logf(rng.uniform()) < dLL)
+        const float dLL = fmul(fmul(-1.f, m1), fadd(amu, fmul(fmul(as, m1), 0.5f)));
+        if (pre.take(rng) < dLL)
         {
             out.accepted = 1u;
             out.mass1 = m1;
@@ -319,13 +336,43 @@ __device__ __noinline__ void decide(const ModelView &mv, const float *erfT, cons
     v->out = out;
 }
 
+__device__ __forceinline__ unsigned int ld_acquire_gpu_u32(const unsigned int *p)
+{
+    unsigned int v;
+    asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ unsigned long long global_timer_ns()
+{
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+    return t;
+}
+
+// One (proposal, row) work item as a CTA sees it.
+struct TaskIn
+{
+    DevProposal pr;
+    uint32_t pi;       // index of the proposal in its batch (where its outcome goes)
+    uint32_t part;     // 0: row r1 (or the only row); 1: row r2 of a two-row move / exchange
+    uint32_t ver1;     // streaming mode: rowVersion[r1] / rowVersion[r2] to wait for ...
+    uint32_t ver2;
+    uint32_t waitMask; // ... when bit 0 / bit 1 is set (the host cannot yet prove the row's last commit has landed)
+};
+
 // One (proposal, row) task, executed by one cluster of nSeg CTAs.  `parity` is the phase of the
-// staging mbarrier (flips every task in the persistent kernel).  Returns true on the lane that owns the
+// staging mbarrier (flips every task in the resident kernel).  Returns true on the lane that owns the
 // proposal's outcome (leader CTA, lane 0, deciding cluster), with the outcome in *outp.
-template <bool HAS_S, bool PERSISTENT>
-__device__ __forceinline__ bool process_task(const ModelView &mv, const float *erfT, const float *erfinvT, float annealingTemp, const DevProposal pr, uint32_t pi, uint32_t part,
+//
+// STREAM: tasks of successive batches are in flight at once, so a row (its AP line and its factor
+// elements) may only be read once every commit the host knows about has landed: the host sends the
+// row's expected commit count, committers bump rowVersion[row] after a fence.  D and the factor columns
+// are constant for the whole update(), so their copies are issued before that wait.
+template <bool HAS_S, bool STREAM>
+__device__ __forceinline__ bool process_task(const ModelView &mv, const float *erfT, const float *erfinvT, float annealingTemp, const TaskIn &in,
                                              uint32_t task, unsigned char *smemRaw, uint32_t parity,
-                                             cg::cluster_group &cluster, uint32_t rank, DevOutcome *outp)
+                                             cg::cluster_group &cluster, uint32_t rank, DevOutcome *outp,
+                                             unsigned long long *verWaitNs)
 {
     EvalSmem *hdr = reinterpret_cast<EvalSmem*>(smemRaw);
     float *bufD = reinterpret_cast<float*>(smemRaw + 256);
@@ -335,6 +382,8 @@ __device__ __forceinline__ bool process_task(const ModelView &mv, const float *e
     float *bufS = bufV2 + mv.segPad;
     const uint32_t nSeg = mv.nSeg;
     const uint32_t tid = threadIdx.x;
+    const DevProposal &pr = in.pr;
+    const uint32_t pi = in.pi, part = in.part;
 
     const uint32_t type = pr.type;
     const uint32_t r1 = pr.r1, c1 = pr.c1, r2 = pr.r2, c2 = pr.c2;
@@ -357,30 +406,50 @@ __device__ __forceinline__ bool process_task(const ModelView &mv, const float *e
     int can1 = 0, can2 = 0;
     if (tid == 0)
     {
+        const uint32_t bytes = lenPad * 4u;
+        const size_t rowOff = static_cast<size_t>(row) * mv.ld + segStart;
         if (len > 0)
         {
-            const uint32_t bytes = lenPad * 4u;
             const uint32_t nStreams = 3u + (useV2 ? 1u : 0u) + (HAS_S ? 1u : 0u);
             mbar_expect_tx(&hdr->bar, bytes * nStreams);
-            const size_t rowOff = static_cast<size_t>(row) * mv.ld + segStart;
             bulk_g2s(bufD, mv.D + rowOff, bytes, &hdr->bar);
-            bulk_g2s(bufAP, mv.AP + rowOff, bytes, &hdr->bar);
             bulk_g2s(bufV1, mv.otherM + static_cast<size_t>(colA) * mv.ldOther + segStart, bytes, &hdr->bar);
             if (useV2) { bulk_g2s(bufV2, mv.otherM + static_cast<size_t>(c2) * mv.ldOther + segStart, bytes, &hdr->bar); }
             if (HAS_S) { bulk_g2s(bufS, mv.S + rowOff, bytes, &hdr->bar); }
         }
         if (rank == 0 && type != kProbe)
         {
-            // current factor-matrix elements (safelyChangeMatrix) and canUseGibbs flags; their latency
-            // hides under the copies.  L2 loads: an earlier batch of this kernel may have written M.
-            M1 = ld_cg_f32(mv.M + static_cast<size_t>(c1) * mv.ldM + r1);
             can1 = mv.otherColNonzero[c1];
-            if (pairType)
+            if (pairType) { can2 = mv.otherColNonzero[c2]; }
+        }
+        if (STREAM)
+        {
+            // both rows of a two-row proposal: the leader also reads the other row's factor element
+            if (in.waitMask != 0u)
             {
-                M2 = ld_cg_f32(mv.M + static_cast<size_t>(c2) * mv.ldM + r2);
-                can2 = mv.otherColNonzero[c2];
+                const unsigned long long t0 = global_timer_ns();
+                if (in.waitMask & 1u) { while (ld_acquire_gpu_u32(mv.rowVersion + r1) != in.ver1) { } }
+                if (in.waitMask & 2u) { while (ld_acquire_gpu_u32(mv.rowVersion + r2) != in.ver2) { } }
+                asm volatile("fence.proxy.async;" ::: "memory");
+                if (verWaitNs) { *verWaitNs = global_timer_ns() - t0; }
             }
         }
+        if (len > 0) { bulk_g2s(bufAP, mv.AP + rowOff, bytes, &hdr->bar); }
+        if (rank == 0 && type != kProbe)
+        {
+            // current factor-matrix elements (safelyChangeMatrix); their latency hides under the copies.
+            // L2 loads: an earlier batch may have written M.
+            M1 = ld_cg_f32(mv.M + static_cast<size_t>(c1) * mv.ldM + r1);
+            if (pairType) { M2 = ld_cg_f32(mv.M + static_cast<size_t>(c2) * mv.ldM + r2); }
+        }
+    }
+    else if (tid == 32 && rank == 0 && (type == 'D' || type == 'M' || type == 'B'))
+    {
+        // PreLog: both candidate log(uniform()) values of the accept test, off the serial tail
+        Pcg r;
+        r.state = pr.rng;
+        hdr->preLog[0] = portable_logf(r.uniform());
+        hdr->preLog[1] = portable_logf(r.uniform());
     }
     stamp(mv, task, rank, 2); // copies issued
 
@@ -479,7 +548,11 @@ __device__ __forceinline__ bool process_task(const ModelView &mv, const float *e
         v.dec.flags = 0u;
         if (decideHere)
         {
-            decide(mv, erfT, erfinvT, annealingTemp, pr, part, twoRow, s, mu, M1, M2, can1, can2, &v);
+            PreLog pre;
+            pre.state0 = pr.rng;
+            pre.logFirst = hdr->preLog[0];
+            pre.logSecond = hdr->preLog[1];
+            decide(mv, erfT, erfinvT, annealingTemp, pr, part, twoRow, s, mu, M1, M2, can1, can2, pre, &v);
             *outp = v.out;
             owner = true;
         }
@@ -489,10 +562,31 @@ __device__ __forceinline__ bool process_task(const ModelView &mv, const float *e
         for (uint32_t q = 1; q < nSeg; ++q) { cluster.map_shared_rank(hdr, q)->dec = v.dec; }
         stamp(mv, task, rank, 6); // decision made
     }
+    return owner;
+}
+
+// Second half of a task: AP[row,:] += delta * other[:,col] (updateAPMatrix, DenseNormalModel.cpp:243-258)
+// from the staged copies, then the row-version bump that lets a later batch read the row.  Separate
+// from process_task so the resident kernel can post the outcome to the host in between.
+template <bool HAS_S>
+__device__ __forceinline__ void commit_task(const ModelView &mv, const TaskIn &in, uint32_t task, unsigned char *smemRaw,
+                                            cg::cluster_group &cluster, uint32_t rank, unsigned long long *commitsDone)
+{
+    EvalSmem *hdr = reinterpret_cast<EvalSmem*>(smemRaw);
+    float *bufD = reinterpret_cast<float*>(smemRaw + 256);
+    float *bufAP = bufD + mv.segPad;
+    float *bufV1 = bufAP + mv.segPad;
+    float *bufV2 = bufV1 + mv.segPad;
+    const uint32_t nSeg = mv.nSeg;
+    const uint32_t tid = threadIdx.x;
+    const uint32_t row = in.part ? in.pr.r2 : in.pr.r1;
+    const uint32_t segStart = rank * mv.seg;
+    const uint32_t len = segStart >= mv.L ? 0u : min(mv.seg, mv.L - segStart);
+    const uint32_t lenPad = (len + 3u) & ~3u;
+
     if (nSeg > 1) { cluster.sync(); } else { __syncthreads(); }
     stamp(mv, task, rank, 7); // decision broadcast
 
-    // ---- commit: AP[row,:] += delta * other[:,col] (updateAPMatrix, DenseNormalModel.cpp:243-258) ----
     const Decision dec = hdr->dec;
     if ((dec.flags & 3u) != 0u && len > 0)
     {
@@ -537,8 +631,23 @@ __device__ __forceinline__ bool process_task(const ModelView &mv, const float *e
             reinterpret_cast<float4*>(apRow)[j] = a;
         }
     }
+    // every CTA of the cluster counts once per row it changed (the host expects nSeg per commit); the
+    // leader's store of the factor element precedes its fence, so the bump publishes that too
+    if ((dec.flags & 7u) != 0u)
+    {
+        __syncthreads();
+        if (tid == 0)
+        {
+            // bar.sync ordered every thread's AP stores before this fence; the fence orders them before
+            // the bumps for every observer (the done count reaches other CTAs by way of the host, hence
+            // system scope)
+            __threadfence_system();
+            if ((dec.flags & 3u) != 0u) { atomicAdd(mv.rowVersion + row, 1u); }
+            if ((dec.flags & 4u) != 0u) { atomicAdd(mv.rowVersion + dec.otherRow, 1u); }
+            if (commitsDone != nullptr) { atomicAdd(commitsDone, 1ull); }
+        }
+    }
     stamp(mv, task, rank, 8); // commit done
-    return owner;
 }
 
 // One launch per conflict-free batch; proposals travel in kernel-parameter space.
@@ -550,8 +659,11 @@ __global__ void __launch_bounds__(kThreads, 2) eval_kernel(const __grid_constant
     cg::cluster_group cluster = cg::this_cluster();
     const uint32_t rank = cluster.block_rank();
     const uint32_t task = blockIdx.y;
-    const uint32_t pi = task < P.nProps ? task : static_cast<uint32_t>(P.extra[task - P.nProps]);
-    const uint32_t part = task < P.nProps ? 0u : 1u;
+    TaskIn in;
+    in.pi = task < P.nProps ? task : static_cast<uint32_t>(P.extra[task - P.nProps]);
+    in.part = task < P.nProps ? 0u : 1u;
+    in.ver1 = in.ver2 = in.waitMask = 0u;
+    in.pr = P.props[in.pi];
     if (threadIdx.x == 0)
     {
         mbar_init(&hdr->bar, 1);
@@ -559,23 +671,26 @@ __global__ void __launch_bounds__(kThreads, 2) eval_kernel(const __grid_constant
     }
     __syncthreads();
     DevOutcome out;
-    const DevProposal pr = P.props[pi];
-    if (process_task<HAS_S, false>(P.mv, P.mv.erf, P.mv.erfinv, P.mv.annealingTemp, pr, pi, part, task, smemRaw, 0u, cluster, rank, &out))
+    if (process_task<HAS_S, false>(P.mv, P.mv.erf, P.mv.erfinv, P.mv.annealingTemp, in, task, smemRaw, 0u, cluster, rank, &out, nullptr))
     {
-        P.mv.outcomes[pi] = out;
+        P.mv.outcomes[in.pi] = out;
     }
+    commit_task<HAS_S>(P.mv, in, task, smemRaw, cluster, rank, nullptr);
 }
 
 // ------------------------------------------------------------------------------------------------
-// Persistent variant: launched once per update(); the host posts each conflict-free batch into pinned
-// memory and bumps a sequence number, CTA 0 pulls the batch across PCIe and releases the grid, every
-// cluster takes tasks round-robin, outcomes go back as self-tagged 16-byte records the host spins on.
-// Removes the per-batch kernel launch + stream synchronise from the serial host<->device loop.
+// Resident ("streaming") variant: launched once per update().  The host generator writes each proposal
+// into its cluster's ring of 64-byte task records in pinned memory THE MOMENT it is generated; every
+// worker cluster polls its own ring across PCIe (one round trip from "posted" to "running", no grid-wide
+// release), so the evaluation of a batch overlaps its generation.  Outcomes go back as self-tagged
+// 16-byte records the host spins on, posted BEFORE the AP commit; cross-batch ordering is per row
+// (rowVersion + a count of finished commits that one extra CTA mirrors to the host), not a grid barrier.
+// Records of cluster c: slots[(c * kStreamRing + (ticket - 1) % kStreamRing) * nSeg + rank].
 // ------------------------------------------------------------------------------------------------
 struct HostOutcome   // one 16-byte store, self-validating for the polling host
 {
     uint32_t mass1Bits, mass2Bits;
-    uint32_t seqAndAccepted; // (batch id << 1) | accepted
+    uint32_t seqAndAccepted; // (chunk tag << 1) | accepted
     uint32_t check;          // outcome_check of the three words above
 };
 
@@ -584,43 +699,19 @@ __host__ __device__ __forceinline__ uint32_t outcome_check(uint32_t w0, uint32_t
     return (w0 * 0x9E3779B1u) ^ (w1 * 0x85EBCA77u) ^ (w2 * 0xC2B2AE3Du) ^ 0x27D4EB2Fu;
 }
 
-// One (proposal, row) work item as the host posts it: the proposal plus which of its rows this is.
-struct TaskRecord    // 64 bytes = one PCIe read
+// checksum of a StreamRecord: word i weighted by an odd constant, word 14 (the checksum itself) skipped
+__host__ __device__ __forceinline__ uint32_t stream_weight(uint32_t i) { return 0x9E3779B1u * (2u * i + 1u); }
+__host__ __device__ __forceinline__ uint32_t stream_check(const uint32_t *w)
 {
-    DevProposal pr;
-    uint32_t pi;      // index of the proposal in the batch (where its outcome goes)
-    uint32_t part;    // 0: row r1 (or the only row); 1: row r2 of a two-row move / exchange
-    uint32_t pad[2];
-};
-
-// host -> device word: batch id in the high bits, task / proposal counts in the low bits, so one
-// uncached load tells CTA 0 everything it needs to release the grid
-__host__ __device__ __forceinline__ unsigned long long pack_seq(unsigned long long batch, uint32_t nProps, uint32_t nTasks)
-{
-    return (batch << 24) | (static_cast<unsigned long long>(nTasks) << 12) | nProps;
+    uint32_t h = 0x27D4EB2Fu;
+    for (uint32_t i = 0; i < 16; ++i)
+    {
+        if (i != 14) { h ^= w[i] * stream_weight(i); }
+    }
+    return h;
 }
 
-struct HostMailbox   // pinned, mapped host memory
-{
-    volatile unsigned long long seq;      // pack_seq(...) of the batch now posted; kExitSeq = leave
-    uint32_t pad[14];
-    TaskRecord tasks[2 * kMaxPersistentBatch * kMaxCluster]; // record of task t for CTA rank q at [t * nSeg + q]
-    HostOutcome outcomes[kMaxPersistentBatch];
-};
-
-struct DeviceMailbox // device memory
-{
-    unsigned long long seq;               // same word, re-published by CTA 0 for the rest of the grid
-    unsigned int doneCtas;                // CTAs that finished all their tasks of the current batch
-    unsigned int exitFlag;
-    unsigned long long busyNs;            // sum over batches of (last CTA done - batch seen), globaltimer
-    unsigned long long batchStartNs;
-    unsigned long long dbg[8];            // debug accumulators (ns): 0 poll->release, 1 release->task start,
-                                          // 2 task duration, 3 tasks, 4 batches, 5 CTA 0 all-done wait,
-                                          // 6 max release->task end, 7 last release time
-};
-
-// Mailbox reads must never be served from L1: the same addresses carry a new batch every few
+// Mailbox reads must never be served from L1: the same addresses carry a new record every few
 // microseconds.  Host memory: ld.volatile (system scope, uncached).
 __device__ __forceinline__ uint4 ld_host_u4(const void *p)
 {
@@ -628,157 +719,170 @@ __device__ __forceinline__ uint4 ld_host_u4(const void *p)
     asm volatile("ld.volatile.global.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "l"(p));
     return v;
 }
-__device__ __forceinline__ unsigned long long ld_sys_u64(const volatile unsigned long long *p)
+
+static const unsigned long long kDoorbellExit = 1ull << 63;
+
+struct StreamParams
 {
-    unsigned long long v;
-    asm volatile("ld.relaxed.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
-    return v;
-}
-__device__ __forceinline__ unsigned long long ld_relaxed_gpu_u64(const unsigned long long *p)
+    const StreamRecord *slots;                 // pinned host memory: record rings of the worker clusters
+    const volatile unsigned long long *doorbell; // pinned host memory: kDoorbellExit retires the mirror CTA
+    HostOutcome *outcomes;                     // pinned host memory
+    volatile unsigned long long *commitsMirror; // pinned host memory: stats->commitsDone as last seen by the mirror CTA
+    StreamStats *stats;
+    unsigned long long serial0;                // first serial this grid will see (multiple of nWorkers)
+    unsigned long long idleTimeoutNs;
+    uint32_t nWorkers;                         // worker clusters; cluster nWorkers only mirrors the commit count
+    uint32_t pollSleepNs;
+};
+
+// The mirror CTA tells the host how many CTA-commits are complete.  acquire on the device counter,
+// release towards the host: whoever learns the count from the host may read the rows those commits wrote.
+__device__ __forceinline__ void mirror_loop(const StreamParams &sp)
 {
-    unsigned long long v;
-    asm volatile("ld.relaxed.gpu.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
-    return v;
-}
-__device__ __forceinline__ void st_release_gpu_u64(unsigned long long *p, unsigned long long v)
-{
-    asm volatile("st.release.gpu.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
-}
-__device__ __forceinline__ unsigned int ld_acquire_gpu_u32(const unsigned int *p)
-{
-    unsigned int v;
-    asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
-    return v;
-}
-__device__ __forceinline__ void fence_acq_rel_gpu()
-{
-    asm volatile("fence.acq_rel.gpu;" ::: "memory");
-}
-__device__ __forceinline__ unsigned long long global_timer_ns()
-{
-    unsigned long long t;
-    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
-    return t;
+    if (threadIdx.x != 0) { return; }
+    unsigned long long mirrored = 0ull;
+    const unsigned long long t0 = global_timer_ns();
+    for (uint32_t it = 0;; ++it)
+    {
+        unsigned long long done;
+        asm volatile("ld.acquire.gpu.global.u64 %0, [%1];" : "=l"(done) : "l"(&sp.stats->commitsDone) : "memory");
+        if (done != mirrored)
+        {
+            __threadfence_system();
+            asm volatile("st.volatile.global.u64 [%0], %1;" ::"l"(sp.commitsMirror), "l"(done) : "memory");
+            mirrored = done;
+        }
+        else
+        {
+            __nanosleep(100);
+        }
+        if ((it & 15u) == 0u)
+        {
+            // the host retires us at the end of update(); the workers have their own idle timeout
+            unsigned long long bell;
+            asm volatile("ld.relaxed.sys.global.u64 %0, [%1];" : "=l"(bell) : "l"(sp.doorbell) : "memory");
+            if (bell & kDoorbellExit) { break; }
+            if (global_timer_ns() - t0 > 3600000000000ull) { break; }
+        }
+    }
 }
 
 template <bool HAS_S>
-__global__ void __launch_bounds__(kThreads, 2) eval_persistent_kernel(const __grid_constant__ ModelView mv,
-                                                                   HostMailbox *hbox, DeviceMailbox *dbox,
-                                                                   unsigned long long firstBatch,
-                                                                   unsigned long long idleTimeoutNs)
+__global__ void __launch_bounds__(kThreads, 2) eval_stream_kernel(const __grid_constant__ ModelView mv,
+                                                               const __grid_constant__ StreamParams sp)
 {
     extern __shared__ __align__(128) unsigned char smemRaw[];
     EvalSmem *hdr = reinterpret_cast<EvalSmem*>(smemRaw);
-    __shared__ unsigned long long sSeq;
-    __shared__ __align__(16) TaskRecord sTask;
+    __shared__ __align__(16) StreamRecord sRec;
     cg::cluster_group cluster = cg::this_cluster();
     const uint32_t rank = cluster.block_rank();
     const uint32_t nSeg = mv.nSeg;
     const uint32_t clusterId = blockIdx.x / nSeg;
-    const uint32_t nClusters = gridDim.x / nSeg;
     const uint32_t tid = threadIdx.x;
+    if (clusterId == sp.nWorkers)
+    {
+        if (rank == 0) { mirror_loop(sp); }
+        return;
+    }
+    // lookup tables of the epilogue live in shared memory for the whole update()
+    float *erfS = reinterpret_cast<float*>(smemRaw + 256) + static_cast<size_t>(HAS_S ? 5 : 4) * mv.segPad;
+    float *erfinvS = erfS + ((CGB_ERF_TABLE_SIZE + 3) & ~3);
+    for (uint32_t i = tid; i < CGB_ERF_TABLE_SIZE; i += kThreads) { erfS[i] = mv.erf[i]; }
+    for (uint32_t i = tid; i < CGB_ERFINV_TABLE_SIZE; i += kThreads) { erfinvS[i] = mv.erfinv[i]; }
     if (tid == 0)
     {
         mbar_init(&hdr->bar, 1);
         fence_mbar_init();
     }
     __syncthreads();
+    const uint32_t ticket0 = static_cast<uint32_t>(sp.serial0 / sp.nWorkers);
     uint32_t parity = 0;
-    for (unsigned long long batch = firstBatch;; ++batch)
+    for (uint32_t j = 0;; ++j)
     {
-        // ---- CTA 0 lane 0: wait for the host's sequence word, re-publish it in device memory ----
-        if (blockIdx.x == 0 && tid == 0)
+        const uint32_t want = ticket0 + j + 1u;
+        const StreamRecord *slot = sp.slots + (static_cast<size_t>(clusterId) * kStreamRing + ((want - 1u) % kStreamRing)) * nSeg + rank;
+        // ---- warp 0 polls the slot: 4 lanes x 16 B, valid when the ticket matches and the checksum holds ----
+        unsigned long long tSeen = 0;
+        if (tid < 32)
         {
-            // every CTA must be out of the previous batch (its commits included) before the next starts
-            if (batch != firstBatch)
-            {
-                const unsigned long long tw = global_timer_ns();
-                while (ld_acquire_gpu_u32(&dbox->doneCtas) != gridDim.x) { }
-                const unsigned long long td = global_timer_ns();
-                dbox->busyNs += td - dbox->batchStartNs;
-                dbox->doneCtas = 0u;
-            }
             const unsigned long long t0 = global_timer_ns();
-            unsigned long long seen = ld_sys_u64(&hbox->seq);
-            while ((seen >> 24) != batch && seen != kExitSeq)
+            bool ok = false, dead = false;
+            uint4 w = make_uint4(0u, 0u, 0u, 0u);
+            while (!ok && !dead)
             {
-                if (global_timer_ns() - t0 > idleTimeoutNs) { seen = kExitSeq; break; }
-                seen = ld_sys_u64(&hbox->seq);
+                if (tid < 4) { w = ld_host_u4(reinterpret_cast<const uint4*>(slot) + tid); }
+                uint32_t h = 0u;
+                if (tid < 4)
+                {
+                    h = (w.x * stream_weight(4u * tid)) ^ (w.y * stream_weight(4u * tid + 1u)) ^ (w.w * stream_weight(4u * tid + 3u));
+                    if (tid != 3) { h ^= w.z * stream_weight(4u * tid + 2u); }
+                }
+                h ^= __shfl_xor_sync(0xffffffffu, h, 1);
+                h ^= __shfl_xor_sync(0xffffffffu, h, 2);
+                h = __shfl_sync(0xffffffffu, h, 0) ^ 0x27D4EB2Fu;
+                const uint32_t ticket = __shfl_sync(0xffffffffu, w.y, 3);
+                const uint32_t check = __shfl_sync(0xffffffffu, w.z, 3);
+                ok = (ticket == want) && (check == h);
+                if (!ok)
+                {
+                    dead = __shfl_sync(0xffffffffu, (global_timer_ns() - t0 > sp.idleTimeoutNs) ? 1 : 0, 0) != 0;
+                    if (sp.pollSleepNs) { __nanosleep(sp.pollSleepNs); }
+                }
             }
-            const unsigned long long tr = global_timer_ns();
-            dbox->batchStartNs = tr;
-            dbox->dbg[4] += 1;
-            dbox->dbg[7] = tr;
-            if (seen == kExitSeq) { dbox->exitFlag = 1u; }
-            st_release_gpu_u64(&dbox->seq, seen);
-        }
-        // ---- everyone: wait for the release (relaxed polls with back-off, one fence at the end) ----
-        if (tid == 0)
-        {
-            unsigned long long seen = ld_relaxed_gpu_u64(&dbox->seq);
-            while ((seen >> 24) != batch && seen != kExitSeq)
-            {
-                __nanosleep(64);
-                seen = ld_relaxed_gpu_u64(&dbox->seq);
-            }
-            fence_acq_rel_gpu();
-            sSeq = seen;
-        }
-        __syncthreads();
-        const unsigned long long word = sSeq;
-        if (word == kExitSeq) { break; }
-        const uint32_t nTasks = static_cast<uint32_t>(word >> 12) & 0xfffu;
-
-        for (uint32_t task = clusterId; task < nTasks; task += nClusters)
-        {
-            // every CTA of the cluster pulls its own copy of the 64-byte task record straight from host
-            // memory (uncached reads of one address by several CTAs would queue up a PCIe round trip each)
-            unsigned long long tTask = 0;
-            if (tid == 0 && rank == 0) { tTask = global_timer_ns(); }
             if (tid < 4)
             {
-                reinterpret_cast<uint4*>(&sTask)[tid] = ld_host_u4(reinterpret_cast<const uint4*>(&hbox->tasks[task * nSeg + rank]) + tid);
+                if (dead) { w.x = kStreamExit; } // lane 2's w.x is the type word
+                reinterpret_cast<uint4*>(&sRec)[tid] = w;
             }
-            __syncthreads();
-            unsigned long long tPull = 0;
-            if (tid == 0 && rank == 0) { tPull = global_timer_ns(); }
-            const DevProposal pr = sTask.pr;
-            const uint32_t pi = sTask.pi, part = sTask.part;
-            DevOutcome out;
-            if (process_task<HAS_S, true>(mv, mv.erf, mv.erfinv, mv.annealingTemp, pr, pi, part, task, smemRaw, parity, cluster, rank, &out))
-            {
-                // one 16-byte store across PCIe; word 2 carries the batch id, word 3 a checksum of the
-                // other three, so the polling host can tell a complete record from a stale or torn one
-                const uint32_t w0 = __float_as_uint(out.mass1), w1 = __float_as_uint(out.mass2);
-                const uint32_t w2 = (static_cast<uint32_t>(batch) << 1) | (out.accepted & 1u);
-                const uint32_t w3 = outcome_check(w0, w1, w2);
-                asm volatile("st.volatile.global.v4.u32 [%0], {%1, %2, %3, %4};"
-                             ::"l"(&hbox->outcomes[pi]), "r"(w0), "r"(w1), "r"(w2), "r"(w3) : "memory");
-            }
-            unsigned long long tProc = 0;
-            if (tid == 0 && rank == 0) { tProc = global_timer_ns(); }
-            parity ^= 1u;
-            __syncthreads(); // staging buffers and sTask are free for the next task
-            if (tid == 0 && rank == 0)
-            {
-                const unsigned long long te = global_timer_ns();
-                atomicAdd(&dbox->dbg[0], tPull - tTask);
-                atomicAdd(&dbox->busyNs, 0ull);
-                atomicAdd(reinterpret_cast<unsigned long long*>(&dbox->batchStartNs) + 0, 0ull);
-                atomicAdd(&dbox->dbg[5], tProc - tPull);
-                const unsigned long long tr = *reinterpret_cast<volatile unsigned long long*>(&dbox->dbg[7]);
-                atomicAdd(&dbox->dbg[1], tTask - tr);
-                atomicAdd(&dbox->dbg[2], te - tTask);
-                atomicAdd(&dbox->dbg[3], 1ull);
-                atomicMax(&dbox->dbg[6], te - tr);
-            }
+            if (tid == 0) { tSeen = global_timer_ns(); }
         }
-        // ---- this CTA is done with the batch: commits visible device-wide, then count ----
         __syncthreads();
-        if (tid == 0)
+        if (sRec.type == kStreamExit) { break; }
+        TaskIn in;
+        in.pr.rng = sRec.rng;
+        in.pr.r1 = sRec.r1; in.pr.c1 = sRec.c1; in.pr.r2 = sRec.r2; in.pr.c2 = sRec.c2;
+        in.pr.m1 = sRec.m1; in.pr.m2 = sRec.m2;
+        in.pr.type = sRec.type & 0xffu;
+        in.waitMask = (sRec.type >> 8) & 3u;
+        in.pr.variant = 0u;
+        in.pr.ch = 0.f;
+        in.pr.pad = 0u;
+        in.pi = sRec.piPart & 0x7fffffffu;
+        in.part = sRec.piPart >> 31;
+        in.ver1 = sRec.ver1;
+        in.ver2 = sRec.ver2;
+        const uint32_t batch = sRec.batch;
+        const uint32_t task = (in.pi % kMaxBatch) + in.part * kMaxBatch; // debug phase-clock slot
+        DevOutcome out;
+        unsigned long long verWait = 0;
+        const bool owner = process_task<HAS_S, true>(mv, erfS, erfinvS, mv.annealingTemp, in, task, smemRaw, parity, cluster, rank, &out, &verWait);
+        unsigned long long tPosted = 0;
+        if (owner)
         {
-            __threadfence();
-            atomicAdd(&dbox->doneCtas, 1u);
+            // one 16-byte store across PCIe; word 2 carries the chunk tag, word 3 a checksum of the
+            // other three, so the polling host can tell a complete record from a stale or torn one
+            const uint32_t w0 = __float_as_uint(out.mass1), w1 = __float_as_uint(out.mass2);
+            const uint32_t w2 = (batch << 1) | (out.accepted & 1u);
+            const uint32_t w3 = outcome_check(w0, w1, w2);
+            asm volatile("st.volatile.global.v4.u32 [%0], {%1, %2, %3, %4};"
+                         ::"l"(sp.outcomes + in.pi), "r"(w0), "r"(w1), "r"(w2), "r"(w3) : "memory");
+            tPosted = global_timer_ns();
+        }
+        commit_task<HAS_S>(mv, in, task, smemRaw, cluster, rank, &sp.stats->commitsDone);
+        parity ^= 1u;
+        __syncthreads(); // staging buffers and sRec are free for the next task
+        if (tid == 0 && rank == 0)
+        {
+            const unsigned long long dt = global_timer_ns() - tSeen;
+            atomicAdd(&sp.stats->taskNs, dt);
+            atomicAdd(&sp.stats->tasks, 1ull);
+            atomicMax(&sp.stats->maxTaskNs, dt);
+            atomicAdd(&sp.stats->verWaitNs, verWait);
+            if (owner)
+            {
+                atomicAdd(&sp.stats->decideNs, tPosted - tSeen);
+                atomicAdd(&sp.stats->outcomes, 1ull);
+            }
         }
     }
 }

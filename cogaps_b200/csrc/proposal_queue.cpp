@@ -38,12 +38,13 @@ void ProposalQueue::init(uint64_t nElements, uint64_t nPatterns, cgb_randstate *
     mUseCachedRng = false;
 }
 
-void ProposalQueue::populate(AtomicDomain &domain, unsigned limit)
+void ProposalQueue::populate(AtomicDomain &domain, unsigned limit, SinkFn sink, void *sinkCtx)
 {
     bool success = true;
     mNumProcessed = 0;
     while (mNumProcessed < limit && success)
     {
+        const size_t before = mQueue.size();
         if (!makeProposal(domain))
         {
             success = false;
@@ -52,6 +53,8 @@ void ProposalQueue::populate(AtomicDomain &domain, unsigned limit)
         else
         {
             ++mNumProcessed;
+            // same-bin moves / exchanges succeed without queueing anything
+            if (sink != nullptr && mQueue.size() > before) { sink(sinkCtx, mQueue.back(), before); }
         }
     }
 }

@@ -32,7 +32,10 @@ class ProposalQueue
 {
 public:
     void init(uint64_t nElements, uint64_t nPatterns, cgb_randstate *rs, float alpha, float lambda);
-    void populate(AtomicDomain &domain, unsigned limit);   // ProposalQueue.cpp:53-76
+    // called for every proposal the moment it is queued, so the device can start on it while the rest of
+    // the batch is still being generated
+    typedef void (*SinkFn)(void *ctx, const HostProposal &prop, size_t index);
+    void populate(AtomicDomain &domain, unsigned limit, SinkFn sink = nullptr, void *sinkCtx = nullptr); // ProposalQueue.cpp:53-76
     void clear();                                           // :78-85
     unsigned nProcessed() const { return mNumProcessed; }
     std::vector<HostProposal> &entries() { return mQueue; }
@@ -106,15 +109,36 @@ struct cgb_sampler
     uint64_t phaseTasks;
     cudaEvent_t evStart, evStop;
 
-    // persistent-kernel mode: mailbox between the host generator and the resident grid
+    // per-row commit counts: the device's counter and what the host knows it will reach
+    uint32_t *dRowVersion;
+    std::vector<uint32_t> rowVersion;
+    // commit tracking: the device counts completed CTA-commits, one extra CTA mirrors the count into
+    // host memory.  rowPending[r] = value commitsExpected had right after the last commit to row r was
+    // recorded; once the mirror has been seen equal to commitsExpected (commitsProven), every commit up
+    // to that ordinal is complete and tasks on those rows need no rowVersion check.
+    volatile unsigned long long *hCommitsMirror; // pinned + mapped
+    std::vector<uint64_t> rowPending;
+    uint64_t commitsExpected, commitsProven;
+
+    // resident-kernel mode: task records streamed to the grid through pinned host memory
     bool usePersistent;
     bool persistentRunning;
-    void *hMailbox;               // cgb::HostMailbox, pinned + mapped
-    void *dMailbox;               // cgb::DeviceMailbox
-    unsigned long long mailSeq;   // id of the last batch posted
-    int persistentGrid;
+    void *hSlots;                 // cgb::StreamRecord[nClusters][kStreamRing][nSeg] + the doorbell line, pinned + mapped
+    size_t nSlotRecords;
+    void *hStreamOutcomes;        // HostOutcome[kMaxPersistentBatch], pinned + mapped
+    void *dStreamStats;           // cgb::StreamStats
+    unsigned long long mailSeq;   // tag of the last chunk posted
+    unsigned long long streamSerial; // next task serial; serial % nClusters = cluster, serial / nClusters + 1 = ticket
+    int persistentGrid;           // CTAs of the resident grid (0 until first launch)
+    uint32_t nClusters;           // worker clusters of the resident grid (one more cluster mirrors the commit count)
     double lastPostTime;
-    uint32_t lastPostedTasks;
+    uint32_t chunkTag;            // low 31 bits of mailSeq for the chunk being posted
+    uint32_t chunkPosted;         // proposals posted in this chunk
+    size_t chunkBase;             // queue index of the chunk's first proposal
+    std::vector<uint64_t> slotOwner;      // per (cluster, ring slot): (mailSeq << 32) | proposal index of the last record
+    std::vector<cgb::DevProposal> posted; // what was sent for each proposal of the chunk (masses as posted)
+    std::vector<uint8_t> arrived;         // outcome of proposal i of the chunk already collected
+    std::vector<cgb::DevOutcome> collected;
 };
 
 #endif // CGB_SAMPLER_H
