@@ -99,7 +99,8 @@ extern "C" const char *cgb_build_report(void)
     static std::string s;
     s = "cogaps_b200: sm_100a; eval kernel: " + std::to_string(kThreads) + " threads/CTA, "
         + std::to_string(kVec) + "-float vectors, clusters <= " + std::to_string(kMaxCluster)
-        + ", <= " + std::to_string(kMaxBatch) + " proposals/launch; TMA bulk staging; no CPU fallback";
+        + ", <= " + std::to_string(kMaxBatch) + " proposals/launch; TMA bulk staging; sparse model: "
+        + std::to_string(kSparseThreads) + " threads/CTA; no CPU fallback";
     return s.c_str();
 }
 
@@ -288,6 +289,7 @@ extern "C" void cgb_sampler_destroy(cgb_sampler *s)
     cudaFree(s->dD); cudaFree(s->dS); cudaFree(s->dAP); cudaFree(s->dM); cudaFree(s->dColNonzero);
     cudaFree(s->dPartials); cudaFree(s->dTickets); cudaFree(s->dReducePartials); cudaFree(s->dPhaseClocks);
     cudaFree(s->dRowVersion); cudaFree(s->dStreamStats);
+    cudaFree(s->dSpRowPtr); cudaFree(s->dSpIdx); cudaFree(s->dSpVal); cudaFree(s->dMrows); cudaFree(s->dZ1); cudaFree(s->dZ2);
     if (s->hCommitsMirror) { cudaFreeHost(const_cast<unsigned long long*>(s->hCommitsMirror)); }
     if (s->hSlots) { cudaFreeHost(s->hSlots); }
     if (s->hStreamOutcomes) { cudaFreeHost(s->hStreamOutcomes); }
@@ -310,7 +312,6 @@ extern "C" int cgb_sampler_create(const float *data, uint32_t nrow, uint32_t nco
     CGB_CHECK(data && params && rs && out, "cgb_sampler_create: NULL argument");
     CGB_CHECK(params->struct_size == sizeof(cgb_params), "cgb_sampler_create: cgb_params ABI mismatch");
     CGB_CHECK(params->nPatterns >= 1, "cgb_sampler_create: nPatterns must be >= 1");
-    if (params->useSparseOptimization) { return fail(CGB_EUNSUPPORTED, "SparseNormalModel is not on the device path yet"); }
     if (!params->asynchronousUpdates) { return fail(CGB_EUNSUPPORTED, "the device path is the asynchronous sampler; asynchronousUpdates must be true"); }
     CGB_TRY(checkSubset(params, nrow, ncol));
     CGB_TRY(ensureDevice());
@@ -319,6 +320,8 @@ extern "C" int cgb_sampler_create(const float *data, uint32_t nrow, uint32_t nco
     if (!s) { return fail(CGB_ENOMEM, "cgb_sampler_create: out of memory"); }
     std::memset(static_cast<void*>(&s->counters), 0, sizeof(s->counters));
     s->dD = s->dS = s->dAP = s->dM = nullptr;
+    s->sparse = params->useSparseOptimization != 0;
+    s->dSpRowPtr = s->dSpIdx = nullptr; s->dSpVal = s->dMrows = s->dZ1 = s->dZ2 = nullptr; s->ldR = 0;
     s->dColNonzero = nullptr; s->dPartials = nullptr; s->dTickets = nullptr; s->dReducePartials = nullptr;
     s->usePersistent = envInt("COGAPS_PERSISTENT", 1) != 0; s->persistentRunning = false;
     s->hSlots = nullptr; s->nSlotRecords = 0; s->hStreamOutcomes = nullptr; s->dStreamStats = nullptr; s->dRowVersion = nullptr;
@@ -364,6 +367,30 @@ extern "C" int cgb_sampler_create(const float *data, uint32_t nrow, uint32_t nco
         s->dataSparsity = 1.f - static_cast<float>(nnz) / size;
     }
     chooseSegments(s);
+    std::vector<uint32_t> spPtr, spIdx;
+    std::vector<float> spVal;
+    if (s->sparse)
+    {
+        // SparseMatrix (data_structures/SparseMatrix.cpp, SparseVector.cpp:20-35): the positive entries of every
+        // sampler row, ascending index
+        s->nSeg = 1;
+        s->ldR = roundUp(s->k, 4);
+        spPtr.assign(s->nRows + 1, 0u);
+        for (uint32_t r = 0; r < s->nRows; ++r)
+        {
+            const float *row = host.data() + static_cast<size_t>(r) * s->ld;
+            for (uint32_t l = 0; l < s->L; ++l)
+            {
+                if (row[l] > 0.f)
+                {
+                    spIdx.push_back(l);
+                    spVal.push_back(row[l]);
+                }
+            }
+            if (spIdx.size() > 0xFFFFFFF0ull) { delete s; return fail(CGB_EUNSUPPORTED, "cgb_sampler_create: more than 2^32 non-zeros"); }
+            spPtr[r + 1] = static_cast<uint32_t>(spIdx.size());
+        }
+    }
 
     int rc = CGB_OK;
     do
@@ -373,7 +400,26 @@ extern "C" int cgb_sampler_create(const float *data, uint32_t nrow, uint32_t nco
 #define CGB_CUDA_BREAK(call) { cudaError_t e__ = (call); if (e__ != cudaSuccess) { rc = fail(e__ == cudaErrorMemoryAllocation ? CGB_ENOMEM : CGB_ECUDA, std::string(#call) + ": " + cudaGetErrorString(e__)); break; } }
         CGB_CUDA_BREAK(cudaStreamCreateWithFlags(&s->stream, cudaStreamNonBlocking));
         CGB_CUDA_BREAK(cudaMalloc(&s->dD, matBytes));
-        CGB_CUDA_BREAK(cudaMalloc(&s->dAP, matBytes));
+        if (!s->sparse) { CGB_CUDA_BREAK(cudaMalloc(&s->dAP, matBytes)); }
+        if (s->sparse)
+        {
+            const size_t nnz = spIdx.size();
+            CGB_CUDA_BREAK(cudaMalloc(&s->dSpRowPtr, sizeof(uint32_t) * (s->nRows + 1)));
+            CGB_CUDA_BREAK(cudaMalloc(&s->dSpIdx, sizeof(uint32_t) * (nnz ? nnz : 1)));
+            CGB_CUDA_BREAK(cudaMalloc(&s->dSpVal, sizeof(float) * (nnz ? nnz : 1)));
+            CGB_CUDA_BREAK(cudaMalloc(&s->dMrows, sizeof(float) * s->nRows * s->ldR));
+            CGB_CUDA_BREAK(cudaMalloc(&s->dZ1, sizeof(float) * s->k));
+            CGB_CUDA_BREAK(cudaMalloc(&s->dZ2, sizeof(float) * s->k * s->k));
+            CGB_CUDA_BREAK(cudaMemcpy(s->dSpRowPtr, spPtr.data(), sizeof(uint32_t) * (s->nRows + 1), cudaMemcpyHostToDevice));
+            if (nnz)
+            {
+                CGB_CUDA_BREAK(cudaMemcpy(s->dSpIdx, spIdx.data(), sizeof(uint32_t) * nnz, cudaMemcpyHostToDevice));
+                CGB_CUDA_BREAK(cudaMemcpy(s->dSpVal, spVal.data(), sizeof(float) * nnz, cudaMemcpyHostToDevice));
+            }
+            CGB_CUDA_BREAK(cudaMemset(s->dMrows, 0, sizeof(float) * s->nRows * s->ldR));
+            CGB_CUDA_BREAK(cudaMemset(s->dZ1, 0, sizeof(float) * s->k));
+            CGB_CUDA_BREAK(cudaMemset(s->dZ2, 0, sizeof(float) * s->k * s->k));
+        }
         CGB_CUDA_BREAK(cudaMalloc(&s->dM, facBytes));
         CGB_CUDA_BREAK(cudaMalloc(&s->dColNonzero, sizeof(int) * s->k));
         CGB_CUDA_BREAK(cudaMalloc(&s->dPartials, sizeof(AlphaPair) * 2 * kMaxPersistentBatch));
@@ -397,7 +443,7 @@ extern "C" int cgb_sampler_create(const float *data, uint32_t nrow, uint32_t nco
         CGB_CUDA_BREAK(cudaEventCreate(&s->evStart));
         CGB_CUDA_BREAK(cudaEventCreate(&s->evStop));
         CGB_CUDA_BREAK(cudaMemcpy(s->dD, host.data(), matBytes, cudaMemcpyHostToDevice));
-        CGB_CUDA_BREAK(cudaMemset(s->dAP, 0, matBytes));
+        if (!s->sparse) { CGB_CUDA_BREAK(cudaMemset(s->dAP, 0, matBytes)); }
         CGB_CUDA_BREAK(cudaMemset(s->dM, 0, facBytes));
         CGB_CUDA_BREAK(cudaMemset(s->dColNonzero, 0, sizeof(int) * s->k));
         CGB_CUDA_BREAK(cudaMemset(s->dTickets, 0, sizeof(uint32_t) * kMaxPersistentBatch));
@@ -405,6 +451,7 @@ extern "C" int cgb_sampler_create(const float *data, uint32_t nrow, uint32_t nco
         CGB_CUDA_BREAK(cudaFuncSetAttribute(eval_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
         CGB_CUDA_BREAK(cudaFuncSetAttribute(eval_stream_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024 - 1024));
         CGB_CUDA_BREAK(cudaFuncSetAttribute(eval_stream_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024 - 1024));
+        CGB_CUDA_BREAK(cudaFuncSetAttribute(eval_stream_sparse_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
         if (s->smemBytes + kStreamTableBytes > 226u * 1024u)
         {
             rc = fail(CGB_EUNSUPPORTED, "row length too large for one cluster of staged segments (raise COGAPS_MAX_CLUSTER)");
@@ -432,6 +479,7 @@ extern "C" int cgb_sampler_set_uncertainty(cgb_sampler *s, const float *unc, uin
                                            const cgb_params *params)
 {
     CGB_CHECK(s && unc && params, "cgb_sampler_set_uncertainty: NULL argument");
+    if (s->sparse) { return CGB_OK; } // SparseNormalModel::setUncertainty is a nop (SparseNormalModel.h:92-98)
     CGB_CUDA(cudaSetDevice(s->device));
     std::vector<float> host;
     uint32_t nRows, L, ld;
@@ -463,6 +511,22 @@ extern "C" int cgb_sampler_set_matrix(cgb_sampler *s, const float *mat)
     {
         for (uint32_t c = 0; c < s->k; ++c) { host[static_cast<size_t>(c) * s->ldM + r] = mat[static_cast<size_t>(r) * s->k + c]; }
     }
+    if (s->sparse)
+    {
+        // HybridMatrix::operator=(Matrix): the row copy keeps the value, the column copy drops it below epsilon
+        std::vector<float> rows(static_cast<size_t>(s->nRows) * s->ldR, 0.f);
+        for (uint32_t r = 0; r < s->nRows; ++r)
+        {
+            for (uint32_t c = 0; c < s->k; ++c)
+            {
+                const float v = mat[static_cast<size_t>(r) * s->k + c];
+                rows[static_cast<size_t>(r) * s->ldR + c] = v;
+                if (v < kEpsilon) { host[static_cast<size_t>(c) * s->ldM + r] = 0.f; }
+            }
+        }
+        CGB_CUDA(cudaMemcpyAsync(s->dMrows, rows.data(), rows.size() * sizeof(float), cudaMemcpyHostToDevice, s->stream));
+        CGB_CUDA(cudaStreamSynchronize(s->stream));
+    }
     CGB_CUDA(cudaMemcpyAsync(s->dM, host.data(), host.size() * sizeof(float), cudaMemcpyHostToDevice, s->stream));
     CGB_CUDA(cudaStreamSynchronize(s->stream));
     return refreshColNonzero(s);
@@ -481,9 +545,20 @@ extern "C" int cgb_sampler_sync(cgb_sampler *s, const cgb_sampler *other)
     CGB_CHECK(other->nRows == s->L && other->L == s->nRows && other->k == s->k, "cgb_sampler_sync: shapes do not transpose");
     CGB_CUDA(cudaSetDevice(s->device));
     // the other sampler's stream may still hold its last commit
+    CGB_CHECK(other->sparse == s->sparse, "cgb_sampler_sync: one sampler is sparse, the other dense");
     CGB_CUDA(cudaStreamSynchronize(other->stream));
-    dim3 grid((s->L + 31) / 32, (s->nRows + 31) / 32);
-    transpose_kernel<<<grid, 256, 0, s->stream>>>(s->dAP, other->dAP, s->nRows, s->L, s->ld, other->ld);
+    if (s->sparse)
+    {
+        // SparseNormalModel::sync (SparseNormalModel.cpp:27-31): point at the other factor, rebuild Z1 / Z2
+        const uint32_t blocks = s->k + s->k * (s->k + 1) / 2;
+        sparse_tables_kernel<<<blocks, kSparseThreads, 0, s->stream>>>(other->dMrows, other->ldR, other->dM, other->ldM,
+            other->nRows, s->k, s->dZ1, s->dZ2);
+    }
+    else
+    {
+        dim3 grid((s->L + 31) / 32, (s->nRows + 31) / 32);
+        transpose_kernel<<<grid, 256, 0, s->stream>>>(s->dAP, other->dAP, s->nRows, s->L, s->ld, other->ld);
+    }
     ++g_kernelLaunches;
     CGB_CUDA(cudaGetLastError());
     // canUseGibbs flags of the other factor, constant for the whole of our next update()
@@ -497,6 +572,7 @@ extern "C" int cgb_sampler_sync(cgb_sampler *s, const cgb_sampler *other)
 extern "C" int cgb_sampler_extra_initialization(cgb_sampler *s)
 {
     CGB_CHECK(s && s->other, "cgb_sampler_extra_initialization: sync() has not been called");
+    if (s->sparse) { return CGB_OK; } // SparseNormalModel::extraInitialization is a nop (SparseNormalModel.cpp:33-37)
     CGB_CUDA(cudaSetDevice(s->device));
     CGB_CUDA(cudaStreamSynchronize(s->other->stream));
     dim3 grid((s->L + 255) / 256, s->nRows);
@@ -524,6 +600,15 @@ static void fillModelView(const cgb_sampler *s, ModelView &mv)
     mv.tickets = s->dTickets;
     mv.phaseClocks = s->dPhaseClocks;
     mv.rowVersion = s->dRowVersion;
+    mv.spRowPtr = s->dSpRowPtr;
+    mv.spIdx = s->dSpIdx;
+    mv.spVal = s->dSpVal;
+    mv.Mrows = s->dMrows;
+    mv.otherMrows = s->other->dMrows;
+    mv.Z1 = s->dZ1;
+    mv.Z2 = s->dZ2;
+    mv.ldR = s->ldR;
+    mv.beta = 100.f; // SparseNormalModel.h:77
     mv.nRows = s->nRows;
     mv.L = s->L;
     mv.k = s->k;
@@ -540,6 +625,7 @@ static void fillModelView(const cgb_sampler *s, ModelView &mv)
 
 static size_t evalSmemBytes(const cgb_sampler *s)
 {
+    if (s->sparse) { return 256 + (static_cast<size_t>(s->ldR) + 4 * kSparseThreads) * sizeof(float); }
     return 256 + static_cast<size_t>(s->hasS ? 5 : 4) * s->segPad * sizeof(float);
 }
 
@@ -556,6 +642,25 @@ static int launchEval(cgb_sampler *s, EvalParams &params)
     }
     params.nTasks = params.nProps + nExtra;
 
+    if (s->sparse)
+    {
+        const double t0s = nowSeconds();
+        if (s->timeKernels) { CGB_CUDA(cudaEventRecord(s->evStart, s->stream)); }
+        eval_sparse_kernel<<<params.nTasks, kSparseThreads, evalSmemBytes(s), s->stream>>>(params);
+        ++g_kernelLaunches;
+        CGB_CUDA(cudaGetLastError());
+        if (s->timeKernels) { CGB_CUDA(cudaEventRecord(s->evStop, s->stream)); }
+        CGB_CUDA(cudaStreamSynchronize(s->stream));
+        if (s->timeKernels)
+        {
+            float ms = 0.f;
+            CGB_CUDA(cudaEventElapsedTime(&ms, s->evStart, s->evStop));
+            s->counters.secondsKernel += static_cast<double>(ms) * 1e-3;
+        }
+        s->counters.secondsDeviceWait += nowSeconds() - t0s;
+        s->counters.nBatches += 1;
+        return CGB_OK;
+    }
     cudaLaunchConfig_t cfg;
     cfg = cudaLaunchConfig_t();
     cfg.gridDim = dim3(s->nSeg, params.nTasks, 1);
@@ -753,7 +858,7 @@ static size_t streamSmemBytes(const cgb_sampler *s) { return evalSmemBytes(s) + 
 static int startPersistent(cgb_sampler *s)
 {
     cudaLaunchConfig_t cfg = cudaLaunchConfig_t();
-    cfg.blockDim = dim3(kThreads, 1, 1);
+    cfg.blockDim = dim3(s->sparse ? kSparseThreads : kThreads, 1, 1);
     cfg.dynamicSmemBytes = streamSmemBytes(s);
     cfg.stream = s->stream;
     cudaLaunchAttribute attr[1];
@@ -769,7 +874,8 @@ static int startPersistent(cgb_sampler *s)
         // the last cluster only mirrors the commit count, the others are workers
         cfg.gridDim = dim3(s->nSeg, 1, 1);
         int maxClusters = 0;
-        if (s->hasS) { CGB_CUDA(cudaOccupancyMaxActiveClusters(&maxClusters, eval_stream_kernel<true>, &cfg)); }
+        if (s->sparse) { CGB_CUDA(cudaOccupancyMaxActiveClusters(&maxClusters, eval_stream_sparse_kernel, &cfg)); }
+        else if (s->hasS) { CGB_CUDA(cudaOccupancyMaxActiveClusters(&maxClusters, eval_stream_kernel<true>, &cfg)); }
         else { CGB_CUDA(cudaOccupancyMaxActiveClusters(&maxClusters, eval_stream_kernel<false>, &cfg)); }
         const int cap = envInt("COGAPS_PERSISTENT_CLUSTERS", 0);
         if (cap > 1 && cap < maxClusters) { maxClusters = cap; }
@@ -806,7 +912,8 @@ static int startPersistent(cgb_sampler *s)
     std::fill(s->rowPending.begin(), s->rowPending.end(), 0ull);
     s->commitsExpected = s->commitsProven = 0;
     CGB_CUDA(cudaEventRecord(s->evStart, s->stream));
-    if (s->hasS) { CGB_CUDA(cudaLaunchKernelEx(&cfg, eval_stream_kernel<true>, mv, sp)); }
+    if (s->sparse) { CGB_CUDA(cudaLaunchKernelEx(&cfg, eval_stream_sparse_kernel, mv, sp)); }
+    else if (s->hasS) { CGB_CUDA(cudaLaunchKernelEx(&cfg, eval_stream_kernel<true>, mv, sp)); }
     else { CGB_CUDA(cudaLaunchKernelEx(&cfg, eval_stream_kernel<false>, mv, sp)); }
     CGB_CUDA(cudaEventRecord(s->evStop, s->stream));
     ++g_kernelLaunches;
@@ -1203,12 +1310,22 @@ extern "C" int cgb_sampler_chisq(const cgb_sampler *cs, float *out)
     cgb_sampler *s = const_cast<cgb_sampler*>(cs);
     CGB_CUDA(cudaSetDevice(s->device));
     const int blocks = static_cast<int>(std::min<uint32_t>(kReduceBlocks, s->nRows));
-    chisq_kernel<<<blocks, 256, 0, s->stream>>>(s->dD, s->hasS ? s->dS : nullptr, s->dAP, s->nRows, s->L, s->ld, s->dReducePartials);
+    if (s->sparse)
+    {
+        CGB_CHECK(s->other != nullptr, "cgb_sampler_chisq: sync() has not been called");
+        CGB_CUDA(cudaStreamSynchronize(s->other->stream));
+        sparse_chisq_kernel<<<blocks, kSparseThreads, s->ldR * sizeof(float), s->stream>>>(s->dD, s->ld, s->dMrows, s->other->dMrows,
+            s->ldR, s->nRows, s->L, s->k, s->dReducePartials);
+    }
+    else
+    {
+        chisq_kernel<<<blocks, 256, 0, s->stream>>>(s->dD, s->hasS ? s->dS : nullptr, s->dAP, s->nRows, s->L, s->ld, s->dReducePartials);
+    }
     ++g_kernelLaunches;
     CGB_CUDA(cudaGetLastError());
     double t = 0.0;
     CGB_TRY(sumPartials(s, blocks, &t));
-    *out = static_cast<float>(t);
+    *out = s->sparse ? static_cast<float>(t) * 100.f : static_cast<float>(t);
     return CGB_OK;
 }
 
@@ -1237,8 +1354,19 @@ extern "C" int cgb_sampler_get_matrix(const cgb_sampler *s, float *out)
 {
     CGB_CHECK(s && out, "cgb_sampler_get_matrix: NULL argument");
     CGB_CUDA(cudaSetDevice(s->device));
-    std::vector<float> host(static_cast<size_t>(s->k) * s->ldM);
     CGB_CUDA(cudaStreamSynchronize(s->stream));
+    if (s->sparse)
+    {
+        // HybridMatrix -> Matrix conversions read the row copy (data_structures/Matrix.cpp)
+        std::vector<float> rows(static_cast<size_t>(s->nRows) * s->ldR);
+        CGB_CUDA(cudaMemcpy(rows.data(), s->dMrows, rows.size() * sizeof(float), cudaMemcpyDeviceToHost));
+        for (uint32_t r = 0; r < s->nRows; ++r)
+        {
+            for (uint32_t c = 0; c < s->k; ++c) { out[static_cast<size_t>(r) * s->k + c] = rows[static_cast<size_t>(r) * s->ldR + c]; }
+        }
+        return CGB_OK;
+    }
+    std::vector<float> host(static_cast<size_t>(s->k) * s->ldM);
     CGB_CUDA(cudaMemcpy(host.data(), s->dM, host.size() * sizeof(float), cudaMemcpyDeviceToHost));
     for (uint32_t r = 0; r < s->nRows; ++r)
     {
@@ -1284,6 +1412,7 @@ extern "C" int cgb_sampler_get_atoms(const cgb_sampler *s, uint64_t *pos, float 
 extern "C" int cgb_sampler_get_ap_row(const cgb_sampler *s, uint32_t row, float *out)
 {
     CGB_CHECK(s && out && row < s->nRows, "cgb_sampler_get_ap_row: bad argument");
+    if (s->sparse) { return fail(CGB_EUNSUPPORTED, "cgb_sampler_get_ap_row: the sparse model keeps no AP matrix"); }
     CGB_CUDA(cudaSetDevice(s->device));
     CGB_CUDA(cudaStreamSynchronize(s->stream));
     CGB_CUDA(cudaMemcpy(out, s->dAP + static_cast<size_t>(row) * s->ld, sizeof(float) * s->L, cudaMemcpyDeviceToHost));

@@ -6,7 +6,8 @@
 
 namespace cgb {
 
-static const int kThreads = 512;      // threads per CTA of the eval kernel (16 warps)
+static const int kThreads = 512;      // threads per CTA of the dense eval kernel (16 warps)
+static const int kSparseThreads = 256; // threads per CTA of the sparse eval kernel: one lane per element of a 256-wide group
 static const int kVec = 4;            // floats per vector access (16 B)
 static const int kMaxBatch = 384;     // proposals per launch carried in kernel-parameter space
 static const int kMaxCluster = 8;     // portable cluster limit
@@ -60,6 +61,17 @@ struct ModelView
     uint32_t *tickets;       // [kMaxPersistentBatch]
     unsigned long long *phaseClocks; // debug: [kMaxBatch][kPhaseSlots] SM clock at each phase, or nullptr
     uint32_t *rowVersion;    // [nRows] CTA-commits applied to each row (AP row + its factor elements)
+    // SparseNormalModel only (all nullptr / 0 for the dense model)
+    const uint32_t *spRowPtr;   // [nRows + 1] non-zeros of each sampler row of D ...
+    const uint32_t *spIdx;      // [nnz]      ... their scan index, ascending within a row
+    const float *spVal;         // [nnz]      ... and value (> 0)
+    float *Mrows;               // [nRows][ldR] row copy of the factor (HybridMatrix::mRows: never zeroed below epsilon;
+                                //             M above is mCols: values below epsilon stored as 0)
+    const float *otherMrows;    // [L][ldR]
+    const float *Z1;            // [k]     lookup tables of the other factor (generateLookupTables)
+    const float *Z2;            // [k][k]
+    uint32_t ldR;               // floats per row of Mrows (k rounded up to 4)
+    float beta;
     uint32_t nRows, L, k;
     uint32_t ld, ldM, ldOther;
     uint32_t seg;            // floats per segment (multiple of 4)

@@ -192,9 +192,13 @@ struct PreLog
 // The serial tail of one proposal: alpha parameters -> gibbsMass / accept test -> deltas
 // (AsynchronousGibbsSampler.h:126-219).  One lane runs it; kept out of line so its registers (f64 log,
 // divisions) do not inflate the allocation of the 255 lanes that only scan.
+// SPARSE: M1/M2 are the row-copy values, C1/C2 the column-copy values of the two elements; both copies are
+// rewritten with HybridMatrix::add / set semantics (data_structures/HybridMatrix.cpp:25-39).
+template <bool SPARSE>
 __device__ __noinline__ void decide(const ModelView &mv, const float *erfT, const float *erfinvT, float T, const DevProposal &pr, uint32_t part, bool twoRow,
-                                    float s, float mu, float M1, float M2, int can1, int can2, const PreLog &pre, Verdict *v)
+                                    float s, float mu, float M1, float M2, float C1, float C2, int can1, int can2, const PreLog &pre, Verdict *v)
 {
+    bool add1 = false, add2 = false; // element changed by changeMatrix (add) rather than safelyChangeMatrix (set)
     const uint32_t type = pr.type;
     const uint32_t r1 = pr.r1, c1 = pr.c1, r2 = pr.r2, c2 = pr.c2;
     const float m1 = pr.m1, m2 = pr.m2;
@@ -240,6 +244,7 @@ __device__ __noinline__ void decide(const ModelView &mv, const float *erfT, cons
             d1 = mass;                      // changeMatrix: no clamp
             M1 = fadd(M1, mass);
             ch1 = true;
+            add1 = true;
         }
     }
     else if (type == 'D')
@@ -287,6 +292,7 @@ __device__ __noinline__ void decide(const ModelView &mv, const float *erfT, cons
             d2 = m1;                        // changeMatrix(r2, c2, mass)
             M2 = fadd(M2, m1);
             ch2 = true;
+            add2 = true;
         }
     }
     else if (type == 'E')
@@ -313,8 +319,26 @@ __device__ __noinline__ void decide(const ModelView &mv, const float *erfT, cons
             }
         }
     }
-    if (ch1) { mv.M[static_cast<size_t>(c1) * mv.ldM + r1] = M1; }
-    if (ch2) { mv.M[static_cast<size_t>(c2) * mv.ldM + r2] = M2; }
+    if (SPARSE)
+    {
+        if (ch1)
+        {
+            mv.Mrows[static_cast<size_t>(r1) * mv.ldR + c1] = M1;
+            const float cv = add1 ? fadd(C1, d1) : M1;
+            mv.M[static_cast<size_t>(c1) * mv.ldM + r1] = (cv < kEpsilon) ? 0.f : cv;
+        }
+        if (ch2)
+        {
+            mv.Mrows[static_cast<size_t>(r2) * mv.ldR + c2] = M2;
+            const float cv = add2 ? fadd(C2, d2) : M2;
+            mv.M[static_cast<size_t>(c2) * mv.ldM + r2] = (cv < kEpsilon) ? 0.f : cv;
+        }
+    }
+    else
+    {
+        if (ch1) { mv.M[static_cast<size_t>(c1) * mv.ldM + r1] = M1; }
+        if (ch2) { mv.M[static_cast<size_t>(c2) * mv.ldM + r2] = M2; }
+    }
     if (twoRow)
     {
         // own row is row `part`; the other row is committed through global memory
@@ -552,7 +576,7 @@ __device__ __forceinline__ bool process_task(const ModelView &mv, const float *e
             pre.state0 = pr.rng;
             pre.logFirst = hdr->preLog[0];
             pre.logSecond = hdr->preLog[1];
-            decide(mv, erfT, erfinvT, annealingTemp, pr, part, twoRow, s, mu, M1, M2, can1, can2, pre, &v);
+            decide<false>(mv, erfT, erfinvT, annealingTemp, pr, part, twoRow, s, mu, M1, M2, 0.f, 0.f, can1, can2, pre, &v);
             *outp = v.out;
             owner = true;
         }
@@ -648,6 +672,293 @@ __device__ __forceinline__ void commit_task(const ModelView &mv, const TaskIn &i
         }
     }
     stamp(mv, task, rank, 8); // commit done
+}
+
+// ------------------------------------------------------------------------------------------------
+// SparseNormalModel (gibbs_sampler/SparseNormalModel.cpp:153-292): no AP matrix; the scan visits the
+// non-zeros of the data row whose factor-column entry is non-zero too and needs, for each, the dot of two
+// factor ROWS (k floats, a gather).  One CTA of 256 threads per (proposal, row).
+//
+// Order of the sums (what oracle mode "device" restates): the visited elements, in ascending scan index,
+// are numbered e = 0,1,...; element e belongs to lane e % 256; a lane adds its elements in order; lanes
+// combine by the xor butterflies of the dense kernel.  The reference walks the same elements in the same
+// order but adds them into one running sum (fp32 re-association only).
+// ------------------------------------------------------------------------------------------------
+struct SparseSmem
+{
+    float warpS[kSparseThreads / 32];
+    float warpMu[kSparseThreads / 32];
+    uint32_t warpCnt[kSparseThreads / 32];
+    float baseS, baseMu;      // Z-table terms of (s, s_mu)
+    Decision dec;
+    float preLog[2];
+    uint32_t pad[2];
+};
+
+// dot of two factor rows, ascending, mul and add rounded separately (gaps::dot, oracle mode "device")
+__device__ __forceinline__ float row_dot(const float *a, const float *b, uint32_t k)
+{
+    float acc = 0.f;
+    for (uint32_t i = 0; i < k; ++i) { acc = fadd(acc, fmul(a[i], b[i])); }
+    return acc;
+}
+
+// smemRaw: [SparseSmem | pad to 256 B][sRow: ldR floats][sIdx 256][sD 256][sV1 256][sV2 256]
+template <bool STREAM>
+__device__ __forceinline__ bool sparse_task(const ModelView &mv, const float *erfT, const float *erfinvT, float annealingTemp, const TaskIn &in,
+                                            unsigned char *smemRaw, DevOutcome *outp, unsigned long long *verWaitNs,
+                                            uint32_t *commitFlags)
+{
+    SparseSmem *hdr = reinterpret_cast<SparseSmem*>(smemRaw);
+    float *sRow = reinterpret_cast<float*>(smemRaw + 256);
+    uint32_t *sIdx = reinterpret_cast<uint32_t*>(sRow + mv.ldR);
+    float *sD = reinterpret_cast<float*>(sIdx + kSparseThreads);
+    float *sV1 = sD + kSparseThreads;
+    float *sV2 = sV1 + kSparseThreads;
+    const uint32_t tid = threadIdx.x, lane = tid & 31u, warp = tid >> 5;
+    const DevProposal &pr = in.pr;
+    const uint32_t pi = in.pi, part = in.part;
+    const uint32_t type = pr.type;
+    const uint32_t r1 = pr.r1, c1 = pr.c1, r2 = pr.r2, c2 = pr.c2;
+    const uint32_t variant = pr.variant;
+    const uint32_t k = mv.k;
+    const bool pairType = (type == 'M') || (type == 'E') || (type == kProbe && variant == 1);
+    const bool twoRow = pairType && (r1 != r2);
+    const bool useV2 = pairType && (r1 == r2);
+    const bool withChange = (type == 'D') || (type == kProbe && variant == 2);
+    const float ch = (type == 'D') ? -pr.m1 : pr.ch;
+    const uint32_t row = part ? r2 : r1;
+    const uint32_t colA = part ? c2 : c1;
+
+    if (STREAM && tid == 0 && in.waitMask != 0u)
+    {
+        const unsigned long long t0 = global_timer_ns();
+        if (in.waitMask & 1u) { while (ld_acquire_gpu_u32(mv.rowVersion + r1) != in.ver1) { } }
+        if (in.waitMask & 2u) { while (ld_acquire_gpu_u32(mv.rowVersion + r2) != in.ver2) { } }
+        if (verWaitNs) { *verWaitNs = global_timer_ns() - t0; }
+    }
+    if (STREAM) { __syncthreads(); }
+    // own factor row (L2 loads: an earlier batch of this kernel may have written it)
+    for (uint32_t i = tid; i < mv.ldR; i += kSparseThreads) { sRow[i] = __ldcg(mv.Mrows + static_cast<size_t>(row) * mv.ldR + i); }
+    float M1 = 0.f, M2 = 0.f, C1 = 0.f, C2 = 0.f;
+    int can1 = 0, can2 = 0;
+    if (tid == 0 && type != kProbe)
+    {
+        M1 = ld_cg_f32(mv.Mrows + static_cast<size_t>(r1) * mv.ldR + c1);
+        C1 = ld_cg_f32(mv.M + static_cast<size_t>(c1) * mv.ldM + r1);
+        can1 = mv.otherColNonzero[c1];
+        if (pairType)
+        {
+            M2 = ld_cg_f32(mv.Mrows + static_cast<size_t>(r2) * mv.ldR + c2);
+            C2 = ld_cg_f32(mv.M + static_cast<size_t>(c2) * mv.ldM + r2);
+            can2 = mv.otherColNonzero[c2];
+        }
+    }
+    else if (tid == 32 && (type == 'D' || type == 'M' || type == 'B'))
+    {
+        Pcg r;
+        r.state = pr.rng;
+        hdr->preLog[0] = portable_logf(r.uniform());
+        hdr->preLog[1] = portable_logf(r.uniform());
+    }
+    __syncthreads();
+    if (tid == 64)
+    {
+        // the table terms: s = Z1[c] (or Z1[c1] - 2 Z2[c2][c1] + Z1[c2]); s_mu = -(A[row,:] . Z2[:,c]) ...
+        float bs, bmu;
+        if (useV2)
+        {
+            bs = fadd(fsub(mv.Z1[c1], fmul(2.f, mv.Z2[static_cast<size_t>(c2) * k + c1])), mv.Z1[c2]);
+            const float *za = mv.Z2 + static_cast<size_t>(c1) * k, *zb = mv.Z2 + static_cast<size_t>(c2) * k;
+            float acc = 0.f;
+            for (uint32_t i = 0; i < k; ++i) { acc = fadd(acc, fmul(sRow[i], fsub(za[i], zb[i]))); } // gaps::dot_diff
+            bmu = fmul(-1.f, acc);
+        }
+        else
+        {
+            bs = mv.Z1[colA];
+            bmu = fmul(-1.f, row_dot(sRow, mv.Z2 + static_cast<size_t>(colA) * k, k));
+            if (withChange) { bmu = fsub(bmu, fmul(ch, mv.Z2[static_cast<size_t>(colA) * k + colA])); }
+        }
+        hdr->baseS = bs;
+        hdr->baseMu = bmu;
+    }
+
+    // ---- the scan over the row's non-zeros, 256 at a time: compact the common ones, one lane each ----
+    const uint32_t start = mv.spRowPtr[row], nnz = mv.spRowPtr[row + 1] - start;
+    const float *V1 = mv.otherM + static_cast<size_t>(colA) * mv.ldOther;
+    const float *V2 = mv.otherM + static_cast<size_t>(c2) * mv.ldOther;
+    float accS = 0.f, accMu = 0.f;
+    uint32_t visited = 0; // elements visited so far (same on every thread)
+    for (uint32_t base = 0; base < nnz; base += kSparseThreads)
+    {
+        const uint32_t j = base + tid;
+        uint32_t l = 0;
+        float d = 0.f, v1 = 0.f, v2 = 0.f;
+        bool pred = false;
+        if (j < nnz)
+        {
+            l = mv.spIdx[start + j];
+            d = mv.spVal[start + j];
+            v1 = V1[l];
+            if (useV2) { v2 = V2[l]; }
+            pred = useV2 ? (v1 != 0.f || v2 != 0.f) : (v1 != 0.f);
+        }
+        const uint32_t ballot = __ballot_sync(0xffffffffu, pred);
+        if (lane == 0) { hdr->warpCnt[warp] = __popc(ballot); }
+        __syncthreads();
+        uint32_t before = 0, total = 0;
+#pragma unroll
+        for (uint32_t w = 0; w < kSparseThreads / 32; ++w)
+        {
+            const uint32_t c = hdr->warpCnt[w];
+            before += (w < warp) ? c : 0u;
+            total += c;
+        }
+        if (pred)
+        {
+            const uint32_t p = before + __popc(ballot & ((1u << lane) - 1u));
+            sIdx[p] = l;
+            sD[p] = d;
+            sV1[p] = v1;
+            sV2[p] = v2;
+        }
+        __syncthreads();
+        // element e = visited + i goes to lane e % 256: this chunk gives every lane at most one element
+        const uint32_t i = (tid + kSparseThreads - (visited % kSparseThreads)) % kSparseThreads;
+        if (i < total)
+        {
+            const uint32_t el = sIdx[i];
+            const float ed = sD[i], ev1 = sV1[i];
+            const float *orow = mv.otherMrows + static_cast<size_t>(el) * mv.ldR;
+            float dotv = 0.f;
+            // ascending k, mul and add rounded separately; 16-byte gathers of the other factor's row
+            for (uint32_t q = 0; q < k; q += 4)
+            {
+                const float4 o4 = *reinterpret_cast<const float4*>(orow + q);
+                dotv = fadd(dotv, fmul(sRow[q], o4.x));
+                if (q + 1 < k) { dotv = fadd(dotv, fmul(sRow[q + 1], o4.y)); }
+                if (q + 2 < k) { dotv = fadd(dotv, fmul(sRow[q + 2], o4.z)); }
+                if (q + 3 < k) { dotv = fadd(dotv, fmul(sRow[q + 3], o4.w)); }
+            }
+            if (useV2)
+            {
+                const float dRecip = fdiv(1.f, ed);
+                const float term1 = fsub(1.f, fmul(dRecip, dRecip));
+                const float vDiff = fsub(ev1, sV2[i]);
+                accS = fadd(accS, fmul(fmul(vDiff, vDiff), term1));
+                accMu = fadd(accMu, fmul(vDiff, fadd(fmul(dotv, term1), dRecip)));
+            }
+            else
+            {
+                const float term1 = fdiv(ev1, ed);
+                const float term2 = fsub(ev1, fdiv(term1, ed));
+                accS = fadd(accS, fsub(fmul(term1, term1), fmul(ev1, ev1)));
+                accMu = fadd(accMu, fadd(term1, fmul(term2, dotv)));
+                if (withChange) { accMu = fadd(accMu, fmul(fmul(term2, orow[colA]), ch)); }
+            }
+        }
+        visited += total;
+        __syncthreads(); // the compaction buffers are rewritten by the next chunk
+    }
+    // lanes -> warp -> CTA: the butterflies of the dense kernel
+#pragma unroll
+    for (int off = 16; off >= 1; off >>= 1)
+    {
+        accS = fadd(accS, __shfl_xor_sync(0xffffffffu, accS, off));
+        accMu = fadd(accMu, __shfl_xor_sync(0xffffffffu, accMu, off));
+    }
+    if (lane == 0)
+    {
+        hdr->warpS[warp] = accS;
+        hdr->warpMu[warp] = accMu;
+    }
+    __syncthreads();
+    bool owner = false;
+    if (tid < 32)
+    {
+        float sS = (tid < kSparseThreads / 32) ? hdr->warpS[tid] : 0.f;
+        float sMu = (tid < kSparseThreads / 32) ? hdr->warpMu[tid] : 0.f;
+#pragma unroll
+        for (int off = 16; off >= 1; off >>= 1)
+        {
+            sS = fadd(sS, __shfl_xor_sync(0xffffffffu, sS, off));
+            sMu = fadd(sMu, __shfl_xor_sync(0xffffffffu, sMu, off));
+        }
+        if (tid == 0)
+        {
+            float s = useV2 ? fsub(hdr->baseS, sS) : fadd(hdr->baseS, sS);
+            float mu = fadd(hdr->baseMu, sMu);
+            s = fmul(s, mv.beta);
+            mu = fmul(mu, mv.beta);
+            bool decideHere = true;
+            if (twoRow)
+            {
+                AlphaPair mine;
+                mine.s = s;
+                mine.s_mu = mu;
+                mv.partials[pi * 2 + part] = mine;
+                __threadfence();
+                const uint32_t ticket = atomicAdd(&mv.tickets[pi], 1u);
+                decideHere = (ticket == 1u);
+                if (decideHere)
+                {
+                    __threadfence();
+                    const volatile AlphaPair *o = &mv.partials[pi * 2 + (1u - part)];
+                    const float os = o->s, omu = o->s_mu;
+                    mv.tickets[pi] = 0u;
+                    const float s1 = part ? os : s, s2 = part ? s : os;
+                    const float mu1 = part ? omu : mu, mu2 = part ? mu : omu;
+                    s = fadd(s1, s2);
+                    mu = fsub(mu1, mu2);
+                }
+            }
+            if (decideHere)
+            {
+                Verdict v;
+                PreLog pre;
+                pre.state0 = pr.rng;
+                pre.logFirst = hdr->preLog[0];
+                pre.logSecond = hdr->preLog[1];
+                decide<true>(mv, erfT, erfinvT, annealingTemp, pr, part, twoRow, s, mu, M1, M2, C1, C2, can1, can2, pre, &v);
+                *outp = v.out;
+                owner = true;
+                *commitFlags = v.dec.flags;
+            }
+        }
+    }
+    return owner;
+}
+
+// The sparse model's commit is the two factor elements decide() stored; this publishes them (deciding lane
+// only, after the outcome has gone to the host): fence, then the row versions and the done count.
+__device__ __forceinline__ void sparse_publish(const ModelView &mv, const TaskIn &in, uint32_t flags, unsigned long long *commitsDone)
+{
+    if ((flags & 7u) == 0u) { return; }
+    const uint32_t row = in.part ? in.pr.r2 : in.pr.r1, otherRow = in.part ? in.pr.r1 : in.pr.r2;
+    __threadfence_system();
+    if ((flags & 3u) != 0u) { atomicAdd(mv.rowVersion + row, 1u); }
+    if ((flags & 4u) != 0u) { atomicAdd(mv.rowVersion + otherRow, 1u); }
+    if (commitsDone != nullptr) { atomicAdd(commitsDone, 1ull); }
+}
+
+// One launch per conflict-free batch, sparse model.
+__global__ void __launch_bounds__(kSparseThreads, 4) eval_sparse_kernel(const __grid_constant__ EvalParams P)
+{
+    extern __shared__ __align__(128) unsigned char smemRaw[];
+    const uint32_t task = blockIdx.x;
+    TaskIn in;
+    in.pi = task < P.nProps ? task : static_cast<uint32_t>(P.extra[task - P.nProps]);
+    in.part = task < P.nProps ? 0u : 1u;
+    in.ver1 = in.ver2 = in.waitMask = 0u;
+    in.pr = P.props[in.pi];
+    DevOutcome out;
+    uint32_t flags = 0u;
+    if (sparse_task<false>(P.mv, P.mv.erf, P.mv.erfinv, P.mv.annealingTemp, in, smemRaw, &out, nullptr, &flags))
+    {
+        P.mv.outcomes[in.pi] = out;
+        sparse_publish(P.mv, in, flags, nullptr);
+    }
 }
 
 // One launch per conflict-free batch; proposals travel in kernel-parameter space.
@@ -767,15 +1078,16 @@ __device__ __forceinline__ void mirror_loop(const StreamParams &sp)
     }
 }
 
-template <bool HAS_S>
-__global__ void __launch_bounds__(kThreads, 2) eval_stream_kernel(const __grid_constant__ ModelView mv,
-                                                               const __grid_constant__ StreamParams sp)
+// MODE 0: dense model, default uncertainty; 1: dense with an S matrix; 2: sparse model
+template <int MODE>
+__device__ __forceinline__ void stream_worker(const ModelView &mv, const StreamParams &sp, unsigned char *smemRaw)
 {
-    extern __shared__ __align__(128) unsigned char smemRaw[];
+    constexpr bool HAS_S = (MODE == 1);
+    constexpr bool SPARSE = (MODE == 2);
     EvalSmem *hdr = reinterpret_cast<EvalSmem*>(smemRaw);
     __shared__ __align__(16) StreamRecord sRec;
     cg::cluster_group cluster = cg::this_cluster();
-    const uint32_t rank = cluster.block_rank();
+    const uint32_t rank = SPARSE ? 0u : cluster.block_rank();
     const uint32_t nSeg = mv.nSeg;
     const uint32_t clusterId = blockIdx.x / nSeg;
     const uint32_t tid = threadIdx.x;
@@ -784,12 +1096,14 @@ __global__ void __launch_bounds__(kThreads, 2) eval_stream_kernel(const __grid_c
         if (rank == 0) { mirror_loop(sp); }
         return;
     }
-    // lookup tables of the epilogue live in shared memory for the whole update()
-    float *erfS = reinterpret_cast<float*>(smemRaw + 256) + static_cast<size_t>(HAS_S ? 5 : 4) * mv.segPad;
+    // lookup tables of the epilogue live in shared memory for the whole update(), behind the staging area
+    const size_t stageFloats = SPARSE ? (static_cast<size_t>(mv.ldR) + 4u * kSparseThreads)
+                                      : static_cast<size_t>(HAS_S ? 5 : 4) * mv.segPad;
+    float *erfS = reinterpret_cast<float*>(smemRaw + 256) + stageFloats;
     float *erfinvS = erfS + ((CGB_ERF_TABLE_SIZE + 3) & ~3);
-    for (uint32_t i = tid; i < CGB_ERF_TABLE_SIZE; i += kThreads) { erfS[i] = mv.erf[i]; }
-    for (uint32_t i = tid; i < CGB_ERFINV_TABLE_SIZE; i += kThreads) { erfinvS[i] = mv.erfinv[i]; }
-    if (tid == 0)
+    for (uint32_t i = tid; i < CGB_ERF_TABLE_SIZE; i += blockDim.x) { erfS[i] = mv.erf[i]; }
+    for (uint32_t i = tid; i < CGB_ERFINV_TABLE_SIZE; i += blockDim.x) { erfinvS[i] = mv.erfinv[i]; }
+    if (!SPARSE && tid == 0)
     {
         mbar_init(&hdr->bar, 1);
         fence_mbar_init();
@@ -855,7 +1169,10 @@ __global__ void __launch_bounds__(kThreads, 2) eval_stream_kernel(const __grid_c
         const uint32_t task = (in.pi % kMaxBatch) + in.part * kMaxBatch; // debug phase-clock slot
         DevOutcome out;
         unsigned long long verWait = 0;
-        const bool owner = process_task<HAS_S, true>(mv, erfS, erfinvS, mv.annealingTemp, in, task, smemRaw, parity, cluster, rank, &out, &verWait);
+        uint32_t sparseFlags = 0u;
+        bool owner;
+        if (SPARSE) { owner = sparse_task<true>(mv, erfS, erfinvS, mv.annealingTemp, in, smemRaw, &out, &verWait, &sparseFlags); }
+        else { owner = process_task<HAS_S, true>(mv, erfS, erfinvS, mv.annealingTemp, in, task, smemRaw, parity, cluster, rank, &out, &verWait); }
         unsigned long long tPosted = 0;
         if (owner)
         {
@@ -868,7 +1185,14 @@ __global__ void __launch_bounds__(kThreads, 2) eval_stream_kernel(const __grid_c
                          ::"l"(sp.outcomes + in.pi), "r"(w0), "r"(w1), "r"(w2), "r"(w3) : "memory");
             tPosted = global_timer_ns();
         }
-        commit_task<HAS_S>(mv, in, task, smemRaw, cluster, rank, &sp.stats->commitsDone);
+        if (SPARSE)
+        {
+            if (owner) { sparse_publish(mv, in, sparseFlags, &sp.stats->commitsDone); }
+        }
+        else
+        {
+            commit_task<HAS_S>(mv, in, task, smemRaw, cluster, rank, &sp.stats->commitsDone);
+        }
         parity ^= 1u;
         __syncthreads(); // staging buffers and sRec are free for the next task
         if (tid == 0 && rank == 0)
@@ -885,6 +1209,21 @@ __global__ void __launch_bounds__(kThreads, 2) eval_stream_kernel(const __grid_c
             }
         }
     }
+}
+
+template <bool HAS_S>
+__global__ void __launch_bounds__(kThreads, 2) eval_stream_kernel(const __grid_constant__ ModelView mv,
+                                                               const __grid_constant__ StreamParams sp)
+{
+    extern __shared__ __align__(128) unsigned char smemRaw[];
+    if (HAS_S) { stream_worker<1>(mv, sp, smemRaw); } else { stream_worker<0>(mv, sp, smemRaw); }
+}
+
+__global__ void __launch_bounds__(kSparseThreads, 4) eval_stream_sparse_kernel(const __grid_constant__ ModelView mv,
+                                                                            const __grid_constant__ StreamParams sp)
+{
+    extern __shared__ __align__(128) unsigned char smemRaw[];
+    stream_worker<2>(mv, sp, smemRaw);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -964,6 +1303,105 @@ __global__ void __launch_bounds__(256) chisq_kernel(const float *__restrict__ D,
     {
         double t = 0.0;
         for (int w = 0; w < 8; ++w) { t += warpSum[w]; }
+        partials[blockIdx.x] = t;
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// SparseNormalModel::generateLookupTables (SparseNormalModel.cpp:294-311): Z1[i] = sum_r rows[r][i]^2
+// (row copy), Z2[i][j] = sum_r cols[i][r] cols[j][r] (column copy) of the OTHER factor.  Element r goes to
+// lane r % 256, lanes add in order, butterflies combine them (oracle mode "device").  Block b < k gives
+// Z1[b]; the others give the pairs (i <= j) in row-major order of the upper triangle.
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(kSparseThreads) sparse_tables_kernel(const float *__restrict__ Mrows, uint32_t ldR,
+                                                                       const float *__restrict__ M, uint32_t ldM,
+                                                                       uint32_t nRows, uint32_t k,
+                                                                       float *__restrict__ Z1, float *__restrict__ Z2)
+{
+    __shared__ float warpSum[kSparseThreads / 32];
+    const uint32_t tid = threadIdx.x;
+    float acc = 0.f;
+    uint32_t zi = 0, zj = 0;
+    const bool isZ1 = blockIdx.x < k;
+    if (isZ1)
+    {
+        zi = blockIdx.x;
+        for (uint32_t r = tid; r < nRows; r += kSparseThreads)
+        {
+            const float v = Mrows[static_cast<size_t>(r) * ldR + zi];
+            acc = fadd(acc, fmul(v, v));
+        }
+    }
+    else
+    {
+        uint32_t p = blockIdx.x - k; // index into the upper triangle, rows of length k, k-1, ...
+        while (p >= k - zi)
+        {
+            p -= k - zi;
+            ++zi;
+        }
+        zj = zi + p;
+        const float *a = M + static_cast<size_t>(zi) * ldM, *b = M + static_cast<size_t>(zj) * ldM;
+        for (uint32_t r = tid; r < nRows; r += kSparseThreads) { acc = fadd(acc, fmul(a[r], b[r])); }
+    }
+#pragma unroll
+    for (int off = 16; off >= 1; off >>= 1) { acc = fadd(acc, __shfl_xor_sync(0xffffffffu, acc, off)); }
+    if ((tid & 31) == 0) { warpSum[tid >> 5] = acc; }
+    __syncthreads();
+    if (tid < 32)
+    {
+        float t = (tid < kSparseThreads / 32) ? warpSum[tid] : 0.f;
+#pragma unroll
+        for (int off = 16; off >= 1; off >>= 1) { t = fadd(t, __shfl_xor_sync(0xffffffffu, t, off)); }
+        if (tid == 0)
+        {
+            if (isZ1) { Z1[zi] = t; }
+            else
+            {
+                Z2[static_cast<size_t>(zi) * k + zj] = t;
+                Z2[static_cast<size_t>(zj) * k + zi] = t;
+            }
+        }
+    }
+}
+
+// SparseNormalModel::chiSq (SparseNormalModel.cpp:39-60): sum over every (row j, scan index i) of dot^2,
+// plus 1 + dot (dot - 2 d - d^2 dot) / d^2 where d > 0, dot = A[j,:] . P[i,:]; times beta on the host.
+// Terms in fp32 as the reference forms them, f64 accumulation in a fixed order.
+__global__ void __launch_bounds__(kSparseThreads) sparse_chisq_kernel(const float *__restrict__ D, uint32_t ld,
+                                                                      const float *__restrict__ Mrows,
+                                                                      const float *__restrict__ otherMrows, uint32_t ldR,
+                                                                      uint32_t nRows, uint32_t L, uint32_t k,
+                                                                      double *__restrict__ partials)
+{
+    extern __shared__ float sOwn[];
+    __shared__ double warpSum[kSparseThreads / 32];
+    double acc = 0.0;
+    for (uint32_t j = blockIdx.x; j < nRows; j += gridDim.x)
+    {
+        __syncthreads();
+        for (uint32_t q = threadIdx.x; q < ldR; q += kSparseThreads) { sOwn[q] = Mrows[static_cast<size_t>(j) * ldR + q]; }
+        __syncthreads();
+        for (uint32_t i = threadIdx.x; i < L; i += kSparseThreads)
+        {
+            const float dot = row_dot(sOwn, otherMrows + static_cast<size_t>(i) * ldR, k);
+            acc += static_cast<double>(fmul(dot, dot));
+            const float d = D[static_cast<size_t>(j) * ld + i];
+            if (d > 0.f)
+            {
+                const float dsq = fmul(d, d);
+                const float t = fdiv(fmul(dot, fsub(fsub(dot, fmul(2.f, d)), fmul(dsq, dot))), dsq);
+                acc += static_cast<double>(fadd(1.f, t));
+            }
+        }
+    }
+    for (int off = 16; off >= 1; off >>= 1) { acc += __shfl_xor_sync(0xffffffffu, acc, off); }
+    if ((threadIdx.x & 31) == 0) { warpSum[threadIdx.x >> 5] = acc; }
+    __syncthreads();
+    if (threadIdx.x == 0)
+    {
+        double t = 0.0;
+        for (int w = 0; w < kSparseThreads / 32; ++w) { t += warpSum[w]; }
         partials[blockIdx.x] = t;
     }
 }

@@ -85,6 +85,12 @@ struct cgb_sampler
     int device;
     cudaStream_t stream;
 
+    // SparseNormalModel: no AP, no S; D also as CSR over sampler rows, the factor in two copies, Z tables
+    bool sparse;
+    uint32_t *dSpRowPtr, *dSpIdx;
+    float *dSpVal, *dMrows, *dZ1, *dZ2;
+    uint32_t ldR;
+
     // device buffers
     float *dD, *dS, *dAP, *dM;
     int *dColNonzero;

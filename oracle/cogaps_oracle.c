@@ -2198,15 +2198,16 @@ int cogaps_oracle_rng_stream(uint32_t seed, int kind, uint32_t n, uint64_t a, ui
     return rc;
 }
 
-int cogaps_oracle_alpha_parameters(const float *data, uint32_t nGenes, uint32_t nSamples, uint32_t k,
-                                   const float *Amat, const float *Pmat, const float *uncertainty,
-                                   uint32_t n, const int32_t *variant, const uint32_t *r1,
-                                   const uint32_t *c1, const uint32_t *r2, const uint32_t *c2,
-                                   const float *ch, float *s_out, float *smu_out, float *ap_out,
-                                   const oracle_options *opt)
+static int alpha_parameters_probe(int sparse, const float *data, uint32_t nGenes, uint32_t nSamples, uint32_t k,
+                                  const float *Amat, const float *Pmat, const float *uncertainty,
+                                  uint32_t n, const int32_t *variant, const uint32_t *r1,
+                                  const uint32_t *c1, const uint32_t *r2, const uint32_t *c2,
+                                  const float *ch, float *s_out, float *smu_out, float *ap_out,
+                                  const oracle_options *opt)
 {
     cgb_params p;
     memset(&p, 0, sizeof(p));
+    p.useSparseOptimization = sparse;
     p.nPatterns = k;
     p.alphaA = p.alphaP = 0.01f;
     p.maxGibbsMassA = p.maxGibbsMassP = 100.f;
@@ -2244,11 +2245,35 @@ int cogaps_oracle_alpha_parameters(const float *data, uint32_t nGenes, uint32_t 
     return rc;
 }
 
-int cogaps_oracle_chisq(const float *data, uint32_t nGenes, uint32_t nSamples, uint32_t k,
-                        const float *Amat, const float *Pmat, const float *uncertainty, float *out)
+int cogaps_oracle_alpha_parameters(const float *data, uint32_t nGenes, uint32_t nSamples, uint32_t k,
+                                   const float *Amat, const float *Pmat, const float *uncertainty,
+                                   uint32_t n, const int32_t *variant, const uint32_t *r1,
+                                   const uint32_t *c1, const uint32_t *r2, const uint32_t *c2,
+                                   const float *ch, float *s_out, float *smu_out, float *ap_out,
+                                   const oracle_options *opt)
+{
+    return alpha_parameters_probe(0, data, nGenes, nSamples, k, Amat, Pmat, uncertainty, n, variant, r1, c1, r2, c2, ch,
+                                  s_out, smu_out, ap_out, opt);
+}
+
+/* the same probe on SparseNormalModel (SparseNormalModel.cpp:153-292) */
+int cogaps_oracle_alpha_parameters_sparse(const float *data, uint32_t nGenes, uint32_t nSamples, uint32_t k,
+                                          const float *Amat, const float *Pmat,
+                                          uint32_t n, const int32_t *variant, const uint32_t *r1,
+                                          const uint32_t *c1, const uint32_t *r2, const uint32_t *c2,
+                                          const float *ch, float *s_out, float *smu_out,
+                                          const oracle_options *opt)
+{
+    return alpha_parameters_probe(1, data, nGenes, nSamples, k, Amat, Pmat, NULL, n, variant, r1, c1, r2, c2, ch,
+                                  s_out, smu_out, NULL, opt);
+}
+
+static int chisq_probe(int sparse, const float *data, uint32_t nGenes, uint32_t nSamples, uint32_t k,
+                       const float *Amat, const float *Pmat, const float *uncertainty, float *out)
 {
     cgb_params p;
     memset(&p, 0, sizeof(p));
+    p.useSparseOptimization = sparse;
     p.nPatterns = k;
     p.alphaA = p.alphaP = 0.01f;
     p.maxGibbsMassA = p.maxGibbsMassP = 100.f;
@@ -2272,4 +2297,17 @@ int cogaps_oracle_chisq(const float *data, uint32_t nGenes, uint32_t nSamples, u
     model_free(&A);
     model_free(&P);
     return 0;
+}
+
+int cogaps_oracle_chisq(const float *data, uint32_t nGenes, uint32_t nSamples, uint32_t k,
+                        const float *Amat, const float *Pmat, const float *uncertainty, float *out)
+{
+    return chisq_probe(0, data, nGenes, nSamples, k, Amat, Pmat, uncertainty, out);
+}
+
+/* SparseNormalModel::chiSq (SparseNormalModel.cpp:39-60) */
+int cogaps_oracle_chisq_sparse(const float *data, uint32_t nGenes, uint32_t nSamples, uint32_t k,
+                               const float *Amat, const float *Pmat, float *out)
+{
+    return chisq_probe(1, data, nGenes, nSamples, k, Amat, Pmat, NULL, out);
 }

@@ -86,6 +86,16 @@ int cogaps_oracle_alpha_parameters(const float *data, uint32_t nGenes, uint32_t 
 int cogaps_oracle_chisq(const float *data, uint32_t nGenes, uint32_t nSamples, uint32_t k,
                         const float *A, const float *P, const float *uncertainty, float *out);
 
+/* the two probes above on SparseNormalModel (default uncertainty only) */
+int cogaps_oracle_alpha_parameters_sparse(const float *data, uint32_t nGenes, uint32_t nSamples, uint32_t k,
+                                          const float *A, const float *P,
+                                          uint32_t n, const int32_t *variant, const uint32_t *r1,
+                                          const uint32_t *c1, const uint32_t *r2, const uint32_t *c2,
+                                          const float *ch, float *s_out, float *smu_out,
+                                          const oracle_options *opt);
+int cogaps_oracle_chisq_sparse(const float *data, uint32_t nGenes, uint32_t nSamples, uint32_t k,
+                               const float *A, const float *P, float *out);
+
 float cogaps_oracle_portable_logf(float x);
 
 #ifdef __cplusplus

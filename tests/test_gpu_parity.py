@@ -182,6 +182,99 @@ def test_run_matches_oracle(oracle, name):
         assert np.array_equal(got.meanPatternAssignment, want.meanPatternAssignment)
 
 
+@pytest.mark.parametrize("shape", [(37, 23, 4), (64, 300, 7), (50, 700, 30), (12, 3000, 5)])
+def test_sparse_alpha_parameters_lockstep(oracle, shape):
+    """SparseNormalModel.cpp:153-292 (all three alphaParameters variants), generateLookupTables (:294-311) and
+    chiSq (:39-60) through the sparse eval kernel, against the oracle in the device's summation order
+    (bit-exact) and in the reference's own order (fp32 re-association only)."""
+    import cogaps_b200 as cg
+    from cogaps_b200._runhelp import make_params
+    g, s, k = shape
+    rng = np.random.default_rng(g * 1000 + s)
+    data = rng.gamma(2.0, 1.0, (g, s)).astype(np.float32)
+    data[rng.random((g, s)) < 0.8] = 0
+    data[0, :] = 0          # an empty data row
+    data[1, :] = 1.5        # and a full one (longer than one 256-wide group when s > 256)
+    A = (rng.gamma(2.0, 0.5, (g, k)) * (rng.random((g, k)) < 0.6)).astype(np.float32)
+    Pm = (rng.gamma(2.0, 0.5, (s, k)) * (rng.random((s, k)) < 0.6)).astype(np.float32)
+    A[2, 0] = 5e-6          # below epsilon: kept in the row copy, dropped from the column copy
+    Pm[3, 1] = 5e-6
+    q = [(0, 0, 0, 0, 0, 0.0), (0, 1, 1, 1, 1, 0.0), (1, 1, 0, 1, 1, 0.0), (2, 1, 1, 1, 1, -0.3)]
+    for _ in range(120):
+        r1, r2 = rng.integers(0, g, 2)
+        c1, c2 = rng.integers(0, k, 2)
+        v = int(rng.integers(0, 3))
+        if v == 1 and rng.random() < 0.6:
+            r2 = r1
+        q.append((v, r1, c1, r2, c2, -float(rng.random())))
+
+    params = make_params(nPatterns=k, useSparseOptimization=1)
+    rs = cg.GapsRandomState(1)
+    a = cg.GibbsSampler(data, True, True, 0.01, 100.0, params, rs)
+    p = cg.GibbsSampler(data, False, False, 0.01, 100.0, params, rs)
+    a.setMatrix(A)
+    p.setMatrix(Pm)
+    a.sync(p)
+    p.sync(a)
+    a.extraInitialization()
+    p.extraInitialization()
+    s_gpu, smu_gpu = a.alphaParameters(q)
+    opts = oracle.options(reduce="device", orderA=a.reductionOrder(), orderP=p.reductionOrder())
+    s_dev, smu_dev = oracle.alpha_parameters_sparse(data, A, Pm, q, options=opts)
+    assert np.array_equal(bits(s_gpu), bits(s_dev))
+    assert np.array_equal(bits(smu_gpu), bits(smu_dev))
+    s_ref, smu_ref = oracle.alpha_parameters_sparse(data, A, Pm, q)
+    # s and s_mu are differences of large table terms and scan sums (times beta = 100): bound the error by the
+    # magnitude of the pieces, not of the result
+    scale = 100.0 * (np.abs(A).max() * np.abs(Pm).max() * k + 1.0) * np.abs(Pm).max() * s
+    assert np.all(np.abs(s_gpu - s_ref) <= 1e-6 * scale)
+    assert np.all(np.abs(smu_gpu - smu_ref) <= 1e-6 * scale)
+    cs = oracle.chisq_sparse(data, A, Pm)
+    assert a.chiSq() == pytest.approx(float(cs[0]), rel=RTOL_CHISQ)
+    assert p.chiSq() == pytest.approx(float(cs[1]), rel=RTOL_CHISQ)
+    assert p.dataSparsity() == pytest.approx(float(cs[2]), abs=1e-7)
+
+
+def test_sparse_chisq_known_answer():
+    """cpp_tests/testSparseGibbsSampler.cpp:13-33: A = P = 0, data(i,j) = i+j+1 on 25x50 => chiSq = 100*nRow*nCol."""
+    import cogaps_b200 as cg
+    from cogaps_b200._runhelp import make_params
+    g, s, k = 25, 50, 7
+    data = (np.add.outer(np.arange(g), np.arange(s)) + 1).astype(np.float32)
+    params = make_params(nPatterns=k, useSparseOptimization=1)
+    rs = cg.GapsRandomState(123)
+    a = cg.GibbsSampler(data, True, True, 0.01, 100.0, params, rs)
+    p = cg.GibbsSampler(data, False, False, 0.01, 100.0, params, rs)
+    a.sync(p)
+    p.sync(a)
+    assert a.chiSq() == pytest.approx(100.0 * g * s, rel=1e-6)
+    assert p.chiSq() == pytest.approx(100.0 * g * s, rel=1e-6)
+
+
+@pytest.mark.parametrize("name", ["sparse_gist", "sparse_modsim", "sparse_120x90", "sparse_k30", "sparse_gist_fixedP"])
+def test_sparse_run_matches_oracle(oracle, name):
+    """gaps::run with sparseOptimization (SparseGibbsSampler): same seed, same data -> same chain as the oracle
+    in device order; the oracle's sparse model is pinned bit-for-bit to the reference build."""
+    import cogaps_b200 as cg
+    data, unc, kw = case_inputs(name)
+    g, s = dims(data, kw)
+    opts = device_options(oracle, g, s)
+    want = oracle.run(data, snapshots=True, options=opts, **kw)
+    got = cg.gaps_run(data, snapshots=True, **kw)
+    assert np.array_equal(got.atomHistoryA, want.atomHistoryA)
+    assert np.array_equal(got.atomHistoryP, want.atomHistoryP)
+    assert got.totalUpdates == want.totalUpdates
+    assert np.float32(got.averageQueueLengthA) == np.float32(want.averageQueueLengthA)
+    assert np.float32(got.averageQueueLengthP) == np.float32(want.averageQueueLengthP)
+    assert_close(got.chisqHistory, want.chisqHistory, RTOL_CHISQ, "chisqHistory")
+    for f in ("Amean", "Asd", "Pmean", "Psd"):
+        assert_close(getattr(got, f), getattr(want, f), RTOL_MEANS, f)
+    if kw.get("whichMatrixFixed", "N") == "N":
+        assert got.meanChiSq == pytest.approx(want.meanChiSq, rel=RTOL_CHISQ)
+    else:
+        assert got.meanChiSq == 0.0
+
+
 def test_posterior_means_are_bit_identical(oracle):
     """Stronger than the stated tolerance: with the oracle in the device's reduction order the whole
     chain — every atom, every mass — is reproduced to the last bit."""
