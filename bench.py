@@ -250,8 +250,11 @@ def main():
     cA, cP = chain.A.counters(), chain.P.counters()
     queued = cA.nProposalsQueued + cP.nProposalsQueued
     batches = cA.nBatches + cP.nBatches
-    h2d_step = queued * 48.0 / args.steps
-    d2h_step = queued * 32.0 / args.steps
+    # every proposal: one 64-byte task record per CTA of its cluster written to pinned host memory and pulled by
+    # the device (two-row moves / exchanges send two), one 16-byte outcome record written back
+    segA, segP = chain.A.reductionOrder()[2], chain.P.reductionOrder()[2]
+    h2d_step = (cA.nProposalsQueued * 64.0 * segA + cP.nProposalsQueued * 64.0 * segP) / args.steps
+    d2h_step = queued * 16.0 / args.steps
 
     if world > 1:
         t = torch.tensor([elapsed], dtype=torch.float64, device="cuda")

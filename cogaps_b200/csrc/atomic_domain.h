@@ -22,6 +22,30 @@ namespace cgb {
 
 static const uint32_t kNoAtom = 0xFFFFFFFFu;
 
+// floor(x / d) for a divisor fixed per sampler (bin length, pattern count): one 64x64->128 multiply and a
+// fix-up instead of a hardware divide; exact for every x
+struct FastDivU64
+{
+    uint64_t d, m;
+    void init(uint64_t divisor)
+    {
+        d = divisor;
+        m = (divisor > 1) ? static_cast<uint64_t>((static_cast<unsigned __int128>(1) << 64) / divisor) : 0;
+    }
+    uint64_t div(uint64_t x) const
+    {
+        if (d == 1) { return x; }
+        uint64_t q = static_cast<uint64_t>((static_cast<unsigned __int128>(x) * m) >> 64); // floor(x/d) - {0,1}
+        uint64_t r = x - q * d;
+        while (r >= d)
+        {
+            ++q;
+            r -= d;
+        }
+        return q;
+    }
+};
+
 struct Atom
 {
     uint64_t pos;
@@ -108,6 +132,7 @@ public:
     {
         mNumBins = nBins;
         mBinLength = 0xFFFFFFFFFFFFFFFFull / nBins;
+        mBinDiv.init(mBinLength);
         mDomainLength = mBinLength * nBins; // ConcurrentAtomicDomain.cpp:14-18
         mBinFirst.assign(nBins, kNoAtom);
         mBitmap.init(nBins);
@@ -127,7 +152,7 @@ public:
     uint32_t atIndex(uint32_t i) const { return mVec[i]; } // mAtoms[index], :34-47
     uint64_t binOf(uint64_t pos) const
     {
-        const uint64_t b = pos / mBinLength;
+        const uint64_t b = mBinDiv.div(pos);
         return b < mNumBins ? b : mNumBins - 1; // pos == domainLength would index one past the end
     }
 
@@ -286,6 +311,7 @@ private:
     }
 
     uint64_t mNumBins, mBinLength, mDomainLength;
+    FastDivU64 mBinDiv;
     std::vector<uint32_t> mBinFirst;
     BinBitmap mBitmap;
     std::vector<Atom> mPool;

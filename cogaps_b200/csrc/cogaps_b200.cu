@@ -312,7 +312,6 @@ extern "C" int cgb_sampler_create(const float *data, uint32_t nrow, uint32_t nco
     CGB_CHECK(data && params && rs && out, "cgb_sampler_create: NULL argument");
     CGB_CHECK(params->struct_size == sizeof(cgb_params), "cgb_sampler_create: cgb_params ABI mismatch");
     CGB_CHECK(params->nPatterns >= 1, "cgb_sampler_create: nPatterns must be >= 1");
-    if (!params->asynchronousUpdates) { return fail(CGB_EUNSUPPORTED, "the device path is the asynchronous sampler; asynchronousUpdates must be true"); }
     CGB_TRY(checkSubset(params, nrow, ncol));
     CGB_TRY(ensureDevice());
 
@@ -469,7 +468,9 @@ extern "C" int cgb_sampler_create(const float *data, uint32_t nrow, uint32_t nco
     // rng seeded from the shared state (this is where the seed consumption order is fixed)
     const uint64_t nElements = static_cast<uint64_t>(s->nRows) * s->k;
     s->domain.init(nElements);
-    s->queue.init(nElements, s->k, rs, alpha, s->lambda);
+    s->sequential = params->asynchronousUpdates == 0;
+    if (s->sequential) { s->seq.init(nElements, s->k, rs, alpha); } // SingleThreadedGibbsSampler.h:66-81
+    else { s->queue.init(nElements, s->k, rs, alpha, s->lambda); }
     *out = s;
     return CGB_OK;
 }
@@ -766,6 +767,20 @@ static inline bool isTwoRow(const DevProposal &p)
 }
 
 // the host-visible half of AsynchronousGibbsSampler::birth/death/move/exchange (:126-219)
+// rows whose AP line / factor element the device rewrites for an outcome: every CTA of the committing
+// cluster bumps the row's version once and counts itself done once (kernels.cuh commit_task)
+static inline void noteCommit(cgb_sampler *s, const DevProposal &dp, bool resident)
+{
+    s->rowVersion[dp.r1] += s->nSeg;
+    if (isTwoRow(dp)) { s->rowVersion[dp.r2] += s->nSeg; }
+    if (resident)
+    {
+        s->commitsExpected += s->nSeg;
+        s->rowPending[dp.r1] = s->commitsExpected;
+        if (isTwoRow(dp)) { s->rowPending[dp.r2] = s->commitsExpected; }
+    }
+}
+
 // `resident`: the commit is made by the resident grid (no kernel boundary orders it before the next batch)
 static int applyOutcome(cgb_sampler *s, const HostProposal &hp, const DevProposal &dp, bool resident, bool accepted, float mass1, float mass2)
 {
@@ -820,17 +835,7 @@ static int applyOutcome(cgb_sampler *s, const HostProposal &hp, const DevProposa
             break;
         default: return fail(CGB_EINTERNAL, "applyOutcome: corrupt proposal type");
     }
-    if (commit)
-    {
-        s->rowVersion[dp.r1] += s->nSeg;
-        if (isTwoRow(dp)) { s->rowVersion[dp.r2] += s->nSeg; }
-        if (resident)
-        {
-            s->commitsExpected += s->nSeg; // every CTA of the committing cluster counts itself done once
-            s->rowPending[dp.r1] = s->commitsExpected;
-            if (isTwoRow(dp)) { s->rowPending[dp.r2] = s->commitsExpected; }
-        }
-    }
+    if (commit) { noteCommit(s, dp, resident); }
     return CGB_OK;
 }
 
@@ -893,6 +898,8 @@ static int startPersistent(cgb_sampler *s)
     mv.annealingTemp = s->annealingTemp; // constant for the whole update() this grid serves
     // cluster c serves serials c, c + nWorkers, ...; its tickets continue where the last grid stopped
     s->streamSerial = (s->streamSerial + s->nClusters - 1) / s->nClusters * s->nClusters;
+    s->nextCluster = 0;
+    s->nextTicket = static_cast<uint32_t>(s->streamSerial / s->nClusters) + 1u;
     volatile unsigned long long *doorbell = reinterpret_cast<volatile unsigned long long*>(static_cast<StreamRecord*>(s->hSlots) + s->nSlotRecords);
     *doorbell = 0ull;
     __sync_synchronize();
@@ -922,42 +929,15 @@ static int startPersistent(cgb_sampler *s)
     return CGB_OK;
 }
 
-// writes the record of serial T into its cluster's ring (one copy per CTA of the cluster); a torn read
-// fails the checksum and is simply polled again
-static void writeRecord(cgb_sampler *s, uint64_t T, const StreamRecord &rec)
+// writes a record into its cluster's ring (one copy per CTA of the cluster); a torn read fails the
+// checksum and is simply polled again
+static inline void writeRecord(cgb_sampler *s, uint32_t cluster, uint32_t ticket, StreamRecord &rec)
 {
-    StreamRecord r = rec;
-    r.ticket = static_cast<uint32_t>(T / s->nClusters) + 1u;
-    r.check = stream_check(reinterpret_cast<const uint32_t*>(&r));
+    rec.ticket = ticket;
+    rec.check = stream_check(reinterpret_cast<const uint32_t*>(&rec));
     StreamRecord *dst = static_cast<StreamRecord*>(s->hSlots)
-        + (static_cast<size_t>(T % s->nClusters) * kStreamRing + ((T / s->nClusters) % kStreamRing)) * s->nSeg;
-    static const int mode = envInt("COGAPS_RECORD_STORES", 0);
-    if (mode == 1)
-    {
-        // non-temporal: no read-for-ownership of a line the device keeps pulling across PCIe
-        const __m128i *src = reinterpret_cast<const __m128i*>(&r);
-        const __m128i w0 = _mm_loadu_si128(src), w1 = _mm_loadu_si128(src + 1), w2 = _mm_loadu_si128(src + 2), w3 = _mm_loadu_si128(src + 3);
-        for (uint32_t q = 0; q < s->nSeg; ++q)
-        {
-            __m128i *d = reinterpret_cast<__m128i*>(dst + q);
-            _mm_stream_si128(d, w0);
-            _mm_stream_si128(d + 1, w1);
-            _mm_stream_si128(d + 2, w2);
-            _mm_stream_si128(d + 3, w3);
-        }
-        return;
-    }
-    for (uint32_t q = 0; q < s->nSeg; ++q) { std::memcpy(static_cast<void*>(dst + q), &r, sizeof(r)); }
-    if (mode == 2)
-    {
-        // ask for ownership of the lines the next few serials will land in while we generate them
-        for (uint64_t U = T + 6; U < T + 8; ++U)
-        {
-            const StreamRecord *nx = static_cast<StreamRecord*>(s->hSlots)
-                + (static_cast<size_t>(U % s->nClusters) * kStreamRing + ((U / s->nClusters) % kStreamRing)) * s->nSeg;
-            for (uint32_t q = 0; q < s->nSeg; ++q) { __builtin_prefetch(nx + q, 1, 3); }
-        }
-    }
+        + (static_cast<size_t>(cluster) * kStreamRing + ((ticket - 1u) % kStreamRing)) * s->nSeg;
+    for (uint32_t q = 0; q < s->nSeg; ++q) { std::memcpy(static_cast<void*>(dst + q), &rec, sizeof(rec)); }
 }
 
 static int stopPersistent(cgb_sampler *s)
@@ -968,7 +948,10 @@ static int stopPersistent(cgb_sampler *s)
     StreamRecord rec;
     std::memset(&rec, 0, sizeof(rec));
     rec.type = kStreamExit;
-    for (uint64_t T = s->streamSerial; T < s->streamSerial + s->nClusters; ++T) { writeRecord(s, T, rec); }
+    for (uint64_t T = s->streamSerial; T < s->streamSerial + s->nClusters; ++T)
+    {
+        writeRecord(s, static_cast<uint32_t>(T % s->nClusters), static_cast<uint32_t>(T / s->nClusters) + 1u, rec);
+    }
     volatile unsigned long long *doorbell = reinterpret_cast<volatile unsigned long long*>(static_cast<StreamRecord*>(s->hSlots) + s->nSlotRecords);
     *doorbell = kDoorbellExit;
     __sync_synchronize();
@@ -1018,7 +1001,7 @@ static int waitOutcome(cgb_sampler *s, uint32_t pi)
     for (;;)
     {
         const uint32_t w2 = o->seqAndAccepted;
-        if ((w2 >> 1) == want)
+        if ((w2 >> 3) == want)
         {
             const uint32_t w0 = o->mass1Bits, w1 = o->mass2Bits, w3 = o->check;
             if (o->seqAndAccepted == w2 && w3 == outcome_check(w0, w1, w2))
@@ -1027,6 +1010,7 @@ static int waitOutcome(cgb_sampler *s, uint32_t pi)
                 std::memcpy(&d.mass1, &w0, 4);
                 std::memcpy(&d.mass2, &w1, 4);
                 d.accepted = w2 & 1u;
+                d.pad[0] = (w2 >> 1) & 3u;
                 s->arrived[idx] = 1;
                 break;
             }
@@ -1058,11 +1042,13 @@ static int beginChunk(cgb_sampler *s, size_t chunkBase)
     if (!s->persistentRunning) { CGB_TRY(startPersistent(s)); }
     s->lastPostTime = t0;
     ++s->mailSeq;
-    s->chunkTag = static_cast<uint32_t>(s->mailSeq) & 0x7fffffffu;
+    s->chunkTag = static_cast<uint32_t>(s->mailSeq) & 0x1fffffffu;
     s->chunkPosted = 0;
     s->chunkBase = chunkBase;
     return CGB_OK;
 }
+
+static int postPrepared(cgb_sampler *s, size_t index);
 
 // posts proposal `index` of the batch (ProposalQueue sink, or the chunk loop for very long batches)
 static int postProposal(cgb_sampler *s, const HostProposal &hp, size_t index)
@@ -1075,15 +1061,21 @@ static int postProposal(cgb_sampler *s, const HostProposal &hp, size_t index)
         s->collected.resize(n);
         s->arrived.resize(n, 0);
     }
+    fillProposal(s, hp, s->posted[index]);
+    return postPrepared(s, index);
+}
+
+// posts s->posted[index]
+static int postPrepared(cgb_sampler *s, size_t index)
+{
     DevProposal &dp = s->posted[index];
-    fillProposal(s, hp, dp);
     s->arrived[index] = 0;
     const uint32_t pi = static_cast<uint32_t>(index - s->chunkBase);
     StreamRecord rec;
     rec.rng = dp.rng;
     rec.r1 = dp.r1; rec.c1 = dp.c1; rec.r2 = dp.r2; rec.c2 = dp.c2;
     rec.m1 = dp.m1; rec.m2 = dp.m2;
-    rec.type = dp.type;
+    rec.type = dp.type | ((dp.pad & 1u) ? kStreamSeq : 0u);
     rec.ver1 = s->rowVersion[dp.r1];
     rec.ver2 = 0u;
     if (!rowSettled(s, dp.r1)) { rec.type |= kStreamWait1; }
@@ -1097,9 +1089,15 @@ static int postProposal(cgb_sampler *s, const HostProposal &hp, size_t index)
     const uint32_t nParts = isTwoRow(dp) ? 2u : 1u;
     for (uint32_t part = 0; part < nParts; ++part)
     {
-        const uint64_t T = s->streamSerial++;
-        const uint32_t cluster = static_cast<uint32_t>(T % s->nClusters);
-        uint64_t &owner = s->slotOwner[static_cast<size_t>(cluster) * kStreamRing + ((T / s->nClusters) % kStreamRing)];
+        // serial T = streamSerial: cluster T % nClusters, ticket T / nClusters + 1, kept incrementally
+        ++s->streamSerial;
+        const uint32_t cluster = s->nextCluster, ticket = s->nextTicket;
+        if (++s->nextCluster == s->nClusters)
+        {
+            s->nextCluster = 0;
+            ++s->nextTicket;
+        }
+        uint64_t &owner = s->slotOwner[static_cast<size_t>(cluster) * kStreamRing + ((ticket - 1u) % kStreamRing)];
         if ((owner >> 32) == (s->mailSeq & 0xffffffffull))
         {
             // the ring slot still holds a record of this chunk: its outcome proves it has been consumed
@@ -1107,7 +1105,7 @@ static int postProposal(cgb_sampler *s, const HostProposal &hp, size_t index)
         }
         owner = ((s->mailSeq & 0xffffffffull) << 32) | pi;
         rec.piPart = pi | (part << 31);
-        writeRecord(s, T, rec);
+        writeRecord(s, cluster, ticket, rec);
     }
     s->chunkPosted += 1;
     return CGB_OK;
@@ -1185,12 +1183,171 @@ static int evaluateQueue(cgb_sampler *s)
     return CGB_OK;
 }
 
+// ------------------------------------------------------------------------------------------------
+// SingleThreadedGibbsSampler (gibbs_sampler/SingleThreadedGibbsSampler.h:94-257): one proposal at a time,
+// one rng stream.  The host draws the type and the atoms, the device evaluates (same kernels, one task in
+// flight) and reports how many draws it took from the stream; the host applies the outcome at once.
+// ------------------------------------------------------------------------------------------------
+static int evalOne(cgb_sampler *s, DevProposal &dp, DevOutcome &o)
+{
+    dp.pad = 1u;
+    dp.variant = 0u;
+    dp.ch = 0.f;
+    dp.rng = s->seq.rng.state;
+    if (s->usePersistent)
+    {
+        CGB_TRY(beginChunk(s, 0));
+        if (s->posted.empty())
+        {
+            s->posted.resize(256);
+            s->collected.resize(256);
+            s->arrived.resize(256, 0);
+        }
+        s->posted[0] = dp;
+        CGB_TRY(postPrepared(s, 0));
+        CGB_TRY(waitOutcome(s, 0));
+        o = s->collected[0];
+    }
+    else
+    {
+        static thread_local EvalParams params;
+        fillModelView(s, params.mv);
+        params.props[0] = dp;
+        params.nProps = 1;
+        CGB_TRY(launchEval(s, params));
+        o = s->hOutcomes[0];
+    }
+    for (uint32_t d = 0; d < o.pad[0]; ++d) { s->seq.rng.advance(); }
+    s->counters.nBatches += s->usePersistent ? 1 : 0;
+    s->counters.nProposalsQueued += 1;
+    s->counters.algorithmicBytes += algorithmicBytes(dp, o, s->L);
+    return CGB_OK;
+}
+
+static int sequentialUpdate(cgb_sampler *s, uint32_t nSteps)
+{
+    SequentialState &q = s->seq;
+    AtomicDomain &dom = s->domain;
+    const bool resident = s->usePersistent;
+    for (uint32_t step = 0; step < nSteps; ++step)
+    {
+        // getUpdateType, :94-111
+        char type = 'B';
+        if (dom.size() >= 2)
+        {
+            const float u1 = q.rng.uniform();
+            if (u1 < 0.5f)
+            {
+                const double nAtoms = static_cast<double>(dom.size());
+                const double numer = nAtoms * q.domainLength;
+                const float deathProb = static_cast<float>(numer / (numer + q.alpha * q.numBins * (q.domainLength - nAtoms)));
+                type = (q.rng.uniform() < deathProb) ? 'D' : 'B';
+            }
+            else
+            {
+                type = (u1 < 0.75f) ? 'M' : 'E';
+            }
+        }
+        DevProposal dp;
+        std::memset(&dp, 0, sizeof(dp));
+        dp.type = static_cast<uint32_t>(type);
+        DevOutcome o;
+        if (type == 'B')
+        {
+            // birth, :130-150
+            uint64_t pos = q.rng.uniform64(1, dom.domainLength());
+            while (dom.occupied(pos)) { pos = q.rng.uniform64(1, dom.domainLength()); }
+            q.binOf(pos, dp.r1, dp.c1);
+            CGB_TRY(evalOne(s, dp, o));
+            if (o.accepted)
+            {
+                dom.insert(pos, o.mass1);
+                noteCommit(s, dp, resident);
+            }
+        }
+        else if (type == 'D')
+        {
+            // death, :154-187
+            const uint32_t id = dom.atIndex(q.rng.uniform32(0, static_cast<uint32_t>(dom.size() - 1)));
+            q.binOf(dom.atom(id).pos, dp.r1, dp.c1);
+            dp.m1 = dom.atom(id).mass;
+            CGB_TRY(evalOne(s, dp, o));
+            if (o.accepted)
+            {
+                if (o.mass1 != dp.m1)
+                {
+                    dom.atom(id).mass = o.mass1;
+                    noteCommit(s, dp, resident);
+                }
+            }
+            else
+            {
+                dom.erase(id);
+                noteCommit(s, dp, resident);
+            }
+        }
+        else if (type == 'M')
+        {
+            // move, :190-219
+            const uint32_t id = dom.atIndex(q.rng.uniform32(0, static_cast<uint32_t>(dom.size() - 1)));
+            const Atom &center = dom.atom(id);
+            const uint64_t lbound = (center.left != kNoAtom) ? dom.atom(center.left).pos : 0;
+            const uint64_t rbound = (center.right != kNoAtom) ? dom.atom(center.right).pos : referenceDoubleToU64(q.domainLength);
+            const uint64_t pos = q.rng.uniform64(lbound + 1, rbound - 1);
+            q.binOf(center.pos, dp.r1, dp.c1);
+            q.binOf(pos, dp.r2, dp.c2);
+            if (dp.r1 == dp.r2 && dp.c1 == dp.c2)
+            {
+                dom.move(id, pos);
+                continue;
+            }
+            dp.m1 = center.mass;
+            CGB_TRY(evalOne(s, dp, o));
+            if (o.accepted)
+            {
+                dom.move(id, pos);
+                noteCommit(s, dp, resident);
+            }
+        }
+        else
+        {
+            // exchange, :223-257 (same-bin exchanges are ignored; canUseGibbs(c1, c2) is tested on the device)
+            const uint32_t id1 = dom.atIndex(q.rng.uniform32(0, static_cast<uint32_t>(dom.size() - 1)));
+            const uint32_t right = dom.atom(id1).right;
+            const uint32_t id2 = (right != kNoAtom) ? right : dom.front();
+            q.binOf(dom.atom(id1).pos, dp.r1, dp.c1);
+            q.binOf(dom.atom(id2).pos, dp.r2, dp.c2);
+            if (dp.r1 == dp.r2 && dp.c1 == dp.c2) { continue; }
+            dp.m1 = dom.atom(id1).mass;
+            dp.m2 = dom.atom(id2).mass;
+            CGB_TRY(evalOne(s, dp, o));
+            if (o.accepted)
+            {
+                dom.atom(id1).mass = o.mass1;
+                dom.atom(id2).mass = o.mass2;
+                noteCommit(s, dp, resident);
+            }
+        }
+    }
+    return CGB_OK;
+}
+
 // AsynchronousGibbsSampler::update, AsynchronousGibbsSampler.h:88-122
 extern "C" int cgb_sampler_update(cgb_sampler *s, uint32_t nSteps, uint32_t nThreads)
 {
     (void)nThreads;
     CGB_CHECK(s && s->other, "cgb_sampler_update: sync() has not been called");
     CGB_CUDA(cudaSetDevice(s->device));
+    if (s->sequential)
+    {
+        const double t0 = nowSeconds();
+        const double waitBefore = s->counters.secondsDeviceWait;
+        const int rcSeq = sequentialUpdate(s, nSteps);
+        const int rcStop = stopPersistent(s);
+        s->counters.secondsHostGenerate += (nowSeconds() - t0) - (s->counters.secondsDeviceWait - waitBefore);
+        s->counters.nProposalsTotal += nSteps;
+        return rcSeq != CGB_OK ? rcSeq : rcStop;
+    }
     if (g_hostProfile < 0) { g_hostProfile = envInt("COGAPS_HOST_PROFILE", 0); }
     uint32_t n = 0;
     while (n < nSteps)

@@ -16,6 +16,7 @@ static const int kStreamRing = 8;     // task-record slots per resident cluster 
 static const uint32_t kStreamExit = 0xFFFFFFFFu; // record type that retires a resident CTA
 static const uint32_t kStreamWait1 = 0x100u;     // record type bits: the host has no proof yet that the last commit
 static const uint32_t kStreamWait2 = 0x200u;     //   to row r1 / r2 has landed, so the task must check rowVersion
+static const uint32_t kStreamSeq = 0x400u;       // record type bit: proposal of the sequential sampler (DevProposal::pad bit 0)
 static const int kPhaseSlots = 12;    // debug phase timestamps per task
 static const uint32_t kProbe = 'P';   // lock-step probe pseudo-proposal
 
@@ -32,7 +33,7 @@ struct DevProposal
     uint32_t type;     // 'B','D','M','E' or kProbe
     uint32_t variant;  // probe only: 0 alphaParameters(r1,c1); 1 (r1,c1,r2,c2); 2 WithChange
     float ch;          // probe only: change for variant 2
-    uint32_t pad;
+    uint32_t pad;      // bit 0: proposal of the sequential sampler (birth threshold, shared rng stream)
 };
 
 struct DevOutcome
@@ -42,7 +43,7 @@ struct DevOutcome
     uint32_t accepted; // B born / D survives / M moved / E exchanged
     float s;           // alpha parameters (annealed) as used by the decision; raw sums for probes
     float s_mu;
-    uint32_t pad[3];
+    uint32_t pad[3];   // pad[0]: draws the epilogue took from the proposal's rng stream (0..2)
 };
 
 // Everything the eval kernel needs about one sampler.

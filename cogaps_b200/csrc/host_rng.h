@@ -140,6 +140,15 @@ struct HostRng : public Pcg
         while (x >= range * iPart) { x = uniform64(); }
         return x / iPart + a;
     }
+    // uniform64(a, b) with iPart = UINT64_MAX / (b + 1 - a) supplied by a caller whose range never changes
+    uint64_t uniform64Fixed(uint64_t a, uint64_t b, uint64_t iPart)
+    {
+        if (b == a) { return a; }
+        const uint64_t range = b + 1 - a;
+        uint64_t x = uniform64();
+        while (x >= range * iPart) { x = uniform64(); }
+        return (iPart == 1 ? x : x / iPart) + a;
+    }
     // math/Random.cpp:125-170
     int poisson(double lambda)
     {

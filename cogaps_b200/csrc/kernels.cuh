@@ -199,6 +199,7 @@ __device__ __noinline__ void decide(const ModelView &mv, const float *erfT, cons
                                     float s, float mu, float M1, float M2, float C1, float C2, int can1, int can2, const PreLog &pre, Verdict *v)
 {
     bool add1 = false, add2 = false; // element changed by changeMatrix (add) rather than safelyChangeMatrix (set)
+    const bool sequential = (pr.pad & 1u) != 0u; // proposal of the SingleThreadedGibbsSampler (one shared stream)
     const uint32_t type = pr.type;
     const uint32_t r1 = pr.r1, c1 = pr.c1, r2 = pr.r2, c2 = pr.c2;
     const float m1 = pr.m1, m2 = pr.m2;
@@ -237,7 +238,8 @@ __device__ __noinline__ void decide(const ModelView &mv, const float *erfT, cons
             mass = fdiv(fmul(-1.f, pre.take(rng)), mv.lambda);
             has = true;
         }
-        if (has && mass >= kEpsilon)
+        // AsynchronousGibbsSampler.h:139 accepts mass >= epsilon, SingleThreadedGibbsSampler.h:144 mass > epsilon
+        if (has && (sequential ? (mass > kEpsilon) : (mass >= kEpsilon)))
         {
             out.accepted = 1u;
             out.mass1 = mass;
@@ -355,6 +357,18 @@ __device__ __noinline__ void decide(const ModelView &mv, const float *erfT, cons
         dec.dOwn1 = d1;
         dec.dOwn2 = d2;
         dec.flags = (ch1 ? 1u : 0u) | (ch2 ? 2u : 0u);
+    }
+    // the sequential sampler continues ITS stream after us: tell it how many draws we made (0, 1 or 2)
+    {
+        Pcg probe;
+        probe.state = pr.rng;
+        uint32_t draws = 0u;
+        if (rng.state != probe.state)
+        {
+            probe.advance();
+            draws = (rng.state == probe.state) ? 1u : 2u;
+        }
+        out.pad[0] = draws;
     }
     v->dec = dec;
     v->out = out;
@@ -1001,7 +1015,7 @@ __global__ void __launch_bounds__(kThreads, 2) eval_kernel(const __grid_constant
 struct HostOutcome   // one 16-byte store, self-validating for the polling host
 {
     uint32_t mass1Bits, mass2Bits;
-    uint32_t seqAndAccepted; // (chunk tag << 1) | accepted
+    uint32_t seqAndAccepted; // (chunk tag << 3) | (rng draws made << 1) | accepted
     uint32_t check;          // outcome_check of the three words above
 };
 
@@ -1158,9 +1172,10 @@ __device__ __forceinline__ void stream_worker(const ModelView &mv, const StreamP
         in.pr.m1 = sRec.m1; in.pr.m2 = sRec.m2;
         in.pr.type = sRec.type & 0xffu;
         in.waitMask = (sRec.type >> 8) & 3u;
+        const uint32_t seqFlag = (sRec.type >> 10) & 1u;
         in.pr.variant = 0u;
         in.pr.ch = 0.f;
-        in.pr.pad = 0u;
+        in.pr.pad = seqFlag;
         in.pi = sRec.piPart & 0x7fffffffu;
         in.part = sRec.piPart >> 31;
         in.ver1 = sRec.ver1;
@@ -1179,7 +1194,7 @@ __device__ __forceinline__ void stream_worker(const ModelView &mv, const StreamP
             // one 16-byte store across PCIe; word 2 carries the chunk tag, word 3 a checksum of the
             // other three, so the polling host can tell a complete record from a stale or torn one
             const uint32_t w0 = __float_as_uint(out.mass1), w1 = __float_as_uint(out.mass2);
-            const uint32_t w2 = (batch << 1) | (out.accepted & 1u);
+            const uint32_t w2 = (batch << 3) | ((out.pad[0] & 3u) << 1) | (out.accepted & 1u);
             const uint32_t w3 = outcome_check(w0, w1, w2);
             asm volatile("st.volatile.global.v4.u32 [%0], {%1, %2, %3, %4};"
                          ::"l"(sp.outcomes + in.pi), "r"(w0), "r"(w1), "r"(w2), "r"(w3) : "memory");

@@ -7,16 +7,6 @@
 
 namespace cgb {
 
-// static_cast<uint64_t>(mDomainLength) as the reference's default build evaluates it
-// (ProposalQueue.cpp:214).  The domain length in f64 is usually exactly 2^64, which is out of range
-// for the cast; the SSE2 code path (cvttsd2si + fix-up) yields 0.  Spelled out here so the behaviour
-// does not depend on our own compiler.
-static uint64_t referenceDoubleToU64(double x)
-{
-    if (x >= 18446744073709551616.0) { return 0; }
-    return static_cast<uint64_t>(x);
-}
-
 void ProposalQueue::init(uint64_t nElements, uint64_t nPatterns, cgb_randstate *rs, float alpha, float lambda)
 {
     mQueue.clear();
@@ -29,6 +19,9 @@ void ProposalQueue::init(uint64_t nElements, uint64_t nPatterns, cgb_randstate *
     mMinAtoms = mMaxAtoms = 0;
     mBinLength = 0xFFFFFFFFFFFFFFFFull / nElements;
     mNumCols = nPatterns;
+    mBinDiv.init(mBinLength);
+    mColDiv.init(mNumCols);
+    mBirthIPart = 0xFFFFFFFFFFFFFFFFull / (mBinLength * nElements);
     mAlpha = static_cast<double>(alpha);              // setAlpha, :39-42
     mDomainLength = static_cast<double>(mBinLength * nElements);
     mNumBins = static_cast<double>(nElements);
@@ -115,8 +108,8 @@ bool ProposalQueue::birth(AtomicDomain &domain)
     prop.atom2 = kNoAtom;
     prop.r2 = prop.c2 = 0;
     // randomFreePosition, ConcurrentAtomicDomain.cpp:53-60
-    uint64_t pos = prop.rng.uniform64(1, domain.domainLength());
-    while (domain.occupied(pos)) { pos = prop.rng.uniform64(1, domain.domainLength()); }
+    uint64_t pos = prop.rng.uniform64Fixed(1, domain.domainLength(), mBirthIPart);
+    while (domain.occupied(pos)) { pos = prop.rng.uniform64Fixed(1, domain.domainLength(), mBirthIPart); }
     prop.pos = 0;
 
     if (moveOverlap(pos))
@@ -124,8 +117,7 @@ bool ProposalQueue::birth(AtomicDomain &domain)
         mRandState->seeder.rollBackOnce();
         return false;
     }
-    prop.r1 = static_cast<uint32_t>((pos / mBinLength) / mNumCols);
-    prop.c1 = static_cast<uint32_t>((pos / mBinLength) % mNumCols);
+    binOf(pos, prop.r1, prop.c1);
     if (rowUsed(prop.r1))
     {
         mRandState->seeder.rollBackOnce();
@@ -149,8 +141,7 @@ bool ProposalQueue::death(AtomicDomain &domain)
     prop.pos = 0;
     prop.atom1 = domain.atIndex(prop.rng.uniform32(0, static_cast<uint32_t>(domain.size() - 1)));
     const uint64_t p1 = domain.atom(prop.atom1).pos;
-    prop.r1 = static_cast<uint32_t>((p1 / mBinLength) / mNumCols);
-    prop.c1 = static_cast<uint32_t>((p1 / mBinLength) % mNumCols);
+    binOf(p1, prop.r1, prop.c1);
     if (rowUsed(prop.r1))
     {
         mRandState->seeder.rollBackOnce();
@@ -186,10 +177,8 @@ bool ProposalQueue::move(AtomicDomain &domain)
 
     prop.pos = prop.rng.uniform64(lbound + 1, rbound - 1);
     const uint64_t p1 = center.pos;
-    prop.r1 = static_cast<uint32_t>((p1 / mBinLength) / mNumCols);
-    prop.c1 = static_cast<uint32_t>((p1 / mBinLength) % mNumCols);
-    prop.r2 = static_cast<uint32_t>((prop.pos / mBinLength) / mNumCols);
-    prop.c2 = static_cast<uint32_t>((prop.pos / mBinLength) % mNumCols);
+    binOf(p1, prop.r1, prop.c1);
+    binOf(prop.pos, prop.r2, prop.c2);
 
     if (rowUsed(prop.r1) || rowUsed(prop.r2))
     {
@@ -220,10 +209,8 @@ bool ProposalQueue::exchange(AtomicDomain &domain)
     const uint32_t right = domain.atom(prop.atom1).right;
     prop.atom2 = (right != kNoAtom) ? right : domain.front();
     const uint64_t p1 = domain.atom(prop.atom1).pos, p2 = domain.atom(prop.atom2).pos;
-    prop.r1 = static_cast<uint32_t>((p1 / mBinLength) / mNumCols);
-    prop.c1 = static_cast<uint32_t>((p1 / mBinLength) % mNumCols);
-    prop.r2 = static_cast<uint32_t>((p2 / mBinLength) / mNumCols);
-    prop.c2 = static_cast<uint32_t>((p2 / mBinLength) % mNumCols);
+    binOf(p1, prop.r1, prop.c1);
+    binOf(p2, prop.r2, prop.c2);
 
     if (rowUsed(prop.r1) || rowUsed(prop.r2))
     {

@@ -27,6 +27,44 @@ struct HostProposal
     char type;
 };
 
+// static_cast<uint64_t>(mDomainLength) as the reference's default build evaluates it
+// (ProposalQueue.cpp:214).  The domain length in f64 is usually exactly 2^64, which is out of range
+// for the cast; the SSE2 code path (cvttsd2si + fix-up) yields 0.  Spelled out here so the behaviour
+// does not depend on our own compiler.
+inline uint64_t referenceDoubleToU64(double x)
+{
+    if (x >= 18446744073709551616.0) { return 0; }
+    return static_cast<uint64_t>(x);
+}
+
+// SingleThreadedGibbsSampler's own state (gibbs_sampler/SingleThreadedGibbsSampler.h:52-81): ONE rng stream
+// shared by proposal generation and evaluation, no queue
+struct SequentialState
+{
+    HostRng rng;
+    uint64_t binLength, numPatterns;
+    FastDivU64 binDiv, colDiv;
+    double numBins, domainLength, alpha;
+    void init(uint64_t nElements, uint64_t nPatterns, cgb_randstate *rs, float a)
+    {
+        rng = HostRng(rs->seeder);
+        numBins = static_cast<double>(nElements);
+        binLength = 0xFFFFFFFFFFFFFFFFull / nElements;
+        numPatterns = nPatterns;
+        binDiv.init(binLength);
+        colDiv.init(nPatterns);
+        domainLength = static_cast<double>(binLength * nElements);
+        alpha = static_cast<double>(a);
+    }
+    void binOf(uint64_t pos, uint32_t &row, uint32_t &col) const
+    {
+        const uint64_t bin = binDiv.div(pos);
+        const uint64_t r = colDiv.div(bin);
+        row = static_cast<uint32_t>(r);
+        col = static_cast<uint32_t>(bin - r * numPatterns);
+    }
+};
+
 // ProposalQueue (atomic/ProposalQueue.h:30-72)
 class ProposalQueue
 {
@@ -56,6 +94,14 @@ private:
     bool rowUsed(uint32_t r) const { return mUsedRows[r] == mEpoch; }
     void useRow(uint32_t r) { mUsedRows[r] = mEpoch; }
     bool moveOverlap(uint64_t pos) const;
+    // (row, col) of the matrix element a position falls in: (pos / binLength) / nPatterns, % nPatterns
+    void binOf(uint64_t pos, uint32_t &row, uint32_t &col) const
+    {
+        const uint64_t bin = mBinDiv.div(pos);
+        const uint64_t r = mColDiv.div(bin);
+        row = static_cast<uint32_t>(r);
+        col = static_cast<uint32_t>(bin - r * mNumCols);
+    }
 
     std::vector<HostProposal> mQueue;
     std::vector<uint32_t> mUsedRows;                        // FixedHashSetU32 (HashSets.cpp:5-37)
@@ -64,6 +110,8 @@ private:
     cgb_randstate *mRandState;
     HostRng mRng;
     uint64_t mMinAtoms, mMaxAtoms, mBinLength, mNumCols;
+    FastDivU64 mBinDiv, mColDiv;
+    uint64_t mBirthIPart;                                   // UINT64_MAX / domainLength: uniform64(1, domainLength)
     double mAlpha, mDomainLength, mNumBins;
     float mLambda, mU1, mU2;
     unsigned mNumProcessed;
@@ -105,6 +153,8 @@ struct cgb_sampler
     // host generator
     cgb::AtomicDomain domain;
     cgb::ProposalQueue queue;
+    bool sequential;              // asynchronousUpdates == 0: SingleThreadedGibbsSampler semantics
+    cgb::SequentialState seq;
     float avgQueueLength, numQueueSamples;
 
     // bench counters
@@ -135,6 +185,7 @@ struct cgb_sampler
     void *dStreamStats;           // cgb::StreamStats
     unsigned long long mailSeq;   // tag of the last chunk posted
     unsigned long long streamSerial; // next task serial; serial % nClusters = cluster, serial / nClusters + 1 = ticket
+    uint32_t nextCluster, nextTicket; // where serial `streamSerial` goes
     int persistentGrid;           // CTAs of the resident grid (0 until first launch)
     uint32_t nClusters;           // worker clusters of the resident grid (one more cluster mirrors the commit count)
     double lastPostTime;

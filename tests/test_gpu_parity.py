@@ -275,6 +275,31 @@ def test_sparse_run_matches_oracle(oracle, name):
         assert got.meanChiSq == 0.0
 
 
+@pytest.mark.parametrize("name", ["modsim_seq", "gist_seq", "sparse_gist_seq"])
+@pytest.mark.parametrize("resident", [True, False])
+def test_sequential_sampler_matches_oracle(oracle, name, resident, monkeypatch):
+    """asynchronousUpdates = FALSE: SingleThreadedGibbsSampler (gibbs_sampler/SingleThreadedGibbsSampler.h:94-257) —
+    one rng stream shared by generation and evaluation, birth accepts mass > epsilon, same-bin exchanges ignored.
+    This is the sampler config C1 names and the one distributed CoGAPS forces (R/DistributedCogaps.R:28-29)."""
+    import cogaps_b200 as cg
+    if not resident:
+        monkeypatch.setenv("COGAPS_PERSISTENT", "0")
+    data, unc, kw = case_inputs(name)
+    if name != "modsim_seq":
+        kw["nIterations"] = min(kw["nIterations"], 30)
+    g, s = dims(data, kw)
+    want = oracle.run(data, snapshots=True, options=device_options(oracle, g, s), **kw)
+    got = cg.gaps_run(data, snapshots=True, **kw)
+    assert np.array_equal(got.atomHistoryA, want.atomHistoryA)
+    assert np.array_equal(got.atomHistoryP, want.atomHistoryP)
+    assert got.totalUpdates == want.totalUpdates
+    assert got.averageQueueLengthA == 0.0 and got.averageQueueLengthP == 0.0
+    assert_close(got.chisqHistory, want.chisqHistory, RTOL_CHISQ, "chisqHistory")
+    for f in ("Amean", "Asd", "Pmean", "Psd"):
+        assert_close(getattr(got, f), getattr(want, f), RTOL_MEANS, f)
+    assert got.meanChiSq == pytest.approx(want.meanChiSq, rel=RTOL_CHISQ)
+
+
 def test_posterior_means_are_bit_identical(oracle):
     """Stronger than the stated tolerance: with the oracle in the device's reduction order the whole
     chain — every atom, every mass — is reproduced to the last bit."""
@@ -285,6 +310,21 @@ def test_posterior_means_are_bit_identical(oracle):
     got = cg.gaps_run(data, snapshots=True, **kw)
     for f in ("Amean", "Asd", "Pmean", "Psd", "snapshotsA", "snapshotsP"):
         assert np.array_equal(bits(getattr(got, f)), bits(getattr(want, f))), f
+
+
+@pytest.mark.parametrize("name", ["gist_async", "syn_203x117", "sparse_120x90"])
+def test_launch_per_batch_and_resident_grid_give_the_same_chain(name, monkeypatch):
+    """cgb_sampler_set_persistent: the resident streaming grid and one kernel launch per conflict-free batch run
+    the same device code on the same proposals, so every output bit agrees."""
+    import cogaps_b200 as cg
+    data, unc, kw = case_inputs(name, nIterations=40, snapshotFrequency=20)
+    resident = cg.gaps_run(data, snapshots=True, **kw)
+    monkeypatch.setenv("COGAPS_PERSISTENT", "0")
+    launched = cg.gaps_run(data, snapshots=True, **kw)
+    assert np.array_equal(resident.atomHistoryA, launched.atomHistoryA)
+    assert launched.nBatchesA > 0 and resident.nBatchesA > 0
+    for f in ("Amean", "Asd", "Pmean", "Psd", "snapshotsA", "snapshotsP", "chisqHistory"):
+        assert np.array_equal(bits(getattr(resident, f)), bits(getattr(launched, f))), f
 
 
 def test_long_rows_use_clusters(oracle):
