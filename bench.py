@@ -63,7 +63,8 @@ def load_peaks():
 
 
 class ClockSampler(object):
-    """nvidia-smi clocks / throttle reasons sampled during the timed region."""
+    """nvidia-smi clocks / throttle reasons, sampled every 100 ms from before the ramp; the JSON line reports the
+    samples that fall inside the timed region (plus the nearest one on either side when the region is short)."""
     Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
          "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
          "clocks_event_reasons.sw_power_cap")
@@ -71,9 +72,10 @@ class ClockSampler(object):
     def __init__(self, index):
         self.rows = []
         self.proc = None
+        self.t_begin = self.t_end = None
         try:
             self.proc = subprocess.Popen(["nvidia-smi", "-i", str(index), "--query-gpu=" + self.Q,
-                                          "--format=csv,noheader,nounits", "-lms", "200"],
+                                          "--format=csv,noheader,nounits", "-lms", "100"],
                                          stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             self.thread = threading.Thread(target=self._read, daemon=True)
             self.thread.start()
@@ -82,19 +84,32 @@ class ClockSampler(object):
 
     def _read(self):
         for line in self.proc.stdout:
-            self.rows.append(line.strip())
+            self.rows.append((time.perf_counter(), line.strip()))
+
+    def begin(self):
+        self.t_begin = time.perf_counter()
+
+    def end(self):
+        self.t_end = time.perf_counter()
 
     def stop(self):
         if self.proc is None:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)   # let the sample that covers the end of the region arrive
         self.proc.terminate()
         try:
             self.proc.wait(timeout=5)
         except subprocess.TimeoutExpired:
             self.proc.kill()
+        t0 = self.t_begin if self.t_begin is not None else 0.0
+        t1 = self.t_end if self.t_end is not None else float("inf")
+        inside = [r for r in self.rows if t0 <= r[0] <= t1]
+        before = [r for r in self.rows if r[0] < t0][-1:]
+        after = [r for r in self.rows if r[0] > t1][:1]
+        chosen = inside if len(inside) >= 2 else before + inside + after
         sm, mx, reasons = [], [], set()
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        for row in self.rows:
+        for _, row in chosen:
             parts = [p.strip() for p in row.split(",")]
             if len(parts) < 7:
                 continue
@@ -107,7 +122,7 @@ class ClockSampler(object):
                 if val.lower().startswith("active"):
                     reasons.add(name)
         return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
-                "reasons": sorted(reasons), "samples": len(sm)}
+                "reasons": sorted(reasons), "samples": len(sm), "samples_inside_timed_region": len(inside)}
 
 
 class Chain(object):
@@ -167,7 +182,7 @@ def run_reference(args, data):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--steps", type=int, default=40)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--ramp", type=int, default=RAMP_ITERS)
@@ -220,6 +235,7 @@ def main():
     check(cg.lib().cgb_set_device(local_rank))
 
     data = make_data(args.rows, args.cols, args.patterns, DATA_SEED + rank)
+    clocks = ClockSampler(local_rank)
     t_setup = time.time()
     chain = Chain(data, args.patterns, CHAIN_SEED + rank)
     chain.ramp(args.ramp)
@@ -237,14 +253,15 @@ def main():
     chain.A.resetCounters()
     chain.P.resetCounters()
     launches0 = cg.lib().cgb_kernel_launch_count()
-    clocks = ClockSampler(local_rank)
     barrier()
+    clocks.begin()
     t0 = time.perf_counter()
     updates = 0
     for _ in range(args.steps):
         updates += chain.step()
     barrier()
     elapsed = time.perf_counter() - t0
+    clocks.end()
     clock_info = clocks.stop()
     launches = cg.lib().cgb_kernel_launch_count() - launches0
     cA, cP = chain.A.counters(), chain.P.counters()
@@ -267,19 +284,17 @@ def main():
         elapsed_max, total_updates, total_launches = elapsed, float(updates), int(launches)
     value = total_updates / elapsed_max
 
-    # ---- roofline pass: per-launch CUDA events on the launching stream (separate from the timed region) ----
+    # ---- roofline: the eval kernel of the timed region itself.  The resident kernel is launched once per
+    # update() (2 per step); its duration comes from CUDA events on its stream, its bytes are the algorithmic
+    # bytes of the proposals it evaluated.  The duration includes the time the grid waits for the
+    # host generator: that is the launch as it runs in the product.
     roofline = None
     if rank == 0:
-        # (a) the resident grid's own clock: bytes over the time the device spent on each batch
-        chain.A.resetCounters()
-        chain.P.resetCounters()
-        for _ in range(2):
-            chain.step()
-        bA, bP = chain.A.counters(), chain.P.counters()
-        busy = {"GBps": (bA.algorithmicBytes + bP.algorithmicBytes) / max(bA.secondsKernel + bP.secondsKernel, 1e-12) / 1e9,
-                "avg_batch_us": (bA.secondsKernel + bP.secondsKernel) / max(bA.nBatches + bP.nBatches, 1) * 1e6,
-                "how": "resident kernel, whole launch (one per update()) timed with CUDA events on its stream: includes the time the grid waits for the host generator"}
-        # (b) the same device code launched once per batch, each launch bracketed by CUDA events on its stream
+        peak, peak_src = load_peaks()
+        resident_bytes = cA.algorithmicBytes + cP.algorithmicBytes
+        resident_time = cA.secondsKernel + cP.secondsKernel
+        n_launch = 2 * args.steps
+        # the same device code launched once per conflict-free batch, each launch bracketed by CUDA events
         for smp in (chain.A, chain.P):
             smp.setPersistent(False)
             smp.setKernelTiming(True)
@@ -290,28 +305,42 @@ def main():
         for smp in (chain.A, chain.P):
             smp.setKernelTiming(False)
             smp.setPersistent(True)
-        peak, peak_src = load_peaks()
         bytes_total = rA.algorithmicBytes + rP.algorithmicBytes
         ktime = rA.secondsKernel + rP.secondsKernel
-        achieved = bytes_total / ktime / 1e9
         traffic = None
         tpath = os.path.join(ROOT, "profiles", "eval_kernel_traffic.json")
         if os.path.exists(tpath):
             with open(tpath) as f:
                 traffic = json.load(f).get("dram_bytes_per_launch")
-        roofline = {"bound": "hbm", "kernel": "eval_kernel (alphaParameters scan + epilogue + AP commit)",
-                    "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                    "peak_source": peak_src, "traffic": traffic,
-                    "how": "per-batch launches of eval_kernel, cudaEvent pairs on the launching stream, 2 steps",
-                    "persistent_grid": busy,
-                    "algorithmic_bytes_per_launch": bytes_total / max(rA.nBatches + rP.nBatches, 1),
-                    "avg_launch_us": ktime / max(rA.nBatches + rP.nBatches, 1) * 1e6,
-                    "A_side": {"GBps": rA.algorithmicBytes / max(rA.secondsKernel, 1e-12) / 1e9,
-                               "avg_launch_us": rA.secondsKernel / max(rA.nBatches, 1) * 1e6,
-                               "proposals_per_launch": rA.nProposalsQueued / max(rA.nBatches, 1)},
-                    "P_side": {"GBps": rP.algorithmicBytes / max(rP.secondsKernel, 1e-12) / 1e9,
-                               "avg_launch_us": rP.secondsKernel / max(rP.nBatches, 1) * 1e6,
-                               "proposals_per_launch": rP.nProposalsQueued / max(rP.nBatches, 1)}}
+        resident = os.environ.get("COGAPS_PERSISTENT", "1") != "0"
+        per_batch = {"kernel": "eval_kernel (one launch per conflict-free batch; same device code)",
+                     "achieved": bytes_total / ktime / 1e9, "frac": bytes_total / ktime / 1e9 / peak,
+                     "algorithmic_bytes_per_launch": bytes_total / max(rA.nBatches + rP.nBatches, 1),
+                     "avg_launch_us": ktime / max(rA.nBatches + rP.nBatches, 1) * 1e6,
+                     "traffic": traffic,
+                     "A_side": {"GBps": rA.algorithmicBytes / max(rA.secondsKernel, 1e-12) / 1e9,
+                                "avg_launch_us": rA.secondsKernel / max(rA.nBatches, 1) * 1e6,
+                                "proposals_per_launch": rA.nProposalsQueued / max(rA.nBatches, 1)},
+                     "P_side": {"GBps": rP.algorithmicBytes / max(rP.secondsKernel, 1e-12) / 1e9,
+                                "avg_launch_us": rP.secondsKernel / max(rP.nBatches, 1) * 1e6,
+                                "proposals_per_launch": rP.nProposalsQueued / max(rP.nBatches, 1)},
+                     "how": "cudaEvent pair around every launch on the launching stream, 2 steps after the timed region"}
+        if resident and resident_time > 0:
+            achieved = resident_bytes / resident_time / 1e9
+            roofline = {"bound": "hbm", "kernel": "eval_stream_kernel (resident grid: alphaParameters scan + epilogue + AP commit)",
+                        "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                        "peak_source": peak_src, "traffic": None,
+                        "algorithmic_bytes_per_launch": resident_bytes / n_launch,
+                        "avg_launch_us": resident_time / n_launch * 1e6, "launches": n_launch,
+                        "how": "timed region: one launch per update(), cudaEvent pair on its stream; bytes = SURVEY 8(d) "
+                               "algorithmic bytes of the proposals evaluated; includes the time the grid waits for the host generator",
+                        "per_batch_launch": per_batch}
+        else:
+            roofline = {"bound": "hbm", "kernel": per_batch["kernel"], "achieved": per_batch["achieved"], "peak": peak,
+                        "unit": "GB/s", "frac": per_batch["frac"], "peak_source": peak_src, "traffic": traffic,
+                        "algorithmic_bytes_per_launch": per_batch["algorithmic_bytes_per_launch"],
+                        "avg_launch_us": per_batch["avg_launch_us"], "how": per_batch["how"],
+                        "A_side": per_batch["A_side"], "P_side": per_batch["P_side"]}
         # chi-sq wall time (second half of BASELINE.json's metric)
         tcs = time.perf_counter()
         for _ in range(5):
@@ -331,8 +360,8 @@ def main():
         upload = 2.0 * data.nbytes
         results = 4.0 * 2 * (args.rows + args.cols) * args.patterns
         e2e = {"value": res.totalUpdates / wall, "unit": "atom-updates/s",
-               "h2d_bytes_per_step": (upload + 48.0 * res.totalUpdates) / n_it,
-               "d2h_bytes_per_step": (results + 32.0 * res.totalUpdates) / n_it,
+               "h2d_bytes_per_step": (upload + h2d_step * args.steps / max(updates, 1) * res.totalUpdates) / n_it,
+               "d2h_bytes_per_step": (results + 16.0 * res.totalUpdates) / n_it,
                "call": "cgb_run (gaps::run): host fp32 matrix in, Amean/Asd/Pmean/Psd out",
                "iterations_per_phase": args.e2e_iters, "atom_updates": int(res.totalUpdates), "wall_s": wall}
 

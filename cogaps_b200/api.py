@@ -197,8 +197,10 @@ def CoGAPS(data, params=None, nPatterns=None, nThreads=1, messages=True, outputF
         raise ValueError("checkpoints not supported in this build")  # R/HelperFunctions.R:225-226
     if params.distributed is not None:
         from .distributed import distributedCogaps
+        # the reference forces the sequential sampler here (R/DistributedCogaps.R:28-29); we follow the caller
         return distributedCogaps(data, params, uncertainty, nThreads=nThreads, messages=messages,
-                                 outputFrequency=outputFrequency, transposeData=transposeData)
+                                 outputFrequency=outputFrequency, transposeData=transposeData,
+                                 sequentialSampler=not asynchronousUpdates)
     nGenes, nSamples = (data.shape[1], data.shape[0]) if transposeData else data.shape
     if params.nPatterns >= min(nGenes, nSamples) and params.subsetDim == 0:
         pass  # R only warns here

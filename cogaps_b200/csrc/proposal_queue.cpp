@@ -5,6 +5,7 @@
 // the bin-indexed AtomicDomain instead of std::map).
 #include "sampler.h"
 
+
 namespace cgb {
 
 void ProposalQueue::init(uint64_t nElements, uint64_t nPatterns, cgb_randstate *rs, float alpha, float lambda)

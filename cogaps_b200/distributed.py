@@ -15,9 +15,11 @@ process group everything runs in this process, one subset after another.
 
 Differences from the reference, on purpose: R's `sample()` stream is not reproducible outside R, so subsets are drawn
 with numpy's PCG64 seeded by `params.seed` (same partition rule: floor(total/nSets) per set, remainder to the last,
-each sorted); and the reference forces its *sequential* sampler inside distributed runs (R/DistributedCogaps.R:28-29)
-while the device path is the asynchronous sampler.  `agnes(..., "complete")` + `cutree` is scipy's complete linkage
-on the same 1 - correlation dissimilarity.
+each sorted).  The reference forces its *sequential* sampler inside distributed runs
+(`allParams$asynchronousUpdates <- FALSE`, R/DistributedCogaps.R:28-29); pass `sequentialSampler=True` for exactly
+that chain on the device (one proposal per host<->device round trip), the default keeps the asynchronous sampler,
+which samples the same posterior and is what a GPU is for.  `agnes(..., "complete")` + `cutree` is scipy's complete
+linkage on the same 1 - correlation dissimilarity.
 """
 import copy
 
@@ -179,7 +181,7 @@ def _default_runner(data, params, uncertainty, subset, subsetDim, runKw):
 
 
 def distributedCogaps(data, params, uncertainty=None, nThreads=1, messages=False, outputFrequency=1000,
-                      transposeData=False, runner=None, device=None):
+                      transposeData=False, runner=None, device=None, sequentialSampler=False):
     """distributedCogaps (R/DistributedCogaps.R:48-119).  Returns a CogapsResult-like object."""
     from .api import CogapsResult
     dist = _dist()
@@ -201,7 +203,7 @@ def distributedCogaps(data, params, uncertainty=None, nThreads=1, messages=False
     subsetDim = 1 if genomeWide else 2
     mine = list(range(rank, len(sets), world))
     runKw = dict(nThreads=nThreads, messages=bool(messages) and rank == 0, outputFrequency=outputFrequency,
-                 uncertainty=uncertainty, transposeData=transposeData)
+                 uncertainty=uncertainty, transposeData=transposeData, asynchronousUpdates=not sequentialSampler)
     counts = [len(s) for s in sets]
     nOther = (ncol if subsetRows else nrow)              # length of the un-partitioned dimension
 

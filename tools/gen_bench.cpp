@@ -17,7 +17,8 @@ int main(int argc, char **argv)
     AtomicDomain domain;
     ProposalQueue queue;
     domain.init(static_cast<uint64_t>(nRows) * k);
-    queue.init(static_cast<uint64_t>(nRows) * k, k, &rs, 0.01f, 0.05f);
+    const float alpha = argc > 4 ? std::atof(argv[4]) : 0.0228f; // alpha * nBins / (1 - accept imbalance) sets the steady size
+    queue.init(static_cast<uint64_t>(nRows) * k, k, &rs, alpha, 0.05f);
     HostRng orng(rs.seeder);
     uint64_t total = 0, batches = 0, queued = 0;
     double tGen = 0, tApply = 0;

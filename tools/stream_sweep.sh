@@ -1,8 +1,6 @@
 #!/bin/bash
 # resident-kernel knob sweep at the bench workload (debug)
-grep MHz /proc/cpuinfo | head -2
-for m in "0 0" "0 1" "1 1"; do
-  set -- $m
-  echo "=== COGAPS_RECORD_STORES=$1 COGAPS_HOST_PROFILE=$2"
-  COGAPS_RECORD_STORES=$1 COGAPS_HOST_PROFILE=$2 timeout 200 python tools/stream_debug.py 2>&1 | tail -7
+for m in 0 1 0 1; do
+  echo "=== COGAPS_GEN_PREFETCH=$m"
+  COGAPS_GEN_PREFETCH=$m timeout 200 python tools/stream_debug.py 2>&1 | tail -3
 done
