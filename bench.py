@@ -42,8 +42,9 @@ RAMP_ITERS = 50          # untimed iterations growing the chain from zero atoms 
 E2E_ITERS = 30           # iterations per phase of the end-to-end / reference gaps::run call
 
 
-def make_data(g=G, s=S, k=K, seed=DATA_SEED):
-    """SURVEY 8(d) C3 recipe: noisy non-negative rank-k matrix, max < 50, fp32."""
+def make_data(g=G, s=S, k=K, seed=DATA_SEED, zero_fraction=0.0):
+    """SURVEY 8(d) C3 recipe: noisy non-negative rank-k matrix, max < 50, fp32; C4: the same with
+    `zero_fraction` of the entries zeroed uniformly at random."""
     rng = np.random.default_rng(seed)
     a0 = (rng.gamma(2.0, 0.5, (g, k)) * (rng.random((g, k)) < 0.3)).astype(np.float32)
     p0 = (rng.gamma(2.0, 0.5, (s, k)) * (rng.random((s, k)) < 0.3)).astype(np.float32)
@@ -51,6 +52,11 @@ def make_data(g=G, s=S, k=K, seed=DATA_SEED):
     noise = rng.standard_normal(m.shape, dtype=np.float32)
     d = np.maximum(m * (1.0 + 0.1 * noise), 0.0)
     d *= np.float32(40.0 / max(float(d.max()), 1e-9))
+    del m, noise
+    if zero_fraction > 0.0:
+        for r0 in range(0, g, 4096):          # row blocks: keeps the mask's footprint small at 50000x30000
+            blk = d[r0:r0 + 4096]
+            blk[rng.random(blk.shape, dtype=np.float32) < zero_fraction] = 0.0
     return np.ascontiguousarray(d, dtype=np.float32)
 
 
@@ -128,11 +134,11 @@ class ClockSampler(object):
 class Chain(object):
     """Both samplers of one factorisation, driven like runOnePhase (GapsRunner.cpp:272-327)."""
 
-    def __init__(self, data, k, seed):
+    def __init__(self, data, k, seed, sparse=False):
         import cogaps_b200 as cg
         from cogaps_b200._runhelp import make_params
         self.cg = cg
-        self.params = make_params(nPatterns=k, seed=seed)
+        self.params = make_params(nPatterns=k, seed=seed, useSparseOptimization=1 if sparse else 0)
         self.rs = cg.GapsRandomState(seed)
         # GapsRunner.cpp:402-406: A sampler sees the data transposed, P sampler as given
         self.A = cg.GibbsSampler(data, True, True, 0.01, 100.0, self.params, self.rs)
@@ -169,8 +175,8 @@ def run_reference(args, data):
     ref = RefLib(variant)
     threads = ref.max_threads()
     t0 = time.time()
-    res = ref.run(data, seed=CHAIN_SEED, nPatterns=K, nIterations=args.e2e_iters, outputFrequency=0,
-                  maxThreads=threads)
+    res = ref.run(data, seed=CHAIN_SEED, nPatterns=args.patterns, nIterations=args.e2e_iters, outputFrequency=0,
+                  maxThreads=threads, useSparseOptimization=1 if args.sparse else 0)
     wall = res.totalRunningTime
     value = res.totalUpdates / wall
     sample = ("one gaps::run call, %d iterations/phase from zero atoms, %d atom updates, %.1f s in gaps::run "
@@ -192,26 +198,35 @@ def main():
     ap.add_argument("--patterns", type=int, default=K)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--sparse", action="store_true",
+                    help="BASELINE.json configs[3]: sparseOptimization (SparseGibbsSampler) on a matrix with --zeros of its "
+                         "entries zeroed; give the shape with --rows/--cols/--patterns (50000 30000 50 for C4)")
+    ap.add_argument("--zeros", type=float, default=0.95)
     args = ap.parse_args()
 
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
     workload = "synthetic dense %dx%d nPatterns=%d" % (args.rows, args.cols, args.patterns)
+    if args.sparse:
+        workload = "synthetic sparse %dx%d (%.0f%% zeros) nPatterns=%d" % (args.rows, args.cols, 100 * args.zeros, args.patterns)
     config = {"workload": workload, "data_seed": DATA_SEED, "chain_seed": CHAIN_SEED,
-              "sampler": "asynchronous, dense normal model, default uncertainty",
+              "sampler": "asynchronous, sparse normal model (sparseOptimization)" if args.sparse
+              else "asynchronous, dense normal model, default uncertainty",
               "step": "one MCMC iteration: A.update(Poisson(atomsA)) + P.sync + P.update(Poisson(atomsP)) + A.sync",
               "ramp_iterations": args.ramp,
               "device_mode": "resident grid per update(); each proposal streamed to its cluster through pinned host memory as it is generated; per-row commit versions instead of grid barriers"
               if os.environ.get("COGAPS_PERSISTENT", "1") != "0" else "one eval-kernel launch per batch",
-              "l2": "inputs larger than L2: 1.6 GB of resident D/AP streamed ~40 GB per step, no flush needed",
+              "l2": ("sparse model: per-proposal traffic is gathers of factor rows (k floats) at the row's non-zeros; "
+                     "the CSR rows + both factors exceed L2 at 50000x30000, no flush needed") if args.sparse
+              else "inputs larger than L2: 1.6 GB of resident D/AP streamed ~40 GB per step, no flush needed",
               "parallelism": "replicas x%d (one independent chain per GPU, no data-path collective)" % world
               if world > 1 else "single chain"}
 
     if args.impl == "reference":
         if rank != 0:
             return 0
-        data = make_data(args.rows, args.cols, args.patterns)
+        data = make_data(args.rows, args.cols, args.patterns, DATA_SEED, args.zeros if args.sparse else 0.0)
         value, wall, updates, threads, sample = run_reference(args, data)
         line = {"impl": "reference", "metric": "atom_updates_per_s", "value": value, "unit": "atom-updates/s",
                 "n_gpus": args.gpus, "steps": 1, "warmup": 0, "ms_per_step": wall * 1e3,
@@ -234,10 +249,10 @@ def main():
     from cogaps_b200._lib import check
     check(cg.lib().cgb_set_device(local_rank))
 
-    data = make_data(args.rows, args.cols, args.patterns, DATA_SEED + rank)
+    data = make_data(args.rows, args.cols, args.patterns, DATA_SEED + rank, args.zeros if args.sparse else 0.0)
     clocks = ClockSampler(local_rank)
     t_setup = time.time()
-    chain = Chain(data, args.patterns, CHAIN_SEED + rank)
+    chain = Chain(data, args.patterns, CHAIN_SEED + rank, sparse=args.sparse)
     chain.ramp(args.ramp)
     for _ in range(args.warmup):
         chain.step()
@@ -354,7 +369,7 @@ def main():
     if rank == 0 and not args.no_e2e:
         t0 = time.perf_counter()
         res = cg.gaps_run(data, seed=CHAIN_SEED, nPatterns=args.patterns, nIterations=args.e2e_iters,
-                          outputFrequency=0, maxThreads=1)
+                          outputFrequency=0, maxThreads=1, useSparseOptimization=1 if args.sparse else 0)
         wall = time.perf_counter() - t0
         n_it = 2 * args.e2e_iters
         upload = 2.0 * data.nbytes

@@ -12,6 +12,7 @@
 #include <cstring>
 #include <new>
 #include <string>
+#include <thread>
 
 using namespace cgb;
 
@@ -230,6 +231,37 @@ static void orientData(const float *data, uint32_t nrow, uint32_t ncol, bool col
     nRows = nSamples;
     ld = roundUp(L, 32);
     out.assign(static_cast<size_t>(nRows) * ld, padValue);
+    if (!subsetData)
+    {
+        // whole matrix: result(i, j) is data(j, i) when genes are in columns, data(i, j) otherwise; in memory
+        // that is either row-by-row copies or a cache-blocked transpose
+        const bool straight = (genesInCols != colmajor); // out row j is contiguous in the input
+        if (straight)
+        {
+            for (uint32_t j = 0; j < nSamples; ++j)
+            {
+                std::memcpy(&out[static_cast<size_t>(j) * ld], data + static_cast<size_t>(j) * nGenes, sizeof(float) * nGenes);
+            }
+        }
+        else
+        {
+            const uint32_t B = 32;
+            for (uint32_t j0 = 0; j0 < nSamples; j0 += B)
+            {
+                const uint32_t j1 = std::min(nSamples, j0 + B);
+                for (uint32_t i0 = 0; i0 < nGenes; i0 += B)
+                {
+                    const uint32_t i1 = std::min(nGenes, i0 + B);
+                    for (uint32_t i = i0; i < i1; ++i)
+                    {
+                        const float *src = data + static_cast<size_t>(i) * nSamples;
+                        for (uint32_t j = j0; j < j1; ++j) { out[static_cast<size_t>(j) * ld + i] = src[j]; }
+                    }
+                }
+            }
+        }
+        return;
+    }
     for (uint32_t j = 0; j < nSamples; ++j)
     {
         for (uint32_t i = 0; i < nGenes; ++i)
@@ -305,9 +337,22 @@ static const int kReduceBlocks = 592; // 148 SMs x 4
 // erf + erfinv tables the resident kernel keeps in shared memory behind the staging buffers
 static const size_t kStreamTableBytes = (((CGB_ERF_TABLE_SIZE + 3) & ~3) + ((CGB_ERFINV_TABLE_SIZE + 3) & ~3)) * sizeof(float);
 
-extern "C" int cgb_sampler_create(const float *data, uint32_t nrow, uint32_t ncol, int32_t colmajor,
-                                  int32_t transpose, int32_t subsetRows, float alpha, float maxGibbsMass,
-                                  const cgb_params *params, cgb_randstate *rs, cgb_sampler **out)
+// The sampler's generator (domain + queue / sequential state).  Separate from the data preparation because
+// this is where seeds are taken from the shared random state, in construction order (A first, then P).
+static void initGenerator(cgb_sampler *s, const cgb_params *params, cgb_randstate *rs)
+{
+    // AsynchronousGibbsSampler ctor, AsynchronousGibbsSampler.h:63-76: domain over nRows*k bins, queue
+    // rng seeded from the shared state
+    const uint64_t nElements = static_cast<uint64_t>(s->nRows) * s->k;
+    s->domain.init(nElements);
+    s->sequential = params->asynchronousUpdates == 0;
+    if (s->sequential) { s->seq.init(nElements, s->k, rs, s->alpha); } // SingleThreadedGibbsSampler.h:66-81
+    else { s->queue.init(nElements, s->k, rs, s->alpha, s->lambda); }
+}
+
+static int samplerCreateImpl(const float *data, uint32_t nrow, uint32_t ncol, int32_t colmajor,
+                             int32_t transpose, int32_t subsetRows, float alpha, float maxGibbsMass,
+                             const cgb_params *params, cgb_randstate *rs, bool withGenerator, cgb_sampler **out)
 {
     CGB_CHECK(data && params && rs && out, "cgb_sampler_create: NULL argument");
     CGB_CHECK(params->struct_size == sizeof(cgb_params), "cgb_sampler_create: cgb_params ABI mismatch");
@@ -464,15 +509,16 @@ extern "C" int cgb_sampler_create(const float *data, uint32_t nrow, uint32_t nco
         return rc;
     }
 
-    // AsynchronousGibbsSampler ctor, AsynchronousGibbsSampler.h:63-76: domain over nRows*k bins, queue
-    // rng seeded from the shared state (this is where the seed consumption order is fixed)
-    const uint64_t nElements = static_cast<uint64_t>(s->nRows) * s->k;
-    s->domain.init(nElements);
-    s->sequential = params->asynchronousUpdates == 0;
-    if (s->sequential) { s->seq.init(nElements, s->k, rs, alpha); } // SingleThreadedGibbsSampler.h:66-81
-    else { s->queue.init(nElements, s->k, rs, alpha, s->lambda); }
+    if (withGenerator) { initGenerator(s, params, rs); }
     *out = s;
     return CGB_OK;
+}
+
+extern "C" int cgb_sampler_create(const float *data, uint32_t nrow, uint32_t ncol, int32_t colmajor,
+                                  int32_t transpose, int32_t subsetRows, float alpha, float maxGibbsMass,
+                                  const cgb_params *params, cgb_randstate *rs, cgb_sampler **out)
+{
+    return samplerCreateImpl(data, nrow, ncol, colmajor, transpose, subsetRows, alpha, maxGibbsMass, params, rs, true, out);
 }
 
 extern "C" int cgb_sampler_set_uncertainty(cgb_sampler *s, const float *unc, uint32_t nrow, uint32_t ncol,
@@ -1893,9 +1939,26 @@ extern "C" int cgb_run(const float *data, uint32_t nrow, uint32_t ncol, int32_t 
     RunGuard g;
     CGB_TRY(cgb_randstate_create(p->seed, &g.rs));
     if (g_tableOverride[0]) { CGB_TRY(cgb_randstate_set_tables(g.rs, g_tableOverride[0], g_tableOverride[1], g_tableOverride[2])); }
-    // GapsRunner.cpp:402-406: A first, then P — this fixes which seeds the two queue rngs get
-    CGB_TRY(cgb_sampler_create(data, nrow, ncol, colmajor, !p->transposeData, !p->subsetGenes, p->alphaA, p->maxGibbsMassA, p, g.rs, &g.A));
-    CGB_TRY(cgb_sampler_create(data, nrow, ncol, colmajor, p->transposeData, p->subsetGenes, p->alphaP, p->maxGibbsMassP, p, g.rs, &g.P));
+    // GapsRunner.cpp:402-406.  The two orientations are prepared concurrently (each is a pass over the whole
+    // matrix on the host: orientation, the fp32 running sum behind lambda, upload); the generators are then
+    // built A first, P second — that fixes which seeds the two queue rngs get.
+    CGB_TRY(ensureDevice());
+    CGB_TRY(uploadTables(g.rs));
+    {
+        int rcP = CGB_OK;
+        std::string errP;
+        std::thread prepP([&]()
+        {
+            rcP = samplerCreateImpl(data, nrow, ncol, colmajor, p->transposeData, p->subsetGenes, p->alphaP, p->maxGibbsMassP, p, g.rs, false, &g.P);
+            if (rcP != CGB_OK) { errP = g_lastError; }
+        });
+        const int rcA = samplerCreateImpl(data, nrow, ncol, colmajor, !p->transposeData, !p->subsetGenes, p->alphaA, p->maxGibbsMassA, p, g.rs, false, &g.A);
+        prepP.join();
+        if (rcA != CGB_OK) { return rcA; }
+        if (rcP != CGB_OK) { return fail(rcP, errP); }
+        initGenerator(g.A, p, g.rs);
+        initGenerator(g.P, p, g.rs);
+    }
     if (uncertainty)
     {
         CGB_TRY(cgb_sampler_set_uncertainty(g.A, uncertainty, nrow, ncol, colmajor, !p->transposeData, !p->subsetGenes, p));
