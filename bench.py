@@ -356,6 +356,35 @@ def main():
                         "algorithmic_bytes_per_launch": per_batch["algorithmic_bytes_per_launch"],
                         "avg_launch_us": per_batch["avg_launch_us"], "how": per_batch["how"],
                         "A_side": per_batch["A_side"], "P_side": per_batch["P_side"]}
+        # ---- the scan kernel with enough work: alphaParameters probes (DenseNormalModel.cpp:162-240 through the same
+        # staging + scan + reduce code, no proposal epilogue), every row once, ONE launch (probe_kernel), CUDA events
+        # around it.  This is what the kernel sustains when the generator is not the limit.
+        if not args.sparse:
+            rngq = np.random.default_rng(5)
+            sat = {}
+            for nm, smp, nrows in (("A", chain.A, args.rows), ("P", chain.P, args.cols)):
+                rows_q = rngq.permutation(nrows)
+                nq = rows_q.size
+                variant = (rngq.random(nq) < 0.5).astype(np.float64)       # half single-column, half same-row pairs
+                c1 = rngq.integers(0, args.patterns, nq)
+                c2 = (c1 + 1 + rngq.integers(0, args.patterns - 1, nq)) % args.patterns
+                q = np.stack([variant, rows_q, c1, rows_q, c2, np.zeros(nq)], axis=1)
+                smp.alphaParameters(q[:1024])                                # warm-up launch
+                smp.setKernelTiming(True)
+                smp.resetCounters()
+                smp.alphaParameters(q)
+                c = smp.counters()
+                smp.setKernelTiming(False)
+                L = args.cols if nm == "A" else args.rows
+                nbytes = float(((variant == 0) * 16.0 + (variant == 1) * 20.0).sum()) * L
+                sat[nm] = {"GBps": nbytes / max(c.secondsKernel, 1e-12) / 1e9, "launches": int(c.nBatches),
+                           "avg_launch_us": c.secondsKernel / max(c.nBatches, 1) * 1e6, "tasks": int(nq), "row_length": int(L)}
+            tot_b = sum(v["GBps"] * v["avg_launch_us"] * v["launches"] for v in sat.values())
+            tot_t = sum(v["avg_launch_us"] * v["launches"] for v in sat.values())
+            roofline["scan_saturated"] = {"achieved": tot_b / tot_t, "frac": tot_b / tot_t / peak, "A_side": sat["A"], "P_side": sat["P"],
+                                          "how": "cgb_sampler_alpha_parameters: the eval kernel's staging + scan + reduce on one "
+                                                 "(row, column) probe per row, all rows in one launch, cudaEvent pair around it; "
+                                                 "bytes = 16 L (one column) or 20 L (two columns of one row) per probe"}
         # chi-sq wall time (second half of BASELINE.json's metric)
         tcs = time.perf_counter()
         for _ in range(5):

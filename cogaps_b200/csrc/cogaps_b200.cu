@@ -291,7 +291,7 @@ static int checkSubset(const cgb_params *p, uint32_t nrow, uint32_t ncol)
 static void segmentsForLength(uint32_t L, uint32_t &nSeg, uint32_t &seg)
 {
     const uint32_t target = static_cast<uint32_t>(envInt("COGAPS_SEG_FLOATS", 5120));
-    const uint32_t maxCluster = static_cast<uint32_t>(envInt("COGAPS_MAX_CLUSTER", 4));
+    const uint32_t maxCluster = static_cast<uint32_t>(envInt("COGAPS_MAX_CLUSTER", 8));
     uint32_t n = 1;
     while (n < maxCluster && n < static_cast<uint32_t>(kMaxCluster) && (L + n - 1) / n > target) { n *= 2; }
     nSeg = n;
@@ -493,10 +493,12 @@ static int samplerCreateImpl(const float *data, uint32_t nrow, uint32_t ncol, in
         CGB_CUDA_BREAK(cudaMemset(s->dTickets, 0, sizeof(uint32_t) * kMaxPersistentBatch));
         CGB_CUDA_BREAK(cudaFuncSetAttribute(eval_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
         CGB_CUDA_BREAK(cudaFuncSetAttribute(eval_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+        CGB_CUDA_BREAK(cudaFuncSetAttribute(probe_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+        CGB_CUDA_BREAK(cudaFuncSetAttribute(probe_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
         CGB_CUDA_BREAK(cudaFuncSetAttribute(eval_stream_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024 - 1024));
         CGB_CUDA_BREAK(cudaFuncSetAttribute(eval_stream_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024 - 1024));
         CGB_CUDA_BREAK(cudaFuncSetAttribute(eval_stream_sparse_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
-        if (s->smemBytes + kStreamTableBytes > 226u * 1024u)
+        if (!s->sparse && s->smemBytes + kStreamTableBytes > 226u * 1024u)
         {
             rc = fail(CGB_EUNSUPPORTED, "row length too large for one cluster of staged segments (raise COGAPS_MAX_CLUSTER)");
             break;
@@ -1464,30 +1466,87 @@ extern "C" int cgb_sampler_alpha_parameters(cgb_sampler *s, uint32_t n, const in
     CGB_CUDA(cudaSetDevice(s->device));
     static thread_local EvalParams params;
     fillModelView(s, params.mv);
-    uint32_t done = 0;
-    while (done < n)
+    std::vector<DevProposal> all(n);
+    std::vector<uint32_t> bulk, rest; // single-row queries go out in one launch; two-row ones need the pairing path
+    for (uint32_t j = 0; j < n; ++j)
     {
-        const uint32_t m = std::min<uint32_t>(kMaxBatch, n - done);
+        CGB_CHECK(variant[j] >= 0 && variant[j] <= 2, "cgb_sampler_alpha_parameters: bad variant");
+        CGB_CHECK(r1[j] < s->nRows && r2[j] < s->nRows && c1[j] < s->k && c2[j] < s->k, "cgb_sampler_alpha_parameters: index out of range");
+        DevProposal &dp = all[j];
+        std::memset(&dp, 0, sizeof(dp));
+        dp.type = kProbe;
+        dp.variant = static_cast<uint32_t>(variant[j]);
+        dp.r1 = r1[j]; dp.c1 = c1[j];
+        dp.r2 = (variant[j] == 1) ? r2[j] : r1[j];
+        dp.c2 = (variant[j] == 1) ? c2[j] : c1[j];
+        dp.ch = ch[j];
+        const bool twoRow = (variant[j] == 1) && (dp.r1 != dp.r2);
+        ((s->sparse || twoRow || n <= static_cast<uint32_t>(kMaxBatch)) ? rest : bulk).push_back(j);
+    }
+    if (!bulk.empty())
+    {
+        const uint32_t m = static_cast<uint32_t>(bulk.size());
+        std::vector<DevProposal> props(m);
+        for (uint32_t i = 0; i < m; ++i) { props[i] = all[bulk[i]]; }
+        std::vector<DevOutcome> outs(m);
+        DevProposal *dProps = nullptr;
+        DevOutcome *dOuts = nullptr;
+        CGB_CUDA(cudaMalloc(&dProps, sizeof(DevProposal) * m));
+        CGB_CUDA(cudaMalloc(&dOuts, sizeof(DevOutcome) * m));
+        CGB_CUDA(cudaMemcpyAsync(dProps, props.data(), sizeof(DevProposal) * m, cudaMemcpyHostToDevice, s->stream));
+        for (uint32_t first = 0; first < m; first += 65535u)
+        {
+            ProbeParams pp;
+            pp.mv = params.mv;
+            pp.props = dProps + first;
+            pp.outs = dOuts + first;
+            cudaLaunchConfig_t cfg = cudaLaunchConfig_t();
+            cfg.gridDim = dim3(s->nSeg, std::min<uint32_t>(65535u, m - first), 1);
+            cfg.blockDim = dim3(kThreads, 1, 1);
+            cfg.dynamicSmemBytes = evalSmemBytes(s);
+            cfg.stream = s->stream;
+            cudaLaunchAttribute attr[1];
+            attr[0].id = cudaLaunchAttributeClusterDimension;
+            attr[0].val.clusterDim.x = s->nSeg;
+            attr[0].val.clusterDim.y = 1;
+            attr[0].val.clusterDim.z = 1;
+            cfg.attrs = attr;
+            cfg.numAttrs = 1;
+            if (s->timeKernels) { CGB_CUDA(cudaEventRecord(s->evStart, s->stream)); }
+            if (s->hasS) { CGB_CUDA(cudaLaunchKernelEx(&cfg, probe_kernel<true>, pp)); }
+            else { CGB_CUDA(cudaLaunchKernelEx(&cfg, probe_kernel<false>, pp)); }
+            ++g_kernelLaunches;
+            if (s->timeKernels)
+            {
+                CGB_CUDA(cudaEventRecord(s->evStop, s->stream));
+                CGB_CUDA(cudaStreamSynchronize(s->stream));
+                float ms = 0.f;
+                CGB_CUDA(cudaEventElapsedTime(&ms, s->evStart, s->evStop));
+                s->counters.secondsKernel += static_cast<double>(ms) * 1e-3;
+            }
+            s->counters.nBatches += 1;
+        }
+        CGB_CUDA(cudaMemcpyAsync(outs.data(), dOuts, sizeof(DevOutcome) * m, cudaMemcpyDeviceToHost, s->stream));
+        CGB_CUDA(cudaStreamSynchronize(s->stream));
+        cudaFree(dProps);
+        cudaFree(dOuts);
         for (uint32_t i = 0; i < m; ++i)
         {
-            const uint32_t j = done + i;
-            CGB_CHECK(variant[j] >= 0 && variant[j] <= 2, "cgb_sampler_alpha_parameters: bad variant");
-            CGB_CHECK(r1[j] < s->nRows && r2[j] < s->nRows && c1[j] < s->k && c2[j] < s->k, "cgb_sampler_alpha_parameters: index out of range");
-            DevProposal &dp = params.props[i];
-            std::memset(&dp, 0, sizeof(dp));
-            dp.type = kProbe;
-            dp.variant = static_cast<uint32_t>(variant[j]);
-            dp.r1 = r1[j]; dp.c1 = c1[j];
-            dp.r2 = (variant[j] == 1) ? r2[j] : r1[j];
-            dp.c2 = (variant[j] == 1) ? c2[j] : c1[j];
-            dp.ch = ch[j];
+            s_out[bulk[i]] = outs[i].s;
+            smu_out[bulk[i]] = outs[i].s_mu;
         }
+    }
+    size_t done = 0;
+    while (done < rest.size())
+    {
+        const uint32_t m = static_cast<uint32_t>(std::min<size_t>(kMaxBatch, rest.size() - done));
+        for (uint32_t i = 0; i < m; ++i) { params.props[i] = all[rest[done + i]]; }
         params.nProps = m;
         CGB_TRY(launchEval(s, params));
         for (uint32_t i = 0; i < m; ++i)
         {
-            s_out[done + i] = s->hOutcomes[i].s;
-            smu_out[done + i] = s->hOutcomes[i].s_mu;
+            s_out[rest[done + i]] = s->hOutcomes[i].s;
+            smu_out[rest[done + i]] = s->hOutcomes[i].s_mu;
         }
         done += m;
     }

@@ -1003,6 +1003,42 @@ __global__ void __launch_bounds__(kThreads, 2) eval_kernel(const __grid_constant
     commit_task<HAS_S>(P.mv, in, task, smemRaw, cluster, rank, nullptr);
 }
 
+// Bulk probes: any number of single-row alphaParameters queries in ONE launch, proposals and results in device
+// memory (cgb_sampler_alpha_parameters).  Same staging + scan + reduce as every proposal; with thousands of tasks
+// queued behind each SM this is the launch that shows what the scan sustains when work is not the limit.
+struct ProbeParams
+{
+    ModelView mv;
+    const DevProposal *props;
+    DevOutcome *outs;
+};
+
+template <bool HAS_S>
+__global__ void __launch_bounds__(kThreads, 2) probe_kernel(const __grid_constant__ ProbeParams P)
+{
+    extern __shared__ __align__(128) unsigned char smemRaw[];
+    EvalSmem *hdr = reinterpret_cast<EvalSmem*>(smemRaw);
+    cg::cluster_group cluster = cg::this_cluster();
+    const uint32_t rank = cluster.block_rank();
+    TaskIn in;
+    in.pi = blockIdx.y;
+    in.part = 0u;
+    in.ver1 = in.ver2 = in.waitMask = 0u;
+    in.pr = P.props[in.pi];
+    if (threadIdx.x == 0)
+    {
+        mbar_init(&hdr->bar, 1);
+        fence_mbar_init();
+    }
+    __syncthreads();
+    DevOutcome out;
+    if (process_task<HAS_S, false>(P.mv, P.mv.erf, P.mv.erfinv, P.mv.annealingTemp, in, 0u, smemRaw, 0u, cluster, rank, &out, nullptr))
+    {
+        P.outs[in.pi] = out;
+    }
+    if (P.mv.nSeg > 1) { cluster.sync(); } // nobody leaves while a peer may still write its shared memory
+}
+
 // ------------------------------------------------------------------------------------------------
 // Resident ("streaming") variant: launched once per update().  The host generator writes each proposal
 // into its cluster's ring of 64-byte task records in pinned memory THE MOMENT it is generated; every

@@ -75,8 +75,8 @@ typedef struct cgb_params
     float maxGibbsMassA;           /* 100 */
     float maxGibbsMassP;           /* 100 */
     int32_t transposeData;
-    int32_t useSparseOptimization; /* SparseNormalModel — CGB_EUNSUPPORTED for now */
-    int32_t asynchronousUpdates;   /* must be 1: the device path is the asynchronous sampler */
+    int32_t useSparseOptimization; /* SparseNormalModel (gibbs_sampler/SparseNormalModel.h); uncertainty is ignored */
+    int32_t asynchronousUpdates;   /* 1: AsynchronousGibbsSampler; 0: SingleThreadedGibbsSampler (one proposal at a time) */
     int32_t takePumpSamples;
     int32_t printMessages;
     int32_t whichMatrixFixed;      /* 'N', 'A' or 'P' */
@@ -225,21 +225,23 @@ int cgb_sampler_alpha_parameters(cgb_sampler *s, uint32_t n, const int32_t *vari
 /* Per-sampler counters accumulated over update() calls (bench.py). */
 typedef struct cgb_sampler_counters
 {
-    uint64_t nBatches;          /* eval-kernel launches */
+    uint64_t nBatches;          /* conflict-free batches evaluated (= eval-kernel launches in launch-per-batch mode) */
     uint64_t nProposalsQueued;  /* proposals evaluated on the device */
     uint64_t nProposalsTotal;   /* nSteps processed (includes same-bin moves/exchanges) */
     double algorithmicBytes;    /* SURVEY 8(d) bytes of the queued proposals */
     double secondsHostGenerate; /* wall time in proposal generation + bookkeeping */
     double secondsDeviceWait;   /* wall time launching + waiting for the device */
-    double secondsKernel;       /* CUDA-event time of eval kernels (only when timing enabled) */
+    double secondsKernel;       /* CUDA-event time of eval kernels: every resident-grid launch; per-batch launches
+                                   only when timing is enabled */
 } cgb_sampler_counters;
 int cgb_sampler_get_counters(const cgb_sampler *s, cgb_sampler_counters *out);
 int cgb_sampler_reset_counters(cgb_sampler *s);
 /* enable CUDA-event timing of every eval-kernel launch (costs a sync each; bench roofline leg) */
 int cgb_sampler_set_kernel_timing(cgb_sampler *s, int32_t enabled);
-/* How update() reaches the device.  1 (default, or COGAPS_PERSISTENT=1): one resident grid per update(),
- * batches posted through a pinned-memory mailbox (no per-batch launch).  0: one eval-kernel launch per
- * conflict-free batch.  Both run the same device code and give bit-identical chains. */
+/* How update() reaches the device.  1 (default, or COGAPS_PERSISTENT=1): one resident grid per update(); every
+ * proposal is written to a pinned-memory record ring the moment it is generated and evaluated while the rest of
+ * its batch is still being generated.  0: one eval-kernel launch per conflict-free batch.  Both run the same
+ * device code and give bit-identical chains. */
 int cgb_sampler_set_persistent(cgb_sampler *s, int32_t enabled);
 
 /* The device reduction order of the scan, so a checker can reproduce it bit-for-bit:
