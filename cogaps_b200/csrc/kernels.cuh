@@ -676,10 +676,11 @@ __device__ __forceinline__ void commit_task(const ModelView &mv, const TaskIn &i
         __syncthreads();
         if (tid == 0)
         {
-            // bar.sync ordered every thread's AP stores before this fence; the fence orders them before
-            // the bumps for every observer (the done count reaches other CTAs by way of the host, hence
-            // system scope)
-            __threadfence_system();
+            // bar.sync ordered every thread's AP stores before this fence; the fence makes them visible
+            // device-wide (L2) before the bumps.  The done count travels on to the host through the mirror
+            // CTA, which acquires it at gpu scope and releases at system scope (mirror_loop), so gpu scope
+            // is enough here and the committer is not held up by a system-scope fence.
+            __threadfence();
             if ((dec.flags & 3u) != 0u) { atomicAdd(mv.rowVersion + row, 1u); }
             if ((dec.flags & 4u) != 0u) { atomicAdd(mv.rowVersion + dec.otherRow, 1u); }
             if (commitsDone != nullptr) { atomicAdd(commitsDone, 1ull); }
@@ -950,7 +951,7 @@ __device__ __forceinline__ void sparse_publish(const ModelView &mv, const TaskIn
 {
     if ((flags & 7u) == 0u) { return; }
     const uint32_t row = in.part ? in.pr.r2 : in.pr.r1, otherRow = in.part ? in.pr.r1 : in.pr.r2;
-    __threadfence_system();
+    __threadfence(); // gpu scope: see commit_task
     if ((flags & 3u) != 0u) { atomicAdd(mv.rowVersion + row, 1u); }
     if ((flags & 4u) != 0u) { atomicAdd(mv.rowVersion + otherRow, 1u); }
     if (commitsDone != nullptr) { atomicAdd(commitsDone, 1ull); }
