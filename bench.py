@@ -173,7 +173,13 @@ def run_reference(args, data):
     from oracle.harness import RefLib
     variant = "fast" if RefLib.available("fast") else "scalar"
     ref = RefLib(variant)
-    threads = ref.max_threads()
+    # every core this process may run on (torchrun exports OMP_NUM_THREADS=1, which would otherwise clamp the
+    # reference to one thread; it passes its thread count explicitly to every `omp parallel`)
+    try:
+        threads = len(os.sched_getaffinity(0))
+    except AttributeError:
+        threads = os.cpu_count() or 1
+    threads = max(threads, ref.max_threads())
     t0 = time.time()
     res = ref.run(data, seed=CHAIN_SEED, nPatterns=args.patterns, nIterations=args.e2e_iters, outputFrequency=0,
                   maxThreads=threads, useSparseOptimization=1 if args.sparse else 0)
@@ -202,6 +208,9 @@ def main():
                     help="BASELINE.json configs[3]: sparseOptimization (SparseGibbsSampler) on a matrix with --zeros of its "
                          "entries zeroed; give the shape with --rows/--cols/--patterns (50000 30000 50 for C4)")
     ap.add_argument("--zeros", type=float, default=0.95)
+    ap.add_argument("--chains", type=int, default=0,
+                    help="extra leg: this many independent chains on ONE GPU, one host thread each, every resident grid "
+                         "taking 1/chains of the device (what distributed CoGAPS does with several sets per worker)")
     args = ap.parse_args()
 
     rank = int(os.environ.get("RANK", "0"))
@@ -393,6 +402,42 @@ def main():
     atomsA, atomsP = chain.A.nAtoms(), chain.P.nAtoms()
     del chain
 
+    # ---- several chains sharing the device (the generator of ONE chain cannot keep a B200 busy) ----
+    multi = None
+    if rank == 0 and args.chains > 1:
+        check(cg.lib().cgb_set_resident_share(args.chains))
+        chains = [Chain(data, args.patterns, CHAIN_SEED + 100 + i, sparse=args.sparse) for i in range(args.chains)]
+        gate = threading.Barrier(args.chains + 1)
+        done_updates = [0] * args.chains
+
+        def drive(i):
+            chains[i].ramp(args.ramp)
+            for _ in range(args.warmup):
+                chains[i].step()
+            gate.wait()
+            n = 0
+            for _ in range(args.steps):
+                n += chains[i].step()
+            done_updates[i] = n
+            gate.wait()
+
+        workers = [threading.Thread(target=drive, args=(i,)) for i in range(args.chains)]
+        for w in workers:
+            w.start()
+        gate.wait()
+        tm0 = time.perf_counter()
+        gate.wait()
+        torch.cuda.synchronize()
+        tm = time.perf_counter() - tm0
+        for w in workers:
+            w.join()
+        multi = {"chains": args.chains, "value": sum(done_updates) / tm, "unit": "atom-updates/s (sum over chains)",
+                 "ms_per_step": tm / args.steps * 1e3, "per_chain": [u / tm for u in done_updates],
+                 "how": "independent chains on one GPU, one host thread each, cgb_set_resident_share(chains); same workload, "
+                        "ramp and step count as the single-chain line"}
+        del chains
+        check(cg.lib().cgb_set_resident_share(1))
+
     # ---- end to end: cgb_run (= gaps::run) on host buffers ----
     e2e = None
     if rank == 0 and not args.no_e2e:
@@ -425,6 +470,8 @@ def main():
                 "host_generate_s_per_step": (cA.secondsHostGenerate + cP.secondsHostGenerate) / args.steps,
                 "device_wait_s_per_step": (cA.secondsDeviceWait + cP.secondsDeviceWait) / args.steps,
                 "h2d_bytes_per_step": h2d_step, "d2h_bytes_per_step": d2h_step, "setup_s": setup_s}
+        if multi is not None:
+            line["multi_chain"] = multi
         print(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()

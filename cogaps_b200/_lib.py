@@ -14,7 +14,7 @@ LIB_PATH = os.path.join(HERE, "libcogaps_b200.so")
 
 # every symbol include/cogaps_b200.h declares
 EXPORTS = [
-    "cgb_last_error", "cgb_build_report", "cgb_set_device", "cgb_kernel_launch_count", "cgb_params_default",
+    "cgb_last_error", "cgb_build_report", "cgb_set_device", "cgb_set_resident_share", "cgb_kernel_launch_count", "cgb_params_default",
     "cgb_run", "cgb_randstate_create", "cgb_randstate_set_tables", "cgb_randstate_get_tables",
     "cgb_randstate_next_seed", "cgb_randstate_destroy", "cgb_rng_create", "cgb_rng_uniform32",
     "cgb_rng_uniform32_range", "cgb_rng_uniform64_range", "cgb_rng_uniform", "cgb_rng_poisson",
@@ -29,7 +29,7 @@ EXPORTS = [
     "cgb_stats_update_a", "cgb_stats_update_p", "cgb_stats_update_pump", "cgb_stats_amean", "cgb_stats_asd",
     "cgb_stats_pmean", "cgb_stats_psd", "cgb_stats_pump_matrix", "cgb_stats_mean_pattern",
     "cgb_stats_mean_chisq", "cgb_sampler_device_matrix", "cgb_stats_device_sums", "cgb_run_set_tables",
-    "cgb_debug_logf", "cgb_debug_host_logf",
+    "cgb_debug_logf", "cgb_debug_host_logf", "cgb_debug_fastdiv",
 ]
 
 _lib = None
@@ -55,6 +55,8 @@ def lib():
     L.cgb_kernel_launch_count.restype = C.c_uint64
     L.cgb_debug_host_logf.restype = C.c_float
     L.cgb_debug_host_logf.argtypes = [C.c_float]
+    L.cgb_debug_fastdiv.restype = C.c_uint64
+    L.cgb_debug_fastdiv.argtypes = [C.c_uint64, C.c_uint64]
     L.cgb_run.argtypes = [c_float_p, C.c_uint32, C.c_uint32, C.c_int32, c_float_p, C.POINTER(CgbParams),
                           C.POINTER(CgbResult)]
     L.cgb_randstate_create.argtypes = [C.c_uint32, C.POINTER(vp)]

@@ -5,6 +5,7 @@
 #include "kernels.cuh"
 #include "sampler.h"
 
+#include <atomic>
 #include <chrono>
 #include <emmintrin.h>
 #include <cstdio>
@@ -20,7 +21,8 @@ using namespace cgb;
 // error plumbing
 // ------------------------------------------------------------------------------------------------
 static thread_local std::string g_lastError;
-static uint64_t g_kernelLaunches = 0;
+static std::atomic<uint64_t> g_kernelLaunches(0);
+static std::atomic<int> g_residentShare(1); // chains that share the device: each resident grid takes 1/share of it
 static int g_device = -1;
 
 static int fail(int code, const std::string &msg)
@@ -111,7 +113,14 @@ extern "C" int cgb_set_device(int device)
     return ensureDevice();
 }
 
-extern "C" uint64_t cgb_kernel_launch_count(void) { return g_kernelLaunches; }
+extern "C" uint64_t cgb_kernel_launch_count(void) { return g_kernelLaunches.load(); }
+
+extern "C" int cgb_set_resident_share(int32_t parts)
+{
+    CGB_CHECK(parts >= 1 && parts <= 64, "cgb_set_resident_share: parts must be in 1..64");
+    g_residentShare.store(parts);
+    return CGB_OK;
+}
 
 extern "C" void cgb_params_default(cgb_params *p)
 {
@@ -350,9 +359,20 @@ static void initGenerator(cgb_sampler *s, const cgb_params *params, cgb_randstat
     else { s->queue.init(nElements, s->k, rs, s->alpha, s->lambda); }
 }
 
+// Hand-over between the two samplers of one run: the one whose orientation is contiguous in the caller's matrix
+// uploads it straight from there; the other takes its copy of D as a device transpose of that upload instead of a
+// second pass over the matrix on the host.
+struct TwinLink
+{
+    std::atomic<int> state;     // 0 pending, 1 uploaded, -1 failed
+    const cgb_sampler *sampler;
+    TwinLink() : state(0), sampler(nullptr) {}
+};
+
 static int samplerCreateImpl(const float *data, uint32_t nrow, uint32_t ncol, int32_t colmajor,
                              int32_t transpose, int32_t subsetRows, float alpha, float maxGibbsMass,
-                             const cgb_params *params, cgb_randstate *rs, bool withGenerator, cgb_sampler **out)
+                             const cgb_params *params, cgb_randstate *rs, bool withGenerator, cgb_sampler **out,
+                             TwinLink *publish = nullptr, TwinLink *twin = nullptr)
 {
     CGB_CHECK(data && params && rs && out, "cgb_sampler_create: NULL argument");
     CGB_CHECK(params->struct_size == sizeof(cgb_params), "cgb_sampler_create: cgb_params ABI mismatch");
@@ -387,29 +407,70 @@ static int samplerCreateImpl(const float *data, uint32_t nrow, uint32_t ncol, in
 
     // DenseNormalModel ctor, DenseNormalModel.h:66-88
     std::vector<float> host;
-    orientData(data, nrow, ncol, colmajor != 0, transpose != 0, subsetRows != 0, params->subsetIndices,
-        params->nSubsetIndices, s->nRows, s->L, s->ld, host, 0.f);
-    CGB_CHECK(s->nRows >= 1 && s->L >= 1, "cgb_sampler_create: empty data");
-    s->ldM = roundUp(s->nRows, 32);
+    const bool wholeMatrix = params->nSubsetIndices == 0;
+    const bool straight = wholeMatrix && ((transpose != 0) != (colmajor != 0)); // a sampler row is contiguous in `data`
+    // direct: no oriented copy on the host at all (dense model; the sparse model builds its CSR from one)
+    const bool direct = wholeMatrix && !s->sparse && (straight || twin != nullptr);
+    const float *meanBase;
+    size_t meanStrideR, meanStrideL;
+    if (direct)
     {
-        // gaps::nonZeroMean (MatrixMath.cpp:39-55): fp32 running sum over everything / count of positives
+        const uint32_t nGenes = transpose ? ncol : nrow, nSamples = transpose ? nrow : ncol;
+        s->L = nGenes;
+        s->nRows = nSamples;
+        s->ld = roundUp(s->L, 32);
+        meanBase = data;
+        meanStrideR = straight ? nGenes : 1;
+        meanStrideL = straight ? 1 : nSamples;
+    }
+    else
+    {
+        orientData(data, nrow, ncol, colmajor != 0, transpose != 0, subsetRows != 0, params->subsetIndices,
+            params->nSubsetIndices, s->nRows, s->L, s->ld, host, 0.f);
+        meanBase = host.data();
+        meanStrideR = s->ld;
+        meanStrideL = 1;
+    }
+    if (!(s->nRows >= 1 && s->L >= 1))
+    {
+        if (publish) { publish->state.store(-1); }
+        delete s;
+        return fail(CGB_EINVAL, "cgb_sampler_create: empty data");
+    }
+    s->ldM = roundUp(s->nRows, 32);
+    // gaps::nonZeroMean (MatrixMath.cpp:39-55): ONE fp32 running sum over everything / count of positives.  The
+    // order of the additions is the result, so this is a serial pass over the whole matrix; it runs on its own
+    // thread beside the allocations and the upload below and is joined before anything needs lambda.
+    struct MeanJob { float sum; unsigned nnz; } meanJob = {0.f, 0u};
+    std::thread meanThread([meanBase, meanStrideR, meanStrideL, &meanJob, s]()
+    {
         float sum = 0.f;
         unsigned nnz = 0;
         for (uint32_t r = 0; r < s->nRows; ++r)
         {
-            const float *row = host.data() + static_cast<size_t>(r) * s->ld;
-            for (uint32_t l = 0; l < s->L; ++l)
+            const float *row = meanBase + static_cast<size_t>(r) * meanStrideR;
+            if (meanStrideL == 1)
             {
-                sum += row[l];
-                if (row[l] > 0.f) { ++nnz; }
+                for (uint32_t l = 0; l < s->L; ++l)
+                {
+                    sum += row[l];
+                    if (row[l] > 0.f) { ++nnz; }
+                }
+            }
+            else
+            {
+                for (uint32_t l = 0; l < s->L; ++l)
+                {
+                    const float v = row[static_cast<size_t>(l) * meanStrideL];
+                    sum += v;
+                    if (v > 0.f) { ++nnz; }
+                }
             }
         }
-        const float meanD = sum / static_cast<float>(nnz);
-        s->lambda = alpha * std::sqrt(static_cast<float>(static_cast<uint64_t>(s->k)) / meanD);
-        s->maxGibbsMass = maxGibbsMass / s->lambda;
-        const float size = static_cast<float>(s->nRows * s->L);                 // gaps::sparsity, MatrixMath.cpp:6-21
-        s->dataSparsity = 1.f - static_cast<float>(nnz) / size;
-    }
+        meanJob.sum = sum;
+        meanJob.nnz = nnz;
+    });
+    struct Joiner { std::thread &t; ~Joiner() { if (t.joinable()) { t.join(); } } } meanJoiner = {meanThread};
     chooseSegments(s);
     std::vector<uint32_t> spPtr, spIdx;
     std::vector<float> spVal;
@@ -431,7 +492,7 @@ static int samplerCreateImpl(const float *data, uint32_t nrow, uint32_t ncol, in
                     spVal.push_back(row[l]);
                 }
             }
-            if (spIdx.size() > 0xFFFFFFF0ull) { delete s; return fail(CGB_EUNSUPPORTED, "cgb_sampler_create: more than 2^32 non-zeros"); }
+            if (spIdx.size() > 0xFFFFFFF0ull) { meanThread.join(); delete s; return fail(CGB_EUNSUPPORTED, "cgb_sampler_create: more than 2^32 non-zeros"); }
             spPtr[r + 1] = static_cast<uint32_t>(spIdx.size());
         }
     }
@@ -486,7 +547,38 @@ static int samplerCreateImpl(const float *data, uint32_t nrow, uint32_t ncol, in
         }
         CGB_CUDA_BREAK(cudaEventCreate(&s->evStart));
         CGB_CUDA_BREAK(cudaEventCreate(&s->evStop));
-        CGB_CUDA_BREAK(cudaMemcpy(s->dD, host.data(), matBytes, cudaMemcpyHostToDevice));
+        if (!direct)
+        {
+            CGB_CUDA_BREAK(cudaMemcpy(s->dD, host.data(), matBytes, cudaMemcpyHostToDevice));
+        }
+        else if (straight)
+        {
+            CGB_CUDA_BREAK(cudaMemset(s->dD, 0, matBytes)); // the pad columns
+            CGB_CUDA_BREAK(cudaMemcpy2D(s->dD, sizeof(float) * s->ld, data, sizeof(float) * s->L, sizeof(float) * s->L, s->nRows,
+                cudaMemcpyHostToDevice));
+        }
+        else
+        {
+            // the twin holds the other orientation: ours is its transpose (pads stay zero)
+            while (twin->state.load() == 0) { __builtin_ia32_pause(); }
+            if (twin->state.load() < 0)
+            {
+                rc = fail(CGB_EINTERNAL, "cgb_sampler_create: the sampler holding the other orientation failed");
+                break;
+            }
+            const cgb_sampler *t = twin->sampler;
+            CGB_CUDA_BREAK(cudaMemsetAsync(s->dD, 0, matBytes, s->stream));
+            dim3 grid((s->L + 31) / 32, (s->nRows + 31) / 32);
+            transpose_kernel<<<grid, 256, 0, s->stream>>>(s->dD, t->dD, s->nRows, s->L, s->ld, t->ld);
+            ++g_kernelLaunches;
+            CGB_CUDA_BREAK(cudaGetLastError());
+            CGB_CUDA_BREAK(cudaStreamSynchronize(s->stream));
+        }
+        if (publish)
+        {
+            publish->sampler = s;
+            publish->state.store(1);
+        }
         if (!s->sparse) { CGB_CUDA_BREAK(cudaMemset(s->dAP, 0, matBytes)); }
         CGB_CUDA_BREAK(cudaMemset(s->dM, 0, facBytes));
         CGB_CUDA_BREAK(cudaMemset(s->dColNonzero, 0, sizeof(int) * s->k));
@@ -505,10 +597,19 @@ static int samplerCreateImpl(const float *data, uint32_t nrow, uint32_t ncol, in
         }
         rc = uploadTables(rs);
     } while (0);
+    meanThread.join();
     if (rc != CGB_OK)
     {
+        if (publish && publish->state.load() == 0) { publish->state.store(-1); }
         cgb_sampler_destroy(s);
         return rc;
+    }
+    {
+        const float meanD = meanJob.sum / static_cast<float>(meanJob.nnz);
+        s->lambda = alpha * std::sqrt(static_cast<float>(static_cast<uint64_t>(s->k)) / meanD);
+        s->maxGibbsMass = maxGibbsMass / s->lambda;
+        const float size = static_cast<float>(s->nRows * s->L);                 // gaps::sparsity, MatrixMath.cpp:6-21
+        s->dataSparsity = 1.f - static_cast<float>(meanJob.nnz) / size;
     }
 
     if (withGenerator) { initGenerator(s, params, rs); }
@@ -932,6 +1033,9 @@ static int startPersistent(cgb_sampler *s)
         else { CGB_CUDA(cudaOccupancyMaxActiveClusters(&maxClusters, eval_stream_kernel<false>, &cfg)); }
         const int cap = envInt("COGAPS_PERSISTENT_CLUSTERS", 0);
         if (cap > 1 && cap < maxClusters) { maxClusters = cap; }
+        // several chains driven by several host threads share the device: every grid must fit beside the others
+        const int share = g_residentShare.load();
+        if (share > 1) { maxClusters = std::max(2, maxClusters / share); }
         if (maxClusters < 2) { return fail(CGB_ECUDA, "resident kernel: fewer than two clusters fit on the device"); }
         s->persistentGrid = maxClusters * static_cast<int>(s->nSeg);
         s->nClusters = static_cast<uint32_t>(maxClusters - 1);
@@ -1946,6 +2050,14 @@ extern "C" int cgb_debug_logf(const float *in, float *out, uint32_t n)
     return CGB_OK;
 }
 
+// host-logic probe: the generator's multiply-high division (atomic_domain.h FastDivU64) against the hardware divide
+extern "C" uint64_t cgb_debug_fastdiv(uint64_t divisor, uint64_t x)
+{
+    FastDivU64 f;
+    f.init(divisor);
+    return f.div(x);
+}
+
 // host portable-log probe: the same header compiled for the host (tests compare both with the oracle)
 extern "C" float cgb_debug_host_logf(float x) { return portable_logf(x); }
 
@@ -1996,6 +2108,7 @@ extern "C" int cgb_run(const float *data, uint32_t nrow, uint32_t ncol, int32_t 
     if (p->nSubsetIndices && !p->subsetGenes) { nSamples = p->nSubsetIndices; }
 
     RunGuard g;
+    const double tEnter = nowSeconds();
     CGB_TRY(cgb_randstate_create(p->seed, &g.rs));
     if (g_tableOverride[0]) { CGB_TRY(cgb_randstate_set_tables(g.rs, g_tableOverride[0], g_tableOverride[1], g_tableOverride[2])); }
     // GapsRunner.cpp:402-406.  The two orientations are prepared concurrently (each is a pass over the whole
@@ -2004,14 +2117,20 @@ extern "C" int cgb_run(const float *data, uint32_t nrow, uint32_t ncol, int32_t 
     CGB_TRY(ensureDevice());
     CGB_TRY(uploadTables(g.rs));
     {
+        // which of the two sees its rows contiguous in the caller's matrix (exactly one does, subsets aside)
+        const bool dense = !p->useSparseOptimization && p->nSubsetIndices == 0;
+        const bool straightA = ((!p->transposeData) != (colmajor != 0));
+        TwinLink link;
+        TwinLink *pubA = (dense && straightA) ? &link : nullptr, *twinA = (dense && !straightA) ? &link : nullptr;
+        TwinLink *pubP = (dense && !straightA) ? &link : nullptr, *twinP = (dense && straightA) ? &link : nullptr;
         int rcP = CGB_OK;
         std::string errP;
         std::thread prepP([&]()
         {
-            rcP = samplerCreateImpl(data, nrow, ncol, colmajor, p->transposeData, p->subsetGenes, p->alphaP, p->maxGibbsMassP, p, g.rs, false, &g.P);
+            rcP = samplerCreateImpl(data, nrow, ncol, colmajor, p->transposeData, p->subsetGenes, p->alphaP, p->maxGibbsMassP, p, g.rs, false, &g.P, pubP, twinP);
             if (rcP != CGB_OK) { errP = g_lastError; }
         });
-        const int rcA = samplerCreateImpl(data, nrow, ncol, colmajor, !p->transposeData, !p->subsetGenes, p->alphaA, p->maxGibbsMassA, p, g.rs, false, &g.A);
+        const int rcA = samplerCreateImpl(data, nrow, ncol, colmajor, !p->transposeData, !p->subsetGenes, p->alphaA, p->maxGibbsMassA, p, g.rs, false, &g.A, pubA, twinA);
         prepP.join();
         if (rcA != CGB_OK) { return rcA; }
         if (rcP != CGB_OK) { return fail(rcP, errP); }
@@ -2037,6 +2156,7 @@ extern "C" int cgb_run(const float *data, uint32_t nrow, uint32_t ncol, int32_t 
     CGB_TRY(cgb_sampler_extra_initialization(g.P));
 
     const double tStart = nowSeconds();
+    if (envInt("COGAPS_HOST_PROFILE", 0)) { std::printf("[cgb_run] setup (tables, both orientations, upload, sync, AP rebuild) %.3f s\n", tStart - tEnter); }
     uint64_t totalUpdates = 0;
     uint32_t nHist = 0, nSnapEq = 0, nSnapSamp = 0;
     double secondsA = 0.0, secondsP = 0.0;
@@ -2144,5 +2264,9 @@ extern "C" int cgb_run(const float *data, uint32_t nrow, uint32_t ncol, int32_t 
     r->secondsUpdateP = secondsP;
     r->secondsDevice = g.A->counters.secondsKernel + g.P->counters.secondsKernel;
     r->algorithmicBytes = g.A->counters.algorithmicBytes + g.P->counters.algorithmicBytes;
+    if (envInt("COGAPS_HOST_PROFILE", 0))
+    {
+        std::printf("[cgb_run] loop %.3f s, results %.3f s (teardown follows)\n", r->totalRunningTime, nowSeconds() - tStart - r->totalRunningTime);
+    }
     return CGB_OK;
 }

@@ -181,8 +181,12 @@ def _default_runner(data, params, uncertainty, subset, subsetDim, runKw):
 
 
 def distributedCogaps(data, params, uncertainty=None, nThreads=1, messages=False, outputFrequency=1000,
-                      transposeData=False, runner=None, device=None, sequentialSampler=False):
-    """distributedCogaps (R/DistributedCogaps.R:48-119).  Returns a CogapsResult-like object."""
+                      transposeData=False, runner=None, device=None, sequentialSampler=False, concurrentSets=1):
+    """distributedCogaps (R/DistributedCogaps.R:48-119).  Returns a CogapsResult-like object.
+
+    concurrentSets > 1: this rank runs that many of its subsets at once, one host thread each, the resident grids
+    sharing the GPU (cgb_set_resident_share) — the reference's BiocParallel workers (R/DistributedCogaps.R:60-68)
+    with threads for processes.  One chain's sequential proposal generator cannot keep a B200 busy; several can."""
     from .api import CogapsResult
     dist = _dist()
     world = dist.get_world_size() if dist else 1
@@ -207,10 +211,24 @@ def distributedCogaps(data, params, uncertainty=None, nThreads=1, messages=False
     counts = [len(s) for s in sets]
     nOther = (ncol if subsetRows else nrow)              # length of the un-partitioned dimension
 
+    def run_all(p):
+        """one run per subset this rank owns, concurrentSets at a time"""
+        if concurrentSets <= 1 or len(mine) <= 1:
+            return [(i, runner(data, p, uncertainty, sets[i], subsetDim, dict(runKw, workerID=i + 1))) for i in mine]
+        from concurrent.futures import ThreadPoolExecutor
+        from ._lib import lib, check
+        check(lib().cgb_set_resident_share(min(concurrentSets, len(mine))))
+        try:
+            with ThreadPoolExecutor(max_workers=concurrentSets) as pool:
+                futs = [(i, pool.submit(runner, data, p, uncertainty, sets[i], subsetDim, dict(runKw, workerID=i + 1))) for i in mine]
+                return [(i, f.result()) for i, f in futs]
+        finally:
+            check(lib().cgb_set_resident_share(1))
+
     # ---- pass 1: ordinary runs on each subset, then match patterns across subsets ----
     firstPass = None
     if params.fixedPatterns is None:
-        firstPass = [(i, runner(data, params, uncertainty, sets[i], subsetDim, dict(runKw, workerID=i + 1))) for i in mine]
+        firstPass = run_all(params)
         unmatchedLocal = [(i, (r.sampleFactors if genomeWide else r.featureLoadings)) for i, r in firstPass]
         unmatched = _all_gather_rows(unmatchedLocal, [nOther] * len(sets), device)
         consensus, clusters = findConsensusMatrix(unmatched, params)
@@ -223,7 +241,7 @@ def distributedCogaps(data, params, uncertainty=None, nThreads=1, messages=False
     p2.cut = min(p2.cut, p2.nPatterns)
     p2.fixedPatterns = consensus
     p2.whichMatrixFixed = "P" if genomeWide else "A"
-    final = [(i, runner(data, p2, uncertainty, sets[i], subsetDim, dict(runKw, workerID=i + 1))) for i in mine]
+    final = run_all(p2)
 
     # ---- stitch: all-gather of the per-shard rows (mean and sd), sum of meanChiSq ----
     meanLocal = [(i, (r.featureLoadings if genomeWide else r.sampleFactors)) for i, r in final]

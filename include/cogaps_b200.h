@@ -54,6 +54,11 @@ const char *cgb_last_error(void);
 const char *cgb_build_report(void);
 /* select the CUDA device used by handles created afterwards (default: COGAPS_DEVICE env or 0) */
 int cgb_set_device(int device);
+/* Several chains on one device, one host thread each (what distributed CoGAPS does with its worker processes,
+ * R/DistributedCogaps.R:60-68): handles are independent, but every sampler's resident grid must fit on the device
+ * beside the others.  Call with the number of chains that will run at once BEFORE creating their samplers; each
+ * resident grid then takes 1/parts of the device.  Default 1. */
+int cgb_set_resident_share(int32_t parts);
 /* number of kernel launches issued by this library since process start (bench.py gpu_launches) */
 uint64_t cgb_kernel_launch_count(void);
 
@@ -302,6 +307,8 @@ int cgb_run_set_tables(const float *erf, const float *erfinv, const float *qgamm
 /* the portable log of csrc/gaps_math.h evaluated on the device / on the host */
 int cgb_debug_logf(const float *in, float *out, uint32_t n);
 float cgb_debug_host_logf(float x);
+/* floor(x / divisor) as the host generator computes it for its per-sampler divisors (tests: == x / divisor) */
+uint64_t cgb_debug_fastdiv(uint64_t divisor, uint64_t x);
 
 #ifdef __cplusplus
 }

@@ -119,6 +119,23 @@ def test_host_portable_log_is_the_oracle_log(oracle):
         assert np.float32(a).view(np.uint32) == np.float32(b).view(np.uint32)
 
 
+def test_generator_division_by_fixed_divisors_is_exact():
+    """The host generator divides positions by the bin length and bins by the pattern count with a multiply-high
+    (atomic_domain.h FastDivU64); bin/row/col of a position decide which matrix element an atom belongs to
+    (ProposalQueue.cpp:174-175), so the quotient must equal the hardware divide for every input."""
+    import cogaps_b200 as cg
+    f = cg.lib().cgb_debug_fastdiv
+    rng = np.random.default_rng(11)
+    M = (1 << 64) - 1
+    divisors = [1, 2, 3, 7, 20, 50, 1363 * 7, 20000 * 20, M // (20000 * 20), M // (25 * 3), M // (200000 * 50), M, M - 1, (1 << 63), (1 << 32) + 1]
+    for d in divisors:
+        xs = [0, 1, d - 1, d, d + 1, 2 * d - 1 if 2 * d - 1 <= M else M, M, M - 1, M // 2] + [int(v) for v in rng.integers(0, M, 200, dtype=np.uint64)]
+        xs += [min(M, d * int(q) + int(r)) for q, r in zip(rng.integers(0, max(M // d, 1), 50, dtype=np.uint64), rng.integers(0, 3, 50))]
+        for x in xs:
+            x = max(0, min(M, x))
+            assert f(d, x) == x // d, (d, x)
+
+
 def test_reduction_order_is_a_function_of_row_length():
     from cogaps_b200.sampler import reduction_order_for_length
     t, v, nseg, seg = reduction_order_for_length(5000)
