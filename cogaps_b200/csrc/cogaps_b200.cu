@@ -775,7 +775,7 @@ static void fillModelView(const cgb_sampler *s, ModelView &mv)
 
 static size_t evalSmemBytes(const cgb_sampler *s)
 {
-    if (s->sparse) { return 256 + (static_cast<size_t>(s->ldR) + 4 * kSparseThreads) * sizeof(float); }
+    if (s->sparse) { return 256 + (static_cast<size_t>(s->ldR) + 4 * kSparseThreads * kSparseGroup) * sizeof(float); }
     return 256 + static_cast<size_t>(s->hasS ? 5 : 4) * s->segPad * sizeof(float);
 }
 

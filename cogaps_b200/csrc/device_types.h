@@ -7,7 +7,8 @@
 namespace cgb {
 
 static const int kThreads = 512;      // threads per CTA of the dense eval kernel (16 warps)
-static const int kSparseThreads = 256; // threads per CTA of the sparse eval kernel: one lane per element of a 256-wide group
+static const int kSparseThreads = 256; // threads per CTA of the sparse eval kernel: visited element e belongs to lane e % 256
+static const int kSparseGroup = 4;     // non-zeros per thread and pass of the sparse scan (1024 per CTA and pass)
 static const int kVec = 4;            // floats per vector access (16 B)
 static const int kMaxBatch = 384;     // proposals per launch carried in kernel-parameter space
 static const int kMaxCluster = 8;     // portable cluster limit

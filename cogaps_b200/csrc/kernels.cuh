@@ -703,7 +703,7 @@ struct SparseSmem
 {
     float warpS[kSparseThreads / 32];
     float warpMu[kSparseThreads / 32];
-    uint32_t warpCnt[kSparseThreads / 32];
+    uint32_t warpCnt[kSparseGroup * (kSparseThreads / 32)];
     float baseS, baseMu;      // Z-table terms of (s, s_mu)
     Decision dec;
     float preLog[2];
@@ -718,7 +718,7 @@ __device__ __forceinline__ float row_dot(const float *a, const float *b, uint32_
     return acc;
 }
 
-// smemRaw: [SparseSmem | pad to 256 B][sRow: ldR floats][sIdx 256][sD 256][sV1 256][sV2 256]
+// smemRaw: [SparseSmem | pad to 256 B][sRow: ldR floats][sIdx][sD][sV1][sV2], 256 * kSparseGroup entries each
 template <bool STREAM>
 __device__ __forceinline__ bool sparse_task(const ModelView &mv, const float *erfT, const float *erfinvT, float annealingTemp, const TaskIn &in,
                                             unsigned char *smemRaw, DevOutcome *outp, unsigned long long *verWaitNs,
@@ -727,9 +727,9 @@ __device__ __forceinline__ bool sparse_task(const ModelView &mv, const float *er
     SparseSmem *hdr = reinterpret_cast<SparseSmem*>(smemRaw);
     float *sRow = reinterpret_cast<float*>(smemRaw + 256);
     uint32_t *sIdx = reinterpret_cast<uint32_t*>(sRow + mv.ldR);
-    float *sD = reinterpret_cast<float*>(sIdx + kSparseThreads);
-    float *sV1 = sD + kSparseThreads;
-    float *sV2 = sV1 + kSparseThreads;
+    float *sD = reinterpret_cast<float*>(sIdx + kSparseThreads * kSparseGroup);
+    float *sV1 = sD + kSparseThreads * kSparseGroup;
+    float *sV2 = sV1 + kSparseThreads * kSparseGroup;
     const uint32_t tid = threadIdx.x, lane = tid & 31u, warp = tid >> 5;
     const DevProposal &pr = in.pr;
     const uint32_t pi = in.pi, part = in.part;
@@ -799,82 +799,120 @@ __device__ __forceinline__ bool sparse_task(const ModelView &mv, const float *er
         hdr->baseMu = bmu;
     }
 
-    // ---- the scan over the row's non-zeros, 256 at a time: compact the common ones, one lane each ----
+    // ---- the scan over the row's non-zeros, kSparseGroup x 256 at a time: compact the common ones, deal them
+    // out to the lanes.  Every load of a group is issued before any is consumed (index/value, then the factor
+    // column gather, then the factor row gathers), so a row of <= 1024 non-zeros pays each dependent latency once.
     const uint32_t start = mv.spRowPtr[row], nnz = mv.spRowPtr[row + 1] - start;
     const float *V1 = mv.otherM + static_cast<size_t>(colA) * mv.ldOther;
     const float *V2 = mv.otherM + static_cast<size_t>(c2) * mv.ldOther;
     float accS = 0.f, accMu = 0.f;
     uint32_t visited = 0; // elements visited so far (same on every thread)
-    for (uint32_t base = 0; base < nnz; base += kSparseThreads)
+    for (uint32_t base = 0; base < nnz; base += kSparseThreads * kSparseGroup)
     {
-        const uint32_t j = base + tid;
-        uint32_t l = 0;
-        float d = 0.f, v1 = 0.f, v2 = 0.f;
-        bool pred = false;
-        if (j < nnz)
-        {
-            l = mv.spIdx[start + j];
-            d = mv.spVal[start + j];
-            v1 = V1[l];
-            if (useV2) { v2 = V2[l]; }
-            pred = useV2 ? (v1 != 0.f || v2 != 0.f) : (v1 != 0.f);
-        }
-        const uint32_t ballot = __ballot_sync(0xffffffffu, pred);
-        if (lane == 0) { hdr->warpCnt[warp] = __popc(ballot); }
-        __syncthreads();
-        uint32_t before = 0, total = 0;
+        uint32_t l[kSparseGroup], ballot[kSparseGroup];
+        float d[kSparseGroup], v1[kSparseGroup], v2[kSparseGroup];
+        bool pred[kSparseGroup];
 #pragma unroll
-        for (uint32_t w = 0; w < kSparseThreads / 32; ++w)
+        for (int g = 0; g < kSparseGroup; ++g)
         {
-            const uint32_t c = hdr->warpCnt[w];
-            before += (w < warp) ? c : 0u;
-            total += c;
+            // sub-group g holds elements base + g * 256 + tid: ascending index is (g, tid) order
+            const uint32_t j = base + g * kSparseThreads + tid;
+            l[g] = 0u;
+            d[g] = 0.f;
+            if (j < nnz)
+            {
+                l[g] = mv.spIdx[start + j];
+                d[g] = mv.spVal[start + j];
+            }
         }
-        if (pred)
+#pragma unroll
+        for (int g = 0; g < kSparseGroup; ++g)
         {
-            const uint32_t p = before + __popc(ballot & ((1u << lane) - 1u));
-            sIdx[p] = l;
-            sD[p] = d;
-            sV1[p] = v1;
-            sV2[p] = v2;
+            const uint32_t j = base + g * kSparseThreads + tid;
+            v1[g] = 0.f;
+            v2[g] = 0.f;
+            if (j < nnz)
+            {
+                v1[g] = V1[l[g]];
+                if (useV2) { v2[g] = V2[l[g]]; }
+            }
+        }
+#pragma unroll
+        for (int g = 0; g < kSparseGroup; ++g)
+        {
+            const uint32_t j = base + g * kSparseThreads + tid;
+            pred[g] = (j < nnz) && (useV2 ? (v1[g] != 0.f || v2[g] != 0.f) : (v1[g] != 0.f));
+            ballot[g] = __ballot_sync(0xffffffffu, pred[g]);
+            if (lane == 0) { hdr->warpCnt[g * (kSparseThreads / 32) + warp] = __popc(ballot[g]); }
         }
         __syncthreads();
-        // element e = visited + i goes to lane e % 256: this chunk gives every lane at most one element
-        const uint32_t i = (tid + kSparseThreads - (visited % kSparseThreads)) % kSparseThreads;
-        if (i < total)
+        uint32_t before[kSparseGroup], total = 0;
+#pragma unroll
+        for (int g = 0; g < kSparseGroup; ++g)
         {
-            const uint32_t el = sIdx[i];
-            const float ed = sD[i], ev1 = sV1[i];
-            const float *orow = mv.otherMrows + static_cast<size_t>(el) * mv.ldR;
-            float dotv = 0.f;
-            // ascending k, mul and add rounded separately; 16-byte gathers of the other factor's row
-            for (uint32_t q = 0; q < k; q += 4)
+            before[g] = total;
+#pragma unroll
+            for (uint32_t w = 0; w < kSparseThreads / 32; ++w)
             {
-                const float4 o4 = *reinterpret_cast<const float4*>(orow + q);
-                dotv = fadd(dotv, fmul(sRow[q], o4.x));
-                if (q + 1 < k) { dotv = fadd(dotv, fmul(sRow[q + 1], o4.y)); }
-                if (q + 2 < k) { dotv = fadd(dotv, fmul(sRow[q + 2], o4.z)); }
-                if (q + 3 < k) { dotv = fadd(dotv, fmul(sRow[q + 3], o4.w)); }
+                const uint32_t c = hdr->warpCnt[g * (kSparseThreads / 32) + w];
+                before[g] += (w < warp) ? c : 0u;
+                total += c;
             }
-            if (useV2)
+        }
+#pragma unroll
+        for (int g = 0; g < kSparseGroup; ++g)
+        {
+            if (pred[g])
             {
-                const float dRecip = fdiv(1.f, ed);
-                const float term1 = fsub(1.f, fmul(dRecip, dRecip));
-                const float vDiff = fsub(ev1, sV2[i]);
-                accS = fadd(accS, fmul(fmul(vDiff, vDiff), term1));
-                accMu = fadd(accMu, fmul(vDiff, fadd(fmul(dotv, term1), dRecip)));
+                const uint32_t p = before[g] + __popc(ballot[g] & ((1u << lane) - 1u));
+                sIdx[p] = l[g];
+                sD[p] = d[g];
+                sV1[p] = v1[g];
+                sV2[p] = v2[g];
             }
-            else
+        }
+        __syncthreads();
+        // element e = visited + i goes to lane e % 256: a lane takes its elements in increasing e
+        const uint32_t first = (tid + kSparseThreads - (visited % kSparseThreads)) % kSparseThreads;
+#pragma unroll
+        for (int m = 0; m < kSparseGroup; ++m)
+        {
+            const uint32_t i = first + m * kSparseThreads;
+            if (i < total)
             {
-                const float term1 = fdiv(ev1, ed);
-                const float term2 = fsub(ev1, fdiv(term1, ed));
-                accS = fadd(accS, fsub(fmul(term1, term1), fmul(ev1, ev1)));
-                accMu = fadd(accMu, fadd(term1, fmul(term2, dotv)));
-                if (withChange) { accMu = fadd(accMu, fmul(fmul(term2, orow[colA]), ch)); }
+                const uint32_t el = sIdx[i];
+                const float ed = sD[i], ev1 = sV1[i];
+                const float *orow = mv.otherMrows + static_cast<size_t>(el) * mv.ldR;
+                float dotv = 0.f;
+                // ascending k, mul and add rounded separately; 16-byte gathers of the other factor's row
+                for (uint32_t q = 0; q < k; q += 4)
+                {
+                    const float4 o4 = *reinterpret_cast<const float4*>(orow + q);
+                    dotv = fadd(dotv, fmul(sRow[q], o4.x));
+                    if (q + 1 < k) { dotv = fadd(dotv, fmul(sRow[q + 1], o4.y)); }
+                    if (q + 2 < k) { dotv = fadd(dotv, fmul(sRow[q + 2], o4.z)); }
+                    if (q + 3 < k) { dotv = fadd(dotv, fmul(sRow[q + 3], o4.w)); }
+                }
+                if (useV2)
+                {
+                    const float dRecip = fdiv(1.f, ed);
+                    const float term1 = fsub(1.f, fmul(dRecip, dRecip));
+                    const float vDiff = fsub(ev1, sV2[i]);
+                    accS = fadd(accS, fmul(fmul(vDiff, vDiff), term1));
+                    accMu = fadd(accMu, fmul(vDiff, fadd(fmul(dotv, term1), dRecip)));
+                }
+                else
+                {
+                    const float term1 = fdiv(ev1, ed);
+                    const float term2 = fsub(ev1, fdiv(term1, ed));
+                    accS = fadd(accS, fsub(fmul(term1, term1), fmul(ev1, ev1)));
+                    accMu = fadd(accMu, fadd(term1, fmul(term2, dotv)));
+                    if (withChange) { accMu = fadd(accMu, fmul(fmul(term2, orow[colA]), ch)); }
+                }
             }
         }
         visited += total;
-        __syncthreads(); // the compaction buffers are rewritten by the next chunk
+        __syncthreads(); // the compaction buffers are rewritten by the next group
     }
     // lanes -> warp -> CTA: the butterflies of the dense kernel
 #pragma unroll
@@ -1148,7 +1186,7 @@ __device__ __forceinline__ void stream_worker(const ModelView &mv, const StreamP
         return;
     }
     // lookup tables of the epilogue live in shared memory for the whole update(), behind the staging area
-    const size_t stageFloats = SPARSE ? (static_cast<size_t>(mv.ldR) + 4u * kSparseThreads)
+    const size_t stageFloats = SPARSE ? (static_cast<size_t>(mv.ldR) + 4u * kSparseThreads * kSparseGroup)
                                       : static_cast<size_t>(HAS_S ? 5 : 4) * mv.segPad;
     float *erfS = reinterpret_cast<float*>(smemRaw + 256) + stageFloats;
     float *erfinvS = erfS + ((CGB_ERF_TABLE_SIZE + 3) & ~3);
