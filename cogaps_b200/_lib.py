@@ -29,7 +29,7 @@ EXPORTS = [
     "cgb_stats_update_a", "cgb_stats_update_p", "cgb_stats_update_pump", "cgb_stats_amean", "cgb_stats_asd",
     "cgb_stats_pmean", "cgb_stats_psd", "cgb_stats_pump_matrix", "cgb_stats_mean_pattern",
     "cgb_stats_mean_chisq", "cgb_sampler_device_matrix", "cgb_stats_device_sums", "cgb_run_set_tables",
-    "cgb_debug_logf", "cgb_debug_host_logf", "cgb_debug_fastdiv",
+    "cgb_debug_logf", "cgb_debug_host_logf", "cgb_debug_fastdiv", "cgb_run_file", "cgb_read_matrix_file",
 ]
 
 _lib = None
@@ -55,6 +55,8 @@ def lib():
     L.cgb_kernel_launch_count.restype = C.c_uint64
     L.cgb_debug_host_logf.restype = C.c_float
     L.cgb_debug_host_logf.argtypes = [C.c_float]
+    L.cgb_read_matrix_file.argtypes = [C.c_char_p, c_float_p, C.c_uint64, C.POINTER(C.c_uint32), C.POINTER(C.c_uint32)]
+    L.cgb_run_file.argtypes = [C.c_char_p, C.c_char_p, C.POINTER(CgbParams), C.POINTER(CgbResult)]
     L.cgb_debug_fastdiv.restype = C.c_uint64
     L.cgb_debug_fastdiv.argtypes = [C.c_uint64, C.c_uint64]
     L.cgb_run.argtypes = [c_float_p, C.c_uint32, C.c_uint32, C.c_int32, c_float_p, C.POINTER(CgbParams),

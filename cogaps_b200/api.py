@@ -160,6 +160,27 @@ def gaps_run(data, uncertainty=None, snapshots=False, **kw):
     return res.finish()
 
 
+def read_matrix_file(path):
+    """A data / uncertainty file as the path overload of gaps::run reads it (.mtx, .csv, .tsv, .gct;
+    src/file_parser/): nrow x ncol fp32 array.  Host only."""
+    nrow, ncol = C.c_uint32(), C.c_uint32()
+    check(lib().cgb_read_matrix_file(str(path).encode(), None, 0, C.byref(nrow), C.byref(ncol)))
+    out = np.zeros((nrow.value, ncol.value), np.float32)
+    check(lib().cgb_read_matrix_file(str(path).encode(), fptr(out), out.size, C.byref(nrow), C.byref(ncol)))
+    return out
+
+
+def gaps_run_file(path, uncertainty_path=None, snapshots=False, **kw):
+    """gaps::run(const std::string &data, ...) (src/GapsRunner.h:19-24) through the C ABI."""
+    nrow, ncol = C.c_uint32(), C.c_uint32()
+    check(lib().cgb_read_matrix_file(str(path).encode(), None, 0, C.byref(nrow), C.byref(ncol)))
+    p = make_params(**kw)
+    res = ResultArrays(p, nrow.value, ncol.value, snapshots=snapshots)
+    unc = str(uncertainty_path).encode() if uncertainty_path else None
+    check(lib().cgb_run_file(str(path).encode(), unc, C.byref(p), C.byref(res.c)))
+    return res.finish()
+
+
 _SNAPSHOT_PHASE = {"equilibration": PHASE_EQUILIBRATION, "sampling": PHASE_SAMPLING, "all": PHASE_ALL}
 
 

@@ -884,6 +884,16 @@ extern "C" int cgb_sampler_debug_phase_clocks(cgb_sampler *s, int32_t enable, do
     return CGB_OK;
 }
 
+// SURVEY 8(d), sparse model: the index bit-flags of the data column and of the factor column(s) — 2 x ceil(L/64)
+// words of 8 bytes per scan, 3 for a same-row pair, twice 2 for a two-row pair; the per-element part (8 B + 4 k B per
+// visited element) is counted on the device (StreamStats::visited) and added when the resident grid retires.
+static double sparseFlagBytes(const DevProposal &p, uint32_t L)
+{
+    const double words = static_cast<double>((L + 63) / 64) * 8.0;
+    if (p.type == 'B' || p.type == 'D') { return 2.0 * words; }
+    return (p.r1 == p.r2) ? 3.0 * words : 4.0 * words;
+}
+
 // reference-formulation bytes of one evaluated proposal (fp32, L = scanned length)
 static double algorithmicBytes(const DevProposal &p, const DevOutcome &o, uint32_t L)
 {
@@ -937,7 +947,7 @@ static int applyOutcome(cgb_sampler *s, const HostProposal &hp, const DevProposa
     o.accepted = accepted ? 1u : 0u;
     o.mass1 = mass1;
     o.mass2 = mass2;
-    s->counters.algorithmicBytes += algorithmicBytes(dp, o, s->L);
+    s->counters.algorithmicBytes += s->sparse ? sparseFlagBytes(dp, s->L) : algorithmicBytes(dp, o, s->L);
     // rows whose AP line / factor element the device rewrites for this outcome: every CTA of the
     // committing cluster bumps the row's version once (kernels.cuh commit_task)
     bool commit = false;
@@ -1114,6 +1124,12 @@ static int stopPersistent(cgb_sampler *s)
     float ms = 0.f;
     CGB_CUDA(cudaEventElapsedTime(&ms, s->evStart, s->evStop));
     s->counters.secondsKernel += static_cast<double>(ms) * 1e-3;
+    if (s->sparse)
+    {
+        unsigned long long visited = 0;
+        CGB_CUDA(cudaMemcpy(&visited, &static_cast<StreamStats*>(s->dStreamStats)->visited, sizeof(visited), cudaMemcpyDeviceToHost));
+        s->counters.algorithmicBytes += static_cast<double>(visited) * (8.0 + 4.0 * s->k);
+    }
     if (s->dPhaseClocks)
     {
         // phase profile: every task slot holds the stamps of the last task that used it
@@ -1372,7 +1388,7 @@ static int evalOne(cgb_sampler *s, DevProposal &dp, DevOutcome &o)
     for (uint32_t d = 0; d < o.pad[0]; ++d) { s->seq.rng.advance(); }
     s->counters.nBatches += s->usePersistent ? 1 : 0;
     s->counters.nProposalsQueued += 1;
-    s->counters.algorithmicBytes += algorithmicBytes(dp, o, s->L);
+    s->counters.algorithmicBytes += s->sparse ? sparseFlagBytes(dp, s->L) : algorithmicBytes(dp, o, s->L);
     return CGB_OK;
 }
 
@@ -2269,4 +2285,50 @@ extern "C" int cgb_run(const float *data, uint32_t nrow, uint32_t ncol, int32_t 
         std::printf("[cgb_run] loop %.3f s, results %.3f s (teardown follows)\n", r->totalRunningTime, nowSeconds() - tStart - r->totalRunningTime);
     }
     return CGB_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
+// gaps::run(const std::string &data, ...) — the path overload (src/GapsRunner.h:19-24, GapsRunner.cpp:119-159)
+// ------------------------------------------------------------------------------------------------
+namespace cgb { bool loadMatrixFile(const char *path, std::vector<float> &out, uint32_t &nrow, uint32_t &ncol, std::string &err); }
+
+extern "C" int cgb_read_matrix_file(const char *path, float *out, uint64_t capacity, uint32_t *nrow, uint32_t *ncol)
+{
+    CGB_CHECK(path && nrow && ncol, "cgb_read_matrix_file: NULL argument");
+    std::vector<float> m;
+    std::string err;
+    if (!loadMatrixFile(path, m, *nrow, *ncol, err)) { return fail(CGB_EINVAL, std::string("cgb_read_matrix_file: ") + err); }
+    if (out != nullptr)
+    {
+        CGB_CHECK(capacity >= m.size(), "cgb_read_matrix_file: output buffer too small");
+        std::memcpy(out, m.data(), m.size() * sizeof(float));
+    }
+    return CGB_OK;
+}
+
+extern "C" int cgb_run_file(const char *dataPath, const char *uncertaintyPath, const cgb_params *p, cgb_result *r)
+{
+    CGB_CHECK(dataPath && p && r, "cgb_run_file: NULL argument");
+    CGB_CHECK(p->struct_size == sizeof(cgb_params), "cgb_run_file: cgb_params ABI mismatch");
+    std::vector<float> data, unc;
+    uint32_t nrow = 0, ncol = 0, urow = 0, ucol = 0;
+    std::string err;
+    if (!loadMatrixFile(dataPath, data, nrow, ncol, err)) { return fail(CGB_EINVAL, std::string("cgb_run_file: ") + err); }
+    const bool haveUnc = uncertaintyPath != nullptr && uncertaintyPath[0] != 0;
+    if (haveUnc)
+    {
+        if (!loadMatrixFile(uncertaintyPath, unc, urow, ucol, err)) { return fail(CGB_EINVAL, std::string("cgb_run_file: ") + err); }
+        CGB_CHECK(urow == nrow && ucol == ncol, "cgb_run_file: uncertainty and data differ in shape");
+    }
+    // a subset read from a file keeps the rows in increasing index order whatever the order of the indices
+    // (Matrix.cpp:113-131 sorts them; the in-memory constructor does not, :30-69)
+    cgb_params q = *p;
+    std::vector<uint32_t> sorted;
+    if (p->nSubsetIndices > 0 && p->subsetIndices != nullptr)
+    {
+        sorted.assign(p->subsetIndices, p->subsetIndices + p->nSubsetIndices);
+        std::sort(sorted.begin(), sorted.end());
+        q.subsetIndices = sorted.data();
+    }
+    return cgb_run(data.data(), nrow, ncol, 0, haveUnc ? unc.data() : nullptr, &q, r);
 }

@@ -109,7 +109,7 @@ struct StreamStats
     unsigned long long decideNs;   // sum over tasks: record seen -> outcome posted (deciding CTA)
     unsigned long long outcomes;
     unsigned long long commitsDone; // CTA-commits completed (AP row written, fenced); the mirror CTA copies it to the host
-    unsigned long long pad;
+    unsigned long long visited;     // sparse model: elements the scans visited (data non-zero and factor non-zero)
 };
 
 struct EvalParams

@@ -1,0 +1,243 @@
+// file_loader.cpp — the path overload of gaps::run (src/GapsRunner.h:19-24): reads a data / uncertainty matrix
+// from a Matrix-Market (.mtx), comma- or tab-separated (.csv / .tsv) or .gct file into a dense fp32 row-major array,
+// with the reference's parsing rules restated:
+//   file type by extension .................. file_parser/FileParser.cpp:69-86
+//   .mtx: '%' comment lines, "nrow ncol [nnz]", then 1-based "row col value" triplets, absent entries are 0
+//                                             file_parser/MtxParser.cpp:8-62
+//   .csv/.tsv: first line = column names; the first cell is empty when row names are present (then the first
+//   cell of every later line is skipped); cells are trimmed of spaces, quotes, CR/LF ... CharacterDelimitedParser.cpp:8-150
+//   .gct: line 2 holds "nrow ncol", line 3 the column names, two leading cells (name, description) per row
+//   values: digits . - only -> decimal parse; otherwise base "e" exponent -> base * powf(10, exponent) in fp32
+//                                             file_parser/MatrixElement.cpp:10-46
+#include "../../include/cogaps_b200.h"
+
+#include <cmath>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <fstream>
+#include <sstream>
+#include <string>
+#include <vector>
+
+namespace cgb {
+
+static const char *kTrimChars = " \r\n\"";
+
+static std::string trim(const std::string &s)
+{
+    const std::size_t a = s.find_first_not_of(kTrimChars);
+    if (a == std::string::npos) { return std::string(); }
+    const std::size_t b = s.find_last_not_of(kTrimChars);
+    return s.substr(a, b - a + 1);
+}
+
+static bool isNumber(const std::string &s)
+{
+    return !s.empty() && s.find_first_not_of("0123456789.-") == std::string::npos;
+}
+
+// what `std::stringstream ss(s); float v; ss >> v;` yields for a token made of digits, '.' and '-': the longest
+// valid prefix, 0 when there is none
+static float streamFloat(const std::string &s)
+{
+    char *end = nullptr;
+    const float v = std::strtof(s.c_str(), &end);
+    return (end == s.c_str()) ? 0.f : v;
+}
+
+static bool parseValue(const std::string &s, float &out, std::string &err)
+{
+    if (isNumber(s))
+    {
+        out = streamFloat(s);
+        return true;
+    }
+    const std::size_t pos = s.find('e');
+    if (pos != std::string::npos)
+    {
+        const std::string base = s.substr(0, pos), expo = s.substr(pos + 1);
+        if (isNumber(base) && isNumber(expo))
+        {
+            out = streamFloat(base) * std::pow(10.f, streamFloat(expo));
+            return true;
+        }
+    }
+    err = "Invalid entry found in input data: " + s;
+    return false;
+}
+
+enum FileType { kInvalid, kMtx, kCsv, kTsv, kGct };
+
+static FileType fileType(const std::string &path)
+{
+    const std::size_t pos = path.find_last_of('.');
+    if (pos == std::string::npos) { return kInvalid; }
+    const std::string ext = path.substr(pos);
+    if (ext.find('/') != std::string::npos) { return kInvalid; }
+    if (ext == ".mtx") { return kMtx; }
+    if (ext == ".csv") { return kCsv; }
+    if (ext == ".tsv") { return kTsv; }
+    if (ext == ".gct") { return kGct; }
+    return kInvalid;
+}
+
+static std::vector<std::string> split(const std::string &line, char delimiter)
+{
+    std::vector<std::string> tokens;
+    std::string cell;
+    std::stringstream ss(line);
+    while (std::getline(ss, cell, delimiter)) { tokens.push_back(trim(cell)); }
+    return tokens;
+}
+
+static bool readMtx(std::ifstream &f, std::vector<float> &out, uint32_t &nrow, uint32_t &ncol, std::string &err)
+{
+    std::string line = "%";
+    while (line.find('%') != std::string::npos)
+    {
+        if (!std::getline(f, line))
+        {
+            err = "Invalid MTX file";
+            return false;
+        }
+    }
+    std::stringstream dims(line);
+    unsigned long r = 0, c = 0;
+    dims >> r >> c;
+    if (r == 0 || c == 0)
+    {
+        err = "Invalid MTX file";
+        return false;
+    }
+    nrow = static_cast<uint32_t>(r);
+    ncol = static_cast<uint32_t>(c);
+    out.assign(static_cast<size_t>(nrow) * ncol, 0.f);
+    unsigned long row = 0, col = 0;
+    std::string val;
+    while (f >> row >> col >> val)
+    {
+        float v;
+        if (!parseValue(val, v, err)) { return false; }
+        if (row < 1 || row > nrow || col < 1 || col > ncol)
+        {
+            err = "MTX entry outside the declared dimensions";
+            return false;
+        }
+        out[static_cast<size_t>(row - 1) * ncol + (col - 1)] = v;
+    }
+    return true;
+}
+
+static bool readDelimited(std::ifstream &f, char delimiter, bool gct, std::vector<float> &out, uint32_t &nrow, uint32_t &ncol,
+                          std::string &err)
+{
+    std::vector<std::string> lines;
+    std::string line;
+    while (std::getline(f, line)) { lines.push_back(line); }
+    size_t firstData;
+    bool rowNames = false;
+    size_t skipCells = 0;
+    if (gct)
+    {
+        if (lines.size() < 3)
+        {
+            err = "Invalid character delimited file";
+            return false;
+        }
+        std::stringstream dims(lines[1]);
+        unsigned long r = 0, c = 0;
+        dims >> r >> c;
+        nrow = static_cast<uint32_t>(r);
+        ncol = static_cast<uint32_t>(c);
+        firstData = 3;
+        skipCells = 2;
+    }
+    else
+    {
+        if (lines.empty())
+        {
+            err = "Invalid character delimited file";
+            return false;
+        }
+        // header: the cells of the first line; an empty first cell means row names are present
+        std::string header = lines[0];
+        std::vector<std::string> cells;
+        {
+            std::string cell;
+            std::stringstream ss(header);
+            while (std::getline(ss, cell, delimiter)) { cells.push_back(cell); }
+            if (!header.empty() && header[header.size() - 1] == delimiter) { cells.push_back(std::string()); }
+        }
+        if (cells.empty())
+        {
+            err = "Invalid character delimited file";
+            return false;
+        }
+        rowNames = trim(cells[0]).empty();
+        ncol = static_cast<uint32_t>(cells.size() - (rowNames ? 1 : 0));
+        nrow = static_cast<uint32_t>(lines.size() - 1); // the reference counts every remaining line
+        firstData = 1;
+        skipCells = rowNames ? 1 : 0;
+    }
+    if (nrow == 0 || ncol == 0)
+    {
+        err = "Invalid character delimited file";
+        return false;
+    }
+    out.assign(static_cast<size_t>(nrow) * ncol, 0.f);
+    uint32_t r = 0;
+    for (size_t i = firstData; i < lines.size() && r < nrow; ++i)
+    {
+        // the reference stops at trailing whitespace-only content (hasNext skips whitespace, then EOF)
+        if (lines[i].find_first_not_of(" \t\r\n") == std::string::npos)
+        {
+            bool onlyBlankAfter = true;
+            for (size_t j = i + 1; j < lines.size(); ++j)
+            {
+                if (lines[j].find_first_not_of(" \t\r\n") != std::string::npos) { onlyBlankAfter = false; }
+            }
+            if (onlyBlankAfter) { break; }
+        }
+        std::vector<std::string> cells = split(lines[i], delimiter);
+        for (size_t c = skipCells; c < cells.size(); ++c)
+        {
+            const size_t col = c - skipCells;
+            if (col >= ncol)
+            {
+                err = "row with more cells than the header";
+                return false;
+            }
+            float v;
+            if (!parseValue(cells[c], v, err)) { return false; }
+            out[static_cast<size_t>(r) * ncol + col] = v;
+        }
+        ++r;
+    }
+    return true;
+}
+
+bool loadMatrixFile(const char *path, std::vector<float> &out, uint32_t &nrow, uint32_t &ncol, std::string &err)
+{
+    const FileType t = fileType(path);
+    if (t == kInvalid)
+    {
+        err = "Invalid file type";
+        return false;
+    }
+    std::ifstream f(path);
+    if (!f.is_open())
+    {
+        err = std::string("cannot open ") + path;
+        return false;
+    }
+    switch (t)
+    {
+        case kMtx: return readMtx(f, out, nrow, ncol, err);
+        case kCsv: return readDelimited(f, ',', false, out, nrow, ncol, err);
+        case kTsv: return readDelimited(f, '\t', false, out, nrow, ncol, err);
+        default: return readDelimited(f, '\t', true, out, nrow, ncol, err);
+    }
+}
+
+} // namespace cgb

@@ -722,7 +722,7 @@ __device__ __forceinline__ float row_dot(const float *a, const float *b, uint32_
 template <bool STREAM>
 __device__ __forceinline__ bool sparse_task(const ModelView &mv, const float *erfT, const float *erfinvT, float annealingTemp, const TaskIn &in,
                                             unsigned char *smemRaw, DevOutcome *outp, unsigned long long *verWaitNs,
-                                            uint32_t *commitFlags)
+                                            uint32_t *commitFlags, unsigned long long *visitedTotal)
 {
     SparseSmem *hdr = reinterpret_cast<SparseSmem*>(smemRaw);
     float *sRow = reinterpret_cast<float*>(smemRaw + 256);
@@ -914,6 +914,7 @@ __device__ __forceinline__ bool sparse_task(const ModelView &mv, const float *er
         visited += total;
         __syncthreads(); // the compaction buffers are rewritten by the next group
     }
+    if (visitedTotal != nullptr && tid == 0) { atomicAdd(visitedTotal, static_cast<unsigned long long>(visited)); }
     // lanes -> warp -> CTA: the butterflies of the dense kernel
 #pragma unroll
     for (int off = 16; off >= 1; off >>= 1)
@@ -1007,7 +1008,7 @@ __global__ void __launch_bounds__(kSparseThreads, 4) eval_sparse_kernel(const __
     in.pr = P.props[in.pi];
     DevOutcome out;
     uint32_t flags = 0u;
-    if (sparse_task<false>(P.mv, P.mv.erf, P.mv.erfinv, P.mv.annealingTemp, in, smemRaw, &out, nullptr, &flags))
+    if (sparse_task<false>(P.mv, P.mv.erf, P.mv.erfinv, P.mv.annealingTemp, in, smemRaw, &out, nullptr, &flags, nullptr))
     {
         P.mv.outcomes[in.pi] = out;
         sparse_publish(P.mv, in, flags, nullptr);
@@ -1261,7 +1262,7 @@ __device__ __forceinline__ void stream_worker(const ModelView &mv, const StreamP
         unsigned long long verWait = 0;
         uint32_t sparseFlags = 0u;
         bool owner;
-        if (SPARSE) { owner = sparse_task<true>(mv, erfS, erfinvS, mv.annealingTemp, in, smemRaw, &out, &verWait, &sparseFlags); }
+        if (SPARSE) { owner = sparse_task<true>(mv, erfS, erfinvS, mv.annealingTemp, in, smemRaw, &out, &verWait, &sparseFlags, &sp.stats->visited); }
         else { owner = process_task<HAS_S, true>(mv, erfS, erfinvS, mv.annealingTemp, in, task, smemRaw, parity, cluster, rank, &out, &verWait); }
         unsigned long long tPosted = 0;
         if (owner)

@@ -141,6 +141,15 @@ typedef struct cgb_result
 int cgb_run(const float *data, uint32_t nrow, uint32_t ncol, int32_t colmajor,
             const float *uncertainty, const cgb_params *params, cgb_result *result);
 
+/* The path overload of gaps::run (src/GapsRunner.h:19-24, GapsRunner.cpp:119-159): data / uncertainty read from
+ * .mtx, .csv, .tsv or .gct files with the reference's parsing rules (src/file_parser/ — FileParser.cpp:69-86,
+ * MtxParser.cpp, CharacterDelimitedParser.cpp, MatrixElement.cpp).  uncertaintyPath may be NULL or "".  Subset
+ * indices are applied in increasing order, as the reference does when it reads a subset from a file
+ * (data_structures/Matrix.cpp:113-131).  Size the result arrays with cgb_read_matrix_file(path, NULL, 0, &nrow, &ncol). */
+int cgb_run_file(const char *dataPath, const char *uncertaintyPath, const cgb_params *params, cgb_result *result);
+/* Reads a matrix file into out (row-major, nrow*ncol floats; NULL: dimensions only).  Host only, no device needed. */
+int cgb_read_matrix_file(const char *path, float *out, uint64_t capacity, uint32_t *nrow, uint32_t *ncol);
+
 /* ------------------------------------------------------------------------------------------
  * GapsRandomState (src/math/Random.h:79-98): the xoroshiro128+ seeder every sampler and every
  * proposal pulls its PCG seed from, plus the three lookup tables.

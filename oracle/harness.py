@@ -47,6 +47,14 @@ class RefLib(object):
     def max_threads(self):
         return self.lib.cogaps_ref_max_threads()
 
+    def read_file(self, path):
+        """Matrix(path, ...) through the reference's own file parsers."""
+        nrow, ncol = C.c_uint32(), C.c_uint32()
+        self.lib.cogaps_ref_read_file(str(path).encode(), None, C.byref(nrow), C.byref(ncol))
+        out = np.zeros((nrow.value, ncol.value), np.float32)
+        self.lib.cogaps_ref_read_file(str(path).encode(), fptr(out), C.byref(nrow), C.byref(ncol))
+        return out
+
     def run(self, data, uncertainty=None, snapshots=False, **kw):
         data = _f32(data)
         unc = _f32(uncertainty) if uncertainty is not None else None

@@ -168,6 +168,17 @@ int cogaps_ref_run(const float *data, uint32_t nrow, uint32_t ncol, const float 
     return 0;
 }
 
+// Matrix(const std::string &path, ...) through the reference's own FileParser (src/data_structures/Matrix.cpp:72-134,
+// src/file_parser/*): what the path overload of gaps::run loads.  out: nrow x ncol row-major, or NULL for dimensions.
+int cogaps_ref_read_file(const char *path, float *out, uint32_t *nrow, uint32_t *ncol)
+{
+    Matrix m(std::string(path), false, false, std::vector<unsigned>());
+    *nrow = m.nRow();
+    *ncol = m.nCol();
+    fromMatrix(m, out);
+    return 0;
+}
+
 // The three lookup tables of GapsRandomState (src/math/Random.cpp:269-295) as this build makes them.
 int cogaps_ref_tables(float *erf, float *erfinv, float *qgamma)
 {

@@ -1,0 +1,141 @@
+"""The path overload of gaps::run (src/GapsRunner.h:19-24): data files are read with the reference's parsing rules
+(src/file_parser/).  The loader is host code: these tests need no GPU.  Where oracle/_ref exists the same files go
+through the reference's own FileParser + Matrix(path, ...) and must give the same bits."""
+import os
+
+import numpy as np
+import pytest
+
+from oracle.harness import RefLib
+
+
+def bits(a):
+    return np.ascontiguousarray(a, dtype=np.float32).view(np.uint32)
+
+
+def _matrix(seed, shape):
+    rng = np.random.default_rng(seed)
+    m = rng.gamma(2.0, 1.5, shape).astype(np.float32)
+    m[rng.random(shape) < 0.3] = 0
+    return m
+
+
+def _sci(v, digits=6):
+    """scientific notation the reference accepts: its number test allows digits, '.', '-' only — no '+'
+    (MatrixElement.cpp:10-13), so 3.2e+00 is an invalid entry there and here"""
+    return (("%." + str(digits) + "e") % v).replace("e+", "e")
+
+
+def _write_delimited(path, m, sep, row_names, quoted=False, crlf=False):
+    eol = "\r\n" if crlf else "\n"
+    q = (lambda s: '"%s"' % s) if quoted else (lambda s: s)
+    with open(path, "w", newline="") as f:
+        header = [q("s%d" % j) for j in range(m.shape[1])]
+        f.write(sep.join(([q("")] if row_names else []) + header) + eol)
+        for i in range(m.shape[0]):
+            cells = [repr(float(v)) if j % 3 else (_sci(v) if v else "0") for j, v in enumerate(m[i])]
+            f.write(sep.join(([q("g%d" % i)] if row_names else []) + cells) + eol)
+
+
+def _expected(m):
+    # what the written text parses to: repr() round-trips fp32 exactly; "%.6e" goes through base * powf(10, exp)
+    out = m.copy()
+    for i in range(m.shape[0]):
+        for j in range(m.shape[1]):
+            if j % 3 == 0 and m[i, j]:
+                base, exp = _sci(m[i, j]).split("e")
+                out[i, j] = np.float32(base) * np.float32(np.power(np.float32(10.0), np.float32(float(exp))))
+    return out
+
+
+@pytest.mark.parametrize("kind", ["csv_names", "csv_plain", "tsv_names", "csv_quoted_crlf"])
+def test_delimited_files(tmp_path, kind):
+    import cogaps_b200 as cg
+    m = _matrix(1, (17, 6))
+    ext, sep = (".tsv", "\t") if kind.startswith("tsv") else (".csv", ",")
+    path = str(tmp_path / ("data" + ext))
+    _write_delimited(path, m, sep, row_names=kind != "csv_plain", quoted="quoted" in kind, crlf="crlf" in kind)
+    got = cg.read_matrix_file(path)
+    assert got.shape == m.shape
+    assert np.allclose(got, _expected(m), rtol=2e-7, atol=0)
+    if RefLib.available("scalar"):
+        assert np.array_equal(bits(got), bits(RefLib("scalar").read_file(path)))
+
+
+def test_matrix_market(tmp_path):
+    import cogaps_b200 as cg
+    m = _matrix(2, (23, 9))
+    path = str(tmp_path / "data.mtx")
+    with open(path, "w") as f:
+        f.write("%%MatrixMarket matrix coordinate real general\n% a comment\n")
+        nz = np.argwhere(m != 0)
+        f.write("%d %d %d\n" % (m.shape[0], m.shape[1], len(nz)))
+        for i, j in nz:
+            f.write("%d %d %s\n" % (i + 1, j + 1, repr(float(m[i, j])) if (i + j) % 2 else _sci(m[i, j], 5)))
+    got = cg.read_matrix_file(path)
+    assert got.shape == m.shape
+    assert np.array_equal(got == 0, m == 0)
+    assert np.allclose(got, m, rtol=2e-5)   # "%.5e" keeps six significant digits
+    if RefLib.available("scalar"):
+        assert np.array_equal(bits(got), bits(RefLib("scalar").read_file(path)))
+
+
+def test_gct(tmp_path):
+    import cogaps_b200 as cg
+    m = _matrix(3, (8, 5))
+    path = str(tmp_path / "data.gct")
+    with open(path, "w") as f:
+        f.write("#1.2\n%d\t%d\n" % m.shape)
+        f.write("\t".join(["NAME", "Description"] + ["s%d" % j for j in range(m.shape[1])]) + "\n")
+        for i in range(m.shape[0]):
+            f.write("\t".join(["g%d" % i, "desc"] + [repr(float(v)) for v in m[i]]) + "\n")
+    got = cg.read_matrix_file(path)
+    assert np.array_equal(bits(got), bits(m))
+    if RefLib.available("scalar"):
+        assert np.array_equal(bits(got), bits(RefLib("scalar").read_file(path)))
+
+
+def test_reference_gist_csv_matches_the_golden_matrix():
+    """inst/extdata/GIST.csv as committed under tests/golden (the matrix the reference's own tests factorise)."""
+    import cogaps_b200 as cg
+    ref_csv = "/root/reference/inst/extdata/GIST.csv"
+    if not os.path.exists(ref_csv):
+        pytest.skip("reference tree not present on this machine")
+    from tests.cases import load_data
+    got = cg.read_matrix_file(ref_csv)
+    assert np.array_equal(bits(got), bits(load_data("gist")))
+
+
+def test_bad_files_are_errors(tmp_path):
+    import cogaps_b200 as cg
+    from cogaps_b200._lib import CogapsError
+    with pytest.raises(CogapsError):
+        cg.read_matrix_file(str(tmp_path / "missing.csv"))
+    bad = tmp_path / "data.txt"
+    bad.write_text("1,2\n3,4\n")
+    with pytest.raises(CogapsError):
+        cg.read_matrix_file(str(bad))              # FileParser.cpp:69-86: unknown extension
+    for cell in ("abc", "3.2e+00"):
+        junk = tmp_path / "junk.csv"
+        junk.write_text(",a,b\nr1,1.0,%s\n" % cell)
+        with pytest.raises(CogapsError):
+            cg.read_matrix_file(str(junk))         # MatrixElement.cpp:25-29: invalid entry
+
+
+@pytest.mark.gpu
+def test_run_from_file_equals_run_from_memory(tmp_path):
+    """gaps::run(path) == gaps::run(matrix) on the matrix the file holds; subsets read from a file are taken in
+    increasing index order (Matrix.cpp:113-131)."""
+    import cogaps_b200 as cg
+    m = _matrix(5, (60, 14))
+    path = str(tmp_path / "data.csv")
+    _write_delimited(path, m, ",", row_names=True)
+    mem = cg.read_matrix_file(path)
+    kw = dict(seed=3, nPatterns=3, nIterations=40, outputFrequency=10, maxThreads=1)
+    a = cg.gaps_run_file(path, **kw)
+    b = cg.gaps_run(mem, **kw)
+    assert np.array_equal(bits(a.Amean), bits(b.Amean)) and np.array_equal(bits(a.Pmean), bits(b.Pmean))
+    sub = [9, 2, 30, 4, 17, 55, 41]
+    a = cg.gaps_run_file(path, subsetGenes=1, subsetIndices=sub, **kw)
+    b = cg.gaps_run(mem, subsetGenes=1, subsetIndices=sorted(sub), **kw)
+    assert np.array_equal(bits(a.Amean), bits(b.Amean)) and np.array_equal(bits(a.Pmean), bits(b.Pmean))
