@@ -279,12 +279,20 @@ def main():
     launches0 = cg.lib().cgb_kernel_launch_count()
     barrier()
     clocks.begin()
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     t0 = time.perf_counter()
+    ev0.record()
     updates = 0
     for _ in range(args.steps):
         updates += chain.step()
+    torch.cuda.synchronize()      # the last A.sync(P) is still in flight on the samplers' streams
+    ev1.record()
     barrier()
-    elapsed = time.perf_counter() - t0
+    elapsed_host = time.perf_counter() - t0
+    # the region on the device clock: two CUDA events around the K steps (a step is a host-driven pipeline of
+    # resident kernels on the samplers' own streams, every update() ends with a stream synchronise, so the
+    # second event is reached when the last step is complete)
+    elapsed = ev0.elapsed_time(ev1) * 1e-3
     clocks.end()
     clock_info = clocks.stop()
     launches = cg.lib().cgb_kernel_launch_count() - launches0
@@ -469,7 +477,9 @@ def main():
                 "batches_per_step": batches / args.steps, "proposals_per_batch": queued / max(batches, 1),
                 "host_generate_s_per_step": (cA.secondsHostGenerate + cP.secondsHostGenerate) / args.steps,
                 "device_wait_s_per_step": (cA.secondsDeviceWait + cP.secondsDeviceWait) / args.steps,
-                "h2d_bytes_per_step": h2d_step, "d2h_bytes_per_step": d2h_step, "setup_s": setup_s}
+                "h2d_bytes_per_step": h2d_step, "d2h_bytes_per_step": d2h_step, "setup_s": setup_s,
+                "timer": "CUDA events around the K timed steps (device clock), max over ranks; host perf_counter over the "
+                         "same region: %.3f ms per step" % (elapsed_host / args.steps * 1e3)}
         if multi is not None:
             line["multi_chain"] = multi
         print(json.dumps(line))
