@@ -191,6 +191,7 @@ static int uploadTables(cgb_randstate *rs)
     CGB_CUDA(cudaMalloc(&rs->dErfinv, sizeof(rs->tables.erfinv)));
     CGB_CUDA(cudaMemcpy(rs->dErf, rs->tables.erf, sizeof(rs->tables.erf), cudaMemcpyHostToDevice));
     CGB_CUDA(cudaMemcpy(rs->dErfinv, rs->tables.erfinv, sizeof(rs->tables.erfinv), cudaMemcpyHostToDevice));
+    CGB_CUDA(cudaStreamSynchronize(cudaStreamLegacy));
     return CGB_OK;
 }
 
@@ -296,13 +297,18 @@ static int checkSubset(const cgb_params *p, uint32_t nrow, uint32_t ncol)
     return CGB_OK;
 }
 
-// one cluster per row scan: nSeg CTAs of kThreads threads, each staging `seg` floats per stream
+// one cluster per row scan: nSeg CTAs of kThreads threads, each staging `seg` floats per stream.  The fewest
+// segments whose staging (4 streams) still lets two CTAs share an SM: 6700 floats -> 107 KB per CTA.  Registers cap
+// an SM at two 512-thread CTAs anyway, so fewer CTAs per row means more rows in flight at once (L = 20000: three
+// segments, 98 resident clusters; four would give 74 and a P-side batch of ~85 tasks would need a second round).
+static const uint32_t kTableSegFloats = 5120; // up to here the epilogue's lookup tables fit in shared memory too
+
 static void segmentsForLength(uint32_t L, uint32_t &nSeg, uint32_t &seg)
 {
-    const uint32_t target = static_cast<uint32_t>(envInt("COGAPS_SEG_FLOATS", 5120));
+    const uint32_t target = static_cast<uint32_t>(envInt("COGAPS_SEG_FLOATS", 6700));
     const uint32_t maxCluster = static_cast<uint32_t>(envInt("COGAPS_MAX_CLUSTER", 8));
     uint32_t n = 1;
-    while (n < maxCluster && n < static_cast<uint32_t>(kMaxCluster) && (L + n - 1) / n > target) { n *= 2; }
+    while (n < maxCluster && n < static_cast<uint32_t>(kMaxCluster) && (L + n - 1) / n > target) { ++n; }
     nSeg = n;
     seg = roundUp((L + n - 1) / n, 4);
 }
@@ -312,6 +318,7 @@ static void chooseSegments(cgb_sampler *s)
     segmentsForLength(s->L, s->nSeg, s->seg);
     s->segPad = roundUp(s->seg, 32);
     s->smemBytes = 256 + static_cast<size_t>(5) * s->segPad * sizeof(float);
+    s->tablesInSmem = s->sparse || s->seg <= kTableSegFloats;
 }
 
 extern "C" int cgb_reduction_order_for_length(uint32_t rowLength, cgb_reduction_order *out)
@@ -391,7 +398,8 @@ static int samplerCreateImpl(const float *data, uint32_t nrow, uint32_t ncol, in
     s->hSlots = nullptr; s->nSlotRecords = 0; s->hStreamOutcomes = nullptr; s->dStreamStats = nullptr; s->dRowVersion = nullptr;
     s->mailSeq = 0; s->streamSerial = 0; s->persistentGrid = 0; s->nClusters = 0; s->lastPostTime = 0.0;
     s->chunkTag = 0; s->chunkPosted = 0; s->chunkBase = 0;
-    s->hCommitsMirror = nullptr; s->commitsExpected = 0; s->commitsProven = 0;
+    s->hCommitsMirror = nullptr;
+    s->commitsExpected[0] = s->commitsExpected[1] = s->provenThrough[0] = s->provenThrough[1] = 0;
     s->dPhaseClocks = nullptr; s->phaseTasks = 0;
     for (int i = 0; i < kPhaseSlots; ++i) { s->phaseSum[i] = 0.0; }
     s->hOutcomes = nullptr; s->hReducePartials = nullptr; s->stream = nullptr; s->evStart = s->evStop = nullptr;
@@ -574,6 +582,10 @@ static int samplerCreateImpl(const float *data, uint32_t nrow, uint32_t ncol, in
             CGB_CUDA_BREAK(cudaGetLastError());
             CGB_CUDA_BREAK(cudaStreamSynchronize(s->stream));
         }
+        // cudaMemcpy from pageable memory and cudaMemset return before the device has finished (the copy is only
+        // staged, the memset only queued) and the samplers' own streams are non-blocking, i.e. NOT ordered behind
+        // the legacy stream these calls use: wait here, before anybody (the twin's transpose first of all) reads D
+        CGB_CUDA_BREAK(cudaStreamSynchronize(cudaStreamLegacy));
         if (publish)
         {
             publish->sampler = s;
@@ -590,12 +602,14 @@ static int samplerCreateImpl(const float *data, uint32_t nrow, uint32_t ncol, in
         CGB_CUDA_BREAK(cudaFuncSetAttribute(eval_stream_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024 - 1024));
         CGB_CUDA_BREAK(cudaFuncSetAttribute(eval_stream_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024 - 1024));
         CGB_CUDA_BREAK(cudaFuncSetAttribute(eval_stream_sparse_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
-        if (!s->sparse && s->smemBytes + kStreamTableBytes > 226u * 1024u)
+        if (!s->sparse && s->smemBytes + (s->tablesInSmem ? kStreamTableBytes : 0) > 226u * 1024u)
         {
             rc = fail(CGB_EUNSUPPORTED, "row length too large for one cluster of staged segments (raise COGAPS_MAX_CLUSTER)");
             break;
         }
         rc = uploadTables(rs);
+        // every memset / copy above went through the legacy stream (see the note at the upload of D)
+        if (rc == CGB_OK) { CGB_CUDA_BREAK(cudaStreamSynchronize(cudaStreamLegacy)); }
     } while (0);
     meanThread.join();
     if (rc != CGB_OK)
@@ -640,6 +654,7 @@ extern "C" int cgb_sampler_set_uncertainty(cgb_sampler *s, const float *unc, uin
     const size_t matBytes = static_cast<size_t>(s->nRows) * s->ld * sizeof(float);
     if (!s->dS) { CGB_CUDA(cudaMalloc(&s->dS, matBytes)); }
     CGB_CUDA(cudaMemcpy(s->dS, host.data(), matBytes, cudaMemcpyHostToDevice));
+    CGB_CUDA(cudaStreamSynchronize(cudaStreamLegacy)); // pageable copy: staged, not necessarily landed
     s->hasS = true;
     return CGB_OK;
 }
@@ -750,6 +765,7 @@ static void fillModelView(const cgb_sampler *s, ModelView &mv)
     mv.tickets = s->dTickets;
     mv.phaseClocks = s->dPhaseClocks;
     mv.rowVersion = s->dRowVersion;
+    mv.tablesInSmem = s->tablesInSmem ? 1u : 0u;
     mv.spRowPtr = s->dSpRowPtr;
     mv.spIdx = s->dSpIdx;
     mv.spVal = s->dSpVal;
@@ -873,6 +889,7 @@ extern "C" int cgb_sampler_debug_phase_clocks(cgb_sampler *s, int32_t enable, do
     {
         CGB_CUDA(cudaMalloc(&s->dPhaseClocks, sizeof(unsigned long long) * kPhaseSlots * 2 * kMaxBatch));
         CGB_CUDA(cudaMemset(s->dPhaseClocks, 0, sizeof(unsigned long long) * kPhaseSlots * 2 * kMaxBatch));
+        CGB_CUDA(cudaStreamSynchronize(cudaStreamLegacy));
     }
     if (!enable && s->dPhaseClocks)
     {
@@ -934,9 +951,11 @@ static inline void noteCommit(cgb_sampler *s, const DevProposal &dp, bool reside
     if (isTwoRow(dp)) { s->rowVersion[dp.r2] += s->nSeg; }
     if (resident)
     {
-        s->commitsExpected += s->nSeg;
-        s->rowPending[dp.r1] = s->commitsExpected;
-        if (isTwoRow(dp)) { s->rowPending[dp.r2] = s->commitsExpected; }
+        // the proposal travelled in the chunk whose tag is still current (outcomes are applied before the next
+        // chunk is opened); every CTA of the committing cluster counts itself done once
+        s->commitsExpected[s->mailSeq & 1ull] += s->nSeg;
+        s->rowPending[dp.r1] = s->mailSeq;
+        if (isTwoRow(dp)) { s->rowPending[dp.r2] = s->mailSeq; }
     }
 }
 
@@ -1002,12 +1021,15 @@ static int applyOutcome(cgb_sampler *s, const HostProposal &hp, const DevProposa
 static inline bool rowSettled(cgb_sampler *s, uint32_t row)
 {
     const uint64_t pend = s->rowPending[row];
-    if (pend <= s->commitsProven) { return true; }
-    // commits finish out of order, so only "all of them" proves anything: the mirror equals what the
-    // host expects (no outcome is applied while a batch is being generated, so the target stands still)
-    if (*s->hCommitsMirror == s->commitsExpected)
+    if (pend == 0) { return true; }
+    const uint64_t q = pend & 1ull;
+    if (pend <= s->provenThrough[q]) { return true; }
+    // Commits finish out of order, so only "all of them" proves anything, and only for the parity the chunk now
+    // being posted does NOT use: its own commits are already landing in its own counter and could stand in for a
+    // straggler of an earlier chunk.  (No outcome is applied while a chunk is posted, so the target stands still.)
+    if (q != (s->mailSeq & 1ull) && s->hCommitsMirror[q] == s->commitsExpected[q])
     {
-        s->commitsProven = s->commitsExpected;
+        s->provenThrough[q] = s->mailSeq - 1; // the newest chunk of that parity
         return true;
     }
     return false;
@@ -1017,7 +1039,7 @@ static inline bool rowSettled(cgb_sampler *s, uint32_t row)
 // resident mode: one grid per update(); every proposal is posted to its cluster's record ring the moment
 // the generator queues it, outcomes come back as self-validating 16-byte records
 // ------------------------------------------------------------------------------------------------
-static size_t streamSmemBytes(const cgb_sampler *s) { return evalSmemBytes(s) + kStreamTableBytes; }
+static size_t streamSmemBytes(const cgb_sampler *s) { return evalSmemBytes(s) + (s->tablesInSmem ? kStreamTableBytes : 0); }
 
 static int startPersistent(cgb_sampler *s)
 {
@@ -1077,9 +1099,10 @@ static int startPersistent(cgb_sampler *s)
     sp.pollSleepNs = static_cast<uint32_t>(envInt("COGAPS_POLL_SLEEP_NS", 0));
     CGB_CUDA(cudaMemsetAsync(sp.stats, 0, sizeof(StreamStats), s->stream));
     // the device counter restarts with the grid; nothing is pending across a kernel boundary
-    *s->hCommitsMirror = 0ull;
+    s->hCommitsMirror[0] = s->hCommitsMirror[1] = 0ull;
     std::fill(s->rowPending.begin(), s->rowPending.end(), 0ull);
-    s->commitsExpected = s->commitsProven = 0;
+    s->commitsExpected[0] = s->commitsExpected[1] = 0;
+    s->provenThrough[0] = s->provenThrough[1] = s->mailSeq;
     CGB_CUDA(cudaEventRecord(s->evStart, s->stream));
     if (s->sparse) { CGB_CUDA(cudaLaunchKernelEx(&cfg, eval_stream_sparse_kernel, mv, sp)); }
     else if (s->hasS) { CGB_CUDA(cudaLaunchKernelEx(&cfg, eval_stream_kernel<true>, mv, sp)); }
@@ -1120,7 +1143,7 @@ static int stopPersistent(cgb_sampler *s)
     s->streamSerial = (s->streamSerial + s->nClusters + s->nClusters - 1) / s->nClusters * s->nClusters;
     CGB_CUDA(cudaStreamSynchronize(s->stream));
     s->persistentRunning = false;
-    s->commitsProven = s->commitsExpected; // the grid has drained: every commit it made is complete
+    s->provenThrough[0] = s->provenThrough[1] = s->mailSeq; // the grid has drained: every commit it made is complete
     float ms = 0.f;
     CGB_CUDA(cudaEventElapsedTime(&ms, s->evStart, s->evStop));
     s->counters.secondsKernel += static_cast<double>(ms) * 1e-3;
@@ -1210,6 +1233,12 @@ static int beginChunk(cgb_sampler *s, size_t chunkBase)
     if (!s->persistentRunning) { CGB_TRY(startPersistent(s)); }
     s->lastPostTime = t0;
     ++s->mailSeq;
+    {
+        // the parity this chunk will use: chunks of it up to mailSeq - 2 are provably complete if their counter
+        // matches now, before this chunk adds to it; otherwise rows they touched keep their rowVersion check
+        const uint64_t q = s->mailSeq & 1ull;
+        if (s->mailSeq >= 2 && s->hCommitsMirror[q] == s->commitsExpected[q]) { s->provenThrough[q] = s->mailSeq - 2; }
+    }
     s->chunkTag = static_cast<uint32_t>(s->mailSeq) & 0x1fffffffu;
     s->chunkPosted = 0;
     s->chunkBase = chunkBase;
@@ -1894,6 +1923,7 @@ extern "C" int cgb_stats_create(uint32_t nGenes, uint32_t nSamples, uint32_t nPa
     if (e == cudaSuccess) { e = cudaMemset(st->dPump, 0, aBytes); }
     if (e == cudaSuccess) { e = cudaMemset(st->dPmean, 0, pBytes); }
     if (e == cudaSuccess) { e = cudaMemset(st->dPsq, 0, pBytes); }
+    if (e == cudaSuccess) { e = cudaStreamSynchronize(cudaStreamLegacy); } // the kernels run on the samplers' non-blocking streams
     if (e != cudaSuccess)
     {
         cgb_stats_destroy(st);

@@ -79,6 +79,7 @@ struct ModelView
     uint32_t seg;            // floats per segment (multiple of 4)
     uint32_t nSeg;           // segments per row = cluster size
     uint32_t segPad;         // floats reserved per stream in shared memory
+    uint32_t tablesInSmem;   // resident grid keeps the erf / erfinv tables in shared memory (short segments only)
     float lambda, maxGibbsMass, annealingTemp;
 };
 
@@ -108,8 +109,12 @@ struct StreamStats
     unsigned long long verWaitNs;  // sum over tasks: time spent waiting for a row version
     unsigned long long decideNs;   // sum over tasks: record seen -> outcome posted (deciding CTA)
     unsigned long long outcomes;
-    unsigned long long commitsDone; // CTA-commits completed (AP row written, fenced); the mirror CTA copies it to the host
     unsigned long long visited;     // sparse model: elements the scans visited (data non-zero and factor non-zero)
+    unsigned long long pad;
+    // CTA-commits completed (AP row written, fenced), one counter per parity of the chunk tag that carried the
+    // proposal; the mirror CTA copies both to the host.  Two counters because commits of the chunk being posted
+    // must not be mistaken for the stragglers of the one before (see rowSettled in cogaps_b200.cu).
+    unsigned long long commitsDone[2];
 };
 
 struct EvalParams

@@ -1128,7 +1128,7 @@ struct StreamParams
     const StreamRecord *slots;                 // pinned host memory: record rings of the worker clusters
     const volatile unsigned long long *doorbell; // pinned host memory: kDoorbellExit retires the mirror CTA
     HostOutcome *outcomes;                     // pinned host memory
-    volatile unsigned long long *commitsMirror; // pinned host memory: stats->commitsDone as last seen by the mirror CTA
+    volatile unsigned long long *commitsMirror; // pinned host memory [2]: stats->commitsDone as last seen by the mirror CTA
     StreamStats *stats;
     unsigned long long serial0;                // first serial this grid will see (multiple of nWorkers)
     unsigned long long idleTimeoutNs;
@@ -1141,22 +1141,25 @@ struct StreamParams
 __device__ __forceinline__ void mirror_loop(const StreamParams &sp)
 {
     if (threadIdx.x != 0) { return; }
-    unsigned long long mirrored = 0ull;
+    unsigned long long mirrored[2] = {0ull, 0ull};
     const unsigned long long t0 = global_timer_ns();
     for (uint32_t it = 0;; ++it)
     {
-        unsigned long long done;
-        asm volatile("ld.acquire.gpu.global.u64 %0, [%1];" : "=l"(done) : "l"(&sp.stats->commitsDone) : "memory");
-        if (done != mirrored)
+        bool changed = false;
+#pragma unroll
+        for (int q = 0; q < 2; ++q)
         {
-            __threadfence_system();
-            asm volatile("st.volatile.global.u64 [%0], %1;" ::"l"(sp.commitsMirror), "l"(done) : "memory");
-            mirrored = done;
+            unsigned long long done;
+            asm volatile("ld.acquire.gpu.global.u64 %0, [%1];" : "=l"(done) : "l"(&sp.stats->commitsDone[q]) : "memory");
+            if (done != mirrored[q])
+            {
+                __threadfence_system();
+                asm volatile("st.volatile.global.u64 [%0], %1;" ::"l"(sp.commitsMirror + q), "l"(done) : "memory");
+                mirrored[q] = done;
+                changed = true;
+            }
         }
-        else
-        {
-            __nanosleep(100);
-        }
+        if (!changed) { __nanosleep(100); }
         if ((it & 15u) == 0u)
         {
             // the host retires us at the end of update(); the workers have their own idle timeout
@@ -1189,10 +1192,16 @@ __device__ __forceinline__ void stream_worker(const ModelView &mv, const StreamP
     // lookup tables of the epilogue live in shared memory for the whole update(), behind the staging area
     const size_t stageFloats = SPARSE ? (static_cast<size_t>(mv.ldR) + 4u * kSparseThreads * kSparseGroup)
                                       : static_cast<size_t>(HAS_S ? 5 : 4) * mv.segPad;
-    float *erfS = reinterpret_cast<float*>(smemRaw + 256) + stageFloats;
-    float *erfinvS = erfS + ((CGB_ERF_TABLE_SIZE + 3) & ~3);
-    for (uint32_t i = tid; i < CGB_ERF_TABLE_SIZE; i += blockDim.x) { erfS[i] = mv.erf[i]; }
-    for (uint32_t i = tid; i < CGB_ERFINV_TABLE_SIZE; i += blockDim.x) { erfinvS[i] = mv.erfinv[i]; }
+    const float *erfS = mv.erf, *erfinvS = mv.erfinv;
+    if (mv.tablesInSmem != 0u)
+    {
+        float *e = reinterpret_cast<float*>(smemRaw + 256) + stageFloats;
+        float *ei = e + ((CGB_ERF_TABLE_SIZE + 3) & ~3);
+        for (uint32_t i = tid; i < CGB_ERF_TABLE_SIZE; i += blockDim.x) { e[i] = mv.erf[i]; }
+        for (uint32_t i = tid; i < CGB_ERFINV_TABLE_SIZE; i += blockDim.x) { ei[i] = mv.erfinv[i]; }
+        erfS = e;
+        erfinvS = ei;
+    }
     if (!SPARSE && tid == 0)
     {
         mbar_init(&hdr->bar, 1);
@@ -1278,11 +1287,11 @@ __device__ __forceinline__ void stream_worker(const ModelView &mv, const StreamP
         }
         if (SPARSE)
         {
-            if (owner) { sparse_publish(mv, in, sparseFlags, &sp.stats->commitsDone); }
+            if (owner) { sparse_publish(mv, in, sparseFlags, &sp.stats->commitsDone[batch & 1u]); }
         }
         else
         {
-            commit_task<HAS_S>(mv, in, task, smemRaw, cluster, rank, &sp.stats->commitsDone);
+            commit_task<HAS_S>(mv, in, task, smemRaw, cluster, rank, &sp.stats->commitsDone[batch & 1u]);
         }
         parity ^= 1u;
         __syncthreads(); // staging buffers and sRec are free for the next task

@@ -149,6 +149,7 @@ struct cgb_sampler
     double *hReducePartials;      // pinned
     uint32_t seg, nSeg, segPad;
     size_t smemBytes;
+    bool tablesInSmem;            // resident grid: erf / erfinv tables copied to shared memory (else read through L2)
 
     // host generator
     cgb::AtomicDomain domain;
@@ -168,13 +169,15 @@ struct cgb_sampler
     // per-row commit counts: the device's counter and what the host knows it will reach
     uint32_t *dRowVersion;
     std::vector<uint32_t> rowVersion;
-    // commit tracking: the device counts completed CTA-commits, one extra CTA mirrors the count into
-    // host memory.  rowPending[r] = value commitsExpected had right after the last commit to row r was
-    // recorded; once the mirror has been seen equal to commitsExpected (commitsProven), every commit up
-    // to that ordinal is complete and tasks on those rows need no rowVersion check.
-    volatile unsigned long long *hCommitsMirror; // pinned + mapped
+    // commit tracking.  The device counts completed CTA-commits per parity of the chunk tag, one extra CTA mirrors
+    // both counts into host memory.  rowPending[r] = tag (mailSeq) of the chunk whose proposal last rewrote row r,
+    // 0 = none.  commitsExpected[q] = commits of every APPLIED outcome from chunks of parity q.  While chunk c is
+    // being posted its own commits already land in counter c & 1, so only the other parity can be proven complete
+    // by "mirror == expected" at any time; the own parity is proven once, before the chunk's first post
+    // (provenThrough[q]: every chunk of parity q up to this tag is complete).
+    volatile unsigned long long *hCommitsMirror; // [2], pinned + mapped
     std::vector<uint64_t> rowPending;
-    uint64_t commitsExpected, commitsProven;
+    uint64_t commitsExpected[2], provenThrough[2];
 
     // resident-kernel mode: task records streamed to the grid through pinned host memory
     bool usePersistent;

@@ -369,10 +369,10 @@ def test_long_rows_use_clusters(oracle):
     """Row lengths beyond one segment: the scan is split over a thread-block cluster (DSMEM reduce)."""
     import cogaps_b200 as cg
     from cogaps_b200.sampler import reduction_order_for_length
-    data = load_data("syn:40:6000:4:3")      # A rows have 6000 samples -> 4 segments
-    assert reduction_order_for_length(6000)[2] > 1
+    data = load_data("syn:40:14000:4:3")     # A rows have 14000 samples -> 3 segments
+    assert reduction_order_for_length(14000)[2] > 1
     kw = dict(seed=5, nPatterns=4, nIterations=25, outputFrequency=5, maxThreads=1)
-    want = oracle.run(data, options=device_options(oracle, 40, 6000), **kw)
+    want = oracle.run(data, options=device_options(oracle, 40, 14000), **kw)
     got = cg.gaps_run(data, **kw)
     assert np.array_equal(got.atomHistoryA, want.atomHistoryA)
     assert np.array_equal(got.atomHistoryP, want.atomHistoryP)
