@@ -7,7 +7,6 @@
 
 #include <atomic>
 #include <chrono>
-#include <emmintrin.h>
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
