@@ -338,6 +338,7 @@ extern "C" void cgb_sampler_destroy(cgb_sampler *s)
     cudaFree(s->dRowVersion); cudaFree(s->dStreamStats);
     cudaFree(s->dSpRowPtr); cudaFree(s->dSpIdx); cudaFree(s->dSpVal); cudaFree(s->dMrows); cudaFree(s->dZ1); cudaFree(s->dZ2);
     if (s->hCommitsMirror) { cudaFreeHost(const_cast<unsigned long long*>(s->hCommitsMirror)); }
+    if (s->hAlive) { cudaFreeHost(const_cast<uint32_t*>(s->hAlive)); }
     if (s->hSlots) { cudaFreeHost(s->hSlots); }
     if (s->hStreamOutcomes) { cudaFreeHost(s->hStreamOutcomes); }
     if (s->hOutcomes) { cudaFreeHost(s->hOutcomes); }
@@ -394,8 +395,15 @@ static int samplerCreateImpl(const float *data, uint32_t nrow, uint32_t ncol, in
     s->dSpRowPtr = s->dSpIdx = nullptr; s->dSpVal = s->dMrows = s->dZ1 = s->dZ2 = nullptr; s->ldR = 0;
     s->dColNonzero = nullptr; s->dPartials = nullptr; s->dTickets = nullptr; s->dReducePartials = nullptr;
     s->usePersistent = envInt("COGAPS_PERSISTENT", 1) != 0; s->persistentRunning = false;
+    // test knobs for the rarely taken paths: every row read behind a rowVersion check; small chunks
+    s->forceRowWait = envInt("COGAPS_FORCE_ROW_WAIT", 0) != 0;
+    {
+        const int cap = envInt("COGAPS_CHUNK_PROPOSALS", kMaxPersistentBatch);
+        s->chunkCap = static_cast<size_t>(cap >= 1 && cap <= kMaxPersistentBatch ? cap : kMaxPersistentBatch);
+    }
     s->hSlots = nullptr; s->nSlotRecords = 0; s->hStreamOutcomes = nullptr; s->dStreamStats = nullptr; s->dRowVersion = nullptr;
-    s->mailSeq = 0; s->streamSerial = 0; s->persistentGrid = 0; s->nClusters = 0; s->lastPostTime = 0.0;
+    s->mailSeq = 0; s->persistentGrid = 0; s->nClusters = 0; s->lastPostTime = 0.0;
+    s->hAlive = nullptr; s->launchEpoch = 0; s->ticketBase = 0; s->aliveNext = 0;
     s->chunkTag = 0; s->chunkPosted = 0; s->chunkBase = 0;
     s->hCommitsMirror = nullptr;
     s->commitsExpected[0] = s->commitsExpected[1] = s->provenThrough[0] = s->provenThrough[1] = 0;
@@ -1021,6 +1029,7 @@ static inline bool rowSettled(cgb_sampler *s, uint32_t row)
 {
     const uint64_t pend = s->rowPending[row];
     if (pend == 0) { return true; }
+    if (s->forceRowWait) { return false; } // tests (COGAPS_FORCE_ROW_WAIT): every such task checks rowVersion
     const uint64_t q = pend & 1ull;
     if (pend <= s->provenThrough[q]) { return true; }
     // Commits finish out of order, so only "all of them" proves anything, and only for the parity the chunk now
@@ -1074,15 +1083,23 @@ static int startPersistent(cgb_sampler *s)
         CGB_CUDA(cudaHostAlloc(&s->hSlots, sizeof(StreamRecord) * (s->nSlotRecords + 1), cudaHostAllocMapped));
         std::memset(s->hSlots, 0, sizeof(StreamRecord) * (s->nSlotRecords + 1));
         s->slotOwner.assign(static_cast<size_t>(s->nClusters) * kStreamRing, ~0ull);
+        void *alive = nullptr;
+        CGB_CUDA(cudaHostAlloc(&alive, sizeof(uint32_t) * s->nClusters, cudaHostAllocMapped));
+        std::memset(alive, 0, sizeof(uint32_t) * s->nClusters);
+        s->hAlive = static_cast<volatile uint32_t*>(alive);
+        s->clusterTicket.assign(s->nClusters, 0u);
+        s->aliveSeen.assign(s->nClusters, 0);
     }
     cfg.gridDim = dim3(s->persistentGrid, 1, 1);
     ModelView mv;
     fillModelView(s, mv);
     mv.annealingTemp = s->annealingTemp; // constant for the whole update() this grid serves
-    // cluster c serves serials c, c + nWorkers, ...; its tickets continue where the last grid stopped
-    s->streamSerial = (s->streamSerial + s->nClusters - 1) / s->nClusters * s->nClusters;
-    s->nextCluster = 0;
-    s->nextTicket = static_cast<uint32_t>(s->streamSerial / s->nClusters) + 1u;
+    // every cluster's tickets start behind the highest one any cluster used under the previous grid
+    std::fill(s->clusterTicket.begin(), s->clusterTicket.end(), s->ticketBase);
+    std::fill(s->aliveSeen.begin(), s->aliveSeen.end(), 0);
+    s->aliveList.clear();
+    s->aliveNext = 0;
+    if (++s->launchEpoch == 0u) { s->launchEpoch = 1u; }
     volatile unsigned long long *doorbell = reinterpret_cast<volatile unsigned long long*>(static_cast<StreamRecord*>(s->hSlots) + s->nSlotRecords);
     *doorbell = 0ull;
     __sync_synchronize();
@@ -1092,7 +1109,9 @@ static int startPersistent(cgb_sampler *s)
     sp.outcomes = static_cast<HostOutcome*>(s->hStreamOutcomes);
     sp.commitsMirror = s->hCommitsMirror;
     sp.stats = static_cast<StreamStats*>(s->dStreamStats);
-    sp.serial0 = s->streamSerial;
+    sp.ticket0 = s->ticketBase;
+    sp.alive = const_cast<uint32_t*>(s->hAlive);
+    sp.epoch = s->launchEpoch;
     sp.idleTimeoutNs = static_cast<unsigned long long>(envInt("COGAPS_PERSISTENT_IDLE_MS", 2000)) * 1000000ull;
     sp.nWorkers = s->nClusters;
     sp.pollSleepNs = static_cast<uint32_t>(envInt("COGAPS_POLL_SLEEP_NS", 0));
@@ -1132,14 +1151,16 @@ static int stopPersistent(cgb_sampler *s)
     StreamRecord rec;
     std::memset(&rec, 0, sizeof(rec));
     rec.type = kStreamExit;
-    for (uint64_t T = s->streamSerial; T < s->streamSerial + s->nClusters; ++T)
+    uint32_t top = s->ticketBase;
+    for (uint32_t c = 0; c < s->nClusters; ++c)
     {
-        writeRecord(s, static_cast<uint32_t>(T % s->nClusters), static_cast<uint32_t>(T / s->nClusters) + 1u, rec);
+        writeRecord(s, c, s->clusterTicket[c] + 1u, rec);
+        top = std::max(top, s->clusterTicket[c] + 1u);
     }
+    s->ticketBase = top + 1u;
     volatile unsigned long long *doorbell = reinterpret_cast<volatile unsigned long long*>(static_cast<StreamRecord*>(s->hSlots) + s->nSlotRecords);
     *doorbell = kDoorbellExit;
     __sync_synchronize();
-    s->streamSerial = (s->streamSerial + s->nClusters + s->nClusters - 1) / s->nClusters * s->nClusters;
     CGB_CUDA(cudaStreamSynchronize(s->stream));
     s->persistentRunning = false;
     s->provenThrough[0] = s->provenThrough[1] = s->mailSeq; // the grid has drained: every commit it made is complete
@@ -1246,10 +1267,40 @@ static int beginChunk(cgb_sampler *s, size_t chunkBase)
 
 static int postPrepared(cgb_sampler *s, size_t index);
 
+// picks up clusters that have reported in since the last look
+static void refreshAlive(cgb_sampler *s)
+{
+    for (uint32_t c = 0; c < s->nClusters; ++c)
+    {
+        if (!s->aliveSeen[c] && s->hAlive[c] == s->launchEpoch)
+        {
+            s->aliveSeen[c] = 1;
+            s->aliveList.push_back(c);
+        }
+    }
+}
+
+static int waitForAnyCluster(cgb_sampler *s)
+{
+    const double t0 = nowSeconds();
+    uint64_t spins = 0;
+    while (s->aliveList.empty())
+    {
+        refreshAlive(s);
+        __builtin_ia32_pause();
+        if ((++spins & 0xffff) == 0 && nowSeconds() - t0 > 20.0)
+        {
+            return fail(CGB_ECUDA, "resident eval kernel: no cluster came up within 20 s (is the device fully occupied by other work?)");
+        }
+    }
+    s->counters.secondsDeviceWait += nowSeconds() - t0;
+    return CGB_OK;
+}
+
 // posts proposal `index` of the batch (ProposalQueue sink, or the chunk loop for very long batches)
 static int postProposal(cgb_sampler *s, const HostProposal &hp, size_t index)
 {
-    if (index < s->chunkBase || index - s->chunkBase >= static_cast<size_t>(kMaxPersistentBatch)) { return CGB_OK; }
+    if (index < s->chunkBase || index - s->chunkBase >= s->chunkCap) { return CGB_OK; }
     if (s->posted.size() <= index)
     {
         const size_t n = std::max<size_t>(index + 1, s->posted.size() * 2 + 256);
@@ -1285,14 +1336,11 @@ static int postPrepared(cgb_sampler *s, size_t index)
     const uint32_t nParts = isTwoRow(dp) ? 2u : 1u;
     for (uint32_t part = 0; part < nParts; ++part)
     {
-        // serial T = streamSerial: cluster T % nClusters, ticket T / nClusters + 1, kept incrementally
-        ++s->streamSerial;
-        const uint32_t cluster = s->nextCluster, ticket = s->nextTicket;
-        if (++s->nextCluster == s->nClusters)
-        {
-            s->nextCluster = 0;
-            ++s->nextTicket;
-        }
+        // round robin over the clusters that have reported in
+        if (s->aliveList.size() < s->nClusters && s->aliveNext % 16 == 0) { refreshAlive(s); }
+        if (s->aliveList.empty()) { CGB_TRY(waitForAnyCluster(s)); }
+        const uint32_t cluster = s->aliveList[s->aliveNext++ % s->aliveList.size()];
+        const uint32_t ticket = ++s->clusterTicket[cluster];
         uint64_t &owner = s->slotOwner[static_cast<size_t>(cluster) * kStreamRing + ((ticket - 1u) % kStreamRing)];
         if ((owner >> 32) == (s->mailSeq & 0xffffffffull))
         {
@@ -1336,7 +1384,7 @@ static int evaluateQueue(cgb_sampler *s)
         // the first chunk was streamed while the generator ran; longer batches continue in chunks
         while (done < q.size())
         {
-            const size_t n = std::min<size_t>(kMaxPersistentBatch, q.size() - done);
+            const size_t n = std::min<size_t>(s->chunkCap, q.size() - done);
             if (done > 0)
             {
                 CGB_TRY(beginChunk(s, done));

@@ -1130,7 +1130,9 @@ struct StreamParams
     HostOutcome *outcomes;                     // pinned host memory
     volatile unsigned long long *commitsMirror; // pinned host memory [2]: stats->commitsDone as last seen by the mirror CTA
     StreamStats *stats;
-    unsigned long long serial0;                // first serial this grid will see (multiple of nWorkers)
+    uint32_t *alive;                           // pinned host memory [nWorkers]: a cluster writes `epoch` here when it starts
+    uint32_t ticket0;                          // every cluster's first ticket is ticket0 + 1
+    uint32_t epoch;
     unsigned long long idleTimeoutNs;
     uint32_t nWorkers;                         // worker clusters; cluster nWorkers only mirrors the commit count
     uint32_t pollSleepNs;
@@ -1208,7 +1210,13 @@ __device__ __forceinline__ void stream_worker(const ModelView &mv, const StreamP
         fence_mbar_init();
     }
     __syncthreads();
-    const uint32_t ticket0 = static_cast<uint32_t>(sp.serial0 / sp.nWorkers);
+    const uint32_t ticket0 = sp.ticket0;
+    // report in: the host hands work only to clusters it knows to be running (all CTAs of a cluster are scheduled
+    // together, so the leader speaks for them)
+    if (rank == 0 && tid == 0)
+    {
+        asm volatile("st.volatile.global.u32 [%0], %1;" ::"l"(sp.alive + clusterId), "r"(sp.epoch) : "memory");
+    }
     uint32_t parity = 0;
     for (uint32_t j = 0;; ++j)
     {

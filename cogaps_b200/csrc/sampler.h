@@ -187,14 +187,24 @@ struct cgb_sampler
     void *hStreamOutcomes;        // HostOutcome[kMaxPersistentBatch], pinned + mapped
     void *dStreamStats;           // cgb::StreamStats
     unsigned long long mailSeq;   // tag of the last chunk posted
-    unsigned long long streamSerial; // next task serial; serial % nClusters = cluster, serial / nClusters + 1 = ticket
-    uint32_t nextCluster, nextTicket; // where serial `streamSerial` goes
+    // Work only goes to clusters that have reported in: a worker cluster writes the launch epoch into hAlive[c]
+    // when it starts, so a grid that is not (yet) fully resident — another chain's grid, another process — can
+    // never be handed a task it cannot run.  Tickets are per cluster, consecutive from ticketBase.
+    volatile uint32_t *hAlive;            // [nClusters], pinned + mapped
+    uint32_t launchEpoch;                 // value the clusters of the current launch report
+    uint32_t ticketBase;                  // ticket0 of the current launch
+    std::vector<uint32_t> clusterTicket;  // last ticket handed to each cluster
+    std::vector<uint32_t> aliveList;      // clusters known to be running, in the order they reported
+    std::vector<uint8_t> aliveSeen;
+    size_t aliveNext;                     // round-robin cursor into aliveList
     int persistentGrid;           // CTAs of the resident grid (0 until first launch)
     uint32_t nClusters;           // worker clusters of the resident grid (one more cluster mirrors the commit count)
     double lastPostTime;
     uint32_t chunkTag;            // low 31 bits of mailSeq for the chunk being posted
     uint32_t chunkPosted;         // proposals posted in this chunk
     size_t chunkBase;             // queue index of the chunk's first proposal
+    size_t chunkCap;              // proposals per chunk (kMaxPersistentBatch; smaller in tests of the chunked path)
+    bool forceRowWait;            // tests: never skip the rowVersion check of a row with a recorded commit
     std::vector<uint64_t> slotOwner;      // per (cluster, ring slot): (mailSeq << 32) | proposal index of the last record
     std::vector<cgb::DevProposal> posted; // what was sent for each proposal of the chunk (masses as posted)
     std::vector<uint8_t> arrived;         // outcome of proposal i of the chunk already collected

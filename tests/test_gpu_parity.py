@@ -9,6 +9,8 @@ The oracle is run in reduce mode "device" (the kernel's association order, queri
 cgb_reduction_order_for_length) with the portable log; everything else in it is the arithmetic pinned
 bit-for-bit to the reference by tests/test_oracle_vs_reference.py.
 """
+import os
+
 import numpy as np
 import pytest
 
@@ -363,6 +365,60 @@ def test_launch_per_batch_and_resident_grid_give_the_same_chain(name, monkeypatc
     assert launched.nBatchesA > 0 and resident.nBatchesA > 0
     for f in ("Amean", "Asd", "Pmean", "Psd", "snapshotsA", "snapshotsP", "chisqHistory"):
         assert np.array_equal(bits(getattr(resident, f)), bits(getattr(launched, f))), f
+
+
+@pytest.mark.parametrize("knobs", [
+    dict(COGAPS_FORCE_ROW_WAIT="1"),                                   # every task on a touched row spins on rowVersion
+    dict(COGAPS_PERSISTENT_CLUSTERS="3"),                              # 2 worker clusters: record rings wrap inside a batch
+    dict(COGAPS_CHUNK_PROPOSALS="7"),                                  # batches longer than a chunk: posted in several
+    dict(COGAPS_PERSISTENT_CLUSTERS="4", COGAPS_CHUNK_PROPOSALS="40", COGAPS_FORCE_ROW_WAIT="1"),
+])
+@pytest.mark.parametrize("name", ["gist_async", "sparse_120x90"])
+def test_rarely_taken_paths_of_the_resident_grid(name, knobs, monkeypatch):
+    """The resident grid's fallbacks — rowVersion waits (normally skipped once the host has proof), ring-slot reuse
+    (normally there are more slots than tasks in flight), chunked batches (normally a batch fits one chunk) — forced
+    by environment knobs read at sampler creation; the chain must not change by a bit."""
+    import cogaps_b200 as cg
+    data, unc, kw = case_inputs(name, nIterations=40, snapshotFrequency=20)
+    plain = cg.gaps_run(data, snapshots=True, **kw)
+    for k, v in knobs.items():
+        monkeypatch.setenv(k, v)
+    forced = cg.gaps_run(data, snapshots=True, **kw)
+    assert np.array_equal(plain.atomHistoryA, forced.atomHistoryA)
+    for f in ("Amean", "Asd", "Pmean", "Psd", "snapshotsA", "snapshotsP", "chisqHistory"):
+        assert np.array_equal(bits(getattr(plain, f)), bits(getattr(forced, f))), f
+
+
+@pytest.mark.skipif(os.environ.get("COGAPS_RUN_STRESS", "0") != "1",
+                    reason="opt-in stress test (COGAPS_RUN_STRESS=1): whole runs, setup and teardown included, from several threads")
+def test_chains_sharing_the_device_do_not_disturb_each_other():
+    """cgb_set_resident_share: three chains driven by three host threads at once give, each, the bits it gives alone."""
+    import threading
+    import cogaps_b200 as cg
+    from cogaps_b200._lib import check
+    cases = ["gist_async", "syn_203x117", "sparse_120x90"]
+    inputs = [case_inputs(n, nIterations=40) for n in cases]
+    alone = [cg.gaps_run(d, **kw) for d, _, kw in inputs]
+    together = [None] * len(cases)
+
+    def drive(i):
+        d, _, kw = inputs[i]
+        together[i] = cg.gaps_run(d, **kw)
+
+    check(cg.lib().cgb_set_resident_share(len(cases)))
+    try:
+        threads = [threading.Thread(target=drive, args=(i,)) for i in range(len(cases))]
+        for t in threads:
+            t.start()
+        for t in threads:
+            t.join()
+    finally:
+        check(cg.lib().cgb_set_resident_share(1))
+    for a, b in zip(alone, together):
+        assert b is not None
+        assert np.array_equal(a.atomHistoryA, b.atomHistoryA)
+        for f in ("Amean", "Pmean", "Asd", "Psd"):
+            assert np.array_equal(bits(getattr(a, f)), bits(getattr(b, f))), f
 
 
 def test_long_rows_use_clusters(oracle):
