@@ -1125,7 +1125,9 @@ static int startPersistent(cgb_sampler *s)
     if (s->sparse) { CGB_CUDA(cudaLaunchKernelEx(&cfg, eval_stream_sparse_kernel, mv, sp)); }
     else if (s->hasS) { CGB_CUDA(cudaLaunchKernelEx(&cfg, eval_stream_kernel<true>, mv, sp)); }
     else { CGB_CUDA(cudaLaunchKernelEx(&cfg, eval_stream_kernel<false>, mv, sp)); }
-    CGB_CUDA(cudaEventRecord(s->evStop, s->stream));
+    // No CUDA call from here until the exit records are posted: the grid only ends when this thread says so, and a
+    // runtime call can block behind another thread's cudaFree / allocation that is itself waiting for the device
+    // to drain (several chains per process) — that would be a deadlock.  evStop is recorded in stopPersistent.
     ++g_kernelLaunches;
     s->persistentRunning = true;
     s->lastPostTime = nowSeconds();
@@ -1161,6 +1163,7 @@ static int stopPersistent(cgb_sampler *s)
     volatile unsigned long long *doorbell = reinterpret_cast<volatile unsigned long long*>(static_cast<StreamRecord*>(s->hSlots) + s->nSlotRecords);
     *doorbell = kDoorbellExit;
     __sync_synchronize();
+    CGB_CUDA(cudaEventRecord(s->evStop, s->stream)); // behind the grid on its stream: marks its end
     CGB_CUDA(cudaStreamSynchronize(s->stream));
     s->persistentRunning = false;
     s->provenThrough[0] = s->provenThrough[1] = s->mailSeq; // the grid has drained: every commit it made is complete
