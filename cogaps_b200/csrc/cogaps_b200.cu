@@ -403,7 +403,7 @@ static int samplerCreateImpl(const float *data, uint32_t nrow, uint32_t ncol, in
     }
     s->hSlots = nullptr; s->nSlotRecords = 0; s->hStreamOutcomes = nullptr; s->dStreamStats = nullptr; s->dRowVersion = nullptr;
     s->mailSeq = 0; s->persistentGrid = 0; s->nClusters = 0; s->lastPostTime = 0.0;
-    s->hAlive = nullptr; s->launchEpoch = 0; s->ticketBase = 0; s->aliveNext = 0;
+    s->hAlive = nullptr; s->launchEpoch = 0; s->ticketBase = 0; s->aliveNext = 0; s->aliveLooks = 0;
     s->chunkTag = 0; s->chunkPosted = 0; s->chunkBase = 0;
     s->hCommitsMirror = nullptr;
     s->commitsExpected[0] = s->commitsExpected[1] = s->provenThrough[0] = s->provenThrough[1] = 0;
@@ -1099,6 +1099,7 @@ static int startPersistent(cgb_sampler *s)
     std::fill(s->aliveSeen.begin(), s->aliveSeen.end(), 0);
     s->aliveList.clear();
     s->aliveNext = 0;
+    s->aliveLooks = 0;
     if (++s->launchEpoch == 0u) { s->launchEpoch = 1u; }
     volatile unsigned long long *doorbell = reinterpret_cast<volatile unsigned long long*>(static_cast<StreamRecord*>(s->hSlots) + s->nSlotRecords);
     *doorbell = 0ull;
@@ -1340,9 +1341,10 @@ static int postPrepared(cgb_sampler *s, size_t index)
     for (uint32_t part = 0; part < nParts; ++part)
     {
         // round robin over the clusters that have reported in
-        if (s->aliveList.size() < s->nClusters && s->aliveNext % 16 == 0) { refreshAlive(s); }
+        if (s->aliveList.size() < s->nClusters && (++s->aliveLooks & 7u) == 0) { refreshAlive(s); } // until all are in
         if (s->aliveList.empty()) { CGB_TRY(waitForAnyCluster(s)); }
-        const uint32_t cluster = s->aliveList[s->aliveNext++ % s->aliveList.size()];
+        if (s->aliveNext >= s->aliveList.size()) { s->aliveNext = 0; }
+        const uint32_t cluster = s->aliveList[s->aliveNext++];
         const uint32_t ticket = ++s->clusterTicket[cluster];
         uint64_t &owner = s->slotOwner[static_cast<size_t>(cluster) * kStreamRing + ((ticket - 1u) % kStreamRing)];
         if ((owner >> 32) == (s->mailSeq & 0xffffffffull))

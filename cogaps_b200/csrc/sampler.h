@@ -197,6 +197,7 @@ struct cgb_sampler
     std::vector<uint32_t> aliveList;      // clusters known to be running, in the order they reported
     std::vector<uint8_t> aliveSeen;
     size_t aliveNext;                     // round-robin cursor into aliveList
+    uint32_t aliveLooks;                  // posts since the launch: cadence of the look for newly started clusters
     int persistentGrid;           // CTAs of the resident grid (0 until first launch)
     uint32_t nClusters;           // worker clusters of the resident grid (one more cluster mirrors the commit count)
     double lastPostTime;
