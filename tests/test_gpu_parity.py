@@ -489,3 +489,55 @@ def test_distributed_modes_single_process():
     res = cg.CoGAPS(data, sc, messages=False, outputFrequency=30)
     assert res.featureLoadings.shape[0] == 1363 and res.sampleFactors.shape[0] == 9
     assert not np.isnan(res.sampleFactors).any()
+
+
+def test_full_size_invariants_20000x5000_k20():
+    """BASELINE.json configs[2] at full size (the bench workload), through properties that need no oracle run:
+    (1) the resident grid and one launch per batch give the same chain, bit for bit, with 3-CTA clusters on the
+        P side (L = 20000);
+    (2) the incrementally maintained AP equals A * P^T rebuilt from the factors: chi-square before and after
+        extraInitialization() agree to fp32 round-off, and the A-side and P-side chi-square are the same number;
+    (3) mass conservation: every factor element is the sum of the masses of the atoms in its bin
+        (changeMatrix / safelyChangeMatrix, DenseNormalModel.cpp:110-123), and no element is negative."""
+    import bench
+    import cogaps_b200 as cg
+    g, s, k = 20000, 5000, 20
+    data = bench.make_data(g, s, k)
+
+    def run(persistent, iters=26):
+        chain = bench.Chain(data, k, 42)
+        for smp in (chain.A, chain.P):
+            smp.setPersistent(persistent)
+        updates = 0
+        for i in range(iters):
+            temp = min(1.0, 2.0 * i / iters)
+            chain.A.setAnnealingTemp(temp)
+            chain.P.setAnnealingTemp(temp)
+            updates += chain.step()
+        return chain, updates
+
+    resident, n1 = run(True)
+    launched, n2 = run(False)
+    assert resident.P.reductionOrder()[2] > 1                      # clusters on the long rows
+    assert n1 == n2 and resident.A.nAtoms() == launched.A.nAtoms() and resident.P.nAtoms() == launched.P.nAtoms()
+    assert resident.A.nAtoms() > 1000
+    Ares, Pres = resident.A.getMatrix(), resident.P.getMatrix()
+    assert np.array_equal(bits(Ares), bits(launched.A.getMatrix()))
+    assert np.array_equal(bits(Pres), bits(launched.P.getMatrix()))
+    csA, csP = resident.A.chiSq(), resident.P.chiSq()
+    assert csA == launched.A.chiSq() and csP == launched.P.chiSq()
+    assert csA == pytest.approx(csP, rel=RTOL_CHISQ)
+    # (2) AP kept by ~10^5 rank-one commits vs rebuilt from the factors
+    resident.A.extraInitialization()
+    resident.P.extraInitialization()
+    assert resident.A.chiSq() == pytest.approx(csA, rel=RTOL_CHISQ)
+    assert resident.P.chiSq() == pytest.approx(csP, rel=RTOL_CHISQ)
+    # (3) atoms <-> matrix
+    for smp, M in ((resident.A, Ares), (resident.P, Pres)):
+        assert (M >= 0).all()
+        pos, mass = smp.atoms()
+        nbins = M.shape[0] * k
+        binlen = np.uint64(0xFFFFFFFFFFFFFFFF // nbins)
+        bins = np.minimum((pos // binlen).astype(np.int64), nbins - 1)
+        summed = np.bincount(bins, weights=mass.astype(np.float64), minlength=nbins).reshape(M.shape[0], k)
+        assert np.allclose(summed, M.astype(np.float64), rtol=1e-4, atol=1e-5)
