@@ -265,3 +265,17 @@ def test_distributed_single_cell_world_size_2_gloo(tmp_path):
     assert np.array_equal(a["P"][:, 0], np.arange(1, 104, dtype=np.float32))
     assert a["P"].shape == (103, 3) and a["A"].shape == (60, 3)
     assert float(a["chisq"]) == pytest.approx(4 * 1.5) and int(a["updates"]) == 40
+
+
+def test_concurrent_sets_give_the_sequential_result():
+    """distributedCogaps(concurrentSets=n): a rank's subsets run from n host threads at once (the reference's
+    BiocParallel workers, R/DistributedCogaps.R:60-68); the stitched result does not depend on it."""
+    import cogaps_b200 as cg
+    from cogaps_b200.distributed import distributedCogaps
+    data = np.ones((60, 103), np.float32)
+    params = cg.CogapsParams(nPatterns=3, distributed="single-cell", seed=42)
+    one = distributedCogaps(data, params, runner=_fake_runner)
+    many = distributedCogaps(data, params, runner=_fake_runner, concurrentSets=3)
+    assert np.array_equal(one.sampleFactors, many.sampleFactors)
+    assert np.array_equal(one.featureLoadings, many.featureLoadings)
+    assert one.metadata["meanChiSq"] == many.metadata["meanChiSq"]
