@@ -47,6 +47,36 @@ class RefLib(object):
     def max_threads(self):
         return self.lib.cogaps_ref_max_threads()
 
+    def alpha_parameters_sparse(self, data, A, P, queries):
+        """SparseNormalModel::alphaParameters* of the reference itself; queries as in alpha_parameters."""
+        data, A, P = _f32(data), _f32(A), _f32(P)
+        g, s = data.shape
+        k = A.shape[1]
+        q = np.asarray(queries, dtype=np.float64).reshape(-1, 6)
+        n = q.shape[0]
+        variant = np.ascontiguousarray(q[:, 0], dtype=np.int32)
+        r1, c1, r2, c2 = (_u32(q[:, i]) for i in (1, 2, 3, 4))
+        ch = _f32(q[:, 5])
+        s_out = np.zeros(n, np.float32)
+        smu_out = np.zeros(n, np.float32)
+        rc = self.lib.cogaps_ref_alpha_parameters_sparse(
+            fptr(data), C.c_uint32(g), C.c_uint32(s), C.c_uint32(k), fptr(A), fptr(P),
+            C.c_uint32(n), variant.ctypes.data_as(c_i32_p), r1.ctypes.data_as(c_u32_p),
+            c1.ctypes.data_as(c_u32_p), r2.ctypes.data_as(c_u32_p), c2.ctypes.data_as(c_u32_p),
+            fptr(ch), fptr(s_out), fptr(smu_out))
+        if rc != 0:
+            raise RuntimeError("cogaps_ref_alpha_parameters_sparse failed")
+        return s_out, smu_out
+
+    def chisq_sparse(self, data, A, P):
+        data, A, P = _f32(data), _f32(A), _f32(P)
+        out = np.zeros(3, np.float32)
+        rc = self.lib.cogaps_ref_chisq_sparse(fptr(data), C.c_uint32(data.shape[0]), C.c_uint32(data.shape[1]),
+                                              C.c_uint32(A.shape[1]), fptr(A), fptr(P), fptr(out))
+        if rc != 0:
+            raise RuntimeError("cogaps_ref_chisq_sparse failed")
+        return out
+
     def read_file(self, path):
         """Matrix(path, ...) through the reference's own file parsers."""
         nrow, ncol = C.c_uint32(), C.c_uint32()

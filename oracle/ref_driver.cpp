@@ -28,6 +28,7 @@
 #define protected public
 #include "math/Random.h"
 #include "gibbs_sampler/DenseNormalModel.h"
+#include "gibbs_sampler/SparseNormalModel.h"
 #include "gibbs_sampler/AsynchronousGibbsSampler.h"
 #undef private
 #undef protected
@@ -310,6 +311,61 @@ int cogaps_ref_chisq(const float *data, uint32_t nGenes, uint32_t nSamples, uint
     PModel.extraInitialization();
     out[0] = AModel.chiSq();
     out[1] = PModel.chiSq();
+    return 0;
+}
+
+// The same two probes on SparseNormalModel (src/gibbs_sampler/SparseNormalModel.cpp:39-60,153-311): the three
+// alphaParameters variants of the A-side model, and chiSq of both models, for given factor matrices.
+int cogaps_ref_alpha_parameters_sparse(const float *data, uint32_t nGenes, uint32_t nSamples, uint32_t k,
+                                       const float *A, const float *P,
+                                       uint32_t n, const int32_t *variant, const uint32_t *r1,
+                                       const uint32_t *c1, const uint32_t *r2, const uint32_t *c2,
+                                       const float *ch, float *s_out, float *smu_out)
+{
+    Matrix D = toMatrix(data, nGenes, nSamples);
+    GapsParameters params(D);
+    params.nPatterns = k;
+    params.printMessages = false;
+    params.useSparseOptimization = true;
+    SparseNormalModel AModel(D, true, true, params, params.alphaA, params.maxGibbsMassA);
+    SparseNormalModel PModel(D, false, false, params, params.alphaP, params.maxGibbsMassP);
+    AModel.setMatrix(toMatrix(A, nGenes, k));
+    PModel.setMatrix(toMatrix(P, nSamples, k));
+    AModel.sync(PModel);
+    PModel.sync(AModel);
+    for (uint32_t i = 0; i < n; ++i)
+    {
+        AlphaParameters a(0.f, 0.f);
+        switch (variant[i])
+        {
+            case 0: a = AModel.alphaParameters(r1[i], c1[i]); break;
+            case 1: a = AModel.alphaParameters(r1[i], c1[i], r2[i], c2[i]); break;
+            case 2: a = AModel.alphaParametersWithChange(r1[i], c1[i], ch[i]); break;
+            default: return -1;
+        }
+        s_out[i] = a.s;
+        smu_out[i] = a.s_mu;
+    }
+    return 0;
+}
+
+int cogaps_ref_chisq_sparse(const float *data, uint32_t nGenes, uint32_t nSamples, uint32_t k,
+                            const float *A, const float *P, float *out)
+{
+    Matrix D = toMatrix(data, nGenes, nSamples);
+    GapsParameters params(D);
+    params.nPatterns = k;
+    params.printMessages = false;
+    params.useSparseOptimization = true;
+    SparseNormalModel AModel(D, true, true, params, params.alphaA, params.maxGibbsMassA);
+    SparseNormalModel PModel(D, false, false, params, params.alphaP, params.maxGibbsMassP);
+    AModel.setMatrix(toMatrix(A, nGenes, k));
+    PModel.setMatrix(toMatrix(P, nSamples, k));
+    AModel.sync(PModel);
+    PModel.sync(AModel);
+    out[0] = AModel.chiSq();
+    out[1] = PModel.chiSq();
+    out[2] = PModel.dataSparsity();
     return 0;
 }
 
