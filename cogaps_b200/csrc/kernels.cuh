@@ -1,10 +1,17 @@
 // kernels.cuh — sm_100a kernels of the Gibbs-sampler hot path.
 //
-//   eval_kernel        one cluster per (proposal, row): TMA bulk-stage the touched D/S/AP row segment
-//                      and the 1-2 factor columns into shared memory, the alphaParameters scan
-//                      (DenseNormalModel.cpp:162-240), gibbsMass / accept epilogue on one lane
-//                      (AsynchronousGibbsSampler.h:126-219), AP commit from shared memory
-//                      (DenseNormalModel.cpp:243-258).  HBM-bound: 12-20 B per row element.
+//   eval_stream_kernel the resident grid (one launch per update()): worker clusters poll rings of task records in
+//                      pinned host memory, run process_task / commit_task (or sparse_task) on each, post outcome
+//                      records; one extra CTA mirrors the count of finished commits to the host
+//   eval_kernel        the same device functions, one launch per conflict-free batch.  process_task: one cluster per
+//                      (proposal, row): TMA bulk-stage the touched D/S/AP row segment and the 1-2 factor columns
+//                      into shared memory, the alphaParameters scan (DenseNormalModel.cpp:162-240), gibbsMass /
+//                      accept epilogue on one lane (AsynchronousGibbsSampler.h:126-219, SingleThreadedGibbsSampler.h:
+//                      130-257); commit_task: AP commit from shared memory (DenseNormalModel.cpp:243-258), row
+//                      version + done count.  12-20 B per row element.
+//   probe_kernel       any number of single-row alphaParameters queries in one launch (the scan at saturation)
+//   eval_sparse_kernel / eval_stream_sparse_kernel, sparse_tables_kernel, sparse_chisq_kernel
+//                      SparseNormalModel (SparseNormalModel.cpp:39-60,153-311)
 //   transpose_kernel   DenseNormalModel::sync (DenseNormalModel.cpp:20-36)
 //   rebuild_ap_kernel  extraInitialization (:38-54)
 //   chisq_kernel       chiSq (:56-68)
