@@ -279,3 +279,23 @@ def test_concurrent_sets_give_the_sequential_result():
     assert np.array_equal(one.sampleFactors, many.sampleFactors)
     assert np.array_equal(one.featureLoadings, many.featureLoadings)
     assert one.metadata["meanChiSq"] == many.metadata["meanChiSq"]
+
+
+def test_header_is_plain_c(tmp_path):
+    """The boundary is a C ABI: include/cogaps_b200.h must compile as C99 with nothing but <stdint.h>, and a C
+    program must link against the library by the declared names."""
+    import subprocess
+    src = tmp_path / "abi.c"
+    src.write_text(
+        '#include "cogaps_b200.h"\n'
+        "int main(void)\n"
+        "{\n"
+        "    cgb_params p;\n"
+        "    cgb_params_default(&p);\n"
+        "    return (p.struct_size == sizeof(cgb_params) && p.nPatterns == 3 && cgb_build_report() != 0) ? 0 : 1;\n"
+        "}\n")
+    exe = tmp_path / "abi"
+    libdir = os.path.join(ROOT, "cogaps_b200")
+    subprocess.check_call(["gcc", "-std=c99", "-Wall", "-Wextra", "-pedantic", "-Werror", "-I", os.path.join(ROOT, "include"),
+                           str(src), "-o", str(exe), "-L", libdir, "-lcogaps_b200", "-Wl,-rpath," + libdir])
+    assert subprocess.call([str(exe)]) == 0
