@@ -12,6 +12,19 @@ def pytest_configure(config):
     config.addinivalue_line("markers", "gpu: needs a CUDA device (run on the B200 box: pytest -m gpu)")
 
 
+def pytest_sessionstart(session):
+    """The built artefacts are git-ignored: in a fresh checkout build them (what __graft_entry__.build() does) before
+    any test imports the package.  This is the test harness building the product, not a fallback inside it."""
+    import shutil
+    import subprocess
+    lib = os.path.join(ROOT, "cogaps_b200", "libcogaps_b200.so")
+    if not os.path.exists(lib) and shutil.which("nvcc"):
+        subprocess.check_call(["make", "-s", "-C", os.path.join(ROOT, "cogaps_b200", "csrc"), "HOSTCXX=/usr/bin/g++"])
+    ref = os.path.join(ROOT, "oracle", "_ref", "libcogaps_ref_scalar.so")
+    if not os.path.exists(ref) and os.path.isdir("/root/reference/src"):
+        subprocess.check_call(["make", "-s", "-C", os.path.join(ROOT, "oracle"), "-j3", "ref"])
+
+
 @pytest.fixture(scope="session")
 def oracle():
     """The CPU checker (oracle/libcogaps_oracle.so), built on demand."""
