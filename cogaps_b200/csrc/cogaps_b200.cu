@@ -329,10 +329,13 @@ extern "C" int cgb_reduction_order_for_length(uint32_t rowLength, cgb_reduction_
     return CGB_OK;
 }
 
+static int stopPersistent(cgb_sampler *s);
+
 extern "C" void cgb_sampler_destroy(cgb_sampler *s)
 {
     if (!s) { return; }
     cudaSetDevice(s->device);
+    if (s->persistentRunning) { stopPersistent(s); } // never free what a resident grid may still touch
     cudaFree(s->dD); cudaFree(s->dS); cudaFree(s->dAP); cudaFree(s->dM); cudaFree(s->dColNonzero);
     cudaFree(s->dPartials); cudaFree(s->dTickets); cudaFree(s->dReducePartials); cudaFree(s->dPhaseClocks);
     cudaFree(s->dRowVersion); cudaFree(s->dStreamStats);
