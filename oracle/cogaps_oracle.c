@@ -1977,6 +1977,216 @@ static float stats_mean_chisq(const stats_t *st, const model_t *P)
     return chisq;
 }
 
+/* ============================ checkpoints ========================================== */
+/* The Archive wire format (utils/Archive.h:16-87): raw little-endian scalars behind a u32 magic number, written in
+ * the order createCheckpoint streams them (GapsRunner.cpp:237-240).  Asynchronous sampler only: the reference's
+ * SingleThreadedGibbsSampler does not save its rng and its operator>> writes instead of reading
+ * (SingleThreadedGibbsSampler.h:260-273), so a sequential run cannot be resumed there either. */
+#define ARCHIVE_MAGIC 0xB123AA4Du
+
+typedef struct { FILE *f; int ok; } archive_t;
+
+static void ar_put(archive_t *ar, const void *v, size_t n) { if (ar->ok && fwrite(v, 1, n, ar->f) != n) { ar->ok = 0; } }
+static void ar_get(archive_t *ar, void *v, size_t n) { if (ar->ok && fread(v, 1, n, ar->f) != n) { ar->ok = 0; } }
+#define AR_PUT(ar, type, val) do { type tmp_ = (type)(val); ar_put((ar), &tmp_, sizeof(tmp_)); } while (0)
+#define AR_GET(ar, lvalue) ar_get((ar), &(lvalue), sizeof(lvalue))
+
+/* Matrix << (Matrix.cpp:182-190): nRows nCols, then every column as a Vector (Vector.cpp:90-98: size, floats) */
+static void ar_put_matrix(archive_t *ar, const float *colMajor, uint32_t rows, uint32_t cols)
+{
+    AR_PUT(ar, uint32_t, rows);
+    AR_PUT(ar, uint32_t, cols);
+    for (uint32_t c = 0; c < cols; ++c)
+    {
+        AR_PUT(ar, uint32_t, rows);
+        ar_put(ar, colMajor + (size_t)c * rows, sizeof(float) * rows);
+    }
+}
+
+static void ar_get_matrix(archive_t *ar, float *colMajor, uint32_t rows, uint32_t cols)
+{
+    uint32_t nr = 0, nc = 0;
+    AR_GET(ar, nr);
+    AR_GET(ar, nc);
+    if (nr != rows || nc != cols) { ar->ok = 0; return; } /* GAPS_ASSERT in Matrix.cpp:196-197 */
+    for (uint32_t c = 0; c < cols && ar->ok; ++c)
+    {
+        uint32_t sz = 0;
+        AR_GET(ar, sz);
+        if (sz != rows) { ar->ok = 0; return; }
+        ar_get(ar, colMajor + (size_t)c * rows, sizeof(float) * rows);
+    }
+}
+
+/* DenseNormalModel << (DenseNormalModel.cpp:260-264) / SparseNormalModel << (SparseNormalModel.cpp:313-317 ->
+ * HybridMatrix.cpp:85-97: rows as Vectors, columns as HybridVectors with their flag words, then beta) */
+static void ar_put_model(archive_t *ar, const model_t *m)
+{
+    if (!m->sparse) { ar_put_matrix(ar, m->M, m->nRows, m->k); return; }
+    AR_PUT(ar, uint32_t, m->nRows);
+    AR_PUT(ar, uint32_t, m->k);
+    for (uint32_t r = 0; r < m->nRows; ++r)
+    {
+        AR_PUT(ar, uint32_t, m->k);
+        ar_put(ar, m->Mrows + (size_t)r * m->k, sizeof(float) * m->k);
+    }
+    uint32_t nWords = m->nRows / 64 + 1; /* HybridVector.cpp:12 */
+    uint64_t *flags = (uint64_t*)malloc(sizeof(uint64_t) * nWords);
+    for (uint32_t c = 0; c < m->k; ++c)
+    {
+        const float *col = m->M + (size_t)c * m->nRows;
+        memset(flags, 0, sizeof(uint64_t) * nWords);
+        for (uint32_t r = 0; r < m->nRows; ++r) { if (col[r] != 0.f) { flags[r / 64] |= 1ull << (r % 64); } }
+        AR_PUT(ar, uint32_t, m->nRows);
+        ar_put(ar, flags, sizeof(uint64_t) * nWords);
+        ar_put(ar, col, sizeof(float) * m->nRows);
+    }
+    free(flags);
+    AR_PUT(ar, float, m->beta);
+}
+
+static void ar_get_model(archive_t *ar, model_t *m)
+{
+    if (!m->sparse) { ar_get_matrix(ar, m->M, m->nRows, m->k); return; }
+    uint32_t nr = 0, nc = 0;
+    AR_GET(ar, nr);
+    AR_GET(ar, nc);
+    if (nr != m->nRows || nc != m->k) { ar->ok = 0; return; }
+    for (uint32_t r = 0; r < m->nRows && ar->ok; ++r)
+    {
+        uint32_t sz = 0;
+        AR_GET(ar, sz);
+        if (sz != m->k) { ar->ok = 0; return; }
+        ar_get(ar, m->Mrows + (size_t)r * m->k, sizeof(float) * m->k);
+    }
+    uint32_t nWords = m->nRows / 64 + 1;
+    uint64_t *flags = (uint64_t*)malloc(sizeof(uint64_t) * nWords);
+    for (uint32_t c = 0; c < m->k && ar->ok; ++c)
+    {
+        uint32_t sz = 0;
+        AR_GET(ar, sz);
+        if (sz != m->nRows) { ar->ok = 0; break; }
+        ar_get(ar, flags, sizeof(uint64_t) * nWords); /* implied by the values: set iff the value is not 0 */
+        ar_get(ar, m->M + (size_t)c * m->nRows, sizeof(float) * m->nRows);
+    }
+    free(flags);
+    AR_GET(ar, m->beta);
+}
+
+/* AsynchronousGibbsSampler << (AsynchronousGibbsSampler.h:221-226): model, ConcurrentAtomicDomain
+ * (ConcurrentAtomicDomain.cpp:134-142: atoms in pick-vector order), ProposalQueue (ProposalQueue.cpp:285-291) */
+static void ar_put_sampler(archive_t *ar, const sampler_t *s)
+{
+    ar_put_model(ar, &s->model);
+    AR_PUT(ar, uint64_t, s->domain.domainLength);
+    AR_PUT(ar, uint64_t, s->domain.n);
+    for (uint32_t i = 0; i < s->domain.n; ++i)
+    {
+        const atom_t *a = &s->domain.pool[s->domain.vec[i]];
+        AR_PUT(ar, uint64_t, a->pos);
+        AR_PUT(ar, float, a->mass);
+    }
+    const queue_t *q = &s->queue;
+    AR_PUT(ar, uint64_t, q->rng.state);
+    AR_PUT(ar, uint64_t, q->minAtoms);
+    AR_PUT(ar, uint64_t, q->maxAtoms);
+    AR_PUT(ar, uint64_t, q->binLength);
+    AR_PUT(ar, uint64_t, q->numCols);
+    AR_PUT(ar, double, q->alpha);
+    AR_PUT(ar, double, q->domainLength);
+    AR_PUT(ar, double, q->numBins);
+    AR_PUT(ar, float, q->lambda);
+    AR_PUT(ar, uint8_t, q->useCachedRng ? 1 : 0);
+    AR_PUT(ar, float, q->u1);
+    AR_PUT(ar, float, q->u2);
+}
+
+static void ar_get_sampler(archive_t *ar, sampler_t *s)
+{
+    ar_get_model(ar, &s->model);
+    uint64_t n = 0;
+    AR_GET(ar, s->domain.domainLength);
+    AR_GET(ar, n);
+    for (uint64_t i = 0; i < n && ar->ok; ++i) /* ConcurrentAtomicDomain.cpp:144-155: inserted in archive order */
+    {
+        uint64_t pos = 0;
+        float mass = 0.f;
+        AR_GET(ar, pos);
+        AR_GET(ar, mass);
+        if (ar->ok) { domain_insert(&s->domain, pos, mass); }
+    }
+    queue_t *q = &s->queue;
+    uint8_t cached = 0;
+    AR_GET(ar, q->rng.state);
+    AR_GET(ar, q->minAtoms);
+    AR_GET(ar, q->maxAtoms);
+    AR_GET(ar, q->binLength);
+    AR_GET(ar, q->numCols);
+    AR_GET(ar, q->alpha);
+    AR_GET(ar, q->domainLength);
+    AR_GET(ar, q->numBins);
+    AR_GET(ar, q->lambda);
+    AR_GET(ar, cached);
+    AR_GET(ar, q->u1);
+    AR_GET(ar, q->u2);
+    q->useCachedRng = cached != 0;
+}
+
+/* GapsParameters << (GapsParameters.cpp:82-88) */
+static void ar_put_params(archive_t *ar, const cgb_params *p, uint32_t nGenes, uint32_t nSamples, uint32_t interval)
+{
+    AR_PUT(ar, uint32_t, p->seed);
+    AR_PUT(ar, uint32_t, nGenes);
+    AR_PUT(ar, uint32_t, nSamples);
+    AR_PUT(ar, uint32_t, p->nPatterns);
+    AR_PUT(ar, uint32_t, p->nIterations);
+    AR_PUT(ar, float, p->alphaA);
+    AR_PUT(ar, float, p->alphaP);
+    AR_PUT(ar, float, p->maxGibbsMassA);
+    AR_PUT(ar, float, p->maxGibbsMassP);
+    AR_PUT(ar, uint8_t, p->useSparseOptimization ? 1 : 0);
+    AR_PUT(ar, uint32_t, interval);
+}
+
+static void ar_get_params(archive_t *ar, cgb_params *p, uint32_t *nGenes, uint32_t *nSamples, uint32_t *interval)
+{
+    uint8_t sparse = 0;
+    AR_GET(ar, p->seed);
+    AR_GET(ar, *nGenes);
+    AR_GET(ar, *nSamples);
+    AR_GET(ar, p->nPatterns);
+    AR_GET(ar, p->nIterations);
+    AR_GET(ar, p->alphaA);
+    AR_GET(ar, p->alphaP);
+    AR_GET(ar, p->maxGibbsMassA);
+    AR_GET(ar, p->maxGibbsMassP);
+    AR_GET(ar, sparse);
+    AR_GET(ar, *interval);
+    p->useSparseOptimization = sparse != 0;
+}
+
+static int archive_open(archive_t *ar, const char *path, int write)
+{
+    ar->f = fopen(path, write ? "wb" : "rb");
+    ar->ok = ar->f != NULL;
+    if (!ar->ok) { return 0; }
+    if (write) { AR_PUT(ar, uint32_t, ARCHIVE_MAGIC); }
+    else
+    {
+        uint32_t magic = 0;
+        AR_GET(ar, magic);
+        if (magic != ARCHIVE_MAGIC) { ar->ok = 0; } /* "incompatible checkpoint file", Archive.h:33-36 */
+    }
+    return ar->ok;
+}
+
+static int archive_close(archive_t *ar)
+{
+    if (ar->f && fclose(ar->f) != 0) { ar->ok = 0; }
+    ar->f = NULL;
+    return ar->ok;
+}
+
 /* ============================ run loop ============================================= */
 static void snapshot(const model_t *m, float *dst)
 {
@@ -1989,11 +2199,28 @@ static void snapshot(const model_t *m, float *dst)
 
 /* runCoGAPSAlgorithm + runOnePhase + updateSampler + displayStatus, GapsRunner.cpp:161-222,272-327,381-503 */
 int cogaps_oracle_run_trace(const float *data, uint32_t nrow, uint32_t ncol, const float *uncertainty,
-                            const cgb_params *p, cgb_result *r, const oracle_options *opt,
+                            const cgb_params *p0, cgb_result *r, const oracle_options *opt,
                             oracle_trace_record *traceBuf, uint64_t capacity, uint64_t *count)
 {
+    cgb_params pv = *p0;
+    const cgb_params *p = &pv;
+    uint32_t ckInterval = opt ? opt->checkpointInterval : 0;
+    const char *ckIn = (opt && opt->checkpointInFile && opt->checkpointInFile[0]) ? opt->checkpointInFile : NULL;
+    const char *ckOut = (opt && opt->checkpointOutFile && opt->checkpointOutFile[0]) ? opt->checkpointOutFile : "gaps_checkpoint.out";
+    if ((ckInterval > 0 || ckIn) && !p->asynchronousUpdates) { return -5; } /* see "checkpoints" above */
     randstate_t *rs = (randstate_t*)malloc(sizeof(randstate_t));
     randstate_init(rs, p->seed, opt);
+    if (ckIn)
+    {
+        /* run_helper, GapsRunner.cpp:99-105: parameters and the seeder come from the file before anything is built */
+        archive_t ar;
+        uint32_t fileGenes = 0, fileSamples = 0;
+        if (!archive_open(&ar, ckIn, 0)) { archive_close(&ar); free(rs); return -1; }
+        ar_get_params(&ar, &pv, &fileGenes, &fileSamples, &ckInterval);
+        AR_GET(&ar, rs->seeder.s[0]);
+        AR_GET(&ar, rs->seeder.s[1]);
+        if (!archive_close(&ar)) { free(rs); return -1; }
+    }
     trace_t trace;
     memset(&trace, 0, sizeof(trace));
     trace.rec = traceBuf;
@@ -2023,6 +2250,35 @@ int cogaps_oracle_run_trace(const float *data, uint32_t nrow, uint32_t ncol, con
     stats_init(&st, nGenes, nSamples, p->nPatterns);
     rng_t rng;
     rng_init(&rng, rs);
+    int rc = 0;
+    int startPhase = CGB_PHASE_EQUILIBRATION;
+    uint32_t startIter = 0;
+    if (ckIn)
+    {
+        /* processCheckpoint, GapsRunner.cpp:258-270 */
+        archive_t ar;
+        cgb_params again = pv;
+        uint32_t g2 = 0, s2 = 0, interval2 = 0;
+        int32_t iPhase = 0;
+        archive_open(&ar, ckIn, 0);
+        ar_get_params(&ar, &again, &g2, &s2, &interval2);
+        if (ar.ok && (g2 != nGenes || s2 != nSamples)) { ar.ok = 0; } /* the data is not what the checkpoint was made from */
+        AR_GET(&ar, rs->seeder.s[0]);
+        AR_GET(&ar, rs->seeder.s[1]);
+        if (ar.ok) { ar_get_sampler(&ar, &A); }
+        if (ar.ok) { ar_get_sampler(&ar, &P); }
+        if (ar.ok) { ar_get_matrix(&ar, st.Amean, nGenes, p->nPatterns); }
+        if (ar.ok) { ar_get_matrix(&ar, st.Astd, nGenes, p->nPatterns); }
+        if (ar.ok) { ar_get_matrix(&ar, st.Pmean, nSamples, p->nPatterns); }
+        if (ar.ok) { ar_get_matrix(&ar, st.Pstd, nSamples, p->nPatterns); }
+        AR_GET(&ar, st.statUpdates);
+        AR_GET(&ar, st.k);
+        AR_GET(&ar, iPhase);
+        AR_GET(&ar, startIter);
+        AR_GET(&ar, rng.state);
+        if (!archive_close(&ar) || (iPhase != CGB_PHASE_EQUILIBRATION && iPhase != CGB_PHASE_SAMPLING)) { rc = -1; goto done; }
+        startPhase = iPhase;
+    }
 
     model_sync(&A.model, &P.model);
     model_sync(&P.model, &A.model);
@@ -2031,12 +2287,44 @@ int cogaps_oracle_run_trace(const float *data, uint32_t nrow, uint32_t ncol, con
 
     uint64_t totalUpdates = 0;
     uint32_t nHist = 0, nSnapEq = 0, nSnapSamp = 0;
-    for (int phase = CGB_PHASE_EQUILIBRATION; phase <= CGB_PHASE_SAMPLING; ++phase)
+    for (int phase = startPhase; phase <= CGB_PHASE_SAMPLING; ++phase)
     {
-        for (uint32_t iter = 0; iter < p->nIterations; ++iter)
+        for (uint32_t iter = (phase == startPhase) ? startIter : 0; iter < p->nIterations; ++iter)
         {
             trace.phase = (uint32_t)phase;
             trace.iter = iter;
+            /* createCheckpoint, GapsRunner.cpp:226-256 */
+            if (ckInterval > 0 && ((iter + 1) % ckInterval) == 0 && p->nSubsetIndices == 0)
+            {
+                size_t len = strlen(ckOut);
+                char *backup = (char*)malloc(len + 8);
+                memcpy(backup, ckOut, len);
+                memcpy(backup + len, ".backup", 8);
+                rename(ckOut, backup);
+                archive_t ar;
+                archive_open(&ar, ckOut, 1);
+                ar_put_params(&ar, p, nGenes, nSamples, ckInterval);
+                AR_PUT(&ar, uint64_t, rs->seeder.s[0]);
+                AR_PUT(&ar, uint64_t, rs->seeder.s[1]);
+                ar_put_sampler(&ar, &A);
+                ar_put_sampler(&ar, &P);
+                ar_put_matrix(&ar, st.Amean, nGenes, p->nPatterns);
+                ar_put_matrix(&ar, st.Astd, nGenes, p->nPatterns);
+                ar_put_matrix(&ar, st.Pmean, nSamples, p->nPatterns);
+                ar_put_matrix(&ar, st.Pstd, nSamples, p->nPatterns);
+                AR_PUT(&ar, uint32_t, st.statUpdates);
+                AR_PUT(&ar, uint32_t, st.k);
+                AR_PUT(&ar, int32_t, phase);
+                AR_PUT(&ar, uint32_t, iter);
+                AR_PUT(&ar, uint64_t, rng.state);
+                int written = archive_close(&ar);
+                remove(backup);
+                free(backup);
+                if (!written) { rc = -1; goto done; }
+                /* "running the extra initialization here allows for consistency with runs started from a checkpoint" */
+                model_extra_initialization(&A.model);
+                model_extra_initialization(&P.model);
+            }
             if (phase == CGB_PHASE_EQUILIBRATION)
             {
                 float temp = (float)(2 * iter) / (float)p->nIterations;
@@ -2133,11 +2421,12 @@ int cogaps_oracle_run_trace(const float *data, uint32_t nrow, uint32_t ncol, con
         }
     }
     if (count) { *count = trace.count; }
+done:
     stats_free(&st);
     sampler_free(&A);
     sampler_free(&P);
     free(rs);
-    return 0;
+    return rc;
 }
 
 int cogaps_oracle_run(const float *data, uint32_t nrow, uint32_t ncol, const float *uncertainty,

@@ -39,6 +39,10 @@ typedef struct oracle_options
     const float *erf;           /* optional table overrides (NULL = built in)   */
     const float *erfinv;
     const float *qgamma;
+    /* checkpoints (GapsParameters.h:37-38,46,56; GapsRunner.cpp:224-270), asynchronous sampler only */
+    uint32_t checkpointInterval;   /* 0 = never */
+    const char *checkpointOutFile; /* NULL = "gaps_checkpoint.out" (GapsParameters.h:83) */
+    const char *checkpointInFile;  /* non-NULL = resume (useCheckPoint) */
 } oracle_options;
 
 /* one evaluated proposal, for lock-step comparison and host-logic replay tests */

@@ -24,6 +24,10 @@ def _u32(a):
     return np.ascontiguousarray(a, dtype=np.uint32)
 
 
+def _path(p):
+    return None if p is None else os.fspath(p).encode()
+
+
 class RefLib(object):
     """The reference C++ core behind oracle/ref_driver.cpp."""
 
@@ -85,13 +89,16 @@ class RefLib(object):
         self.lib.cogaps_ref_read_file(str(path).encode(), fptr(out), C.byref(nrow), C.byref(ncol))
         return out
 
-    def run(self, data, uncertainty=None, snapshots=False, **kw):
+    def run(self, data, uncertainty=None, snapshots=False, checkpointInterval=0, checkpointOutFile=None,
+            checkpointInFile=None, **kw):
+        """gaps::run; the checkpoint arguments are the reference's own (GapsParameters.h:37-38,46,56)."""
         data = _f32(data)
         unc = _f32(uncertainty) if uncertainty is not None else None
         p = make_params(**kw)
         res = ResultArrays(p, data.shape[0], data.shape[1], snapshots=snapshots)
-        rc = self.lib.cogaps_ref_run(fptr(data), C.c_uint32(data.shape[0]), C.c_uint32(data.shape[1]),
-                                     fptr(unc), C.byref(p), C.byref(res.c))
+        rc = self.lib.cogaps_ref_run_checkpointed(
+            fptr(data), C.c_uint32(data.shape[0]), C.c_uint32(data.shape[1]), fptr(unc), C.byref(p), C.byref(res.c),
+            C.c_uint32(checkpointInterval), _path(checkpointOutFile), _path(checkpointInFile))
         if rc != 0:
             raise RuntimeError("cogaps_ref_run failed: %d" % rc)
         return res.finish()
@@ -154,6 +161,9 @@ class OracleOptions(C.Structure):
         ("erf", c_float_p),
         ("erfinv", c_float_p),
         ("qgamma", c_float_p),
+        ("checkpointInterval", C.c_uint32),
+        ("checkpointOutFile", C.c_char_p),
+        ("checkpointInFile", C.c_char_p),
     ]
 
 
@@ -186,7 +196,8 @@ class OracleLib(object):
         self.lib.cogaps_oracle_portable_logf.argtypes = [C.c_float]
 
     @staticmethod
-    def options(reduce="scalar", math="libm", orderA=None, orderP=None, tables=None):
+    def options(reduce="scalar", math="libm", orderA=None, orderP=None, tables=None, checkpointInterval=0,
+                checkpointOutFile=None, checkpointInFile=None):
         o = OracleOptions()
         o.reduceMode = {"scalar": REDUCE_SCALAR, "avx8": REDUCE_AVX8, "device": REDUCE_DEVICE}[reduce]
         o.mathMode = {"libm": MATH_LIBM, "portable": MATH_PORTABLE}[math]
@@ -199,6 +210,9 @@ class OracleLib(object):
             erf, erfinv, qgamma = (_f32(t) for t in tables)
             keep = [erf, erfinv, qgamma]
             o.erf, o.erfinv, o.qgamma = fptr(erf), fptr(erfinv), fptr(qgamma)
+        o.checkpointInterval = checkpointInterval
+        o.checkpointOutFile = _path(checkpointOutFile)
+        o.checkpointInFile = _path(checkpointInFile)
         o._keepalive = keep
         return o
 

@@ -88,9 +88,12 @@ int cogaps_ref_max_threads(void)
 #endif
 }
 
-// gaps::run on an in-memory matrix (src/GapsRunner.cpp:113-117).
-int cogaps_ref_run(const float *data, uint32_t nrow, uint32_t ncol, const float *uncertainty,
-                   const cgb_params *p, cgb_result *r)
+// gaps::run on an in-memory matrix (src/GapsRunner.cpp:113-117), with the reference's own checkpointing
+// (createCheckpoint / processCheckpoint, GapsRunner.cpp:224-270): interval 0 = never write one;
+// inFile non-empty = resume from that file (params.useCheckPoint, run_helper :96-107).
+int cogaps_ref_run_checkpointed(const float *data, uint32_t nrow, uint32_t ncol, const float *uncertainty,
+                                const cgb_params *p, cgb_result *r, uint32_t checkpointInterval,
+                                const char *checkpointOutFile, const char *checkpointInFile)
 {
     Matrix D = toMatrix(data, nrow, ncol);
     Matrix U = (uncertainty != NULL) ? toMatrix(uncertainty, nrow, ncol) : Matrix();
@@ -103,7 +106,13 @@ int cogaps_ref_run(const float *data, uint32_t nrow, uint32_t ncol, const float 
     params.nIterations = p->nIterations;
     params.maxThreads = p->maxThreads;
     params.outputFrequency = p->outputFrequency;
-    params.checkpointInterval = 0;
+    params.checkpointInterval = checkpointInterval;
+    if (checkpointOutFile != NULL && checkpointOutFile[0] != 0) { params.checkpointOutFile = checkpointOutFile; }
+    if (checkpointInFile != NULL && checkpointInFile[0] != 0)
+    {
+        params.checkpointFile = checkpointInFile;
+        params.useCheckPoint = true;
+    }
     params.snapshotFrequency = p->snapshotFrequency;
     params.snapshotPhase = static_cast<GapsAlgorithmPhase>(p->snapshotPhase);
     params.alphaA = p->alphaA;
@@ -167,6 +176,12 @@ int cogaps_ref_run(const float *data, uint32_t nrow, uint32_t ncol, const float 
     r->averageQueueLengthA = res.averageQueueLengthA;
     r->averageQueueLengthP = res.averageQueueLengthP;
     return 0;
+}
+
+int cogaps_ref_run(const float *data, uint32_t nrow, uint32_t ncol, const float *uncertainty,
+                   const cgb_params *p, cgb_result *r)
+{
+    return cogaps_ref_run_checkpointed(data, nrow, ncol, uncertainty, p, r, 0, NULL, NULL);
 }
 
 // Matrix(const std::string &path, ...) through the reference's own FileParser (src/data_structures/Matrix.cpp:72-134,
