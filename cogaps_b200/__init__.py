@@ -3,6 +3,7 @@
 Layout: csrc/ holds the CUDA kernels and the C ABI (libcogaps_b200.so, declared in include/cogaps_b200.h);
 this package is the thin host-side mirror of the reference's R/C++ interface for that path.
 """
-from .api import CoGAPS, CogapsParams, CogapsResult, gaps_run, gaps_run_file, read_matrix_file  # noqa: F401
+from .api import (CoGAPS, CogapsParams, CogapsResult, gaps_run, gaps_run_file, read_matrix_file,  # noqa: F401
+                  checkpoint_info, checkpoint_rewrite)
 from .sampler import GapsRandomState, GapsRng, GibbsSampler, GapsStatistics  # noqa: F401
 from ._lib import CogapsError, LIB_PATH, lib  # noqa: F401

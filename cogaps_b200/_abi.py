@@ -8,6 +8,7 @@ CGB_ECUDA = -3
 CGB_ENOMEM = -4
 CGB_EUNSUPPORTED = -5
 CGB_EINTERNAL = -6
+CGB_EINTERRUPTED = -7
 
 ERF_TABLE_SIZE = 3001
 ERFINV_TABLE_SIZE = 5001
@@ -134,4 +135,43 @@ class CgbReductionOrder(C.Structure):
         ("vectorWidth", C.c_uint32),
         ("nSegments", C.c_uint32),
         ("segmentLength", C.c_uint32),
+    ]
+
+
+INTERRUPT_FN = C.CFUNCTYPE(C.c_int32, C.c_void_p)
+
+
+class CgbRunOptions(C.Structure):
+    """struct cgb_run_options — checkpoints (GapsParameters.h:37-38,46,56) and the per-iteration interrupt poll."""
+    _fields_ = [
+        ("struct_size", C.c_uint32),
+        ("checkpointInterval", C.c_uint32),
+        ("checkpointOutFile", C.c_char_p),
+        ("checkpointInFile", C.c_char_p),
+        ("interrupt", INTERRUPT_FN),
+        ("interruptUser", C.c_void_p),
+    ]
+
+
+class CgbCheckpointInfo(C.Structure):
+    """struct cgb_checkpoint_info"""
+    _fields_ = [
+        ("struct_size", C.c_uint32),
+        ("seed", C.c_uint32),
+        ("nGenes", C.c_uint32),
+        ("nSamples", C.c_uint32),
+        ("nPatterns", C.c_uint32),
+        ("nIterations", C.c_uint32),
+        ("alphaA", C.c_float),
+        ("alphaP", C.c_float),
+        ("maxGibbsMassA", C.c_float),
+        ("maxGibbsMassP", C.c_float),
+        ("useSparseOptimization", C.c_int32),
+        ("checkpointInterval", C.c_uint32),
+        ("phase", C.c_int32),
+        ("iter", C.c_uint32),
+        ("nAtomsA", C.c_uint64),
+        ("nAtomsP", C.c_uint64),
+        ("statUpdates", C.c_uint32),
+        ("fileBytes", C.c_uint64),
     ]

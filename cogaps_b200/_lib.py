@@ -6,8 +6,8 @@ and on a machine without an sm_100-class GPU every compute entry point returns C
 import ctypes as C
 import os
 
-from ._abi import (CgbParams, CgbResult, CgbSamplerCounters, CgbReductionOrder, c_float_p, c_u32_p,
-                   c_u64_p, c_i32_p)
+from ._abi import (CgbParams, CgbResult, CgbSamplerCounters, CgbReductionOrder, CgbRunOptions, CgbCheckpointInfo,
+                   c_float_p, c_u32_p, c_u64_p, c_i32_p)
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(HERE, "libcogaps_b200.so")
@@ -30,6 +30,9 @@ EXPORTS = [
     "cgb_stats_pmean", "cgb_stats_psd", "cgb_stats_pump_matrix", "cgb_stats_mean_pattern",
     "cgb_stats_mean_chisq", "cgb_sampler_device_matrix", "cgb_stats_device_sums", "cgb_run_set_tables",
     "cgb_debug_logf", "cgb_debug_host_logf", "cgb_debug_fastdiv", "cgb_run_file", "cgb_read_matrix_file",
+    "cgb_run_ex", "cgb_sampler_serialize", "cgb_sampler_deserialize", "cgb_sampler_set_atoms", "cgb_stats_serialize",
+    "cgb_stats_deserialize", "cgb_randstate_get_state", "cgb_randstate_set_state", "cgb_rng_get_state", "cgb_rng_set_state",
+    "cgb_checkpoint_info_read", "cgb_checkpoint_rewrite",
 ]
 
 _lib = None
@@ -121,6 +124,19 @@ def lib():
                                         c_u64_p, c_u64_p, c_u32_p]
     L.cgb_run_set_tables.argtypes = [c_float_p, c_float_p, c_float_p]
     L.cgb_debug_logf.argtypes = [c_float_p, c_float_p, C.c_uint32]
+    L.cgb_run_ex.argtypes = [c_float_p, C.c_uint32, C.c_uint32, C.c_int32, c_float_p, C.POINTER(CgbParams),
+                             C.POINTER(CgbRunOptions), C.POINTER(CgbResult)]
+    L.cgb_sampler_serialize.argtypes = [vp, vp, C.c_uint64, c_u64_p]
+    L.cgb_sampler_deserialize.argtypes = [vp, vp, C.c_uint64]
+    L.cgb_sampler_set_atoms.argtypes = [vp, c_u64_p, c_float_p, C.c_uint64]
+    L.cgb_stats_serialize.argtypes = [vp, vp, C.c_uint64, c_u64_p]
+    L.cgb_stats_deserialize.argtypes = [vp, vp, C.c_uint64]
+    L.cgb_randstate_get_state.argtypes = [vp, c_u64_p]
+    L.cgb_randstate_set_state.argtypes = [vp, c_u64_p]
+    L.cgb_rng_get_state.argtypes = [vp, c_u64_p]
+    L.cgb_rng_set_state.argtypes = [vp, C.c_uint64]
+    L.cgb_checkpoint_info_read.argtypes = [C.c_char_p, C.POINTER(CgbCheckpointInfo)]
+    L.cgb_checkpoint_rewrite.argtypes = [C.c_char_p, C.c_char_p]
     _lib = L
     return L
 

@@ -10,11 +10,12 @@ and packs parameters exactly like getGapsParameters (src/Cogaps.cpp:63-139) and 
 All computation happens in libcogaps_b200.so on the GPU.
 """
 import ctypes as C
+import os
 import time
 
 import numpy as np
 
-from ._abi import PHASE_ALL, PHASE_EQUILIBRATION, PHASE_SAMPLING
+from ._abi import PHASE_ALL, PHASE_EQUILIBRATION, PHASE_SAMPLING, CgbRunOptions, CgbCheckpointInfo, INTERRUPT_FN
 from ._lib import lib, check
 from ._runhelp import make_params, ResultArrays, fptr
 
@@ -147,17 +148,52 @@ class CogapsResult(object):
         return self.metadata["meanChiSq"]
 
 
-def gaps_run(data, uncertainty=None, snapshots=False, **kw):
+def _path(p):
+    return None if p is None else os.fspath(p).encode()
+
+
+def gaps_run(data, uncertainty=None, snapshots=False, checkpointInterval=0, checkpointOutFile=None,
+             checkpointInFile=None, interrupt=None, **kw):
     """gaps::run (src/GapsRunner.h:14-24) through the C ABI: data nrow x ncol fp32 host array -> result arrays.
-    Keyword arguments are the fields of cgb_params / GapsParameters."""
+    Keyword arguments are the fields of cgb_params / GapsParameters.  The checkpoint arguments are the reference's
+    (GapsParameters.h:37-38,46,56; GapsRunner.cpp:224-270): a checkpoint file is written every `checkpointInterval`
+    iterations, `checkpointInFile` resumes from one (seed, nIterations, alphas, maxGibbsMass, sparseOptimization and
+    the interval then come from the file).  `interrupt` is a callable polled once per iteration on this thread
+    (Rcpp::checkUserInterrupt, GapsRunner.cpp:280); a true return stops the run with CogapsError(CGB_EINTERRUPTED)."""
     data = np.ascontiguousarray(data, dtype=np.float32)
     unc = np.ascontiguousarray(uncertainty, dtype=np.float32) if uncertainty is not None else None
     if unc is not None and unc.shape != data.shape:
         raise ValueError("uncertainty must have the same dimensions as the data")
     p = make_params(**kw)
     res = ResultArrays(p, data.shape[0], data.shape[1], snapshots=snapshots)
-    check(lib().cgb_run(fptr(data), data.shape[0], data.shape[1], 0, fptr(unc), C.byref(p), C.byref(res.c)))
+    if not checkpointInterval and checkpointInFile is None and interrupt is None:
+        check(lib().cgb_run(fptr(data), data.shape[0], data.shape[1], 0, fptr(unc), C.byref(p), C.byref(res.c)))
+        return res.finish()
+    opt = CgbRunOptions()
+    opt.struct_size = C.sizeof(CgbRunOptions)
+    opt.checkpointInterval = int(checkpointInterval)
+    opt.checkpointOutFile = _path(checkpointOutFile)
+    opt.checkpointInFile = _path(checkpointInFile)
+    callback = INTERRUPT_FN(lambda _user: 1 if interrupt() else 0) if interrupt is not None else None
+    if callback is not None:
+        opt.interrupt = callback        # `callback` stays referenced until the call returns
+    check(lib().cgb_run_ex(fptr(data), data.shape[0], data.shape[1], 0, fptr(unc), C.byref(p), C.byref(opt), C.byref(res.c)))
     return res.finish()
+
+
+def checkpoint_info(path):
+    """What a checkpoint file holds (cgb_checkpoint_info_read): dict of the archived parameters, the phase and
+    iteration a resumed run starts with, atom counts.  Host only."""
+    info = CgbCheckpointInfo()
+    info.struct_size = C.sizeof(CgbCheckpointInfo)
+    check(lib().cgb_checkpoint_info_read(_path(path), C.byref(info)))
+    return {name: getattr(info, name) for name, _ in CgbCheckpointInfo._fields_ if name != "struct_size"}
+
+
+def checkpoint_rewrite(in_path, out_path):
+    """Parse a checkpoint completely and write it back through the library's own writer (byte-identical for a file the
+    reference wrote).  Host only."""
+    check(lib().cgb_checkpoint_rewrite(_path(in_path), _path(out_path)))
 
 
 def read_matrix_file(path):
@@ -214,8 +250,14 @@ def CoGAPS(data, params=None, nPatterns=None, nThreads=1, messages=True, outputF
             raise ValueError("negative values in uncertainty matrix")
         if params.sparseOptimization:
             raise ValueError("must use default uncertainty when enabling sparseOptimization")
-    if checkpointInFile is not None or checkpointInterval:
-        raise ValueError("checkpoints not supported in this build")  # R/HelperFunctions.R:225-226
+    checkpointing = checkpointInFile is not None or bool(checkpointInterval)
+    if checkpointing and params.distributed is not None:
+        raise ValueError("checkpoints not supported for distributed cogaps")      # R/HelperFunctions.R:221-222
+    if checkpointing and params.subsetDim:
+        checkpointInterval = 0                    # createCheckpoint skips subset runs (GapsRunner.cpp:232)
+    if checkpointing and not asynchronousUpdates:
+        raise ValueError("checkpoints need asynchronousUpdates=True: the reference's sequential sampler cannot be "
+                         "resumed either (SingleThreadedGibbsSampler.h:260-273)")
     if params.distributed is not None:
         from .distributed import distributedCogaps
         # the reference forces the sequential sampler here (R/DistributedCogaps.R:28-29); we follow the caller
@@ -240,7 +282,11 @@ def CoGAPS(data, params=None, nPatterns=None, nThreads=1, messages=True, outputF
         kw["subsetIndices"] = np.asarray(params.subsetIndices, dtype=np.uint32)
     if params.fixedPatterns is not None:
         kw["fixedPatterns"] = np.asarray(params.fixedPatterns, dtype=np.float32)
-    res = gaps_run(data, uncertainty=uncertainty, snapshots=bool(nSnapshots), **kw)
+    if checkpointInFile is not None:
+        # the run continues with the archived nPatterns; the result arrays must be sized for it
+        kw["nPatterns"] = int(checkpoint_info(checkpointInFile)["nPatterns"])
+    res = gaps_run(data, uncertainty=uncertainty, snapshots=bool(nSnapshots), checkpointInterval=int(checkpointInterval or 0),
+                   checkpointOutFile=checkpointOutFile, checkpointInFile=checkpointInFile, **kw)
     extras = dict(nBatchesA=res.nBatchesA, nBatchesP=res.nBatchesP, secondsUpdateA=res.secondsUpdateA,
                   secondsUpdateP=res.secondsUpdateP, algorithmicBytes=res.algorithmicBytes)
     return CogapsResult(res, params, extras)

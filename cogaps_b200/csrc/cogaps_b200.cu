@@ -2163,6 +2163,271 @@ extern "C" uint64_t cgb_debug_fastdiv(uint64_t divisor, uint64_t x)
 extern "C" float cgb_debug_host_logf(float x) { return portable_logf(x); }
 
 // ------------------------------------------------------------------------------------------------
+// Checkpoints: device-resident state <-> the images of checkpoint.h (Archive << / >> of the Sampler concept,
+// AsynchronousGibbsSampler.h:221-233; GapsStatistics.cpp:164-176)
+// ------------------------------------------------------------------------------------------------
+static const char *kSequentialCheckpointMsg =
+    "checkpoints need the asynchronous sampler: the reference's SingleThreadedGibbsSampler does not archive its rng "
+    "and cannot read its own archive (SingleThreadedGibbsSampler.h:260-273)";
+
+// [k][ld] on the device -> [k][rows] on the host
+static int downloadPatternMajor(const float *dev, uint32_t rows, uint32_t k, uint32_t ld, std::vector<float> &out)
+{
+    std::vector<float> host(static_cast<size_t>(k) * ld);
+    CGB_CUDA(cudaMemcpy(host.data(), dev, host.size() * sizeof(float), cudaMemcpyDeviceToHost));
+    out.resize(static_cast<size_t>(k) * rows);
+    for (uint32_t c = 0; c < k; ++c) { std::memcpy(out.data() + static_cast<size_t>(c) * rows, host.data() + static_cast<size_t>(c) * ld, sizeof(float) * rows); }
+    return CGB_OK;
+}
+
+// [k][rows] on the host -> [k][ld] on the device, padding zeroed
+static int uploadPatternMajor(float *dev, uint32_t rows, uint32_t k, uint32_t ld, const std::vector<float> &in)
+{
+    std::vector<float> host(static_cast<size_t>(k) * ld, 0.f);
+    for (uint32_t c = 0; c < k; ++c) { std::memcpy(host.data() + static_cast<size_t>(c) * ld, in.data() + static_cast<size_t>(c) * rows, sizeof(float) * rows); }
+    CGB_CUDA(cudaMemcpy(dev, host.data(), host.size() * sizeof(float), cudaMemcpyHostToDevice));
+    return CGB_OK;
+}
+
+static int samplerToImage(const cgb_sampler *s, SamplerImage &img)
+{
+    if (s->sequential) { return fail(CGB_EUNSUPPORTED, kSequentialCheckpointMsg); }
+    CGB_CHECK(!s->persistentRunning, "checkpoint: called in the middle of an update");
+    CGB_CUDA(cudaSetDevice(s->device));
+    CGB_CUDA(cudaStreamSynchronize(s->stream));
+    img.sparse = s->sparse;
+    img.nRows = s->nRows;
+    img.k = s->k;
+    CGB_TRY(downloadPatternMajor(s->dM, s->nRows, s->k, s->ldM, img.cols));
+    img.rows.clear();
+    img.beta = 0.f;
+    if (s->sparse)
+    {
+        std::vector<float> rows(static_cast<size_t>(s->nRows) * s->ldR);
+        CGB_CUDA(cudaMemcpy(rows.data(), s->dMrows, rows.size() * sizeof(float), cudaMemcpyDeviceToHost));
+        img.rows.resize(static_cast<size_t>(s->nRows) * s->k);
+        for (uint32_t r = 0; r < s->nRows; ++r) { std::memcpy(img.rows.data() + static_cast<size_t>(r) * s->k, rows.data() + static_cast<size_t>(r) * s->ldR, sizeof(float) * s->k); }
+        img.beta = 100.f; // SparseNormalModel.h:77
+    }
+    img.domainLength = s->domain.domainLength();
+    const size_t n = static_cast<size_t>(s->domain.size());
+    img.pos.resize(n);
+    img.mass.resize(n);
+    for (size_t i = 0; i < n; ++i)
+    {
+        const Atom &a = s->domain.atom(s->domain.atIndex(static_cast<uint32_t>(i)));
+        img.pos[i] = a.pos;
+        img.mass[i] = a.mass;
+    }
+    s->queue.save(img.queue);
+    return CGB_OK;
+}
+
+static int setAtoms(cgb_sampler *s, const uint64_t *pos, const float *mass, uint64_t n)
+{
+    const uint64_t nBins = static_cast<uint64_t>(s->nRows) * s->k;
+    CGB_CHECK(n <= nBins, "checkpoint: more atoms than the domain can ever hold is not a state this sampler produced");
+    s->domain.init(nBins);
+    for (uint64_t i = 0; i < n; ++i)
+    {
+        if (pos[i] > s->domain.domainLength() || s->domain.occupied(pos[i]))
+        {
+            s->domain.init(nBins);
+            return fail(CGB_EINVAL, "checkpoint: atom position outside the domain or used twice");
+        }
+        s->domain.insert(pos[i], mass[i]);
+    }
+    return CGB_OK;
+}
+
+static int imageToSampler(cgb_sampler *s, const SamplerImage &img)
+{
+    if (s->sequential) { return fail(CGB_EUNSUPPORTED, kSequentialCheckpointMsg); }
+    CGB_CHECK(!s->persistentRunning, "checkpoint: called in the middle of an update");
+    CGB_CHECK(img.sparse == s->sparse, "checkpoint: made with the other data model (useSparseOptimization differs)");
+    CGB_CHECK(img.nRows == s->nRows && img.k == s->k, "checkpoint: factor matrix shape differs from this sampler's");
+    CGB_CHECK(img.domainLength == s->domain.domainLength(), "checkpoint: atomic domain length differs from this sampler's");
+    CGB_CHECK(img.pos.size() == img.mass.size(), "checkpoint: atom arrays differ in length");
+    QueueState probe;
+    s->queue.save(probe);
+    CGB_CHECK(probe.binLength == img.queue.binLength && probe.numCols == img.queue.numCols && probe.numBins == img.queue.numBins
+              && probe.domainLength == img.queue.domainLength, "checkpoint: proposal queue geometry differs from this sampler's");
+    CGB_CUDA(cudaSetDevice(s->device));
+    CGB_CUDA(cudaStreamSynchronize(s->stream));
+    CGB_TRY(uploadPatternMajor(s->dM, s->nRows, s->k, s->ldM, img.cols));
+    if (s->sparse)
+    {
+        CGB_CHECK(img.rows.size() == static_cast<size_t>(s->nRows) * s->k, "checkpoint: row copy of the factor matrix missing");
+        std::vector<float> rows(static_cast<size_t>(s->nRows) * s->ldR, 0.f);
+        for (uint32_t r = 0; r < s->nRows; ++r) { std::memcpy(rows.data() + static_cast<size_t>(r) * s->ldR, img.rows.data() + static_cast<size_t>(r) * s->k, sizeof(float) * s->k); }
+        CGB_CUDA(cudaMemcpy(s->dMrows, rows.data(), rows.size() * sizeof(float), cudaMemcpyHostToDevice));
+    }
+    CGB_CUDA(cudaStreamSynchronize(cudaStreamLegacy)); // the kernels run on non-blocking streams (see samplerCreateImpl)
+    CGB_TRY(refreshColNonzero(s));
+    CGB_TRY(setAtoms(s, img.pos.data(), img.mass.data(), img.pos.size()));
+    if (!s->queue.restore(img.queue)) { return fail(CGB_EINTERNAL, "checkpoint: queue state rejected after it was checked"); }
+    return CGB_OK;
+}
+
+static int statsToImage(const cgb_stats *st, StatsImage &img)
+{
+    // every statistics update ends with a synchronise of the stream it ran on (statsUpdate), nothing is in flight
+    CGB_CUDA(cudaSetDevice(st->device));
+    img.nGenes = st->nGenes;
+    img.nSamples = st->nSamples;
+    img.k = st->k;
+    CGB_TRY(downloadPatternMajor(st->dAmean, st->nGenes, st->k, st->ldA, img.aMean));
+    CGB_TRY(downloadPatternMajor(st->dAsq, st->nGenes, st->k, st->ldA, img.aSq));
+    CGB_TRY(downloadPatternMajor(st->dPmean, st->nSamples, st->k, st->ldP, img.pMean));
+    CGB_TRY(downloadPatternMajor(st->dPsq, st->nSamples, st->k, st->ldP, img.pSq));
+    img.statUpdates = st->statUpdates;
+    img.numPatterns = st->k;
+    return CGB_OK;
+}
+
+static int imageToStats(cgb_stats *st, const StatsImage &img)
+{
+    CGB_CHECK(img.nGenes == st->nGenes && img.nSamples == st->nSamples && img.k == st->k && img.numPatterns == st->k,
+              "checkpoint: statistics shape differs from this run's");
+    CGB_CUDA(cudaSetDevice(st->device));
+    CGB_TRY(uploadPatternMajor(st->dAmean, st->nGenes, st->k, st->ldA, img.aMean));
+    CGB_TRY(uploadPatternMajor(st->dAsq, st->nGenes, st->k, st->ldA, img.aSq));
+    CGB_TRY(uploadPatternMajor(st->dPmean, st->nSamples, st->k, st->ldP, img.pMean));
+    CGB_TRY(uploadPatternMajor(st->dPsq, st->nSamples, st->k, st->ldP, img.pSq));
+    CGB_CUDA(cudaStreamSynchronize(cudaStreamLegacy));
+    st->statUpdates = img.statUpdates;
+    return CGB_OK;
+}
+
+static int copyOut(const std::vector<uint8_t> &bytes, void *buf, uint64_t capacity, uint64_t *size, const char *who)
+{
+    *size = bytes.size();
+    if (buf != nullptr)
+    {
+        if (capacity < bytes.size()) { return fail(CGB_EINVAL, std::string(who) + ": buffer too small"); }
+        std::memcpy(buf, bytes.data(), bytes.size());
+    }
+    return CGB_OK;
+}
+
+extern "C" int cgb_sampler_serialize(const cgb_sampler *s, void *buf, uint64_t capacity, uint64_t *size)
+{
+    CGB_CHECK(s && size, "cgb_sampler_serialize: NULL argument");
+    SamplerImage img;
+    CGB_TRY(samplerToImage(s, img));
+    ByteWriter w;
+    putSampler(w, img);
+    return copyOut(w.bytes(), buf, capacity, size, "cgb_sampler_serialize");
+}
+
+extern "C" int cgb_sampler_deserialize(cgb_sampler *s, const void *buf, uint64_t size)
+{
+    CGB_CHECK(s && buf, "cgb_sampler_deserialize: NULL argument");
+    SamplerImage img;
+    std::string err;
+    ByteReader r(static_cast<const uint8_t*>(buf), static_cast<size_t>(size));
+    if (!getSampler(r, s->sparse, img, err)) { return fail(CGB_EINVAL, "cgb_sampler_deserialize: " + err); }
+    CGB_CHECK(r.remaining() == 0, "cgb_sampler_deserialize: trailing bytes");
+    return imageToSampler(s, img);
+}
+
+extern "C" int cgb_sampler_set_atoms(cgb_sampler *s, const uint64_t *pos, const float *mass, uint64_t n)
+{
+    CGB_CHECK(s && (n == 0 || (pos && mass)), "cgb_sampler_set_atoms: NULL argument");
+    CGB_CHECK(!s->persistentRunning, "cgb_sampler_set_atoms: called in the middle of an update");
+    return setAtoms(s, pos, mass, n);
+}
+
+extern "C" int cgb_stats_serialize(const cgb_stats *st, void *buf, uint64_t capacity, uint64_t *size)
+{
+    CGB_CHECK(st && size, "cgb_stats_serialize: NULL argument");
+    StatsImage img;
+    CGB_TRY(statsToImage(st, img));
+    ByteWriter w;
+    putStats(w, img);
+    return copyOut(w.bytes(), buf, capacity, size, "cgb_stats_serialize");
+}
+
+extern "C" int cgb_stats_deserialize(cgb_stats *st, const void *buf, uint64_t size)
+{
+    CGB_CHECK(st && buf, "cgb_stats_deserialize: NULL argument");
+    StatsImage img;
+    std::string err;
+    ByteReader r(static_cast<const uint8_t*>(buf), static_cast<size_t>(size));
+    if (!getStats(r, img, err)) { return fail(CGB_EINVAL, "cgb_stats_deserialize: " + err); }
+    CGB_CHECK(r.remaining() == 0, "cgb_stats_deserialize: trailing bytes");
+    return imageToStats(st, img);
+}
+
+extern "C" int cgb_randstate_get_state(const cgb_randstate *rs, uint64_t state[2])
+{
+    CGB_CHECK(rs && state, "cgb_randstate_get_state: NULL argument");
+    rs->seeder.getState(state);
+    return CGB_OK;
+}
+
+extern "C" int cgb_randstate_set_state(cgb_randstate *rs, const uint64_t state[2])
+{
+    CGB_CHECK(rs && state, "cgb_randstate_set_state: NULL argument");
+    rs->seeder.setState(state);
+    return CGB_OK;
+}
+
+extern "C" int cgb_rng_get_state(const cgb_rng *r, uint64_t *state)
+{
+    CGB_CHECK(r && state, "cgb_rng_get_state: NULL argument");
+    *state = r->rng.state;
+    return CGB_OK;
+}
+
+extern "C" int cgb_rng_set_state(cgb_rng *r, uint64_t state)
+{
+    CGB_CHECK(r != nullptr, "cgb_rng_set_state: NULL argument");
+    r->rng.state = state;
+    return CGB_OK;
+}
+
+extern "C" int cgb_checkpoint_info_read(const char *path, cgb_checkpoint_info *out)
+{
+    CGB_CHECK(path && out, "cgb_checkpoint_info_read: NULL argument");
+    CGB_CHECK(out->struct_size == sizeof(cgb_checkpoint_info), "cgb_checkpoint_info_read: cgb_checkpoint_info ABI mismatch");
+    std::vector<uint8_t> raw;
+    std::string err;
+    if (!readWholeFile(path, raw, err)) { return fail(CGB_EINVAL, "cgb_checkpoint_info_read: " + err); }
+    CheckpointImage c;
+    ByteReader r(raw.data(), raw.size());
+    if (!getCheckpoint(r, c, err)) { return fail(CGB_EINVAL, std::string("cgb_checkpoint_info_read: ") + path + ": " + err); }
+    out->seed = c.params.seed;
+    out->nGenes = c.params.nGenes;
+    out->nSamples = c.params.nSamples;
+    out->nPatterns = c.params.nPatterns;
+    out->nIterations = c.params.nIterations;
+    out->alphaA = c.params.alphaA;
+    out->alphaP = c.params.alphaP;
+    out->maxGibbsMassA = c.params.maxGibbsMassA;
+    out->maxGibbsMassP = c.params.maxGibbsMassP;
+    out->useSparseOptimization = c.params.useSparseOptimization ? 1 : 0;
+    out->checkpointInterval = c.params.checkpointInterval;
+    out->phase = c.phase;
+    out->iter = c.iter;
+    out->nAtomsA = c.A.pos.size();
+    out->nAtomsP = c.P.pos.size();
+    out->statUpdates = c.stats.statUpdates;
+    out->fileBytes = raw.size();
+    return CGB_OK;
+}
+
+extern "C" int cgb_checkpoint_rewrite(const char *inPath, const char *outPath)
+{
+    CGB_CHECK(inPath && outPath, "cgb_checkpoint_rewrite: NULL argument");
+    CheckpointImage c;
+    std::string err;
+    if (!readCheckpointFile(inPath, c, err)) { return fail(CGB_EINVAL, std::string("cgb_checkpoint_rewrite: ") + inPath + ": " + err); }
+    if (!writeCheckpointFile(outPath, c, err)) { return fail(CGB_EINVAL, "cgb_checkpoint_rewrite: " + err); }
+    return CGB_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
 // gaps::run — runCoGAPSAlgorithm / runOnePhase / updateSampler / displayStatus
 // (src/GapsRunner.cpp:161-222, 272-327, 381-503)
 // ------------------------------------------------------------------------------------------------
@@ -2193,12 +2458,74 @@ extern "C" int cgb_run_set_tables(const float *erf, const float *erfinv, const f
     return CGB_OK;
 }
 
+// createCheckpoint (GapsRunner.cpp:226-256): archive the run, then rebuild AP from the factors so that the chain
+// that carries on is the one a resumed run will follow
+static int createCheckpoint(const cgb_params *p, uint32_t nGenes, uint32_t nSamples, uint32_t interval, const char *path,
+                            RunGuard &g, int phase, uint32_t iter)
+{
+    CheckpointImage c;
+    c.params.seed = p->seed;
+    c.params.nGenes = nGenes;
+    c.params.nSamples = nSamples;
+    c.params.nPatterns = p->nPatterns;
+    c.params.nIterations = p->nIterations;
+    c.params.alphaA = p->alphaA;
+    c.params.alphaP = p->alphaP;
+    c.params.maxGibbsMassA = p->maxGibbsMassA;
+    c.params.maxGibbsMassP = p->maxGibbsMassP;
+    c.params.useSparseOptimization = p->useSparseOptimization != 0;
+    c.params.checkpointInterval = interval;
+    g.rs->seeder.getState(c.seeder);
+    CGB_TRY(samplerToImage(g.A, c.A));
+    CGB_TRY(samplerToImage(g.P, c.P));
+    CGB_TRY(statsToImage(g.st, c.stats));
+    c.phase = phase;
+    c.iter = iter;
+    c.rng = g.rng->rng.state;
+    std::string err;
+    if (!writeCheckpointFile(path, c, err)) { return fail(CGB_EINVAL, "checkpoint: " + err); }
+    CGB_TRY(cgb_sampler_extra_initialization(g.A));
+    CGB_TRY(cgb_sampler_extra_initialization(g.P));
+    return CGB_OK;
+}
+
 extern "C" int cgb_run(const float *data, uint32_t nrow, uint32_t ncol, int32_t colmajor,
                        const float *uncertainty, const cgb_params *p, cgb_result *r)
 {
-    CGB_CHECK(data && p && r, "cgb_run: NULL argument");
-    CGB_CHECK(p->struct_size == sizeof(cgb_params), "cgb_run: cgb_params ABI mismatch");
+    return cgb_run_ex(data, nrow, ncol, colmajor, uncertainty, p, nullptr, r);
+}
+
+extern "C" int cgb_run_ex(const float *data, uint32_t nrow, uint32_t ncol, int32_t colmajor, const float *uncertainty,
+                          const cgb_params *p0, const cgb_run_options *opt, cgb_result *r)
+{
+    CGB_CHECK(data && p0 && r, "cgb_run: NULL argument");
+    CGB_CHECK(p0->struct_size == sizeof(cgb_params), "cgb_run: cgb_params ABI mismatch");
     CGB_CHECK(r->struct_size == sizeof(cgb_result), "cgb_run: cgb_result ABI mismatch");
+    CGB_CHECK(opt == nullptr || opt->struct_size == sizeof(cgb_run_options), "cgb_run_ex: cgb_run_options ABI mismatch");
+    cgb_params pv = *p0; // a checkpoint overwrites some of the caller's parameters (run_helper, GapsRunner.cpp:99-105)
+    const cgb_params *p = &pv;
+    uint32_t ckInterval = opt ? opt->checkpointInterval : 0;
+    const char *ckIn = (opt && opt->checkpointInFile && opt->checkpointInFile[0]) ? opt->checkpointInFile : nullptr;
+    const char *ckOut = (opt && opt->checkpointOutFile && opt->checkpointOutFile[0]) ? opt->checkpointOutFile : "gaps_checkpoint.out";
+    uint64_t ckSeeder[2] = {0, 0};
+    if (ckIn)
+    {
+        ParamsImage pi;
+        std::string err;
+        if (!readCheckpointHeader(ckIn, pi, ckSeeder, err)) { return fail(CGB_EINVAL, std::string("cgb_run_ex: ") + ckIn + ": " + err); }
+        // the caller sized its result arrays from its own nPatterns; the reference would silently switch to the file's
+        CGB_CHECK(pi.nPatterns == p0->nPatterns, "cgb_run_ex: nPatterns differs from the checkpoint's (cgb_checkpoint_info_read tells what it holds)");
+        pv.seed = pi.seed;
+        pv.nPatterns = pi.nPatterns;
+        pv.nIterations = pi.nIterations;
+        pv.alphaA = pi.alphaA;
+        pv.alphaP = pi.alphaP;
+        pv.maxGibbsMassA = pi.maxGibbsMassA;
+        pv.maxGibbsMassP = pi.maxGibbsMassP;
+        pv.useSparseOptimization = pi.useSparseOptimization ? 1 : 0;
+        ckInterval = pi.checkpointInterval;
+    }
+    if ((ckInterval > 0 || ckIn) && !p->asynchronousUpdates) { return fail(CGB_EUNSUPPORTED, kSequentialCheckpointMsg); }
     const int fixed = p->whichMatrixFixed ? p->whichMatrixFixed : 'N';
     CGB_CHECK(fixed == 'N' || fixed == 'A' || fixed == 'P', "cgb_run: whichMatrixFixed must be 'N', 'A' or 'P'");
     const bool useFixed = p->fixedPatterns != nullptr && fixed != 'N';
@@ -2210,7 +2537,8 @@ extern "C" int cgb_run(const float *data, uint32_t nrow, uint32_t ncol, int32_t 
 
     RunGuard g;
     const double tEnter = nowSeconds();
-    CGB_TRY(cgb_randstate_create(p->seed, &g.rs));
+    CGB_TRY(cgb_randstate_create(p0->seed, &g.rs)); // the caller builds GapsRandomState from ITS seed (Cogaps.cpp:141-142)
+    if (ckIn) { g.rs->seeder.setState(ckSeeder); }
     if (g_tableOverride[0]) { CGB_TRY(cgb_randstate_set_tables(g.rs, g_tableOverride[0], g_tableOverride[1], g_tableOverride[2])); }
     // GapsRunner.cpp:402-406.  The two orientations are prepared concurrently (each is a pass over the whole
     // matrix on the host: orientation, the fp32 running sum behind lambda, upload); the generators are then
@@ -2250,6 +2578,24 @@ extern "C" int cgb_run(const float *data, uint32_t nrow, uint32_t ncol, int32_t 
     }
     CGB_TRY(cgb_stats_create(nGenes, nSamples, p->nPatterns, &g.st));
     CGB_TRY(cgb_rng_create(g.rs, &g.rng)); // GapsRunner.cpp:437
+    int startPhase = CGB_PHASE_EQUILIBRATION;
+    uint32_t startIter = 0;
+    if (ckIn)
+    {
+        // processCheckpoint, GapsRunner.cpp:258-270
+        CheckpointImage c;
+        std::string err;
+        if (!readCheckpointFile(ckIn, c, err)) { return fail(CGB_EINVAL, std::string("cgb_run_ex: ") + ckIn + ": " + err); }
+        CGB_CHECK(c.params.nGenes == nGenes && c.params.nSamples == nSamples, "cgb_run_ex: the checkpoint was made from data of another shape");
+        CGB_CHECK(c.phase == CGB_PHASE_EQUILIBRATION || c.phase == CGB_PHASE_SAMPLING, "cgb_run_ex: checkpoint holds an unknown phase");
+        g.rs->seeder.setState(c.seeder);
+        CGB_TRY(imageToSampler(g.A, c.A));
+        CGB_TRY(imageToSampler(g.P, c.P));
+        CGB_TRY(imageToStats(g.st, c.stats));
+        startPhase = c.phase;
+        startIter = c.iter;
+        g.rng->rng.state = c.rng;
+    }
 
     CGB_TRY(cgb_sampler_sync(g.A, g.P));
     CGB_TRY(cgb_sampler_sync(g.P, g.A));
@@ -2261,11 +2607,17 @@ extern "C" int cgb_run(const float *data, uint32_t nrow, uint32_t ncol, int32_t 
     uint64_t totalUpdates = 0;
     uint32_t nHist = 0, nSnapEq = 0, nSnapSamp = 0;
     double secondsA = 0.0, secondsP = 0.0;
-    for (int phase = CGB_PHASE_EQUILIBRATION; phase <= CGB_PHASE_SAMPLING; ++phase)
+    for (int phase = startPhase; phase <= CGB_PHASE_SAMPLING; ++phase)
     {
         if (p->printMessages) { std::printf(phase == CGB_PHASE_EQUILIBRATION ? "-- Equilibration Phase --\n" : "-- Sampling Phase --\n"); }
-        for (uint32_t iter = 0; iter < p->nIterations; ++iter)
+        for (uint32_t iter = (phase == startPhase) ? startIter : 0; iter < p->nIterations; ++iter)
         {
+            // gaps_check_interrupt + createCheckpoint, GapsRunner.cpp:280-282
+            if (opt && opt->interrupt && opt->interrupt(opt->interruptUser) != 0) { return fail(CGB_EINTERRUPTED, "cgb_run_ex: interrupted by the caller"); }
+            if (ckInterval > 0 && ((iter + 1) % ckInterval) == 0 && p->nSubsetIndices == 0)
+            {
+                CGB_TRY(createCheckpoint(p, nGenes, nSamples, ckInterval, ckOut, g, phase, iter));
+            }
             if (phase == CGB_PHASE_EQUILIBRATION)
             {
                 const float temp = static_cast<float>(2 * iter) / static_cast<float>(p->nIterations);

@@ -44,6 +44,9 @@ public:
         mState[0] = mPrev[0];
         mState[1] = mPrev[1];
     }
+    // what operator<< archives (math/Random.cpp:250-260): the current state, not the roll-back copy
+    void getState(uint64_t out[2]) const { out[0] = mState[0]; out[1] = mState[1]; }
+    void setState(const uint64_t in[2]) { mState[0] = in[0]; mState[1] = in[1]; }
 private:
     static uint64_t rotl(uint64_t x, int k) { return (x << k) | (x >> (64 - k)); }
     uint64_t mState[2];

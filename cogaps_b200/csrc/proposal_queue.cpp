@@ -32,6 +32,39 @@ void ProposalQueue::init(uint64_t nElements, uint64_t nPatterns, cgb_randstate *
     mUseCachedRng = false;
 }
 
+void ProposalQueue::save(QueueState &out) const
+{
+    out.rng = mRng.state;
+    out.minAtoms = mMinAtoms;
+    out.maxAtoms = mMaxAtoms;
+    out.binLength = mBinLength;
+    out.numCols = mNumCols;
+    out.alpha = mAlpha;
+    out.domainLength = mDomainLength;
+    out.numBins = mNumBins;
+    out.lambda = mLambda;
+    out.useCachedRng = mUseCachedRng;
+    out.u1 = mU1;
+    out.u2 = mU2;
+}
+
+bool ProposalQueue::restore(const QueueState &in)
+{
+    if (in.binLength != mBinLength || in.numCols != mNumCols || in.numBins != mNumBins || in.domainLength != mDomainLength)
+    {
+        return false;
+    }
+    mRng.state = in.rng;
+    mMinAtoms = in.minAtoms;
+    mMaxAtoms = in.maxAtoms;
+    mAlpha = in.alpha;
+    mLambda = in.lambda;
+    mUseCachedRng = in.useCachedRng;
+    mU1 = in.u1;
+    mU2 = in.u2;
+    return true;
+}
+
 void ProposalQueue::populate(AtomicDomain &domain, unsigned limit, SinkFn sink, void *sinkCtx)
 {
     bool success = true;

@@ -8,6 +8,7 @@
 #define CGB_SAMPLER_H
 
 #include "atomic_domain.h"
+#include "checkpoint.h"
 #include "device_types.h"
 #include "host_rng.h"
 
@@ -83,6 +84,10 @@ public:
     void rejectBirth() { --mMaxAtoms; }
     uint64_t minAtoms() const { return mMinAtoms; }
     uint64_t maxAtoms() const { return mMaxAtoms; }
+    // the members operator<< archives (ProposalQueue.cpp:285-299); restore() refuses a state whose bin geometry
+    // is not this queue's (the file was made from a matrix of another shape)
+    void save(QueueState &out) const;
+    bool restore(const QueueState &in);
 
 private:
     float deathProb(double nAtoms) const;                   // :123-127

@@ -37,6 +37,16 @@ class GapsRandomState(object):
         check(lib().cgb_randstate_next_seed(self._h, C.byref(out)))
         return out.value
 
+    def getState(self):
+        """the xoroshiro128+ state `Archive << randState` writes (math/Random.cpp:250-254,347-351)"""
+        st = (C.c_uint64 * 2)()
+        check(lib().cgb_randstate_get_state(self._h, st))
+        return int(st[0]), int(st[1])
+
+    def setState(self, state):
+        st = (C.c_uint64 * 2)(int(state[0]), int(state[1]))
+        check(lib().cgb_randstate_set_state(self._h, st))
+
     def __del__(self):
         if getattr(self, "_h", None):
             lib().cgb_randstate_destroy(self._h)
@@ -50,6 +60,15 @@ class GapsRng(object):
         self._rs = randState
         self._h = C.c_void_p()
         check(lib().cgb_rng_create(randState._h, C.byref(self._h)))
+
+    def getState(self):
+        """the PCG state `Archive << rng` writes (math/Random.cpp:202-206)"""
+        out = C.c_uint64()
+        check(lib().cgb_rng_get_state(self._h, C.byref(out)))
+        return out.value
+
+    def setState(self, state):
+        check(lib().cgb_rng_set_state(self._h, C.c_uint64(int(state))))
 
     def uniform32(self, a=None, b=None):
         out = C.c_uint32()
@@ -175,6 +194,26 @@ class GibbsSampler(object):
             check(lib().cgb_sampler_get_atoms(self._h, pos.ctypes.data_as(c_u64_p), fptr(mass), n.value, C.byref(n)))
         return pos, mass
 
+    def setAtoms(self, pos, mass):
+        """Replace the atomic domain; the order given becomes the pick order (ConcurrentAtomicDomain.cpp:144-155)."""
+        pos = np.ascontiguousarray(pos, dtype=np.uint64)
+        mass = _f32(mass)
+        assert pos.shape == mass.shape
+        check(lib().cgb_sampler_set_atoms(self._h, pos.ctypes.data_as(c_u64_p), fptr(mass), pos.size))
+
+    def serialize(self):
+        """`Archive << sampler` (AsynchronousGibbsSampler.h:221-226): bytes in the reference's wire format."""
+        n = C.c_uint64()
+        check(lib().cgb_sampler_serialize(self._h, None, 0, C.byref(n)))
+        buf = (C.c_uint8 * n.value)()
+        check(lib().cgb_sampler_serialize(self._h, buf, n.value, C.byref(n)))
+        return bytes(buf)
+
+    def deserialize(self, raw):
+        """`Archive >> sampler` (:228-233); sync() / extraInitialization() are the caller's to repeat."""
+        buf = (C.c_uint8 * len(raw)).from_buffer_copy(raw)
+        check(lib().cgb_sampler_deserialize(self._h, buf, len(raw)))
+
     def apRow(self, row):
         out = np.zeros(self.rowLength, np.float32)
         check(lib().cgb_sampler_get_ap_row(self._h, row, fptr(out)))
@@ -270,6 +309,18 @@ class GapsStatistics(object):
         out = C.c_float()
         check(lib().cgb_stats_mean_chisq(self._h, P._h, C.byref(out)))
         return out.value
+
+    def serialize(self):
+        """`Archive << stats` (GapsStatistics.cpp:164-169)"""
+        n = C.c_uint64()
+        check(lib().cgb_stats_serialize(self._h, None, 0, C.byref(n)))
+        buf = (C.c_uint8 * n.value)()
+        check(lib().cgb_stats_serialize(self._h, buf, n.value, C.byref(n)))
+        return bytes(buf)
+
+    def deserialize(self, raw):
+        buf = (C.c_uint8 * len(raw)).from_buffer_copy(raw)
+        check(lib().cgb_stats_deserialize(self._h, buf, len(raw)))
 
     def deviceSums(self):
         a, a2, p, p2 = C.c_void_p(), C.c_void_p(), C.c_void_p(), C.c_void_p()

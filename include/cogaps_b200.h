@@ -309,6 +309,76 @@ int cgb_stats_device_sums(const cgb_stats *st, void **AmeanSum, void **AsqSum, v
                           void **PsqSum, uint64_t *ldA, uint64_t *ldP, uint32_t *nUpdates);
 
 /* ------------------------------------------------------------------------------------------
+ * Checkpoints and interrupts (GapsRunner.cpp:224-270,280; utils/Archive.h:16-87).
+ *
+ * The wire format is the reference's own: a file written here is byte-identical to the one the reference
+ * writes for the same state, and either side resumes from the other's.  Asynchronous sampler only — the
+ * reference's SingleThreadedGibbsSampler does not archive its rng stream and its operator>> writes instead of
+ * reading (SingleThreadedGibbsSampler.h:260-273), so there is nothing to be compatible with: asking for a
+ * checkpoint with asynchronousUpdates == 0 fails with CGB_EUNSUPPORTED.
+ * ---------------------------------------------------------------------------------------- */
+#define CGB_EINTERRUPTED -7   /* the interrupt callback asked to stop (Rcpp::checkUserInterrupt, utils/GlobalConfig.h:16-20) */
+
+typedef struct cgb_run_options
+{
+    uint32_t struct_size;          /* = sizeof(cgb_run_options) */
+    uint32_t checkpointInterval;   /* GapsParameters.h:46; 0 = never.  As in createCheckpoint (GapsRunner.cpp:226-256) a
+                                    * checkpoint is taken at the top of every iteration with (iter+1) % interval == 0, in
+                                    * both phases, never when subsetting; taking one rebuilds AP from the factors
+                                    * (extraInitialization), so the chain differs from a run without checkpoints exactly
+                                    * as the reference's does. */
+    const char *checkpointOutFile; /* :38; NULL or "" = "gaps_checkpoint.out" (:83) */
+    const char *checkpointInFile;  /* :37,56 (useCheckPoint); NULL or "" = start from scratch.  seed, nPatterns,
+                                    * nIterations, alpha*, maxGibbsMass*, useSparseOptimization and checkpointInterval
+                                    * are then taken from the file (run_helper, GapsRunner.cpp:99-105). */
+    int32_t (*interrupt)(void *user); /* polled once per iteration on the calling thread (GapsRunner.cpp:280);
+                                       * non-zero return stops the run with CGB_EINTERRUPTED.  NULL = never. */
+    void *interruptUser;
+} cgb_run_options;
+
+/* cgb_run with checkpoints / interrupt polling; options == NULL is exactly cgb_run. */
+int cgb_run_ex(const float *data, uint32_t nrow, uint32_t ncol, int32_t colmajor, const float *uncertainty,
+               const cgb_params *params, const cgb_run_options *options, cgb_result *result);
+
+/* `Archive << sampler` / `Archive >> sampler` of the Sampler concept (AsynchronousGibbsSampler.h:221-233): the bytes the
+ * reference streams for the factor matrix, the atomic domain (atoms in pick order) and the proposal queue.  Size the
+ * buffer with buf == NULL.  Deserialising replaces the factor matrix, the atoms and the queue state of a sampler of the
+ * same shape and model; call sync() / extraInitialization() afterwards, as runCoGAPSAlgorithm does (GapsRunner.cpp:444-447). */
+int cgb_sampler_serialize(const cgb_sampler *s, void *buf, uint64_t capacity, uint64_t *size);
+int cgb_sampler_deserialize(cgb_sampler *s, const void *buf, uint64_t size);
+/* Replace the atomic domain: atoms are inserted in the order given, which becomes the pick order
+ * (ConcurrentAtomicDomain.cpp:144-155).  The factor matrix is not touched (cgb_sampler_set_matrix). */
+int cgb_sampler_set_atoms(cgb_sampler *s, const uint64_t *pos, const float *mass, uint64_t n);
+/* `Archive << stats` / `>>` (GapsStatistics.cpp:164-176): the four running sums, statUpdates, nPatterns */
+int cgb_stats_serialize(const cgb_stats *st, void *buf, uint64_t capacity, uint64_t *size);
+int cgb_stats_deserialize(cgb_stats *st, const void *buf, uint64_t size);
+/* seeder state of a GapsRandomState (math/Random.cpp:347-357) */
+int cgb_randstate_get_state(const cgb_randstate *rs, uint64_t state[2]);
+int cgb_randstate_set_state(cgb_randstate *rs, const uint64_t state[2]);
+/* PCG state of a GapsRng (math/Random.cpp:202-212) */
+int cgb_rng_get_state(const cgb_rng *r, uint64_t *state);
+int cgb_rng_set_state(cgb_rng *r, uint64_t state);
+
+/* What a checkpoint file holds.  Host only, no device needed. */
+typedef struct cgb_checkpoint_info
+{
+    uint32_t struct_size;
+    uint32_t seed, nGenes, nSamples, nPatterns, nIterations;
+    float alphaA, alphaP, maxGibbsMassA, maxGibbsMassP;
+    int32_t useSparseOptimization;
+    uint32_t checkpointInterval;
+    int32_t phase;                 /* CGB_PHASE_EQUILIBRATION or CGB_PHASE_SAMPLING */
+    uint32_t iter;                 /* the iteration the resumed run starts with */
+    uint64_t nAtomsA, nAtomsP;
+    uint32_t statUpdates;
+    uint64_t fileBytes;
+} cgb_checkpoint_info;
+int cgb_checkpoint_info_read(const char *path, cgb_checkpoint_info *out);
+/* Parses inPath completely (every structural check a resume would make) and writes it back out through the library's
+ * own writer; the result is byte-identical for any file the reference wrote.  Host only. */
+int cgb_checkpoint_rewrite(const char *inPath, const char *outPath);
+
+/* ------------------------------------------------------------------------------------------
  * Test hooks (no reference counterpart)
  * ---------------------------------------------------------------------------------------- */
 /* lookup tables cgb_run hands to the GapsRandomState it creates (NULLs restore the built-ins) */

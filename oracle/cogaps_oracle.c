@@ -2251,6 +2251,7 @@ int cogaps_oracle_run_trace(const float *data, uint32_t nrow, uint32_t ncol, con
     rng_t rng;
     rng_init(&rng, rs);
     int rc = 0;
+    uint32_t nCheckpoints = 0;
     int startPhase = CGB_PHASE_EQUILIBRATION;
     uint32_t startIter = 0;
     if (ckIn)
@@ -2321,6 +2322,7 @@ int cogaps_oracle_run_trace(const float *data, uint32_t nrow, uint32_t ncol, con
                 remove(backup);
                 free(backup);
                 if (!written) { rc = -1; goto done; }
+                if (opt && opt->stopAfterCheckpoints > 0 && ++nCheckpoints == opt->stopAfterCheckpoints) { rc = -7; goto done; }
                 /* "running the extra initialization here allows for consistency with runs started from a checkpoint" */
                 model_extra_initialization(&A.model);
                 model_extra_initialization(&P.model);

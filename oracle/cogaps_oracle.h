@@ -43,6 +43,8 @@ typedef struct oracle_options
     uint32_t checkpointInterval;   /* 0 = never */
     const char *checkpointOutFile; /* NULL = "gaps_checkpoint.out" (GapsParameters.h:83) */
     const char *checkpointInFile;  /* non-NULL = resume (useCheckPoint) */
+    uint32_t stopAfterCheckpoints; /* tests: return -7 right after writing this many checkpoints (a user interrupt,
+                                    * GapsRunner.cpp:280, at a known place); 0 = run to the end */
 } oracle_options;
 
 /* one evaluated proposal, for lock-step comparison and host-logic replay tests */

@@ -164,6 +164,7 @@ class OracleOptions(C.Structure):
         ("checkpointInterval", C.c_uint32),
         ("checkpointOutFile", C.c_char_p),
         ("checkpointInFile", C.c_char_p),
+        ("stopAfterCheckpoints", C.c_uint32),
     ]
 
 
@@ -197,7 +198,7 @@ class OracleLib(object):
 
     @staticmethod
     def options(reduce="scalar", math="libm", orderA=None, orderP=None, tables=None, checkpointInterval=0,
-                checkpointOutFile=None, checkpointInFile=None):
+                checkpointOutFile=None, checkpointInFile=None, stopAfterCheckpoints=0):
         o = OracleOptions()
         o.reduceMode = {"scalar": REDUCE_SCALAR, "avx8": REDUCE_AVX8, "device": REDUCE_DEVICE}[reduce]
         o.mathMode = {"libm": MATH_LIBM, "portable": MATH_PORTABLE}[math]
@@ -213,6 +214,7 @@ class OracleLib(object):
         o.checkpointInterval = checkpointInterval
         o.checkpointOutFile = _path(checkpointOutFile)
         o.checkpointInFile = _path(checkpointInFile)
+        o.stopAfterCheckpoints = stopAfterCheckpoints
         o._keepalive = keep
         return o
 
@@ -232,6 +234,8 @@ class OracleLib(object):
         else:
             rc = self.lib.cogaps_oracle_run(fptr(data), C.c_uint32(data.shape[0]), C.c_uint32(data.shape[1]),
                                             fptr(unc), C.byref(p), C.byref(res.c), C.byref(opt))
+        if rc == -7 and opt.stopAfterCheckpoints:
+            return None     # stopped on request right after a checkpoint; the file is the product of the call
         if rc != 0:
             raise RuntimeError("cogaps_oracle_run failed: %d" % rc)
         out = res.finish()
