@@ -16,7 +16,7 @@ import numpy as np
 import pytest
 
 from tests.cases import load_data
-from tests.checkpoint_format import parse, parse_file
+from tests.checkpoint_format import parse_file
 from tests.golden.make_checkpoint_fixtures import CHECKPOINT_CASES, FIELDS
 
 GOLDEN = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
@@ -143,7 +143,6 @@ def test_sequential_sampler_has_no_checkpoints(oracle):
     """The reference's SingleThreadedGibbsSampler does not archive its rng and cannot read its own archive
     (SingleThreadedGibbsSampler.h:260-273); the oracle and the library refuse instead of inventing a format."""
     import cogaps_b200 as cg
-    from oracle.harness import OracleLib  # noqa: F401
     data = load_data("modsim")
     with pytest.raises(RuntimeError, match="-5"):
         oracle.run(data, options=oracle.options(checkpointInterval=10), seed=1, nPatterns=3, nIterations=20,
