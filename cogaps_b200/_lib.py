@@ -32,7 +32,7 @@ EXPORTS = [
     "cgb_debug_logf", "cgb_debug_host_logf", "cgb_debug_fastdiv", "cgb_run_file", "cgb_read_matrix_file",
     "cgb_run_ex", "cgb_sampler_serialize", "cgb_sampler_deserialize", "cgb_sampler_set_atoms", "cgb_stats_serialize",
     "cgb_stats_deserialize", "cgb_randstate_get_state", "cgb_randstate_set_state", "cgb_rng_get_state", "cgb_rng_set_state",
-    "cgb_checkpoint_info_read", "cgb_checkpoint_rewrite",
+    "cgb_checkpoint_info_read", "cgb_checkpoint_rewrite", "cgb_read_matrix_csr",
 ]
 
 _lib = None
@@ -137,6 +137,8 @@ def lib():
     L.cgb_rng_set_state.argtypes = [vp, C.c_uint64]
     L.cgb_checkpoint_info_read.argtypes = [C.c_char_p, C.POINTER(CgbCheckpointInfo)]
     L.cgb_checkpoint_rewrite.argtypes = [C.c_char_p, C.c_char_p]
+    L.cgb_read_matrix_csr.argtypes = [C.c_char_p, C.c_int32, c_u32_p, c_u32_p, c_u32_p, C.c_uint64, c_u32_p, c_float_p,
+                                      C.c_uint64, c_u64_p]
     _lib = L
     return L
 

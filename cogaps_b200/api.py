@@ -206,6 +206,22 @@ def read_matrix_file(path):
     return out
 
 
+def read_matrix_csr(path, by_rows=True):
+    """The compressed rows (or columns) of a Matrix-Market file as the sparse model's loader builds them
+    (cgb_read_matrix_csr): (nrow, ncol, ptr, idx, val).  Host only."""
+    from ._abi import c_u32_p
+    nrow, ncol, nnz = C.c_uint32(), C.c_uint32(), C.c_uint64()
+    raw = os.fspath(path).encode()
+    check(lib().cgb_read_matrix_csr(raw, int(bool(by_rows)), C.byref(nrow), C.byref(ncol), None, 0, None, None, 0, C.byref(nnz)))
+    major = nrow.value if by_rows else ncol.value
+    ptr = np.zeros(major + 1, np.uint32)
+    idx = np.zeros(max(nnz.value, 1), np.uint32)
+    val = np.zeros(max(nnz.value, 1), np.float32)
+    check(lib().cgb_read_matrix_csr(raw, int(bool(by_rows)), C.byref(nrow), C.byref(ncol), ptr.ctypes.data_as(c_u32_p), ptr.size,
+                                    idx.ctypes.data_as(c_u32_p), fptr(val), idx.size, C.byref(nnz)))
+    return nrow.value, ncol.value, ptr, idx[:nnz.value], val[:nnz.value]
+
+
 def gaps_run_file(path, uncertainty_path=None, snapshots=False, **kw):
     """gaps::run(const std::string &data, ...) (src/GapsRunner.h:19-24) through the C ABI."""
     nrow, ncol = C.c_uint32(), C.c_uint32()

@@ -379,12 +379,23 @@ struct TwinLink
     TwinLink() : state(0), sampler(nullptr) {}
 };
 
+// The data of ONE sampler already in compressed rows (sampler rows x L, ascending index, positive entries only):
+// what the Matrix-Market loader hands over instead of a dense matrix (sparse model, whole matrix only)
+struct CsrView
+{
+    uint32_t nRows, L;
+    const std::vector<uint32_t> *ptr, *idx;
+    const std::vector<float> *val;
+};
+
 static int samplerCreateImpl(const float *data, uint32_t nrow, uint32_t ncol, int32_t colmajor,
                              int32_t transpose, int32_t subsetRows, float alpha, float maxGibbsMass,
                              const cgb_params *params, cgb_randstate *rs, bool withGenerator, cgb_sampler **out,
-                             TwinLink *publish = nullptr, TwinLink *twin = nullptr)
+                             TwinLink *publish = nullptr, TwinLink *twin = nullptr, const CsrView *csr = nullptr)
 {
-    CGB_CHECK(data && params && rs && out, "cgb_sampler_create: NULL argument");
+    CGB_CHECK((data || csr) && params && rs && out, "cgb_sampler_create: NULL argument");
+    CGB_CHECK(csr == nullptr || (params->useSparseOptimization != 0 && params->nSubsetIndices == 0 && twin == nullptr && publish == nullptr),
+              "cgb_sampler_create: compressed-row input is for the sparse model on the whole matrix");
     CGB_CHECK(params->struct_size == sizeof(cgb_params), "cgb_sampler_create: cgb_params ABI mismatch");
     CGB_CHECK(params->nPatterns >= 1, "cgb_sampler_create: nPatterns must be >= 1");
     CGB_TRY(checkSubset(params, nrow, ncol));
@@ -431,7 +442,15 @@ static int samplerCreateImpl(const float *data, uint32_t nrow, uint32_t ncol, in
     const bool direct = wholeMatrix && !s->sparse && (straight || twin != nullptr);
     const float *meanBase;
     size_t meanStrideR, meanStrideL;
-    if (direct)
+    if (csr)
+    {
+        s->L = csr->L;
+        s->nRows = csr->nRows;
+        s->ld = roundUp(s->L, 32);
+        meanBase = nullptr;
+        meanStrideR = meanStrideL = 0;
+    }
+    else if (direct)
     {
         const uint32_t nGenes = transpose ? ncol : nrow, nSamples = transpose ? nrow : ncol;
         s->L = nGenes;
@@ -460,10 +479,19 @@ static int samplerCreateImpl(const float *data, uint32_t nrow, uint32_t ncol, in
     // order of the additions is the result, so this is a serial pass over the whole matrix; it runs on its own
     // thread beside the allocations and the upload below and is joined before anything needs lambda.
     struct MeanJob { float sum; unsigned nnz; } meanJob = {0.f, 0u};
-    std::thread meanThread([meanBase, meanStrideR, meanStrideL, &meanJob, s]()
+    std::thread meanThread([meanBase, meanStrideR, meanStrideL, &meanJob, s, csr]()
     {
         float sum = 0.f;
         unsigned nnz = 0;
+        if (csr)
+        {
+            // the same running sum: the elements that are not stored are zeros and add nothing
+            const std::vector<float> &v = *csr->val;
+            for (size_t i = 0; i < v.size(); ++i) { sum += v[i]; }
+            meanJob.sum = sum;
+            meanJob.nnz = static_cast<unsigned>(v.size());
+            return;
+        }
         for (uint32_t r = 0; r < s->nRows; ++r)
         {
             const float *row = meanBase + static_cast<size_t>(r) * meanStrideR;
@@ -490,10 +518,19 @@ static int samplerCreateImpl(const float *data, uint32_t nrow, uint32_t ncol, in
     });
     struct Joiner { std::thread &t; ~Joiner() { if (t.joinable()) { t.join(); } } } meanJoiner = {meanThread};
     chooseSegments(s);
-    std::vector<uint32_t> spPtr, spIdx;
-    std::vector<float> spVal;
-    if (s->sparse)
+    std::vector<uint32_t> spPtrOwn, spIdxOwn;
+    std::vector<float> spValOwn;
+    const std::vector<uint32_t> &spPtr = csr ? *csr->ptr : spPtrOwn, &spIdx = csr ? *csr->idx : spIdxOwn;
+    const std::vector<float> &spVal = csr ? *csr->val : spValOwn;
+    if (csr)
     {
+        s->nSeg = 1;
+        s->ldR = roundUp(s->k, 4);
+    }
+    else if (s->sparse)
+    {
+        std::vector<uint32_t> &spPtr = spPtrOwn, &spIdx = spIdxOwn;
+        std::vector<float> &spVal = spValOwn;
         // SparseMatrix (data_structures/SparseMatrix.cpp, SparseVector.cpp:20-35): the positive entries of every
         // sampler row, ascending index
         s->nSeg = 1;
@@ -565,7 +602,18 @@ static int samplerCreateImpl(const float *data, uint32_t nrow, uint32_t ncol, in
         }
         CGB_CUDA_BREAK(cudaEventCreate(&s->evStart));
         CGB_CUDA_BREAK(cudaEventCreate(&s->evStop));
-        if (!direct)
+        if (csr)
+        {
+            // the dense copy the chi-square kernels walk is rebuilt on the device from the rows just uploaded (pageable
+            // copies through the legacy stream: staged, not necessarily landed — wait before our own stream reads them)
+            CGB_CUDA_BREAK(cudaStreamSynchronize(cudaStreamLegacy));
+            CGB_CUDA_BREAK(cudaMemsetAsync(s->dD, 0, matBytes, s->stream));
+            csr_scatter_kernel<<<s->nRows, 256, 0, s->stream>>>(s->dSpRowPtr, s->dSpIdx, s->dSpVal, s->ld, s->dD);
+            ++g_kernelLaunches;
+            CGB_CUDA_BREAK(cudaGetLastError());
+            CGB_CUDA_BREAK(cudaStreamSynchronize(s->stream));
+        }
+        else if (!direct)
         {
             CGB_CUDA_BREAK(cudaMemcpy(s->dD, host.data(), matBytes, cudaMemcpyHostToDevice));
         }
@@ -2495,10 +2543,27 @@ extern "C" int cgb_run(const float *data, uint32_t nrow, uint32_t ncol, int32_t 
     return cgb_run_ex(data, nrow, ncol, colmajor, uncertainty, p, nullptr, r);
 }
 
+// both orientations of a Matrix-Market file in compressed rows (see cgb_run_file)
+struct CsrPair
+{
+    std::vector<uint32_t> rowPtr, rowIdx, colPtr, colIdx; // by file row / by file column
+    std::vector<float> rowVal, colVal;
+};
+
+static int runCore(const float *data, const CsrPair *csr, uint32_t nrow, uint32_t ncol, int32_t colmajor, const float *uncertainty,
+                   const cgb_params *p0, const cgb_run_options *opt, cgb_result *r);
+
 extern "C" int cgb_run_ex(const float *data, uint32_t nrow, uint32_t ncol, int32_t colmajor, const float *uncertainty,
                           const cgb_params *p0, const cgb_run_options *opt, cgb_result *r)
 {
-    CGB_CHECK(data && p0 && r, "cgb_run: NULL argument");
+    CGB_CHECK(data != nullptr, "cgb_run: NULL argument");
+    return runCore(data, nullptr, nrow, ncol, colmajor, uncertainty, p0, opt, r);
+}
+
+static int runCore(const float *data, const CsrPair *csr, uint32_t nrow, uint32_t ncol, int32_t colmajor, const float *uncertainty,
+                   const cgb_params *p0, const cgb_run_options *opt, cgb_result *r)
+{
+    CGB_CHECK((data || csr) && p0 && r, "cgb_run: NULL argument");
     CGB_CHECK(p0->struct_size == sizeof(cgb_params), "cgb_run: cgb_params ABI mismatch");
     CGB_CHECK(r->struct_size == sizeof(cgb_result), "cgb_run: cgb_result ABI mismatch");
     CGB_CHECK(opt == nullptr || opt->struct_size == sizeof(cgb_run_options), "cgb_run_ex: cgb_run_options ABI mismatch");
@@ -2552,14 +2617,25 @@ extern "C" int cgb_run_ex(const float *data, uint32_t nrow, uint32_t ncol, int32
         TwinLink link;
         TwinLink *pubA = (dense && straightA) ? &link : nullptr, *twinA = (dense && !straightA) ? &link : nullptr;
         TwinLink *pubP = (dense && !straightA) ? &link : nullptr, *twinP = (dense && straightA) ? &link : nullptr;
+        // compressed-row input: a sampler built with transpose == true has the file's rows as its rows
+        // (orientData: nRows = transpose ? nrow : ncol), the other one the file's columns
+        CsrView byRow = {nrow, ncol, nullptr, nullptr, nullptr}, byCol = {ncol, nrow, nullptr, nullptr, nullptr};
+        if (csr)
+        {
+            CGB_CHECK(p->useSparseOptimization && p->nSubsetIndices == 0 && !uncertainty, "cgb_run: compressed-row input needs the sparse model, the whole matrix and default uncertainty");
+            byRow.ptr = &csr->rowPtr; byRow.idx = &csr->rowIdx; byRow.val = &csr->rowVal;
+            byCol.ptr = &csr->colPtr; byCol.idx = &csr->colIdx; byCol.val = &csr->colVal;
+        }
+        const CsrView *csrP = csr ? (p->transposeData ? &byRow : &byCol) : nullptr;
+        const CsrView *csrA = csr ? (p->transposeData ? &byCol : &byRow) : nullptr;
         int rcP = CGB_OK;
         std::string errP;
         std::thread prepP([&]()
         {
-            rcP = samplerCreateImpl(data, nrow, ncol, colmajor, p->transposeData, p->subsetGenes, p->alphaP, p->maxGibbsMassP, p, g.rs, false, &g.P, pubP, twinP);
+            rcP = samplerCreateImpl(data, nrow, ncol, colmajor, p->transposeData, p->subsetGenes, p->alphaP, p->maxGibbsMassP, p, g.rs, false, &g.P, pubP, twinP, csrP);
             if (rcP != CGB_OK) { errP = g_lastError; }
         });
-        const int rcA = samplerCreateImpl(data, nrow, ncol, colmajor, !p->transposeData, !p->subsetGenes, p->alphaA, p->maxGibbsMassA, p, g.rs, false, &g.A, pubA, twinA);
+        const int rcA = samplerCreateImpl(data, nrow, ncol, colmajor, !p->transposeData, !p->subsetGenes, p->alphaA, p->maxGibbsMassA, p, g.rs, false, &g.A, pubA, twinA, csrA);
         prepP.join();
         if (rcA != CGB_OK) { return rcA; }
         if (rcP != CGB_OK) { return fail(rcP, errP); }
@@ -2727,7 +2803,66 @@ extern "C" int cgb_run_ex(const float *data, uint32_t nrow, uint32_t ncol, int32
 // ------------------------------------------------------------------------------------------------
 // gaps::run(const std::string &data, ...) — the path overload (src/GapsRunner.h:19-24, GapsRunner.cpp:119-159)
 // ------------------------------------------------------------------------------------------------
-namespace cgb { bool loadMatrixFile(const char *path, std::vector<float> &out, uint32_t &nrow, uint32_t &ncol, std::string &err); }
+namespace cgb {
+bool loadMatrixFile(const char *path, std::vector<float> &out, uint32_t &nrow, uint32_t &ncol, std::string &err);
+bool loadMtxTriplets(const char *path, std::vector<uint32_t> &rows, std::vector<uint32_t> &cols, std::vector<float> &vals,
+                     uint32_t &nrow, uint32_t &ncol, std::string &err);
+void compressTriplets(const std::vector<uint32_t> &major, const std::vector<uint32_t> &minor, const std::vector<float> &vals,
+                      uint32_t nMajor, std::vector<uint32_t> &ptr, std::vector<uint32_t> &idx, std::vector<float> &out,
+                      bool &anyNegative);
+}
+
+static bool endsWith(const char *s, const char *suffix)
+{
+    const size_t n = std::strlen(s), m = std::strlen(suffix);
+    return n >= m && std::strcmp(s + n - m, suffix) == 0;
+}
+
+// Matrix-Market -> both orientations in compressed rows, no dense matrix in between.  False (with err empty) when the
+// file holds something the compressed form cannot carry bit for bit (a negative value: lambda sums those too).
+static bool loadMtxCsrPair(const char *path, CsrPair &pair, uint32_t &nrow, uint32_t &ncol, std::string &err)
+{
+    std::vector<uint32_t> rows, cols;
+    std::vector<float> vals;
+    if (!loadMtxTriplets(path, rows, cols, vals, nrow, ncol, err)) { return false; }
+    if (vals.size() > 0xFFFFFFF0ull) { err = "more than 2^32 entries"; return false; }
+    bool negRow = false, negCol = false;
+    compressTriplets(rows, cols, vals, nrow, pair.rowPtr, pair.rowIdx, pair.rowVal, negRow);
+    compressTriplets(cols, rows, vals, ncol, pair.colPtr, pair.colIdx, pair.colVal, negCol);
+    return !(negRow || negCol);
+}
+
+/* Host only: the compressed rows (byRows != 0) or compressed columns of a Matrix-Market file as the sparse model's
+ * loader builds them.  ptr has nMajor + 1 entries; idx / val are written when non-NULL and large enough. */
+extern "C" int cgb_read_matrix_csr(const char *path, int32_t byRows, uint32_t *nrow, uint32_t *ncol, uint32_t *ptr,
+                                   uint64_t ptrCapacity, uint32_t *idx, float *val, uint64_t capacity, uint64_t *nnz)
+{
+    CGB_CHECK(path && nrow && ncol && nnz, "cgb_read_matrix_csr: NULL argument");
+    CsrPair pair;
+    std::string err;
+    if (!loadMtxCsrPair(path, pair, *nrow, *ncol, err))
+    {
+        return fail(err.empty() ? CGB_EUNSUPPORTED : CGB_EINVAL, std::string("cgb_read_matrix_csr: ") + (err.empty() ? "negative entries: use the dense loader" : err));
+    }
+    const std::vector<uint32_t> &p = byRows ? pair.rowPtr : pair.colPtr, &i = byRows ? pair.rowIdx : pair.colIdx;
+    const std::vector<float> &v = byRows ? pair.rowVal : pair.colVal;
+    *nnz = v.size();
+    if (ptr)
+    {
+        CGB_CHECK(ptrCapacity >= p.size(), "cgb_read_matrix_csr: ptr buffer too small");
+        std::memcpy(ptr, p.data(), p.size() * sizeof(uint32_t));
+    }
+    if (idx && val)
+    {
+        CGB_CHECK(capacity >= v.size(), "cgb_read_matrix_csr: idx / val buffers too small");
+        if (!v.empty())
+        {
+            std::memcpy(idx, i.data(), i.size() * sizeof(uint32_t));
+            std::memcpy(val, v.data(), v.size() * sizeof(float));
+        }
+    }
+    return CGB_OK;
+}
 
 extern "C" int cgb_read_matrix_file(const char *path, float *out, uint64_t capacity, uint32_t *nrow, uint32_t *ncol)
 {
@@ -2750,6 +2885,20 @@ extern "C" int cgb_run_file(const char *dataPath, const char *uncertaintyPath, c
     std::vector<float> data, unc;
     uint32_t nrow = 0, ncol = 0, urow = 0, ucol = 0;
     std::string err;
+    // The sparse model on a whole Matrix-Market file: triplets go straight to the compressed rows both samplers keep
+    // (SparseMatrix(path, ...), data_structures/SparseMatrix.cpp:52-107, never forms a dense matrix either); the dense
+    // copy the chi-square kernels read is rebuilt on the device.  COGAPS_MTX_DENSE=1 forces the dense route (tests).
+    const bool uncGiven = uncertaintyPath != nullptr && uncertaintyPath[0] != 0; // then the dense route validates it as before
+    if (p->useSparseOptimization && p->nSubsetIndices == 0 && !uncGiven && endsWith(dataPath, ".mtx") && envInt("COGAPS_MTX_DENSE", 0) == 0)
+    {
+        CsrPair pair;
+        if (loadMtxCsrPair(dataPath, pair, nrow, ncol, err))
+        {
+            return runCore(nullptr, &pair, nrow, ncol, 0, nullptr, p, nullptr, r); // uncertainty is ignored by the sparse model
+        }
+        if (!err.empty()) { return fail(CGB_EINVAL, std::string("cgb_run_file: ") + err); }
+        // negative entries: fall through to the dense route, which carries them into lambda like the reference
+    }
     if (!loadMatrixFile(dataPath, data, nrow, ncol, err)) { return fail(CGB_EINVAL, std::string("cgb_run_file: ") + err); }
     const bool haveUnc = uncertaintyPath != nullptr && uncertaintyPath[0] != 0;
     if (haveUnc)

@@ -11,6 +11,7 @@
 //                                             file_parser/MatrixElement.cpp:10-46
 #include "../../include/cogaps_b200.h"
 
+#include <algorithm>
 #include <cmath>
 #include <cstdio>
 #include <cstdlib>
@@ -18,6 +19,7 @@
 #include <fstream>
 #include <sstream>
 #include <string>
+#include <utility>
 #include <vector>
 
 namespace cgb {
@@ -127,6 +129,109 @@ static bool readMtx(std::ifstream &f, std::vector<float> &out, uint32_t &nrow, u
         out[static_cast<size_t>(row - 1) * ncol + (col - 1)] = v;
     }
     return true;
+}
+
+// ---- Matrix-Market straight to compressed rows ("loaders straight to device layouts") ----
+// Same parsing as readMtx, but the triplets are kept as triplets.  Semantics of the dense reader that must survive:
+// a later entry for the same cell overwrites an earlier one; explicit zeros are cells like any other (they simply are
+// not positive); everything not listed is 0.
+bool loadMtxTriplets(const char *path, std::vector<uint32_t> &rows, std::vector<uint32_t> &cols, std::vector<float> &vals,
+                     uint32_t &nrow, uint32_t &ncol, std::string &err)
+{
+    if (fileType(path) != kMtx)
+    {
+        err = "not a Matrix-Market file";
+        return false;
+    }
+    std::ifstream f(path);
+    if (!f.is_open())
+    {
+        err = std::string("cannot open ") + path;
+        return false;
+    }
+    std::string line = "%";
+    while (line.find('%') != std::string::npos)
+    {
+        if (!std::getline(f, line))
+        {
+            err = "Invalid MTX file";
+            return false;
+        }
+    }
+    std::stringstream dims(line);
+    unsigned long r = 0, c = 0, declared = 0;
+    dims >> r >> c >> declared;
+    if (r == 0 || c == 0)
+    {
+        err = "Invalid MTX file";
+        return false;
+    }
+    nrow = static_cast<uint32_t>(r);
+    ncol = static_cast<uint32_t>(c);
+    rows.clear(); cols.clear(); vals.clear();
+    if (declared > 0 && declared <= static_cast<unsigned long>(nrow) * ncol)
+    {
+        rows.reserve(declared); cols.reserve(declared); vals.reserve(declared);
+    }
+    unsigned long row = 0, col = 0;
+    std::string val;
+    while (f >> row >> col >> val)
+    {
+        float v;
+        if (!parseValue(val, v, err)) { return false; }
+        if (row < 1 || row > nrow || col < 1 || col > ncol)
+        {
+            err = "MTX entry outside the declared dimensions";
+            return false;
+        }
+        rows.push_back(static_cast<uint32_t>(row - 1));
+        cols.push_back(static_cast<uint32_t>(col - 1));
+        vals.push_back(v);
+    }
+    return true;
+}
+
+// Compressed rows of an nMajor x nMinor matrix from triplets (major[i], minor[i], vals[i]): within a row ascending
+// minor index, of several entries for one cell the LAST in file order, entries that are not positive dropped
+// (SparseVector keeps v > 0 only, SparseVector.cpp:20-35).  anyNegative reports a value < 0 anywhere (the dense path's
+// lambda sums those too, so the caller falls back to it).
+void compressTriplets(const std::vector<uint32_t> &major, const std::vector<uint32_t> &minor, const std::vector<float> &vals,
+                      uint32_t nMajor, std::vector<uint32_t> &ptr, std::vector<uint32_t> &idx, std::vector<float> &out,
+                      bool &anyNegative)
+{
+    const size_t n = vals.size();
+    // stable counting sort by major index keeps file order inside a row
+    std::vector<size_t> start(static_cast<size_t>(nMajor) + 1, 0);
+    for (size_t i = 0; i < n; ++i) { ++start[major[i] + 1]; }
+    for (uint32_t r = 0; r < nMajor; ++r) { start[r + 1] += start[r]; }
+    std::vector<uint32_t> order(n);
+    {
+        std::vector<size_t> fill(start.begin(), start.end() - 1);
+        for (size_t i = 0; i < n; ++i) { order[fill[major[i]]++] = static_cast<uint32_t>(i); }
+    }
+    ptr.assign(static_cast<size_t>(nMajor) + 1, 0u);
+    idx.clear(); out.clear();
+    idx.reserve(n); out.reserve(n);
+    anyNegative = false;
+    std::vector<std::pair<uint32_t, uint32_t> > rowEntries; // (minor, position in file)
+    for (uint32_t r = 0; r < nMajor; ++r)
+    {
+        rowEntries.clear();
+        for (size_t j = start[r]; j < start[r + 1]; ++j) { rowEntries.push_back(std::make_pair(minor[order[j]], order[j])); }
+        std::sort(rowEntries.begin(), rowEntries.end()); // by minor, then by file position
+        for (size_t j = 0; j < rowEntries.size(); ++j)
+        {
+            if (j + 1 < rowEntries.size() && rowEntries[j + 1].first == rowEntries[j].first) { continue; } // overwritten later
+            const float v = vals[rowEntries[j].second];
+            if (v < 0.f) { anyNegative = true; }
+            if (v > 0.f)
+            {
+                idx.push_back(rowEntries[j].first);
+                out.push_back(v);
+            }
+        }
+        ptr[r + 1] = static_cast<uint32_t>(idx.size());
+    }
 }
 
 static bool readDelimited(std::ifstream &f, char delimiter, bool gct, std::vector<float> &out, uint32_t &nrow, uint32_t &ncol,

@@ -13,6 +13,7 @@
 //   eval_sparse_kernel / eval_stream_sparse_kernel, sparse_tables_kernel, sparse_chisq_kernel
 //                      SparseNormalModel (SparseNormalModel.cpp:39-60,153-311)
 //   transpose_kernel   DenseNormalModel::sync (DenseNormalModel.cpp:20-36)
+//   csr_scatter_kernel compressed rows -> dense D (Matrix-Market input of the sparse model)
 //   rebuild_ap_kernel  extraInitialization (:38-54)
 //   chisq_kernel       chiSq (:56-68)
 //   col_nonzero_kernel canUseGibbs precompute (:100-108)
@@ -1339,6 +1340,19 @@ __global__ void __launch_bounds__(kSparseThreads, 4) eval_stream_sparse_kernel(c
 {
     extern __shared__ __align__(128) unsigned char smemRaw[];
     stream_worker<2>(mv, sp, smemRaw);
+}
+
+// ------------------------------------------------------------------------------------------------
+// compressed rows -> the zero-filled dense copy (one CTA per sampler row; D was cleared beforehand).  Used when the
+// data arrives as Matrix-Market triplets and never exists as a dense matrix on the host.
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) csr_scatter_kernel(const uint32_t *__restrict__ rowPtr, const uint32_t *__restrict__ idx,
+                                                          const float *__restrict__ val, uint32_t ld, float *__restrict__ D)
+{
+    const uint32_t r = blockIdx.x;
+    const uint32_t b = rowPtr[r], e = rowPtr[r + 1];
+    float *row = D + static_cast<size_t>(r) * ld;
+    for (uint32_t i = b + threadIdx.x; i < e; i += blockDim.x) { row[idx[i]] = val[i]; }
 }
 
 // ------------------------------------------------------------------------------------------------

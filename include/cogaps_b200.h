@@ -150,6 +150,15 @@ int cgb_run_file(const char *dataPath, const char *uncertaintyPath, const cgb_pa
 /* Reads a matrix file into out (row-major, nrow*ncol floats; NULL: dimensions only).  Host only, no device needed. */
 int cgb_read_matrix_file(const char *path, float *out, uint64_t capacity, uint32_t *nrow, uint32_t *ncol);
 
+/* The compressed rows (byRows != 0) or compressed columns of a Matrix-Market file exactly as cgb_run_file hands them to
+ * the sparse model's two samplers (SparseMatrix(path, ...), data_structures/SparseMatrix.cpp:52-107; SparseVector keeps
+ * the positive entries in ascending index order, SparseVector.cpp:20-35): with useSparseOptimization, a whole-matrix
+ * .mtx input never exists as a dense matrix on the host.  A later entry for a cell overwrites an earlier one, like the
+ * dense reader.  ptr gets nMajor + 1 offsets; idx / val are filled when non-NULL (size them with a first call).  A file
+ * with a negative value is refused with CGB_EUNSUPPORTED (cgb_run_file then takes the dense route).  Host only. */
+int cgb_read_matrix_csr(const char *path, int32_t byRows, uint32_t *nrow, uint32_t *ncol, uint32_t *ptr,
+                        uint64_t ptrCapacity, uint32_t *idx, float *val, uint64_t capacity, uint64_t *nnz);
+
 /* ------------------------------------------------------------------------------------------
  * GapsRandomState (src/math/Random.h:79-98): the xoroshiro128+ seeder every sampler and every
  * proposal pulls its PCG seed from, plus the three lookup tables.

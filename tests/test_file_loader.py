@@ -139,3 +139,97 @@ def test_run_from_file_equals_run_from_memory(tmp_path):
     a = cg.gaps_run_file(path, subsetGenes=1, subsetIndices=sub, **kw)
     b = cg.gaps_run(mem, subsetGenes=1, subsetIndices=sorted(sub), **kw)
     assert np.array_equal(bits(a.Amean), bits(b.Amean)) and np.array_equal(bits(a.Pmean), bits(b.Pmean))
+
+
+def _write_mtx(path, m, rng, duplicates=0, explicit_zeros=0, shuffle=True):
+    """Matrix-Market text of m with the entries in random order, `duplicates` cells listed twice (the later value is
+    the one m holds) and `explicit_zeros` zero cells listed as 0."""
+    nz = [(i, j, float(m[i, j])) for i, j in np.argwhere(m != 0)]
+    if shuffle:
+        rng.shuffle(nz)
+    lines = ["%d %d %s" % (i + 1, j + 1, repr(v)) for i, j, v in nz]
+    for i, j, v in nz[:duplicates]:
+        lines.insert(int(rng.integers(0, lines.index("%d %d %s" % (i + 1, j + 1, repr(v))) + 1)),
+                     "%d %d %s" % (i + 1, j + 1, repr(v + 1.5)))          # an earlier, overwritten value
+    zeros = np.argwhere(m == 0)
+    for i, j in zeros[rng.permutation(len(zeros))[:explicit_zeros]]:
+        lines.insert(int(rng.integers(0, len(lines) + 1)), "%d %d 0" % (i + 1, j + 1))
+    with open(path, "w") as f:
+        f.write("%%MatrixMarket matrix coordinate real general\n")
+        f.write("%d %d %d\n" % (m.shape[0], m.shape[1], len(lines)))
+        f.write("\n".join(lines) + "\n")
+
+
+def _csr_of(dense):
+    ptr, idx, val = [0], [], []
+    for row in dense:
+        cols = np.nonzero(row > 0)[0]
+        idx.extend(cols)
+        val.extend(row[cols])
+        ptr.append(len(idx))
+    return np.array(ptr, np.uint32), np.array(idx, np.uint32), np.array(val, np.float32)
+
+
+@pytest.mark.parametrize("shape,seed", [((23, 9), 2), ((7, 64), 3), ((1, 5), 4), ((40, 1), 5)])
+def test_matrix_market_straight_to_compressed_rows(tmp_path, shape, seed):
+    """with sparseOptimization a .mtx file goes straight to the compressed rows of both samplers
+    (SparseMatrix(path), SparseMatrix.cpp:52-107).  They must be what the dense route derives from the same file."""
+    import cogaps_b200 as cg
+    rng = np.random.default_rng(seed)
+    m = _matrix(seed, shape)
+    m[0, :] = 0                                            # an empty row, and maybe an empty column
+    path = str(tmp_path / "data.mtx")
+    _write_mtx(path, m, rng, duplicates=min(3, int((m != 0).sum())), explicit_zeros=min(4, int((m == 0).sum())))
+    dense = cg.read_matrix_file(path)
+    assert np.array_equal(bits(dense), bits(m))            # the dense reader: last entry for a cell wins
+    for by_rows, want in ((True, dense), (False, dense.T)):
+        nrow, ncol, ptr, idx, val = cg.read_matrix_csr(path, by_rows=by_rows)
+        assert (nrow, ncol) == shape
+        wptr, widx, wval = _csr_of(want)
+        assert np.array_equal(ptr, wptr) and np.array_equal(idx, widx) and np.array_equal(bits(val), bits(wval))
+
+
+def test_matrix_market_compressed_rows_edge_cases(tmp_path):
+    import cogaps_b200 as cg
+    from cogaps_b200._lib import CogapsError
+    path = tmp_path / "data.mtx"
+    path.write_text("%%MatrixMarket matrix coordinate real general\n3 4 0\n")            # no entries at all
+    nrow, ncol, ptr, idx, val = cg.read_matrix_csr(path)
+    assert (nrow, ncol, idx.size) == (3, 4, 0) and np.array_equal(ptr, np.zeros(4, np.uint32))
+    path.write_text("%%MatrixMarket matrix coordinate real general\n3 4 2\n1 1 2.5\n2 3 -1.0\n")
+    with pytest.raises(CogapsError) as e:                                                  # lambda sums negatives too:
+        cg.read_matrix_csr(path)                                                           # only the dense route carries them
+    assert e.value.code == -5
+    path.write_text("%%MatrixMarket matrix coordinate real general\n3 4 1\n4 1 2.5\n")   # outside the declared shape
+    with pytest.raises(CogapsError):
+        cg.read_matrix_csr(path)
+    with pytest.raises(CogapsError):
+        cg.read_matrix_csr(tmp_path / "data.csv")
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("transpose", [0, 1])
+def test_sparse_run_from_matrix_market_never_needs_the_dense_matrix(tmp_path, transpose, monkeypatch):
+    """cgb_run_file on a .mtx with sparseOptimization: compressed rows straight from the triplets, the dense copy the
+    chi-square kernels read rebuilt on the device (csr_scatter_kernel).  Every output bit equals the dense route's and
+    the in-memory run's."""
+    import cogaps_b200 as cg
+    rng = np.random.default_rng(11)
+    m = _matrix(11, (90, 37))
+    m[rng.random(m.shape) < 0.5] = 0
+    m[3, :] = 0
+    path = str(tmp_path / "data.mtx")
+    _write_mtx(path, m, rng, duplicates=5, explicit_zeros=6)
+    kw = dict(seed=4, nPatterns=4, nIterations=40, outputFrequency=10, useSparseOptimization=1, transposeData=transpose)
+    straight = cg.gaps_run_file(path, **kw)
+    monkeypatch.setenv("COGAPS_MTX_DENSE", "1")
+    dense_route = cg.gaps_run_file(path, **kw)
+    monkeypatch.delenv("COGAPS_MTX_DENSE")
+    memory = cg.gaps_run(cg.read_matrix_file(path), **kw)
+    for other in (dense_route, memory):
+        for f in ("Amean", "Asd", "Pmean", "Psd", "chisqHistory"):
+            assert np.array_equal(bits(getattr(straight, f)), bits(getattr(other, f))), f
+        assert np.array_equal(straight.atomHistoryA, other.atomHistoryA)
+        assert np.array_equal(straight.atomHistoryP, other.atomHistoryP)
+        assert straight.totalUpdates == other.totalUpdates
+        assert np.float32(straight.meanChiSq) == np.float32(other.meanChiSq)
