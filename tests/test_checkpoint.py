@@ -362,3 +362,37 @@ def test_gpu_sampler_archive_round_trip(sparse):
     # a dense archive does not go into a sparse sampler of the same shape, nor A's into P
     with pytest.raises(cg.CogapsError):
         p2.deserialize(blobA)
+
+
+def test_reader_survives_random_damage(tmp_path):
+    """A checkpoint is an input file: whatever bytes it holds, the reader either accepts a structurally valid archive
+    or reports CGB_EINVAL — it never crashes, hangs or allocates from a corrupt header (sizes are checked against the
+    bytes that are left before anything is resized)."""
+    import cogaps_b200 as cg
+    rng = np.random.default_rng(2026)
+    path = tmp_path / "fuzz.out"
+    accepted = 0
+    for name in sorted(CHECKPOINT_CASES):
+        raw = read(golden_file(name))
+        for trial in range(150):
+            b = bytearray(raw)
+            kind = trial % 3
+            if kind == 0:                                   # flip a few bits anywhere
+                for _ in range(int(rng.integers(1, 4))):
+                    b[int(rng.integers(0, len(b)))] ^= 1 << int(rng.integers(0, 8))
+            elif kind == 1:                                 # overwrite an aligned word with an extreme value
+                off = int(rng.integers(0, len(b) - 8))
+                b[off:off + 4] = int(rng.choice([0, 1, 0x7FFFFFFF, 0xFFFFFFFF, 0x80000000])).to_bytes(4, "little")
+            else:                                           # cut the tail and / or splice a random block
+                cut = int(rng.integers(1, len(b)))
+                b = b[:cut] + bytearray(rng.integers(0, 256, int(rng.integers(0, 64)), dtype=np.uint8).tobytes())
+            path.write_bytes(bytes(b))
+            try:
+                info = cg.checkpoint_info(path)
+                cg.checkpoint_rewrite(path, tmp_path / "fuzz_copy.out")
+                assert read(tmp_path / "fuzz_copy.out") == bytes(b) or name == "sparse"   # flag words are re-derived
+                assert info["fileBytes"] == len(b)
+                accepted += 1
+            except cg.CogapsError as e:
+                assert e.code == -1
+    assert accepted > 0      # damage inside a float payload is still a valid archive
