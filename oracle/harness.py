@@ -101,7 +101,13 @@ class RefLib(object):
             C.c_uint32(checkpointInterval), _path(checkpointOutFile), _path(checkpointInFile))
         if rc != 0:
             raise RuntimeError("cogaps_ref_run failed: %d" % rc)
-        return res.finish()
+        out = res.finish()
+        # the reference's own phases (its clock readings at GapsRunner.cpp:400-473): seconds before the sampler loop
+        # and inside it; totalRunningTime above is the wall time of the whole gaps::run call
+        load, loop = C.c_double(), C.c_double()
+        self.lib.cogaps_ref_last_run_seconds(C.byref(load), C.byref(loop))
+        out.secondsLoading, out.secondsSamplerLoop = load.value, loop.value
+        return out
 
     def tables(self):
         erf = np.zeros(ERF_TABLE_SIZE, np.float32)

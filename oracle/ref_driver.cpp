@@ -38,6 +38,7 @@
 #include "GapsRunner.h"
 #include "data_structures/Matrix.h"
 #include "utils/GlobalConfig.h"
+#include <boost/date_time/posix_time/posix_time.hpp> // the shim: its clock_marks, see cogaps_ref_last_run_seconds
 
 #include "../include/cogaps_b200.h"
 
@@ -70,7 +71,19 @@ static void fromMatrix(const Matrix &m, float *out)
     }
 }
 
+static double g_lastLoadSeconds = -1.0, g_lastLoopSeconds = -1.0;
+
 extern "C" {
+
+// Phases of the last cogaps_ref_run* call by the reference's own clock readings: everything before the sampler loop
+// (Matrix copies, both samplers' constructors, sync, extraInitialization) and the loop itself (both phases) — the
+// interval GapsResult::totalRunningTime covers, in whole seconds there.  -1 when unknown.
+int cogaps_ref_last_run_seconds(double *load, double *loop)
+{
+    *load = g_lastLoadSeconds;
+    *loop = g_lastLoopSeconds;
+    return 0;
+}
 
 const char *cogaps_ref_build_report(void)
 {
@@ -135,9 +148,22 @@ int cogaps_ref_run_checkpointed(const float *data, uint32_t nrow, uint32_t ncol,
     }
 
     GapsRandomState randState(params.seed);
+    boost::posix_time::marks().n = 0;
     std::chrono::steady_clock::time_point t0 = std::chrono::steady_clock::now();
     GapsResult res = gaps::run(D, params, U, &randState);
     std::chrono::steady_clock::time_point t1 = std::chrono::steady_clock::now();
+    {
+        // the reference's own clock readings (see ref_shim/.../posix_time.hpp): [0] loading starts, [1] loading done,
+        // [2] sampler loop starts (GapsRunner.cpp:450), latest = loop done (:473; a distributed run reads it once more
+        // for its "finished" line, a few microseconds later)
+        const boost::posix_time::clock_marks &m = boost::posix_time::marks();
+        g_lastLoadSeconds = g_lastLoopSeconds = -1.0;
+        if (m.n >= 4)
+        {
+            g_lastLoadSeconds = std::chrono::duration<double>(m.t[2] - t0).count();
+            g_lastLoopSeconds = std::chrono::duration<double>(m.t[63] - m.t[2]).count();
+        }
+    }
 
     fromMatrix(res.Amean, r->Amean);
     fromMatrix(res.Asd, r->Asd);
