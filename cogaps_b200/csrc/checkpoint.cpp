@@ -67,7 +67,7 @@ static void putMatrix(ByteWriter &w, const std::vector<float> &colMajor, uint32_
 // a matrix as large as the file could possibly hold, so that a corrupt header cannot ask for terabytes
 static bool plausible(const ByteReader &r, uint64_t rows, uint64_t cols)
 {
-    return rows > 0 && cols > 0 && rows * cols <= r.remaining() / sizeof(float);
+    return rows > 0 && cols > 0 && cols <= (r.remaining() / sizeof(float)) / rows; // no product: it could wrap
 }
 
 static bool getMatrix(ByteReader &r, std::vector<float> &colMajor, uint32_t &rows, uint32_t &cols, std::string &err)

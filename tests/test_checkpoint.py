@@ -135,6 +135,11 @@ def test_library_rejects_damaged_files(tmp_path):
     bad.write_bytes(bytes(huge))
     with pytest.raises(cg.CogapsError, match="does not fit the file"):
         cg.checkpoint_info(bad)
+    both = bytearray(raw)                                # rows x columns that would wrap a 64-bit product
+    both[4 + 41 + 16:4 + 41 + 24] = (0xFFFFFFFF).to_bytes(4, "little") * 2
+    bad.write_bytes(bytes(both))
+    with pytest.raises(cg.CogapsError, match="does not fit the file"):
+        cg.checkpoint_info(bad)
     with pytest.raises(cg.CogapsError, match="cannot open"):
         cg.checkpoint_info(tmp_path / "missing.out")
 
