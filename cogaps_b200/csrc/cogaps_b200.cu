@@ -30,6 +30,29 @@ static int fail(int code, const std::string &msg)
     return code;
 }
 
+// Nothing may leave the library as a C++ exception (include/cogaps_b200.h: status codes only): every entry point that
+// can allocate or start a thread runs its body through this.
+template <class Body>
+static int guarded(const char *who, Body body) noexcept
+{
+    try
+    {
+        return body();
+    }
+    catch (const std::bad_alloc &)
+    {
+        return fail(CGB_ENOMEM, std::string(who) + ": out of host memory");
+    }
+    catch (const std::exception &e)
+    {
+        return fail(CGB_EINTERNAL, std::string(who) + ": " + e.what());
+    }
+    catch (...)
+    {
+        return fail(CGB_EINTERNAL, std::string(who) + ": unknown exception");
+    }
+}
+
 #define CGB_CUDA(call)                                                                                  \
     do                                                                                                  \
     {                                                                                                   \
@@ -106,19 +129,29 @@ extern "C" const char *cgb_build_report(void)
     return s.c_str();
 }
 
-extern "C" int cgb_set_device(int device)
+static int cgb_set_device_body(int device)
 {
     g_device = device;
     return ensureDevice();
 }
 
+extern "C" int cgb_set_device(int device)
+{
+    return guarded("cgb_set_device", [&]() { return cgb_set_device_body(device); });
+}
+
 extern "C" uint64_t cgb_kernel_launch_count(void) { return g_kernelLaunches.load(); }
 
-extern "C" int cgb_set_resident_share(int32_t parts)
+static int cgb_set_resident_share_body(int32_t parts)
 {
     CGB_CHECK(parts >= 1 && parts <= 64, "cgb_set_resident_share: parts must be in 1..64");
     g_residentShare.store(parts);
     return CGB_OK;
+}
+
+extern "C" int cgb_set_resident_share(int32_t parts)
+{
+    return guarded("cgb_set_resident_share", [&]() { return cgb_set_resident_share_body(parts); });
 }
 
 extern "C" void cgb_params_default(cgb_params *p)
@@ -142,14 +175,19 @@ extern "C" void cgb_params_default(cgb_params *p)
 // ------------------------------------------------------------------------------------------------
 // GapsRandomState / GapsRng
 // ------------------------------------------------------------------------------------------------
-extern "C" int cgb_randstate_create(uint32_t seed, cgb_randstate **out)
+static int cgb_randstate_create_body(uint32_t seed, cgb_randstate **out)
 {
     CGB_CHECK(out != nullptr, "cgb_randstate_create: out is NULL");
     *out = new (std::nothrow) cgb_randstate(seed);
     return *out ? CGB_OK : fail(CGB_ENOMEM, "cgb_randstate_create: out of memory");
 }
 
-extern "C" int cgb_randstate_set_tables(cgb_randstate *rs, const float *erf, const float *erfinv, const float *qgamma)
+extern "C" int cgb_randstate_create(uint32_t seed, cgb_randstate **out)
+{
+    return guarded("cgb_randstate_create", [&]() { return cgb_randstate_create_body(seed, out); });
+}
+
+static int cgb_randstate_set_tables_body(cgb_randstate *rs, const float *erf, const float *erfinv, const float *qgamma)
 {
     CGB_CHECK(rs && erf && erfinv && qgamma, "cgb_randstate_set_tables: NULL argument");
     CGB_CHECK(rs->dErf == nullptr, "cgb_randstate_set_tables: tables already uploaded; set them before creating samplers");
@@ -159,7 +197,12 @@ extern "C" int cgb_randstate_set_tables(cgb_randstate *rs, const float *erf, con
     return CGB_OK;
 }
 
-extern "C" int cgb_randstate_get_tables(const cgb_randstate *rs, float *erf, float *erfinv, float *qgamma)
+extern "C" int cgb_randstate_set_tables(cgb_randstate *rs, const float *erf, const float *erfinv, const float *qgamma)
+{
+    return guarded("cgb_randstate_set_tables", [&]() { return cgb_randstate_set_tables_body(rs, erf, erfinv, qgamma); });
+}
+
+static int cgb_randstate_get_tables_body(const cgb_randstate *rs, float *erf, float *erfinv, float *qgamma)
 {
     CGB_CHECK(rs && erf && erfinv && qgamma, "cgb_randstate_get_tables: NULL argument");
     std::memcpy(erf, rs->tables.erf, sizeof(rs->tables.erf));
@@ -168,11 +211,21 @@ extern "C" int cgb_randstate_get_tables(const cgb_randstate *rs, float *erf, flo
     return CGB_OK;
 }
 
-extern "C" int cgb_randstate_next_seed(cgb_randstate *rs, uint64_t *out)
+extern "C" int cgb_randstate_get_tables(const cgb_randstate *rs, float *erf, float *erfinv, float *qgamma)
+{
+    return guarded("cgb_randstate_get_tables", [&]() { return cgb_randstate_get_tables_body(rs, erf, erfinv, qgamma); });
+}
+
+static int cgb_randstate_next_seed_body(cgb_randstate *rs, uint64_t *out)
 {
     CGB_CHECK(rs && out, "cgb_randstate_next_seed: NULL argument");
     *out = rs->seeder.next();
     return CGB_OK;
+}
+
+extern "C" int cgb_randstate_next_seed(cgb_randstate *rs, uint64_t *out)
+{
+    return guarded("cgb_randstate_next_seed", [&]() { return cgb_randstate_next_seed_body(rs, out); });
 }
 
 extern "C" void cgb_randstate_destroy(cgb_randstate *rs)
@@ -194,7 +247,7 @@ static int uploadTables(cgb_randstate *rs)
     return CGB_OK;
 }
 
-extern "C" int cgb_rng_create(cgb_randstate *rs, cgb_rng **out)
+static int cgb_rng_create_body(cgb_randstate *rs, cgb_rng **out)
 {
     CGB_CHECK(rs && out, "cgb_rng_create: NULL argument");
     cgb_rng *r = new (std::nothrow) cgb_rng();
@@ -204,21 +257,36 @@ extern "C" int cgb_rng_create(cgb_randstate *rs, cgb_rng **out)
     *out = r;
     return CGB_OK;
 }
+
+extern "C" int cgb_rng_create(cgb_randstate *rs, cgb_rng **out)
+{
+    return guarded("cgb_rng_create", [&]() { return cgb_rng_create_body(rs, out); });
+}
 extern "C" int cgb_rng_uniform32(cgb_rng *r, uint32_t *out) { *out = r->rng.next(); return CGB_OK; }
 extern "C" int cgb_rng_uniform32_range(cgb_rng *r, uint32_t a, uint32_t b, uint32_t *out) { *out = r->rng.uniform32(a, b); return CGB_OK; }
 extern "C" int cgb_rng_uniform64_range(cgb_rng *r, uint64_t a, uint64_t b, uint64_t *out) { *out = r->rng.uniform64(a, b); return CGB_OK; }
 extern "C" int cgb_rng_uniform(cgb_rng *r, float *out) { *out = r->rng.uniform(); return CGB_OK; }
 extern "C" int cgb_rng_poisson(cgb_rng *r, double lambda, int32_t *out) { *out = r->rng.poisson(lambda); return CGB_OK; }
 extern "C" int cgb_rng_exponential(cgb_rng *r, float lambda, float *out) { *out = r->rng.exponential(lambda); return CGB_OK; }
-extern "C" int cgb_rng_trunc_normal(cgb_rng *r, float a, float b, float mean, float sd, float *out, int32_t *has)
+static int cgb_rng_trunc_normal_body(cgb_rng *r, float a, float b, float mean, float sd, float *out, int32_t *has)
 {
     *has = trunc_normal(r->rng, r->rs->tables.erf, r->rs->tables.erfinv, a, b, mean, sd, out) ? 1 : 0;
     return CGB_OK;
 }
-extern "C" int cgb_rng_trunc_gamma_upper(cgb_rng *r, float b, float scale, float *out)
+
+extern "C" int cgb_rng_trunc_normal(cgb_rng *r, float a, float b, float mean, float sd, float *out, int32_t *has)
+{
+    return guarded("cgb_rng_trunc_normal", [&]() { return cgb_rng_trunc_normal_body(r, a, b, mean, sd, out, has); });
+}
+static int cgb_rng_trunc_gamma_upper_body(cgb_rng *r, float b, float scale, float *out)
 {
     *out = r->rng.truncGammaUpper(r->rs->tables.qgamma, b, scale);
     return CGB_OK;
+}
+
+extern "C" int cgb_rng_trunc_gamma_upper(cgb_rng *r, float b, float scale, float *out)
+{
+    return guarded("cgb_rng_trunc_gamma_upper", [&]() { return cgb_rng_trunc_gamma_upper_body(r, b, scale, out); });
 }
 extern "C" void cgb_rng_destroy(cgb_rng *r) { delete r; }
 
@@ -320,13 +388,18 @@ static void chooseSegments(cgb_sampler *s)
     s->tablesInSmem = s->sparse || s->seg <= kTableSegFloats;
 }
 
-extern "C" int cgb_reduction_order_for_length(uint32_t rowLength, cgb_reduction_order *out)
+static int cgb_reduction_order_for_length_body(uint32_t rowLength, cgb_reduction_order *out)
 {
     CGB_CHECK(out && rowLength, "cgb_reduction_order_for_length: bad argument");
     out->threadsPerSegment = kThreads;
     out->vectorWidth = kVec;
     segmentsForLength(rowLength, out->nSegments, out->segmentLength);
     return CGB_OK;
+}
+
+extern "C" int cgb_reduction_order_for_length(uint32_t rowLength, cgb_reduction_order *out)
+{
+    return guarded("cgb_reduction_order_for_length", [&]() { return cgb_reduction_order_for_length_body(rowLength, out); });
 }
 
 static int stopPersistent(cgb_sampler *s);
@@ -689,14 +762,21 @@ static int samplerCreateImpl(const float *data, uint32_t nrow, uint32_t ncol, in
     return CGB_OK;
 }
 
-extern "C" int cgb_sampler_create(const float *data, uint32_t nrow, uint32_t ncol, int32_t colmajor,
+static int cgb_sampler_create_body(const float *data, uint32_t nrow, uint32_t ncol, int32_t colmajor,
                                   int32_t transpose, int32_t subsetRows, float alpha, float maxGibbsMass,
                                   const cgb_params *params, cgb_randstate *rs, cgb_sampler **out)
 {
     return samplerCreateImpl(data, nrow, ncol, colmajor, transpose, subsetRows, alpha, maxGibbsMass, params, rs, true, out);
 }
 
-extern "C" int cgb_sampler_set_uncertainty(cgb_sampler *s, const float *unc, uint32_t nrow, uint32_t ncol,
+extern "C" int cgb_sampler_create(const float *data, uint32_t nrow, uint32_t ncol, int32_t colmajor,
+                                  int32_t transpose, int32_t subsetRows, float alpha, float maxGibbsMass,
+                                  const cgb_params *params, cgb_randstate *rs, cgb_sampler **out)
+{
+    return guarded("cgb_sampler_create", [&]() { return cgb_sampler_create_body(data, nrow, ncol, colmajor, transpose, subsetRows, alpha, maxGibbsMass, params, rs, out); });
+}
+
+static int cgb_sampler_set_uncertainty_body(cgb_sampler *s, const float *unc, uint32_t nrow, uint32_t ncol,
                                            int32_t colmajor, int32_t transpose, int32_t subsetRows,
                                            const cgb_params *params)
 {
@@ -717,6 +797,13 @@ extern "C" int cgb_sampler_set_uncertainty(cgb_sampler *s, const float *unc, uin
     return CGB_OK;
 }
 
+extern "C" int cgb_sampler_set_uncertainty(cgb_sampler *s, const float *unc, uint32_t nrow, uint32_t ncol,
+                                           int32_t colmajor, int32_t transpose, int32_t subsetRows,
+                                           const cgb_params *params)
+{
+    return guarded("cgb_sampler_set_uncertainty", [&]() { return cgb_sampler_set_uncertainty_body(s, unc, nrow, ncol, colmajor, transpose, subsetRows, params); });
+}
+
 static int refreshColNonzero(cgb_sampler *s)
 {
     col_nonzero_kernel<<<s->k, 256, 0, s->stream>>>(s->dM, s->nRows, s->ldM, s->dColNonzero);
@@ -725,7 +812,7 @@ static int refreshColNonzero(cgb_sampler *s)
     return CGB_OK;
 }
 
-extern "C" int cgb_sampler_set_matrix(cgb_sampler *s, const float *mat)
+static int cgb_sampler_set_matrix_body(cgb_sampler *s, const float *mat)
 {
     CGB_CHECK(s && mat, "cgb_sampler_set_matrix: NULL argument");
     CGB_CUDA(cudaSetDevice(s->device));
@@ -755,14 +842,24 @@ extern "C" int cgb_sampler_set_matrix(cgb_sampler *s, const float *mat)
     return refreshColNonzero(s);
 }
 
-extern "C" int cgb_sampler_set_annealing_temp(cgb_sampler *s, float temp)
+extern "C" int cgb_sampler_set_matrix(cgb_sampler *s, const float *mat)
+{
+    return guarded("cgb_sampler_set_matrix", [&]() { return cgb_sampler_set_matrix_body(s, mat); });
+}
+
+static int cgb_sampler_set_annealing_temp_body(cgb_sampler *s, float temp)
 {
     CGB_CHECK(s != nullptr, "cgb_sampler_set_annealing_temp: NULL sampler");
     s->annealingTemp = temp;
     return CGB_OK;
 }
 
-extern "C" int cgb_sampler_sync(cgb_sampler *s, const cgb_sampler *other)
+extern "C" int cgb_sampler_set_annealing_temp(cgb_sampler *s, float temp)
+{
+    return guarded("cgb_sampler_set_annealing_temp", [&]() { return cgb_sampler_set_annealing_temp_body(s, temp); });
+}
+
+static int cgb_sampler_sync_body(cgb_sampler *s, const cgb_sampler *other)
 {
     CGB_CHECK(s && other, "cgb_sampler_sync: NULL argument");
     CGB_CHECK(other->nRows == s->L && other->L == s->nRows && other->k == s->k, "cgb_sampler_sync: shapes do not transpose");
@@ -792,7 +889,12 @@ extern "C" int cgb_sampler_sync(cgb_sampler *s, const cgb_sampler *other)
     return CGB_OK;
 }
 
-extern "C" int cgb_sampler_extra_initialization(cgb_sampler *s)
+extern "C" int cgb_sampler_sync(cgb_sampler *s, const cgb_sampler *other)
+{
+    return guarded("cgb_sampler_sync", [&]() { return cgb_sampler_sync_body(s, other); });
+}
+
+static int cgb_sampler_extra_initialization_body(cgb_sampler *s)
 {
     CGB_CHECK(s && s->other, "cgb_sampler_extra_initialization: sync() has not been called");
     if (s->sparse) { return CGB_OK; } // SparseNormalModel::extraInitialization is a nop (SparseNormalModel.cpp:33-37)
@@ -803,6 +905,11 @@ extern "C" int cgb_sampler_extra_initialization(cgb_sampler *s)
     ++g_kernelLaunches;
     CGB_CUDA(cudaGetLastError());
     return CGB_OK;
+}
+
+extern "C" int cgb_sampler_extra_initialization(cgb_sampler *s)
+{
+    return guarded("cgb_sampler_extra_initialization", [&]() { return cgb_sampler_extra_initialization_body(s); });
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -934,7 +1041,7 @@ static int launchEval(cgb_sampler *s, EvalParams &params)
 }
 
 // debug: per-phase SM-clock offsets of the leader CTA of every task, averaged (COGAPS phase profile)
-extern "C" int cgb_sampler_debug_phase_clocks(cgb_sampler *s, int32_t enable, double *out, uint64_t *nTasks)
+static int cgb_sampler_debug_phase_clocks_body(cgb_sampler *s, int32_t enable, double *out, uint64_t *nTasks)
 {
     CGB_CHECK(s != nullptr, "cgb_sampler_debug_phase_clocks: NULL sampler");
     CGB_CUDA(cudaSetDevice(s->device));
@@ -957,6 +1064,11 @@ extern "C" int cgb_sampler_debug_phase_clocks(cgb_sampler *s, int32_t enable, do
     for (int i = 0; i < kPhaseSlots; ++i) { s->phaseSum[i] = 0.0; }
     s->phaseTasks = 0;
     return CGB_OK;
+}
+
+extern "C" int cgb_sampler_debug_phase_clocks(cgb_sampler *s, int32_t enable, double *out, uint64_t *nTasks)
+{
+    return guarded("cgb_sampler_debug_phase_clocks", [&]() { return cgb_sampler_debug_phase_clocks_body(s, enable, out, nTasks); });
 }
 
 // SURVEY 8(d), sparse model: the index bit-flags of the data column and of the factor column(s) — 2 x ceil(L/64)
@@ -1633,7 +1745,7 @@ static int sequentialUpdate(cgb_sampler *s, uint32_t nSteps)
 }
 
 // AsynchronousGibbsSampler::update, AsynchronousGibbsSampler.h:88-122
-extern "C" int cgb_sampler_update(cgb_sampler *s, uint32_t nSteps, uint32_t nThreads)
+static int cgb_sampler_update_body(cgb_sampler *s, uint32_t nSteps, uint32_t nThreads)
 {
     (void)nThreads;
     CGB_CHECK(s && s->other, "cgb_sampler_update: sync() has not been called");
@@ -1710,7 +1822,12 @@ extern "C" int cgb_sampler_update(cgb_sampler *s, uint32_t nSteps, uint32_t nThr
     return CGB_OK;
 }
 
-extern "C" int cgb_sampler_alpha_parameters(cgb_sampler *s, uint32_t n, const int32_t *variant,
+extern "C" int cgb_sampler_update(cgb_sampler *s, uint32_t nSteps, uint32_t nThreads)
+{
+    return guarded("cgb_sampler_update", [&]() { return cgb_sampler_update_body(s, nSteps, nThreads); });
+}
+
+static int cgb_sampler_alpha_parameters_body(cgb_sampler *s, uint32_t n, const int32_t *variant,
                                             const uint32_t *r1, const uint32_t *c1, const uint32_t *r2,
                                             const uint32_t *c2, const float *ch, float *s_out, float *smu_out)
 {
@@ -1805,6 +1922,13 @@ extern "C" int cgb_sampler_alpha_parameters(cgb_sampler *s, uint32_t n, const in
     return CGB_OK;
 }
 
+extern "C" int cgb_sampler_alpha_parameters(cgb_sampler *s, uint32_t n, const int32_t *variant,
+                                            const uint32_t *r1, const uint32_t *c1, const uint32_t *r2,
+                                            const uint32_t *c2, const float *ch, float *s_out, float *smu_out)
+{
+    return guarded("cgb_sampler_alpha_parameters", [&]() { return cgb_sampler_alpha_parameters_body(s, n, variant, r1, c1, r2, c2, ch, s_out, smu_out); });
+}
+
 // ------------------------------------------------------------------------------------------------
 // reductions and accessors
 // ------------------------------------------------------------------------------------------------
@@ -1818,7 +1942,7 @@ static int sumPartials(cgb_sampler *s, int nBlocks, double *out)
     return CGB_OK;
 }
 
-extern "C" int cgb_sampler_chisq(const cgb_sampler *cs, float *out)
+static int cgb_sampler_chisq_body(const cgb_sampler *cs, float *out)
 {
     CGB_CHECK(cs && out, "cgb_sampler_chisq: NULL argument");
     cgb_sampler *s = const_cast<cgb_sampler*>(cs);
@@ -1843,28 +1967,48 @@ extern "C" int cgb_sampler_chisq(const cgb_sampler *cs, float *out)
     return CGB_OK;
 }
 
-extern "C" int cgb_sampler_n_atoms(const cgb_sampler *s, uint64_t *out)
+extern "C" int cgb_sampler_chisq(const cgb_sampler *cs, float *out)
+{
+    return guarded("cgb_sampler_chisq", [&]() { return cgb_sampler_chisq_body(cs, out); });
+}
+
+static int cgb_sampler_n_atoms_body(const cgb_sampler *s, uint64_t *out)
 {
     CGB_CHECK(s && out, "cgb_sampler_n_atoms: NULL argument");
     *out = s->domain.size();
     return CGB_OK;
 }
 
-extern "C" int cgb_sampler_data_sparsity(const cgb_sampler *s, float *out)
+extern "C" int cgb_sampler_n_atoms(const cgb_sampler *s, uint64_t *out)
+{
+    return guarded("cgb_sampler_n_atoms", [&]() { return cgb_sampler_n_atoms_body(s, out); });
+}
+
+static int cgb_sampler_data_sparsity_body(const cgb_sampler *s, float *out)
 {
     CGB_CHECK(s && out, "cgb_sampler_data_sparsity: NULL argument");
     *out = s->dataSparsity;
     return CGB_OK;
 }
 
-extern "C" int cgb_sampler_average_queue_length(const cgb_sampler *s, float *out)
+extern "C" int cgb_sampler_data_sparsity(const cgb_sampler *s, float *out)
+{
+    return guarded("cgb_sampler_data_sparsity", [&]() { return cgb_sampler_data_sparsity_body(s, out); });
+}
+
+static int cgb_sampler_average_queue_length_body(const cgb_sampler *s, float *out)
 {
     CGB_CHECK(s && out, "cgb_sampler_average_queue_length: NULL argument");
     *out = s->avgQueueLength;
     return CGB_OK;
 }
 
-extern "C" int cgb_sampler_get_matrix(const cgb_sampler *s, float *out)
+extern "C" int cgb_sampler_average_queue_length(const cgb_sampler *s, float *out)
+{
+    return guarded("cgb_sampler_average_queue_length", [&]() { return cgb_sampler_average_queue_length_body(s, out); });
+}
+
+static int cgb_sampler_get_matrix_body(const cgb_sampler *s, float *out)
 {
     CGB_CHECK(s && out, "cgb_sampler_get_matrix: NULL argument");
     CGB_CUDA(cudaSetDevice(s->device));
@@ -1889,7 +2033,12 @@ extern "C" int cgb_sampler_get_matrix(const cgb_sampler *s, float *out)
     return CGB_OK;
 }
 
-extern "C" int cgb_sampler_shape(const cgb_sampler *s, uint32_t *rows, uint32_t *nPatterns, uint32_t *rowLength)
+extern "C" int cgb_sampler_get_matrix(const cgb_sampler *s, float *out)
+{
+    return guarded("cgb_sampler_get_matrix", [&]() { return cgb_sampler_get_matrix_body(s, out); });
+}
+
+static int cgb_sampler_shape_body(const cgb_sampler *s, uint32_t *rows, uint32_t *nPatterns, uint32_t *rowLength)
 {
     CGB_CHECK(s != nullptr, "cgb_sampler_shape: NULL sampler");
     if (rows) { *rows = s->nRows; }
@@ -1898,7 +2047,12 @@ extern "C" int cgb_sampler_shape(const cgb_sampler *s, uint32_t *rows, uint32_t 
     return CGB_OK;
 }
 
-extern "C" int cgb_sampler_lambda(const cgb_sampler *s, float *lambda, float *maxGibbsMass)
+extern "C" int cgb_sampler_shape(const cgb_sampler *s, uint32_t *rows, uint32_t *nPatterns, uint32_t *rowLength)
+{
+    return guarded("cgb_sampler_shape", [&]() { return cgb_sampler_shape_body(s, rows, nPatterns, rowLength); });
+}
+
+static int cgb_sampler_lambda_body(const cgb_sampler *s, float *lambda, float *maxGibbsMass)
 {
     CGB_CHECK(s != nullptr, "cgb_sampler_lambda: NULL sampler");
     if (lambda) { *lambda = s->lambda; }
@@ -1906,7 +2060,12 @@ extern "C" int cgb_sampler_lambda(const cgb_sampler *s, float *lambda, float *ma
     return CGB_OK;
 }
 
-extern "C" int cgb_sampler_get_atoms(const cgb_sampler *s, uint64_t *pos, float *mass, uint64_t capacity, uint64_t *count)
+extern "C" int cgb_sampler_lambda(const cgb_sampler *s, float *lambda, float *maxGibbsMass)
+{
+    return guarded("cgb_sampler_lambda", [&]() { return cgb_sampler_lambda_body(s, lambda, maxGibbsMass); });
+}
+
+static int cgb_sampler_get_atoms_body(const cgb_sampler *s, uint64_t *pos, float *mass, uint64_t capacity, uint64_t *count)
 {
     CGB_CHECK(s && count, "cgb_sampler_get_atoms: NULL argument");
     *count = s->domain.size();
@@ -1923,7 +2082,12 @@ extern "C" int cgb_sampler_get_atoms(const cgb_sampler *s, uint64_t *pos, float 
     return CGB_OK;
 }
 
-extern "C" int cgb_sampler_get_ap_row(const cgb_sampler *s, uint32_t row, float *out)
+extern "C" int cgb_sampler_get_atoms(const cgb_sampler *s, uint64_t *pos, float *mass, uint64_t capacity, uint64_t *count)
+{
+    return guarded("cgb_sampler_get_atoms", [&]() { return cgb_sampler_get_atoms_body(s, pos, mass, capacity, count); });
+}
+
+static int cgb_sampler_get_ap_row_body(const cgb_sampler *s, uint32_t row, float *out)
 {
     CGB_CHECK(s && out && row < s->nRows, "cgb_sampler_get_ap_row: bad argument");
     if (s->sparse) { return fail(CGB_EUNSUPPORTED, "cgb_sampler_get_ap_row: the sparse model keeps no AP matrix"); }
@@ -1933,28 +2097,48 @@ extern "C" int cgb_sampler_get_ap_row(const cgb_sampler *s, uint32_t row, float 
     return CGB_OK;
 }
 
-extern "C" int cgb_sampler_get_counters(const cgb_sampler *s, cgb_sampler_counters *out)
+extern "C" int cgb_sampler_get_ap_row(const cgb_sampler *s, uint32_t row, float *out)
+{
+    return guarded("cgb_sampler_get_ap_row", [&]() { return cgb_sampler_get_ap_row_body(s, row, out); });
+}
+
+static int cgb_sampler_get_counters_body(const cgb_sampler *s, cgb_sampler_counters *out)
 {
     CGB_CHECK(s && out, "cgb_sampler_get_counters: NULL argument");
     *out = s->counters;
     return CGB_OK;
 }
 
-extern "C" int cgb_sampler_reset_counters(cgb_sampler *s)
+extern "C" int cgb_sampler_get_counters(const cgb_sampler *s, cgb_sampler_counters *out)
+{
+    return guarded("cgb_sampler_get_counters", [&]() { return cgb_sampler_get_counters_body(s, out); });
+}
+
+static int cgb_sampler_reset_counters_body(cgb_sampler *s)
 {
     CGB_CHECK(s != nullptr, "cgb_sampler_reset_counters: NULL sampler");
     std::memset(static_cast<void*>(&s->counters), 0, sizeof(s->counters));
     return CGB_OK;
 }
 
-extern "C" int cgb_sampler_set_kernel_timing(cgb_sampler *s, int32_t enabled)
+extern "C" int cgb_sampler_reset_counters(cgb_sampler *s)
+{
+    return guarded("cgb_sampler_reset_counters", [&]() { return cgb_sampler_reset_counters_body(s); });
+}
+
+static int cgb_sampler_set_kernel_timing_body(cgb_sampler *s, int32_t enabled)
 {
     CGB_CHECK(s != nullptr, "cgb_sampler_set_kernel_timing: NULL sampler");
     s->timeKernels = enabled != 0;
     return CGB_OK;
 }
 
-extern "C" int cgb_sampler_set_persistent(cgb_sampler *s, int32_t enabled)
+extern "C" int cgb_sampler_set_kernel_timing(cgb_sampler *s, int32_t enabled)
+{
+    return guarded("cgb_sampler_set_kernel_timing", [&]() { return cgb_sampler_set_kernel_timing_body(s, enabled); });
+}
+
+static int cgb_sampler_set_persistent_body(cgb_sampler *s, int32_t enabled)
 {
     CGB_CHECK(s != nullptr, "cgb_sampler_set_persistent: NULL sampler");
     CGB_CHECK(!s->persistentRunning, "cgb_sampler_set_persistent: called in the middle of an update");
@@ -1962,7 +2146,12 @@ extern "C" int cgb_sampler_set_persistent(cgb_sampler *s, int32_t enabled)
     return CGB_OK;
 }
 
-extern "C" int cgb_sampler_reduction_order(const cgb_sampler *s, cgb_reduction_order *out)
+extern "C" int cgb_sampler_set_persistent(cgb_sampler *s, int32_t enabled)
+{
+    return guarded("cgb_sampler_set_persistent", [&]() { return cgb_sampler_set_persistent_body(s, enabled); });
+}
+
+static int cgb_sampler_reduction_order_body(const cgb_sampler *s, cgb_reduction_order *out)
 {
     CGB_CHECK(s && out, "cgb_sampler_reduction_order: NULL argument");
     out->threadsPerSegment = kThreads;
@@ -1972,12 +2161,22 @@ extern "C" int cgb_sampler_reduction_order(const cgb_sampler *s, cgb_reduction_o
     return CGB_OK;
 }
 
-extern "C" int cgb_sampler_device_matrix(const cgb_sampler *s, void **dev, uint64_t *ld)
+extern "C" int cgb_sampler_reduction_order(const cgb_sampler *s, cgb_reduction_order *out)
+{
+    return guarded("cgb_sampler_reduction_order", [&]() { return cgb_sampler_reduction_order_body(s, out); });
+}
+
+static int cgb_sampler_device_matrix_body(const cgb_sampler *s, void **dev, uint64_t *ld)
 {
     CGB_CHECK(s && dev && ld, "cgb_sampler_device_matrix: NULL argument");
     *dev = s->dM;
     *ld = s->ldM;
     return CGB_OK;
+}
+
+extern "C" int cgb_sampler_device_matrix(const cgb_sampler *s, void **dev, uint64_t *ld)
+{
+    return guarded("cgb_sampler_device_matrix", [&]() { return cgb_sampler_device_matrix_body(s, dev, ld); });
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -2000,7 +2199,7 @@ extern "C" void cgb_stats_destroy(cgb_stats *st)
     delete st;
 }
 
-extern "C" int cgb_stats_create(uint32_t nGenes, uint32_t nSamples, uint32_t nPatterns, cgb_stats **out)
+static int cgb_stats_create_body(uint32_t nGenes, uint32_t nSamples, uint32_t nPatterns, cgb_stats **out)
 {
     CGB_CHECK(out && nGenes && nSamples && nPatterns, "cgb_stats_create: bad argument");
     CGB_TRY(ensureDevice());
@@ -2036,6 +2235,11 @@ extern "C" int cgb_stats_create(uint32_t nGenes, uint32_t nSamples, uint32_t nPa
     return CGB_OK;
 }
 
+extern "C" int cgb_stats_create(uint32_t nGenes, uint32_t nSamples, uint32_t nPatterns, cgb_stats **out)
+{
+    return guarded("cgb_stats_create", [&]() { return cgb_stats_create_body(nGenes, nSamples, nPatterns, out); });
+}
+
 // mode 0: update (both, P normalised by its column max); 1: updateA; 2: updateP (norm forced to 1)
 static int statsUpdate(cgb_stats *st, const cgb_sampler *A, const cgb_sampler *P, int mode)
 {
@@ -2064,11 +2268,11 @@ static int statsUpdate(cgb_stats *st, const cgb_sampler *A, const cgb_sampler *P
     return CGB_OK;
 }
 
-extern "C" int cgb_stats_update(cgb_stats *st, const cgb_sampler *A, const cgb_sampler *P) { return statsUpdate(st, A, P, 0); }
-extern "C" int cgb_stats_update_a(cgb_stats *st, const cgb_sampler *A, const cgb_sampler *P) { return statsUpdate(st, A, P, 1); }
-extern "C" int cgb_stats_update_p(cgb_stats *st, const cgb_sampler *A, const cgb_sampler *P) { return statsUpdate(st, A, P, 2); }
+extern "C" int cgb_stats_update(cgb_stats *st, const cgb_sampler *A, const cgb_sampler *P) { return guarded("cgb_stats_update", [&]() { return statsUpdate(st, A, P, 0); }); }
+extern "C" int cgb_stats_update_a(cgb_stats *st, const cgb_sampler *A, const cgb_sampler *P) { return guarded("cgb_stats_update_a", [&]() { return statsUpdate(st, A, P, 1); }); }
+extern "C" int cgb_stats_update_p(cgb_stats *st, const cgb_sampler *A, const cgb_sampler *P) { return guarded("cgb_stats_update_p", [&]() { return statsUpdate(st, A, P, 2); }); }
 
-extern "C" int cgb_stats_update_pump(cgb_stats *st, const cgb_sampler *A)
+static int cgb_stats_update_pump_body(cgb_stats *st, const cgb_sampler *A)
 {
     CGB_CHECK(st && A && A->nRows == st->nGenes, "cgb_stats_update_pump: bad argument");
     CGB_CUDA(cudaSetDevice(st->device));
@@ -2078,6 +2282,11 @@ extern "C" int cgb_stats_update_pump(cgb_stats *st, const cgb_sampler *A)
     CGB_CUDA(cudaGetLastError());
     CGB_CUDA(cudaStreamSynchronize(A->stream));
     return CGB_OK;
+}
+
+extern "C" int cgb_stats_update_pump(cgb_stats *st, const cgb_sampler *A)
+{
+    return guarded("cgb_stats_update_pump", [&]() { return cgb_stats_update_pump_body(st, A); });
 }
 
 static int downloadFactor(const float *dev, uint32_t rows, uint32_t k, uint32_t ld, std::vector<float> &host)
@@ -2124,18 +2333,23 @@ static int statsSd(const cgb_stats *st, const float *devMean, const float *devSq
     return CGB_OK;
 }
 
-extern "C" int cgb_stats_amean(const cgb_stats *st, float *out) { return statsMean(st, st ? st->dAmean : nullptr, st ? st->nGenes : 0, st ? st->ldA : 0, st ? static_cast<float>(st->statUpdates) : 1.f, out); }
-extern "C" int cgb_stats_pmean(const cgb_stats *st, float *out) { return statsMean(st, st ? st->dPmean : nullptr, st ? st->nSamples : 0, st ? st->ldP : 0, st ? static_cast<float>(st->statUpdates) : 1.f, out); }
-extern "C" int cgb_stats_asd(const cgb_stats *st, float *out) { return statsSd(st, st ? st->dAmean : nullptr, st ? st->dAsq : nullptr, st ? st->nGenes : 0, st ? st->ldA : 0, out); }
-extern "C" int cgb_stats_psd(const cgb_stats *st, float *out) { return statsSd(st, st ? st->dPmean : nullptr, st ? st->dPsq : nullptr, st ? st->nSamples : 0, st ? st->ldP : 0, out); }
+extern "C" int cgb_stats_amean(const cgb_stats *st, float *out) { return guarded("cgb_stats_amean", [&]() { return statsMean(st, st ? st->dAmean : nullptr, st ? st->nGenes : 0, st ? st->ldA : 0, st ? static_cast<float>(st->statUpdates) : 1.f, out); }); }
+extern "C" int cgb_stats_pmean(const cgb_stats *st, float *out) { return guarded("cgb_stats_pmean", [&]() { return statsMean(st, st ? st->dPmean : nullptr, st ? st->nSamples : 0, st ? st->ldP : 0, st ? static_cast<float>(st->statUpdates) : 1.f, out); }); }
+extern "C" int cgb_stats_asd(const cgb_stats *st, float *out) { return guarded("cgb_stats_asd", [&]() { return statsSd(st, st ? st->dAmean : nullptr, st ? st->dAsq : nullptr, st ? st->nGenes : 0, st ? st->ldA : 0, out); }); }
+extern "C" int cgb_stats_psd(const cgb_stats *st, float *out) { return guarded("cgb_stats_psd", [&]() { return statsSd(st, st ? st->dPmean : nullptr, st ? st->dPsq : nullptr, st ? st->nSamples : 0, st ? st->ldP : 0, out); }); }
 
-extern "C" int cgb_stats_pump_matrix(const cgb_stats *st, float *out)
+static int cgb_stats_pump_matrix_body(const cgb_stats *st, float *out)
 {
     const float denom = (st && st->pumpUpdates != 0) ? static_cast<float>(st->pumpUpdates) : 1.f;
     return statsMean(st, st ? st->dPump : nullptr, st ? st->nGenes : 0, st ? st->ldA : 0, denom, out);
 }
 
-extern "C" int cgb_stats_mean_pattern(const cgb_stats *cst, float *out)
+extern "C" int cgb_stats_pump_matrix(const cgb_stats *st, float *out)
+{
+    return guarded("cgb_stats_pump_matrix", [&]() { return cgb_stats_pump_matrix_body(st, out); });
+}
+
+static int cgb_stats_mean_pattern_body(const cgb_stats *cst, float *out)
 {
     CGB_CHECK(cst && out, "cgb_stats_mean_pattern: NULL argument");
     cgb_stats *st = const_cast<cgb_stats*>(cst);
@@ -2149,7 +2363,12 @@ extern "C" int cgb_stats_mean_pattern(const cgb_stats *cst, float *out)
     return statsMean(st, st->dScratch, st->nGenes, st->ldA, 1.f, out);
 }
 
-extern "C" int cgb_stats_mean_chisq(const cgb_stats *st, const cgb_sampler *cP, float *out)
+extern "C" int cgb_stats_mean_pattern(const cgb_stats *cst, float *out)
+{
+    return guarded("cgb_stats_mean_pattern", [&]() { return cgb_stats_mean_pattern_body(cst, out); });
+}
+
+static int cgb_stats_mean_chisq_body(const cgb_stats *st, const cgb_sampler *cP, float *out)
 {
     CGB_CHECK(st && cP && out, "cgb_stats_mean_chisq: NULL argument");
     cgb_sampler *P = const_cast<cgb_sampler*>(cP);
@@ -2167,7 +2386,12 @@ extern "C" int cgb_stats_mean_chisq(const cgb_stats *st, const cgb_sampler *cP, 
     return CGB_OK;
 }
 
-extern "C" int cgb_stats_device_sums(const cgb_stats *st, void **AmeanSum, void **AsqSum, void **PmeanSum,
+extern "C" int cgb_stats_mean_chisq(const cgb_stats *st, const cgb_sampler *cP, float *out)
+{
+    return guarded("cgb_stats_mean_chisq", [&]() { return cgb_stats_mean_chisq_body(st, cP, out); });
+}
+
+static int cgb_stats_device_sums_body(const cgb_stats *st, void **AmeanSum, void **AsqSum, void **PmeanSum,
                                      void **PsqSum, uint64_t *ldA, uint64_t *ldP, uint32_t *nUpdates)
 {
     CGB_CHECK(st != nullptr, "cgb_stats_device_sums: NULL stats");
@@ -2181,8 +2405,14 @@ extern "C" int cgb_stats_device_sums(const cgb_stats *st, void **AmeanSum, void 
     return CGB_OK;
 }
 
+extern "C" int cgb_stats_device_sums(const cgb_stats *st, void **AmeanSum, void **AsqSum, void **PmeanSum,
+                                     void **PsqSum, uint64_t *ldA, uint64_t *ldP, uint32_t *nUpdates)
+{
+    return guarded("cgb_stats_device_sums", [&]() { return cgb_stats_device_sums_body(st, AmeanSum, AsqSum, PmeanSum, PsqSum, ldA, ldP, nUpdates); });
+}
+
 // device portable-log probe (tests)
-extern "C" int cgb_debug_logf(const float *in, float *out, uint32_t n)
+static int cgb_debug_logf_body(const float *in, float *out, uint32_t n)
 {
     CGB_CHECK(in && out, "cgb_debug_logf: NULL argument");
     CGB_TRY(ensureDevice());
@@ -2197,6 +2427,11 @@ extern "C" int cgb_debug_logf(const float *in, float *out, uint32_t n)
     cudaFree(dIn);
     cudaFree(dOut);
     return CGB_OK;
+}
+
+extern "C" int cgb_debug_logf(const float *in, float *out, uint32_t n)
+{
+    return guarded("cgb_debug_logf", [&]() { return cgb_debug_logf_body(in, out, n); });
 }
 
 // host-logic probe: the generator's multiply-high division (atomic_domain.h FastDivU64) against the hardware divide
@@ -2358,7 +2593,7 @@ static int copyOut(const std::vector<uint8_t> &bytes, void *buf, uint64_t capaci
     return CGB_OK;
 }
 
-extern "C" int cgb_sampler_serialize(const cgb_sampler *s, void *buf, uint64_t capacity, uint64_t *size)
+static int cgb_sampler_serialize_body(const cgb_sampler *s, void *buf, uint64_t capacity, uint64_t *size)
 {
     CGB_CHECK(s && size, "cgb_sampler_serialize: NULL argument");
     SamplerImage img;
@@ -2368,7 +2603,12 @@ extern "C" int cgb_sampler_serialize(const cgb_sampler *s, void *buf, uint64_t c
     return copyOut(w.bytes(), buf, capacity, size, "cgb_sampler_serialize");
 }
 
-extern "C" int cgb_sampler_deserialize(cgb_sampler *s, const void *buf, uint64_t size)
+extern "C" int cgb_sampler_serialize(const cgb_sampler *s, void *buf, uint64_t capacity, uint64_t *size)
+{
+    return guarded("cgb_sampler_serialize", [&]() { return cgb_sampler_serialize_body(s, buf, capacity, size); });
+}
+
+static int cgb_sampler_deserialize_body(cgb_sampler *s, const void *buf, uint64_t size)
 {
     CGB_CHECK(s && buf, "cgb_sampler_deserialize: NULL argument");
     SamplerImage img;
@@ -2379,14 +2619,24 @@ extern "C" int cgb_sampler_deserialize(cgb_sampler *s, const void *buf, uint64_t
     return imageToSampler(s, img);
 }
 
-extern "C" int cgb_sampler_set_atoms(cgb_sampler *s, const uint64_t *pos, const float *mass, uint64_t n)
+extern "C" int cgb_sampler_deserialize(cgb_sampler *s, const void *buf, uint64_t size)
+{
+    return guarded("cgb_sampler_deserialize", [&]() { return cgb_sampler_deserialize_body(s, buf, size); });
+}
+
+static int cgb_sampler_set_atoms_body(cgb_sampler *s, const uint64_t *pos, const float *mass, uint64_t n)
 {
     CGB_CHECK(s && (n == 0 || (pos && mass)), "cgb_sampler_set_atoms: NULL argument");
     CGB_CHECK(!s->persistentRunning, "cgb_sampler_set_atoms: called in the middle of an update");
     return setAtoms(s, pos, mass, n);
 }
 
-extern "C" int cgb_stats_serialize(const cgb_stats *st, void *buf, uint64_t capacity, uint64_t *size)
+extern "C" int cgb_sampler_set_atoms(cgb_sampler *s, const uint64_t *pos, const float *mass, uint64_t n)
+{
+    return guarded("cgb_sampler_set_atoms", [&]() { return cgb_sampler_set_atoms_body(s, pos, mass, n); });
+}
+
+static int cgb_stats_serialize_body(const cgb_stats *st, void *buf, uint64_t capacity, uint64_t *size)
 {
     CGB_CHECK(st && size, "cgb_stats_serialize: NULL argument");
     StatsImage img;
@@ -2396,7 +2646,12 @@ extern "C" int cgb_stats_serialize(const cgb_stats *st, void *buf, uint64_t capa
     return copyOut(w.bytes(), buf, capacity, size, "cgb_stats_serialize");
 }
 
-extern "C" int cgb_stats_deserialize(cgb_stats *st, const void *buf, uint64_t size)
+extern "C" int cgb_stats_serialize(const cgb_stats *st, void *buf, uint64_t capacity, uint64_t *size)
+{
+    return guarded("cgb_stats_serialize", [&]() { return cgb_stats_serialize_body(st, buf, capacity, size); });
+}
+
+static int cgb_stats_deserialize_body(cgb_stats *st, const void *buf, uint64_t size)
 {
     CGB_CHECK(st && buf, "cgb_stats_deserialize: NULL argument");
     StatsImage img;
@@ -2407,35 +2662,60 @@ extern "C" int cgb_stats_deserialize(cgb_stats *st, const void *buf, uint64_t si
     return imageToStats(st, img);
 }
 
-extern "C" int cgb_randstate_get_state(const cgb_randstate *rs, uint64_t state[2])
+extern "C" int cgb_stats_deserialize(cgb_stats *st, const void *buf, uint64_t size)
+{
+    return guarded("cgb_stats_deserialize", [&]() { return cgb_stats_deserialize_body(st, buf, size); });
+}
+
+static int cgb_randstate_get_state_body(const cgb_randstate *rs, uint64_t state[2])
 {
     CGB_CHECK(rs && state, "cgb_randstate_get_state: NULL argument");
     rs->seeder.getState(state);
     return CGB_OK;
 }
 
-extern "C" int cgb_randstate_set_state(cgb_randstate *rs, const uint64_t state[2])
+extern "C" int cgb_randstate_get_state(const cgb_randstate *rs, uint64_t state[2])
+{
+    return guarded("cgb_randstate_get_state", [&]() { return cgb_randstate_get_state_body(rs, state); });
+}
+
+static int cgb_randstate_set_state_body(cgb_randstate *rs, const uint64_t state[2])
 {
     CGB_CHECK(rs && state, "cgb_randstate_set_state: NULL argument");
     rs->seeder.setState(state);
     return CGB_OK;
 }
 
-extern "C" int cgb_rng_get_state(const cgb_rng *r, uint64_t *state)
+extern "C" int cgb_randstate_set_state(cgb_randstate *rs, const uint64_t state[2])
+{
+    return guarded("cgb_randstate_set_state", [&]() { return cgb_randstate_set_state_body(rs, state); });
+}
+
+static int cgb_rng_get_state_body(const cgb_rng *r, uint64_t *state)
 {
     CGB_CHECK(r && state, "cgb_rng_get_state: NULL argument");
     *state = r->rng.state;
     return CGB_OK;
 }
 
-extern "C" int cgb_rng_set_state(cgb_rng *r, uint64_t state)
+extern "C" int cgb_rng_get_state(const cgb_rng *r, uint64_t *state)
+{
+    return guarded("cgb_rng_get_state", [&]() { return cgb_rng_get_state_body(r, state); });
+}
+
+static int cgb_rng_set_state_body(cgb_rng *r, uint64_t state)
 {
     CGB_CHECK(r != nullptr, "cgb_rng_set_state: NULL argument");
     r->rng.state = state;
     return CGB_OK;
 }
 
-extern "C" int cgb_checkpoint_info_read(const char *path, cgb_checkpoint_info *out)
+extern "C" int cgb_rng_set_state(cgb_rng *r, uint64_t state)
+{
+    return guarded("cgb_rng_set_state", [&]() { return cgb_rng_set_state_body(r, state); });
+}
+
+static int cgb_checkpoint_info_read_body(const char *path, cgb_checkpoint_info *out)
 {
     CGB_CHECK(path && out, "cgb_checkpoint_info_read: NULL argument");
     CGB_CHECK(out->struct_size == sizeof(cgb_checkpoint_info), "cgb_checkpoint_info_read: cgb_checkpoint_info ABI mismatch");
@@ -2465,7 +2745,12 @@ extern "C" int cgb_checkpoint_info_read(const char *path, cgb_checkpoint_info *o
     return CGB_OK;
 }
 
-extern "C" int cgb_checkpoint_rewrite(const char *inPath, const char *outPath)
+extern "C" int cgb_checkpoint_info_read(const char *path, cgb_checkpoint_info *out)
+{
+    return guarded("cgb_checkpoint_info_read", [&]() { return cgb_checkpoint_info_read_body(path, out); });
+}
+
+static int cgb_checkpoint_rewrite_body(const char *inPath, const char *outPath)
 {
     CGB_CHECK(inPath && outPath, "cgb_checkpoint_rewrite: NULL argument");
     CheckpointImage c;
@@ -2473,6 +2758,11 @@ extern "C" int cgb_checkpoint_rewrite(const char *inPath, const char *outPath)
     if (!readCheckpointFile(inPath, c, err)) { return fail(CGB_EINVAL, std::string("cgb_checkpoint_rewrite: ") + inPath + ": " + err); }
     if (!writeCheckpointFile(outPath, c, err)) { return fail(CGB_EINVAL, "cgb_checkpoint_rewrite: " + err); }
     return CGB_OK;
+}
+
+extern "C" int cgb_checkpoint_rewrite(const char *inPath, const char *outPath)
+{
+    return guarded("cgb_checkpoint_rewrite", [&]() { return cgb_checkpoint_rewrite_body(inPath, outPath); });
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -2498,12 +2788,17 @@ struct RunGuard
 
 static const float *g_tableOverride[3] = {nullptr, nullptr, nullptr};
 // tables used by cgb_run for the GapsRandomState it creates internally (NULLs restore the built-ins)
-extern "C" int cgb_run_set_tables(const float *erf, const float *erfinv, const float *qgamma)
+static int cgb_run_set_tables_body(const float *erf, const float *erfinv, const float *qgamma)
 {
     g_tableOverride[0] = erf;
     g_tableOverride[1] = erfinv;
     g_tableOverride[2] = qgamma;
     return CGB_OK;
+}
+
+extern "C" int cgb_run_set_tables(const float *erf, const float *erfinv, const float *qgamma)
+{
+    return guarded("cgb_run_set_tables", [&]() { return cgb_run_set_tables_body(erf, erfinv, qgamma); });
 }
 
 // createCheckpoint (GapsRunner.cpp:226-256): archive the run, then rebuild AP from the factors so that the chain
@@ -2537,10 +2832,16 @@ static int createCheckpoint(const cgb_params *p, uint32_t nGenes, uint32_t nSamp
     return CGB_OK;
 }
 
-extern "C" int cgb_run(const float *data, uint32_t nrow, uint32_t ncol, int32_t colmajor,
+static int cgb_run_body(const float *data, uint32_t nrow, uint32_t ncol, int32_t colmajor,
                        const float *uncertainty, const cgb_params *p, cgb_result *r)
 {
     return cgb_run_ex(data, nrow, ncol, colmajor, uncertainty, p, nullptr, r);
+}
+
+extern "C" int cgb_run(const float *data, uint32_t nrow, uint32_t ncol, int32_t colmajor,
+                       const float *uncertainty, const cgb_params *p, cgb_result *r)
+{
+    return guarded("cgb_run", [&]() { return cgb_run_body(data, nrow, ncol, colmajor, uncertainty, p, r); });
 }
 
 // both orientations of a Matrix-Market file in compressed rows (see cgb_run_file)
@@ -2553,11 +2854,17 @@ struct CsrPair
 static int runCore(const float *data, const CsrPair *csr, uint32_t nrow, uint32_t ncol, int32_t colmajor, const float *uncertainty,
                    const cgb_params *p0, const cgb_run_options *opt, cgb_result *r);
 
-extern "C" int cgb_run_ex(const float *data, uint32_t nrow, uint32_t ncol, int32_t colmajor, const float *uncertainty,
+static int cgb_run_ex_body(const float *data, uint32_t nrow, uint32_t ncol, int32_t colmajor, const float *uncertainty,
                           const cgb_params *p0, const cgb_run_options *opt, cgb_result *r)
 {
     CGB_CHECK(data != nullptr, "cgb_run: NULL argument");
     return runCore(data, nullptr, nrow, ncol, colmajor, uncertainty, p0, opt, r);
+}
+
+extern "C" int cgb_run_ex(const float *data, uint32_t nrow, uint32_t ncol, int32_t colmajor, const float *uncertainty,
+                          const cgb_params *p0, const cgb_run_options *opt, cgb_result *r)
+{
+    return guarded("cgb_run_ex", [&]() { return cgb_run_ex_body(data, nrow, ncol, colmajor, uncertainty, p0, opt, r); });
 }
 
 static int runCore(const float *data, const CsrPair *csr, uint32_t nrow, uint32_t ncol, int32_t colmajor, const float *uncertainty,
@@ -2632,10 +2939,16 @@ static int runCore(const float *data, const CsrPair *csr, uint32_t nrow, uint32_
         std::string errP;
         std::thread prepP([&]()
         {
-            rcP = samplerCreateImpl(data, nrow, ncol, colmajor, p->transposeData, p->subsetGenes, p->alphaP, p->maxGibbsMassP, p, g.rs, false, &g.P, pubP, twinP, csrP);
-            if (rcP != CGB_OK) { errP = g_lastError; }
+            rcP = guarded("cgb_run (P sampler)", [&]() { return samplerCreateImpl(data, nrow, ncol, colmajor, p->transposeData, p->subsetGenes, p->alphaP, p->maxGibbsMassP, p, g.rs, false, &g.P, pubP, twinP, csrP); });
+            if (rcP != CGB_OK)
+            {
+                errP = g_lastError;
+                if (pubP && pubP->state.load() == 0) { pubP->state.store(-1); } // never leave the twin waiting
+            }
         });
-        const int rcA = samplerCreateImpl(data, nrow, ncol, colmajor, !p->transposeData, !p->subsetGenes, p->alphaA, p->maxGibbsMassA, p, g.rs, false, &g.A, pubA, twinA, csrA);
+        struct JoinOnExit { std::thread &t; ~JoinOnExit() { if (t.joinable()) { t.join(); } } } joinP = {prepP};
+        const int rcA = guarded("cgb_run (A sampler)", [&]() { return samplerCreateImpl(data, nrow, ncol, colmajor, !p->transposeData, !p->subsetGenes, p->alphaA, p->maxGibbsMassA, p, g.rs, false, &g.A, pubA, twinA, csrA); });
+        if (rcA != CGB_OK && pubA && pubA->state.load() == 0) { pubA->state.store(-1); }
         prepP.join();
         if (rcA != CGB_OK) { return rcA; }
         if (rcP != CGB_OK) { return fail(rcP, errP); }
@@ -2834,7 +3147,7 @@ static bool loadMtxCsrPair(const char *path, CsrPair &pair, uint32_t &nrow, uint
 
 /* Host only: the compressed rows (byRows != 0) or compressed columns of a Matrix-Market file as the sparse model's
  * loader builds them.  ptr has nMajor + 1 entries; idx / val are written when non-NULL and large enough. */
-extern "C" int cgb_read_matrix_csr(const char *path, int32_t byRows, uint32_t *nrow, uint32_t *ncol, uint32_t *ptr,
+static int cgb_read_matrix_csr_body(const char *path, int32_t byRows, uint32_t *nrow, uint32_t *ncol, uint32_t *ptr,
                                    uint64_t ptrCapacity, uint32_t *idx, float *val, uint64_t capacity, uint64_t *nnz)
 {
     CGB_CHECK(path && nrow && ncol && nnz, "cgb_read_matrix_csr: NULL argument");
@@ -2864,7 +3177,13 @@ extern "C" int cgb_read_matrix_csr(const char *path, int32_t byRows, uint32_t *n
     return CGB_OK;
 }
 
-extern "C" int cgb_read_matrix_file(const char *path, float *out, uint64_t capacity, uint32_t *nrow, uint32_t *ncol)
+extern "C" int cgb_read_matrix_csr(const char *path, int32_t byRows, uint32_t *nrow, uint32_t *ncol, uint32_t *ptr,
+                                   uint64_t ptrCapacity, uint32_t *idx, float *val, uint64_t capacity, uint64_t *nnz)
+{
+    return guarded("cgb_read_matrix_csr", [&]() { return cgb_read_matrix_csr_body(path, byRows, nrow, ncol, ptr, ptrCapacity, idx, val, capacity, nnz); });
+}
+
+static int cgb_read_matrix_file_body(const char *path, float *out, uint64_t capacity, uint32_t *nrow, uint32_t *ncol)
 {
     CGB_CHECK(path && nrow && ncol, "cgb_read_matrix_file: NULL argument");
     std::vector<float> m;
@@ -2878,7 +3197,12 @@ extern "C" int cgb_read_matrix_file(const char *path, float *out, uint64_t capac
     return CGB_OK;
 }
 
-extern "C" int cgb_run_file(const char *dataPath, const char *uncertaintyPath, const cgb_params *p, cgb_result *r)
+extern "C" int cgb_read_matrix_file(const char *path, float *out, uint64_t capacity, uint32_t *nrow, uint32_t *ncol)
+{
+    return guarded("cgb_read_matrix_file", [&]() { return cgb_read_matrix_file_body(path, out, capacity, nrow, ncol); });
+}
+
+static int cgb_run_file_body(const char *dataPath, const char *uncertaintyPath, const cgb_params *p, cgb_result *r)
 {
     CGB_CHECK(dataPath && p && r, "cgb_run_file: NULL argument");
     CGB_CHECK(p->struct_size == sizeof(cgb_params), "cgb_run_file: cgb_params ABI mismatch");
@@ -2917,4 +3241,9 @@ extern "C" int cgb_run_file(const char *dataPath, const char *uncertaintyPath, c
         q.subsetIndices = sorted.data();
     }
     return cgb_run(data.data(), nrow, ncol, 0, haveUnc ? unc.data() : nullptr, &q, r);
+}
+
+extern "C" int cgb_run_file(const char *dataPath, const char *uncertaintyPath, const cgb_params *p, cgb_result *r)
+{
+    return guarded("cgb_run_file", [&]() { return cgb_run_file_body(dataPath, uncertaintyPath, p, r); });
 }
