@@ -81,25 +81,65 @@ class CogapsParams(object):
                 raise ValueError("can't fix P matrix when running single-cell CoGAPS")
             if self.distributed == "genome-wide" and self.whichMatrixFixed == "A":
                 raise ValueError("can't fix A matrix when running genome-wide CoGAPS")
+            if self.fixedPatterns is not None and self.explicitSets is None:
+                raise ValueError("doing manual pattern matching without using explicit subsets")
+            nGroups = len(set(self.samplingAnnotation)) if self.samplingAnnotation is not None else 0
+            nWeights = len(self.samplingWeight) if self.samplingWeight is not None else 0
+            if nGroups != nWeights:
+                raise ValueError("samplingWeight has mismatched size with amount of distinct annotations")
             if self.cut > self.nPatterns:
                 raise ValueError("cut must be less than or equal to nPatterns")
+            if nWeights and not hasattr(self.samplingWeight, "keys"):
+                raise ValueError("samplingWeight must be a named vector")
+            if self.explicitSets is not None:
+                if not isinstance(self.explicitSets, (list, tuple)):
+                    raise ValueError("explicitSets must be a list")
+                if len(self.explicitSets) != self.nSets:
+                    raise ValueError("nSets doesn't match length of explicitSets")
+                if self.samplingAnnotation is not None:
+                    raise ValueError("explicitSets and samplingAnnotation/samplingWeight are both set")
+                isChar = [all(isinstance(x, str) for x in s) for s in self.explicitSets]
+                isNum = [all(not isinstance(x, str) for x in s) for s in self.explicitSets]
+                if not all(isNum) and not all(isChar):
+                    raise ValueError("explicitSets must be a list of numeric or character")
         return True
 
     def setParam(self, name, value):
         """setParam, R/methods-CogapsParams.R — nSets/nPatterns re-derive their dependents"""
         if name not in _PARAM_DEFAULTS:
             raise ValueError("invalid slot name %r for CogapsParams" % name)
+        if name in ("samplingAnnotation", "samplingWeight"):
+            raise ValueError("please set '%s' with setAnnotationWeights" % name)       # methods-CogapsParams.R:111-114
+        before = dict(self.__dict__)                  # R objects have value semantics: a rejected change leaves no trace
         setattr(self, name, value)
         if name == "nSets":
             self.minNS = int(np.ceil(value / 2.0))
             self.maxNS = self.minNS + value
         if name == "nPatterns":
             self.cut = min(self.cut, value)
-        self.validate()
+        try:
+            self.validate()
+        except ValueError:
+            self.__dict__.clear()
+            self.__dict__.update(before)
+            raise
         return self
 
     def getParam(self, name):
         return getattr(self, name)
+
+    def setAnnotationWeights(self, annotation, weights):
+        """setAnnotationWeights (R/methods-CogapsParams.R:170-187): a label per row (column) being partitioned and a
+        {label: weight} mapping for the weighted subsets of distributed CoGAPS"""
+        before = (self.samplingAnnotation, self.samplingWeight)
+        self.samplingAnnotation = list(annotation)
+        self.samplingWeight = dict(weights)
+        try:
+            self.validate()
+        except ValueError:
+            self.samplingAnnotation, self.samplingWeight = before
+            raise
+        return self
 
     def setFixedPatterns(self, fixedPatterns, whichMatrixFixed):
         self.fixedPatterns = np.asarray(fixedPatterns, dtype=np.float32)

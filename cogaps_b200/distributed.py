@@ -26,14 +26,48 @@ import copy
 import numpy as np
 
 
-def createSets(total, nSets, seed, explicitSets=None):
-    """sampleUniformly / sampleWithExplictSets (R/SubsetData.R:63-116): list of sorted 1-based index arrays."""
+def createSets(total, nSets, seed, explicitSets=None, samplingAnnotation=None, samplingWeight=None, names=None):
+    """createSets (R/SubsetData.R:85-116): list of 1-based index arrays, each sorted.
+
+    explicitSets       sampleWithExplictSets (:8-30): index lists as given, or lists of names looked up in `names`
+                       (geneNames for genome-wide, sampleNames for single-cell) with `which(allNames %in% set)`
+    samplingAnnotation sampleWithAnnotationWeights (:39-58): every set draws floor(total/nSets) group labels with
+                       probability proportional to samplingWeight (a {group: weight} mapping), then that many members
+                       of each group WITH replacement — a set may hold an index more than once, as in the reference
+    otherwise          sampleUniformly (:67-79): a random partition, floor(total/nSets) per set, the rest to the last
+    """
     if explicitSets is not None:
         if len(explicitSets) != nSets:
             raise ValueError("nSets does not match number of explicit sets given")
-        return [np.sort(np.asarray(s, dtype=np.int64)) for s in explicitSets]
+        if all(len(s) and all(isinstance(x, str) for x in s) for s in explicitSets):
+            if names is None:
+                raise ValueError("named explicitSets need geneNames / sampleNames")
+            allNames = np.asarray(list(names), dtype=object)
+            sets = []
+            for s in explicitSets:
+                wanted = set(s)
+                if not wanted.issubset(set(allNames.tolist())):
+                    raise ValueError("some named genes in explicitSets not found")
+                sets.append(np.nonzero(np.array([n in wanted for n in allNames]))[0].astype(np.int64) + 1)
+            return sets
+        return [np.asarray(s, dtype=np.int64) for s in explicitSets]   # returned as given (:13)
     rng = np.random.default_rng(int(seed))
     setSize = total // nSets
+    if samplingAnnotation is not None:
+        annotation = np.asarray(list(samplingAnnotation), dtype=object)
+        if annotation.size != total:
+            raise ValueError("samplingAnnotation must label every row (column) being partitioned")
+        groups = sorted(set(annotation.tolist()))
+        weight = np.array([float(dict(samplingWeight)[g]) for g in groups], dtype=np.float64)   # sorted by name (:42-45)
+        if (weight < 0).any() or weight.sum() <= 0:
+            raise ValueError("samplingWeight must be non-negative and not all zero")
+        members = {g: np.nonzero(annotation == g)[0].astype(np.int64) + 1 for g in groups}
+        sets = []
+        for _ in range(nSets):
+            counts = rng.multinomial(setSize, weight / weight.sum())       # sample(groups, setSize, TRUE, prob=weight)
+            picks = [rng.choice(members[g], size=int(c), replace=True) for g, c in zip(groups, counts)]
+            sets.append(np.sort(np.concatenate(picks)) if picks else np.zeros(0, np.int64))
+        return sets
     remaining = np.arange(1, total + 1, dtype=np.int64)
     sets = []
     for _ in range(nSets - 1):
@@ -201,7 +235,8 @@ def distributedCogaps(data, params, uncertainty=None, nThreads=1, messages=False
     nrow, ncol = data.shape
     subsetRows = bool(transposeData) != genomeWide       # createSets, R/SubsetData.R:87-88
     total = nrow if subsetRows else ncol
-    sets = createSets(total, params.nSets, params.seed, params.explicitSets)
+    sets = createSets(total, params.nSets, params.seed, params.explicitSets, params.samplingAnnotation, params.samplingWeight,
+                      names=params.geneNames if genomeWide else params.sampleNames)
     if min(len(s) for s in sets) < params.nPatterns:
         raise ValueError("data subset dimension less than nPatterns")
     subsetDim = 1 if genomeWide else 2

@@ -159,6 +159,18 @@ def test_sequential_sampler_has_no_checkpoints(oracle):
         cg.CoGAPS(data, nPatterns=3, checkpointInterval=10, asynchronousUpdates=False, messages=False)
 
 
+def test_user_api_checkpoint_arguments_are_validated_like_the_reference():
+    """CoGAPS(checkpointInterval=, checkpointOutFile=, checkpointInFile=) — R/CoGAPS.R:90-156; distributed runs refuse
+    checkpoints (R/HelperFunctions.R:237-238)."""
+    import cogaps_b200 as cg
+    data = load_data("modsim")
+    params = cg.CogapsParams(nPatterns=3, distributed="genome-wide")
+    with pytest.raises(ValueError, match="distributed"):
+        cg.CoGAPS(data, params, checkpointInFile=golden_file("dense"), messages=False)
+    with pytest.raises(ValueError, match="distributed"):
+        cg.CoGAPS(data, params, checkpointInterval=100, messages=False)
+
+
 def test_resuming_with_other_npatterns_is_refused(tmp_path):
     import cogaps_b200 as cg
     with pytest.raises(cg.CogapsError, match="nPatterns differs"):

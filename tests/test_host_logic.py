@@ -180,6 +180,46 @@ def test_create_sets_partitions_like_reference():
         createSets(10, 3, 1, explicitSets=[[1, 2], [3]])
 
 
+def test_create_sets_with_annotation_weights_and_named_sets():
+    """sampleWithAnnotationWeights (R/SubsetData.R:39-58) and named explicit sets (:15-29)."""
+    import cogaps_b200 as cg
+    from cogaps_b200.distributed import createSets
+    annotation = ["b"] * 40 + ["a"] * 50 + ["c"] * 10
+    sets = createSets(100, 4, seed=3, samplingAnnotation=annotation, samplingWeight={"a": 3.0, "c": 1.0, "b": 0.0})
+    assert [len(s) for s in sets] == [25, 25, 25, 25]                      # floor(total / nSets) draws each
+    allidx = np.concatenate(sets)
+    assert allidx.min() >= 41 and allidx.max() <= 100                       # weight 0: group "b" (1..40) never drawn
+    assert all(np.all(np.diff(s) >= 0) for s in sets)                       # sorted, repeats allowed (replace=TRUE)
+    share_a = np.mean((allidx >= 41) & (allidx <= 90))
+    assert 0.55 < share_a < 0.95                                            # about 3:1 in favour of "a"
+    assert all(np.array_equal(x, y) for x, y in zip(sets, createSets(100, 4, seed=3, samplingAnnotation=annotation,
+                                                                      samplingWeight={"a": 3.0, "c": 1.0, "b": 0.0})))
+    names = ["g%d" % i for i in range(1, 11)]
+    sets = createSets(10, 2, seed=1, explicitSets=[["g3", "g1", "g7"], ["g10", "g2"]], names=names)
+    assert [s.tolist() for s in sets] == [[1, 3, 7], [2, 10]]               # which(allNames %in% set)
+    with pytest.raises(ValueError, match="not found"):
+        createSets(10, 2, seed=1, explicitSets=[["g3", "nope"], ["g2"]], names=names)
+    assert [s.tolist() for s in createSets(10, 2, seed=1, explicitSets=[[5, 2, 9], [1]])] == [[5, 2, 9], [1]]  # as given
+
+    # validity rules of the S4 class (R/class-CogapsParams.R:161-189) and the dedicated setter
+    p = cg.CogapsParams(nPatterns=3, distributed="genome-wide")
+    with pytest.raises(ValueError, match="setAnnotationWeights"):
+        p.setParam("samplingWeight", {"a": 1.0})
+    p.setAnnotationWeights(["a", "b", "a"], {"a": 1.0, "b": 2.0})
+    with pytest.raises(ValueError, match="mismatched size"):
+        p.setAnnotationWeights(["a", "b", "a"], {"a": 1.0})
+    p = cg.CogapsParams(nPatterns=3, distributed="single-cell")
+    with pytest.raises(ValueError, match="length of explicitSets"):
+        p.setParam("explicitSets", [[1, 2], [3, 4]])                        # nSets is 4
+    assert p.explicitSets is None                                           # a rejected change leaves no trace
+    p.setParam("nSets", 2)
+    p.setParam("explicitSets", [[1, 2], [3, 4]])
+    with pytest.raises(ValueError, match="numeric or character"):
+        p.setParam("explicitSets", [[1, 2], ["x"]])
+    with pytest.raises(ValueError, match="manual pattern matching"):
+        cg.CogapsParams(nPatterns=3, distributed="single-cell", fixedPatterns=np.ones((4, 3)), whichMatrixFixed="A")
+
+
 def _synthetic_patterns(nSets=4, k=3, length=60, seed=0):
     rng = np.random.default_rng(seed)
     base = rng.gamma(2.0, 1.0, (length, k))
