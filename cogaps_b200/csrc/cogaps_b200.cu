@@ -354,13 +354,17 @@ static void orientData(const float *data, uint32_t nrow, uint32_t ncol, bool col
     }
 }
 
-static int checkSubset(const cgb_params *p, uint32_t nrow, uint32_t ncol)
+// The reference indexes the data with whatever it is given (data_structures/Matrix.cpp:30-69); an index past the
+// end is undefined behaviour there and an error here.  Indices address rows of the caller's matrix when
+// subsetGenes != genesInCols, columns otherwise (orientData below).
+static int checkSubset(const cgb_params *p, uint32_t nrow, uint32_t ncol, bool genesInCols, bool subsetGenes)
 {
+    const uint32_t bound = (subsetGenes != genesInCols) ? nrow : ncol;
     for (uint32_t i = 0; i < p->nSubsetIndices; ++i)
     {
         CGB_CHECK(p->subsetIndices && p->subsetIndices[i] >= 1, "subset indices are 1-based (R convention)");
+        CGB_CHECK(p->subsetIndices[i] <= bound, "subset index past the end of the data");
     }
-    (void)nrow; (void)ncol;
     return CGB_OK;
 }
 
@@ -471,7 +475,7 @@ static int samplerCreateImpl(const float *data, uint32_t nrow, uint32_t ncol, in
               "cgb_sampler_create: compressed-row input is for the sparse model on the whole matrix");
     CGB_CHECK(params->struct_size == sizeof(cgb_params), "cgb_sampler_create: cgb_params ABI mismatch");
     CGB_CHECK(params->nPatterns >= 1, "cgb_sampler_create: nPatterns must be >= 1");
-    CGB_TRY(checkSubset(params, nrow, ncol));
+    CGB_TRY(checkSubset(params, nrow, ncol, transpose != 0, subsetRows != 0));
     CGB_TRY(ensureDevice());
 
     cgb_sampler *s = new (std::nothrow) cgb_sampler();
@@ -783,6 +787,7 @@ static int cgb_sampler_set_uncertainty_body(cgb_sampler *s, const float *unc, ui
     CGB_CHECK(s && unc && params, "cgb_sampler_set_uncertainty: NULL argument");
     if (s->sparse) { return CGB_OK; } // SparseNormalModel::setUncertainty is a nop (SparseNormalModel.h:92-98)
     CGB_CUDA(cudaSetDevice(s->device));
+    CGB_TRY(checkSubset(params, nrow, ncol, transpose != 0, subsetRows != 0));
     std::vector<float> host;
     uint32_t nRows, L, ld;
     // pads are 1 like mSMatrix.pad(1.f) (DenseNormalModel.h:87,94); the kernels never read them as data

@@ -163,6 +163,28 @@ def test_params_validation_mirrors_reference():
         cg.CogapsParams(nPatterns=3, distributed="single-cell", fixedPatterns=np.ones((4, 3)), whichMatrixFixed="P")
 
 
+def test_subset_indices_are_bounds_checked_before_anything_else():
+    """The reference indexes its matrix with whatever it is given (Matrix.cpp:30-69: undefined behaviour past the end);
+    the library refuses — and does so before it looks for a device, so this runs anywhere."""
+    import ctypes as C
+    import cogaps_b200 as cg
+    from cogaps_b200._lib import lib
+    from cogaps_b200._runhelp import make_params, fptr
+    data = np.ones((6, 4), np.float32)
+    rs = cg.GapsRandomState(1)
+    for transpose, subsetRows, bad, good in ((1, 0, [7], [6]), (0, 1, [7], [6]), (1, 1, [5], [4]), (0, 0, [5], [4]), (0, 0, [0], [1])):
+        for idx, want in ((bad, -1), (good, None)):
+            p = make_params(nPatterns=2, subsetIndices=idx, subsetGenes=subsetRows)
+            h = C.c_void_p()
+            rc = lib().cgb_sampler_create(fptr(data), 6, 4, 0, transpose, subsetRows, 0.01, 100.0, C.byref(p), rs._h, C.byref(h))
+            if want is not None:
+                assert rc == want and b"subset ind" in lib().cgb_last_error()
+            elif rc == 0:
+                lib().cgb_sampler_destroy(h)          # a GPU is present: the sampler was really built
+            else:
+                assert rc == -2                       # CGB_ENODEVICE: the indices passed, the device is what is missing
+
+
 # ---------------------------------------------------------------------------------------------
 # distributed driver
 # ---------------------------------------------------------------------------------------------
