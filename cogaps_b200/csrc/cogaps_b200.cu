@@ -1144,50 +1144,8 @@ static int applyOutcome(cgb_sampler *s, const HostProposal &hp, const DevProposa
     s->counters.algorithmicBytes += s->sparse ? sparseFlagBytes(dp, s->L) : algorithmicBytes(dp, o, s->L);
     // rows whose AP line / factor element the device rewrites for this outcome: every CTA of the
     // committing cluster bumps the row's version once (kernels.cuh commit_task)
-    bool commit = false;
-    switch (hp.type)
-    {
-        case 'B':
-            if (accepted)
-            {
-                s->queue.acceptBirth();
-                s->domain.atom(hp.atom1).mass = mass1;
-                commit = true;
-            }
-            else
-            {
-                s->queue.rejectBirth();
-                s->domain.cacheErase(hp.atom1);
-            }
-            break;
-        case 'D':
-            if (accepted)
-            {
-                s->queue.rejectDeath();
-                s->domain.atom(hp.atom1).mass = mass1;
-                commit = (mass1 != dp.m1);
-            }
-            else
-            {
-                s->queue.acceptDeath();
-                s->domain.cacheErase(hp.atom1);
-                commit = true;
-            }
-            break;
-        case 'M':
-            if (accepted) { s->domain.move(hp.atom1, hp.pos); }
-            commit = accepted;
-            break;
-        case 'E':
-            if (accepted)
-            {
-                s->domain.atom(hp.atom1).mass = mass1;
-                s->domain.atom(hp.atom2).mass = mass2;
-            }
-            commit = accepted;
-            break;
-        default: return fail(CGB_EINTERNAL, "applyOutcome: corrupt proposal type");
-    }
+    if (hp.type != 'B' && hp.type != 'D' && hp.type != 'M' && hp.type != 'E') { return fail(CGB_EINTERNAL, "applyOutcome: corrupt proposal type"); }
+    const bool commit = applyToDomain(s->domain, s->queue, hp, accepted, mass1, mass2, dp.m1);
     if (commit) { noteCommit(s, dp, resident); }
     return CGB_OK;
 }

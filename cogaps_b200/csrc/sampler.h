@@ -123,6 +123,61 @@ private:
     bool mUseCachedRng;
 };
 
+// What one evaluated proposal does to the host's state once its outcome is known — the domain / queue half of
+// AsynchronousGibbsSampler::birth/death/move/exchange (AsynchronousGibbsSampler.h:126-219).  `accepted` means: B the
+// atom is born with mass1; D the atom survives with mass1; M the atom moves to hp.pos; E both masses change.
+// postedMass1 is atom1's mass as the evaluator was given it.  Returns true when the factor matrix changed, i.e. the
+// device committed a row for this proposal; type is left for the caller to reject when it is none of B/D/M/E.
+inline bool applyToDomain(AtomicDomain &domain, ProposalQueue &queue, const HostProposal &hp, bool accepted,
+                          float mass1, float mass2, float postedMass1)
+{
+    bool commit = false;
+    switch (hp.type)
+    {
+        case 'B':
+            if (accepted)
+            {
+                queue.acceptBirth();
+                domain.atom(hp.atom1).mass = mass1;
+                commit = true;
+            }
+            else
+            {
+                queue.rejectBirth();
+                domain.cacheErase(hp.atom1);
+            }
+            break;
+        case 'D':
+            if (accepted)
+            {
+                queue.rejectDeath();
+                domain.atom(hp.atom1).mass = mass1;
+                commit = (mass1 != postedMass1);
+            }
+            else
+            {
+                queue.acceptDeath();
+                domain.cacheErase(hp.atom1);
+                commit = true;
+            }
+            break;
+        case 'M':
+            if (accepted) { domain.move(hp.atom1, hp.pos); }
+            commit = accepted;
+            break;
+        case 'E':
+            if (accepted)
+            {
+                domain.atom(hp.atom1).mass = mass1;
+                domain.atom(hp.atom2).mass = mass2;
+            }
+            commit = accepted;
+            break;
+        default: break;
+    }
+    return commit;
+}
+
 } // namespace cgb
 
 struct cgb_sampler

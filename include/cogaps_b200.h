@@ -398,6 +398,34 @@ float cgb_debug_host_logf(float x);
 /* floor(x / divisor) as the host generator computes it for its per-sampler divisors (tests: == x / divisor) */
 uint64_t cgb_debug_fastdiv(uint64_t divisor, uint64_t x);
 
+/* One evaluated proposal of a recorded run (layout of the oracle's trace records, oracle/cogaps_oracle.h) */
+typedef struct cgb_trace_record
+{
+    uint32_t phase;     /* CGB_PHASE_EQUILIBRATION / CGB_PHASE_SAMPLING */
+    uint32_t iter;
+    uint32_t side;      /* 'A' or 'P' */
+    uint32_t batch;     /* batch index within this update() call */
+    uint32_t type;      /* 'B', 'D', 'M', 'E' */
+    uint32_t r1, c1, r2, c2;
+    uint32_t accepted;  /* B: born; D: the atom survives; M: moved; E: masses changed */
+    uint64_t pos;       /* birth position / move destination */
+    uint64_t atom1Pos;
+    uint64_t atom2Pos;
+    uint64_t rngState;  /* PCG state handed to the evaluator */
+    float mass1, mass2; /* atom masses before evaluation */
+    float newMass1, newMass2;
+    float s, s_mu;
+} cgb_trace_record;
+/* Host only, no device: runs the library's own proposal generator and atomic domain (the code cgb_sampler_update
+ * drives; atomic/ProposalQueue.cpp:53-283, ConcurrentAtomicDomain.cpp:14-132) through a whole gaps::run on `data`
+ * (nrow x ncol row-major; asynchronous sampler, whole untransposed matrix) with the OUTCOME of every proposal taken
+ * from `trace`, and compares every proposal it queues — type, bins, positions, atom masses, PCG state, batch
+ * boundaries — with the trace.  CGB_OK when all n records match and none is left over; otherwise CGB_EINTERNAL and
+ * cgb_debug_replay_message() says which field of which record differs.  *checked = records matched. */
+int cgb_debug_replay_generator(const float *data, uint32_t nrow, uint32_t ncol, const cgb_params *params,
+                               const cgb_trace_record *trace, uint64_t n, uint64_t *checked);
+const char *cgb_debug_replay_message(void);
+
 #ifdef __cplusplus
 }
 #endif

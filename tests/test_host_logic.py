@@ -361,3 +361,72 @@ def test_header_is_plain_c(tmp_path):
     subprocess.check_call(["gcc", "-std=c99", "-Wall", "-Wextra", "-pedantic", "-Werror", "-I", os.path.join(ROOT, "include"),
                            str(src), "-o", str(exe), "-L", libdir, "-lcogaps_b200", "-Wl,-rpath," + libdir])
     assert subprocess.call([str(exe)]) == 0
+
+
+# ---------------------------------------------------------------------------------------------
+# the product's proposal generator against the oracle's trace, no GPU needed
+# ---------------------------------------------------------------------------------------------
+REPLAY_CASES = {
+    "modsim": ("modsim", dict(seed=42, nPatterns=3, nIterations=300, outputFrequency=0)),
+    "gist": ("gist", dict(seed=42, nPatterns=7, nIterations=40, outputFrequency=0)),
+    "gist_sparse": ("gist", dict(seed=9, nPatterns=4, nIterations=40, outputFrequency=0, useSparseOptimization=1)),
+    "syn_wide": ("syn:40:700:4:9", dict(seed=9, nPatterns=4, nIterations=40, outputFrequency=0)),
+    "gist_fixedP": ("gist", dict(seed=8, nPatterns=3, nIterations=40, outputFrequency=0, whichMatrixFixed="P")),
+}
+
+
+def _replay(data, trace, **kw):
+    import ctypes as C
+    from cogaps_b200._lib import lib
+    from cogaps_b200._runhelp import make_params, fptr
+    data = np.ascontiguousarray(data, dtype=np.float32)
+    p = make_params(**kw)
+    checked = C.c_uint64()
+    rc = lib().cgb_debug_replay_generator(fptr(data), data.shape[0], data.shape[1], C.byref(p),
+                                          trace.ctypes.data_as(C.c_void_p), trace.size, C.byref(checked))
+    return rc, checked.value, lib().cgb_debug_replay_message().decode()
+
+
+@pytest.mark.parametrize("name", sorted(REPLAY_CASES))
+def test_generator_replays_the_oracle_trace(oracle, name):
+    """ProposalQueue + AtomicDomain of the LIBRARY (what cgb_sampler_update drives) against the oracle's record of a
+    whole run: every queued proposal — type, bins, positions, atom masses, PCG state, batch boundaries — must be the
+    one the oracle (pinned to the reference's ProposalQueue.cpp / ConcurrentAtomicDomain.cpp) evaluated at that point,
+    given the same outcomes.  This holds the sequential half of the hot path to the reference without a GPU."""
+    from tests.cases import load_data
+    dataset, kw = REPLAY_CASES[name]
+    data = load_data(dataset)
+    if "whichMatrixFixed" in kw:
+        kw = dict(kw, fixedPatterns=np.random.default_rng(7).gamma(2.0, 0.5, (data.shape[1], kw["nPatterns"])).astype(np.float32))
+    res = oracle.run(data, trace_capacity=400000, **kw)
+    assert 1000 < res.trace_total <= 400000
+    rc, checked, msg = _replay(data, res.trace, **kw)
+    assert rc == 0, msg
+    assert checked == res.trace_total
+
+
+def test_generator_replay_notices_a_wrong_trace(oracle):
+    from tests.cases import load_data
+    data = load_data("modsim")
+    kw = dict(seed=42, nPatterns=3, nIterations=60, outputFrequency=0)
+    trace = oracle.run(data, trace_capacity=100000, **kw).trace
+    for field, at in (("rngState", 50), ("r1", 333), ("accepted", 40), ("newMass1", 700)):
+        bad = trace.copy()
+        if field == "accepted":
+            at = int(np.nonzero((bad["type"] == ord("B")) & (bad["accepted"] == 1))[0][5])
+            bad[field][at] = 0                      # a birth that now fails: the atom count diverges from here on
+        elif field == "newMass1":
+            at = int(np.nonzero(bad["accepted"] == 1)[0][200])
+            bad[field][at] += np.float32(0.25)      # seen when that atom is next picked
+        else:
+            bad[field][at] ^= 1
+        rc, checked, msg = _replay(data, bad, **kw)
+        assert rc != 0 and checked >= at and msg, (field, checked, msg)
+        if field in ("rngState", "r1"):
+            assert checked == at and ("rng state" in msg or "r1" in msg)
+    rc, checked, msg = _replay(data, trace[:-7], **kw)
+    assert rc != 0 and "more proposals than the trace" in msg
+    rc, checked, msg = _replay(data, trace, **dict(kw, seed=43))
+    assert rc == 0          # not a typo: the seeder starts from seed|1 (Random.cpp:222-223), 42 and 43 are one stream
+    rc, checked, msg = _replay(data, trace, **dict(kw, seed=44))
+    assert rc != 0 and checked == 0
