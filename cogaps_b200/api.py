@@ -262,14 +262,24 @@ def read_matrix_csr(path, by_rows=True):
     return nrow.value, ncol.value, ptr, idx[:nnz.value], val[:nnz.value]
 
 
-def gaps_run_file(path, uncertainty_path=None, snapshots=False, **kw):
-    """gaps::run(const std::string &data, ...) (src/GapsRunner.h:19-24) through the C ABI."""
+def gaps_run_file(path, uncertainty_path=None, snapshots=False, checkpointInterval=0, checkpointOutFile=None,
+                  checkpointInFile=None, **kw):
+    """gaps::run(const std::string &data, ...) (src/GapsRunner.h:19-24) through the C ABI; checkpoint arguments as in
+    gaps_run."""
     nrow, ncol = C.c_uint32(), C.c_uint32()
     check(lib().cgb_read_matrix_file(str(path).encode(), None, 0, C.byref(nrow), C.byref(ncol)))
     p = make_params(**kw)
     res = ResultArrays(p, nrow.value, ncol.value, snapshots=snapshots)
     unc = str(uncertainty_path).encode() if uncertainty_path else None
-    check(lib().cgb_run_file(str(path).encode(), unc, C.byref(p), C.byref(res.c)))
+    if not checkpointInterval and checkpointInFile is None:
+        check(lib().cgb_run_file(str(path).encode(), unc, C.byref(p), C.byref(res.c)))
+        return res.finish()
+    opt = CgbRunOptions()
+    opt.struct_size = C.sizeof(CgbRunOptions)
+    opt.checkpointInterval = int(checkpointInterval)
+    opt.checkpointOutFile = _path(checkpointOutFile)
+    opt.checkpointInFile = _path(checkpointInFile)
+    check(lib().cgb_run_file_ex(str(path).encode(), unc, C.byref(p), C.byref(opt), C.byref(res.c)))
     return res.finish()
 
 

@@ -3165,7 +3165,7 @@ extern "C" int cgb_read_matrix_file(const char *path, float *out, uint64_t capac
     return guarded("cgb_read_matrix_file", [&]() { return cgb_read_matrix_file_body(path, out, capacity, nrow, ncol); });
 }
 
-static int cgb_run_file_body(const char *dataPath, const char *uncertaintyPath, const cgb_params *p, cgb_result *r)
+static int cgb_run_file_ex_body(const char *dataPath, const char *uncertaintyPath, const cgb_params *p, const cgb_run_options *opt, cgb_result *r)
 {
     CGB_CHECK(dataPath && p && r, "cgb_run_file: NULL argument");
     CGB_CHECK(p->struct_size == sizeof(cgb_params), "cgb_run_file: cgb_params ABI mismatch");
@@ -3181,7 +3181,7 @@ static int cgb_run_file_body(const char *dataPath, const char *uncertaintyPath, 
         CsrPair pair;
         if (loadMtxCsrPair(dataPath, pair, nrow, ncol, err))
         {
-            return runCore(nullptr, &pair, nrow, ncol, 0, nullptr, p, nullptr, r); // uncertainty is ignored by the sparse model
+            return runCore(nullptr, &pair, nrow, ncol, 0, nullptr, p, opt, r); // uncertainty is ignored by the sparse model
         }
         if (!err.empty()) { return fail(CGB_EINVAL, std::string("cgb_run_file: ") + err); }
         // negative entries: fall through to the dense route, which carries them into lambda like the reference
@@ -3203,10 +3203,15 @@ static int cgb_run_file_body(const char *dataPath, const char *uncertaintyPath, 
         std::sort(sorted.begin(), sorted.end());
         q.subsetIndices = sorted.data();
     }
-    return cgb_run(data.data(), nrow, ncol, 0, haveUnc ? unc.data() : nullptr, &q, r);
+    return cgb_run_ex(data.data(), nrow, ncol, 0, haveUnc ? unc.data() : nullptr, &q, opt, r);
+}
+
+extern "C" int cgb_run_file_ex(const char *dataPath, const char *uncertaintyPath, const cgb_params *p, const cgb_run_options *opt, cgb_result *r)
+{
+    return guarded("cgb_run_file_ex", [&]() { return cgb_run_file_ex_body(dataPath, uncertaintyPath, p, opt, r); });
 }
 
 extern "C" int cgb_run_file(const char *dataPath, const char *uncertaintyPath, const cgb_params *p, cgb_result *r)
 {
-    return guarded("cgb_run_file", [&]() { return cgb_run_file_body(dataPath, uncertaintyPath, p, r); });
+    return guarded("cgb_run_file", [&]() { return cgb_run_file_ex_body(dataPath, uncertaintyPath, p, nullptr, r); });
 }

@@ -40,6 +40,7 @@ extern "C" {
 #define CGB_ENOMEM       -4
 #define CGB_EUNSUPPORTED -5   /* feature of the reference not on this path yet */
 #define CGB_EINTERNAL    -6
+#define CGB_EINTERRUPTED -7   /* cgb_run_ex: the interrupt callback asked to stop (Rcpp::checkUserInterrupt, utils/GlobalConfig.h:16-20) */
 
 #define CGB_ERF_TABLE_SIZE     3001  /* math/Random.h:13 */
 #define CGB_ERFINV_TABLE_SIZE  5001  /* math/Random.h:14 */
@@ -326,8 +327,6 @@ int cgb_stats_device_sums(const cgb_stats *st, void **AmeanSum, void **AsqSum, v
  * reading (SingleThreadedGibbsSampler.h:260-273), so there is nothing to be compatible with: asking for a
  * checkpoint with asynchronousUpdates == 0 fails with CGB_EUNSUPPORTED.
  * ---------------------------------------------------------------------------------------- */
-#define CGB_EINTERRUPTED -7   /* the interrupt callback asked to stop (Rcpp::checkUserInterrupt, utils/GlobalConfig.h:16-20) */
-
 typedef struct cgb_run_options
 {
     uint32_t struct_size;          /* = sizeof(cgb_run_options) */
@@ -348,6 +347,10 @@ typedef struct cgb_run_options
 /* cgb_run with checkpoints / interrupt polling; options == NULL is exactly cgb_run. */
 int cgb_run_ex(const float *data, uint32_t nrow, uint32_t ncol, int32_t colmajor, const float *uncertainty,
                const cgb_params *params, const cgb_run_options *options, cgb_result *result);
+
+/* the path overload with the same options (gaps::run(const std::string&, ...) reads checkpoints too, GapsRunner.cpp:119-159) */
+int cgb_run_file_ex(const char *dataPath, const char *uncertaintyPath, const cgb_params *params,
+                    const cgb_run_options *options, cgb_result *result);
 
 /* `Archive << sampler` / `Archive >> sampler` of the Sampler concept (AsynchronousGibbsSampler.h:221-233): the bytes the
  * reference streams for the factor matrix, the atomic domain (atoms in pick order) and the proposal queue.  Size the
