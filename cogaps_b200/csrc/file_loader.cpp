@@ -12,7 +12,9 @@
 #include "../../include/cogaps_b200.h"
 
 #include <algorithm>
+#include <charconv>
 #include <cmath>
+#include <system_error>
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
@@ -43,6 +45,12 @@ static bool isNumber(const std::string &s)
 // valid prefix, 0 when there is none
 static float streamFloat(const std::string &s)
 {
+    // from_chars is correctly rounded like glibc's strtof and takes the longest valid prefix too; it is several times
+    // faster.  It reports overflow / underflow instead of saturating, so those rare tokens go through strtof.
+    float fast = 0.f;
+    const std::from_chars_result res = std::from_chars(s.data(), s.data() + s.size(), fast, std::chars_format::fixed);
+    if (res.ec == std::errc()) { return fast; }
+    if (res.ec == std::errc::invalid_argument) { return 0.f; }
     char *end = nullptr;
     const float v = std::strtof(s.c_str(), &end);
     return (end == s.c_str()) ? 0.f : v;
@@ -135,6 +143,38 @@ static bool readMtx(std::ifstream &f, std::vector<float> &out, uint32_t &nrow, u
 // Same parsing as readMtx, but the triplets are kept as triplets.  Semantics of the dense reader that must survive:
 // a later entry for the same cell overwrites an earlier one; explicit zeros are cells like any other (they simply are
 // not positive); everything not listed is 0.
+// what `stream >> unsignedLong` accepts: optional whitespace, digits.  False (cursor unchanged) when no digit follows —
+// the reference's read loop simply ends there (MtxParser.cpp:35-47 reads while the stream is good)
+static bool scanUnsigned(const char *&p, const char *end, unsigned long &out)
+{
+    const char *q = p;
+    while (q < end && (*q == ' ' || *q == '\t' || *q == '\n' || *q == '\r' || *q == '\v' || *q == '\f')) { ++q; }
+    if (q < end && *q == '+') { ++q; }
+    if (q >= end || *q < '0' || *q > '9') { return false; }
+    unsigned long v = 0;
+    while (q < end && *q >= '0' && *q <= '9')
+    {
+        v = v * 10 + static_cast<unsigned long>(*q - '0');
+        ++q;
+    }
+    out = v;
+    p = q;
+    return true;
+}
+
+// what `stream >> std::string` yields: the next run of non-whitespace characters
+static bool scanToken(const char *&p, const char *end, std::string &out)
+{
+    const char *q = p;
+    while (q < end && (*q == ' ' || *q == '\t' || *q == '\n' || *q == '\r' || *q == '\v' || *q == '\f')) { ++q; }
+    if (q >= end) { return false; }
+    const char *b = q;
+    while (q < end && !(*q == ' ' || *q == '\t' || *q == '\n' || *q == '\r' || *q == '\v' || *q == '\f')) { ++q; }
+    out.assign(b, q);
+    p = q;
+    return true;
+}
+
 bool loadMtxTriplets(const char *path, std::vector<uint32_t> &rows, std::vector<uint32_t> &cols, std::vector<float> &vals,
                      uint32_t &nrow, uint32_t &ncol, std::string &err)
 {
@@ -143,24 +183,43 @@ bool loadMtxTriplets(const char *path, std::vector<uint32_t> &rows, std::vector<
         err = "not a Matrix-Market file";
         return false;
     }
-    std::ifstream f(path);
-    if (!f.is_open())
+    // the whole file in one read, then a hand-rolled scan: the stream extractors of the dense reader cost about a
+    // microsecond per entry, which is minutes at the 10^8 entries of a single-cell matrix
+    std::string text;
     {
-        err = std::string("cannot open ") + path;
-        return false;
+        std::FILE *f = std::fopen(path, "rb");
+        if (!f)
+        {
+            err = std::string("cannot open ") + path;
+            return false;
+        }
+        char buf[1 << 16];
+        size_t n = 0;
+        while ((n = std::fread(buf, 1, sizeof(buf), f)) > 0) { text.append(buf, n); }
+        std::fclose(f);
     }
-    std::string line = "%";
-    while (line.find('%') != std::string::npos)
+    const char *p = text.data(), *end = text.data() + text.size();
+    // header: lines are skipped while they contain a '%' anywhere (MtxParser.cpp:14-20), the first one that does not
+    // holds "nrow ncol [nnz]"
+    std::string line;
+    for (;;)
     {
-        if (!std::getline(f, line))
+        if (p >= end)
         {
             err = "Invalid MTX file";
             return false;
         }
+        const char *nl = static_cast<const char*>(std::memchr(p, '\n', static_cast<size_t>(end - p)));
+        const char *lineEnd = nl ? nl : end;
+        line.assign(p, lineEnd);
+        p = nl ? nl + 1 : end;
+        if (line.find('%') == std::string::npos) { break; }
     }
-    std::stringstream dims(line);
     unsigned long r = 0, c = 0, declared = 0;
-    dims >> r >> c >> declared;
+    {
+        const char *q = line.data(), *qe = line.data() + line.size();
+        if (scanUnsigned(q, qe, r) && scanUnsigned(q, qe, c)) { scanUnsigned(q, qe, declared); }
+    }
     if (r == 0 || c == 0)
     {
         err = "Invalid MTX file";
@@ -175,7 +234,7 @@ bool loadMtxTriplets(const char *path, std::vector<uint32_t> &rows, std::vector<
     }
     unsigned long row = 0, col = 0;
     std::string val;
-    while (f >> row >> col >> val)
+    while (scanUnsigned(p, end, row) && scanUnsigned(p, end, col) && scanToken(p, end, val))
     {
         float v;
         if (!parseValue(val, v, err)) { return false; }
@@ -200,35 +259,45 @@ void compressTriplets(const std::vector<uint32_t> &major, const std::vector<uint
                       bool &anyNegative)
 {
     const size_t n = vals.size();
-    // stable counting sort by major index keeps file order inside a row
-    std::vector<size_t> start(static_cast<size_t>(nMajor) + 1, 0);
-    for (size_t i = 0; i < n; ++i) { ++start[major[i] + 1]; }
-    for (uint32_t r = 0; r < nMajor; ++r) { start[r + 1] += start[r]; }
-    std::vector<uint32_t> order(n);
+    // two stable counting sorts (by minor, then by major): entries end up grouped by row, ascending minor inside a
+    // row, and entries for the same cell in file order — O(n), no comparison sort
+    uint32_t nMinor = 0;
+    for (size_t i = 0; i < n; ++i) { if (minor[i] >= nMinor) { nMinor = minor[i] + 1; } }
+    std::vector<uint32_t> byMinor(n), order(n);
     {
-        std::vector<size_t> fill(start.begin(), start.end() - 1);
-        for (size_t i = 0; i < n; ++i) { order[fill[major[i]]++] = static_cast<uint32_t>(i); }
+        std::vector<size_t> fill(static_cast<size_t>(nMinor) + 1, 0);
+        for (size_t i = 0; i < n; ++i) { ++fill[minor[i] + 1]; }
+        for (uint32_t m = 0; m < nMinor; ++m) { fill[m + 1] += fill[m]; }
+        for (size_t i = 0; i < n; ++i) { byMinor[fill[minor[i]]++] = static_cast<uint32_t>(i); }
+    }
+    {
+        std::vector<size_t> fill(static_cast<size_t>(nMajor) + 1, 0);
+        for (size_t i = 0; i < n; ++i) { ++fill[major[i] + 1]; }
+        for (uint32_t r = 0; r < nMajor; ++r) { fill[r + 1] += fill[r]; }
+        for (size_t j = 0; j < n; ++j) { order[fill[major[byMinor[j]]]++] = byMinor[j]; }
     }
     ptr.assign(static_cast<size_t>(nMajor) + 1, 0u);
     idx.clear(); out.clear();
     idx.reserve(n); out.reserve(n);
     anyNegative = false;
-    std::vector<std::pair<uint32_t, uint32_t> > rowEntries; // (minor, position in file)
+    size_t j = 0;
     for (uint32_t r = 0; r < nMajor; ++r)
     {
-        rowEntries.clear();
-        for (size_t j = start[r]; j < start[r + 1]; ++j) { rowEntries.push_back(std::make_pair(minor[order[j]], order[j])); }
-        std::sort(rowEntries.begin(), rowEntries.end()); // by minor, then by file position
-        for (size_t j = 0; j < rowEntries.size(); ++j)
+        while (j < n && major[order[j]] == r)
         {
-            if (j + 1 < rowEntries.size() && rowEntries[j + 1].first == rowEntries[j].first) { continue; } // overwritten later
-            const float v = vals[rowEntries[j].second];
-            if (v < 0.f) { anyNegative = true; }
-            if (v > 0.f)
+            const uint32_t e = order[j];
+            const bool overwrittenLater = j + 1 < n && major[order[j + 1]] == r && minor[order[j + 1]] == minor[e];
+            if (!overwrittenLater)
             {
-                idx.push_back(rowEntries[j].first);
-                out.push_back(v);
+                const float v = vals[e];
+                if (v < 0.f) { anyNegative = true; }
+                if (v > 0.f)
+                {
+                    idx.push_back(minor[e]);
+                    out.push_back(v);
+                }
             }
+            ++j;
         }
         ptr[r + 1] = static_cast<uint32_t>(idx.size());
     }

@@ -233,3 +233,31 @@ def test_sparse_run_from_matrix_market_never_needs_the_dense_matrix(tmp_path, tr
         assert np.array_equal(straight.atomHistoryP, other.atomHistoryP)
         assert straight.totalUpdates == other.totalUpdates
         assert np.float32(straight.meanChiSq) == np.float32(other.meanChiSq)
+
+
+def test_number_tokens_parse_like_the_reference(tmp_path):
+    """MatrixElement.cpp:10-46: a token of digits, '.', '-' goes through the stream extractor (longest valid prefix, 0
+    when there is none); base 'e' exponent is base * powf(10, exponent).  Odd but legal tokens, against the reference's
+    own parser where it is built, and against Python's correctly rounded float32 otherwise."""
+    import cogaps_b200 as cg
+    tokens = ["7", "007", "3.", ".25", "-0", "-.5", "0.1", "16777217", "123456789.125", "0.000001", "1e3", "2.5e-3", "-1e2",
+              "1.17549435e-38", "3.4028234e38", "0.30000001192092896", "4.35", "1e0", "9.999999e-1"]
+    path = tmp_path / "tokens.csv"
+    path.write_text(",v\n" + "".join("r%d,%s\n" % (i, t) for i, t in enumerate(tokens)))
+    got = cg.read_matrix_file(path)[:, 0]
+    plain = [i for i, t in enumerate(tokens) if "e" not in t]
+    assert np.array_equal(bits(got[plain]), bits(np.array([float(tokens[i]) for i in plain], np.float32)))
+    if RefLib.available("scalar"):
+        assert np.array_equal(bits(got), bits(RefLib("scalar").read_file(str(path))[:, 0]))
+    # the same tokens as Matrix-Market values, through the triplet scanner
+    mtx = tmp_path / "tokens.mtx"
+    mtx.write_text("%%MatrixMarket matrix coordinate real general\n%d 1 %d\n" % (len(tokens), len(tokens))
+                   + "".join("%d 1 %s\n" % (i + 1, t) for i, t in enumerate(tokens)))
+    dense = cg.read_matrix_file(mtx)[:, 0]
+    assert np.array_equal(bits(dense), bits(got))
+    pos = [i for i in range(len(tokens)) if got[i] > 0]
+    nonneg = tmp_path / "nonneg.mtx"
+    nonneg.write_text("%%MatrixMarket matrix coordinate real general\n%d 1 %d\n" % (len(tokens), len(pos))
+                      + "".join("%d  1\t%s\r\n" % (i + 1, tokens[i]) for i in pos))        # odd spacing, CRLF
+    nrow, ncol, ptr, idx, val = cg.read_matrix_csr(nonneg, by_rows=False)
+    assert np.array_equal(idx, np.array(pos, np.uint32)) and np.array_equal(bits(val), bits(got[pos]))
