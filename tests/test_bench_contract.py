@@ -37,3 +37,19 @@ def test_other_ranks_of_the_reference_arm_do_nothing():
     done = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--gpus", "2"],
                           check=True, capture_output=True, text=True, env=env, timeout=120)
     assert done.stdout.strip() == ""
+
+
+def test_c5_row_shard_tool_dry_run_world_2_gloo():
+    """tools/bench_c5.py (BASELINE configs[4]: row-shard over N GPUs + all-gather of the per-shard P rows): the
+    sharding arithmetic, the gather of ragged pattern-major blocks and the JSON line, without a GPU."""
+    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2", "--master-addr", "127.0.0.1",
+           "--master-port", "29547", os.path.join(ROOT, "tools", "bench_c5.py"), "--dry-run", "--backend", "gloo",
+           "--cells-total", "777", "--genes", "40", "--patterns", "6"]
+    done = subprocess.run(cmd, check=True, capture_output=True, text=True, timeout=300)
+    lines = [ln for ln in done.stdout.splitlines() if ln.startswith("{")]
+    assert len(lines) == 1
+    line = json.loads(lines[0])
+    assert line["n_gpus"] == 2 and line["config"]["cells_per_gpu"] == [388, 389]         # remainder to the last set
+    g = line["allgather"]
+    assert g["gathered_shape"] == [777, 6] and g["checksum_matches_sum_of_shards"] is True
+    assert g["bytes_per_rank"] == 6 * 416 * 4 and g["backend"] == "gloo"                 # padded to the widest shard's stride
