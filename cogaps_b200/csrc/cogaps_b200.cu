@@ -569,27 +569,7 @@ static int samplerCreateImpl(const float *data, uint32_t nrow, uint32_t ncol, in
             meanJob.nnz = static_cast<unsigned>(v.size());
             return;
         }
-        for (uint32_t r = 0; r < s->nRows; ++r)
-        {
-            const float *row = meanBase + static_cast<size_t>(r) * meanStrideR;
-            if (meanStrideL == 1)
-            {
-                for (uint32_t l = 0; l < s->L; ++l)
-                {
-                    sum += row[l];
-                    if (row[l] > 0.f) { ++nnz; }
-                }
-            }
-            else
-            {
-                for (uint32_t l = 0; l < s->L; ++l)
-                {
-                    const float v = row[static_cast<size_t>(l) * meanStrideL];
-                    sum += v;
-                    if (v > 0.f) { ++nnz; }
-                }
-            }
-        }
+        runningSum(meanBase, s->nRows, s->L, meanStrideR, meanStrideL, sum, nnz);
         meanJob.sum = sum;
         meanJob.nnz = nnz;
     });
@@ -2407,6 +2387,21 @@ extern "C" uint64_t cgb_debug_fastdiv(uint64_t divisor, uint64_t x)
 
 // host portable-log probe: the same header compiled for the host (tests compare both with the oracle)
 extern "C" float cgb_debug_host_logf(float x) { return portable_logf(x); }
+
+// the running sum / positive count behind lambda exactly as the samplers take it: over the rows of a row-major
+// nrow x ncol matrix (byColumns == 0) or down its columns (the blocked walk)
+extern "C" int cgb_debug_running_sum(const float *data, uint32_t nrow, uint32_t ncol, int32_t byColumns, float *sum, uint32_t *nnz)
+{
+    if (!data || !sum || !nnz) { return fail(CGB_EINVAL, "cgb_debug_running_sum: NULL argument"); }
+    return guarded("cgb_debug_running_sum", [&]()
+    {
+        unsigned n = 0;
+        if (byColumns) { runningSum(data, ncol, nrow, 1, ncol, *sum, n); }
+        else { runningSum(data, nrow, ncol, ncol, 1, *sum, n); }
+        *nnz = n;
+        return CGB_OK;
+    });
+}
 
 // ------------------------------------------------------------------------------------------------
 // Checkpoints: device-resident state <-> the images of checkpoint.h (Archive << / >> of the Sampler concept,

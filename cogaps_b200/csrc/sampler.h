@@ -13,6 +13,7 @@
 #include "host_rng.h"
 
 #include <cuda_runtime.h>
+#include <new>
 #include <string>
 #include <vector>
 
@@ -122,6 +123,82 @@ private:
     unsigned mNumProcessed;
     bool mUseCachedRng;
 };
+
+// gaps::nonZeroMean's numerator and denominator (MatrixMath.cpp:39-55): ONE fp32 running sum over the sampler's rows in
+// order, and the count of positive elements.  The order of the additions is the result, so the chain of dependent
+// adds cannot be split; what can be helped is the memory side.  Row r starts at base + r * strideR, its elements are
+// strideL floats apart.  When the rows run down the columns of a row-major matrix (strideR == 1) the plain walk
+// touches a new cache line per element and thrashes any host whose L2 does not hold one full sweep (a 9x slowdown was
+// measured on such a box); 16 sampler rows at a time are therefore gathered into a contiguous strip first — a
+// streaming transpose of one cache line's width — and summed from there in exactly the same order.
+inline void runningSum(const float *base, uint32_t nRows, uint32_t L, size_t strideR, size_t strideL, float &sumOut, unsigned &nnzOut)
+{
+    // runs on a helper thread: no exception may start here, so the strip is allocated nothrow and the plain walk is
+    // the fallback
+    struct Strip
+    {
+        enum { kRows = 16 };
+        float *data;
+        Strip() : data(nullptr) {}
+        ~Strip() { delete[] data; }
+        bool reserveFor(uint32_t rowLength)
+        {
+            data = new (std::nothrow) float[static_cast<size_t>(kRows) * rowLength];
+            return data != nullptr;
+        }
+    } strip;
+    float sum = 0.f;
+    unsigned nnz = 0;
+    if (strideL == 1)
+    {
+        for (uint32_t r = 0; r < nRows; ++r)
+        {
+            const float *row = base + static_cast<size_t>(r) * strideR;
+            for (uint32_t l = 0; l < L; ++l)
+            {
+                sum += row[l];
+                if (row[l] > 0.f) { ++nnz; }
+            }
+        }
+    }
+    else if (strideR == 1 && strip.reserveFor(L))
+    {
+        const uint32_t B = Strip::kRows;
+        for (uint32_t r0 = 0; r0 < nRows; r0 += B)
+        {
+            const uint32_t w = (nRows - r0 < B) ? nRows - r0 : B;
+            for (uint32_t l = 0; l < L; ++l)
+            {
+                const float *src = base + static_cast<size_t>(l) * strideL + r0;
+                for (uint32_t j = 0; j < w; ++j) { strip.data[static_cast<size_t>(j) * L + l] = src[j]; }
+            }
+            for (uint32_t j = 0; j < w; ++j)
+            {
+                const float *row = strip.data + static_cast<size_t>(j) * L;
+                for (uint32_t l = 0; l < L; ++l)
+                {
+                    sum += row[l];
+                    if (row[l] > 0.f) { ++nnz; }
+                }
+            }
+        }
+    }
+    else
+    {
+        for (uint32_t r = 0; r < nRows; ++r)
+        {
+            const float *row = base + static_cast<size_t>(r) * strideR;
+            for (uint32_t l = 0; l < L; ++l)
+            {
+                const float v = row[static_cast<size_t>(l) * strideL];
+                sum += v;
+                if (v > 0.f) { ++nnz; }
+            }
+        }
+    }
+    sumOut = sum;
+    nnzOut = nnz;
+}
 
 // What one evaluated proposal does to the host's state once its outcome is known — the domain / queue half of
 // AsynchronousGibbsSampler::birth/death/move/exchange (AsynchronousGibbsSampler.h:126-219).  `accepted` means: B the

@@ -398,6 +398,9 @@ int cgb_run_set_tables(const float *erf, const float *erfinv, const float *qgamm
 /* the portable log of csrc/gaps_math.h evaluated on the device / on the host */
 int cgb_debug_logf(const float *in, float *out, uint32_t n);
 float cgb_debug_host_logf(float x);
+/* the fp32 running sum and positive count behind lambda (gaps::nonZeroMean, MatrixMath.cpp:39-55) as the samplers take
+ * them: row by row over a row-major nrow x ncol matrix, or (byColumns != 0) column by column */
+int cgb_debug_running_sum(const float *data, uint32_t nrow, uint32_t ncol, int32_t byColumns, float *sum, uint32_t *nnz);
 /* floor(x / divisor) as the host generator computes it for its per-sampler divisors (tests: == x / divisor) */
 uint64_t cgb_debug_fastdiv(uint64_t divisor, uint64_t x);
 

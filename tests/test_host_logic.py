@@ -430,3 +430,21 @@ def test_generator_replay_notices_a_wrong_trace(oracle):
     assert rc == 0          # not a typo: the seeder starts from seed|1 (Random.cpp:222-223), 42 and 43 are one stream
     rc, checked, msg = _replay(data, trace, **dict(kw, seed=44))
     assert rc != 0 and checked == 0
+
+
+@pytest.mark.parametrize("shape", [(1, 1), (3, 5), (37, 16), (40, 17), (129, 31), (500, 203)])
+def test_running_sum_behind_lambda_is_order_exact(shape):
+    """gaps::nonZeroMean (MatrixMath.cpp:39-55) is one fp32 running sum: the ORDER of the additions is the result.  The
+    samplers take it row by row, or — for the sampler whose rows run down the caller's columns — through 16-row strips
+    gathered into contiguous memory first; both must be the plain sequential sum in that order, bit for bit."""
+    import ctypes as C
+    from cogaps_b200._lib import lib, check
+    from cogaps_b200._runhelp import fptr
+    rng = np.random.default_rng(shape[0] * 1000 + shape[1])
+    data = (rng.gamma(2.0, 3.0, shape) * (rng.random(shape) < 0.7)).astype(np.float32)
+    for by_columns, order in ((0, data.ravel()), (1, data.T.ravel())):
+        want = np.add.accumulate(order, dtype=np.float32)[-1]        # accumulate is strictly sequential
+        s, n = C.c_float(), C.c_uint32()
+        check(lib().cgb_debug_running_sum(fptr(data), shape[0], shape[1], by_columns, C.byref(s), C.byref(n)))
+        assert np.float32(s.value).view(np.uint32) == np.float32(want).view(np.uint32)
+        assert n.value == int((data > 0).sum())
