@@ -225,6 +225,25 @@ def test_oracle_and_live_reference_agree_on_files_and_resumes(oracle, name, tmp_
             assert np.array_equal(bits(getattr(ores, f)), bits(getattr(ofull, f))), f
 
 
+def test_what_the_archive_leaves_out_restarts_like_in_the_reference(oracle, tmp_path):
+    """Pump statistics, the chi-square / atom histories, totalUpdates and the queue-length averages are not archived
+    (GapsStatistics.cpp:164-169 writes the four sums only): after a resume they restart, identically in the reference
+    and the oracle."""
+    ref = ref_or_skip()
+    data = load_data("gist")
+    kw = dict(seed=21, nPatterns=4, nIterations=30, outputFrequency=10, takePumpSamples=1)
+    ck = tmp_path / "pump.out"
+    rfull = ref.run(data, checkpointInterval=20, checkpointOutFile=ck, **kw)
+    rres = ref.run(data, checkpointInFile=ck, checkpointOutFile=tmp_path / "r2.out", **kw)
+    ores = oracle.run(data, options=oracle.options(checkpointInFile=ck, checkpointOutFile=tmp_path / "o2.out"), **kw)
+    assert np.array_equal(rres.pumpMatrix, ores.pumpMatrix)
+    assert np.array_equal(rres.meanPatternAssignment, ores.meanPatternAssignment)
+    assert not np.array_equal(rres.pumpMatrix, rfull.pumpMatrix)           # ten samples instead of thirty
+    assert np.array_equal(bits(rres.Amean), bits(rfull.Amean))             # while the archived sums carry on exactly
+    assert rres.totalUpdates == ores.totalUpdates < rfull.totalUpdates
+    assert np.float32(rres.averageQueueLengthA) == np.float32(ores.averageQueueLengthA)
+
+
 # ------------------------------------------------------------------------------------------------
 # GPU: cgb_run_ex and the sampler-level Archive<< / >> against the oracle in device order
 # ------------------------------------------------------------------------------------------------
