@@ -448,3 +448,27 @@ def test_running_sum_behind_lambda_is_order_exact(shape):
         check(lib().cgb_debug_running_sum(fptr(data), shape[0], shape[1], by_columns, C.byref(s), C.byref(n)))
         assert np.float32(s.value).view(np.uint32) == np.float32(want).view(np.uint32)
         assert n.value == int((data > 0).sum())
+
+
+def test_distributed_driver_with_named_explicit_sets():
+    """explicitSets given by sample name travel through distributedCogaps (R/SubsetData.R:15-29): each subset run sees
+    exactly the named columns, and the stitched rows come back in the order of the sets."""
+    import cogaps_b200 as cg
+    from cogaps_b200.distributed import distributedCogaps
+    rng = np.random.default_rng(3)
+    data = rng.gamma(2.0, 1.0, (30, 12)).astype(np.float32)
+    names = ["cell%02d" % j for j in range(12)]
+    params = cg.CogapsParams(nPatterns=3, distributed="single-cell", seed=42)
+    params.setParam("sampleNames", names)
+    params.setParam("nSets", 2)
+    params.setParam("explicitSets", [names[0:12:2], names[1:12:2]])
+    seen = []
+
+    def runner(d, p, unc, subset, subsetDim, runKw):
+        seen.append((np.asarray(subset).tolist(), subsetDim))
+        return _fake_runner(d, p, unc, subset, subsetDim, runKw)
+
+    res = distributedCogaps(data, params, runner=runner)
+    assert seen[0] == ([1, 3, 5, 7, 9, 11], 2) and seen[1] == ([2, 4, 6, 8, 10, 12], 2)
+    assert [s.tolist() for s in res.metadata["subsets"]] == [[1, 3, 5, 7, 9, 11], [2, 4, 6, 8, 10, 12]]
+    assert res.sampleFactors.shape == (12, 3)
