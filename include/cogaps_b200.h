@@ -335,7 +335,9 @@ typedef struct cgb_run_options
                                     * both phases, never when subsetting; taking one rebuilds AP from the factors
                                     * (extraInitialization), so the chain differs from a run without checkpoints exactly
                                     * as the reference's does. */
-    const char *checkpointOutFile; /* :38; NULL or "" = "gaps_checkpoint.out" (:83) */
+    const char *checkpointOutFile; /* :38; NULL or "" = "gaps_checkpoint.out" (:83).  A checkpoint that cannot be written
+                                    * ends the run with CGB_EINVAL; the reference's Archive ignores a stream that failed
+                                    * to open and carries on without one. */
     const char *checkpointInFile;  /* :37,56 (useCheckPoint); NULL or "" = start from scratch.  seed, nPatterns,
                                     * nIterations, alpha*, maxGibbsMass*, useSparseOptimization and checkpointInterval
                                     * are then taken from the file (run_helper, GapsRunner.cpp:99-105). */
