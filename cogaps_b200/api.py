@@ -246,6 +246,19 @@ def read_matrix_file(path):
     return out
 
 
+def write_matrix_csv(path, mat):
+    """FileParser::writeToCsv (file_parser/FileParser.h:59-89): the matrix as the reference writes it.  Host only."""
+    mat = np.ascontiguousarray(mat, dtype=np.float32)
+    check(lib().cgb_write_matrix_csv(os.fspath(path).encode(), fptr(mat), mat.shape[0], mat.shape[1]))
+
+
+def write_result_files(prefix, result):
+    """GapsResult::writeToFile (GapsResult.cpp:27-35): <prefix>_<nPatterns>_{Amean,Pmean,Asd,Psd}.csv from a gaps_run
+    result.  Host only."""
+    check(lib().cgb_result_write_files(os.fspath(prefix).encode(), result.nGenes, result.nSamples, result.nPatterns,
+                                       C.byref(result.c)))
+
+
 def read_matrix_csr(path, by_rows=True):
     """The compressed rows (or columns) of a Matrix-Market file as the sparse model's loader builds them
     (cgb_read_matrix_csr): (nrow, ncol, ptr, idx, val).  Host only."""

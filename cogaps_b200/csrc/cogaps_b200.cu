@@ -3083,6 +3083,34 @@ void compressTriplets(const std::vector<uint32_t> &major, const std::vector<uint
                       bool &anyNegative);
 }
 
+namespace cgb { bool writeMatrixCsv(const char *path, const float *mat, uint32_t nrow, uint32_t ncol, std::string &err); }
+
+extern "C" int cgb_write_matrix_csv(const char *path, const float *mat, uint32_t nrow, uint32_t ncol)
+{
+    if (!path || !mat) { return fail(CGB_EINVAL, "cgb_write_matrix_csv: NULL argument"); }
+    return guarded("cgb_write_matrix_csv", [&]()
+    {
+        std::string err;
+        if (!writeMatrixCsv(path, mat, nrow, ncol, err)) { return fail(CGB_EINVAL, "cgb_write_matrix_csv: " + err); }
+        return CGB_OK;
+    });
+}
+
+// GapsResult::writeToFile (GapsResult.cpp:27-35)
+extern "C" int cgb_result_write_files(const char *pathPrefix, uint32_t nGenes, uint32_t nSamples, uint32_t nPatterns, const cgb_result *r)
+{
+    if (!pathPrefix || !r || !r->Amean || !r->Pmean || !r->Asd || !r->Psd) { return fail(CGB_EINVAL, "cgb_result_write_files: NULL argument"); }
+    return guarded("cgb_result_write_files", [&]()
+    {
+        const std::string label = std::string(pathPrefix) + "_" + std::to_string(nPatterns) + "_";
+        CGB_TRY(cgb_write_matrix_csv((label + "Amean.csv").c_str(), r->Amean, nGenes, nPatterns));
+        CGB_TRY(cgb_write_matrix_csv((label + "Pmean.csv").c_str(), r->Pmean, nSamples, nPatterns));
+        CGB_TRY(cgb_write_matrix_csv((label + "Asd.csv").c_str(), r->Asd, nGenes, nPatterns));
+        CGB_TRY(cgb_write_matrix_csv((label + "Psd.csv").c_str(), r->Psd, nSamples, nPatterns));
+        return CGB_OK;
+    });
+}
+
 static bool endsWith(const char *s, const char *suffix)
 {
     const size_t n = std::strlen(s), m = std::strlen(suffix);

@@ -391,6 +391,51 @@ static bool readDelimited(std::ifstream &f, char delimiter, bool gct, std::vecto
     return true;
 }
 
+// FileParser::writeToCsv (file_parser/FileParser.h:59-89): "" then "Col<j>" headers, "Row<i>" row names, values
+// through operator<<(float) — the default stream format, i.e. %g with six significant digits
+bool writeMatrixCsv(const char *path, const float *mat, uint32_t nrow, uint32_t ncol, std::string &err)
+{
+    if (fileType(path) != kCsv)
+    {
+        err = "output file must be a csv";
+        return false;
+    }
+    std::FILE *f = std::fopen(path, "w");
+    if (!f)
+    {
+        err = std::string("cannot create ") + path;
+        return false;
+    }
+    std::string text = "\"\"";
+    char buf[48];
+    for (uint32_t j = 0; j < ncol; ++j)
+    {
+        std::snprintf(buf, sizeof(buf), ",\"Col%u\"", j);
+        text += buf;
+    }
+    text += "\n";
+    for (uint32_t i = 0; i < nrow; ++i)
+    {
+        std::snprintf(buf, sizeof(buf), "\"Row%u\"", i);
+        text += buf;
+        for (uint32_t j = 0; j < ncol; ++j)
+        {
+            std::snprintf(buf, sizeof(buf), ",%g", static_cast<double>(mat[static_cast<size_t>(i) * ncol + j]));
+            text += buf;
+        }
+        text += "\n";
+        if (text.size() > (1u << 20))
+        {
+            if (std::fwrite(text.data(), 1, text.size(), f) != text.size()) { std::fclose(f); err = std::string("write error on ") + path; return false; }
+            text.clear();
+        }
+    }
+    const bool wrote = text.empty() || std::fwrite(text.data(), 1, text.size(), f) == text.size();
+    const bool closed = std::fclose(f) == 0;
+    if (!wrote || !closed) { err = std::string("write error on ") + path; }
+    return wrote && closed;
+}
+
 bool loadMatrixFile(const char *path, std::vector<float> &out, uint32_t &nrow, uint32_t &ncol, std::string &err)
 {
     const FileType t = fileType(path);

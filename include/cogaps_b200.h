@@ -151,6 +151,12 @@ int cgb_run_file(const char *dataPath, const char *uncertaintyPath, const cgb_pa
 /* Reads a matrix file into out (row-major, nrow*ncol floats; NULL: dimensions only).  Host only, no device needed. */
 int cgb_read_matrix_file(const char *path, float *out, uint64_t capacity, uint32_t *nrow, uint32_t *ncol);
 
+/* FileParser::writeToCsv (file_parser/FileParser.h:59-89) and GapsResult::writeToFile (GapsResult.cpp:27-35): a matrix
+ * (row-major) as the reference writes it — "" and "Col<j>" headers, "Row<i>" names, values in the default stream format
+ * (%g, six significant digits) — and the four result matrices to <prefix>_<nPatterns>_{Amean,Pmean,Asd,Psd}.csv.  Host only. */
+int cgb_write_matrix_csv(const char *path, const float *mat, uint32_t nrow, uint32_t ncol);
+int cgb_result_write_files(const char *pathPrefix, uint32_t nGenes, uint32_t nSamples, uint32_t nPatterns, const cgb_result *result);
+
 /* The compressed rows (byRows != 0) or compressed columns of a Matrix-Market file exactly as cgb_run_file hands them to
  * the sparse model's two samplers (SparseMatrix(path, ...), data_structures/SparseMatrix.cpp:52-107; SparseVector keeps
  * the positive entries in ascending index order, SparseVector.cpp:20-35): with useSparseOptimization, a whole-matrix

@@ -89,6 +89,11 @@ class RefLib(object):
         self.lib.cogaps_ref_read_file(str(path).encode(), fptr(out), C.byref(nrow), C.byref(ncol))
         return out
 
+    def write_csv(self, path, mat):
+        """FileParser::writeToCsv of the reference itself."""
+        mat = _f32(mat)
+        self.lib.cogaps_ref_write_csv(_path(path), fptr(mat), C.c_uint32(mat.shape[0]), C.c_uint32(mat.shape[1]))
+
     def run(self, data, uncertainty=None, snapshots=False, checkpointInterval=0, checkpointOutFile=None,
             checkpointInFile=None, **kw):
         """gaps::run; the checkpoint arguments are the reference's own (GapsParameters.h:37-38,46,56)."""

@@ -37,6 +37,7 @@
 #include "GapsResult.h"
 #include "GapsRunner.h"
 #include "data_structures/Matrix.h"
+#include "file_parser/FileParser.h"
 #include "utils/GlobalConfig.h"
 #include <boost/date_time/posix_time/posix_time.hpp> // the shim: its clock_marks, see cogaps_ref_last_run_seconds
 
@@ -218,6 +219,13 @@ int cogaps_ref_read_file(const char *path, float *out, uint32_t *nrow, uint32_t 
     *nrow = m.nRow();
     *ncol = m.nCol();
     fromMatrix(m, out);
+    return 0;
+}
+
+// FileParser::writeToCsv through the reference itself (src/file_parser/FileParser.h:59-89)
+int cogaps_ref_write_csv(const char *path, const float *data, uint32_t nrow, uint32_t ncol)
+{
+    FileParser::writeToCsv(std::string(path), toMatrix(data, nrow, ncol));
     return 0;
 }
 

@@ -261,3 +261,39 @@ def test_number_tokens_parse_like_the_reference(tmp_path):
                       + "".join("%d  1\t%s\r\n" % (i + 1, tokens[i]) for i in pos))        # odd spacing, CRLF
     nrow, ncol, ptr, idx, val = cg.read_matrix_csr(nonneg, by_rows=False)
     assert np.array_equal(idx, np.array(pos, np.uint32)) and np.array_equal(bits(val), bits(got[pos]))
+
+
+def test_result_matrices_are_written_like_the_reference(tmp_path):
+    """FileParser::writeToCsv (FileParser.h:59-89) / GapsResult::writeToFile (GapsResult.cpp:27-35): byte for byte against
+    the reference's own writer where it is built, and readable by the csv reader either way."""
+    import ctypes as C
+    import cogaps_b200 as cg
+    from cogaps_b200._runhelp import make_params, ResultArrays
+    rng = np.random.default_rng(8)
+    m = (rng.gamma(2.0, 1.5, (19, 5)) * 10.0 ** rng.integers(-9, 9, (19, 5))).astype(np.float32)
+    m[0, 0], m[1, 1], m[2, 2], m[3, 3] = 0.0, 1.0, 123456.0, 1234567.0        # %g: 0, 1, 123456, 1.23457e+06
+    ours = tmp_path / "ours.csv"
+    cg.write_matrix_csv(ours, m)
+    text = ours.read_text()
+    assert text.splitlines()[0] == '"",' + ",".join('"Col%d"' % j for j in range(5))
+    assert text.splitlines()[2].startswith('"Row1",')
+    if RefLib.available("scalar"):
+        theirs = tmp_path / "theirs.csv"
+        RefLib("scalar").write_csv(theirs, m)
+        assert ours.read_bytes() == theirs.read_bytes()
+    # six significant digits come back; "1.23457e+06" is not a number the reference's reader accepts ('+'), so stay below
+    small = np.where(np.abs(m) < 1e5, m, np.float32(2.5)).astype(np.float32)
+    small[np.abs(small) < 1e-4] = np.float32(0.125)
+    cg.write_matrix_csv(ours, small)
+    assert np.allclose(cg.read_matrix_file(ours), small, rtol=1e-5)
+    # the four result files
+    p = make_params(nPatterns=3)
+    res = ResultArrays(p, 7, 4)
+    for name, arr in (("Amean", res.Amean), ("Asd", res.Asd), ("Pmean", res.Pmean), ("Psd", res.Psd)):
+        arr[...] = rng.random(arr.shape, dtype=np.float32)
+    cg.write_result_files(tmp_path / "run", res)
+    for name, arr in (("Amean", res.Amean), ("Asd", res.Asd), ("Pmean", res.Pmean), ("Psd", res.Psd)):
+        back = cg.read_matrix_file(tmp_path / ("run_3_%s.csv" % name))
+        assert back.shape == arr.shape and np.allclose(back, arr, rtol=1e-5, atol=1e-9)
+    with pytest.raises(cg.CogapsError, match="must be a csv"):
+        cg.write_matrix_csv(tmp_path / "x.tsv", m)
