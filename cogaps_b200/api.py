@@ -236,6 +236,23 @@ def checkpoint_rewrite(in_path, out_path):
     check(lib().cgb_checkpoint_rewrite(_path(in_path), _path(out_path)))
 
 
+def buildReport():
+    """buildReport() (R/CoGAPS.R; getBuildReport_cpp, src/Cogaps.cpp:217-220): how the library was built"""
+    return lib().cgb_build_report().decode()
+
+
+def checkpointsEnabled():
+    """checkpointsEnabled() (checkpointsEnabled_cpp, src/Cogaps.cpp:223-231): always — cgb_run_ex reads and writes the
+    reference's checkpoint files"""
+    return True
+
+
+def compiledWithOpenMPSupport():
+    """compiledWithOpenMPSupport() (src/Cogaps.cpp:234-242): no host thread team here; the fan-out over the proposals of a
+    batch is the GPU"""
+    return False
+
+
 def read_matrix_file(path):
     """A data / uncertainty file as the path overload of gaps::run reads it (.mtx, .csv, .tsv, .gct;
     src/file_parser/): nrow x ncol fp32 array.  Host only."""
