@@ -29,22 +29,15 @@ struct Side
     char name;
 };
 
-// gaps::nonZeroMean over the sampler's orientation, one fp32 running sum (MatrixMath.cpp:39-55); lambda as the
-// model's constructor derives it (DenseNormalModel.h:75-77)
+// lambda as the model's constructor derives it (DenseNormalModel.h:75-77) from gaps::nonZeroMean over the sampler's
+// orientation — through the same runningSum the samplers use (sampler.h), so the replay also holds that to the oracle:
+// a same-bin exchange draws its new mass with scale 1 / lambda (ProposalQueue.cpp:266-276)
 float lambdaOf(const float *data, uint32_t nrow, uint32_t ncol, bool rowsAreDataRows, float alpha, uint32_t k)
 {
     float sum = 0.f;
     unsigned nnz = 0;
-    const uint32_t nRows = rowsAreDataRows ? nrow : ncol, L = rowsAreDataRows ? ncol : nrow;
-    for (uint32_t r = 0; r < nRows; ++r)
-    {
-        for (uint32_t l = 0; l < L; ++l)
-        {
-            const float v = rowsAreDataRows ? data[static_cast<size_t>(r) * ncol + l] : data[static_cast<size_t>(l) * ncol + r];
-            sum += v;
-            if (v > 0.f) { ++nnz; }
-        }
-    }
+    if (rowsAreDataRows) { runningSum(data, nrow, ncol, ncol, 1, sum, nnz); }
+    else { runningSum(data, ncol, nrow, 1, ncol, sum, nnz); }
     const float meanD = sum / static_cast<float>(nnz);
     return alpha * std::sqrt(static_cast<float>(static_cast<uint64_t>(k)) / meanD);
 }

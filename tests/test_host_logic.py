@@ -426,6 +426,10 @@ def test_generator_replay_notices_a_wrong_trace(oracle):
             assert checked == at and ("rng state" in msg or "r1" in msg)
     rc, checked, msg = _replay(data, trace[:-7], **kw)
     assert rc != 0 and "more proposals than the trace" in msg
+    # lambda (alpha * sqrt(k / nonZeroMean(D)), through the samplers' own running sum) is held too: a same-bin exchange
+    # draws its new mass with scale 1 / lambda, so other data under the same trace shows up in an atom's mass
+    rc, checked, msg = _replay(data * np.float32(1.5), trace, **kw)
+    assert rc != 0 and "mass bits" in msg
     rc, checked, msg = _replay(data, trace, **dict(kw, seed=43))
     assert rc == 0          # not a typo: the seeder starts from seed|1 (Random.cpp:222-223), 42 and 43 are one stream
     rc, checked, msg = _replay(data, trace, **dict(kw, seed=44))
