@@ -253,6 +253,20 @@ def compiledWithOpenMPSupport():
     return False
 
 
+def getFileInfo(path):
+    """getFileInfo_cpp (src/Cogaps.cpp:245-256): dimensions, rowNames, colNames of a data file.  As in the reference,
+    colNames come from the header of .csv / .tsv files and rowNames are always empty.  Host only."""
+    raw = os.fspath(path).encode()
+    nrow, ncol = C.c_uint32(), C.c_uint32()
+    check(lib().cgb_read_matrix_file(raw, None, 0, C.byref(nrow), C.byref(ncol)))
+    needed, count = C.c_uint64(), C.c_uint32()
+    check(lib().cgb_file_col_names(raw, None, 0, C.byref(needed), C.byref(count)))
+    buf = C.create_string_buffer(max(int(needed.value), 1))
+    check(lib().cgb_file_col_names(raw, buf, needed.value, C.byref(needed), C.byref(count)))
+    names = buf.raw[:needed.value].split(b"\0")[:count.value]
+    return {"dimensions": (nrow.value, ncol.value), "rowNames": [], "colNames": [n.decode(errors="replace") for n in names]}
+
+
 def read_matrix_file(path):
     """A data / uncertainty file as the path overload of gaps::run reads it (.mtx, .csv, .tsv, .gct;
     src/file_parser/): nrow x ncol fp32 array.  Host only."""

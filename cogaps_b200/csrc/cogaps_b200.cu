@@ -3083,6 +3083,35 @@ void compressTriplets(const std::vector<uint32_t> &major, const std::vector<uint
                       bool &anyNegative);
 }
 
+namespace cgb { bool loadColumnNames(const char *path, std::vector<std::string> &names, std::string &err); }
+
+// getFileInfo_cpp's colNames (src/Cogaps.cpp:245-256): the names, each followed by a NUL, packed into buf
+extern "C" int cgb_file_col_names(const char *path, char *buf, uint64_t capacity, uint64_t *needed, uint32_t *count)
+{
+    if (!path || !needed || !count) { return fail(CGB_EINVAL, "cgb_file_col_names: NULL argument"); }
+    return guarded("cgb_file_col_names", [&]()
+    {
+        std::vector<std::string> names;
+        std::string err;
+        if (!loadColumnNames(path, names, err)) { return fail(CGB_EINVAL, "cgb_file_col_names: " + err); }
+        uint64_t total = 0;
+        for (size_t i = 0; i < names.size(); ++i) { total += names[i].size() + 1; }
+        *needed = total;
+        *count = static_cast<uint32_t>(names.size());
+        if (buf != nullptr)
+        {
+            if (capacity < total) { return fail(CGB_EINVAL, "cgb_file_col_names: buffer too small"); }
+            char *p = buf;
+            for (size_t i = 0; i < names.size(); ++i)
+            {
+                std::memcpy(p, names[i].c_str(), names[i].size() + 1);
+                p += names[i].size() + 1;
+            }
+        }
+        return CGB_OK;
+    });
+}
+
 namespace cgb { bool writeMatrixCsv(const char *path, const float *mat, uint32_t nrow, uint32_t ncol, std::string &err); }
 
 extern "C" int cgb_write_matrix_csv(const char *path, const float *mat, uint32_t nrow, uint32_t ncol)

@@ -436,6 +436,49 @@ bool writeMatrixCsv(const char *path, const float *mat, uint32_t nrow, uint32_t 
     return wrote && closed;
 }
 
+// FileParser::colNames (what getFileInfo_cpp hands to R, src/Cogaps.cpp:245-256): the trimmed cells of the header line
+// of a .csv / .tsv file, without the empty corner cell when row names are present
+// (CharacterDelimitedParser.cpp:78-98).  .gct and .mtx files have none — and no parser of the reference ever fills
+// rowNames, so those are always empty.
+bool loadColumnNames(const char *path, std::vector<std::string> &names, std::string &err)
+{
+    names.clear();
+    const FileType t = fileType(path);
+    if (t == kInvalid)
+    {
+        err = "Invalid file type";
+        return false;
+    }
+    if (t == kMtx || t == kGct) { return true; }
+    std::ifstream f(path);
+    if (!f.is_open())
+    {
+        err = std::string("cannot open ") + path;
+        return false;
+    }
+    std::string header;
+    if (!std::getline(f, header))
+    {
+        err = "Invalid character delimited file";
+        return false;
+    }
+    const char delimiter = (t == kCsv) ? ',' : '\t';
+    std::vector<std::string> cells;
+    {
+        std::string cell;
+        std::stringstream ss(header);
+        while (std::getline(ss, cell, delimiter)) { cells.push_back(cell); }
+        if (!header.empty() && header[header.size() - 1] == delimiter) { cells.push_back(std::string()); }
+    }
+    for (size_t i = 0; i < cells.size(); ++i)
+    {
+        const std::string name = trim(cells[i]);
+        if (i == 0 && name.empty()) { continue; } // the corner cell above the row names
+        names.push_back(name);
+    }
+    return true;
+}
+
 bool loadMatrixFile(const char *path, std::vector<float> &out, uint32_t &nrow, uint32_t &ncol, std::string &err)
 {
     const FileType t = fileType(path);

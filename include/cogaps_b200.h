@@ -151,6 +151,12 @@ int cgb_run_file(const char *dataPath, const char *uncertaintyPath, const cgb_pa
 /* Reads a matrix file into out (row-major, nrow*ncol floats; NULL: dimensions only).  Host only, no device needed. */
 int cgb_read_matrix_file(const char *path, float *out, uint64_t capacity, uint32_t *nrow, uint32_t *ncol);
 
+/* getFileInfo_cpp (src/Cogaps.cpp:245-256) = cgb_read_matrix_file(path, NULL, 0, &nrow, &ncol) for the dimensions plus
+ * this for colNames: the header cells of a .csv / .tsv file as FileParser::colNames returns them, each followed by a NUL,
+ * packed into buf (size it with buf == NULL).  .mtx and .gct files have none, and rowNames are empty for every format in
+ * the reference (no parser fills them), so there is nothing to export for those.  Host only. */
+int cgb_file_col_names(const char *path, char *buf, uint64_t capacity, uint64_t *needed, uint32_t *count);
+
 /* FileParser::writeToCsv (file_parser/FileParser.h:59-89) and GapsResult::writeToFile (GapsResult.cpp:27-35): a matrix
  * (row-major) as the reference writes it — "" and "Col<j>" headers, "Row<i>" names, values in the default stream format
  * (%g, six significant digits) — and the four result matrices to <prefix>_<nPatterns>_{Amean,Pmean,Asd,Psd}.csv.  Host only. */

@@ -89,6 +89,18 @@ class RefLib(object):
         self.lib.cogaps_ref_read_file(str(path).encode(), fptr(out), C.byref(nrow), C.byref(ncol))
         return out
 
+    def file_info(self, path):
+        """getFileInfo_cpp through the reference's own FileParser: (nrow, ncol), rowNames, colNames"""
+        nrow, ncol = C.c_uint32(), C.c_uint32()
+        counts = (C.c_uint32 * 2)()
+        buf = C.create_string_buffer(1 << 20)
+        rc = self.lib.cogaps_ref_file_info(_path(path), C.byref(nrow), C.byref(ncol), buf, C.c_uint64(len(buf)), counts)
+        if rc != 0:
+            raise RuntimeError("cogaps_ref_file_info failed")
+        names = buf.raw.split(b"\0")[:counts[0] + counts[1]]
+        names = [n.decode(errors="replace") for n in names]
+        return (nrow.value, ncol.value), names[:counts[0]], names[counts[0]:]
+
     def write_csv(self, path, mat):
         """FileParser::writeToCsv of the reference itself."""
         mat = _f32(mat)

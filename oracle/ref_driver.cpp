@@ -222,6 +222,30 @@ int cogaps_ref_read_file(const char *path, float *out, uint32_t *nrow, uint32_t 
     return 0;
 }
 
+// getFileInfo_cpp's three fields through the reference's own FileParser (src/Cogaps.cpp:245-256): names are packed
+// NUL-separated into buf; counts[0] = rowNames, counts[1] = colNames
+int cogaps_ref_file_info(const char *path, uint32_t *nrow, uint32_t *ncol, char *buf, uint64_t capacity, uint32_t *counts)
+{
+    FileParser fp((std::string(path)));
+    *nrow = fp.nRow();
+    *ncol = fp.nCol();
+    std::vector<std::string> rows = fp.rowNames(), cols = fp.colNames();
+    counts[0] = static_cast<uint32_t>(rows.size());
+    counts[1] = static_cast<uint32_t>(cols.size());
+    uint64_t used = 0;
+    for (size_t pass = 0; pass < 2; ++pass)
+    {
+        const std::vector<std::string> &v = pass == 0 ? rows : cols;
+        for (size_t i = 0; i < v.size(); ++i)
+        {
+            if (used + v[i].size() + 1 > capacity) { return -1; }
+            std::memcpy(buf + used, v[i].c_str(), v[i].size() + 1);
+            used += v[i].size() + 1;
+        }
+    }
+    return 0;
+}
+
 // FileParser::writeToCsv through the reference itself (src/file_parser/FileParser.h:59-89)
 int cogaps_ref_write_csv(const char *path, const float *data, uint32_t nrow, uint32_t ncol)
 {

@@ -297,3 +297,35 @@ def test_result_matrices_are_written_like_the_reference(tmp_path):
         assert back.shape == arr.shape and np.allclose(back, arr, rtol=1e-5, atol=1e-9)
     with pytest.raises(cg.CogapsError, match="must be a csv"):
         cg.write_matrix_csv(tmp_path / "x.tsv", m)
+
+
+def test_file_info_like_the_reference(tmp_path):
+    """getFileInfo_cpp (src/Cogaps.cpp:245-256): dimensions, rowNames (never filled by any parser of the reference),
+    colNames (header cells of .csv / .tsv)."""
+    import cogaps_b200 as cg
+    m = _matrix(4, (6, 4))
+    files = {}
+    for kind, ext, sep, names, quoted in (("csv_names", ".csv", ",", True, False), ("csv_plain", ".csv", ",", False, False),
+                                          ("tsv_quoted", ".tsv", "\t", True, True)):
+        path = tmp_path / (kind + ext)
+        _write_delimited(str(path), m, sep, row_names=names, quoted=quoted)
+        files[kind] = path
+    mtx = tmp_path / "data.mtx"
+    _write_mtx(str(mtx), m, np.random.default_rng(1))
+    files["mtx"] = mtx
+    gct = tmp_path / "data.gct"
+    with open(gct, "w") as f:
+        f.write("#1.2\n%d\t%d\n" % m.shape)
+        f.write("\t".join(["NAME", "Description"] + ["s%d" % j for j in range(m.shape[1])]) + "\n")
+        for i in range(m.shape[0]):
+            f.write("\t".join(["g%d" % i, "desc"] + [repr(float(v)) for v in m[i]]) + "\n")
+    files["gct"] = gct
+    for kind, path in files.items():
+        info = cg.getFileInfo(path)
+        assert info["dimensions"] == (6, 4), kind
+        assert info["rowNames"] == []
+        want = ["s%d" % j for j in range(4)] if kind.startswith(("csv", "tsv")) else []
+        assert info["colNames"] == want, kind
+        if RefLib.available("scalar"):
+            dims, rows, cols = RefLib("scalar").file_info(path)
+            assert (dims, rows, cols) == (info["dimensions"], info["rowNames"], info["colNames"]), kind
