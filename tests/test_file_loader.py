@@ -329,3 +329,44 @@ def test_file_info_like_the_reference(tmp_path):
         if RefLib.available("scalar"):
             dims, rows, cols = RefLib("scalar").file_info(path)
             assert (dims, rows, cols) == (info["dimensions"], info["rowNames"], info["colNames"]), kind
+
+
+def test_triplet_scanner_agrees_with_the_dense_reader_on_random_files(tmp_path):
+    """Differential test of the two Matrix-Market readers (the stream-extractor one that mirrors MtxParser.cpp and the
+    hand-rolled scanner behind the compressed-row route): random files with comments, ragged whitespace, CRLF, duplicate
+    cells, explicit zeros, scientific notation and trailing junk must give the same matrix or the same kind of error."""
+    import cogaps_b200 as cg
+    from cogaps_b200._lib import CogapsError
+    rng = np.random.default_rng(77)
+    seps = [" ", "  ", "\t", " \t "]
+    for trial in range(120):
+        nrow, ncol = int(rng.integers(1, 9)), int(rng.integers(1, 9))
+        n = int(rng.integers(0, 2 * nrow * ncol + 1))
+        lines = ["%%MatrixMarket matrix coordinate real general"]
+        for _ in range(int(rng.integers(0, 3))):
+            lines.append("% comment " + "x" * int(rng.integers(0, 5)))
+        lines.append("%d %d %d" % (nrow, ncol, n))
+        for _ in range(n):
+            i, j = int(rng.integers(1, nrow + 1)), int(rng.integers(1, ncol + 1))
+            kind = int(rng.integers(0, 6))
+            v = float(np.float32(rng.gamma(2.0, 2.0)))
+            tok = {0: repr(v), 1: "0", 2: "%d" % int(v), 3: _sci(v, 4), 4: "%.3f" % v, 5: ".5"}[kind]
+            lines.append(seps[int(rng.integers(0, 4))].join([str(i), str(j), tok]) + ("  " if rng.random() < 0.2 else ""))
+        if trial % 10 == 7:
+            lines.append("%d %d 1.0" % (nrow + 1, 1))               # outside the declared shape: an error in both
+        if trial % 10 == 3:
+            lines.append("junk that ends the triplets")              # both readers stop here without complaint
+        text = ("\r\n" if trial % 4 == 1 else "\n").join(lines) + ("\n" if trial % 3 else "")
+        path = tmp_path / ("f%d.mtx" % trial)
+        path.write_text(text)
+        try:
+            dense = cg.read_matrix_file(path)
+        except CogapsError:
+            with pytest.raises(CogapsError):
+                cg.read_matrix_csr(path)
+            continue
+        for by_rows, want in ((True, dense), (False, dense.T)):
+            r, c, ptr, idx, val = cg.read_matrix_csr(path, by_rows=by_rows)
+            wptr, widx, wval = _csr_of(want)
+            assert (r, c) == dense.shape
+            assert np.array_equal(ptr, wptr) and np.array_equal(idx, widx) and np.array_equal(bits(val), bits(wval)), trial
