@@ -346,15 +346,27 @@ def CoGAPS(data, params=None, nPatterns=None, nThreads=1, messages=True, outputF
             raise ValueError("unrecognized argument: %s" % k)
         params.setParam(k, v)
     params.validate()
-    data = np.asarray(data)
+    # `data` may be the name of a .mtx / .csv / .tsv / .gct file (cogaps_from_file_cpp, src/Cogaps.cpp:188-202): the
+    # library reads it itself; the matrix checks below are for in-memory data only, as in R (checkDataMatrix)
+    fromFile = isinstance(data, (str, os.PathLike))
+    if fromFile:
+        if uncertainty is not None and not isinstance(uncertainty, (str, os.PathLike)):
+            raise ValueError("uncertainty must be same data type as data (file name)")   # R/HelperFunctions.R:207-208
+        fileShape = getFileInfo(data)["dimensions"]      # also: "unsupported file extension" (R/HelperFunctions.R:8-12)
+        if uncertainty is not None and params.sparseOptimization:
+            raise ValueError("must use default uncertainty when enabling sparseOptimization")
+    else:
+        if isinstance(uncertainty, (str, os.PathLike)):
+            raise ValueError("uncertainty must be a matrix unless data is a file path")  # R/HelperFunctions.R:209-210
+        data = np.asarray(data)
     # checkInputs, R/HelperFunctions.R:203-260
-    if data.ndim != 2:
+    if not fromFile and data.ndim != 2:
         raise ValueError("data must be a matrix")
-    if np.isnan(data).any():
+    if not fromFile and np.isnan(data).any():
         raise ValueError("NA values in data")
-    if (data < 0).any():
+    if not fromFile and (data < 0).any():
         raise ValueError("negative values in data matrix")
-    if uncertainty is not None:
+    if uncertainty is not None and not fromFile:
         uncertainty = np.asarray(uncertainty)
         if (uncertainty < 0).any():
             raise ValueError("negative values in uncertainty matrix")
@@ -374,7 +386,8 @@ def CoGAPS(data, params=None, nPatterns=None, nThreads=1, messages=True, outputF
         return distributedCogaps(data, params, uncertainty, nThreads=nThreads, messages=messages,
                                  outputFrequency=outputFrequency, transposeData=transposeData,
                                  sequentialSampler=not asynchronousUpdates)
-    nGenes, nSamples = (data.shape[1], data.shape[0]) if transposeData else data.shape
+    shape = fileShape if fromFile else data.shape
+    nGenes, nSamples = (shape[1], shape[0]) if transposeData else shape
     if params.nPatterns >= min(nGenes, nSamples) and params.subsetDim == 0:
         pass  # R only warns here
     kw = dict(seed=int(params.seed), nPatterns=int(params.nPatterns), nIterations=int(params.nIterations),
@@ -395,8 +408,13 @@ def CoGAPS(data, params=None, nPatterns=None, nThreads=1, messages=True, outputF
     if checkpointInFile is not None:
         # the run continues with the archived nPatterns; the result arrays must be sized for it
         kw["nPatterns"] = int(checkpoint_info(checkpointInFile)["nPatterns"])
-    res = gaps_run(data, uncertainty=uncertainty, snapshots=bool(nSnapshots), checkpointInterval=int(checkpointInterval or 0),
-                   checkpointOutFile=checkpointOutFile, checkpointInFile=checkpointInFile, **kw)
+    if fromFile:
+        res = gaps_run_file(data, uncertainty_path=uncertainty, snapshots=bool(nSnapshots),
+                            checkpointInterval=int(checkpointInterval or 0), checkpointOutFile=checkpointOutFile,
+                            checkpointInFile=checkpointInFile, **kw)
+    else:
+        res = gaps_run(data, uncertainty=uncertainty, snapshots=bool(nSnapshots), checkpointInterval=int(checkpointInterval or 0),
+                       checkpointOutFile=checkpointOutFile, checkpointInFile=checkpointInFile, **kw)
     extras = dict(nBatchesA=res.nBatchesA, nBatchesP=res.nBatchesP, secondsUpdateA=res.secondsUpdateA,
                   secondsUpdateP=res.secondsUpdateP, algorithmicBytes=res.algorithmicBytes)
     return CogapsResult(res, params, extras)

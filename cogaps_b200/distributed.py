@@ -22,6 +22,7 @@ which samples the same posterior and is what a GPU is for.  `agnes(..., "complet
 linkage on the same 1 - correlation dissimilarity.
 """
 import copy
+import os
 
 import numpy as np
 
@@ -232,7 +233,11 @@ def distributedCogaps(data, params, uncertainty=None, nThreads=1, messages=False
             device = torch.device("cuda", torch.cuda.current_device())
     runner = runner or _default_runner
     genomeWide = params.distributed == "genome-wide"
-    nrow, ncol = data.shape
+    if isinstance(data, (str, os.PathLike)):             # a data file: every subset run reads its own rows (columns)
+        from .api import getFileInfo
+        nrow, ncol = getFileInfo(data)["dimensions"]
+    else:
+        nrow, ncol = data.shape
     subsetRows = bool(transposeData) != genomeWide       # createSets, R/SubsetData.R:87-88
     total = nrow if subsetRows else ncol
     sets = createSets(total, params.nSets, params.seed, params.explicitSets, params.samplingAnnotation, params.samplingWeight,

@@ -476,3 +476,32 @@ def test_distributed_driver_with_named_explicit_sets():
     assert seen[0] == ([1, 3, 5, 7, 9, 11], 2) and seen[1] == ([2, 4, 6, 8, 10, 12], 2)
     assert [s.tolist() for s in res.metadata["subsets"]] == [[1, 3, 5, 7, 9, 11], [2, 4, 6, 8, 10, 12]]
     assert res.sampleFactors.shape == (12, 3)
+
+
+def test_cogaps_accepts_a_data_file_name(tmp_path):
+    """CoGAPS(data = "file.mtx" / .csv / .tsv / .gct) — R/CoGAPS.R:90-156 with cogaps_from_file_cpp underneath: the checks
+    that need no device, and the distributed driver's plumbing with a stand-in runner."""
+    import cogaps_b200 as cg
+    from cogaps_b200.distributed import distributedCogaps
+    rng = np.random.default_rng(5)
+    m = rng.gamma(2.0, 1.0, (30, 12)).astype(np.float32)
+    path = tmp_path / "data.csv"
+    cg.write_matrix_csv(path, m)
+    assert cg.getFileInfo(path)["dimensions"] == (30, 12)
+    with pytest.raises(ValueError, match="same data type"):
+        cg.CoGAPS(path, nPatterns=3, uncertainty=np.ones_like(m), messages=False)
+    with pytest.raises(ValueError, match="file path"):
+        cg.CoGAPS(m, nPatterns=3, uncertainty=str(path), messages=False)
+    with pytest.raises(cg.CogapsError):
+        cg.CoGAPS(tmp_path / "data.txt", nPatterns=3, messages=False)                 # unsupported extension
+    seen = []
+
+    def runner(d, p, unc, subset, subsetDim, runKw):
+        seen.append((str(d), len(subset), subsetDim))
+        return _fake_runner(np.zeros((30, 12), np.float32), p, unc, subset, subsetDim, runKw)
+
+    params = cg.CogapsParams(nPatterns=3, distributed="single-cell", seed=42)
+    params.setParam("nSets", 3)
+    res = distributedCogaps(str(path), params, runner=runner)
+    assert seen[0] == (str(path), 4, 2) and len(seen) == 6                            # three subsets of four cells, two passes
+    assert res.sampleFactors.shape == (12, 3)
