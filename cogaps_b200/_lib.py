@@ -33,7 +33,7 @@ EXPORTS = [
     "cgb_run_ex", "cgb_sampler_serialize", "cgb_sampler_deserialize", "cgb_sampler_set_atoms", "cgb_stats_serialize",
     "cgb_stats_deserialize", "cgb_randstate_get_state", "cgb_randstate_set_state", "cgb_rng_get_state", "cgb_rng_set_state",
     "cgb_checkpoint_info_read", "cgb_checkpoint_rewrite", "cgb_read_matrix_csr",
-    "cgb_debug_replay_generator", "cgb_debug_replay_message", "cgb_run_file_ex", "cgb_debug_running_sum", "cgb_write_matrix_csv", "cgb_result_write_files", "cgb_file_col_names",
+    "cgb_debug_replay_generator", "cgb_debug_replay_message", "cgb_run_file_ex", "cgb_debug_running_sum", "cgb_write_matrix_csv", "cgb_result_write_files", "cgb_file_col_names", "cgb_debug_domain_fuzz",
 ]
 
 _lib = None
@@ -142,6 +142,7 @@ def lib():
                                       C.c_uint64, c_u64_p]
     L.cgb_debug_replay_generator.argtypes = [c_float_p, C.c_uint32, C.c_uint32, C.POINTER(CgbParams), vp, C.c_uint64, c_u64_p]
     L.cgb_debug_replay_message.restype = C.c_char_p
+    L.cgb_debug_domain_fuzz.argtypes = [C.c_uint64, C.c_uint64, C.c_uint32, c_u64_p]
     L.cgb_file_col_names.argtypes = [C.c_char_p, C.c_char_p, C.c_uint64, c_u64_p, c_u32_p]
     L.cgb_write_matrix_csv.argtypes = [C.c_char_p, c_float_p, C.c_uint32, C.c_uint32]
     L.cgb_result_write_files.argtypes = [C.c_char_p, C.c_uint32, C.c_uint32, C.c_uint32, C.POINTER(CgbResult)]

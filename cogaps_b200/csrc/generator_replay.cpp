@@ -10,6 +10,7 @@
 // through the very function the product applies outcomes with (applyToDomain, sampler.h).
 #include "sampler.h"
 
+#include <algorithm>
 #include <cmath>
 #include <cstdio>
 #include <cstring>
@@ -167,6 +168,117 @@ extern "C" int cgb_debug_replay_generator(const float *data, uint32_t nrow, uint
             g_replayMessage = "the trace holds proposals the generator never queued";
             return CGB_EINTERNAL;
         }
+        return CGB_OK;
+    }
+    catch (const std::exception &e)
+    {
+        g_replayMessage = e.what();
+        return CGB_ENOMEM;
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// Test hook, host only: the bin-indexed atomic domain (atomic_domain.h) against the reference's own data structures
+// restated naively — std::map<position, atom> for order and neighbours, std::vector for the pick order with
+// swap-with-last erases (ConcurrentAtomicDomain.cpp:14-132) — under a random workload of inserts, batched erases
+// (cacheErase + flushEraseCache) and in-gap moves, including positions in the last bin and at domainLength itself.
+// ------------------------------------------------------------------------------------------------
+#include <map>
+
+extern "C" int cgb_debug_domain_fuzz(uint64_t seed, uint64_t nBins, uint32_t nOps, uint64_t *opsDone)
+{
+    g_replayMessage.clear();
+    if (!opsDone || nBins == 0) { g_replayMessage = "bad argument"; return CGB_EINVAL; }
+    try
+    {
+        AtomicDomain dom;
+        dom.init(nBins);
+        Xoroshiro128plus seeder(seed);
+        HostRng rng(seeder);
+        std::map<uint64_t, uint32_t> byPos;      // position -> atom id in `dom`
+        std::vector<uint64_t> pick;              // the reference's mAtoms, as positions
+        std::map<uint64_t, size_t> pickIndex;    // position -> index in `pick` (the model's ConcurrentAtom::mIndex)
+        const uint32_t growUntil = nOps / 8;     // inserts dominate until the domain holds this many atoms
+        const uint64_t len = dom.domainLength();
+        for (uint32_t op = 0; op < nOps; ++op)
+        {
+            *opsDone = op;
+            const uint32_t kind = rng.uniform32(0, 9);
+            if (kind < (pick.size() < growUntil ? 7u : 4u) || pick.size() < 4)
+            {
+                // insert at a free position; now and then in the last bin or at the very end of the domain
+                uint64_t pos = rng.uniform64(1, len);
+                if (kind == 0) { pos = len - rng.uniform64(0, 3); }
+                if (byPos.count(pos)) { if (!dom.occupied(pos)) { g_replayMessage = "occupied() misses an atom"; return CGB_EINTERNAL; } continue; }
+                if (dom.occupied(pos)) { g_replayMessage = "occupied() reports a free position"; return CGB_EINTERNAL; }
+                const uint32_t id = dom.insert(pos, static_cast<float>(op));
+                byPos[pos] = id;
+                pickIndex[pos] = pick.size();
+                pick.push_back(pos);
+            }
+            else if (kind < 8)
+            {
+                // a batch of erases: cached in any order, flushed in increasing position order, swap-with-last each
+                const uint32_t n = rng.uniform32(1, 3);
+                std::vector<uint64_t> victims;
+                for (uint32_t i = 0; i < n && victims.size() < pick.size(); ++i)
+                {
+                    const uint64_t pos = pick[rng.uniform32(0, static_cast<uint32_t>(pick.size() - 1))];
+                    bool dup = false;
+                    for (size_t j = 0; j < victims.size(); ++j) { dup = dup || victims[j] == pos; }
+                    if (!dup) { victims.push_back(pos); dom.cacheErase(byPos[pos]); }
+                }
+                dom.flushEraseCache();
+                std::sort(victims.begin(), victims.end());
+                for (size_t j = 0; j < victims.size(); ++j)
+                {
+                    const size_t at = pickIndex[victims[j]];
+                    pick[at] = pick.back();
+                    pickIndex[pick[at]] = at;
+                    pick.pop_back();
+                    pickIndex.erase(victims[j]);
+                    byPos.erase(victims[j]);
+                }
+            }
+            else
+            {
+                // move inside the gap between the neighbours (ProposalQueue.cpp:209-248)
+                const uint32_t vi = rng.uniform32(0, static_cast<uint32_t>(pick.size() - 1));
+                const uint64_t pos = pick[vi];
+                std::map<uint64_t, uint32_t>::iterator it = byPos.find(pos), nx = it, pv = it;
+                ++nx;
+                const uint64_t hi = (nx != byPos.end()) ? nx->first : len + 1;
+                const uint64_t lo = (it != byPos.begin()) ? (--pv)->first : 0;
+                if (hi - lo < 2) { continue; }
+                const uint64_t to = rng.uniform64(lo + 1, hi - 1);
+                if (to == pos) { continue; }
+                const uint32_t id = it->second;
+                dom.move(id, to);
+                byPos.erase(it);
+                byPos[to] = id;
+                pickIndex.erase(pos);
+                pickIndex[to] = vi;
+                pick[vi] = to;
+            }
+            // compare: size, pick order, sorted order with neighbours, first atom
+            if (dom.size() != pick.size() || byPos.size() != pick.size()) { g_replayMessage = "size differs from the model"; return CGB_EINTERNAL; }
+            if ((op & 1023u) == 0 || op + 1 == nOps || (pick.size() < 64 && (op & 15u) == 0))
+            {
+                if (!dom.checkInvariants()) { g_replayMessage = "checkInvariants failed"; return CGB_EINTERNAL; }
+                for (size_t i = 0; i < pick.size(); ++i)
+                {
+                    if (dom.atom(dom.atIndex(static_cast<uint32_t>(i))).pos != pick[i]) { g_replayMessage = "pick order differs from the model"; return CGB_EINTERNAL; }
+                }
+                uint32_t a = dom.front();
+                for (std::map<uint64_t, uint32_t>::const_iterator it = byPos.begin(); it != byPos.end(); ++it)
+                {
+                    if (a == kNoAtom || dom.atom(a).pos != it->first || a != it->second) { g_replayMessage = "sorted order differs from the model"; return CGB_EINTERNAL; }
+                    a = dom.atom(a).right;
+                }
+                if (a != kNoAtom) { g_replayMessage = "the domain holds atoms the model does not"; return CGB_EINTERNAL; }
+            }
+        }
+        *opsDone = nOps;
         return CGB_OK;
     }
     catch (const std::exception &e)

@@ -445,6 +445,11 @@ typedef struct cgb_trace_record
 int cgb_debug_replay_generator(const float *data, uint32_t nrow, uint32_t ncol, const cgb_params *params,
                                const cgb_trace_record *trace, uint64_t n, uint64_t *checked);
 const char *cgb_debug_replay_message(void);
+/* Host only: the library's bin-indexed atomic domain against a naive restatement of the reference's structures (a sorted
+ * map for order and neighbours, a vector with swap-with-last erases for the pick order — ConcurrentAtomicDomain.cpp:
+ * 14-132) under nOps random inserts, batched erases and in-gap moves over nBins bins.  CGB_OK, or CGB_EINTERNAL with
+ * cgb_debug_replay_message() and *opsDone = the operation that diverged. */
+int cgb_debug_domain_fuzz(uint64_t seed, uint64_t nBins, uint32_t nOps, uint64_t *opsDone);
 
 #ifdef __cplusplus
 }

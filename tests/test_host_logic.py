@@ -505,3 +505,16 @@ def test_cogaps_accepts_a_data_file_name(tmp_path):
     res = distributedCogaps(str(path), params, runner=runner)
     assert seen[0] == (str(path), 4, 2) and len(seen) == 6                            # three subsets of four cells, two passes
     assert res.sampleFactors.shape == (12, 3)
+
+
+@pytest.mark.parametrize("seed,nBins,nOps", [(1, 60, 20000), (2, 3, 5000), (3, 4000, 120000), (4, 1, 2000), (5, 400000, 200000)])
+def test_atomic_domain_against_a_naive_model(seed, nBins, nOps):
+    """atomic_domain.h (first-atom-of-each-bin table + hierarchical bitmap + linked atoms) against the reference's own
+    structures restated naively — a sorted map and a swap-erase vector (ConcurrentAtomicDomain.cpp:14-132) — under
+    random inserts, batched erases and in-gap moves: crowded bins (60 bins, thousands of atoms), a single bin, the
+    bench-like sparse regime, positions in the last bin and at domainLength itself."""
+    import ctypes as C
+    from cogaps_b200._lib import lib
+    done = C.c_uint64()
+    rc = lib().cgb_debug_domain_fuzz(seed, nBins, nOps, C.byref(done))
+    assert rc == 0 and done.value == nOps, (done.value, lib().cgb_debug_replay_message().decode())
