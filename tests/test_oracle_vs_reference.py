@@ -266,3 +266,31 @@ def test_dense_and_sparse_models_agree_where_their_assumptions_coincide(oracle):
     assert np.all(np.abs(smu_d - smu_s) <= 1e-3 * np.maximum(np.abs(smu_d), scale))
     cd, cs = oracle.chisq(data, A, Pm), oracle.chisq_sparse(data, A, Pm)
     assert cs[0] == pytest.approx(cd[0], rel=1e-3) and cs[1] == pytest.approx(cd[1], rel=1e-3)
+
+
+def test_fixed_matrix_behaviour_of_the_reference_suite(oracle):
+    """tests/testthat/test_fixed_matrix.R: with P (or A) fixed to a previous run's result the other factor is recovered
+    better than with a random fixed matrix, and the fixed factor's reported mean is all zeros (only the free factor's
+    statistics are accumulated, GapsRunner.cpp:301-308)."""
+    data = load_data("gist")
+    kw = dict(seed=42, nPatterns=5, nIterations=100, outputFrequency=0)
+    res1 = oracle.run(data, **kw)
+    rng = np.random.default_rng(1)
+    for which, free, fixed, rows in (("P", "Amean", "Pmean", data.shape[1]), ("A", "Pmean", "Amean", data.shape[0])):
+        res2 = oracle.run(data, whichMatrixFixed=which, fixedPatterns=getattr(res1, fixed), **kw)
+        res3 = oracle.run(data, whichMatrixFixed=which, fixedPatterns=rng.uniform(1, 10, (rows, 5)).astype(np.float32), **kw)
+        assert abs((getattr(res1, free) - getattr(res2, free)).sum()) < abs((getattr(res1, free) - getattr(res3, free)).sum())
+        assert getattr(res3, fixed).min() == 0.0 and getattr(res3, fixed).max() == 0.0
+        assert res3.meanChiSq == 0.0                                    # GapsRunner.cpp:478-485
+
+
+def test_reported_mean_chisq_matches_the_recomputation(oracle):
+    """tests/testthat/test_chisq.R: meanChiSq == sum(((D - Amean Pmean^T) / unc)^2) to float precision times the size of
+    the matrix, with an explicit uncertainty of 0.1 D."""
+    data = load_data("gist")
+    unc = (0.1 * data).astype(np.float32)
+    assert unc.min() > 0
+    res = oracle.run(data, uncertainty=unc, seed=1, nPatterns=3, nIterations=300, outputFrequency=0)
+    M = res.Amean.astype(np.float64) @ res.Pmean.astype(np.float64).T
+    calculated = (((data.astype(np.float64) - M) / unc.astype(np.float64)) ** 2).sum()
+    assert res.meanChiSq == pytest.approx(calculated, rel=1e-7 * data.size)
