@@ -225,6 +225,25 @@ def test_oracle_and_live_reference_agree_on_files_and_resumes(oracle, name, tmp_
             assert np.array_equal(bits(getattr(ores, f)), bits(getattr(ofull, f))), f
 
 
+def test_checkpoint_system_as_the_reference_suite_tests_it(oracle, tmp_path):
+    """tests/testthat/test_checkpoints.R: GIST, checkpointInterval=51, nIterations=100, seed 22; the second run resumes
+    with ANOTHER seed (33) and must reproduce the first run's matrices — seed and random state come from the file."""
+    data = load_data("gist")
+    ck = tmp_path / "test.out"
+    kw = dict(nPatterns=7, nIterations=100, outputFrequency=0)
+    run1 = oracle.run(data, options=oracle.options(checkpointInterval=51, checkpointOutFile=ck), seed=22, **kw)
+    run2 = oracle.run(data, options=oracle.options(checkpointInFile=ck, checkpointOutFile=tmp_path / "again.out"), seed=33, **kw)
+    assert np.array_equal(bits(run1.Amean), bits(run2.Amean)) and np.array_equal(bits(run1.Pmean), bits(run2.Pmean))
+    assert run2.seed == 22
+    from oracle.harness import RefLib
+    if RefLib.available("scalar"):
+        ref = RefLib("scalar")
+        r1 = ref.run(data, checkpointInterval=51, checkpointOutFile=tmp_path / "ref.out", seed=22, **kw)
+        r2 = ref.run(data, checkpointInFile=tmp_path / "ref.out", checkpointOutFile=tmp_path / "ref2.out", seed=33, **kw)
+        assert np.array_equal(bits(r1.Amean), bits(r2.Amean)) and np.array_equal(bits(r1.Amean), bits(run1.Amean))
+        assert read(tmp_path / "ref.out") == read(ck)
+
+
 def test_what_the_archive_leaves_out_restarts_like_in_the_reference(oracle, tmp_path):
     """Pump statistics, the chi-square / atom histories, totalUpdates and the queue-length averages are not archived
     (GapsStatistics.cpp:164-169 writes the four sums only): after a resume they restart, identically in the reference
