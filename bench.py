@@ -136,7 +136,7 @@ class ClockSampler(object):
 class Chain(object):
     """Both samplers of one factorisation, driven like runOnePhase (GapsRunner.cpp:272-327)."""
 
-    def __init__(self, data, k, seed, sparse=False):
+    def __init__(self, data, k, seed, sparse=False, updateMode=0):
         import cogaps_b200 as cg
         from cogaps_b200._runhelp import make_params
         self.cg = cg
@@ -150,6 +150,9 @@ class Chain(object):
         self.P.sync(self.A)
         self.A.extraInitialization()
         self.P.extraInitialization()
+        if updateMode:
+            self.A.setUpdateMode(updateMode)
+            self.P.setUpdateMode(updateMode)
 
     def step(self):
         nA = self.rng.poisson(float(max(self.A.nAtoms(), 10)))

@@ -51,6 +51,7 @@ class CgbParams(C.Structure):
         ("fixedPatterns", c_float_p),
         ("workerID", C.c_uint32),
         ("runningDistributed", C.c_int32),
+        ("updateMode", C.c_int32),
     ]
 
     @classmethod

@@ -34,6 +34,7 @@ EXPORTS = [
     "cgb_stats_deserialize", "cgb_randstate_get_state", "cgb_randstate_set_state", "cgb_rng_get_state", "cgb_rng_set_state",
     "cgb_checkpoint_info_read", "cgb_checkpoint_rewrite", "cgb_read_matrix_csr",
     "cgb_debug_replay_generator", "cgb_debug_replay_message", "cgb_run_file_ex", "cgb_debug_running_sum", "cgb_write_matrix_csv", "cgb_result_write_files", "cgb_file_col_names", "cgb_debug_domain_fuzz",
+    "cgb_sampler_set_update_mode", "cgb_sweep_reduction_order_for_length",
 ]
 
 _lib = None
@@ -110,6 +111,8 @@ def lib():
     L.cgb_sampler_set_persistent.argtypes = [vp, C.c_int32]
     L.cgb_sampler_reduction_order.argtypes = [vp, C.POINTER(CgbReductionOrder)]
     L.cgb_reduction_order_for_length.argtypes = [C.c_uint32, C.POINTER(CgbReductionOrder)]
+    L.cgb_sweep_reduction_order_for_length.argtypes = [C.c_uint32, C.POINTER(CgbReductionOrder)]
+    L.cgb_sampler_set_update_mode.argtypes = [vp, C.c_int32]
     L.cgb_stats_create.argtypes = [C.c_uint32, C.c_uint32, C.c_uint32, C.POINTER(vp)]
     L.cgb_stats_destroy.argtypes = [vp]
     L.cgb_stats_destroy.restype = None

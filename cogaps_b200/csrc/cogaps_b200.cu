@@ -3,8 +3,10 @@
 // point that computes needs an sm_100-class device and fails with CGB_ENODEVICE / CGB_ECUDA otherwise.
 #include "../../include/cogaps_b200.h"
 #include "kernels.cuh"
+#include "sweep.cuh"
 #include "sampler.h"
 
+#include <algorithm>
 #include <atomic>
 #include <chrono>
 #include <cstdio>
@@ -233,6 +235,7 @@ extern "C" void cgb_randstate_destroy(cgb_randstate *rs)
     if (!rs) { return; }
     if (rs->dErf) { cudaFree(rs->dErf); }
     if (rs->dErfinv) { cudaFree(rs->dErfinv); }
+    if (rs->dQgamma) { cudaFree(rs->dQgamma); }
     delete rs;
 }
 
@@ -243,6 +246,8 @@ static int uploadTables(cgb_randstate *rs)
     CGB_CUDA(cudaMalloc(&rs->dErfinv, sizeof(rs->tables.erfinv)));
     CGB_CUDA(cudaMemcpy(rs->dErf, rs->tables.erf, sizeof(rs->tables.erf), cudaMemcpyHostToDevice));
     CGB_CUDA(cudaMemcpy(rs->dErfinv, rs->tables.erfinv, sizeof(rs->tables.erfinv), cudaMemcpyHostToDevice));
+    CGB_CUDA(cudaMalloc(&rs->dQgamma, sizeof(rs->tables.qgamma)));
+    CGB_CUDA(cudaMemcpy(rs->dQgamma, rs->tables.qgamma, sizeof(rs->tables.qgamma), cudaMemcpyHostToDevice));
     CGB_CUDA(cudaStreamSynchronize(cudaStreamLegacy));
     return CGB_OK;
 }
@@ -416,6 +421,8 @@ extern "C" void cgb_sampler_destroy(cgb_sampler *s)
     cudaFree(s->dD); cudaFree(s->dS); cudaFree(s->dAP); cudaFree(s->dM); cudaFree(s->dColNonzero);
     cudaFree(s->dPartials); cudaFree(s->dTickets); cudaFree(s->dReducePartials); cudaFree(s->dPhaseClocks);
     cudaFree(s->dRowVersion); cudaFree(s->dStreamStats);
+    cudaFree(s->dSwPos); cudaFree(s->dSwMass); cudaFree(s->dSwCount); cudaFree(s->dSwCounters);
+    if (s->hSwCounters) { cudaFreeHost(s->hSwCounters); }
     cudaFree(s->dSpRowPtr); cudaFree(s->dSpIdx); cudaFree(s->dSpVal); cudaFree(s->dMrows); cudaFree(s->dZ1); cudaFree(s->dZ2);
     if (s->hCommitsMirror) { cudaFreeHost(const_cast<unsigned long long*>(s->hCommitsMirror)); }
     if (s->hAlive) { cudaFreeHost(const_cast<uint32_t*>(s->hAlive)); }
@@ -1688,11 +1695,296 @@ static int sequentialUpdate(cgb_sampler *s, uint32_t nSteps)
 }
 
 // AsynchronousGibbsSampler::update, AsynchronousGibbsSampler.h:88-122
+
+// ------------------------------------------------------------------------------------------------
+// Row-parallel sweep (sweep.cuh; cgb_params.updateMode == CGB_UPDATE_SWEEP): the whole update() is ONE launch with one
+// CTA per row of the factor matrix.  The atoms live on the device, one run sorted by position per row; the host only
+// draws the Philox key from the seeder, forms the proposal weights, and reads the counters back.
+// ------------------------------------------------------------------------------------------------
+static const uint32_t kSweepInitialCap = 64;
+static const size_t kSweepMaxSmem = 227u * 1024u;
+
+static uint32_t sweepThreadsForLength(uint32_t L) { return L <= 4096u ? 128u : (L <= 16384u ? 256u : 512u); }
+
+static int cgb_sweep_reduction_order_for_length_body(uint32_t rowLength, cgb_reduction_order *out)
+{
+    CGB_CHECK(out && rowLength, "cgb_sweep_reduction_order_for_length: bad argument");
+    out->threadsPerSegment = sweepThreadsForLength(rowLength);
+    out->vectorWidth = kVec;
+    out->nSegments = 1;
+    out->segmentLength = roundUp(rowLength, 4);
+    return CGB_OK;
+}
+
+extern "C" int cgb_sweep_reduction_order_for_length(uint32_t rowLength, cgb_reduction_order *out)
+{
+    return guarded("cgb_sweep_reduction_order_for_length", [&]() { return cgb_sweep_reduction_order_for_length_body(rowLength, out); });
+}
+
+// The proposal weights of one update(), in f64, operation for operation what oracle/cogaps_oracle.c sweep_rates does
+// (this file is compiled with -ffp-contract=off): a birth falls into a given row with probability (1 - pDeath)/2/nRows;
+// a given atom is picked for a death / move / exchange with probability pDeath/2/n, 1/4/n, 1/4/n
+// (ProposalQueue.cpp:123-160, with the atom count frozen at the start of the update).
+struct SweepRates { double birthRow, deathAtom, moveAtom, exchAtom, perAtom; };
+
+static SweepRates sweepRates(uint64_t nAtoms, uint32_t nRows, uint32_t k, uint64_t binLength, double alpha)
+{
+    SweepRates w;
+    if (nAtoms < 2)
+    {
+        w.birthRow = 1.0 / static_cast<double>(nRows); // "always birth when 0 or 1 atoms exist", ProposalQueue.cpp:139-142
+        w.deathAtom = w.moveAtom = w.exchAtom = 0.0;
+    }
+    else
+    {
+        const uint64_t nElements = static_cast<uint64_t>(nRows) * k;
+        const double domainLength = static_cast<double>(binLength * nElements);
+        const double numer = static_cast<double>(nAtoms) * domainLength;
+        const float pDeath = static_cast<float>(numer / (numer + alpha * static_cast<double>(nElements) * (domainLength - static_cast<double>(nAtoms))));
+        w.birthRow = 0.5 * (1.0 - static_cast<double>(pDeath)) / static_cast<double>(nRows);
+        w.deathAtom = 0.5 * static_cast<double>(pDeath) / static_cast<double>(nAtoms);
+        w.moveAtom = 0.25 / static_cast<double>(nAtoms);
+        w.exchAtom = 0.25 / static_cast<double>(nAtoms);
+    }
+    w.perAtom = w.deathAtom + w.moveAtom + w.exchAtom;
+    return w;
+}
+
+// (re)allocates the per-row atom store with `cap` slots per row, keeping what the rows hold
+static int sweepEnsureStore(cgb_sampler *s, uint32_t cap)
+{
+    if (s->dSwCounters == nullptr)
+    {
+        CGB_CUDA(cudaMalloc(&s->dSwCounters, sizeof(SweepCounters)));
+        CGB_CUDA(cudaHostAlloc(&s->hSwCounters, sizeof(SweepCounters), cudaHostAllocDefault));
+    }
+    if (s->dSwPos != nullptr && cap <= s->swCap) { return CGB_OK; }
+    uint64_t *pos = nullptr;
+    float *mass = nullptr;
+    CGB_CUDA(cudaMalloc(&pos, static_cast<size_t>(s->nRows) * cap * sizeof(uint64_t)));
+    if (cudaMalloc(&mass, static_cast<size_t>(s->nRows) * cap * sizeof(float)) != cudaSuccess)
+    {
+        cudaFree(pos);
+        return fail(CGB_ENOMEM, "sweep: out of device memory for the atom store");
+    }
+    if (s->dSwPos != nullptr)
+    {
+        sweep_regrow_kernel<<<s->nRows, 64, 0, s->stream>>>(s->dSwPos, s->dSwMass, s->dSwCount, s->swCap, pos, mass, cap, s->nRows);
+        g_kernelLaunches.fetch_add(1);
+        CGB_CUDA(cudaGetLastError());
+        CGB_CUDA(cudaStreamSynchronize(s->stream));
+        cudaFree(s->dSwPos);
+        cudaFree(s->dSwMass);
+    }
+    else
+    {
+        CGB_CUDA(cudaMalloc(&s->dSwCount, static_cast<size_t>(s->nRows) * sizeof(uint32_t)));
+        CGB_CUDA(cudaMemsetAsync(s->dSwCount, 0, static_cast<size_t>(s->nRows) * sizeof(uint32_t), s->stream));
+        CGB_CUDA(cudaStreamSynchronize(s->stream));
+        s->swTotalAtoms = 0;
+    }
+    s->dSwPos = pos;
+    s->dSwMass = mass;
+    s->swCap = cap;
+    return CGB_OK;
+}
+
+static uint32_t sweepCapFor(uint32_t cap, uint32_t maxCount)
+{
+    // the store grows between updates so that a row practically never fills up within one (oracle: sweep_update)
+    return (2u * maxCount > cap) ? roundUp(4u * maxCount, 32u) : cap;
+}
+
+// host atomic domain -> per-row store (entering sweep mode)
+static int sweepFromDomain(cgb_sampler *s)
+{
+    const uint64_t n = s->domain.size();
+    const uint64_t binLength = s->domain.binLength();
+    const uint64_t Lseg = binLength * s->k;
+    std::vector<std::pair<uint64_t, float> > atoms(n);
+    for (uint64_t i = 0; i < n; ++i)
+    {
+        const Atom &a = s->domain.atom(s->domain.atIndex(static_cast<uint32_t>(i)));
+        atoms[i] = std::make_pair(a.pos, a.mass);
+    }
+    std::sort(atoms.begin(), atoms.end());
+    std::vector<uint32_t> count(s->nRows, 0u);
+    std::vector<uint32_t> rowOf(n);
+    uint32_t maxCount = 0;
+    for (uint64_t i = 0; i < n; ++i)
+    {
+        uint64_t row = atoms[i].first / Lseg;
+        if (row >= s->nRows) { row = s->nRows - 1; } // pos == domainLength lies one past the last bin (ProposalQueue.cpp:214)
+        rowOf[i] = static_cast<uint32_t>(row);
+        maxCount = std::max(maxCount, ++count[row]);
+    }
+    uint32_t cap = std::max(kSweepInitialCap, s->swCap);
+    cap = std::max(cap, sweepCapFor(cap, maxCount));
+    if (s->dSwPos != nullptr && cap > s->swCap)
+    {
+        cudaFree(s->dSwPos); cudaFree(s->dSwMass); cudaFree(s->dSwCount);
+        s->dSwPos = nullptr; s->dSwMass = nullptr; s->dSwCount = nullptr; s->swCap = 0;
+    }
+    CGB_TRY(sweepEnsureStore(s, cap));
+    std::vector<uint64_t> pos(static_cast<size_t>(s->nRows) * s->swCap, 0ull);
+    std::vector<float> mass(static_cast<size_t>(s->nRows) * s->swCap, 0.f);
+    std::fill(count.begin(), count.end(), 0u);
+    for (uint64_t i = 0; i < n; ++i)
+    {
+        const uint32_t row = rowOf[i];
+        uint64_t local = atoms[i].first - static_cast<uint64_t>(row) * Lseg;
+        if (local >= Lseg) { local = Lseg - 1; }
+        const size_t at = static_cast<size_t>(row) * s->swCap + count[row]++;
+        pos[at] = local;
+        mass[at] = atoms[i].second;
+    }
+    CGB_CUDA(cudaMemcpy(s->dSwPos, pos.data(), pos.size() * sizeof(uint64_t), cudaMemcpyHostToDevice));
+    CGB_CUDA(cudaMemcpy(s->dSwMass, mass.data(), mass.size() * sizeof(float), cudaMemcpyHostToDevice));
+    CGB_CUDA(cudaMemcpy(s->dSwCount, count.data(), count.size() * sizeof(uint32_t), cudaMemcpyHostToDevice));
+    CGB_CUDA(cudaStreamSynchronize(cudaStreamLegacy));
+    s->swTotalAtoms = n;
+    return CGB_OK;
+}
+
+// per-row store -> (position in the whole domain, mass), rows in order, ascending position within a row
+static int sweepDownloadAtoms(const cgb_sampler *s, std::vector<uint64_t> &posOut, std::vector<float> &massOut)
+{
+    posOut.clear();
+    massOut.clear();
+    if (s->dSwPos == nullptr) { return CGB_OK; }
+    CGB_CUDA(cudaStreamSynchronize(s->stream));
+    std::vector<uint32_t> count(s->nRows);
+    std::vector<uint64_t> pos(static_cast<size_t>(s->nRows) * s->swCap);
+    std::vector<float> mass(static_cast<size_t>(s->nRows) * s->swCap);
+    CGB_CUDA(cudaMemcpy(count.data(), s->dSwCount, count.size() * sizeof(uint32_t), cudaMemcpyDeviceToHost));
+    CGB_CUDA(cudaMemcpy(pos.data(), s->dSwPos, pos.size() * sizeof(uint64_t), cudaMemcpyDeviceToHost));
+    CGB_CUDA(cudaMemcpy(mass.data(), s->dSwMass, mass.size() * sizeof(float), cudaMemcpyDeviceToHost));
+    const uint64_t Lseg = (0xFFFFFFFFFFFFFFFFull / (static_cast<uint64_t>(s->nRows) * s->k)) * s->k;
+    for (uint32_t r = 0; r < s->nRows; ++r)
+    {
+        CGB_CHECK(count[r] <= s->swCap, "sweep: a row's atom count exceeds its store");
+        for (uint32_t i = 0; i < count[r]; ++i)
+        {
+            posOut.push_back(static_cast<uint64_t>(r) * Lseg + pos[static_cast<size_t>(r) * s->swCap + i]);
+            massOut.push_back(mass[static_cast<size_t>(r) * s->swCap + i]);
+        }
+    }
+    return CGB_OK;
+}
+
+static int setAtoms(cgb_sampler *s, const uint64_t *pos, const float *mass, uint64_t n);
+
+static int cgb_sampler_set_update_mode_body(cgb_sampler *s, int32_t mode)
+{
+    CGB_CHECK(s != nullptr, "cgb_sampler_set_update_mode: NULL sampler");
+    CGB_CHECK(mode == CGB_UPDATE_EXACT || mode == CGB_UPDATE_SWEEP, "cgb_sampler_set_update_mode: unknown mode");
+    CGB_CHECK(!s->persistentRunning, "cgb_sampler_set_update_mode: called in the middle of an update");
+    if (mode == s->updateMode) { return CGB_OK; }
+    CGB_CUDA(cudaSetDevice(s->device));
+    if (mode == CGB_UPDATE_SWEEP)
+    {
+        if (s->sparse) { return fail(CGB_EUNSUPPORTED, "cgb_sampler_set_update_mode: the sweep is built for the dense model; the sparse model runs the exact path"); }
+        CGB_TRY(sweepFromDomain(s));
+    }
+    else
+    {
+        std::vector<uint64_t> pos;
+        std::vector<float> mass;
+        CGB_TRY(sweepDownloadAtoms(s, pos, mass));
+        CGB_TRY(setAtoms(s, pos.data(), mass.data(), pos.size()));
+    }
+    s->updateMode = mode;
+    return CGB_OK;
+}
+
+extern "C" int cgb_sampler_set_update_mode(cgb_sampler *s, int32_t mode)
+{
+    return guarded("cgb_sampler_set_update_mode", [&]() { return cgb_sampler_set_update_mode_body(s, mode); });
+}
+
+template <int T, bool HAS_S, bool ROW_SMEM>
+static int sweepLaunchInstance(cgb_sampler *s, const SweepArgs &args, size_t smem)
+{
+    if (s->swSmemConfigured[ROW_SMEM ? 1 : 0] != smem)
+    {
+        CGB_CUDA(cudaFuncSetAttribute(sweep_kernel<T, HAS_S, ROW_SMEM>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
+        s->swSmemConfigured[ROW_SMEM ? 1 : 0] = smem;
+    }
+    sweep_kernel<T, HAS_S, ROW_SMEM><<<s->nRows, T, smem, s->stream>>>(args);
+    g_kernelLaunches.fetch_add(1);
+    return CGB_OK;
+}
+
+template <int T>
+static int sweepLaunchThreads(cgb_sampler *s, const SweepArgs &args, size_t smem, bool rowSmem)
+{
+    if (s->hasS) { return rowSmem ? sweepLaunchInstance<T, true, true>(s, args, smem) : sweepLaunchInstance<T, true, false>(s, args, smem); }
+    return rowSmem ? sweepLaunchInstance<T, false, true>(s, args, smem) : sweepLaunchInstance<T, false, false>(s, args, smem);
+}
+
+static int sweepUpdate(cgb_sampler *s, uint32_t nSteps)
+{
+    const double t0 = nowSeconds();
+    CGB_TRY(sweepEnsureStore(s, std::max(kSweepInitialCap, s->swCap)));
+    SweepArgs args;
+    fillModelView(s, args.mv);
+    args.pos = s->dSwPos;
+    args.mass = s->dSwMass;
+    args.count = s->dSwCount;
+    args.qgamma = s->rs->dQgamma;
+    args.counters = static_cast<SweepCounters*>(s->dSwCounters);
+    args.key = s->rs->seeder.next();                      // one seeder value per update()
+    args.binLength = 0xFFFFFFFFFFFFFFFFull / (static_cast<uint64_t>(s->nRows) * s->k);
+    const SweepRates w = sweepRates(s->swTotalAtoms, s->nRows, s->k, args.binLength, static_cast<double>(s->alpha));
+    args.birthRow = w.birthRow;
+    args.deathAtom = w.deathAtom;
+    args.moveAtom = w.moveAtom;
+    args.exchAtom = w.exchAtom;
+    args.perAtom = w.perAtom;
+    args.cap = s->swCap;
+    args.nSteps = nSteps;
+    const size_t base = sweepRowOffset(s->swCap, s->k);
+    const size_t staged = base + static_cast<size_t>(s->hasS ? 3 : 2) * s->ld * sizeof(float);
+    const bool rowSmem = staged <= kSweepMaxSmem && envInt("COGAPS_SWEEP_ROW_SMEM", 1) != 0;
+    const size_t smem = rowSmem ? staged : base;
+    CGB_CHECK(smem <= kSweepMaxSmem, "sweep: a row's atom store no longer fits in shared memory");
+    CGB_CUDA(cudaMemsetAsync(s->dSwCounters, 0, sizeof(SweepCounters), s->stream));
+    CGB_CUDA(cudaEventRecord(s->evStart, s->stream));
+    const uint32_t T = sweepThreadsForLength(s->L);
+    if (T == 128u) { CGB_TRY(sweepLaunchThreads<128>(s, args, smem, rowSmem)); }
+    else if (T == 256u) { CGB_TRY(sweepLaunchThreads<256>(s, args, smem, rowSmem)); }
+    else { CGB_TRY(sweepLaunchThreads<512>(s, args, smem, rowSmem)); }
+    CGB_CUDA(cudaGetLastError());
+    CGB_CUDA(cudaEventRecord(s->evStop, s->stream));
+    sweep_max_count_kernel<<<(s->nRows + 255u) / 256u, 256, 0, s->stream>>>(s->dSwCount, s->nRows, &static_cast<SweepCounters*>(s->dSwCounters)->maxCount);
+    g_kernelLaunches.fetch_add(1);
+    CGB_CUDA(cudaGetLastError());
+    CGB_CUDA(cudaMemcpyAsync(s->hSwCounters, s->dSwCounters, sizeof(SweepCounters), cudaMemcpyDeviceToHost, s->stream));
+    const double tw = nowSeconds();
+    CGB_CUDA(cudaStreamSynchronize(s->stream));
+    s->counters.secondsDeviceWait += nowSeconds() - tw;
+    const SweepCounters &c = *static_cast<const SweepCounters*>(s->hSwCounters);
+    float ms = 0.f;
+    CGB_CUDA(cudaEventElapsedTime(&ms, s->evStart, s->evStop));
+    s->counters.secondsKernel += static_cast<double>(ms) * 1e-3;
+    s->counters.nBatches += 1;
+    s->counters.nProposalsQueued += c.scans1 + c.scans2;
+    s->counters.nProposalsTotal += c.steps;
+    s->counters.algorithmicBytes += static_cast<double>(s->L) * (16.0 * static_cast<double>(c.scans1) + 20.0 * static_cast<double>(c.scans2) + 4.0 * static_cast<double>(c.commits));
+    s->swTotalAtoms = static_cast<uint64_t>(static_cast<long long>(s->swTotalAtoms) + c.atomDelta);
+    s->swOverflow += c.overflow;
+    const uint32_t cap = sweepCapFor(s->swCap, c.maxCount);
+    if (cap > s->swCap) { CGB_TRY(sweepEnsureStore(s, cap)); }
+    s->counters.secondsHostGenerate += tw - t0;
+    return CGB_OK;
+}
+
 static int cgb_sampler_update_body(cgb_sampler *s, uint32_t nSteps, uint32_t nThreads)
 {
     (void)nThreads;
     CGB_CHECK(s && s->other, "cgb_sampler_update: sync() has not been called");
     CGB_CUDA(cudaSetDevice(s->device));
+    if (s->updateMode == CGB_UPDATE_SWEEP) { return sweepUpdate(s, nSteps); }
     if (s->sequential)
     {
         const double t0 = nowSeconds();
@@ -1918,7 +2210,7 @@ extern "C" int cgb_sampler_chisq(const cgb_sampler *cs, float *out)
 static int cgb_sampler_n_atoms_body(const cgb_sampler *s, uint64_t *out)
 {
     CGB_CHECK(s && out, "cgb_sampler_n_atoms: NULL argument");
-    *out = s->domain.size();
+    *out = (s->updateMode == CGB_UPDATE_SWEEP) ? s->swTotalAtoms : s->domain.size();
     return CGB_OK;
 }
 
@@ -2011,6 +2303,22 @@ extern "C" int cgb_sampler_lambda(const cgb_sampler *s, float *lambda, float *ma
 static int cgb_sampler_get_atoms_body(const cgb_sampler *s, uint64_t *pos, float *mass, uint64_t capacity, uint64_t *count)
 {
     CGB_CHECK(s && count, "cgb_sampler_get_atoms: NULL argument");
+    if (s->updateMode == CGB_UPDATE_SWEEP)
+    {
+        // position order (the sweep has no pick vector)
+        std::vector<uint64_t> p;
+        std::vector<float> m;
+        CGB_CUDA(cudaSetDevice(s->device));
+        CGB_TRY(sweepDownloadAtoms(s, p, m));
+        *count = p.size();
+        if (pos && mass)
+        {
+            const uint64_t n = std::min<uint64_t>(capacity, p.size());
+            std::copy(p.begin(), p.begin() + n, pos);
+            std::copy(m.begin(), m.begin() + n, mass);
+        }
+        return CGB_OK;
+    }
     *count = s->domain.size();
     if (pos && mass)
     {
@@ -2451,6 +2759,14 @@ static int samplerToImage(const cgb_sampler *s, SamplerImage &img)
         img.beta = 100.f; // SparseNormalModel.h:77
     }
     img.domainLength = s->domain.domainLength();
+    s->queue.save(img.queue);
+    if (s->updateMode == CGB_UPDATE_SWEEP)
+    {
+        // the atoms live in the device's per-row store; archived in position order, the window collapsed onto the count
+        CGB_TRY(sweepDownloadAtoms(s, img.pos, img.mass));
+        img.queue.minAtoms = img.queue.maxAtoms = img.pos.size();
+        return CGB_OK;
+    }
     const size_t n = static_cast<size_t>(s->domain.size());
     img.pos.resize(n);
     img.mass.resize(n);
@@ -2460,7 +2776,6 @@ static int samplerToImage(const cgb_sampler *s, SamplerImage &img)
         img.pos[i] = a.pos;
         img.mass[i] = a.mass;
     }
-    s->queue.save(img.queue);
     return CGB_OK;
 }
 
@@ -2476,8 +2791,16 @@ static int setAtoms(cgb_sampler *s, const uint64_t *pos, const float *mass, uint
             s->domain.init(nBins);
             return fail(CGB_EINVAL, "checkpoint: atom position outside the domain or used twice");
         }
+        if (!(mass[i] >= 0.f) || !(mass[i] <= 3.0e38f))
+        {
+            s->domain.init(nBins);
+            return fail(CGB_EINVAL, "checkpoint: atom mass negative or not finite");
+        }
         s->domain.insert(pos[i], mass[i]);
     }
+    // the generator's atom-count window (ProposalQueue.cpp:59-60 asserts min == max == domain.size() before it draws)
+    if (!s->sequential) { s->queue.setAtomCount(n); }
+    if (s->updateMode == CGB_UPDATE_SWEEP) { CGB_TRY(sweepFromDomain(s)); }
     return CGB_OK;
 }
 
@@ -2489,6 +2812,10 @@ static int imageToSampler(cgb_sampler *s, const SamplerImage &img)
     CGB_CHECK(img.nRows == s->nRows && img.k == s->k, "checkpoint: factor matrix shape differs from this sampler's");
     CGB_CHECK(img.domainLength == s->domain.domainLength(), "checkpoint: atomic domain length differs from this sampler's");
     CGB_CHECK(img.pos.size() == img.mass.size(), "checkpoint: atom arrays differ in length");
+    // a checkpoint is taken between updates, where the window has collapsed (ProposalQueue.cpp:59-60); anything else would
+    // let the first update pick from atoms that do not exist
+    CGB_CHECK(img.queue.minAtoms == img.queue.maxAtoms && img.queue.maxAtoms == img.pos.size(),
+              "checkpoint: archived atom counts of the proposal queue disagree with the archived atoms");
     QueueState probe;
     s->queue.save(probe);
     CGB_CHECK(probe.binLength == img.queue.binLength && probe.numCols == img.queue.numCols && probe.numBins == img.queue.numBins
@@ -2923,6 +3250,8 @@ static int runCore(const float *data, const CsrPair *csr, uint32_t nrow, uint32_
         if (fixed == 'A') { CGB_TRY(cgb_sampler_set_matrix(g.A, p->fixedPatterns)); }
         if (fixed == 'P') { CGB_TRY(cgb_sampler_set_matrix(g.P, p->fixedPatterns)); }
     }
+    CGB_CHECK(p->updateMode == CGB_UPDATE_EXACT || p->updateMode == CGB_UPDATE_SWEEP, "cgb_run: unknown updateMode");
+    CGB_CHECK(p->updateMode == CGB_UPDATE_EXACT || !p->useSparseOptimization, "cgb_run: the sweep is built for the dense model (useSparseOptimization runs the exact path)");
     CGB_TRY(cgb_stats_create(nGenes, nSamples, p->nPatterns, &g.st));
     CGB_TRY(cgb_rng_create(g.rs, &g.rng)); // GapsRunner.cpp:437
     int startPhase = CGB_PHASE_EQUILIBRATION;
@@ -2948,6 +3277,8 @@ static int runCore(const float *data, const CsrPair *csr, uint32_t nrow, uint32_
     CGB_TRY(cgb_sampler_sync(g.P, g.A));
     CGB_TRY(cgb_sampler_extra_initialization(g.A));
     CGB_TRY(cgb_sampler_extra_initialization(g.P));
+    CGB_TRY(cgb_sampler_set_update_mode(g.A, p->updateMode));
+    CGB_TRY(cgb_sampler_set_update_mode(g.P, p->updateMode));
 
     const double tStart = nowSeconds();
     if (envInt("COGAPS_HOST_PROFILE", 0)) { std::printf("[cgb_run] setup (tables, both orientations, upload, sync, AP rebuild) %.3f s\n", tStart - tEnter); }
@@ -2971,8 +3302,11 @@ static int runCore(const float *data, const CsrPair *csr, uint32_t nrow, uint32_
                 g.A->annealingTemp = gmin(1.f, temp);
                 g.P->annealingTemp = gmin(1.f, temp);
             }
-            const unsigned atomsA = static_cast<unsigned>(g.A->domain.size());
-            const unsigned atomsP = static_cast<unsigned>(g.P->domain.size());
+            uint64_t nAtomsA = 0, nAtomsP = 0;
+            CGB_TRY(cgb_sampler_n_atoms(g.A, &nAtomsA));
+            CGB_TRY(cgb_sampler_n_atoms(g.P, &nAtomsP));
+            const unsigned atomsA = static_cast<unsigned>(nAtomsA);
+            const unsigned atomsP = static_cast<unsigned>(nAtomsP);
             const unsigned nA = static_cast<unsigned>(g.rng->rng.poisson(static_cast<double>(atomsA < 10u ? 10u : atomsA)));
             const unsigned nP = static_cast<unsigned>(g.rng->rng.poisson(static_cast<double>(atomsP < 10u ? 10u : atomsP)));
             // updateSampler, GapsRunner.cpp:201-222
@@ -3022,7 +3356,10 @@ static int runCore(const float *data, const CsrPair *csr, uint32_t nrow, uint32_
             {
                 float cs = 0.f;
                 CGB_TRY(cgb_sampler_chisq(fixed == 'P' ? g.A : g.P, &cs));
-                const unsigned a = static_cast<unsigned>(g.A->domain.size()), b = static_cast<unsigned>(g.P->domain.size());
+                uint64_t na = 0, nb = 0;
+                CGB_TRY(cgb_sampler_n_atoms(g.A, &na));
+                CGB_TRY(cgb_sampler_n_atoms(g.P, &nb));
+                const unsigned a = static_cast<unsigned>(na), b = static_cast<unsigned>(nb);
                 if (nHist < r->historyCapacity)
                 {
                     if (r->chisqHistory) { r->chisqHistory[nHist] = cs; }
@@ -3049,6 +3386,11 @@ static int runCore(const float *data, const CsrPair *csr, uint32_t nrow, uint32_
     r->nSnapshotsSampling = nSnapSamp;
     r->seed = p->seed;
     r->totalUpdates = totalUpdates;
+    if (p->updateMode == CGB_UPDATE_SWEEP)
+    {
+        // the sweep rounds each row's share of nSteps stochastically: report the proposals actually made
+        r->totalUpdates = (fixed != 'A' ? g.A->counters.nProposalsTotal : 0) + (fixed != 'P' ? g.P->counters.nProposalsTotal : 0);
+    }
     r->averageQueueLengthA = g.A->avgQueueLength;
     r->averageQueueLengthP = g.P->avgQueueLength;
     r->meanChiSq = 0.f; // GapsRunner.cpp:478-485: zero whenever a matrix is fixed

@@ -177,6 +177,52 @@ CGB_HD float portable_logf(float x)
     return static_cast<float>(portable_log_f64(static_cast<double>(x)));
 }
 
+
+// ---- portable exp ------------------------------------------------------------------------------
+// exp() from IEEE +,*,fma and floor only (same bits on host, device and in the oracle): x = n ln2 + r with |r| <= ln2/2,
+// degree-13 Taylor polynomial in f64, scaled by 2^n, rounded once to f32 by the caller.  Used by the sweep's same-bin
+// exchange (GapsRng::truncGammaUpper, math/Random.cpp:194-200), whose std::exp no GPU reproduces bit for bit.
+CGB_HD double portable_exp_f64(double x)
+{
+    if (x != x) { return x; }
+    if (x > 700.0)
+    {
+#if defined(__CUDA_ARCH__)
+        return __longlong_as_double(0x7ff0000000000000ll);
+#else
+        return INFINITY;
+#endif
+    }
+    if (x < -700.0) { return 0.0; }
+    const double n = floor(dfma(x, 1.4426950408889634074, 0.5));
+    double r = dfma(-n, 0.69314718036912381649, x);
+    r = dfma(-n, 1.9082149292705877e-10, r);
+    double p = 1.0 / 6227020800.0;
+    p = dfma(p, r, 1.0 / 479001600.0);
+    p = dfma(p, r, 1.0 / 39916800.0);
+    p = dfma(p, r, 1.0 / 3628800.0);
+    p = dfma(p, r, 1.0 / 362880.0);
+    p = dfma(p, r, 1.0 / 40320.0);
+    p = dfma(p, r, 1.0 / 5040.0);
+    p = dfma(p, r, 1.0 / 720.0);
+    p = dfma(p, r, 1.0 / 120.0);
+    p = dfma(p, r, 1.0 / 24.0);
+    p = dfma(p, r, 1.0 / 6.0);
+    p = dfma(p, r, 0.5);
+    p = dfma(p, r, 1.0);
+    p = dfma(p, r, 1.0);
+    const uint64_t bits = static_cast<uint64_t>(static_cast<int64_t>(n) + 1023) << 52; // 2^n, |n| <= 1010 here
+#if defined(__CUDA_ARCH__)
+    return dmul(p, __longlong_as_double(static_cast<long long>(bits)));
+#else
+    union { double d; uint64_t u; } sc;
+    sc.u = bits;
+    return p * sc.d;
+#endif
+}
+
+CGB_HD float portable_expf(float x) { return static_cast<float>(portable_exp_f64(static_cast<double>(x))); }
+
 // ---- PCG32 XSH-RR, increment 55 (math/Random.cpp:40-56) -----------------------------------------
 struct Pcg
 {

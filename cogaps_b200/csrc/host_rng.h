@@ -201,11 +201,12 @@ struct HostRng : public Pcg
 // GapsRandomState (math/Random.h:79-98)
 struct cgb_randstate
 {
-    explicit cgb_randstate(uint32_t seed) : seeder(seed), dErf(nullptr), dErfinv(nullptr), device(-1) { tables.generate(); }
+    explicit cgb_randstate(uint32_t seed) : seeder(seed), dErf(nullptr), dErfinv(nullptr), dQgamma(nullptr), device(-1) { tables.generate(); }
     cgb::Xoroshiro128plus seeder;
     cgb::LookupTables tables;
     float *dErf;     // device copies, uploaded lazily by the first sampler
     float *dErfinv;
+    float *dQgamma;
     int device;
 };
 

@@ -178,6 +178,7 @@ struct Verdict
 {
     Decision dec;
     DevOutcome out;
+    float newM1, newM2; // the factor elements (r1,c1) / (r2,c2) after the proposal (dense model)
 };
 
 // The accept tests take log(uniform()) of the proposal's own PCG stream, as its first draw (move, death
@@ -380,6 +381,8 @@ __device__ __noinline__ void decide(const ModelView &mv, const float *erfT, cons
     }
     v->dec = dec;
     v->out = out;
+    v->newM1 = M1;
+    v->newM2 = M2;
 }
 
 __device__ __forceinline__ unsigned int ld_acquire_gpu_u32(const unsigned int *p)

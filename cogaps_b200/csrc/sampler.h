@@ -85,6 +85,8 @@ public:
     void rejectBirth() { --mMaxAtoms; }
     uint64_t minAtoms() const { return mMinAtoms; }
     uint64_t maxAtoms() const { return mMaxAtoms; }
+    // the atomic domain was replaced wholesale (set_atoms, a checkpoint, the sweep store): the window collapses onto its size
+    void setAtomCount(uint64_t n) { mMinAtoms = mMaxAtoms = n; }
     // the members operator<< archives (ProposalQueue.cpp:285-299); restore() refuses a state whose bin geometry
     // is not this queue's (the file was made from a matrix of another shape)
     void save(QueueState &out) const;
@@ -294,6 +296,18 @@ struct cgb_sampler
     bool sequential;              // asynchronousUpdates == 0: SingleThreadedGibbsSampler semantics
     cgb::SequentialState seq;
     float avgQueueLength, numQueueSamples;
+
+    // row-parallel sweep (sweep.cuh): the atoms live on the device, one sorted run per row of the factor matrix
+    int updateMode;               // CGB_UPDATE_EXACT / CGB_UPDATE_SWEEP
+    uint64_t *dSwPos;             // [nRows][swCap] positions relative to the row's segment of the atomic domain
+    float *dSwMass;               // [nRows][swCap]
+    uint32_t *dSwCount;           // [nRows]
+    uint32_t swCap;
+    void *dSwCounters;            // cgb::SweepCounters
+    void *hSwCounters;            // pinned copy
+    uint64_t swTotalAtoms;
+    uint64_t swOverflow;          // births dropped because a row's store was full (expected 0; the store regrows between updates)
+    size_t swSmemConfigured[2];   // dynamic shared memory already requested for the kernel instance in use, per ROW_SMEM
 
     // bench counters
     cgb_sampler_counters counters;

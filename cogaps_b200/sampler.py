@@ -246,6 +246,10 @@ class GibbsSampler(object):
     def setPersistent(self, enabled):
         check(lib().cgb_sampler_set_persistent(self._h, int(bool(enabled))))
 
+    def setUpdateMode(self, mode):
+        """0: the reference's chain, proposal for proposal; 1: row-parallel sweep (cgb_sampler_set_update_mode)"""
+        check(lib().cgb_sampler_set_update_mode(self._h, int(mode)))
+
     def reductionOrder(self):
         o = CgbReductionOrder()
         check(lib().cgb_sampler_reduction_order(self._h, C.byref(o)))
@@ -340,4 +344,11 @@ def reduction_order_for_length(rowLength):
     """(threadsPerSegment, vectorWidth, nSegments, segmentLength) of the eval kernel for rows of this length."""
     o = CgbReductionOrder()
     check(lib().cgb_reduction_order_for_length(rowLength, C.byref(o)))
+    return (o.threadsPerSegment, o.vectorWidth, o.nSegments, o.segmentLength)
+
+
+def sweep_reduction_order_for_length(rowLength):
+    """The same for the row-parallel sweep (cgb_params.updateMode = UPDATE_SWEEP): one segment per row."""
+    o = CgbReductionOrder()
+    check(lib().cgb_sweep_reduction_order_for_length(rowLength, C.byref(o)))
     return (o.threadsPerSegment, o.vectorWidth, o.nSegments, o.segmentLength)

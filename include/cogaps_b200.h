@@ -46,6 +46,9 @@ extern "C" {
 #define CGB_ERFINV_TABLE_SIZE  5001  /* math/Random.h:14 */
 #define CGB_QGAMMA_TABLE_SIZE  5001  /* math/Random.h:15 */
 
+#define CGB_UPDATE_EXACT 0
+#define CGB_UPDATE_SWEEP 1
+
 #define CGB_PHASE_EQUILIBRATION 1    /* GapsParameters.h:19-24 */
 #define CGB_PHASE_SAMPLING      2
 #define CGB_PHASE_ALL           3
@@ -92,6 +95,12 @@ typedef struct cgb_params
     const float *fixedPatterns;    /* rows(of the fixed matrix) x nPatterns row-major, or NULL */
     uint32_t workerID;             /* default 1 */
     int32_t runningDistributed;
+    int32_t updateMode;            /* CGB_UPDATE_EXACT (default): the reference's chain, proposal for proposal.
+                                    * CGB_UPDATE_SWEEP: row-parallel sweep (dense model) — every row of the factor runs
+                                    * the same four proposal types on its own segment of the atomic domain, all rows at
+                                    * once, draws from Philox4x32-10.  A different chain for the same seed, validated
+                                    * statistically against the reference and bit for bit against oracle/ (see
+                                    * cgb_sampler_set_update_mode). */
 } cgb_params;
 
 /* fill *p with the reference defaults (GapsParameters.h:79-114) */
@@ -296,6 +305,21 @@ typedef struct cgb_reduction_order
 int cgb_sampler_reduction_order(const cgb_sampler *s, cgb_reduction_order *out);
 /* the same, for any sampler whose rows have this length (no device needed) */
 int cgb_reduction_order_for_length(uint32_t rowLength, cgb_reduction_order *out);
+
+/* ------------------------------------------------------------------------------------------
+ * Row-parallel sweep (no counterpart in the reference; BASELINE north star: "a conflict-partitioned commit step — atoms
+ * binned by row so non-conflicting updates apply in parallel within one sweep", device-side counter-based draws).
+ * The loop it stands in for is AsynchronousGibbsSampler::update (AsynchronousGibbsSampler.h:88-122).  Row r of the factor
+ * matrix owns the segment [r*k*binLength, (r+1)*k*binLength) of the atomic domain (ProposalQueue.cpp:172-173) and, given
+ * the other factor, the rows are independent; in this mode every row runs the reference's four proposal types on its own
+ * segment — same evaluation code — one CTA per row, the whole update() in one launch, the row's D / AP lines staged once
+ * in shared memory.  Dense model only.  A different chain from the reference's for the same seed: validated against it
+ * statistically, and bit for bit against oracle/cogaps_oracle.c (sweep_row).  Switching converts the atoms between the
+ * host's atomic domain and the device's per-row store; cgb_sampler_update then takes the mode's path.
+ * ---------------------------------------------------------------------------------------- */
+int cgb_sampler_set_update_mode(cgb_sampler *s, int32_t mode);   /* CGB_UPDATE_EXACT / CGB_UPDATE_SWEEP */
+/* reduction order of the sweep's scans (one segment per row, thread count chosen from the row length; no device needed) */
+int cgb_sweep_reduction_order_for_length(uint32_t rowLength, cgb_reduction_order *out);
 
 /* ------------------------------------------------------------------------------------------
  * GapsStatistics (src/GapsStatistics.h:17-64): running sums for Amean/Asd/Pmean/Psd kept on

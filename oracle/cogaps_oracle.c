@@ -1507,6 +1507,14 @@ typedef struct
     int asynchronous;
     uint32_t side;
     trace_t *trace;
+    /* row-parallel sweep mode (cgb_params.updateMode == CGB_UPDATE_SWEEP; no reference counterpart, see "sweep" below) */
+    int sweep;
+    uint64_t *swPos;      /* [nRows][swCap] atom positions relative to the row's domain segment, ascending */
+    float *swMass;        /* [nRows][swCap] */
+    uint32_t *swCount;    /* [nRows] */
+    uint32_t swCap;
+    uint64_t swTotal;     /* atoms in all rows */
+    uint64_t swSteps, swScans, swOverflow;
 } sampler_t;
 
 static void sampler_init(sampler_t *s, const float *data, uint32_t nrow, uint32_t ncol, int transpose, int subsetRows,
@@ -1521,6 +1529,8 @@ static void sampler_init(sampler_t *s, const float *data, uint32_t nrow, uint32_
     s->asynchronous = p->asynchronousUpdates != 0;
     s->side = isA ? 'A' : 'P';
     s->trace = trace;
+    s->sweep = (p->updateMode == 1); /* CGB_UPDATE_SWEEP */
+    s->alpha = (double)alpha;
     if (s->asynchronous)
     {
         /* AsynchronousGibbsSampler ctor, AsynchronousGibbsSampler.h:63-76 */
@@ -1545,6 +1555,9 @@ static void sampler_free(sampler_t *s)
     model_free(&s->model);
     domain_free(&s->domain);
     if (s->asynchronous) { queue_free(&s->queue); }
+    free(s->swPos);
+    free(s->swMass);
+    free(s->swCount);
 }
 
 static oracle_trace_record *trace_begin(sampler_t *s, const proposal_t *p, uint32_t batch)
@@ -1846,10 +1859,376 @@ static void seq_update(sampler_t *s, unsigned nSteps)
     }
 }
 
+
+/* ============================ row-parallel sweep =================================== */
+/* NO REFERENCE COUNTERPART AS A WHOLE.  The north star's throughput mode: "a conflict-partitioned commit step (atoms
+ * binned by row so non-conflicting updates apply in parallel within one sweep)" with counter-based device-side draws.
+ * It is a DIFFERENT CHAIN from the reference's for the same seed and is validated against the reference
+ * statistically; this restatement is what the CUDA sweep kernel (cogaps_b200/csrc/sweep.cuh) is held to bit for bit.
+ *
+ * Why it is a valid sampler: row r of the factor matrix owns the contiguous segment [r*k*binLength, (r+1)*k*binLength)
+ * of the atomic domain (ProposalQueue.cpp:172-173), the other factor is constant during update()
+ * (GapsRunner.cpp:201-222), and the likelihood terms of different rows share no element of D / AP
+ * (DenseNormalModel.cpp:162-240 reads row `row` only).  Given the other factor, the rows are therefore independent, and
+ * every row runs the reference's own four proposal types — same evaluation code as the asynchronous sampler
+ * (AsynchronousGibbsSampler.h:126-219) — on its own segment, sequentially, all rows at once.  What changes:
+ *   - the birth/death balance uses the total atom count frozen at the start of update() (the reference tracks it
+ *     proposal by proposal, ProposalQueue.cpp:123-160);
+ *   - moves are bounded by the row's segment and the exchange partner of a row's last atom is the row's first atom
+ *     (the reference bounds by the whole domain and wraps at its end, ProposalQueue.cpp:213-214,254);
+ *   - draws come from Philox4x32-10 keyed by one seeder value per update() and countered by row, so the result does
+ *     not depend on how rows are scheduled.
+ * Expected proposals of a row: the reference gives each of its nSteps proposals to a birth with probability
+ * (1 - pDeath)/2, spread evenly over the rows, and to a death / move / exchange of a uniformly chosen atom with
+ * probability pDeath/2, 1/4, 1/4 (ProposalQueue.cpp:129-160).  A row holding m of the n atoms therefore expects
+ * nSteps * ((1-pDeath)/2/nRows + m*(pDeath/2 + 1/2)/n) proposals; it takes that many, rounded stochastically, and picks
+ * each proposal's type with the same weights evaluated at its current atom count. */
+#define CGB_UPDATE_SWEEP 1
+
+static const uint32_t kPhiloxM0 = 0xD2511F53u, kPhiloxM1 = 0xCD9E8D57u, kPhiloxW0 = 0x9E3779B9u, kPhiloxW1 = 0xBB67AE85u;
+
+typedef struct
+{
+    uint32_t key[2];
+    uint32_t ctr[4];
+    uint32_t buf[4];
+    uint32_t have;
+} philox_t;
+
+static void philox_block(const uint32_t ctrIn[4], const uint32_t keyIn[2], uint32_t out[4])
+{
+    uint32_t c0 = ctrIn[0], c1 = ctrIn[1], c2 = ctrIn[2], c3 = ctrIn[3];
+    uint32_t k0 = keyIn[0], k1 = keyIn[1];
+    for (int round = 0; round < 10; ++round)
+    {
+        uint64_t p0 = (uint64_t)kPhiloxM0 * c0;
+        uint64_t p1 = (uint64_t)kPhiloxM1 * c2;
+        uint32_t n0 = (uint32_t)(p1 >> 32) ^ c1 ^ k0;
+        uint32_t n1 = (uint32_t)p1;
+        uint32_t n2 = (uint32_t)(p0 >> 32) ^ c3 ^ k1;
+        uint32_t n3 = (uint32_t)p0;
+        c0 = n0; c1 = n1; c2 = n2; c3 = n3;
+        k0 += kPhiloxW0;
+        k1 += kPhiloxW1;
+    }
+    out[0] = c0; out[1] = c1; out[2] = c2; out[3] = c3;
+}
+
+/* known-answer probe for tests/test_sweep.py */
+void cogaps_oracle_philox(const uint32_t ctr[4], const uint32_t key[2], uint32_t out[4]) { philox_block(ctr, key, out); }
+
+static void philox_init(philox_t *g, uint64_t key, uint32_t row)
+{
+    g->key[0] = (uint32_t)key;
+    g->key[1] = (uint32_t)(key >> 32);
+    g->ctr[0] = row; g->ctr[1] = 0; g->ctr[2] = 0; g->ctr[3] = 0;
+    g->have = 0;
+}
+
+static uint32_t philox_u32(philox_t *g)
+{
+    if (g->have == 0)
+    {
+        philox_block(g->ctr, g->key, g->buf);
+        g->ctr[1] += 1;
+        g->have = 4;
+    }
+    uint32_t v = g->buf[4 - g->have];
+    g->have -= 1;
+    return v;
+}
+
+static uint64_t philox_u64(philox_t *g)
+{
+    uint64_t lo = philox_u32(g);
+    uint64_t hi = philox_u32(g);
+    return (hi << 32) | lo;
+}
+
+static float philox_uniform(philox_t *g) { return (float)philox_u32(g) / 4294967296.0f; }
+
+static uint64_t mulhi64(uint64_t a, uint64_t b) { return (uint64_t)(((unsigned __int128)a * b) >> 64); }
+static uint32_t mulhi32(uint32_t a, uint32_t b) { return (uint32_t)(((uint64_t)a * b) >> 32); }
+
+/* exp() from IEEE +,*,fma and floor only, so host, oracle and device agree bit for bit: x = n ln2 + r, |r| <= ln2/2,
+ * degree-13 Taylor polynomial in f64, scaled by 2^n; rounded once to f32 by the caller */
+static double portable_exp_f64(double x)
+{
+    if (x != x) { return x; }
+    if (x > 700.0) { return INFINITY; }
+    if (x < -700.0) { return 0.0; }
+    double n = floor(fma(x, 1.4426950408889634074, 0.5));
+    double r = fma(-n, 0.69314718036912381649, x);      /* ln2 high part: 32 significant bits */
+    r = fma(-n, 1.9082149292705877e-10, r);             /* ln2 low part */
+    double p = 1.0 / 6227020800.0;
+    p = fma(p, r, 1.0 / 479001600.0);
+    p = fma(p, r, 1.0 / 39916800.0);
+    p = fma(p, r, 1.0 / 3628800.0);
+    p = fma(p, r, 1.0 / 362880.0);
+    p = fma(p, r, 1.0 / 40320.0);
+    p = fma(p, r, 1.0 / 5040.0);
+    p = fma(p, r, 1.0 / 720.0);
+    p = fma(p, r, 1.0 / 120.0);
+    p = fma(p, r, 1.0 / 24.0);
+    p = fma(p, r, 1.0 / 6.0);
+    p = fma(p, r, 0.5);
+    p = fma(p, r, 1.0);
+    p = fma(p, r, 1.0);
+    union { double d; uint64_t u; } sc;
+    sc.u = (uint64_t)((int64_t)n + 1023) << 52;          /* 2^n, n in [-1010, 1010] here */
+    return p * sc.d;
+}
+
+float cogaps_oracle_portable_expf(float x) { return (float)portable_exp_f64((double)x); }
+
+/* GapsRng::truncGammaUpper (Random.cpp:194-200) with the portable exp */
+static float sweep_trunc_gamma_upper(rng_t *r, float b, float scale)
+{
+    float q = b / scale;
+    float upper = 1.f - cogaps_oracle_portable_expf(-q) * (1.f + q);
+    const unsigned ndx = (unsigned)rng_uniform_ab(r, 0.f, upper * 5000.f);
+    return r->rs->qgamma[ndx] * scale;
+}
+
+static void sweep_alloc(sampler_t *s, uint32_t cap)
+{
+    uint32_t R = s->model.nRows;
+    uint64_t *pos = (uint64_t*)calloc((size_t)R * cap, sizeof(uint64_t));
+    float *mass = (float*)calloc((size_t)R * cap, sizeof(float));
+    if (s->swPos)
+    {
+        for (uint32_t r = 0; r < R; ++r)
+        {
+            memcpy(pos + (size_t)r * cap, s->swPos + (size_t)r * s->swCap, sizeof(uint64_t) * s->swCount[r]);
+            memcpy(mass + (size_t)r * cap, s->swMass + (size_t)r * s->swCap, sizeof(float) * s->swCount[r]);
+        }
+        free(s->swPos);
+        free(s->swMass);
+    }
+    else
+    {
+        s->swCount = (uint32_t*)calloc(R, sizeof(uint32_t));
+    }
+    s->swPos = pos;
+    s->swMass = mass;
+    s->swCap = cap;
+}
+
+/* the constants of one update(), formed in f64 by the host side of the product in exactly these operations */
+typedef struct
+{
+    double birthRow, deathAtom, moveAtom, exchAtom;
+} sweep_rates_t;
+
+static sweep_rates_t sweep_rates(uint64_t nAtoms, uint32_t nRows, uint32_t k, uint64_t binLength, double alpha)
+{
+    sweep_rates_t w;
+    if (nAtoms < 2)
+    {
+        /* "always birth when 0 or 1 atoms exist", ProposalQueue.cpp:139-142 */
+        w.birthRow = 1.0 / (double)nRows;
+        w.deathAtom = w.moveAtom = w.exchAtom = 0.0;
+        return w;
+    }
+    /* deathProb, ProposalQueue.cpp:123-127 (float result) */
+    uint64_t nElements = (uint64_t)nRows * k;
+    double domainLength = (double)(binLength * nElements);
+    double numer = (double)nAtoms * domainLength;
+    float pDeath = (float)(numer / (numer + alpha * (double)nElements * (domainLength - (double)nAtoms)));
+    w.birthRow = 0.5 * (1.0 - (double)pDeath) / (double)nRows;
+    w.deathAtom = 0.5 * (double)pDeath / (double)nAtoms;
+    w.moveAtom = 0.25 / (double)nAtoms;
+    w.exchAtom = 0.25 / (double)nAtoms;
+    return w;
+}
+
+static void sweep_insert(uint64_t *pos, float *mass, uint32_t m, uint32_t idx, uint64_t p, float v)
+{
+    for (uint32_t i = m; i > idx; --i) { pos[i] = pos[i - 1]; mass[i] = mass[i - 1]; }
+    pos[idx] = p;
+    mass[idx] = v;
+}
+
+static void sweep_erase(uint64_t *pos, float *mass, uint32_t m, uint32_t idx)
+{
+    for (uint32_t i = idx; i + 1 < m; ++i) { pos[i] = pos[i + 1]; mass[i] = mass[i + 1]; }
+}
+
+static void sweep_row(sampler_t *s, uint32_t row, uint64_t key, unsigned nSteps, const sweep_rates_t *w, uint64_t binLength)
+{
+    model_t *m = &s->model;
+    const uint32_t k = m->k;
+    const uint64_t Lseg = binLength * k;
+    uint64_t *pos = s->swPos + (size_t)row * s->swCap;
+    float *mass = s->swMass + (size_t)row * s->swCap;
+    uint32_t cnt = s->swCount[row];
+    philox_t g;
+    philox_init(&g, key, row);
+    const double perAtom = w->deathAtom + w->moveAtom + w->exchAtom;
+    double lam = (double)nSteps * (w->birthRow + (double)cnt * perAtom);
+    if (lam > 1.0e9) { lam = 1.0e9; }
+    uint32_t steps = (uint32_t)lam;
+    float frac = (float)(lam - (double)steps);
+    if (philox_uniform(&g) < frac) { steps += 1; }
+    for (uint32_t step = 0; step < steps; ++step)
+    {
+        s->swSteps += 1;
+        const double b = w->birthRow, d = (double)cnt * w->deathAtom, mv = (double)cnt * w->moveAtom;
+        const double tot = b + (double)cnt * perAtom;
+        const double x = (double)philox_uniform(&g) * tot;
+        rng_t rng;
+        rng.rs = s->rs;
+        if (cnt == 0 || x < b)
+        {
+            /* ProposalQueue::birth (:162-187) within the row's segment + AsynchronousGibbsSampler::birth (:126-144) */
+            const uint64_t p = 1 + mulhi64(philox_u64(&g), Lseg - 1);
+            rng.state = philox_u64(&g);
+            uint32_t idx = 0;
+            while (idx < cnt && pos[idx] < p) { ++idx; }
+            if (idx < cnt && pos[idx] == p) { continue; }              /* occupied (randomFreePosition would redraw) */
+            if (cnt == s->swCap) { s->swOverflow += 1; continue; }     /* the row's atom store is full */
+            const uint32_t col = (uint32_t)(p / binLength);
+            float v = 0.f;
+            int has;
+            if (model_can_use_gibbs(m, col))
+            {
+                s->swScans += 1;
+                alpha_t a = alpha_scale(model_alpha(m, row, col), m->annealingTemp);
+                has = gibbs_mass(a, 0.f, m->maxGibbsMass, &rng, 1, m->lambda, &v);
+            }
+            else
+            {
+                v = rng_exponential(&rng, m->lambda);
+                has = 1;
+            }
+            if (has && v >= EPSILON)
+            {
+                sweep_insert(pos, mass, cnt, idx, p, v);
+                cnt += 1;
+                model_change_matrix(m, row, col, v);
+            }
+        }
+        else if (x < b + d)
+        {
+            /* ProposalQueue::death (:189-207) + AsynchronousGibbsSampler::death (:147-180) */
+            const uint32_t idx = mulhi32(philox_u32(&g), cnt);
+            rng.state = philox_u64(&g);
+            const uint32_t col = (uint32_t)(pos[idx] / binLength);
+            const float old = mass[idx];
+            float rebirth = old;
+            s->swScans += 1;
+            alpha_t a = alpha_scale(model_alpha_with_change(m, row, col, -1.f * old), m->annealingTemp);
+            if (model_can_use_gibbs(m, col))
+            {
+                float gm;
+                if (gibbs_mass(a, 0.f, m->maxGibbsMass, &rng, 1, m->lambda, &gm)) { rebirth = gm; }
+            }
+            float deltaLL = rebirth * (a.s_mu - a.s * rebirth / 2.f);
+            if (rs_logf(s->rs, rng_uniform(&rng)) < deltaLL)
+            {
+                if (rebirth != old)
+                {
+                    model_safely_change_matrix(m, row, col, rebirth - old);
+                    mass[idx] = rebirth;
+                }
+            }
+            else
+            {
+                model_safely_change_matrix(m, row, col, -1.f * old);
+                sweep_erase(pos, mass, cnt, idx);
+                cnt -= 1;
+            }
+        }
+        else if (x < b + d + mv)
+        {
+            /* ProposalQueue::move (:209-248) bounded by the segment + AsynchronousGibbsSampler::move (:183-196) */
+            const uint32_t idx = mulhi32(philox_u32(&g), cnt);
+            const uint64_t draw = philox_u64(&g);
+            rng.state = philox_u64(&g);
+            const uint64_t lb = idx > 0 ? pos[idx - 1] : 0;
+            const uint64_t rb = idx + 1 < cnt ? pos[idx + 1] : Lseg;
+            if (rb - lb < 2) { continue; }
+            const uint64_t p = lb + 1 + mulhi64(draw, rb - lb - 1);
+            const uint32_t c1 = (uint32_t)(pos[idx] / binLength), c2 = (uint32_t)(p / binLength);
+            if (c1 == c2)
+            {
+                pos[idx] = p; /* "automatically accept moves in same bin" */
+                continue;
+            }
+            s->swScans += 1;
+            alpha_t a = alpha_scale(model_alpha2(m, row, c1, row, c2), m->annealingTemp);
+            const float am = mass[idx];
+            float deltaLL = -1.f * am * (a.s_mu + a.s * am / 2.f);
+            if (rs_logf(s->rs, rng_uniform(&rng)) < deltaLL)
+            {
+                pos[idx] = p;
+                model_safely_change_matrix(m, row, c1, -am);
+                model_change_matrix(m, row, c2, am);
+            }
+        }
+        else
+        {
+            /* ProposalQueue::exchange (:250-283) within the row + AsynchronousGibbsSampler::exchange (:200-219) */
+            const uint32_t idx = mulhi32(philox_u32(&g), cnt);
+            rng.state = philox_u64(&g);
+            if (cnt < 2) { continue; }
+            const uint32_t j = idx + 1 < cnt ? idx + 1 : 0;
+            const uint32_t c1 = (uint32_t)(pos[idx] / binLength), c2 = (uint32_t)(pos[j] / binLength);
+            const float m1 = mass[idx], m2 = mass[j];
+            if (c1 == c2)
+            {
+                float newMass = sweep_trunc_gamma_upper(&rng, m1 + m2, 1.f / m->lambda);
+                float delta = (m1 > m2) ? newMass - m1 : m2 - newMass;
+                if (m1 + delta > EPSILON && m2 - delta > EPSILON)
+                {
+                    mass[idx] = m1 + delta;
+                    mass[j] = m2 - delta;
+                }
+                continue;
+            }
+            if (model_can_use_gibbs(m, c1) || model_can_use_gibbs(m, c2))
+            {
+                s->swScans += 1;
+                alpha_t a = alpha_scale(model_alpha2(m, row, c1, row, c2), m->annealingTemp);
+                float gm;
+                int has = gibbs_mass(a, -m1, m2, &rng, 0, 0.f, &gm);
+                float n1 = m1 + gm, n2 = m2 - gm;
+                if (has && n1 > EPSILON && n2 > EPSILON)
+                {
+                    model_safely_change_matrix(m, row, c1, n1 - m1);
+                    model_safely_change_matrix(m, row, c2, n2 - m2);
+                    mass[idx] = n1;
+                    mass[j] = n2;
+                }
+            }
+        }
+    }
+    s->swTotal = s->swTotal + cnt - s->swCount[row];
+    s->swCount[row] = cnt;
+}
+
+static void sweep_update(sampler_t *s, unsigned nSteps)
+{
+    model_t *m = &s->model;
+    if (s->swPos == NULL) { sweep_alloc(s, 64); }
+    const uint64_t nElements = (uint64_t)m->nRows * m->k;
+    const uint64_t binLength = 0xFFFFFFFFFFFFFFFFull / nElements;
+    const uint64_t key = xoro_next(&s->rs->seeder);       /* one seeder value per update() */
+    const sweep_rates_t w = sweep_rates(s->swTotal, m->nRows, m->k, binLength, s->alpha);
+    for (uint32_t row = 0; row < m->nRows; ++row) { sweep_row(s, row, key, nSteps, &w, binLength); }
+    /* the store grows between updates so that a row practically never fills up within one */
+    uint32_t maxCount = 0;
+    for (uint32_t row = 0; row < m->nRows; ++row) { if (s->swCount[row] > maxCount) { maxCount = s->swCount[row]; } }
+    if (2 * maxCount > s->swCap) { sweep_alloc(s, (4 * maxCount + 31u) / 32u * 32u); }
+}
+
 static void sampler_update(sampler_t *s, unsigned nSteps)
 {
+    if (s->sweep) { sweep_update(s, nSteps); return; }
     if (s->asynchronous) { async_update(s, nSteps); } else { seq_update(s, nSteps); }
 }
+
+static unsigned sampler_n_atoms(const sampler_t *s) { return s->sweep ? (unsigned)s->swTotal : s->domain.n; }
 
 /* ============================ statistics =========================================== */
 /* GapsStatistics, GapsStatistics.h:17-64; sums stored column-major like the reference */
@@ -2333,7 +2712,7 @@ int cogaps_oracle_run_trace(const float *data, uint32_t nrow, uint32_t ncol, con
                 A.model.annealingTemp = fminr(1.f, temp);
                 P.model.annealingTemp = fminr(1.f, temp);
             }
-            unsigned atomsA = A.domain.n, atomsP = P.domain.n;
+            unsigned atomsA = sampler_n_atoms(&A), atomsP = sampler_n_atoms(&P);
             unsigned nA = (unsigned)rng_poisson(&rng, (double)(atomsA < 10 ? 10u : atomsA));
             unsigned nP = (unsigned)rng_poisson(&rng, (double)(atomsP < 10 ? 10u : atomsP));
             /* updateSampler, GapsRunner.cpp:201-222 */
@@ -2347,7 +2726,7 @@ int cogaps_oracle_run_trace(const float *data, uint32_t nrow, uint32_t ncol, con
                 sampler_update(&P, nP);
                 if (fixed != 'A') { model_sync(&A.model, &P.model); }
             }
-            totalUpdates += nA + nP;
+            totalUpdates += (A.sweep || P.sweep) ? 0 : nA + nP;
             if (phase == CGB_PHASE_SAMPLING)
             {
                 if (useFixed)
@@ -2384,8 +2763,8 @@ int cogaps_oracle_run_trace(const float *data, uint32_t nrow, uint32_t ncol, con
                 if (nHist < r->historyCapacity)
                 {
                     if (r->chisqHistory) { r->chisqHistory[nHist] = cs; }
-                    if (r->atomHistoryA) { r->atomHistoryA[nHist] = A.domain.n; }
-                    if (r->atomHistoryP) { r->atomHistoryP[nHist] = P.domain.n; }
+                    if (r->atomHistoryA) { r->atomHistoryA[nHist] = sampler_n_atoms(&A); }
+                    if (r->atomHistoryP) { r->atomHistoryP[nHist] = sampler_n_atoms(&P); }
                     ++nHist;
                 }
             }
@@ -2400,7 +2779,7 @@ int cogaps_oracle_run_trace(const float *data, uint32_t nrow, uint32_t ncol, con
     r->nSnapshotsEquilibration = nSnapEq;
     r->nSnapshotsSampling = nSnapSamp;
     r->seed = p->seed;
-    r->totalUpdates = totalUpdates;
+    r->totalUpdates = (A.sweep || P.sweep) ? A.swSteps + P.swSteps : totalUpdates; /* sweep: proposals actually made */
     r->totalRunningTime = 0.0;
     r->averageQueueLengthA = A.asynchronous ? A.avgQueueLength : 0.f;
     r->averageQueueLengthP = P.asynchronous ? P.avgQueueLength : 0.f;

@@ -103,6 +103,9 @@ int cogaps_oracle_chisq_sparse(const float *data, uint32_t nGenes, uint32_t nSam
                                const float *A, const float *P, float *out);
 
 float cogaps_oracle_portable_logf(float x);
+/* the sweep's building blocks (cogaps_b200/csrc/sweep.cuh, gaps_math.h): Philox4x32-10 block function, portable exp */
+void cogaps_oracle_philox(const uint32_t ctr[4], const uint32_t key[2], uint32_t out[4]);
+float cogaps_oracle_portable_expf(float x);
 
 #ifdef __cplusplus
 }
