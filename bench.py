@@ -6,10 +6,16 @@ configuration the metric is quoted on; recipe SURVEY.md 8(d)).  A "step" is one 
 hot path exactly as GapsRunner.cpp:294-296 drives it: nA ~ Poisson(atomsA), nP ~ Poisson(atomsP),
 A.update(nA) -> P.sync(A) -> P.update(nP) -> A.sync(P).
 
+  Two ways through update() are measured in every run, on the SAME chain state (--mode picks which one is `value`):
+    sweep (default) : the row-parallel sweep (cgb_params.updateMode = CGB_UPDATE_SWEEP; sweep.cuh) — the north star's
+           design: whole update() in one launch, one CTA per factor row, row staged once in shared memory, counter-based
+           device-side draws, transport between adjacent rows.  A different chain from the reference's for the same seed
+           (validated statistically against the reference, bit for bit against oracle/).
+    exact : the reference's chain proposal for proposal (host generator + resident evaluator grid).  Its numbers are
+           reported under "exact_mode" (or as `value` with --mode exact), measured at the same steady-state atom count:
+           the chain is grown by the sweep (fast), then the samplers are switched over (cgb_sampler_set_update_mode).
   value  : atom-updates/s over K timed steps with D/S/AP/factors resident in HBM, after a ramp that grows
-           the chain from zero atoms (untimed) and W warm-up steps.  Host generator + device evaluator:
-           every batch's proposals go H2D as kernel parameters and its outcomes come back D2H, inside the
-           timed region, because that is what the path is.
+           the chain from zero atoms to its steady state (untimed) and W warm-up steps.
   e2e    : the same metric through the reference-facing entry point cgb_run (= gaps::run) on HOST buffers:
            upload of both data orientations, the whole two-phase run from zero atoms, statistics, download
            of Amean/Asd/Pmean/Psd — wall clock of the call.  `--impl reference` runs the reference's own
@@ -40,8 +46,9 @@ sys.path.insert(0, ROOT)
 G, S, K = 20000, 5000, 20
 DATA_SEED = 20260117
 CHAIN_SEED = 42
-RAMP_ITERS = 50          # untimed iterations growing the chain from zero atoms before warm-up
-E2E_ITERS = 30           # iterations per phase of the end-to-end / reference gaps::run call
+RAMP_ITERS = 400         # untimed sweep iterations growing the chain from zero atoms to its steady state before warm-up
+E2E_ITERS = 40           # iterations per phase of the end-to-end / reference gaps::run call
+EXACT_STEPS = 10         # timed exact-mode steps at the steady state (each ~35 ms there)
 
 
 def make_data(g=G, s=S, k=K, seed=DATA_SEED, zero_fraction=0.0):
@@ -223,6 +230,15 @@ def main():
                     help="BASELINE.json configs[3]: sparseOptimization (SparseGibbsSampler) on a matrix with --zeros of its "
                          "entries zeroed; give the shape with --rows/--cols/--patterns (50000 30000 50 for C4)")
     ap.add_argument("--zeros", type=float, default=0.95)
+    ap.add_argument("--mode", default="sweep", choices=["sweep", "exact"],
+                    help="which path through update() the headline `value` / `e2e` / `roofline` describe (both are measured)")
+    ap.add_argument("--exact-steps", type=int, default=EXACT_STEPS)
+    ap.add_argument("--no-c5", action="store_true", help="N > 1: skip the configs[4] record (sharded 200000x30000 + P all-gather)")
+    ap.add_argument("--c5-genes", type=int, default=30000)
+    ap.add_argument("--c5-cells", type=int, default=200000)
+    ap.add_argument("--c5-patterns", type=int, default=50)
+    ap.add_argument("--c5-ramp", type=int, default=10)
+    ap.add_argument("--c5-steps", type=int, default=3)
     ap.add_argument("--chains", type=int, default=0,
                     help="extra leg: this many independent chains on ONE GPU, one host thread each, every resident grid "
                          "taking 1/chains of the device (what distributed CoGAPS does with several sets per worker)")
@@ -273,74 +289,140 @@ def main():
     from cogaps_b200._lib import check
     check(cg.lib().cgb_set_device(local_rank))
 
-    data = make_data(args.rows, args.cols, args.patterns, DATA_SEED + rank, args.zeros if args.sparse else 0.0)
-    clocks = ClockSampler(local_rank)
-    t_setup = time.time()
-    chain = Chain(data, args.patterns, CHAIN_SEED + rank, sparse=args.sparse)
-    chain.ramp(args.ramp)
-    for _ in range(args.warmup):
-        chain.step()
-    setup_s = time.time() - t_setup
-
     def barrier():
         torch.cuda.synchronize()
         if world > 1:
             dist.barrier()
         torch.cuda.synchronize()
 
-    # ---- timed region: exactly K steps ----
-    chain.A.resetCounters()
-    chain.P.resetCounters()
-    launches0 = cg.lib().cgb_kernel_launch_count()
-    barrier()
-    clocks.begin()
-    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    t0 = time.perf_counter()
-    ev0.record()
-    updates = 0
-    for _ in range(args.steps):
-        updates += chain.step()
-    torch.cuda.synchronize()      # the last A.sync(P) is still in flight on the samplers' streams
-    ev1.record()
-    barrier()
-    elapsed_host = time.perf_counter() - t0
-    # the region on the device clock: two CUDA events around the K steps (a step is a host-driven pipeline of
-    # resident kernels on the samplers' own streams, every update() ends with a stream synchronise, so the
-    # second event is reached when the last step is complete)
-    elapsed = ev0.elapsed_time(ev1) * 1e-3
-    clocks.end()
-    clock_info = clocks.stop()
-    launches = cg.lib().cgb_kernel_launch_count() - launches0
-    cA, cP = chain.A.counters(), chain.P.counters()
+    def reduce_max_sum(elapsed, sums):
+        """max over ranks of the device time, sum over ranks of the counts"""
+        if world == 1:
+            return elapsed, [float(x) for x in sums]
+        t = torch.tensor([elapsed], dtype=torch.float64, device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        u = torch.tensor([float(x) for x in sums], dtype=torch.float64, device="cuda")
+        dist.all_reduce(u, op=dist.ReduceOp.SUM)
+        return float(t.item()), [float(x) for x in u.tolist()]
+
+    def timed_steps(chain, steps, clock=None):
+        """exactly `steps` iterations between barriers; device time from a CUDA event pair around them"""
+        chain.A.resetCounters()
+        chain.P.resetCounters()
+        launches0 = cg.lib().cgb_kernel_launch_count()
+        barrier()
+        if clock is not None:
+            clock.begin()
+        ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        t0 = time.perf_counter()
+        ev0.record()
+        asked = 0
+        for _ in range(steps):
+            asked += chain.step()
+        torch.cuda.synchronize()      # every update() ends with a stream synchronise; the last A.sync(P) may still run
+        ev1.record()
+        barrier()
+        host = time.perf_counter() - t0
+        if clock is not None:
+            clock.end()
+        cA, cP = chain.A.counters(), chain.P.counters()
+        return {"elapsed": ev0.elapsed_time(ev1) * 1e-3, "host": host, "asked": asked,
+                "made": int(cA.nProposalsTotal + cP.nProposalsTotal), "cA": cA, "cP": cP,
+                "launches": int(cg.lib().cgb_kernel_launch_count() - launches0), "steps": steps}
+
+    dense = not args.sparse
+    mode = args.mode if dense else "exact"
+    config["update_mode"] = ("sweep: row-parallel (one CTA per factor row, whole update() in one launch, Philox draws, transport "
+                             "between adjacent rows); a different chain from the reference's for the same seed — validated "
+                             "statistically against it and bit for bit against oracle/; the reference's own chain is measured "
+                             "in the same run under exact_mode") if mode == "sweep" else \
+                            "exact: the reference's chain proposal for proposal (host generator + resident evaluator grid)"
+    data = make_data(args.rows, args.cols, args.patterns, DATA_SEED + rank, args.zeros if args.sparse else 0.0)
+    clocks = ClockSampler(local_rank)
+    t_setup = time.time()
+    # the chain grows to its steady state in sweep mode (seconds instead of minutes), untimed
+    chain = Chain(data, args.patterns, CHAIN_SEED + rank, sparse=args.sparse, updateMode=1 if dense else 0)
+    chain.ramp(args.ramp if dense else min(args.ramp, 50))
+    for _ in range(args.warmup):
+        chain.step()
+    setup_s = time.time() - t_setup
+    peak, peak_src = load_peaks()
+    L_A, L_P = args.cols, args.rows
+
+    # ---- timed region 1 (dense model): exactly K steps of the sweep ----
+    sweep = None
+    if dense:
+        r = timed_steps(chain, args.steps, clocks if mode == "sweep" else None)
+        el, (made, launches) = reduce_max_sum(r["elapsed"], [r["made"], r["launches"]])
+        cA, cP = r["cA"], r["cP"]
+        ktime = cA.secondsKernel + cP.secondsKernel
+        kbytes = cA.algorithmicBytes + cP.algorithmicBytes
+        sweep = {"value": made / el, "unit": "atom-updates/s", "ms_per_step": el / args.steps * 1e3, "steps": args.steps,
+                 "atom_updates": int(made), "gpu_launches": int(launches),
+                 "atoms": {"A": int(chain.A.nAtoms()), "P": int(chain.P.nAtoms())},
+                 "host_ms_per_step": r["host"] / args.steps * 1e3,
+                 "kernel_ms_per_step": {"A": cA.secondsKernel / args.steps * 1e3, "P": cP.secondsKernel / args.steps * 1e3},
+                 "roofline": {"bound": "hbm", "kernel": "sweep_kernel + sweep_transport_kernel (one update() = one launch of each)",
+                              "achieved": kbytes / max(ktime, 1e-12) / 1e9, "peak": peak, "unit": "GB/s",
+                              "frac": kbytes / max(ktime, 1e-12) / 1e9 / peak, "peak_source": peak_src,
+                              "algorithmic_bytes_per_launch": kbytes / (2.0 * args.steps),
+                              "avg_launch_us": ktime / (2.0 * args.steps) * 1e6, "launches": 2 * args.steps,
+                              "traffic": None,
+                              "A_side": {"GBps": cA.algorithmicBytes / max(cA.secondsKernel, 1e-12) / 1e9},
+                              "P_side": {"GBps": cP.algorithmicBytes / max(cP.secondsKernel, 1e-12) / 1e9},
+                              "how": "cudaEvent pair on the launching stream around the row sweep + transport launches of every "
+                                     "update() in the timed region; bytes = SURVEY 8(d) algorithmic bytes of the proposals evaluated "
+                                     "(16 L per birth/death scan, 20 L per same-row move/exchange, 32 L per two-row one, +4 L per "
+                                     "rewritten AP line).  The kernel stages a row once and serves all its proposals from shared "
+                                     "memory, so the bytes it really moves are far fewer (traffic_estimate; ncu capture in profiles/) "
+                                     "and a fraction above 1 is possible: the sweep is bound by instruction issue and the serial "
+                                     "decision of each proposal, not by HBM"}}
+        # what the sweep really moves per update(): every active row's D and AP lines once in, dirty AP lines once out
+        lines_in = 2.0
+        sweep["roofline"]["traffic_estimate"] = {
+            "bytes_per_launch": (args.rows * L_A + args.cols * L_P) * 4.0 * (lines_in + 1.0) / 2.0,
+            "how": "upper bound: (D + AP read, AP written) x every row of both samplers, per update() launch; measured per "
+                   "launch by ncu in profiles/r2_sweep_kernel_ncu.csv"}
+        sweep["roofline"]["dram_frac_estimate"] = sweep["roofline"]["traffic_estimate"]["bytes_per_launch"] / \
+            max(ktime / (2.0 * args.steps), 1e-12) / 1e9 / peak
+
+    # ---- timed region 2: the reference's own chain (exact mode) from the same state ----
+    if dense:
+        chain.A.setUpdateMode(0)
+        chain.P.setUpdateMode(0)
+        for _ in range(args.warmup):
+            chain.step()
+    exact_steps = args.steps if (mode == "exact") else min(args.steps, args.exact_steps)
+    r = timed_steps(chain, exact_steps, clocks if mode == "exact" else None)
+    el, (made, launches) = reduce_max_sum(r["elapsed"], [r["asked"], r["launches"]])
+    cA, cP = r["cA"], r["cP"]
     queued = cA.nProposalsQueued + cP.nProposalsQueued
     batches = cA.nBatches + cP.nBatches
     # every proposal: one 64-byte task record per CTA of its cluster written to pinned host memory and pulled by
     # the device (two-row moves / exchanges send two), one 16-byte outcome record written back
     segA, segP = chain.A.reductionOrder()[2], chain.P.reductionOrder()[2]
-    h2d_step = (cA.nProposalsQueued * 64.0 * segA + cP.nProposalsQueued * 64.0 * segP) / args.steps
-    d2h_step = queued * 16.0 / args.steps
+    h2d_step = (cA.nProposalsQueued * 64.0 * segA + cP.nProposalsQueued * 64.0 * segP) / exact_steps
+    d2h_step = queued * 16.0 / exact_steps
+    exact = {"value": made / el, "unit": "atom-updates/s", "ms_per_step": el / exact_steps * 1e3, "steps": exact_steps,
+             "atom_updates": int(made), "gpu_launches": int(launches),
+             "atoms": {"A": int(chain.A.nAtoms()), "P": int(chain.P.nAtoms())},
+             "host_ms_per_step": r["host"] / exact_steps * 1e3,
+             "batches_per_step": batches / exact_steps, "proposals_per_batch": queued / max(batches, 1),
+             "host_generate_s_per_step": (cA.secondsHostGenerate + cP.secondsHostGenerate) / exact_steps,
+             "device_wait_s_per_step": (cA.secondsDeviceWait + cP.secondsDeviceWait) / exact_steps,
+             "h2d_bytes_per_step": h2d_step, "d2h_bytes_per_step": d2h_step}
+    clock_info = clocks.stop()
 
-    if world > 1:
-        t = torch.tensor([elapsed], dtype=torch.float64, device="cuda")
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        elapsed_max = float(t.item())
-        u = torch.tensor([float(updates), float(launches)], dtype=torch.float64, device="cuda")
-        dist.all_reduce(u, op=dist.ReduceOp.SUM)
-        total_updates, total_launches = float(u[0].item()), int(u[1].item())
-    else:
-        elapsed_max, total_updates, total_launches = elapsed, float(updates), int(launches)
-    value = total_updates / elapsed_max
-
-    # ---- roofline: the eval kernel of the timed region itself.  The resident kernel is launched once per
+    # ---- exact-mode roofline: the eval kernel of the timed region itself.  The resident kernel is launched once per
     # update() (2 per step); its duration comes from CUDA events on its stream, its bytes are the algorithmic
     # bytes (SURVEY 8d) of the proposals it evaluated.  The duration includes the time the grid waits for the
     # host generator: that is the launch as it runs in the product.
-    roofline = None
+    chisq_ms = None
+    timings = {}
     if rank == 0:
-        peak, peak_src = load_peaks()
         resident_bytes = cA.algorithmicBytes + cP.algorithmicBytes
         resident_time = cA.secondsKernel + cP.secondsKernel
-        n_launch = 2 * args.steps
+        n_launch = 2 * exact_steps
         # the same device code launched once per conflict-free batch, each launch bracketed by CUDA events
         for smp in (chain.A, chain.P):
             smp.setPersistent(False)
@@ -391,7 +473,7 @@ def main():
         # ---- the scan kernel with enough work: alphaParameters probes (DenseNormalModel.cpp:162-240 through the same
         # staging + scan + reduce code, no proposal epilogue), every row once, ONE launch (probe_kernel), CUDA events
         # around it.  This is what the kernel sustains when the generator is not the limit.
-        if not args.sparse:
+        if dense:
             rngq = np.random.default_rng(5)
             sat = {}
             for nm, smp, nrows in (("A", chain.A, args.rows), ("P", chain.P, args.cols)):
@@ -417,15 +499,27 @@ def main():
                                           "how": "cgb_sampler_alpha_parameters: the eval kernel's staging + scan + reduce on one "
                                                  "(row, column) probe per row, all rows in one launch, cudaEvent pair around it; "
                                                  "bytes = 16 L (one column) or 20 L (two columns of one row) per probe"}
-        # chi-sq wall time (second half of BASELINE.json's metric)
-        tcs = time.perf_counter()
-        for _ in range(5):
-            chain.P.chiSq()
-        chisq_ms = (time.perf_counter() - tcs) / 5 * 1e3
-    atomsA, atomsP = chain.A.nAtoms(), chain.P.nAtoms()
+        exact["roofline"] = roofline
+        # ---- chi-sq wall time (second half of BASELINE.json's metric) and the other whole-matrix passes of the path ----
+        def wall_ms(fn, n=5):
+            fn()
+            torch.cuda.synchronize()
+            t = time.perf_counter()
+            for _ in range(n):
+                fn()
+            torch.cuda.synchronize()
+            return (time.perf_counter() - t) / n * 1e3
+        chisq_ms = wall_ms(chain.P.chiSq)
+        nbytes = 8.0 * args.rows * args.cols            # D and AP once (S is derived)
+        timings = {"chisq_ms": chisq_ms, "chisq_frac_of_hbm_peak": nbytes / (chisq_ms * 1e-3) / 1e9 / peak if dense else None,
+                   "sync_ms": wall_ms(lambda: chain.A.sync(chain.P)) if dense else None,
+                   "extra_init_ms": wall_ms(chain.P.extraInitialization, 3) if dense else None}
+        if dense:
+            timings["sync_frac_of_hbm_peak"] = nbytes / (timings["sync_ms"] * 1e-3) / 1e9 / peak
+            timings["extra_init_frac_of_hbm_peak"] = 4.0 * args.rows * args.cols / (timings["extra_init_ms"] * 1e-3) / 1e9 / peak
     del chain
 
-    # ---- several chains sharing the device (the generator of ONE chain cannot keep a B200 busy) ----
+    # ---- several chains sharing the device (the generator of ONE exact-mode chain cannot keep a B200 busy) ----
     multi = None
     if rank == 0 and args.chains > 1:
         check(cg.lib().cgb_set_resident_share(args.chains))
@@ -434,12 +528,12 @@ def main():
         done_updates = [0] * args.chains
 
         def drive(i):
-            chains[i].ramp(args.ramp)
+            chains[i].ramp(min(args.ramp, 50))
             for _ in range(args.warmup):
                 chains[i].step()
             gate.wait()
             n = 0
-            for _ in range(args.steps):
+            for _ in range(exact_steps):
                 n += chains[i].step()
             done_updates[i] = n
             gate.wait()
@@ -455,36 +549,47 @@ def main():
         for w in workers:
             w.join()
         multi = {"chains": args.chains, "value": sum(done_updates) / tm, "unit": "atom-updates/s (sum over chains)",
-                 "ms_per_step": tm / args.steps * 1e3, "per_chain": [u / tm for u in done_updates],
-                 "how": "independent chains on one GPU, one host thread each, cgb_set_resident_share(chains); same workload, "
-                        "ramp and step count as the single-chain line"}
+                 "ms_per_step": tm / exact_steps * 1e3, "per_chain": [u / tm for u in done_updates],
+                 "how": "independent exact-mode chains on one GPU, one host thread each, cgb_set_resident_share(chains)"}
         del chains
         check(cg.lib().cgb_set_resident_share(1))
 
-    # ---- end to end: cgb_run (= gaps::run) on host buffers ----
-    e2e = None
-    if rank == 0 and not args.no_e2e:
-        # three identical calls (same seed, same chain), the median by wall clock: the call is about a second and its
+    # ---- end to end: cgb_run (= gaps::run) on host buffers, both modes ----
+    def e2e_of(update_mode, n_calls):
+        # identical calls (same seed, same chain), the median by wall clock: the call is about a second and its
         # allocation / teardown share varies from box to box and run to run
         calls = []
-        for _ in range(3):
+        for _ in range(n_calls):
             t0 = time.perf_counter()
             res = cg.gaps_run(data, seed=CHAIN_SEED, nPatterns=args.patterns, nIterations=args.e2e_iters,
-                              outputFrequency=0, maxThreads=1, useSparseOptimization=1 if args.sparse else 0)
-            calls.append((time.perf_counter() - t0, float(res.totalRunningTime)))
-        wall, loop_s = sorted(calls)[1]
+                              outputFrequency=0, maxThreads=1, useSparseOptimization=1 if args.sparse else 0,
+                              updateMode=update_mode)
+            calls.append((time.perf_counter() - t0, float(res.totalRunningTime), int(res.totalUpdates)))
+        wall, loop_s, upd = sorted(calls)[len(calls) // 2]
         n_it = 2 * args.e2e_iters
         upload = 2.0 * data.nbytes
         results = 4.0 * 2 * (args.rows + args.cols) * args.patterns
-        e2e = {"value": res.totalUpdates / wall, "unit": "atom-updates/s",
-               "h2d_bytes_per_step": (upload + h2d_step * args.steps / max(updates, 1) * res.totalUpdates) / n_it,
-               "d2h_bytes_per_step": (results + 16.0 * res.totalUpdates) / n_it,
-               "call": "cgb_run (gaps::run): host fp32 matrix in, Amean/Asd/Pmean/Psd out",
-               "iterations_per_phase": args.e2e_iters, "atom_updates": int(res.totalUpdates), "wall_s": wall,
-               "wall_s_of_each_call": [c[0] for c in calls], "how": "median of three identical calls",
-               # the part of the call the reference arm's value covers (its sampler loop, GapsRunner.cpp:450,473)
-               "sampler_loop_s": loop_s,
-               "sampler_loop_value": res.totalUpdates / max(loop_s, 1e-9)}
+        per_update_h2d = (h2d_step * exact_steps / max(exact["atom_updates"], 1)) if update_mode == 0 else 0.0
+        per_update_d2h = 16.0 if update_mode == 0 else 0.0
+        return {"value": upd / wall, "unit": "atom-updates/s",
+                "h2d_bytes_per_step": (upload + per_update_h2d * upd) / n_it + (0.0 if update_mode == 0 else 2 * 512.0),
+                "d2h_bytes_per_step": (results + per_update_d2h * upd) / n_it + (0.0 if update_mode == 0 else 2 * 72.0),
+                "call": "cgb_run (gaps::run): host fp32 matrix in, Amean/Asd/Pmean/Psd out; updateMode=%d" % update_mode,
+                "iterations_per_phase": args.e2e_iters, "atom_updates": upd, "wall_s": wall,
+                "wall_s_of_each_call": [c[0] for c in calls], "how": "median of %d identical calls" % n_calls,
+                # the part of the call the reference arm's value covers (its sampler loop, GapsRunner.cpp:450,473)
+                "sampler_loop_s": loop_s, "sampler_loop_value": upd / max(loop_s, 1e-9)}
+
+    if rank == 0 and not args.no_e2e:
+        if dense:
+            sweep["e2e"] = e2e_of(1, 3)
+        exact["e2e"] = e2e_of(0, 3)
+
+    # ---- BASELINE.json configs[4] on N > 1 GPUs: every rank runs its 200000/N x 30000 k=50 sparse shard, then the NCCL
+    # all-gather of the per-shard P rows through the C ABI (cgb_comm_init / cgb_allgather_rows) ----
+    c5 = None
+    if world > 1 and not args.no_c5:
+        c5 = run_c5(args, rank, world, local_rank, barrier, reduce_max_sum)
 
     cpu_baseline = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
@@ -492,24 +597,92 @@ def main():
         cpu_baseline = {"value": v, "unit": "atom-updates/s", "cores": threads, "kind": "reference", "sample": sample}
 
     if rank == 0:
-        line = {"metric": "atom_updates_per_s", "value": value, "unit": "atom-updates/s", "n_gpus": args.gpus,
-                "steps": args.steps, "warmup": args.warmup, "ms_per_step": elapsed_max / args.steps * 1e3,
+        head = sweep if mode == "sweep" else exact
+        line = {"metric": "atom_updates_per_s", "value": head["value"], "unit": "atom-updates/s", "n_gpus": args.gpus,
+                "steps": head["steps"], "warmup": args.warmup, "ms_per_step": head["ms_per_step"],
                 "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
-                "data": "synthetic", "config": config, "clocks": clock_info, "e2e": e2e,
-                "gpu_launches": total_launches, "roofline": roofline, "cpu_baseline": cpu_baseline,
-                "chisq_ms": chisq_ms, "atoms": {"A": int(atomsA), "P": int(atomsP)},
-                "batches_per_step": batches / args.steps, "proposals_per_batch": queued / max(batches, 1),
-                "host_generate_s_per_step": (cA.secondsHostGenerate + cP.secondsHostGenerate) / args.steps,
-                "device_wait_s_per_step": (cA.secondsDeviceWait + cP.secondsDeviceWait) / args.steps,
-                "h2d_bytes_per_step": h2d_step, "d2h_bytes_per_step": d2h_step, "setup_s": setup_s,
+                "data": "synthetic", "config": config, "clocks": clock_info, "e2e": head.get("e2e"),
+                "gpu_launches": head["gpu_launches"], "roofline": head["roofline"], "cpu_baseline": cpu_baseline,
+                "mode": mode, "atoms": head["atoms"], "setup_s": setup_s,
+                "chisq_ms": chisq_ms, "whole_matrix_passes": timings,
                 "timer": "CUDA events around the K timed steps (device clock), max over ranks; host perf_counter over the "
-                         "same region: %.3f ms per step" % (elapsed_host / args.steps * 1e3)}
+                         "same region: %.3f ms per step" % head["host_ms_per_step"]}
+        if dense:
+            line["sweep_mode"] = sweep
+        line["exact_mode"] = exact
+        # kept at top level for continuity with round 1 (exact mode)
+        line["host_generate_s_per_step"] = exact["host_generate_s_per_step"]
+        line["device_wait_s_per_step"] = exact["device_wait_s_per_step"]
         if multi is not None:
             line["multi_chain"] = multi
+        if c5 is not None:
+            line["c5"] = c5
         print(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()
     return 0
+
+
+def run_c5(args, rank, world, local_rank, barrier, reduce_max_sum):
+    """BASELINE.json configs[4]: distributed scCoGAPS row-shard of 200000 x 30000, nPatterns=50 (sparse model) over the
+    ranks, then the all-gather of the per-shard P rows (stitchTogether, R/DistributedCogaps.R:226-278) through the C ABI's
+    own NCCL communicator, straight from the samplers' device matrices."""
+    import torch
+    import torch.distributed as dist
+    import cogaps_b200 as cg
+    genes, cells_total, k = args.c5_genes, args.c5_cells, args.c5_patterns
+    base = cells_total // world
+    sizes = [base] * (world - 1) + [cells_total - base * (world - 1)]      # R/SubsetData.R:63-75,90
+    cells = sizes[rank]
+    t0 = time.time()
+    data = make_data(genes, cells, k, DATA_SEED + 1000 + rank, 0.95)        # genes x this rank's cells (C4 recipe)
+    chain = Chain(data, k, CHAIN_SEED + rank, sparse=True)
+    del data
+    chain.ramp(args.c5_ramp)
+    setup_s = time.time() - t0
+    chain.A.resetCounters()
+    chain.P.resetCounters()
+    barrier()
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    ev0.record()
+    asked = 0
+    for _ in range(args.c5_steps):
+        asked += chain.step()
+    torch.cuda.synchronize()
+    ev1.record()
+    barrier()
+    elapsed = ev0.elapsed_time(ev1) * 1e-3
+    # the C ABI's communicator: rank 0 makes the id, the launcher's process group carries it to the others
+    ids = [cg.Comm.unique_id() if rank == 0 else None]
+    dist.broadcast_object_list(ids, src=0)
+    comm = cg.Comm(ids[0], rank, world)
+    comm.allgatherRows(chain.P, sizes)                                      # warm-up: communicator channels, staging buffers
+    barrier()
+    full = comm.allgatherRows(chain.P, sizes)                               # (cells_total, k) on the host of every rank
+    gather_ms = comm.last_ms
+    mine = chain.P.getMatrix()
+    row0 = sum(sizes[:rank])
+    ok = bool(np.array_equal(full[row0:row0 + cells], mine))
+    checksum = float(full.astype(np.float64).sum())
+    own = float(mine.astype(np.float64).sum())
+    el, (updates, own_sum, oks) = reduce_max_sum(elapsed, [asked, own, 1.0 if ok else 0.0])
+    gm, _ = reduce_max_sum(gather_ms, [0.0])
+    atoms = {"A": int(chain.A.nAtoms()), "P": int(chain.P.nAtoms())}
+    del chain, comm
+    if rank != 0:
+        return None
+    return {"workload": "synthetic sparse %dx%d (95%% zeros) nPatterns=%d, cells sharded over %d GPUs (%s per GPU)"
+                        % (genes, cells_total, k, world, sizes),
+            "value": updates / el, "unit": "atom-updates/s (sum over shards)", "ms_per_step": el / args.c5_steps * 1e3,
+            "steps": args.c5_steps, "ramp_iterations": args.c5_ramp, "per_rank_updates_per_s": updates / el / world,
+            "sampler": "asynchronous, sparse normal model, exact mode", "atoms_rank0": atoms, "setup_s_rank0": setup_s,
+            "allgather": {"what": "per-shard P rows (cells x nPatterns), pattern-major device blocks straight from the samplers",
+                          "api": "cgb_comm_init + cgb_allgather_rows (ncclAllGather on the library's own stream)",
+                          "allgather_us": gm * 1e3, "bytes_per_rank": int(k * ((max(sizes) + 31) // 32 * 32) * 4),
+                          "bytes_total": int(k * ((max(sizes) + 31) // 32 * 32) * 4 * world),
+                          "every_rank_found_its_own_rows_in_place": bool(oks == world),
+                          "checksum_matches_sum_of_shards": bool(abs(checksum - own_sum) <= 1e-6 * max(1.0, abs(own_sum)))},
+            "scaling": "strong (the matrix is fixed; each GPU owns cells_total / N cells)"}
 
 
 if __name__ == "__main__":

@@ -6,5 +6,5 @@ this package is the thin host-side mirror of the reference's R/C++ interface for
 from .api import (CoGAPS, CogapsParams, CogapsResult, gaps_run, gaps_run_file, read_matrix_file,  # noqa: F401
                   checkpoint_info, checkpoint_rewrite, read_matrix_csr, write_matrix_csv, write_result_files,
                   buildReport, checkpointsEnabled, compiledWithOpenMPSupport, getFileInfo)
-from .sampler import GapsRandomState, GapsRng, GibbsSampler, GapsStatistics  # noqa: F401
+from .sampler import GapsRandomState, GapsRng, GibbsSampler, GapsStatistics, Comm  # noqa: F401
 from ._lib import CogapsError, LIB_PATH, lib  # noqa: F401

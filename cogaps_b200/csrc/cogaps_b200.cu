@@ -12,6 +12,7 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <mutex>
 #include <new>
 #include <string>
 #include <thread>
@@ -25,6 +26,9 @@ static thread_local std::string g_lastError;
 static std::atomic<uint64_t> g_kernelLaunches(0);
 static std::atomic<int> g_residentShare(1); // chains that share the device: each resident grid takes 1/share of it
 static int g_device = -1;
+// Set once a tool that serialises kernel launches (Nsight Compute, compute-sanitizer, CUDA_LAUNCH_BLOCKING=1) is known to
+// be attached: a resident grid that converses with the host cannot run under one, so samplers use one launch per batch.
+static std::atomic<int> g_serialisedLaunches(-1); // -1 unknown, 0 no, 1 yes
 
 static int fail(int code, const std::string &msg)
 {
@@ -96,6 +100,35 @@ static int envInt(const char *name, int dflt)
 {
     const char *v = std::getenv(name);
     return (v && *v) ? std::atoi(v) : dflt;
+}
+
+
+// A resident grid needs the host to keep running while it is on the device.  Tools that hold the host inside the launch
+// call until the kernel has ended make that impossible; they announce themselves through the environment.
+static bool serialisingToolAnnounced()
+{
+    const char *blocking = std::getenv("CUDA_LAUNCH_BLOCKING");
+    if (blocking && blocking[0] == '1') { return true; }
+    static const char *const names[] = {"CUDA_INJECTION64_PATH", "CUDA_INJECTION32_PATH", "NV_COMPUTE_PROFILER_PERFWORKS_DIR",
+                                        "NV_NSIGHT_INJECTION_PORT_BASE", "NV_NSIGHT_INJECTION_TRANSPORT_TYPE", "COMPUTE_SANITIZER_INJECTION",
+                                        "NV_SANITIZER_INJECTION_PORT_BASE", "NSYS_PROFILING_SESSION_ID"};
+    for (size_t i = 0; i < sizeof(names) / sizeof(names[0]); ++i)
+    {
+        const char *v = std::getenv(names[i]);
+        if (v && v[0]) { return true; }
+    }
+    return false;
+}
+
+static bool residentGridAllowed()
+{
+    int known = g_serialisedLaunches.load();
+    if (known < 0)
+    {
+        known = serialisingToolAnnounced() ? 1 : 0;
+        g_serialisedLaunches.store(known);
+    }
+    return known == 0;
 }
 
 static int ensureDevice()
@@ -492,7 +525,7 @@ static int samplerCreateImpl(const float *data, uint32_t nrow, uint32_t ncol, in
     s->sparse = params->useSparseOptimization != 0;
     s->dSpRowPtr = s->dSpIdx = nullptr; s->dSpVal = s->dMrows = s->dZ1 = s->dZ2 = nullptr; s->ldR = 0;
     s->dColNonzero = nullptr; s->dPartials = nullptr; s->dTickets = nullptr; s->dReducePartials = nullptr;
-    s->usePersistent = envInt("COGAPS_PERSISTENT", 1) != 0; s->persistentRunning = false;
+    s->usePersistent = envInt("COGAPS_PERSISTENT", residentGridAllowed() ? 1 : 0) != 0; s->persistentRunning = false;
     // test knobs for the rarely taken paths: every row read behind a rowVersion check; small chunks
     s->forceRowWait = envInt("COGAPS_FORCE_ROW_WAIT", 0) != 0;
     {
@@ -892,7 +925,7 @@ static int cgb_sampler_extra_initialization_body(cgb_sampler *s)
     if (s->sparse) { return CGB_OK; } // SparseNormalModel::extraInitialization is a nop (SparseNormalModel.cpp:33-37)
     CGB_CUDA(cudaSetDevice(s->device));
     CGB_CUDA(cudaStreamSynchronize(s->other->stream));
-    dim3 grid((s->L + 255) / 256, s->nRows);
+    dim3 grid(s->nRows, (s->L + 1023) / 1024);
     rebuild_ap_kernel<<<grid, 256, 0, s->stream>>>(s->dAP, s->dM, s->other->dM, s->nRows, s->L, s->k, s->ld, s->ldM, s->other->ldM);
     ++g_kernelLaunches;
     CGB_CUDA(cudaGetLastError());
@@ -1162,8 +1195,11 @@ static inline bool rowSettled(cgb_sampler *s, uint32_t row)
 // ------------------------------------------------------------------------------------------------
 static size_t streamSmemBytes(const cgb_sampler *s) { return evalSmemBytes(s) + (s->tablesInSmem ? kStreamTableBytes : 0); }
 
+static const int kResidentUnavailable = 1; // startPersistent / beginChunk: fall back to one launch per batch
+
 static int startPersistent(cgb_sampler *s)
 {
+    if (g_serialisedLaunches.load() == 1) { s->usePersistent = false; return kResidentUnavailable; }
     cudaLaunchConfig_t cfg = cudaLaunchConfig_t();
     cfg.blockDim = dim3(s->sparse ? kSparseThreads : kThreads, 1, 1);
     cfg.dynamicSmemBytes = streamSmemBytes(s);
@@ -1236,9 +1272,20 @@ static int startPersistent(cgb_sampler *s)
     s->commitsExpected[0] = s->commitsExpected[1] = 0;
     s->provenThrough[0] = s->provenThrough[1] = s->mailSeq;
     CGB_CUDA(cudaEventRecord(s->evStart, s->stream));
+    const double tLaunch = nowSeconds();
     if (s->sparse) { CGB_CUDA(cudaLaunchKernelEx(&cfg, eval_stream_sparse_kernel, mv, sp)); }
     else if (s->hasS) { CGB_CUDA(cudaLaunchKernelEx(&cfg, eval_stream_kernel<true>, mv, sp)); }
     else { CGB_CUDA(cudaLaunchKernelEx(&cfg, eval_stream_kernel<false>, mv, sp)); }
+    if (nowSeconds() - tLaunch > 0.5e-9 * static_cast<double>(sp.idleTimeoutNs))
+    {
+        // The launch call came back only after the workers' idle timeout: something unannounced serialises launches and
+        // the grid has come and gone without us.  From here on this process uses one launch per batch.
+        g_serialisedLaunches.store(1);
+        s->usePersistent = false;
+        ++g_kernelLaunches;
+        CGB_CUDA(cudaStreamSynchronize(s->stream));
+        return kResidentUnavailable;
+    }
     // No CUDA call from here until the exit records are posted: the grid only ends when this thread says so, and a
     // runtime call can block behind another thread's cudaFree / allocation that is itself waiting for the device
     // to drain (several chains per process) — that would be a deadlock.  evStop is recorded in stopPersistent.
@@ -1367,7 +1414,11 @@ static int beginChunk(cgb_sampler *s, size_t chunkBase)
     {
         CGB_TRY(stopPersistent(s)); // the grid may be about to give up waiting (idle timeout): restart it
     }
-    if (!s->persistentRunning) { CGB_TRY(startPersistent(s)); }
+    if (!s->persistentRunning)
+    {
+        const int rc = startPersistent(s);
+        if (rc != CGB_OK) { return rc; } // including kResidentUnavailable
+    }
     s->lastPostTime = t0;
     ++s->mailSeq;
     {
@@ -1558,7 +1609,11 @@ static int evalOne(cgb_sampler *s, DevProposal &dp, DevOutcome &o)
     dp.rng = s->seq.rng.state;
     if (s->usePersistent)
     {
-        CGB_TRY(beginChunk(s, 0));
+        const int rcBegin = beginChunk(s, 0);
+        if (rcBegin != CGB_OK && rcBegin != kResidentUnavailable) { return rcBegin; }
+    }
+    if (s->usePersistent)
+    {
         if (s->posted.empty())
         {
             s->posted.resize(256);
@@ -1590,7 +1645,6 @@ static int sequentialUpdate(cgb_sampler *s, uint32_t nSteps)
 {
     SequentialState &q = s->seq;
     AtomicDomain &dom = s->domain;
-    const bool resident = s->usePersistent;
     for (uint32_t step = 0; step < nSteps; ++step)
     {
         // getUpdateType, :94-111
@@ -1624,7 +1678,7 @@ static int sequentialUpdate(cgb_sampler *s, uint32_t nSteps)
             if (o.accepted)
             {
                 dom.insert(pos, o.mass1);
-                noteCommit(s, dp, resident);
+                noteCommit(s, dp, s->usePersistent);
             }
         }
         else if (type == 'D')
@@ -1639,13 +1693,13 @@ static int sequentialUpdate(cgb_sampler *s, uint32_t nSteps)
                 if (o.mass1 != dp.m1)
                 {
                     dom.atom(id).mass = o.mass1;
-                    noteCommit(s, dp, resident);
+                    noteCommit(s, dp, s->usePersistent);
                 }
             }
             else
             {
                 dom.erase(id);
-                noteCommit(s, dp, resident);
+                noteCommit(s, dp, s->usePersistent);
             }
         }
         else if (type == 'M')
@@ -1668,7 +1722,7 @@ static int sequentialUpdate(cgb_sampler *s, uint32_t nSteps)
             if (o.accepted)
             {
                 dom.move(id, pos);
-                noteCommit(s, dp, resident);
+                noteCommit(s, dp, s->usePersistent);
             }
         }
         else
@@ -1687,7 +1741,7 @@ static int sequentialUpdate(cgb_sampler *s, uint32_t nSteps)
             {
                 dom.atom(id1).mass = o.mass1;
                 dom.atom(id2).mass = o.mass2;
-                noteCommit(s, dp, resident);
+                noteCommit(s, dp, s->usePersistent);
             }
         }
     }
@@ -1704,7 +1758,8 @@ static int sequentialUpdate(cgb_sampler *s, uint32_t nSteps)
 static const uint32_t kSweepInitialCap = 64;
 static const size_t kSweepMaxSmem = 227u * 1024u;
 
-static uint32_t sweepThreadsForLength(uint32_t L) { return L <= 4096u ? 128u : (L <= 16384u ? 256u : 512u); }
+static uint32_t sweepThreadsForLength(uint32_t L) { return L <= 10240u ? 256u : 512u; }
+static const int kSweepKeep = 10; // float4 per thread and column kept in registers between scan and commit (512-thread rows up to 20480 floats)
 
 static int cgb_sweep_reduction_order_for_length_body(uint32_t rowLength, cgb_reduction_order *out)
 {
@@ -1902,24 +1957,54 @@ extern "C" int cgb_sampler_set_update_mode(cgb_sampler *s, int32_t mode)
     return guarded("cgb_sampler_set_update_mode", [&]() { return cgb_sampler_set_update_mode_body(s, mode); });
 }
 
-template <int T, bool HAS_S, bool ROW_SMEM>
+// The opt-in shared-memory limit is a property of the kernel instance, not of a sampler: it only ever grows, under a
+// lock (several chains may share the process).
+template <class Kernel>
+static int sweepGrowSmemLimit(Kernel kernel, size_t smem)
+{
+    static std::mutex lock;
+    static size_t configured = 48u * 1024u;
+    std::lock_guard<std::mutex> hold(lock);
+    if (smem > configured)
+    {
+        CGB_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
+        configured = smem;
+    }
+    return CGB_OK;
+}
+
+template <int T, int NV, bool HAS_S, bool ROW_SMEM>
 static int sweepLaunchInstance(cgb_sampler *s, const SweepArgs &args, size_t smem)
 {
-    if (s->swSmemConfigured[ROW_SMEM ? 1 : 0] != smem)
-    {
-        CGB_CUDA(cudaFuncSetAttribute(sweep_kernel<T, HAS_S, ROW_SMEM>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
-        s->swSmemConfigured[ROW_SMEM ? 1 : 0] = smem;
-    }
-    sweep_kernel<T, HAS_S, ROW_SMEM><<<s->nRows, T, smem, s->stream>>>(args);
+    CGB_TRY(sweepGrowSmemLimit(sweep_kernel<T, NV, HAS_S, ROW_SMEM>, smem));
+    sweep_kernel<T, NV, HAS_S, ROW_SMEM><<<s->nRows, T, smem, s->stream>>>(args);
     g_kernelLaunches.fetch_add(1);
     return CGB_OK;
 }
 
-template <int T>
-static int sweepLaunchThreads(cgb_sampler *s, const SweepArgs &args, size_t smem, bool rowSmem)
+template <int T, bool HAS_S>
+static int sweepLaunchRows(cgb_sampler *s, const SweepArgs &args, size_t smem, bool rowSmem)
 {
-    if (s->hasS) { return rowSmem ? sweepLaunchInstance<T, true, true>(s, args, smem) : sweepLaunchInstance<T, true, false>(s, args, smem); }
-    return rowSmem ? sweepLaunchInstance<T, false, true>(s, args, smem) : sweepLaunchInstance<T, false, false>(s, args, smem);
+    const bool keep = rowSmem && T == 512 && (s->L + kVec - 1) / kVec <= static_cast<uint32_t>(kSweepKeep) * T;
+    if (!rowSmem) { return sweepLaunchInstance<T, 0, HAS_S, false>(s, args, smem); }
+    if (keep) { return sweepLaunchInstance<T, (T == 512 ? kSweepKeep : 0), HAS_S, true>(s, args, smem); }
+    return sweepLaunchInstance<T, 0, HAS_S, true>(s, args, smem);
+}
+
+template <int T, bool HAS_S>
+static int sweepLaunchTransport(cgb_sampler *s, SweepArgs &args)
+{
+    // pairs (r, r+1) with even r on even-numbered updates of this sampler, odd r on odd-numbered ones
+    const uint32_t colour = static_cast<uint32_t>(s->swUpdates & 1ull);
+    const uint32_t pairs = (s->nRows - colour) / 2u;
+    if (s->nRows >= 2u && pairs > 0u)
+    {
+        args.colour = colour;
+        sweep_transport_kernel<T, HAS_S><<<pairs, T, 0, s->stream>>>(args);
+        g_kernelLaunches.fetch_add(1);
+        CGB_CUDA(cudaGetLastError());
+    }
+    return CGB_OK;
 }
 
 static int sweepUpdate(cgb_sampler *s, uint32_t nSteps)
@@ -1935,6 +2020,9 @@ static int sweepUpdate(cgb_sampler *s, uint32_t nSteps)
     args.counters = static_cast<SweepCounters*>(s->dSwCounters);
     args.key = s->rs->seeder.next();                      // one seeder value per update()
     args.binLength = 0xFFFFFFFFFFFFFFFFull / (static_cast<uint64_t>(s->nRows) * s->k);
+    args.binMagic = (args.binLength > 1) ? static_cast<uint64_t>((static_cast<unsigned __int128>(1) << 64) / args.binLength) : 0ull;
+    args.colour = 0;
+    args.pad = 0;
     const SweepRates w = sweepRates(s->swTotalAtoms, s->nRows, s->k, args.binLength, static_cast<double>(s->alpha));
     args.birthRow = w.birthRow;
     args.deathAtom = w.deathAtom;
@@ -1951,10 +2039,28 @@ static int sweepUpdate(cgb_sampler *s, uint32_t nSteps)
     CGB_CUDA(cudaMemsetAsync(s->dSwCounters, 0, sizeof(SweepCounters), s->stream));
     CGB_CUDA(cudaEventRecord(s->evStart, s->stream));
     const uint32_t T = sweepThreadsForLength(s->L);
-    if (T == 128u) { CGB_TRY(sweepLaunchThreads<128>(s, args, smem, rowSmem)); }
-    else if (T == 256u) { CGB_TRY(sweepLaunchThreads<256>(s, args, smem, rowSmem)); }
-    else { CGB_TRY(sweepLaunchThreads<512>(s, args, smem, rowSmem)); }
+    if (T == 256u)
+    {
+        if (s->hasS) { CGB_TRY((sweepLaunchRows<256, true>(s, args, smem, rowSmem))); } else { CGB_TRY((sweepLaunchRows<256, false>(s, args, smem, rowSmem))); }
+    }
+    else
+    {
+        if (s->hasS) { CGB_TRY((sweepLaunchRows<512, true>(s, args, smem, rowSmem))); } else { CGB_TRY((sweepLaunchRows<512, false>(s, args, smem, rowSmem))); }
+    }
     CGB_CUDA(cudaGetLastError());
+    if (envInt("COGAPS_SWEEP_TRANSPORT", 1) != 0)
+    {
+        // transport between adjacent rows (see sweep.cuh)
+        if (T == 256u)
+        {
+            if (s->hasS) { CGB_TRY((sweepLaunchTransport<256, true>(s, args))); } else { CGB_TRY((sweepLaunchTransport<256, false>(s, args))); }
+        }
+        else
+        {
+            if (s->hasS) { CGB_TRY((sweepLaunchTransport<512, true>(s, args))); } else { CGB_TRY((sweepLaunchTransport<512, false>(s, args))); }
+        }
+    }
+    s->swUpdates += 1;
     CGB_CUDA(cudaEventRecord(s->evStop, s->stream));
     sweep_max_count_kernel<<<(s->nRows + 255u) / 256u, 256, 0, s->stream>>>(s->dSwCount, s->nRows, &static_cast<SweepCounters*>(s->dSwCounters)->maxCount);
     g_kernelLaunches.fetch_add(1);
@@ -1968,9 +2074,9 @@ static int sweepUpdate(cgb_sampler *s, uint32_t nSteps)
     CGB_CUDA(cudaEventElapsedTime(&ms, s->evStart, s->evStop));
     s->counters.secondsKernel += static_cast<double>(ms) * 1e-3;
     s->counters.nBatches += 1;
-    s->counters.nProposalsQueued += c.scans1 + c.scans2;
+    s->counters.nProposalsQueued += c.scans1 + c.scans2 + c.scansX;
     s->counters.nProposalsTotal += c.steps;
-    s->counters.algorithmicBytes += static_cast<double>(s->L) * (16.0 * static_cast<double>(c.scans1) + 20.0 * static_cast<double>(c.scans2) + 4.0 * static_cast<double>(c.commits));
+    s->counters.algorithmicBytes += static_cast<double>(s->L) * (16.0 * static_cast<double>(c.scans1) + 20.0 * static_cast<double>(c.scans2) + 32.0 * static_cast<double>(c.scansX) + 4.0 * static_cast<double>(c.commits));
     s->swTotalAtoms = static_cast<uint64_t>(static_cast<long long>(s->swTotalAtoms) + c.atomDelta);
     s->swOverflow += c.overflow;
     const uint32_t cap = sweepCapFor(s->swCap, c.maxCount);
@@ -2004,10 +2110,11 @@ static int cgb_sampler_update_body(cgb_sampler *s, uint32_t nSteps, uint32_t nTh
         SinkCtx sink;
         sink.s = s;
         sink.rc = CGB_OK;
+        int rcBegin = CGB_OK;
+        if (s->usePersistent) { rcBegin = beginChunk(s, 0); }
+        if (rcBegin != CGB_OK && rcBegin != kResidentUnavailable) { return rcBegin; }
         if (s->usePersistent)
         {
-            const int rcBegin = beginChunk(s, 0);
-            if (rcBegin != CGB_OK) { return rcBegin; }
             g_prof = g_hostProfile > 0 && ((g_profCounter++ & 15ull) == 0ull);
             if (g_prof) { ++g_profBatches; }
             const unsigned long long tp = g_prof ? tsc() : 0ull;
@@ -3411,6 +3518,219 @@ static int runCore(const float *data, const CsrPair *csr, uint32_t nrow, uint32_
         std::printf("[cgb_run] loop %.3f s, results %.3f s (teardown follows)\n", r->totalRunningTime, nowSeconds() - tStart - r->totalRunningTime);
     }
     return CGB_OK;
+}
+
+
+// ------------------------------------------------------------------------------------------------
+// Multi-GPU: one process per GPU, each running an independent chain on its own shard (what distributed
+// CoGAPS does per set, R/DistributedCogaps.R:48-119).  The only exchange on the path is the concatenation of per-shard
+// factor rows (stitchTogether, R/DistributedCogaps.R:226-278): an NCCL all-gather straight from device memory.  NCCL is
+// bound at run time (dlopen) so that a process which already carries one (torch) shares it and a single-GPU host needs none.
+// ------------------------------------------------------------------------------------------------
+#include <dlfcn.h>
+
+namespace {
+struct NcclUniqueId { char internal[CGB_COMM_UNIQUE_ID_BYTES]; };
+typedef int (*NcclGetUniqueIdFn)(NcclUniqueId*);
+typedef int (*NcclCommInitRankFn)(void**, int, NcclUniqueId, int);
+typedef int (*NcclCommDestroyFn)(void*);
+typedef int (*NcclAllGatherFn)(const void*, void*, size_t, int, void*, cudaStream_t);
+typedef const char *(*NcclGetErrorStringFn)(int);
+struct NcclApi
+{
+    void *handle;
+    NcclGetUniqueIdFn getUniqueId;
+    NcclCommInitRankFn commInitRank;
+    NcclCommDestroyFn commDestroy;
+    NcclAllGatherFn allGather;
+    NcclGetErrorStringFn errorString;
+};
+NcclApi g_nccl = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
+std::mutex g_ncclLock;
+const int kNcclFloat32 = 7; // ncclFloat32 (nccl.h)
+}
+
+static int loadNccl()
+{
+    std::lock_guard<std::mutex> hold(g_ncclLock);
+    if (g_nccl.handle) { return CGB_OK; }
+    const char *names[] = {std::getenv("COGAPS_NCCL_LIB"), "libnccl.so.2", "libnccl.so"};
+    void *h = nullptr;
+    for (size_t i = 0; i < sizeof(names) / sizeof(names[0]) && !h; ++i)
+    {
+        if (names[i] && names[i][0]) { h = dlopen(names[i], RTLD_NOW | RTLD_LOCAL); }
+    }
+    if (!h) { return fail(CGB_EUNSUPPORTED, "multi-GPU: libnccl.so.2 not found (set COGAPS_NCCL_LIB to its path)"); }
+    NcclApi api;
+    api.handle = h;
+    api.getUniqueId = reinterpret_cast<NcclGetUniqueIdFn>(dlsym(h, "ncclGetUniqueId"));
+    api.commInitRank = reinterpret_cast<NcclCommInitRankFn>(dlsym(h, "ncclCommInitRank"));
+    api.commDestroy = reinterpret_cast<NcclCommDestroyFn>(dlsym(h, "ncclCommDestroy"));
+    api.allGather = reinterpret_cast<NcclAllGatherFn>(dlsym(h, "ncclAllGather"));
+    api.errorString = reinterpret_cast<NcclGetErrorStringFn>(dlsym(h, "ncclGetErrorString"));
+    if (!api.getUniqueId || !api.commInitRank || !api.commDestroy || !api.allGather)
+    {
+        dlclose(h);
+        return fail(CGB_EUNSUPPORTED, "multi-GPU: the NCCL library lacks ncclGetUniqueId / ncclCommInitRank / ncclAllGather");
+    }
+    g_nccl = api;
+    return CGB_OK;
+}
+
+static int ncclFail(const char *what, int rc)
+{
+    const char *msg = g_nccl.errorString ? g_nccl.errorString(rc) : "";
+    return fail(CGB_ECUDA, std::string(what) + ": NCCL error " + std::to_string(rc) + " " + (msg ? msg : ""));
+}
+
+struct cgb_comm
+{
+    void *comm;
+    int rank, nRanks, device;
+    cudaStream_t stream;
+    cudaEvent_t ev0, ev1;
+    float *dSend, *dRecv;   // staging: [k][ldMax] and [nRanks][k][ldMax]
+    size_t sendFloats, recvFloats;
+};
+
+static int cgb_comm_get_unique_id_body(uint8_t *id)
+{
+    CGB_CHECK(id != nullptr, "cgb_comm_get_unique_id: NULL argument");
+    CGB_TRY(loadNccl());
+    NcclUniqueId u;
+    const int rc = g_nccl.getUniqueId(&u);
+    if (rc != 0) { return ncclFail("cgb_comm_get_unique_id", rc); }
+    std::memcpy(id, u.internal, CGB_COMM_UNIQUE_ID_BYTES);
+    return CGB_OK;
+}
+
+extern "C" int cgb_comm_get_unique_id(uint8_t *id)
+{
+    return guarded("cgb_comm_get_unique_id", [&]() { return cgb_comm_get_unique_id_body(id); });
+}
+
+extern "C" void cgb_comm_destroy(cgb_comm *c)
+{
+    if (!c) { return; }
+    cudaSetDevice(c->device);
+    if (c->comm && g_nccl.commDestroy) { g_nccl.commDestroy(c->comm); }
+    cudaFree(c->dSend);
+    cudaFree(c->dRecv);
+    if (c->ev0) { cudaEventDestroy(c->ev0); }
+    if (c->ev1) { cudaEventDestroy(c->ev1); }
+    if (c->stream) { cudaStreamDestroy(c->stream); }
+    delete c;
+}
+
+static int cgb_comm_init_body(const uint8_t *id, int32_t rank, int32_t nRanks, cgb_comm **out)
+{
+    CGB_CHECK(id && out, "cgb_comm_init: NULL argument");
+    CGB_CHECK(nRanks >= 1 && rank >= 0 && rank < nRanks, "cgb_comm_init: rank must be in [0, nRanks)");
+    CGB_TRY(ensureDevice());
+    CGB_TRY(loadNccl());
+    cgb_comm *c = new (std::nothrow) cgb_comm();
+    if (!c) { return fail(CGB_ENOMEM, "cgb_comm_init: out of memory"); }
+    c->rank = rank;
+    c->nRanks = nRanks;
+    c->device = g_device;
+    NcclUniqueId u;
+    std::memcpy(u.internal, id, CGB_COMM_UNIQUE_ID_BYTES);
+    int rc = CGB_OK;
+    do
+    {
+        if (cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking) != cudaSuccess || cudaEventCreate(&c->ev0) != cudaSuccess
+            || cudaEventCreate(&c->ev1) != cudaSuccess) { rc = fail(CGB_ECUDA, "cgb_comm_init: stream / event creation failed"); break; }
+        const int nrc = g_nccl.commInitRank(&c->comm, nRanks, u, rank);
+        if (nrc != 0) { c->comm = nullptr; rc = ncclFail("cgb_comm_init (ncclCommInitRank)", nrc); break; }
+    } while (false);
+    if (rc != CGB_OK) { cgb_comm_destroy(c); return rc; }
+    *out = c;
+    return CGB_OK;
+}
+
+extern "C" int cgb_comm_init(const uint8_t *id, int32_t rank, int32_t nRanks, cgb_comm **out)
+{
+    return guarded("cgb_comm_init", [&]() { return cgb_comm_init_body(id, rank, nRanks, out); });
+}
+
+// gathers pattern-major device blocks ([k][ld], element (row r, pattern p) at dev[p*ld + r]; rowsPerRank[rank] rows here)
+// of every rank into one row-major host matrix (sum of rows) x k, ranks in order
+static int allgatherRows(cgb_comm *c, const float *dev, uint64_t ld, uint32_t k, const uint32_t *rowsPerRank, float *out, double *deviceMs)
+{
+    CGB_CHECK(c && dev && rowsPerRank && out, "cgb_allgather_rows: NULL argument");
+    CGB_CUDA(cudaSetDevice(c->device));
+    uint32_t maxRows = 0;
+    uint64_t totalRows = 0;
+    for (int r = 0; r < c->nRanks; ++r) { maxRows = std::max(maxRows, rowsPerRank[r]); totalRows += rowsPerRank[r]; }
+    const uint32_t mine = rowsPerRank[c->rank];
+    CGB_CHECK(mine <= ld, "cgb_allgather_rows: rowsPerRank[rank] exceeds the block's stride");
+    const size_t ldMax = roundUp(std::max(maxRows, 1u), 32);
+    const size_t sendFloats = static_cast<size_t>(k) * ldMax, recvFloats = sendFloats * c->nRanks;
+    if (sendFloats > c->sendFloats)
+    {
+        cudaFree(c->dSend); c->dSend = nullptr; c->sendFloats = 0;
+        CGB_CUDA(cudaMalloc(&c->dSend, sendFloats * sizeof(float)));
+        c->sendFloats = sendFloats;
+    }
+    if (recvFloats > c->recvFloats)
+    {
+        cudaFree(c->dRecv); c->dRecv = nullptr; c->recvFloats = 0;
+        CGB_CUDA(cudaMalloc(&c->dRecv, recvFloats * sizeof(float)));
+        c->recvFloats = recvFloats;
+    }
+    // equal-size blocks for the collective: this rank's k columns, each padded to the widest shard
+    CGB_CUDA(cudaMemsetAsync(c->dSend, 0, sendFloats * sizeof(float), c->stream));
+    CGB_CUDA(cudaMemcpy2DAsync(c->dSend, ldMax * sizeof(float), dev, ld * sizeof(float), static_cast<size_t>(mine) * sizeof(float), k,
+                               cudaMemcpyDeviceToDevice, c->stream));
+    CGB_CUDA(cudaEventRecord(c->ev0, c->stream));
+    const int nrc = g_nccl.allGather(c->dSend, c->dRecv, sendFloats, kNcclFloat32, c->comm, c->stream);
+    if (nrc != 0) { return ncclFail("cgb_allgather_rows (ncclAllGather)", nrc); }
+    CGB_CUDA(cudaEventRecord(c->ev1, c->stream));
+    std::vector<float> host(recvFloats);
+    CGB_CUDA(cudaMemcpyAsync(host.data(), c->dRecv, recvFloats * sizeof(float), cudaMemcpyDeviceToHost, c->stream));
+    CGB_CUDA(cudaStreamSynchronize(c->stream));
+    if (deviceMs)
+    {
+        float ms = 0.f;
+        CGB_CUDA(cudaEventElapsedTime(&ms, c->ev0, c->ev1));
+        *deviceMs = ms;
+    }
+    uint64_t row0 = 0;
+    for (int r = 0; r < c->nRanks; ++r)
+    {
+        const float *blk = host.data() + static_cast<size_t>(r) * sendFloats;
+        for (uint32_t i = 0; i < rowsPerRank[r]; ++i)
+        {
+            for (uint32_t p = 0; p < k; ++p) { out[(row0 + i) * k + p] = blk[static_cast<size_t>(p) * ldMax + i]; }
+        }
+        row0 += rowsPerRank[r];
+    }
+    (void)totalRows;
+    return CGB_OK;
+}
+
+static int cgb_allgather_rows_body(cgb_comm *c, const cgb_sampler *s, const uint32_t *rowsPerRank, float *out, double *deviceMs)
+{
+    CGB_CHECK(c && s && rowsPerRank, "cgb_allgather_rows: NULL argument");
+    CGB_CHECK(rowsPerRank[c->rank] == s->nRows, "cgb_allgather_rows: rowsPerRank[rank] is not this sampler's row count");
+    CGB_CUDA(cudaSetDevice(s->device));
+    CGB_CUDA(cudaStreamSynchronize(s->stream));
+    return allgatherRows(c, s->dM, s->ldM, s->k, rowsPerRank, out, deviceMs);
+}
+
+extern "C" int cgb_allgather_rows(cgb_comm *c, const cgb_sampler *s, const uint32_t *rowsPerRank, float *out, double *deviceMs)
+{
+    return guarded("cgb_allgather_rows", [&]() { return cgb_allgather_rows_body(c, s, rowsPerRank, out, deviceMs); });
+}
+
+static int cgb_allgather_device_rows_body(cgb_comm *c, const void *dev, uint64_t ld, uint32_t k, const uint32_t *rowsPerRank, float *out, double *deviceMs)
+{
+    return allgatherRows(c, static_cast<const float*>(dev), ld, k, rowsPerRank, out, deviceMs);
+}
+
+extern "C" int cgb_allgather_device_rows(cgb_comm *c, const void *dev, uint64_t ld, uint32_t k, const uint32_t *rowsPerRank, float *out, double *deviceMs)
+{
+    return guarded("cgb_allgather_device_rows", [&]() { return cgb_allgather_device_rows_body(c, dev, ld, k, rowsPerRank, out, deviceMs); });
 }
 
 // ------------------------------------------------------------------------------------------------

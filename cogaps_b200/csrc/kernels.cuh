@@ -1155,7 +1155,7 @@ __device__ __forceinline__ void mirror_loop(const StreamParams &sp)
 {
     if (threadIdx.x != 0) { return; }
     unsigned long long mirrored[2] = {0ull, 0ull};
-    const unsigned long long t0 = global_timer_ns();
+    unsigned long long tLast = global_timer_ns(); // last time a counter moved
     for (uint32_t it = 0;; ++it)
     {
         bool changed = false;
@@ -1175,11 +1175,15 @@ __device__ __forceinline__ void mirror_loop(const StreamParams &sp)
         if (!changed) { __nanosleep(100); }
         if ((it & 15u) == 0u)
         {
-            // the host retires us at the end of update(); the workers have their own idle timeout
+            // the host retires us at the end of update().  Without the host (a profiler or CUDA_LAUNCH_BLOCKING holds
+            // it inside the launch call until the grid has ended) the workers leave after their idle timeout and
+            // nothing will ever commit again: leave shortly after them instead of holding the device.
             unsigned long long bell;
             asm volatile("ld.relaxed.sys.global.u64 %0, [%1];" : "=l"(bell) : "l"(sp.doorbell) : "memory");
             if (bell & kDoorbellExit) { break; }
-            if (global_timer_ns() - t0 > 3600000000000ull) { break; }
+            const unsigned long long now = global_timer_ns();
+            if (changed) { tLast = now; }
+            if (now - tLast > sp.idleTimeoutNs + sp.idleTimeoutNs / 2ull) { break; }
         }
     }
 }
@@ -1392,15 +1396,22 @@ __global__ void __launch_bounds__(256) rebuild_ap_kernel(float *__restrict__ AP,
                                                          uint32_t L, uint32_t k, uint32_t ld, uint32_t ldM,
                                                          uint32_t ldOther)
 {
-    const uint32_t r = blockIdx.y;
-    const uint32_t l = blockIdx.x * blockDim.x + threadIdx.x;
+    // one sampler row per blockIdx.x (rows can exceed the 65535 limit of the other grid dimensions), 1024 elements of
+    // it per block: 16-byte loads of the other factor's columns, the row's k factor elements broadcast from registers
+    const uint32_t r = blockIdx.x;
+    const uint32_t l = (blockIdx.y * blockDim.x + threadIdx.x) * 4u;
     if (r >= nRows || l >= L) { return; }
-    float acc = 0.f;
+    float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
     for (uint32_t c = 0; c < k; ++c)
     {
-        acc = fadd(acc, fmul(otherM[static_cast<size_t>(c) * ldOther + l], M[static_cast<size_t>(c) * ldM + r]));
+        const float m = __ldg(M + static_cast<size_t>(c) * ldM + r);
+        const float4 o = __ldg(reinterpret_cast<const float4*>(otherM + static_cast<size_t>(c) * ldOther + l)); // padded with zeros
+        acc.x = fadd(acc.x, fmul(o.x, m));
+        acc.y = fadd(acc.y, fmul(o.y, m));
+        acc.z = fadd(acc.z, fmul(o.z, m));
+        acc.w = fadd(acc.w, fmul(o.w, m));
     }
-    AP[static_cast<size_t>(r) * ld + l] = acc;
+    reinterpret_cast<float4*>(AP + static_cast<size_t>(r) * ld + l)[0] = acc; // the pad of the line gets exact zeros
 }
 
 // ------------------------------------------------------------------------------------------------

@@ -306,8 +306,8 @@ struct cgb_sampler
     void *dSwCounters;            // cgb::SweepCounters
     void *hSwCounters;            // pinned copy
     uint64_t swTotalAtoms;
+    uint64_t swUpdates;           // update() calls made in sweep mode: its parity picks which adjacent-row pairs get their turn
     uint64_t swOverflow;          // births dropped because a row's store was full (expected 0; the store regrows between updates)
-    size_t swSmemConfigured[2];   // dynamic shared memory already requested for the kernel instance in use, per ROW_SMEM
 
     // bench counters
     cgb_sampler_counters counters;

