@@ -47,7 +47,7 @@ G, S, K = 20000, 5000, 20
 DATA_SEED = 20260117
 CHAIN_SEED = 42
 RAMP_ITERS = 400         # untimed sweep iterations growing the chain from zero atoms to its steady state before warm-up
-E2E_ITERS = 40           # iterations per phase of the end-to-end / reference gaps::run call
+E2E_ITERS = 100          # iterations per phase of the end-to-end / reference gaps::run call
 EXACT_STEPS = 10         # timed exact-mode steps at the steady state (each ~35 ms there)
 
 

@@ -1424,19 +1424,30 @@ __global__ void __launch_bounds__(256) chisq_kernel(const float *__restrict__ D,
                                                     const float *__restrict__ AP, uint32_t nRows, uint32_t L,
                                                     uint32_t ld, double *__restrict__ partials)
 {
+    // 16-byte loads; the lines are padded (D and AP with zeros, a term of exactly 0) so whole vectors are read.  A block
+    // walks rows blockIdx.x, + gridDim.x, ...; a thread's f64 sum takes its elements in that fixed order.
     __shared__ double warpSum[8];
     double acc = 0.0;
+    const uint32_t nVec = (L + 3u) / 4u;
     for (uint32_t r = blockIdx.x; r < nRows; r += gridDim.x)
     {
-        const float *d = D + static_cast<size_t>(r) * ld;
-        const float *a = AP + static_cast<size_t>(r) * ld;
-        const float *s = S ? S + static_cast<size_t>(r) * ld : nullptr;
-        for (uint32_t l = threadIdx.x; l < L; l += blockDim.x)
+        const float4 *d = reinterpret_cast<const float4*>(D + static_cast<size_t>(r) * ld);
+        const float4 *a = reinterpret_cast<const float4*>(AP + static_cast<size_t>(r) * ld);
+        const float4 *s = S ? reinterpret_cast<const float4*>(S + static_cast<size_t>(r) * ld) : nullptr;
+#pragma unroll 2
+        for (uint32_t j = threadIdx.x; j < nVec; j += blockDim.x)
         {
-            const float dv = d[l];
-            const float sv = s ? s[l] : derive_s(dv);
-            const float t = fdiv(fsub(dv, a[l]), sv);
-            acc += static_cast<double>(fmul(t, t));
+            const float4 dv = __ldcs(d + j), av = __ldcs(a + j);
+            float4 sv;
+            if (s) { sv = __ldcs(s + j); }
+            else { sv = make_float4(derive_s(dv.x), derive_s(dv.y), derive_s(dv.z), derive_s(dv.w)); }
+            const uint32_t base = j * 4u;
+            const float t0 = fdiv(fsub(dv.x, av.x), sv.x), t1 = fdiv(fsub(dv.y, av.y), sv.y);
+            const float t2 = fdiv(fsub(dv.z, av.z), sv.z), t3 = fdiv(fsub(dv.w, av.w), sv.w);
+            acc += static_cast<double>(fmul(t0, t0));
+            if (base + 1u < L) { acc += static_cast<double>(fmul(t1, t1)); }
+            if (base + 2u < L) { acc += static_cast<double>(fmul(t2, t2)); }
+            if (base + 3u < L) { acc += static_cast<double>(fmul(t3, t3)); }
         }
     }
     for (int off = 16; off >= 1; off >>= 1) { acc += __shfl_xor_sync(0xffffffffu, acc, off); }

@@ -43,6 +43,12 @@
 
 #include "../include/cogaps_b200.h"
 
+// what runs the algorithm: the reference's own gaps::run, or (oracle/cuda_adapter.cpp, which includes this file) the
+// reference's run loop instantiated with the sampler that forwards to the C ABI
+#ifndef COGAPS_REF_RUN
+#define COGAPS_REF_RUN gaps::run
+#endif
+
 #ifdef _OPENMP
 #include <omp.h>
 #endif
@@ -151,7 +157,7 @@ int cogaps_ref_run_checkpointed(const float *data, uint32_t nrow, uint32_t ncol,
     GapsRandomState randState(params.seed);
     boost::posix_time::marks().n = 0;
     std::chrono::steady_clock::time_point t0 = std::chrono::steady_clock::now();
-    GapsResult res = gaps::run(D, params, U, &randState);
+    GapsResult res = COGAPS_REF_RUN(D, params, U, &randState);
     std::chrono::steady_clock::time_point t1 = std::chrono::steady_clock::now();
     {
         // the reference's own clock readings (see ref_shim/.../posix_time.hpp): [0] loading starts, [1] loading done,
