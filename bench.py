@@ -237,8 +237,8 @@ def main():
     ap.add_argument("--c5-genes", type=int, default=30000)
     ap.add_argument("--c5-cells", type=int, default=200000)
     ap.add_argument("--c5-patterns", type=int, default=50)
-    ap.add_argument("--c5-ramp", type=int, default=10)
-    ap.add_argument("--c5-steps", type=int, default=3)
+    ap.add_argument("--c5-ramp", type=int, default=40)
+    ap.add_argument("--c5-steps", type=int, default=5)
     ap.add_argument("--chains", type=int, default=0,
                     help="extra leg: this many independent chains on ONE GPU, one host thread each, every resident grid "
                          "taking 1/chains of the device (what distributed CoGAPS does with several sets per worker)")

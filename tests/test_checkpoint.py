@@ -451,3 +451,73 @@ def test_reader_survives_random_damage(tmp_path):
             except cg.CogapsError as e:
                 assert e.code == -1
     assert accepted > 0      # damage inside a float payload is still a valid archive
+
+
+@pytest.mark.gpu
+def test_resume_refuses_atom_counts_that_disagree_with_the_atoms(oracle, tmp_path):
+    """a damaged or crafted checkpoint whose archived proposal-queue atom counts (minAtoms / maxAtoms) do not
+    match the archived atom list must be refused at resume — it would let the first update pick from atoms that do not
+    exist — and so must a negative or non-finite atom mass.  The reader alone (cgb_checkpoint_rewrite) accepts such a
+    file: the counts are only meaningful against the sampler."""
+    import struct
+    import cogaps_b200 as cg
+    from cogaps_b200 import CogapsError
+    dataset, interval, kw = GPU_CASES["gist_dense"]
+    data = load_data(dataset)
+    good = tmp_path / "good.out"
+    oracle.run(data, options=device_options(oracle, data, kw, checkpointInterval=interval, checkpointOutFile=good), **kw)
+    raw = bytearray(good.read_bytes())
+    c = parse_file(good)
+    assert c["A"]["minAtoms"] == c["A"]["maxAtoms"] == c["A"]["pos"].size
+    # (1) the A sampler's queue record: rng, minAtoms, maxAtoms follow its atoms
+    key = struct.pack("<QQQ", c["A"]["rng"], c["A"]["minAtoms"], c["A"]["maxAtoms"])
+    at = bytes(raw).find(key)
+    assert at > 0 and bytes(raw).find(key, at + 1) < 0
+    for lo, hi in ((c["A"]["minAtoms"] + 3, c["A"]["maxAtoms"] + 3), (c["A"]["minAtoms"] - 1, c["A"]["maxAtoms"])):
+        bad = bytearray(raw)
+        bad[at + 8:at + 24] = struct.pack("<QQ", lo, hi)
+        path = tmp_path / "counts.out"
+        path.write_bytes(bytes(bad))
+        with pytest.raises(CogapsError) as err:
+            cg.gaps_run(data, checkpointInFile=path, checkpointOutFile=tmp_path / "unused.out", **kw)
+        assert err.value.code == -1 and "atom counts" in str(err.value)
+    # (2) a negative and a NaN mass in the A sampler's first atom (8-byte position, 4-byte mass)
+    first = struct.pack("<Qf", int(c["A"]["pos"][0]), float(c["A"]["mass"][0]))
+    at = bytes(raw).find(first)
+    assert at > 0
+    for mass in (-1.0, float("nan")):
+        bad = bytearray(raw)
+        bad[at + 8:at + 12] = struct.pack("<f", mass)
+        path = tmp_path / "mass.out"
+        path.write_bytes(bytes(bad))
+        with pytest.raises(CogapsError) as err:
+            cg.gaps_run(data, checkpointInFile=path, checkpointOutFile=tmp_path / "unused.out", **kw)
+        assert err.value.code == -1 and "mass" in str(err.value)
+    # the untouched file still resumes
+    cg.gaps_run(data, checkpointInFile=good, checkpointOutFile=tmp_path / "unused.out", **kw)
+
+
+@pytest.mark.gpu
+def test_set_atoms_keeps_the_generator_in_step():
+    """cgb_sampler_set_atoms used to leave the proposal queue's atom counts stale; an update right after it
+    must run (it asserts min == max == domain size on entry, ProposalQueue.cpp:59-60)."""
+    import bench
+    data = load_data("gist")
+    chain = bench.Chain(data, 4, 3)
+    for _ in range(5):
+        chain.step()
+    pos, mass = chain.A.atoms()
+    keep = pos.size // 2
+    chain.A.setAtoms(pos[:keep], mass[:keep])
+    assert chain.A.nAtoms() == keep
+    # matrix and atoms are the caller's to keep consistent: every element = the sum of the masses in its bin
+    nbins = chain.A.nRows * 4
+    binlen = np.uint64(0xFFFFFFFFFFFFFFFF // nbins)
+    b = np.minimum((pos[:keep] // binlen).astype(np.int64), nbins - 1)
+    M = np.bincount(b, weights=mass[:keep].astype(np.float64), minlength=nbins).reshape(chain.A.nRows, 4).astype(np.float32)
+    chain.A.setMatrix(M)
+    chain.P.sync(chain.A)
+    chain.A.extraInitialization()
+    for _ in range(3):
+        chain.step()
+    assert chain.A.nAtoms() > 0
