@@ -10,6 +10,7 @@ and packs parameters exactly like getGapsParameters (src/Cogaps.cpp:63-139) and 
 All computation happens in libcogaps_b200.so on the GPU.
 """
 import ctypes as C
+import copy
 import os
 import time
 
@@ -339,8 +340,10 @@ def CoGAPS(data, params=None, nPatterns=None, nThreads=1, messages=True, outputF
     R/HelperFunctions.R:165-183: unknown names are an error)."""
     if params is None:
         params = CogapsParams(nPatterns=nPatterns if nPatterns is not None else 7)
-    elif nPatterns is not None:
-        params.setParam("nPatterns", nPatterns)
+    else:
+        params = copy.copy(params)          # R passes parameters by value: the caller's object is never changed
+        if nPatterns is not None:
+            params.setParam("nPatterns", nPatterns)
     for k, v in kwargs.items():
         if k not in _PARAM_DEFAULTS:
             raise ValueError("unrecognized argument: %s" % k)
@@ -397,23 +400,27 @@ def CoGAPS(data, params=None, nPatterns=None, nThreads=1, messages=True, outputF
               asynchronousUpdates=int(bool(asynchronousUpdates)), takePumpSamples=int(bool(params.takePumpSamples)),
               printMessages=int(bool(messages) and workerID == 1), whichMatrixFixed=params.whichMatrixFixed,
               workerID=int(workerID))
+    if checkpointInFile is not None:
+        # the run continues with the archived nPatterns and nIterations (run_helper, GapsRunner.cpp:99-105); the result
+        # arrays (histories, snapshots) must be sized for them
+        info = checkpoint_info(checkpointInFile)
+        kw["nPatterns"] = int(info["nPatterns"])
+        kw["nIterations"] = int(info["nIterations"])
     if nSnapshots:
-        kw["snapshotFrequency"] = max(1, int(params.nIterations) // int(nSnapshots))  # Cogaps.cpp:95-99
+        # Cogaps.cpp:95-99: plain integer division — more snapshots asked for than iterations means none are taken
+        kw["snapshotFrequency"] = int(kw["nIterations"]) // int(nSnapshots)
         kw["snapshotPhase"] = _SNAPSHOT_PHASE[snapshotPhase]
     if params.subsetDim:
         kw["subsetGenes"] = 1 if params.subsetDim == 1 else 0                          # Cogaps.cpp:120-126
         kw["subsetIndices"] = np.asarray(params.subsetIndices, dtype=np.uint32)
     if params.fixedPatterns is not None:
         kw["fixedPatterns"] = np.asarray(params.fixedPatterns, dtype=np.float32)
-    if checkpointInFile is not None:
-        # the run continues with the archived nPatterns; the result arrays must be sized for it
-        kw["nPatterns"] = int(checkpoint_info(checkpointInFile)["nPatterns"])
     if fromFile:
-        res = gaps_run_file(data, uncertainty_path=uncertainty, snapshots=bool(nSnapshots),
+        res = gaps_run_file(data, uncertainty_path=uncertainty, snapshots=bool(kw.get("snapshotFrequency")),
                             checkpointInterval=int(checkpointInterval or 0), checkpointOutFile=checkpointOutFile,
                             checkpointInFile=checkpointInFile, **kw)
     else:
-        res = gaps_run(data, uncertainty=uncertainty, snapshots=bool(nSnapshots), checkpointInterval=int(checkpointInterval or 0),
+        res = gaps_run(data, uncertainty=uncertainty, snapshots=bool(kw.get("snapshotFrequency")), checkpointInterval=int(checkpointInterval or 0),
                        checkpointOutFile=checkpointOutFile, checkpointInFile=checkpointInFile, **kw)
     extras = dict(nBatchesA=res.nBatchesA, nBatchesP=res.nBatchesP, secondsUpdateA=res.secondsUpdateA,
                   secondsUpdateP=res.secondsUpdateP, algorithmicBytes=res.algorithmicBytes)

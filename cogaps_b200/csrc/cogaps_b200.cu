@@ -1758,7 +1758,12 @@ static int sequentialUpdate(cgb_sampler *s, uint32_t nSteps)
 static const uint32_t kSweepInitialCap = 64;
 static const size_t kSweepMaxSmem = 227u * 1024u;
 
-static uint32_t sweepThreadsForLength(uint32_t L) { return L <= 10240u ? 256u : 512u; }
+static uint32_t sweepThreadsForLength(uint32_t L)
+{
+    const int forced = envInt("COGAPS_SWEEP_THREADS", 0); // experiments: 128 / 256 / 512 (changes the reduction order)
+    if (forced == 128 || forced == 256 || forced == 512) { return static_cast<uint32_t>(forced); }
+    return L <= 10240u ? 256u : 512u;
+}
 static const int kSweepKeep = 10; // float4 per thread and column kept in registers between scan and commit (512-thread rows up to 20480 floats)
 
 static int cgb_sweep_reduction_order_for_length_body(uint32_t rowLength, cgb_reduction_order *out)
@@ -2039,7 +2044,11 @@ static int sweepUpdate(cgb_sampler *s, uint32_t nSteps)
     CGB_CUDA(cudaMemsetAsync(s->dSwCounters, 0, sizeof(SweepCounters), s->stream));
     CGB_CUDA(cudaEventRecord(s->evStart, s->stream));
     const uint32_t T = sweepThreadsForLength(s->L);
-    if (T == 256u)
+    if (T == 128u)
+    {
+        if (s->hasS) { CGB_TRY((sweepLaunchRows<128, true>(s, args, smem, rowSmem))); } else { CGB_TRY((sweepLaunchRows<128, false>(s, args, smem, rowSmem))); }
+    }
+    else if (T == 256u)
     {
         if (s->hasS) { CGB_TRY((sweepLaunchRows<256, true>(s, args, smem, rowSmem))); } else { CGB_TRY((sweepLaunchRows<256, false>(s, args, smem, rowSmem))); }
     }
@@ -2051,7 +2060,11 @@ static int sweepUpdate(cgb_sampler *s, uint32_t nSteps)
     if (envInt("COGAPS_SWEEP_TRANSPORT", 1) != 0)
     {
         // transport between adjacent rows (see sweep.cuh)
-        if (T == 256u)
+        if (T == 128u)
+        {
+            if (s->hasS) { CGB_TRY((sweepLaunchTransport<128, true>(s, args))); } else { CGB_TRY((sweepLaunchTransport<128, false>(s, args))); }
+        }
+        else if (T == 256u)
         {
             if (s->hasS) { CGB_TRY((sweepLaunchTransport<256, true>(s, args))); } else { CGB_TRY((sweepLaunchTransport<256, false>(s, args))); }
         }
@@ -3455,7 +3468,8 @@ static int runCore(const float *data, const CsrPair *csr, uint32_t nrow, uint32_
                         if (r->snapshotsA) { CGB_TRY(cgb_sampler_get_matrix(g.A, r->snapshotsA + static_cast<size_t>(slot) * nGenes * p->nPatterns)); }
                         if (r->snapshotsP) { CGB_TRY(cgb_sampler_get_matrix(g.P, r->snapshotsP + static_cast<size_t>(slot) * nSamples * p->nPatterns)); }
                     }
-                    if (phase == CGB_PHASE_EQUILIBRATION) { ++nSnapEq; } else { ++nSnapSamp; }
+                    // only snapshots that were stored are counted: the caller splits its arrays by these numbers
+                    if (slot < r->snapshotCapacity) { if (phase == CGB_PHASE_EQUILIBRATION) { ++nSnapEq; } else { ++nSnapSamp; } }
                 }
             }
             // displayStatus, GapsRunner.cpp:161-199
@@ -3890,7 +3904,17 @@ static int cgb_run_file_ex_body(const char *dataPath, const char *uncertaintyPat
     // (SparseMatrix(path, ...), data_structures/SparseMatrix.cpp:52-107, never forms a dense matrix either); the dense
     // copy the chi-square kernels read is rebuilt on the device.  COGAPS_MTX_DENSE=1 forces the dense route (tests).
     const bool uncGiven = uncertaintyPath != nullptr && uncertaintyPath[0] != 0; // then the dense route validates it as before
-    if (p->useSparseOptimization && p->nSubsetIndices == 0 && !uncGiven && endsWith(dataPath, ".mtx") && envInt("COGAPS_MTX_DENSE", 0) == 0)
+    // a resumed run takes useSparseOptimization from the checkpoint (run_helper, GapsRunner.cpp:99-105): that flag, not
+    // the caller's, picks the route
+    bool sparseModel = p->useSparseOptimization != 0;
+    if (opt && opt->checkpointInFile && opt->checkpointInFile[0])
+    {
+        ParamsImage pi;
+        uint64_t seederState[2];
+        std::string herr;
+        if (readCheckpointHeader(opt->checkpointInFile, pi, seederState, herr)) { sparseModel = pi.useSparseOptimization != 0; }
+    }
+    if (sparseModel && p->nSubsetIndices == 0 && !uncGiven && endsWith(dataPath, ".mtx") && envInt("COGAPS_MTX_DENSE", 0) == 0)
     {
         CsrPair pair;
         if (loadMtxCsrPair(dataPath, pair, nrow, ncol, err))

@@ -20,6 +20,7 @@
 #include <cstring>
 #include <fstream>
 #include <sstream>
+#include <limits>
 #include <string>
 #include <utility>
 #include <vector>
@@ -53,7 +54,12 @@ static float streamFloat(const std::string &s)
     if (res.ec == std::errc::invalid_argument) { return 0.f; }
     char *end = nullptr;
     const float v = std::strtof(s.c_str(), &end);
-    return (end == s.c_str()) ? 0.f : v;
+    if (end == s.c_str()) { return 0.f; }
+    // out of range: the stream extractor stores +/-FLT_MAX for an overflow (num_get, LWG 23) where strtof returns
+    // +/-inf; an underflow keeps strtof's (denormal or zero) value
+    if (v > std::numeric_limits<float>::max()) { return std::numeric_limits<float>::max(); }
+    if (v < -std::numeric_limits<float>::max()) { return -std::numeric_limits<float>::max(); }
+    return v;
 }
 
 static bool parseValue(const std::string &s, float &out, std::string &err)
@@ -118,6 +124,11 @@ static bool readMtx(std::ifstream &f, std::vector<float> &out, uint32_t &nrow, u
     if (r == 0 || c == 0)
     {
         err = "Invalid MTX file";
+        return false;
+    }
+    if (r > 0xFFFFFFFFul || c > 0xFFFFFFFFul)
+    {
+        err = "MTX dimensions exceed 32 bits";
         return false;
     }
     nrow = static_cast<uint32_t>(r);
@@ -225,6 +236,11 @@ bool loadMtxTriplets(const char *path, std::vector<uint32_t> &rows, std::vector<
         err = "Invalid MTX file";
         return false;
     }
+    if (r > 0xFFFFFFFFul || c > 0xFFFFFFFFul)
+    {
+        err = "MTX dimensions exceed 32 bits";
+        return false;
+    }
     nrow = static_cast<uint32_t>(r);
     ncol = static_cast<uint32_t>(c);
     rows.clear(); cols.clear(); vals.clear();
@@ -241,6 +257,11 @@ bool loadMtxTriplets(const char *path, std::vector<uint32_t> &rows, std::vector<
         if (row < 1 || row > nrow || col < 1 || col > ncol)
         {
             err = "MTX entry outside the declared dimensions";
+            return false;
+        }
+        if (vals.size() >= 0xFFFFFFFFul)
+        {
+            err = "MTX file holds more than 2^32 - 1 entries";   // the compressed rows index them with 32 bits
             return false;
         }
         rows.push_back(static_cast<uint32_t>(row - 1));

@@ -203,12 +203,13 @@ struct PreLog
 // divisions) do not inflate the allocation of the 255 lanes that only scan.
 // SPARSE: M1/M2 are the row-copy values, C1/C2 the column-copy values of the two elements; both copies are
 // rewritten with HybridMatrix::add / set semantics (data_structures/HybridMatrix.cpp:25-39).
-template <bool SPARSE>
-__device__ __noinline__ void decide(const ModelView &mv, const float *erfT, const float *erfinvT, float T, const DevProposal &pr, uint32_t part, bool twoRow,
-                                    float s, float mu, float M1, float M2, float C1, float C2, int can1, int can2, const PreLog &pre, Verdict *v)
+// LEAN (the sweep, which inlines it): asynchronous sampler's proposals only, no probes, no count of the draws taken.
+template <bool SPARSE, bool LEAN>
+__device__ __forceinline__ void decide_body(const ModelView &mv, const float *erfT, const float *erfinvT, float T, const DevProposal &pr, uint32_t part, bool twoRow,
+                                            float s, float mu, float M1, float M2, float C1, float C2, int can1, int can2, const PreLog &pre, Verdict *v)
 {
     bool add1 = false, add2 = false; // element changed by changeMatrix (add) rather than safelyChangeMatrix (set)
-    const bool sequential = (pr.pad & 1u) != 0u; // proposal of the SingleThreadedGibbsSampler (one shared stream)
+    const bool sequential = !LEAN && (pr.pad & 1u) != 0u; // proposal of the SingleThreadedGibbsSampler (one shared stream)
     const uint32_t type = pr.type;
     const uint32_t r1 = pr.r1, c1 = pr.c1, r2 = pr.r2, c2 = pr.c2;
     const float m1 = pr.m1, m2 = pr.m2;
@@ -228,7 +229,7 @@ __device__ __noinline__ void decide(const ModelView &mv, const float *erfT, cons
     rng.state = pr.rng;
     float d1 = 0.f, d2 = 0.f;   // deltas of element (r1,c1) and (r2,c2)
     bool ch1 = false, ch2 = false;
-    if (type == kProbe)
+    if (!LEAN && type == kProbe)
     {
         out.s = s;
         out.s_mu = mu;
@@ -368,6 +369,7 @@ __device__ __noinline__ void decide(const ModelView &mv, const float *erfT, cons
         dec.flags = (ch1 ? 1u : 0u) | (ch2 ? 2u : 0u);
     }
     // the sequential sampler continues ITS stream after us: tell it how many draws we made (0, 1 or 2)
+    if (!LEAN)
     {
         Pcg probe;
         probe.state = pr.rng;
@@ -383,6 +385,13 @@ __device__ __noinline__ void decide(const ModelView &mv, const float *erfT, cons
     v->out = out;
     v->newM1 = M1;
     v->newM2 = M2;
+}
+
+template <bool SPARSE>
+__device__ __noinline__ void decide(const ModelView &mv, const float *erfT, const float *erfinvT, float T, const DevProposal &pr, uint32_t part, bool twoRow,
+                                    float s, float mu, float M1, float M2, float C1, float C2, int can1, int can2, const PreLog &pre, Verdict *v)
+{
+    decide_body<SPARSE, false>(mv, erfT, erfinvT, T, pr, part, twoRow, s, mu, M1, M2, C1, C2, can1, can2, pre, v);
 }
 
 __device__ __forceinline__ unsigned int ld_acquire_gpu_u32(const unsigned int *p)

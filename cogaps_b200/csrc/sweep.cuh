@@ -404,7 +404,7 @@ __device__ __forceinline__ bool sweep_decide(const ModelView &mv, SweepCtl *ctl,
     pre.logFirst = ctl->log0;
     pre.logSecond = ctl->log1;
     Verdict v;
-    decide<false>(mv, mv.erf, mv.erfinv, mv.annealingTemp, pr, 0u, false, s, mu, M1, M2, 0.f, 0.f, can1, can2, pre, &v);
+    decide_body<false, true>(mv, mv.erf, mv.erfinv, mv.annealingTemp, pr, 0u, false, s, mu, M1, M2, 0.f, 0.f, can1, can2, pre, &v);
     if (v.dec.flags & 1u) { M1 = v.newM1; }
     if (v.dec.flags & 2u) { M2 = v.newM2; }
     ctl->d1 = v.dec.dOwn1;
@@ -415,7 +415,7 @@ __device__ __forceinline__ bool sweep_decide(const ModelView &mv, SweepCtl *ctl,
 }
 
 template <int T, int NV, bool HAS_S, bool ROW_SMEM>
-__global__ void __launch_bounds__(T, (T <= 256 ? 4 : 1)) sweep_kernel(const __grid_constant__ SweepArgs a)
+__global__ void __launch_bounds__(T, (T <= 128 ? 5 : (T <= 256 ? 4 : 1))) sweep_kernel(const __grid_constant__ SweepArgs a)
 {
     extern __shared__ __align__(128) unsigned char smemRaw[];
     const ModelView &mv = a.mv;

@@ -370,3 +370,23 @@ def test_triplet_scanner_agrees_with_the_dense_reader_on_random_files(tmp_path):
             wptr, widx, wval = _csr_of(want)
             assert (r, c) == dense.shape
             assert np.array_equal(ptr, wptr) and np.array_equal(idx, widx) and np.array_equal(bits(val), bits(wval)), trial
+
+
+def test_overflowing_token_saturates_like_the_stream_extractor(tmp_path):
+    """a numeric token too large for a float is +/-FLT_MAX through `stringstream >> float` (what the reference's
+    parser uses), not +/-inf as strtof returns — an inf would turn D, lambda and chi-square into NaN."""
+    import cogaps_b200 as cg
+    path = tmp_path / "big.csv"
+    path.write_text(',a,b\nr1,1' + '0' * 45 + ',2\nr2,-9' + '9' * 50 + ',0.5\n')
+    m = cg.read_matrix_file(path)
+    fmax = np.finfo(np.float32).max
+    assert m.shape == (2, 2) and m[0, 0] == fmax and m[1, 0] == -fmax and m[0, 1] == 2 and m[1, 1] == 0.5
+
+
+def test_mtx_dimensions_beyond_32_bits_are_refused(tmp_path):
+    import cogaps_b200 as cg
+    from cogaps_b200 import CogapsError
+    path = tmp_path / "huge.mtx"
+    path.write_text("%%MatrixMarket matrix coordinate real general\n5000000000 3 1\n1 1 2.0\n")
+    with pytest.raises(CogapsError):
+        cg.read_matrix_file(path)
