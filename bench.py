@@ -331,7 +331,7 @@ def main():
                 "launches": int(cg.lib().cgb_kernel_launch_count() - launches0), "steps": steps}
 
     dense = not args.sparse
-    mode = args.mode if dense else "exact"
+    mode = args.mode
     config["update_mode"] = ("sweep: row-parallel (one CTA per factor row, whole update() in one launch, Philox draws, transport "
                              "between adjacent rows); a different chain from the reference's for the same seed — validated "
                              "statistically against it and bit for bit against oracle/; the reference's own chain is measured "
@@ -341,17 +341,17 @@ def main():
     clocks = ClockSampler(local_rank)
     t_setup = time.time()
     # the chain grows to its steady state in sweep mode (seconds instead of minutes), untimed
-    chain = Chain(data, args.patterns, CHAIN_SEED + rank, sparse=args.sparse, updateMode=1 if dense else 0)
-    chain.ramp(args.ramp if dense else min(args.ramp, 50))
+    chain = Chain(data, args.patterns, CHAIN_SEED + rank, sparse=args.sparse, updateMode=1)
+    chain.ramp(args.ramp)
     for _ in range(args.warmup):
         chain.step()
     setup_s = time.time() - t_setup
     peak, peak_src = load_peaks()
     L_A, L_P = args.cols, args.rows
 
-    # ---- timed region 1 (dense model): exactly K steps of the sweep ----
+    # ---- timed region 1: exactly K steps of the sweep ----
     sweep = None
-    if dense:
+    if True:
         r = timed_steps(chain, args.steps, clocks if mode == "sweep" else None)
         el, (made, launches) = reduce_max_sum(r["elapsed"], [r["made"], r["launches"]])
         cA, cP = r["cA"], r["cP"]
@@ -362,7 +362,7 @@ def main():
                  "atoms": {"A": int(chain.A.nAtoms()), "P": int(chain.P.nAtoms())},
                  "host_ms_per_step": r["host"] / args.steps * 1e3,
                  "kernel_ms_per_step": {"A": cA.secondsKernel / args.steps * 1e3, "P": cP.secondsKernel / args.steps * 1e3},
-                 "roofline": {"bound": "hbm", "kernel": "sweep_kernel + sweep_transport_kernel (one update() = one launch of each)",
+                 "roofline": {"bound": "hbm", "kernel": ("sweep_kernel" if dense else "sweep_sparse_kernel") + " + sweep_transport_kernel (one update() = one launch of each)",
                               "achieved": kbytes / max(ktime, 1e-12) / 1e9, "peak": peak, "unit": "GB/s",
                               "frac": kbytes / max(ktime, 1e-12) / 1e9 / peak, "peak_source": peak_src,
                               "algorithmic_bytes_per_launch": kbytes / (2.0 * args.steps),
@@ -379,19 +379,19 @@ def main():
                                      "decision of each proposal, not by HBM"}}
         # what the sweep really moves per update(): every active row's D and AP lines once in, dirty AP lines once out
         lines_in = 2.0
-        sweep["roofline"]["traffic_estimate"] = {
+        if dense:
+          sweep["roofline"]["traffic_estimate"] = {
             "bytes_per_launch": (args.rows * L_A + args.cols * L_P) * 4.0 * (lines_in + 1.0) / 2.0,
             "how": "upper bound: (D + AP read, AP written) x every row of both samplers, per update() launch; measured per "
                    "launch by ncu in profiles/r2_sweep_kernel_ncu.csv"}
-        sweep["roofline"]["dram_frac_estimate"] = sweep["roofline"]["traffic_estimate"]["bytes_per_launch"] / \
+          sweep["roofline"]["dram_frac_estimate"] = sweep["roofline"]["traffic_estimate"]["bytes_per_launch"] / \
             max(ktime / (2.0 * args.steps), 1e-12) / 1e9 / peak
 
     # ---- timed region 2: the reference's own chain (exact mode) from the same state ----
-    if dense:
-        chain.A.setUpdateMode(0)
-        chain.P.setUpdateMode(0)
-        for _ in range(args.warmup):
-            chain.step()
+    chain.A.setUpdateMode(0)
+    chain.P.setUpdateMode(0)
+    for _ in range(args.warmup):
+        chain.step()
     exact_steps = args.steps if (mode == "exact") else min(args.steps, args.exact_steps)
     r = timed_steps(chain, exact_steps, clocks if mode == "exact" else None)
     el, (made, launches) = reduce_max_sum(r["elapsed"], [r["asked"], r["launches"]])
@@ -581,8 +581,7 @@ def main():
                 "sampler_loop_s": loop_s, "sampler_loop_value": upd / max(loop_s, 1e-9)}
 
     if rank == 0 and not args.no_e2e:
-        if dense:
-            sweep["e2e"] = e2e_of(1, 3)
+        sweep["e2e"] = e2e_of(1, 3)
         exact["e2e"] = e2e_of(0, 3)
 
     # ---- BASELINE.json configs[4] on N > 1 GPUs: every rank runs its 200000/N x 30000 k=50 sparse shard, then the NCCL
@@ -607,8 +606,7 @@ def main():
                 "chisq_ms": chisq_ms, "whole_matrix_passes": timings,
                 "timer": "CUDA events around the K timed steps (device clock), max over ranks; host perf_counter over the "
                          "same region: %.3f ms per step" % head["host_ms_per_step"]}
-        if dense:
-            line["sweep_mode"] = sweep
+        line["sweep_mode"] = sweep
         line["exact_mode"] = exact
         # kept at top level for continuity with round 1 (exact mode)
         line["host_generate_s_per_step"] = exact["host_generate_s_per_step"]

@@ -1943,7 +1943,6 @@ static int cgb_sampler_set_update_mode_body(cgb_sampler *s, int32_t mode)
     CGB_CUDA(cudaSetDevice(s->device));
     if (mode == CGB_UPDATE_SWEEP)
     {
-        if (s->sparse) { return fail(CGB_EUNSUPPORTED, "cgb_sampler_set_update_mode: the sweep is built for the dense model; the sparse model runs the exact path"); }
         CGB_TRY(sweepFromDomain(s));
     }
     else
@@ -1996,7 +1995,9 @@ static int sweepLaunchRows(cgb_sampler *s, const SweepArgs &args, size_t smem, b
     return sweepLaunchInstance<T, 0, HAS_S, true>(s, args, smem);
 }
 
-template <int T, bool HAS_S>
+static size_t sweepSparseScanBytes() { return static_cast<size_t>(4) * kSparseThreads * kSparseGroup * sizeof(float); }
+
+template <int T, bool HAS_S, bool SPARSE = false>
 static int sweepLaunchTransport(cgb_sampler *s, SweepArgs &args)
 {
     // pairs (r, r+1) with even r on even-numbered updates of this sampler, odd r on odd-numbered ones
@@ -2005,7 +2006,8 @@ static int sweepLaunchTransport(cgb_sampler *s, SweepArgs &args)
     if (s->nRows >= 2u && pairs > 0u)
     {
         args.colour = colour;
-        sweep_transport_kernel<T, HAS_S><<<pairs, T, 0, s->stream>>>(args);
+        const size_t dyn = SPARSE ? ((static_cast<size_t>(s->ldR) * sizeof(float) + 127u) & ~static_cast<size_t>(127u)) + sweepSparseScanBytes() : 0u;
+        sweep_transport_kernel<T, HAS_S, SPARSE><<<pairs, T, dyn, s->stream>>>(args);
         g_kernelLaunches.fetch_add(1);
         CGB_CUDA(cudaGetLastError());
     }
@@ -2036,15 +2038,21 @@ static int sweepUpdate(cgb_sampler *s, uint32_t nSteps)
     args.perAtom = w.perAtom;
     args.cap = s->swCap;
     args.nSteps = nSteps;
-    const size_t base = sweepRowOffset(s->swCap, s->k);
+    const size_t base = s->sparse ? sweepSparseScanOffset(s->swCap, s->k, s->ldR) + sweepSparseScanBytes() : sweepRowOffset(s->swCap, s->k);
     const size_t staged = base + static_cast<size_t>(s->hasS ? 3 : 2) * s->ld * sizeof(float);
-    const bool rowSmem = staged <= kSweepMaxSmem && envInt("COGAPS_SWEEP_ROW_SMEM", 1) != 0;
+    const bool rowSmem = !s->sparse && staged <= kSweepMaxSmem && envInt("COGAPS_SWEEP_ROW_SMEM", 1) != 0;
     const size_t smem = rowSmem ? staged : base;
     CGB_CHECK(smem <= kSweepMaxSmem, "sweep: a row's atom store no longer fits in shared memory");
     CGB_CUDA(cudaMemsetAsync(s->dSwCounters, 0, sizeof(SweepCounters), s->stream));
     CGB_CUDA(cudaEventRecord(s->evStart, s->stream));
-    const uint32_t T = sweepThreadsForLength(s->L);
-    if (T == 128u)
+    const uint32_t T = s->sparse ? static_cast<uint32_t>(kSparseThreads) : sweepThreadsForLength(s->L);
+    if (s->sparse)
+    {
+        CGB_TRY(sweepGrowSmemLimit(sweep_sparse_kernel, smem));
+        sweep_sparse_kernel<<<s->nRows, kSparseThreads, smem, s->stream>>>(args);
+        g_kernelLaunches.fetch_add(1);
+    }
+    else if (T == 128u)
     {
         if (s->hasS) { CGB_TRY((sweepLaunchRows<128, true>(s, args, smem, rowSmem))); } else { CGB_TRY((sweepLaunchRows<128, false>(s, args, smem, rowSmem))); }
     }
@@ -2060,7 +2068,8 @@ static int sweepUpdate(cgb_sampler *s, uint32_t nSteps)
     if (envInt("COGAPS_SWEEP_TRANSPORT", 1) != 0)
     {
         // transport between adjacent rows (see sweep.cuh)
-        if (T == 128u)
+        if (s->sparse) { CGB_TRY((sweepLaunchTransport<kSparseThreads, false, true>(s, args))); }
+        else if (T == 128u)
         {
             if (s->hasS) { CGB_TRY((sweepLaunchTransport<128, true>(s, args))); } else { CGB_TRY((sweepLaunchTransport<128, false>(s, args))); }
         }
@@ -2089,7 +2098,18 @@ static int sweepUpdate(cgb_sampler *s, uint32_t nSteps)
     s->counters.nBatches += 1;
     s->counters.nProposalsQueued += c.scans1 + c.scans2 + c.scansX;
     s->counters.nProposalsTotal += c.steps;
-    s->counters.algorithmicBytes += static_cast<double>(s->L) * (16.0 * static_cast<double>(c.scans1) + 20.0 * static_cast<double>(c.scans2) + 32.0 * static_cast<double>(c.scansX) + 4.0 * static_cast<double>(c.commits));
+    if (s->sparse)
+    {
+        // SURVEY 8(d), sparse: 2 flag words streams per single-column scan (3 for a same-row pair, 4 for a two-row one) of
+        // ceil(L / 64) * 8 bytes, plus 8 + 4k bytes per common non-zero
+        const double flagBytes = static_cast<double>((s->L + 63u) / 64u) * 8.0;
+        s->counters.algorithmicBytes += flagBytes * (2.0 * static_cast<double>(c.scans1) + 3.0 * static_cast<double>(c.scans2) + 4.0 * static_cast<double>(c.scansX))
+            + static_cast<double>(c.visited) * (8.0 + 4.0 * s->k);
+    }
+    else
+    {
+        s->counters.algorithmicBytes += static_cast<double>(s->L) * (16.0 * static_cast<double>(c.scans1) + 20.0 * static_cast<double>(c.scans2) + 32.0 * static_cast<double>(c.scansX) + 4.0 * static_cast<double>(c.commits));
+    }
     s->swTotalAtoms = static_cast<uint64_t>(static_cast<long long>(s->swTotalAtoms) + c.atomDelta);
     s->swOverflow += c.overflow;
     const uint32_t cap = sweepCapFor(s->swCap, c.maxCount);
@@ -3371,7 +3391,6 @@ static int runCore(const float *data, const CsrPair *csr, uint32_t nrow, uint32_
         if (fixed == 'P') { CGB_TRY(cgb_sampler_set_matrix(g.P, p->fixedPatterns)); }
     }
     CGB_CHECK(p->updateMode == CGB_UPDATE_EXACT || p->updateMode == CGB_UPDATE_SWEEP, "cgb_run: unknown updateMode");
-    CGB_CHECK(p->updateMode == CGB_UPDATE_EXACT || !p->useSparseOptimization, "cgb_run: the sweep is built for the dense model (useSparseOptimization runs the exact path)");
     CGB_TRY(cgb_stats_create(nGenes, nSamples, p->nPatterns, &g.st));
     CGB_TRY(cgb_rng_create(g.rs, &g.rng)); // GapsRunner.cpp:437
     int startPhase = CGB_PHASE_EQUILIBRATION;

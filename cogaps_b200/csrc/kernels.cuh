@@ -178,7 +178,8 @@ struct Verdict
 {
     Decision dec;
     DevOutcome out;
-    float newM1, newM2; // the factor elements (r1,c1) / (r2,c2) after the proposal (dense model)
+    float newM1, newM2; // the factor elements (r1,c1) / (r2,c2) after the proposal (sparse model: the row copy)
+    float newC1, newC2; // sparse model: the column copy (values below epsilon stored as 0)
 };
 
 // The accept tests take log(uniform()) of the proposal's own PCG stream, as its first draw (move, death
@@ -337,13 +338,15 @@ __device__ __forceinline__ void decide_body(const ModelView &mv, const float *er
         {
             mv.Mrows[static_cast<size_t>(r1) * mv.ldR + c1] = M1;
             const float cv = add1 ? fadd(C1, d1) : M1;
-            mv.M[static_cast<size_t>(c1) * mv.ldM + r1] = (cv < kEpsilon) ? 0.f : cv;
+            C1 = (cv < kEpsilon) ? 0.f : cv;
+            mv.M[static_cast<size_t>(c1) * mv.ldM + r1] = C1;
         }
         if (ch2)
         {
             mv.Mrows[static_cast<size_t>(r2) * mv.ldR + c2] = M2;
             const float cv = add2 ? fadd(C2, d2) : M2;
-            mv.M[static_cast<size_t>(c2) * mv.ldM + r2] = (cv < kEpsilon) ? 0.f : cv;
+            C2 = (cv < kEpsilon) ? 0.f : cv;
+            mv.M[static_cast<size_t>(c2) * mv.ldM + r2] = C2;
         }
     }
     else
@@ -385,6 +388,8 @@ __device__ __forceinline__ void decide_body(const ModelView &mv, const float *er
     v->out = out;
     v->newM1 = M1;
     v->newM2 = M2;
+    v->newC1 = C1;
+    v->newC2 = C2;
 }
 
 template <bool SPARSE>
@@ -738,6 +743,157 @@ __device__ __forceinline__ float row_dot(const float *a, const float *b, uint32_
     return acc;
 }
 
+// The Z-table terms of one sparse scan (SparseNormalModel.cpp:153-292): s = Z1[c] (or Z1[c1] - 2 Z2[c2][c1] + Z1[c2]);
+// s_mu = -(A[row,:] . Z2[:,c]) ...  One lane computes them while the others gather.
+__device__ __forceinline__ void sparse_table_terms(const ModelView &mv, const float *sRow, uint32_t colA, uint32_t c1, uint32_t c2,
+                                                   bool useV2, bool withChange, float ch, float &bsOut, float &bmuOut)
+{
+    const uint32_t k = mv.k;
+    float bs, bmu;
+    if (useV2)
+    {
+        bs = fadd(fsub(mv.Z1[c1], fmul(2.f, mv.Z2[static_cast<size_t>(c2) * k + c1])), mv.Z1[c2]);
+        const float *za = mv.Z2 + static_cast<size_t>(c1) * k, *zb = mv.Z2 + static_cast<size_t>(c2) * k;
+        float acc = 0.f;
+        for (uint32_t i = 0; i < k; ++i) { acc = fadd(acc, fmul(sRow[i], fsub(za[i], zb[i]))); } // gaps::dot_diff
+        bmu = fmul(-1.f, acc);
+    }
+    else
+    {
+        bs = mv.Z1[colA];
+        bmu = fmul(-1.f, row_dot(sRow, mv.Z2 + static_cast<size_t>(colA) * k, k));
+        if (withChange) { bmu = fsub(bmu, fmul(ch, mv.Z2[static_cast<size_t>(colA) * k + colA])); }
+    }
+    bsOut = bs;
+    bmuOut = bmu;
+}
+
+// The scan over one data row's non-zeros (the whole CTA of kSparseThreads; contains __syncthreads): per-lane partial
+// sums in accS / accMu, elements visited in `visited` (same on every thread).  warpCnt: kSparseGroup * 8 counters.
+__device__ __forceinline__ void sparse_scan_row(const ModelView &mv, uint32_t *warpCnt, const float *sRow, uint32_t *sIdx, float *sD,
+                                                float *sV1, float *sV2, uint32_t row, uint32_t colA, uint32_t c2, bool useV2,
+                                                bool withChange, float ch, float &accS, float &accMu, uint32_t &visited)
+{
+    const uint32_t tid = threadIdx.x, lane = tid & 31u, warp = tid >> 5;
+    const uint32_t k = mv.k;
+    // ---- the scan over the row's non-zeros, kSparseGroup x 256 at a time: compact the common ones, deal them
+    // out to the lanes.  Every load of a group is issued before any is consumed (index/value, then the factor
+    // column gather, then the factor row gathers), so a row of <= 1024 non-zeros pays each dependent latency once.
+    const uint32_t start = mv.spRowPtr[row], nnz = mv.spRowPtr[row + 1] - start;
+    const float *V1 = mv.otherM + static_cast<size_t>(colA) * mv.ldOther;
+    const float *V2 = mv.otherM + static_cast<size_t>(c2) * mv.ldOther;
+    accS = 0.f;
+    accMu = 0.f;
+    visited = 0; // elements visited so far (same on every thread)
+    for (uint32_t base = 0; base < nnz; base += kSparseThreads * kSparseGroup)
+    {
+        uint32_t l[kSparseGroup], ballot[kSparseGroup];
+        float d[kSparseGroup], v1[kSparseGroup], v2[kSparseGroup];
+        bool pred[kSparseGroup];
+#pragma unroll
+        for (int g = 0; g < kSparseGroup; ++g)
+        {
+            // sub-group g holds elements base + g * 256 + tid: ascending index is (g, tid) order
+            const uint32_t j = base + g * kSparseThreads + tid;
+            l[g] = 0u;
+            d[g] = 0.f;
+            if (j < nnz)
+            {
+                l[g] = mv.spIdx[start + j];
+                d[g] = mv.spVal[start + j];
+            }
+        }
+#pragma unroll
+        for (int g = 0; g < kSparseGroup; ++g)
+        {
+            const uint32_t j = base + g * kSparseThreads + tid;
+            v1[g] = 0.f;
+            v2[g] = 0.f;
+            if (j < nnz)
+            {
+                v1[g] = V1[l[g]];
+                if (useV2) { v2[g] = V2[l[g]]; }
+            }
+        }
+#pragma unroll
+        for (int g = 0; g < kSparseGroup; ++g)
+        {
+            const uint32_t j = base + g * kSparseThreads + tid;
+            pred[g] = (j < nnz) && (useV2 ? (v1[g] != 0.f || v2[g] != 0.f) : (v1[g] != 0.f));
+            ballot[g] = __ballot_sync(0xffffffffu, pred[g]);
+            if (lane == 0) { warpCnt[g * (kSparseThreads / 32) + warp] = __popc(ballot[g]); }
+        }
+        __syncthreads();
+        uint32_t before[kSparseGroup], total = 0;
+#pragma unroll
+        for (int g = 0; g < kSparseGroup; ++g)
+        {
+            before[g] = total;
+#pragma unroll
+            for (uint32_t w = 0; w < kSparseThreads / 32; ++w)
+            {
+                const uint32_t c = warpCnt[g * (kSparseThreads / 32) + w];
+                before[g] += (w < warp) ? c : 0u;
+                total += c;
+            }
+        }
+#pragma unroll
+        for (int g = 0; g < kSparseGroup; ++g)
+        {
+            if (pred[g])
+            {
+                const uint32_t p = before[g] + __popc(ballot[g] & ((1u << lane) - 1u));
+                sIdx[p] = l[g];
+                sD[p] = d[g];
+                sV1[p] = v1[g];
+                sV2[p] = v2[g];
+            }
+        }
+        __syncthreads();
+        // element e = visited + i goes to lane e % 256: a lane takes its elements in increasing e
+        const uint32_t first = (tid + kSparseThreads - (visited % kSparseThreads)) % kSparseThreads;
+#pragma unroll
+        for (int m = 0; m < kSparseGroup; ++m)
+        {
+            const uint32_t i = first + m * kSparseThreads;
+            if (i < total)
+            {
+                const uint32_t el = sIdx[i];
+                const float ed = sD[i], ev1 = sV1[i];
+                const float *orow = mv.otherMrows + static_cast<size_t>(el) * mv.ldR;
+                float dotv = 0.f;
+                // ascending k, mul and add rounded separately; 16-byte gathers of the other factor's row
+                for (uint32_t q = 0; q < k; q += 4)
+                {
+                    const float4 o4 = *reinterpret_cast<const float4*>(orow + q);
+                    dotv = fadd(dotv, fmul(sRow[q], o4.x));
+                    if (q + 1 < k) { dotv = fadd(dotv, fmul(sRow[q + 1], o4.y)); }
+                    if (q + 2 < k) { dotv = fadd(dotv, fmul(sRow[q + 2], o4.z)); }
+                    if (q + 3 < k) { dotv = fadd(dotv, fmul(sRow[q + 3], o4.w)); }
+                }
+                if (useV2)
+                {
+                    const float dRecip = fdiv(1.f, ed);
+                    const float term1 = fsub(1.f, fmul(dRecip, dRecip));
+                    const float vDiff = fsub(ev1, sV2[i]);
+                    accS = fadd(accS, fmul(fmul(vDiff, vDiff), term1));
+                    accMu = fadd(accMu, fmul(vDiff, fadd(fmul(dotv, term1), dRecip)));
+                }
+                else
+                {
+                    const float term1 = fdiv(ev1, ed);
+                    const float term2 = fsub(ev1, fdiv(term1, ed));
+                    accS = fadd(accS, fsub(fmul(term1, term1), fmul(ev1, ev1)));
+                    accMu = fadd(accMu, fadd(term1, fmul(term2, dotv)));
+                    if (withChange) { accMu = fadd(accMu, fmul(fmul(term2, orow[colA]), ch)); }
+                }
+            }
+        }
+        visited += total;
+        __syncthreads(); // the compaction buffers are rewritten by the next group
+    }
+}
+
 // smemRaw: [SparseSmem | pad to 256 B][sRow: ldR floats][sIdx][sD][sV1][sV2], 256 * kSparseGroup entries each
 template <bool STREAM>
 __device__ __forceinline__ bool sparse_task(const ModelView &mv, const float *erfT, const float *erfinvT, float annealingTemp, const TaskIn &in,
@@ -799,141 +955,15 @@ __device__ __forceinline__ bool sparse_task(const ModelView &mv, const float *er
     __syncthreads();
     if (tid == 64)
     {
-        // the table terms: s = Z1[c] (or Z1[c1] - 2 Z2[c2][c1] + Z1[c2]); s_mu = -(A[row,:] . Z2[:,c]) ...
         float bs, bmu;
-        if (useV2)
-        {
-            bs = fadd(fsub(mv.Z1[c1], fmul(2.f, mv.Z2[static_cast<size_t>(c2) * k + c1])), mv.Z1[c2]);
-            const float *za = mv.Z2 + static_cast<size_t>(c1) * k, *zb = mv.Z2 + static_cast<size_t>(c2) * k;
-            float acc = 0.f;
-            for (uint32_t i = 0; i < k; ++i) { acc = fadd(acc, fmul(sRow[i], fsub(za[i], zb[i]))); } // gaps::dot_diff
-            bmu = fmul(-1.f, acc);
-        }
-        else
-        {
-            bs = mv.Z1[colA];
-            bmu = fmul(-1.f, row_dot(sRow, mv.Z2 + static_cast<size_t>(colA) * k, k));
-            if (withChange) { bmu = fsub(bmu, fmul(ch, mv.Z2[static_cast<size_t>(colA) * k + colA])); }
-        }
+        sparse_table_terms(mv, sRow, colA, c1, c2, useV2, withChange, ch, bs, bmu);
         hdr->baseS = bs;
         hdr->baseMu = bmu;
     }
 
-    // ---- the scan over the row's non-zeros, kSparseGroup x 256 at a time: compact the common ones, deal them
-    // out to the lanes.  Every load of a group is issued before any is consumed (index/value, then the factor
-    // column gather, then the factor row gathers), so a row of <= 1024 non-zeros pays each dependent latency once.
-    const uint32_t start = mv.spRowPtr[row], nnz = mv.spRowPtr[row + 1] - start;
-    const float *V1 = mv.otherM + static_cast<size_t>(colA) * mv.ldOther;
-    const float *V2 = mv.otherM + static_cast<size_t>(c2) * mv.ldOther;
     float accS = 0.f, accMu = 0.f;
-    uint32_t visited = 0; // elements visited so far (same on every thread)
-    for (uint32_t base = 0; base < nnz; base += kSparseThreads * kSparseGroup)
-    {
-        uint32_t l[kSparseGroup], ballot[kSparseGroup];
-        float d[kSparseGroup], v1[kSparseGroup], v2[kSparseGroup];
-        bool pred[kSparseGroup];
-#pragma unroll
-        for (int g = 0; g < kSparseGroup; ++g)
-        {
-            // sub-group g holds elements base + g * 256 + tid: ascending index is (g, tid) order
-            const uint32_t j = base + g * kSparseThreads + tid;
-            l[g] = 0u;
-            d[g] = 0.f;
-            if (j < nnz)
-            {
-                l[g] = mv.spIdx[start + j];
-                d[g] = mv.spVal[start + j];
-            }
-        }
-#pragma unroll
-        for (int g = 0; g < kSparseGroup; ++g)
-        {
-            const uint32_t j = base + g * kSparseThreads + tid;
-            v1[g] = 0.f;
-            v2[g] = 0.f;
-            if (j < nnz)
-            {
-                v1[g] = V1[l[g]];
-                if (useV2) { v2[g] = V2[l[g]]; }
-            }
-        }
-#pragma unroll
-        for (int g = 0; g < kSparseGroup; ++g)
-        {
-            const uint32_t j = base + g * kSparseThreads + tid;
-            pred[g] = (j < nnz) && (useV2 ? (v1[g] != 0.f || v2[g] != 0.f) : (v1[g] != 0.f));
-            ballot[g] = __ballot_sync(0xffffffffu, pred[g]);
-            if (lane == 0) { hdr->warpCnt[g * (kSparseThreads / 32) + warp] = __popc(ballot[g]); }
-        }
-        __syncthreads();
-        uint32_t before[kSparseGroup], total = 0;
-#pragma unroll
-        for (int g = 0; g < kSparseGroup; ++g)
-        {
-            before[g] = total;
-#pragma unroll
-            for (uint32_t w = 0; w < kSparseThreads / 32; ++w)
-            {
-                const uint32_t c = hdr->warpCnt[g * (kSparseThreads / 32) + w];
-                before[g] += (w < warp) ? c : 0u;
-                total += c;
-            }
-        }
-#pragma unroll
-        for (int g = 0; g < kSparseGroup; ++g)
-        {
-            if (pred[g])
-            {
-                const uint32_t p = before[g] + __popc(ballot[g] & ((1u << lane) - 1u));
-                sIdx[p] = l[g];
-                sD[p] = d[g];
-                sV1[p] = v1[g];
-                sV2[p] = v2[g];
-            }
-        }
-        __syncthreads();
-        // element e = visited + i goes to lane e % 256: a lane takes its elements in increasing e
-        const uint32_t first = (tid + kSparseThreads - (visited % kSparseThreads)) % kSparseThreads;
-#pragma unroll
-        for (int m = 0; m < kSparseGroup; ++m)
-        {
-            const uint32_t i = first + m * kSparseThreads;
-            if (i < total)
-            {
-                const uint32_t el = sIdx[i];
-                const float ed = sD[i], ev1 = sV1[i];
-                const float *orow = mv.otherMrows + static_cast<size_t>(el) * mv.ldR;
-                float dotv = 0.f;
-                // ascending k, mul and add rounded separately; 16-byte gathers of the other factor's row
-                for (uint32_t q = 0; q < k; q += 4)
-                {
-                    const float4 o4 = *reinterpret_cast<const float4*>(orow + q);
-                    dotv = fadd(dotv, fmul(sRow[q], o4.x));
-                    if (q + 1 < k) { dotv = fadd(dotv, fmul(sRow[q + 1], o4.y)); }
-                    if (q + 2 < k) { dotv = fadd(dotv, fmul(sRow[q + 2], o4.z)); }
-                    if (q + 3 < k) { dotv = fadd(dotv, fmul(sRow[q + 3], o4.w)); }
-                }
-                if (useV2)
-                {
-                    const float dRecip = fdiv(1.f, ed);
-                    const float term1 = fsub(1.f, fmul(dRecip, dRecip));
-                    const float vDiff = fsub(ev1, sV2[i]);
-                    accS = fadd(accS, fmul(fmul(vDiff, vDiff), term1));
-                    accMu = fadd(accMu, fmul(vDiff, fadd(fmul(dotv, term1), dRecip)));
-                }
-                else
-                {
-                    const float term1 = fdiv(ev1, ed);
-                    const float term2 = fsub(ev1, fdiv(term1, ed));
-                    accS = fadd(accS, fsub(fmul(term1, term1), fmul(ev1, ev1)));
-                    accMu = fadd(accMu, fadd(term1, fmul(term2, dotv)));
-                    if (withChange) { accMu = fadd(accMu, fmul(fmul(term2, orow[colA]), ch)); }
-                }
-            }
-        }
-        visited += total;
-        __syncthreads(); // the compaction buffers are rewritten by the next group
-    }
+    uint32_t visited = 0;
+    sparse_scan_row(mv, hdr->warpCnt, sRow, sIdx, sD, sV1, sV2, row, colA, c2, useV2, withChange, ch, accS, accMu, visited);
     if (visitedTotal != nullptr && tid == 0) { atomicAdd(visitedTotal, static_cast<unsigned long long>(visited)); }
     // lanes -> warp -> CTA: the butterflies of the dense kernel
 #pragma unroll

@@ -27,6 +27,7 @@ struct SweepCounters
     unsigned long long commits;   // AP lines rewritten: +4*L each
     unsigned long long overflow;  // births dropped because the row's atom store was full
     unsigned long long rowsActive; // rows that made at least one proposal (their D / AP lines were staged)
+    unsigned long long visited;   // sparse model: common non-zeros the scans visited (8 + 4k algorithmic bytes each)
     long long atomDelta;          // change of the total atom count
     unsigned int maxCount;        // largest per-row atom count after the sweep
     unsigned int pad;
@@ -131,13 +132,15 @@ struct SweepSmem
     uint32_t count;
     uint32_t dirty;
     uint32_t pad;
+    float baseS, baseMu;  // sparse model: the Z-table terms of the scan in flight
+    uint32_t warpCnt[kSparseGroup * (kSparseThreads / 32)]; // sparse model: compaction counters of sparse_scan_row
 };
 
-static const uint32_t kSweepHdrBytes = 512;
+static const uint32_t kSweepHdrBytes = 640;
 static_assert(sizeof(SweepSmem) <= kSweepHdrBytes, "SweepSmem outgrew its slot");
 static const uint32_t kSweepDrawBytes = kSweepDrawRing * sizeof(SweepDraw);
 
-// dynamic shared memory of one CTA: [SweepSmem | 512][draw ring][pos: cap u64][mass: cap f32][M row: k f32]
+// dynamic shared memory of one CTA: [SweepSmem | 640][draw ring][pos: cap u64][mass: cap f32][M row: k f32]
 // [canUseGibbs: k i32] then, 128-byte aligned, the staged lines D, AP (, S) of `ld` floats each when the row is kept in
 // shared memory
 __host__ __device__ inline uint32_t sweepRowOffset(uint32_t cap, uint32_t k)
@@ -642,6 +645,200 @@ __global__ void __launch_bounds__(T, (T <= 128 ? 5 : (T <= 256 ? 4 : 1))) sweep_
     }
 }
 
+
+// ------------------------------------------------------------------------------------------------
+// The sweep over the SparseNormalModel (SparseNormalModel.cpp:153-292): same row independence — a scan reads the data
+// row's non-zeros, the row's own factor row and the other factor — same proposals, same draws, same transport.  There is
+// no AP line to stage: what stays in shared memory across the row's proposals is its factor row in both copies (the row
+// copy, and the column copy in which values below epsilon are stored as 0, data_structures/HybridMatrix.cpp:25-39);
+// the scan itself is the exact path's (sparse_scan_row: compact the common non-zeros, gather the other factor's rows).
+// dynamic shared memory: [SweepSmem | 640][draw ring][pos][mass][sRow: ldR f32][sCol: k f32][canUseGibbs: k i32], then
+// 128-byte aligned [sIdx][sD][sV1][sV2], kSparseThreads * kSparseGroup entries each
+// ------------------------------------------------------------------------------------------------
+__host__ __device__ inline uint32_t sweepSparseScanOffset(uint32_t cap, uint32_t k, uint32_t ldR)
+{
+    const uint32_t bytes = kSweepHdrBytes + kSweepDrawBytes + cap * 12u + (ldR + 2u * k) * 4u;
+    return (bytes + 127u) & ~127u;
+}
+
+__global__ void __launch_bounds__(kSparseThreads, 4) sweep_sparse_kernel(const __grid_constant__ SweepArgs a)
+{
+    constexpr int T = kSparseThreads;
+    extern __shared__ __align__(128) unsigned char smemRaw[];
+    const ModelView &mv = a.mv;
+    SweepSmem *hdr = reinterpret_cast<SweepSmem*>(smemRaw);
+    SweepDraw *draws = reinterpret_cast<SweepDraw*>(smemRaw + kSweepHdrBytes);
+    uint64_t *sPos = reinterpret_cast<uint64_t*>(smemRaw + kSweepHdrBytes + kSweepDrawBytes);
+    float *sMass = reinterpret_cast<float*>(sPos + a.cap);
+    float *sRow = sMass + a.cap;
+    float *sCol = sRow + mv.ldR;
+    int *sCan = reinterpret_cast<int*>(sCol + mv.k);
+    uint32_t *sIdx = reinterpret_cast<uint32_t*>(smemRaw + sweepSparseScanOffset(a.cap, mv.k, mv.ldR));
+    float *sD = reinterpret_cast<float*>(sIdx + kSparseThreads * kSparseGroup);
+    float *sV1 = sD + kSparseThreads * kSparseGroup;
+    float *sV2 = sV1 + kSparseThreads * kSparseGroup;
+    const uint32_t tid = threadIdx.x;
+    const uint32_t row = blockIdx.x;
+
+    uint32_t cnt = 0u;
+    if (tid == 0)
+    {
+        cnt = a.count[row];
+        double lam = dmul(static_cast<double>(a.nSteps), dadd(a.birthRow, dmul(static_cast<double>(cnt), a.perAtom)));
+        if (lam > 1.0e9) { lam = 1.0e9; }
+        uint32_t steps = __double2uint_rz(lam);
+        const float frac = __double2float_rn(dadd(lam, -static_cast<double>(steps)));
+        uint32_t w[4];
+        philox_block(row, 0xFFFFFFFFu, 0u, 0u, static_cast<uint32_t>(a.key), static_cast<uint32_t>(a.key >> 32), w);
+        if (u32_uniform(w[0]) < frac) { steps += 1u; }
+        hdr->steps = steps;
+        hdr->count = cnt;
+    }
+    __syncthreads();
+    const uint32_t steps = hdr->steps;
+    if (steps == 0u) { return; }
+    const uint32_t cnt0 = hdr->count;
+    for (uint32_t i = tid; i < kSweepDrawRing && i < steps; i += T) { sweep_make_draw(a.key, row, i, 0u, &draws[i]); }
+    for (uint32_t i = tid; i < cnt0; i += T)
+    {
+        sPos[i] = a.pos[static_cast<size_t>(row) * a.cap + i];
+        sMass[i] = a.mass[static_cast<size_t>(row) * a.cap + i];
+    }
+    for (uint32_t i = tid; i < mv.ldR; i += T) { sRow[i] = __ldcg(mv.Mrows + static_cast<size_t>(row) * mv.ldR + i); }
+    for (uint32_t c = tid; c < mv.k; c += T)
+    {
+        sCol[c] = __ldcg(mv.M + static_cast<size_t>(c) * mv.ldM + row);
+        sCan[c] = mv.otherColNonzero[c];
+    }
+    __syncthreads();
+
+    unsigned long long nScan1 = 0ull, nScan2 = 0ull, nOverflow = 0ull, nVisited = 0ull;
+    SweepPick pick;
+    pick.idx = pick.idx2 = 0u;
+    pick.newPos = 0ull;
+    if (tid == 0) { sweep_propose(a, row, draws[0], sPos, sMass, sCan, cnt, &hdr->ctl[0], &pick, &nOverflow); }
+    for (uint32_t step = 0; step < steps; ++step)
+    {
+        SweepCtl *ctl = &hdr->ctl[step & 1u];
+        if ((step & 31u) == 0u && step > 0u)
+        {
+            const uint32_t base = step + 32u;
+            if (tid >= 32u && tid < 64u && base + (tid - 32u) < steps) { sweep_make_draw(a.key, row, base + (tid - 32u), 0u, &draws[(base + (tid - 32u)) % kSweepDrawRing]); }
+        }
+        __syncthreads(); // proposal `step` is published
+        const uint32_t type = ctl->type;
+        if (type == 0u)
+        {
+            if (tid == 0 && step + 1u < steps) { sweep_propose(a, row, draws[(step + 1u) % kSweepDrawRing], sPos, sMass, sCan, cnt, &hdr->ctl[(step + 1u) & 1u], &pick, &nOverflow); }
+            continue;
+        }
+        const uint32_t c1 = ctl->c1, c2 = ctl->c2;
+        const bool pairType = (type == 'M') || (type == 'E');
+        const bool withChange = (type == 'D');
+        const float ch = -ctl->m1;
+        float accS = 0.f, accMu = 0.f;
+        uint32_t visited = 0u;
+        if (ctl->scan != 0u)
+        {
+            if (tid == 64)
+            {
+                float bs, bmu;
+                sparse_table_terms(mv, sRow, c1, c1, c2, pairType, withChange, ch, bs, bmu);
+                hdr->baseS = bs;
+                hdr->baseMu = bmu;
+            }
+            sparse_scan_row(mv, hdr->warpCnt, sRow, sIdx, sD, sV1, sV2, row, c1, c2, pairType, withChange, ch, accS, accMu, visited);
+        }
+        sweep_reduce<T>(hdr, accS, accMu);
+        if (tid == 0)
+        {
+            float sTot = 0.f, muTot = 0.f;
+            if (ctl->scan != 0u)
+            {
+                sTot = fmul(pairType ? fsub(hdr->baseS, accS) : fadd(hdr->baseS, accS), mv.beta);
+                muTot = fmul(fadd(hdr->baseMu, accMu), mv.beta);
+                if (pairType) { ++nScan2; } else { ++nScan1; }
+                nVisited += visited;
+            }
+            DevProposal pr;
+            pr.rng = ctl->seed;
+            pr.r1 = pr.r2 = row;
+            pr.c1 = c1;
+            pr.c2 = c2;
+            pr.m1 = ctl->m1;
+            pr.m2 = ctl->m2;
+            pr.type = type;
+            pr.variant = 0u;
+            pr.ch = 0.f;
+            pr.pad = 0u;
+            PreLog pre;
+            pre.state0 = pr.rng;
+            pre.logFirst = ctl->log0;
+            pre.logSecond = ctl->log1;
+            Verdict v;
+            decide_body<true, true>(mv, mv.erf, mv.erfinv, mv.annealingTemp, pr, 0u, false, sTot, muTot, sRow[c1], sRow[c2], sCol[c1], sCol[c2],
+                                    sCan[c1], sCan[c2], pre, &v);
+            if (v.dec.flags & 1u) { sRow[c1] = v.newM1; sCol[c1] = v.newC1; }
+            if (v.dec.flags & 2u) { sRow[c2] = v.newM2; sCol[c2] = v.newC2; }
+            const bool accepted = v.out.accepted != 0u;
+            if (type == 'B')
+            {
+                if (accepted)
+                {
+                    for (uint32_t i = cnt; i > pick.idx; --i) { sPos[i] = sPos[i - 1u]; sMass[i] = sMass[i - 1u]; }
+                    sPos[pick.idx] = pick.newPos;
+                    sMass[pick.idx] = v.out.mass1;
+                    cnt += 1u;
+                }
+            }
+            else if (type == 'D')
+            {
+                if (accepted) { sMass[pick.idx] = v.out.mass1; }
+                else
+                {
+                    for (uint32_t i = pick.idx; i + 1u < cnt; ++i) { sPos[i] = sPos[i + 1u]; sMass[i] = sMass[i + 1u]; }
+                    cnt -= 1u;
+                }
+            }
+            else if (type == 'M')
+            {
+                if (accepted) { sPos[pick.idx] = pick.newPos; }
+            }
+            else if (accepted)
+            {
+                sMass[pick.idx] = v.out.mass1;
+                sMass[pick.idx2] = v.out.mass2;
+            }
+            if (step + 1u < steps) { sweep_propose(a, row, draws[(step + 1u) % kSweepDrawRing], sPos, sMass, sCan, cnt, &hdr->ctl[(step + 1u) & 1u], &pick, &nOverflow); }
+        }
+        // the factor row and the next proposal become visible at the next iteration's barrier
+    }
+    if (tid == 0) { hdr->count = cnt; }
+    __syncthreads();
+    const uint32_t cntEnd = hdr->count;
+    for (uint32_t i = tid; i < cntEnd; i += T)
+    {
+        a.pos[static_cast<size_t>(row) * a.cap + i] = sPos[i];
+        a.mass[static_cast<size_t>(row) * a.cap + i] = sMass[i];
+    }
+    if (tid == 0)
+    {
+        a.count[row] = cntEnd;
+        SweepCounters *c = a.counters;
+        atomicAdd(&c->steps, static_cast<unsigned long long>(steps));
+        atomicAdd(&c->rowsActive, 1ull);
+        if (nScan1) { atomicAdd(&c->scans1, nScan1); }
+        if (nScan2) { atomicAdd(&c->scans2, nScan2); }
+        if (nVisited) { atomicAdd(&c->visited, nVisited); }
+        if (nOverflow) { atomicAdd(&c->overflow, nOverflow); }
+        if (cntEnd != cnt0)
+        {
+            atomicAdd(reinterpret_cast<unsigned long long*>(&c->atomDelta),
+                      static_cast<unsigned long long>(static_cast<long long>(cntEnd) - static_cast<long long>(cnt0)));
+        }
+    }
+}
+
 // ------------------------------------------------------------------------------------------------
 // Transport between adjacent rows (oracle: sweep_pair).  What the row-local sweep cannot do is carry an atom from one row
 // to another, which the reference's move does all the time (its bounds are the atom's neighbours in the WHOLE domain,
@@ -653,9 +850,12 @@ __global__ void __launch_bounds__(T, (T <= 128 ? 5 : (T <= 256 ? 4 : 1))) sweep_
 // as AlphaParameters::operator+ does, AlphaParameters.cpp:11-14), or exchange mass between a and b.  Few proposals per
 // pair, no reuse: the lines are read and rewritten where they live (L2 / HBM).
 // ------------------------------------------------------------------------------------------------
-template <int T, bool HAS_S>
+// SPARSE: the SparseNormalModel's scans (T = kSparseThreads; dynamic shared memory: [sRow: ldR f32] then, 128-byte aligned,
+// [sIdx][sD][sV1][sV2] of kSparseThreads * kSparseGroup entries each)
+template <int T, bool HAS_S, bool SPARSE>
 __global__ void __launch_bounds__(T) sweep_transport_kernel(const __grid_constant__ SweepArgs a)
 {
+    extern __shared__ __align__(128) unsigned char transportDyn[];
     __shared__ SweepSmem hdrStore;
     __shared__ SweepDraw draws[32];
     SweepSmem *hdr = &hdrStore;
@@ -687,7 +887,7 @@ __global__ void __launch_bounds__(T) sweep_transport_kernel(const __grid_constan
     __syncthreads();
     const uint32_t steps = hdr->steps;
     if (steps == 0u) { return; }
-    unsigned long long nScan2 = 0ull, nScanX = 0ull, nCommit = 0ull, nOverflow = 0ull;
+    unsigned long long nScan2 = 0ull, nScanX = 0ull, nCommit = 0ull, nOverflow = 0ull, nVisited = 0ull;
     for (uint32_t step = 0; step < steps; ++step)
     {
         SweepCtl *ctl = &hdr->ctl[step & 1u]; // double-buffered: thread 0 may run one proposal ahead of a slow reader
@@ -770,10 +970,46 @@ __global__ void __launch_bounds__(T) sweep_transport_kernel(const __grid_constan
         const uint32_t r1 = ctl->r1, r2 = ctl->r2, c1 = ctl->c1, c2 = ctl->c2;
         const float *gV1 = mv.otherM + static_cast<size_t>(c1) * mv.ldOther;
         const float *gV2 = mv.otherM + static_cast<size_t>(c2) * mv.ldOther;
-        float *ap1 = mv.AP + static_cast<size_t>(r1) * mv.ld, *ap2 = mv.AP + static_cast<size_t>(r2) * mv.ld;
+        float *ap1 = SPARSE ? nullptr : mv.AP + static_cast<size_t>(r1) * mv.ld, *ap2 = SPARSE ? nullptr : mv.AP + static_cast<size_t>(r2) * mv.ld;
         float4 unused1[1], unused2[1];
         float s = 0.f, mu = 0.f;
-        if (r1 == r2)
+        uint32_t visitedHere = 0u;
+        if (SPARSE)
+        {
+            // SparseNormalModel::alphaParameters(r1,c1,r2,c2) (SparseNormalModel.cpp:200-292): one two-column scan of the
+            // row, or alphaParameters(r1,c1) + alphaParameters(r2,c2), each with its table terms and beta before the sum
+            float *sRow = reinterpret_cast<float*>(transportDyn);
+            uint32_t *sIdx = reinterpret_cast<uint32_t*>(transportDyn + ((mv.ldR * 4u + 127u) & ~127u));
+            float *sD = reinterpret_cast<float*>(sIdx + kSparseThreads * kSparseGroup);
+            float *sV1 = sD + kSparseThreads * kSparseGroup;
+            float *sV2 = sV1 + kSparseThreads * kSparseGroup;
+            const bool sameRow = (r1 == r2);
+            float sPart[2] = {0.f, 0.f}, muPart[2] = {0.f, 0.f};
+            for (uint32_t part = 0; part < (sameRow ? 1u : 2u); ++part)
+            {
+                const uint32_t rowP = part ? r2 : r1, colP = part ? c2 : c1;
+                __syncthreads(); // the previous part's factor row and warp totals are no longer read
+                for (uint32_t i = tid; i < mv.ldR; i += T) { sRow[i] = __ldcg(mv.Mrows + static_cast<size_t>(rowP) * mv.ldR + i); }
+                __syncthreads();
+                if (tid == 64)
+                {
+                    float bs, bmu;
+                    sparse_table_terms(mv, sRow, colP, c1, c2, sameRow, false, 0.f, bs, bmu);
+                    hdr->baseS = bs;
+                    hdr->baseMu = bmu;
+                }
+                float accS = 0.f, accMu = 0.f;
+                uint32_t visited = 0u;
+                sparse_scan_row(mv, hdr->warpCnt, sRow, sIdx, sD, sV1, sV2, rowP, colP, c2, sameRow, false, 0.f, accS, accMu, visited);
+                sweep_reduce<T>(hdr, accS, accMu);
+                sPart[part] = fmul(sameRow ? fsub(hdr->baseS, accS) : fadd(hdr->baseS, accS), mv.beta);
+                muPart[part] = fmul(fadd(hdr->baseMu, accMu), mv.beta);
+                visitedHere += visited;
+            }
+            s = sameRow ? sPart[0] : fadd(sPart[0], sPart[1]);
+            mu = sameRow ? muPart[0] : fsub(muPart[0], muPart[1]);
+        }
+        else if (r1 == r2)
         {
             sweep_scan<T, 0, HAS_S, true, false>(mv.D + static_cast<size_t>(r1) * mv.ld, HAS_S ? mv.S + static_cast<size_t>(r1) * mv.ld : nullptr,
                                                  ap1, gV1, gV2, L, 0.f, s, mu, unused1, unused2);
@@ -795,9 +1031,38 @@ __global__ void __launch_bounds__(T) sweep_transport_kernel(const __grid_constan
         }
         if (tid == 0)
         {
-            float M1 = ld_cg_f32(mv.M + static_cast<size_t>(c1) * mv.ldM + r1), M2 = ld_cg_f32(mv.M + static_cast<size_t>(c2) * mv.ldM + r2);
             DevOutcome out;
-            const bool accepted = sweep_decide(mv, ctl, s, mu, M1, M2, mv.otherColNonzero[c1], mv.otherColNonzero[c2], &out);
+            bool accepted;
+            if (SPARSE)
+            {
+                DevProposal pr;
+                pr.rng = ctl->seed;
+                pr.r1 = r1; pr.c1 = c1; pr.r2 = r2; pr.c2 = c2;
+                pr.m1 = ctl->m1;
+                pr.m2 = ctl->m2;
+                pr.type = type;
+                pr.variant = 0u;
+                pr.ch = 0.f;
+                pr.pad = 0u;
+                PreLog pre;
+                pre.state0 = pr.rng;
+                pre.logFirst = ctl->log0;
+                pre.logSecond = ctl->log1;
+                Verdict v;
+                decide_body<true, true>(mv, mv.erf, mv.erfinv, mv.annealingTemp, pr, 0u, false, s, mu,
+                                        ld_cg_f32(mv.Mrows + static_cast<size_t>(r1) * mv.ldR + c1), ld_cg_f32(mv.Mrows + static_cast<size_t>(r2) * mv.ldR + c2),
+                                        ld_cg_f32(mv.M + static_cast<size_t>(c1) * mv.ldM + r1), ld_cg_f32(mv.M + static_cast<size_t>(c2) * mv.ldM + r2),
+                                        mv.otherColNonzero[c1], mv.otherColNonzero[c2], pre, &v);
+                ctl->flags = 0u; // no AP line to rewrite
+                out = v.out;
+                accepted = v.out.accepted != 0u;
+                nVisited += visitedHere;
+            }
+            else
+            {
+                float M1 = ld_cg_f32(mv.M + static_cast<size_t>(c1) * mv.ldM + r1), M2 = ld_cg_f32(mv.M + static_cast<size_t>(c2) * mv.ldM + r2);
+                accepted = sweep_decide(mv, ctl, s, mu, M1, M2, mv.otherColNonzero[c1], mv.otherColNonzero[c2], &out);
+            }
             if (cross) { ++nScanX; } else { ++nScan2; }
             if (ctl->flags & 1u) { ++nCommit; }
             if (cross && (ctl->flags & 2u)) { ++nCommit; }
@@ -846,6 +1111,7 @@ __global__ void __launch_bounds__(T) sweep_transport_kernel(const __grid_constan
         atomicAdd(&c->steps, static_cast<unsigned long long>(steps));
         if (nScan2) { atomicAdd(&c->scans2, nScan2); }
         if (nScanX) { atomicAdd(&c->scansX, nScanX); }
+        if (nVisited) { atomicAdd(&c->visited, nVisited); }
         if (nCommit) { atomicAdd(&c->commits, nCommit); }
         if (nOverflow) { atomicAdd(&c->overflow, nOverflow); }
     }

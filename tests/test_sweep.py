@@ -119,6 +119,25 @@ def test_sweep_reconstruction_matches_the_exact_chain(oracle):
     assert int(s.atomHistoryA[-1]) == pytest.approx(int(e.atomHistoryA[-1]), rel=0.15)
 
 
+@pytest.mark.parametrize("name,k,its", [("gist", 7, 400), ("spz:120:90:4:3:80", 4, 400)])
+def test_sparse_sweep_agrees_statistically_with_the_reference(oracle, name, k, its):
+    """the same Tier-3 comparison for the sweep over the sparse model, against the reference's own SparseNormalModel chain"""
+    from oracle.harness import RefLib
+    if not RefLib.available("scalar"):
+        pytest.skip("oracle/_ref not built here (needs /root/reference)")
+    data = load_data(name)
+    seeds = list(range(1, 12, 2))
+    ref = _stat_rows(RefLib("scalar").run, data, k, its, seeds, useSparseOptimization=1)
+    swp = _stat_rows(oracle.run, data, k, its, seeds, updateMode=SWEEP, useSparseOptimization=1)
+    for j, what in enumerate(("atoms A", "atoms P", "chi-square", "meanChiSq")):
+        mr, ms = ref[:, j].mean(), swp[:, j].mean()
+        sd = np.sqrt(0.5 * (ref[:, j].var(ddof=1) + swp[:, j].var(ddof=1)))
+        se = sd * np.sqrt(2.0 / len(seeds))
+        if j >= 2:
+            assert abs(mr - ms) <= max(3.0 * se, 0.03 * abs(mr)), "%s: reference %.1f vs sweep %.1f (se %.1f)" % (what, mr, ms, se)
+        assert abs(mr - ms) <= max((0.2 if j < 2 else 0.1) * abs(mr), sd), what
+
+
 def test_sweep_keeps_mass_and_atoms_in_step(oracle):
     """changeMatrix / safelyChangeMatrix bookkeeping of the sweep: snapshots are non-negative and zero exactly where a
     fixed matrix must not move"""
@@ -182,6 +201,39 @@ def test_sweep_run_matches_oracle(oracle, name):
         assert np.array_equal(bits(got.snapshotsP[-1]), bits(want.snapshotsP[-1]))
     if RUN_CASES[name].get("pump"):
         assert np.array_equal(got.pumpMatrix, want.pumpMatrix)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("name", ["sparse_gist", "sparse_modsim", "sparse_120x90", "sparse_k30", "sparse_gist_fixedP"])
+def test_sparse_sweep_run_matches_oracle(oracle, name):
+    """the sweep over the SparseNormalModel (sweep_sparse_kernel + the sparse transport): same chain as the oracle's sweep
+    on its sparse model — no AP line here, the row's factor row in both copies lives in shared memory instead"""
+    import cogaps_b200 as cg
+    data, unc, kw = case_inputs(name, updateMode=SWEEP)
+    want = oracle.run(data, snapshots=True, options=sweep_options(oracle, data.shape[0], data.shape[1]), **kw)
+    got = cg.gaps_run(data, snapshots=True, **kw)
+    check_run(got, want, kw)
+    if kw.get("snapshotFrequency"):
+        assert np.array_equal(bits(got.snapshotsA[-1]), bits(want.snapshotsA[-1]))
+        assert np.array_equal(bits(got.snapshotsP[-1]), bits(want.snapshotsP[-1]))
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("spec,k", [("spz:3000:30000:8:7:95", 50), ("spz:26000:2500:8:9:95", 50)])
+def test_sparse_sweep_c4_shaped_rows(oracle, spec, k):
+    """BASELINE configs[3]'s row shape in sweep mode: 30000-long rows at 95 % zeros (more than one 1024-entry group per
+    scan), nPatterns = 50, both orientations"""
+    import cogaps_b200 as cg
+    data = load_data(spec)
+    kw = dict(seed=17, nPatterns=k, nIterations=8, outputFrequency=4, maxThreads=1, useSparseOptimization=1, snapshotFrequency=8,
+              updateMode=SWEEP)
+    want = oracle.run(data, snapshots=True, options=sweep_options(oracle, data.shape[0], data.shape[1]), **kw)
+    got = cg.gaps_run(data, snapshots=True, **kw)
+    assert np.array_equal(got.atomHistoryA, want.atomHistoryA), (got.atomHistoryA, want.atomHistoryA)
+    assert np.array_equal(got.atomHistoryP, want.atomHistoryP)
+    assert got.totalUpdates == want.totalUpdates
+    assert np.array_equal(bits(got.snapshotsA[-1]), bits(want.snapshotsA[-1]))
+    assert np.array_equal(bits(got.snapshotsP[-1]), bits(want.snapshotsP[-1]))
 
 
 @pytest.mark.gpu
