@@ -1761,8 +1761,10 @@ static const size_t kSweepMaxSmem = 227u * 1024u;
 static uint32_t sweepThreadsForLength(uint32_t L)
 {
     const int forced = envInt("COGAPS_SWEEP_THREADS", 0); // experiments: 128 / 256 / 512 (changes the reduction order)
-    if (forced == 128 || forced == 256 || forced == 512) { return static_cast<uint32_t>(forced); }
-    return L <= 10240u ? 256u : 512u;
+    if (forced == 128 || forced == 256 || forced == 512 || forced == 1024) { return static_cast<uint32_t>(forced); }
+    const int forcedLong = envInt("COGAPS_SWEEP_THREADS_LONG", 0); // the same for rows beyond 10240 floats only
+    if (L > 10240u && (forcedLong == 512 || forcedLong == 1024)) { return static_cast<uint32_t>(forcedLong); }
+    return L <= 10240u ? 256u : 1024u; // measured at C3: 1024 threads on the 20000-long rows beat 512 by 5 %
 }
 static const int kSweepKeep = 10; // float4 per thread and column kept in registers between scan and commit (512-thread rows up to 20480 floats)
 
@@ -1989,9 +1991,10 @@ static int sweepLaunchInstance(cgb_sampler *s, const SweepArgs &args, size_t sme
 template <int T, bool HAS_S>
 static int sweepLaunchRows(cgb_sampler *s, const SweepArgs &args, size_t smem, bool rowSmem)
 {
-    const bool keep = rowSmem && T == 512 && (s->L + kVec - 1) / kVec <= static_cast<uint32_t>(kSweepKeep) * T;
+    constexpr int kKeep = (T == 512) ? kSweepKeep : 0; // at 1024 threads (64 registers) keeping the columns spills: measured slower
+    const bool keep = rowSmem && kKeep > 0 && (s->L + kVec - 1) / kVec <= static_cast<uint32_t>(kKeep) * T && envInt("COGAPS_SWEEP_KEEP", 1) != 0;
     if (!rowSmem) { return sweepLaunchInstance<T, 0, HAS_S, false>(s, args, smem); }
-    if (keep) { return sweepLaunchInstance<T, (T == 512 ? kSweepKeep : 0), HAS_S, true>(s, args, smem); }
+    if (keep) { return sweepLaunchInstance<T, kKeep, HAS_S, true>(s, args, smem); }
     return sweepLaunchInstance<T, 0, HAS_S, true>(s, args, smem);
 }
 
@@ -2060,6 +2063,10 @@ static int sweepUpdate(cgb_sampler *s, uint32_t nSteps)
     {
         if (s->hasS) { CGB_TRY((sweepLaunchRows<256, true>(s, args, smem, rowSmem))); } else { CGB_TRY((sweepLaunchRows<256, false>(s, args, smem, rowSmem))); }
     }
+    else if (T == 1024u)
+    {
+        if (s->hasS) { CGB_TRY((sweepLaunchRows<1024, true>(s, args, smem, rowSmem))); } else { CGB_TRY((sweepLaunchRows<1024, false>(s, args, smem, rowSmem))); }
+    }
     else
     {
         if (s->hasS) { CGB_TRY((sweepLaunchRows<512, true>(s, args, smem, rowSmem))); } else { CGB_TRY((sweepLaunchRows<512, false>(s, args, smem, rowSmem))); }
@@ -2076,6 +2083,10 @@ static int sweepUpdate(cgb_sampler *s, uint32_t nSteps)
         else if (T == 256u)
         {
             if (s->hasS) { CGB_TRY((sweepLaunchTransport<256, true>(s, args))); } else { CGB_TRY((sweepLaunchTransport<256, false>(s, args))); }
+        }
+        else if (T == 1024u)
+        {
+            if (s->hasS) { CGB_TRY((sweepLaunchTransport<1024, true>(s, args))); } else { CGB_TRY((sweepLaunchTransport<1024, false>(s, args))); }
         }
         else
         {

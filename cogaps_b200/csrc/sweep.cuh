@@ -853,7 +853,7 @@ __global__ void __launch_bounds__(kSparseThreads, 4) sweep_sparse_kernel(const _
 // SPARSE: the SparseNormalModel's scans (T = kSparseThreads; dynamic shared memory: [sRow: ldR f32] then, 128-byte aligned,
 // [sIdx][sD][sV1][sV2] of kSparseThreads * kSparseGroup entries each)
 template <int T, bool HAS_S, bool SPARSE>
-__global__ void __launch_bounds__(T) sweep_transport_kernel(const __grid_constant__ SweepArgs a)
+__global__ void __launch_bounds__(T, (T <= 256 ? 4 : (T <= 512 ? 2 : 1))) sweep_transport_kernel(const __grid_constant__ SweepArgs a)
 {
     extern __shared__ __align__(128) unsigned char transportDyn[];
     __shared__ SweepSmem hdrStore;
