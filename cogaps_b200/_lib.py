@@ -35,7 +35,7 @@ EXPORTS = [
     "cgb_checkpoint_info_read", "cgb_checkpoint_rewrite", "cgb_read_matrix_csr",
     "cgb_debug_replay_generator", "cgb_debug_replay_message", "cgb_run_file_ex", "cgb_debug_running_sum", "cgb_write_matrix_csv", "cgb_result_write_files", "cgb_file_col_names", "cgb_debug_domain_fuzz",
     "cgb_sampler_set_update_mode", "cgb_sweep_reduction_order_for_length",
-    "cgb_comm_get_unique_id", "cgb_comm_init", "cgb_comm_destroy", "cgb_allgather_rows", "cgb_allgather_device_rows",
+    "cgb_sampler_set_resident_share", "cgb_comm_get_unique_id", "cgb_comm_init", "cgb_comm_destroy", "cgb_allgather_rows", "cgb_allgather_device_rows",
 ]
 
 _lib = None
@@ -114,6 +114,7 @@ def lib():
     L.cgb_reduction_order_for_length.argtypes = [C.c_uint32, C.POINTER(CgbReductionOrder)]
     L.cgb_sweep_reduction_order_for_length.argtypes = [C.c_uint32, C.POINTER(CgbReductionOrder)]
     L.cgb_sampler_set_update_mode.argtypes = [vp, C.c_int32]
+    L.cgb_sampler_set_resident_share.argtypes = [vp, C.c_int32]
     L.cgb_comm_get_unique_id.argtypes = [vp]
     L.cgb_comm_init.argtypes = [vp, C.c_int32, C.c_int32, C.POINTER(vp)]
     L.cgb_comm_destroy.argtypes = [vp]

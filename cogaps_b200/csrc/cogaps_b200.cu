@@ -12,6 +12,7 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <map>
 #include <mutex>
 #include <new>
 #include <string>
@@ -454,7 +455,7 @@ extern "C" void cgb_sampler_destroy(cgb_sampler *s)
     cudaFree(s->dD); cudaFree(s->dS); cudaFree(s->dAP); cudaFree(s->dM); cudaFree(s->dColNonzero);
     cudaFree(s->dPartials); cudaFree(s->dTickets); cudaFree(s->dReducePartials); cudaFree(s->dPhaseClocks);
     cudaFree(s->dRowVersion); cudaFree(s->dStreamStats);
-    cudaFree(s->dSwPos); cudaFree(s->dSwMass); cudaFree(s->dSwCount); cudaFree(s->dSwCounters);
+    cudaFree(s->dSwPos); cudaFree(s->dSwMass); cudaFree(s->dSwCount); cudaFree(s->dSwCounters); cudaFree(s->dSwOrder);
     if (s->hSwCounters) { cudaFreeHost(s->hSwCounters); }
     cudaFree(s->dSpRowPtr); cudaFree(s->dSpIdx); cudaFree(s->dSpVal); cudaFree(s->dMrows); cudaFree(s->dZ1); cudaFree(s->dZ2);
     if (s->hCommitsMirror) { cudaFreeHost(const_cast<unsigned long long*>(s->hCommitsMirror)); }
@@ -1223,7 +1224,7 @@ static int startPersistent(cgb_sampler *s)
         const int cap = envInt("COGAPS_PERSISTENT_CLUSTERS", 0);
         if (cap > 1 && cap < maxClusters) { maxClusters = cap; }
         // several chains driven by several host threads share the device: every grid must fit beside the others
-        const int share = g_residentShare.load();
+        const int share = s->residentShare > 0 ? s->residentShare : g_residentShare.load();
         if (share > 1) { maxClusters = std::max(2, maxClusters / share); }
         if (maxClusters < 2) { return fail(CGB_ECUDA, "resident kernel: fewer than two clusters fit on the device"); }
         s->persistentGrid = maxClusters * static_cast<int>(s->nSeg);
@@ -1757,14 +1758,16 @@ static int sequentialUpdate(cgb_sampler *s, uint32_t nSteps)
 // ------------------------------------------------------------------------------------------------
 static const uint32_t kSweepInitialCap = 64;
 static const size_t kSweepMaxSmem = 227u * 1024u;
+static const uint32_t kSweepOrderFromRows = 148; // fewer rows than SMs: nothing to order
+static const uint32_t kSweepThreadsLong = 512;    // threads per row beyond 10240 floats (measured at C3's 20000-long rows, see sweepStageFor)
 
 static uint32_t sweepThreadsForLength(uint32_t L)
 {
-    const int forced = envInt("COGAPS_SWEEP_THREADS", 0); // experiments: 128 / 256 / 512 (changes the reduction order)
+    const int forcedLong = envInt("COGAPS_SWEEP_THREADS_LONG", 0); // experiments: rows beyond 10240 floats only
+    if (L > 10240u && (forcedLong == 256 || forcedLong == 512 || forcedLong == 1024)) { return static_cast<uint32_t>(forcedLong); }
+    const int forced = envInt("COGAPS_SWEEP_THREADS", 0); // experiments: 128 / 256 / 512 / 1024 (changes the reduction order)
     if (forced == 128 || forced == 256 || forced == 512 || forced == 1024) { return static_cast<uint32_t>(forced); }
-    const int forcedLong = envInt("COGAPS_SWEEP_THREADS_LONG", 0); // the same for rows beyond 10240 floats only
-    if (L > 10240u && (forcedLong == 512 || forcedLong == 1024)) { return static_cast<uint32_t>(forcedLong); }
-    return L <= 10240u ? 256u : 1024u; // measured at C3: 1024 threads on the 20000-long rows beat 512 by 5 %
+    return L <= 10240u ? 256u : kSweepThreadsLong;
 }
 static const int kSweepKeep = 10; // float4 per thread and column kept in registers between scan and commit (512-thread rows up to 20480 floats)
 
@@ -1969,33 +1972,37 @@ template <class Kernel>
 static int sweepGrowSmemLimit(Kernel kernel, size_t smem)
 {
     static std::mutex lock;
-    static size_t configured = 48u * 1024u;
+    static std::map<const void*, size_t> configured; // per instance: every instantiation has the same pointer type
     std::lock_guard<std::mutex> hold(lock);
-    if (smem > configured)
+    size_t &have = configured[reinterpret_cast<const void*>(kernel)];
+    if (have == 0u) { have = 48u * 1024u; }
+    if (smem > have)
     {
         CGB_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
-        configured = smem;
+        have = smem;
     }
     return CGB_OK;
 }
 
-template <int T, int NV, bool HAS_S, bool ROW_SMEM>
+template <int T, int NV, bool HAS_S, int STAGE>
 static int sweepLaunchInstance(cgb_sampler *s, const SweepArgs &args, size_t smem)
 {
-    CGB_TRY(sweepGrowSmemLimit(sweep_kernel<T, NV, HAS_S, ROW_SMEM>, smem));
-    sweep_kernel<T, NV, HAS_S, ROW_SMEM><<<s->nRows, T, smem, s->stream>>>(args);
+    CGB_TRY(sweepGrowSmemLimit(sweep_kernel<T, NV, HAS_S, STAGE>, smem));
+    sweep_kernel<T, NV, HAS_S, STAGE><<<s->nRows, T, smem, s->stream>>>(args);
     g_kernelLaunches.fetch_add(1);
     return CGB_OK;
 }
 
+// stage: 0 rows walked where they live, 1 D and AP lines in shared memory, 2 the AP line only
 template <int T, bool HAS_S>
-static int sweepLaunchRows(cgb_sampler *s, const SweepArgs &args, size_t smem, bool rowSmem)
+static int sweepLaunchRows(cgb_sampler *s, const SweepArgs &args, size_t smem, int stage)
 {
     constexpr int kKeep = (T == 512) ? kSweepKeep : 0; // at 1024 threads (64 registers) keeping the columns spills: measured slower
-    const bool keep = rowSmem && kKeep > 0 && (s->L + kVec - 1) / kVec <= static_cast<uint32_t>(kKeep) * T && envInt("COGAPS_SWEEP_KEEP", 1) != 0;
-    if (!rowSmem) { return sweepLaunchInstance<T, 0, HAS_S, false>(s, args, smem); }
-    if (keep) { return sweepLaunchInstance<T, kKeep, HAS_S, true>(s, args, smem); }
-    return sweepLaunchInstance<T, 0, HAS_S, true>(s, args, smem);
+    const bool keep = stage == 1 && kKeep > 0 && (s->L + kVec - 1) / kVec <= static_cast<uint32_t>(kKeep) * T && envInt("COGAPS_SWEEP_KEEP", 1) != 0;
+    if (stage == 0) { return sweepLaunchInstance<T, 0, HAS_S, 0>(s, args, smem); }
+    if (stage == 2) { return sweepLaunchInstance<T, 0, HAS_S, 2>(s, args, smem); }
+    if (keep) { return sweepLaunchInstance<T, kKeep, HAS_S, 1>(s, args, smem); }
+    return sweepLaunchInstance<T, 0, HAS_S, 1>(s, args, smem);
 }
 
 static size_t sweepSparseScanBytes() { return static_cast<size_t>(4) * kSparseThreads * kSparseGroup * sizeof(float); }
@@ -2028,11 +2035,12 @@ static int sweepUpdate(cgb_sampler *s, uint32_t nSteps)
     args.count = s->dSwCount;
     args.qgamma = s->rs->dQgamma;
     args.counters = static_cast<SweepCounters*>(s->dSwCounters);
+    args.order = nullptr;
     args.key = s->rs->seeder.next();                      // one seeder value per update()
     args.binLength = 0xFFFFFFFFFFFFFFFFull / (static_cast<uint64_t>(s->nRows) * s->k);
     args.binMagic = (args.binLength > 1) ? static_cast<uint64_t>((static_cast<unsigned __int128>(1) << 64) / args.binLength) : 0ull;
     args.colour = 0;
-    args.pad = 0;
+    args.profile = envInt("COGAPS_SWEEP_PROFILE", 0) != 0 ? 1u : 0u;
     const SweepRates w = sweepRates(s->swTotalAtoms, s->nRows, s->k, args.binLength, static_cast<double>(s->alpha));
     args.birthRow = w.birthRow;
     args.deathAtom = w.deathAtom;
@@ -2042,12 +2050,27 @@ static int sweepUpdate(cgb_sampler *s, uint32_t nSteps)
     args.cap = s->swCap;
     args.nSteps = nSteps;
     const size_t base = s->sparse ? sweepSparseScanOffset(s->swCap, s->k, s->ldR) + sweepSparseScanBytes() : sweepRowOffset(s->swCap, s->k);
-    const size_t staged = base + static_cast<size_t>(s->hasS ? 3 : 2) * s->ld * sizeof(float);
-    const bool rowSmem = !s->sparse && staged <= kSweepMaxSmem && envInt("COGAPS_SWEEP_ROW_SMEM", 1) != 0;
-    const size_t smem = rowSmem ? staged : base;
+    const size_t lineBytes = static_cast<size_t>(s->ld) * sizeof(float);
+    // What a row keeps in shared memory (COGAPS_SWEEP_STAGE overrides): its D and AP lines where four rows fit on an SM that
+    // way (rows up to 10240 floats); beyond, the AP line only — two 20000-float rows per SM with D through L2 measured 15 %
+    // faster than one row with both lines (C3's P side).  A row that does not fit falls back to the next smaller footprint.
+    int stage = s->sparse ? 0 : envInt("COGAPS_SWEEP_STAGE", envInt("COGAPS_SWEEP_ROW_SMEM", 1) != 0 ? (s->L <= 10240u ? 1 : 2) : 0);
+    if (stage == 1 && base + (s->hasS ? 3u : 2u) * lineBytes > kSweepMaxSmem) { stage = 2; }
+    if (stage == 2 && base + lineBytes > kSweepMaxSmem) { stage = 0; }
+    if (stage < 0 || stage > 2) { stage = 0; }
+    const size_t smem = base + (stage == 1 ? (s->hasS ? 3u : 2u) * lineBytes : (stage == 2 ? lineBytes : 0u));
     CGB_CHECK(smem <= kSweepMaxSmem, "sweep: a row's atom store no longer fits in shared memory");
     CGB_CUDA(cudaMemsetAsync(s->dSwCounters, 0, sizeof(SweepCounters), s->stream));
     CGB_CUDA(cudaEventRecord(s->evStart, s->stream));
+    if (s->nRows > kSweepOrderFromRows && envInt("COGAPS_SWEEP_ORDER", 1) != 0)
+    {
+        // longest chains first (sweep_order_kernel); with few rows every row has a CTA slot of its own from the start
+        if (s->dSwOrder == nullptr) { CGB_CUDA(cudaMalloc(&s->dSwOrder, static_cast<size_t>(s->nRows) * sizeof(uint32_t))); }
+        sweep_order_kernel<<<1, 1024, 0, s->stream>>>(s->dSwCount, s->nRows, s->dSwOrder);
+        g_kernelLaunches.fetch_add(1);
+        CGB_CUDA(cudaGetLastError());
+        args.order = s->dSwOrder;
+    }
     const uint32_t T = s->sparse ? static_cast<uint32_t>(kSparseThreads) : sweepThreadsForLength(s->L);
     if (s->sparse)
     {
@@ -2057,19 +2080,19 @@ static int sweepUpdate(cgb_sampler *s, uint32_t nSteps)
     }
     else if (T == 128u)
     {
-        if (s->hasS) { CGB_TRY((sweepLaunchRows<128, true>(s, args, smem, rowSmem))); } else { CGB_TRY((sweepLaunchRows<128, false>(s, args, smem, rowSmem))); }
+        if (s->hasS) { CGB_TRY((sweepLaunchRows<128, true>(s, args, smem, stage))); } else { CGB_TRY((sweepLaunchRows<128, false>(s, args, smem, stage))); }
     }
     else if (T == 256u)
     {
-        if (s->hasS) { CGB_TRY((sweepLaunchRows<256, true>(s, args, smem, rowSmem))); } else { CGB_TRY((sweepLaunchRows<256, false>(s, args, smem, rowSmem))); }
+        if (s->hasS) { CGB_TRY((sweepLaunchRows<256, true>(s, args, smem, stage))); } else { CGB_TRY((sweepLaunchRows<256, false>(s, args, smem, stage))); }
     }
     else if (T == 1024u)
     {
-        if (s->hasS) { CGB_TRY((sweepLaunchRows<1024, true>(s, args, smem, rowSmem))); } else { CGB_TRY((sweepLaunchRows<1024, false>(s, args, smem, rowSmem))); }
+        if (s->hasS) { CGB_TRY((sweepLaunchRows<1024, true>(s, args, smem, stage))); } else { CGB_TRY((sweepLaunchRows<1024, false>(s, args, smem, stage))); }
     }
     else
     {
-        if (s->hasS) { CGB_TRY((sweepLaunchRows<512, true>(s, args, smem, rowSmem))); } else { CGB_TRY((sweepLaunchRows<512, false>(s, args, smem, rowSmem))); }
+        if (s->hasS) { CGB_TRY((sweepLaunchRows<512, true>(s, args, smem, stage))); } else { CGB_TRY((sweepLaunchRows<512, false>(s, args, smem, stage))); }
     }
     CGB_CUDA(cudaGetLastError());
     if (envInt("COGAPS_SWEEP_TRANSPORT", 1) != 0)
@@ -2120,6 +2143,21 @@ static int sweepUpdate(cgb_sampler *s, uint32_t nSteps)
     else
     {
         s->counters.algorithmicBytes += static_cast<double>(s->L) * (16.0 * static_cast<double>(c.scans1) + 20.0 * static_cast<double>(c.scans2) + 32.0 * static_cast<double>(c.scansX) + 4.0 * static_cast<double>(c.commits));
+    }
+    if (args.profile != 0u)
+    {
+        // debug: where thread 0 of a row's CTA spends its cycles, per evaluated proposal
+        const double nEval = static_cast<double>(std::max<unsigned long long>(1ull, c.scans1 + c.scans2));
+        static const char *const names[8] = {"wait:published", "scan+reduce", "decide", "wait:decided", "commit", "propose next", "no-eval proposals", "tail"};
+        std::fprintf(stderr, "[sweep profile L=%u T=%u rows=%llu evals=%.0f steps=%llu kernel %.3f ms] cycles per evaluated proposal:", s->L, T,
+                     c.rowsActive, nEval, c.steps, ms);
+        double tot = 0.0;
+        for (int i = 0; i < 8; ++i)
+        {
+            std::fprintf(stderr, " %s %.0f;", names[i], static_cast<double>(c.phase[i]) / nEval);
+            tot += static_cast<double>(c.phase[i]);
+        }
+        std::fprintf(stderr, " total %.0f\n", tot / nEval);
     }
     s->swTotalAtoms = static_cast<uint64_t>(static_cast<long long>(s->swTotalAtoms) + c.atomDelta);
     s->swOverflow += c.overflow;
@@ -2551,6 +2589,20 @@ static int cgb_sampler_set_persistent_body(cgb_sampler *s, int32_t enabled)
 extern "C" int cgb_sampler_set_persistent(cgb_sampler *s, int32_t enabled)
 {
     return guarded("cgb_sampler_set_persistent", [&]() { return cgb_sampler_set_persistent_body(s, enabled); });
+}
+
+static int cgb_sampler_set_resident_share_body(cgb_sampler *s, int32_t parts)
+{
+    CGB_CHECK(s != nullptr, "cgb_sampler_set_resident_share: NULL sampler");
+    CGB_CHECK(parts >= 1 && parts <= 64, "cgb_sampler_set_resident_share: parts must be in 1..64");
+    CGB_CHECK(s->persistentGrid == 0, "cgb_sampler_set_resident_share: the sampler's resident grid has already been sized (call before the first update)");
+    s->residentShare = parts;
+    return CGB_OK;
+}
+
+extern "C" int cgb_sampler_set_resident_share(cgb_sampler *s, int32_t parts)
+{
+    return guarded("cgb_sampler_set_resident_share", [&]() { return cgb_sampler_set_resident_share_body(s, parts); });
 }
 
 static int cgb_sampler_reduction_order_body(const cgb_sampler *s, cgb_reduction_order *out)

@@ -302,6 +302,7 @@ struct cgb_sampler
     uint64_t *dSwPos;             // [nRows][swCap] positions relative to the row's segment of the atomic domain
     float *dSwMass;               // [nRows][swCap]
     uint32_t *dSwCount;           // [nRows]
+    uint32_t *dSwOrder;           // [nRows] rows by decreasing atom count: the order CTAs take them in (sweep_order_kernel)
     uint32_t swCap;
     void *dSwCounters;            // cgb::SweepCounters
     void *hSwCounters;            // pinned copy
@@ -350,6 +351,7 @@ struct cgb_sampler
     size_t aliveNext;                     // round-robin cursor into aliveList
     uint32_t aliveLooks;                  // posts since the launch: cadence of the look for newly started clusters
     int persistentGrid;           // CTAs of the resident grid (0 until first launch)
+    int residentShare;            // this sampler's grid takes 1/share of the device (0: the process default)
     uint32_t nClusters;           // worker clusters of the resident grid (one more cluster mirrors the commit count)
     double lastPostTime;
     uint32_t chunkTag;            // low 31 bits of mailSeq for the chunk being posted

@@ -31,6 +31,7 @@ struct SweepCounters
     long long atomDelta;          // change of the total atom count
     unsigned int maxCount;        // largest per-row atom count after the sweep
     unsigned int pad;
+    unsigned long long phase[8];  // COGAPS_SWEEP_PROFILE: SM cycles thread 0 spent per phase of a proposal, summed over rows
 };
 
 struct SweepArgs
@@ -41,13 +42,14 @@ struct SweepArgs
     uint32_t *count;      // [nRows]
     const float *qgamma;  // truncGammaUpper's table (same-bin exchanges)
     SweepCounters *counters;
+    const uint32_t *order; // rows in the order they are handed to CTAs (sweep_order_kernel), or NULL: by index
     uint64_t key;         // Philox key: one seeder value per update()
     uint64_t binLength;
     uint64_t binMagic;    // floor(2^64 / binLength): floor(x / binLength) = mulhi(x, binMagic) + {0,1,2}
     double birthRow, deathAtom, moveAtom, exchAtom, perAtom; // proposal weights, see sweepRates() in cogaps_b200.cu
     uint32_t cap, nSteps;
     uint32_t colour;      // transport kernel: pairs (r, r+1) with r = colour, colour + 2, ...
-    uint32_t pad;
+    uint32_t profile;     // debug: thread 0 clocks the phases of every proposal into counters->phase
 };
 
 // Philox4x32-10 (Salmon et al., SC'11) block function
@@ -134,13 +136,14 @@ struct SweepSmem
     uint32_t pad;
     float baseS, baseMu;  // sparse model: the Z-table terms of the scan in flight
     uint32_t warpCnt[kSparseGroup * (kSparseThreads / 32)]; // sparse model: compaction counters of sparse_scan_row
+    unsigned long long phase[8]; // debug profile (SweepArgs::profile)
 };
 
-static const uint32_t kSweepHdrBytes = 640;
+static const uint32_t kSweepHdrBytes = 768;
 static_assert(sizeof(SweepSmem) <= kSweepHdrBytes, "SweepSmem outgrew its slot");
 static const uint32_t kSweepDrawBytes = kSweepDrawRing * sizeof(SweepDraw);
 
-// dynamic shared memory of one CTA: [SweepSmem | 640][draw ring][pos: cap u64][mass: cap f32][M row: k f32]
+// dynamic shared memory of one CTA: [SweepSmem | 768][draw ring][pos: cap u64][mass: cap f32][M row: k f32]
 // [canUseGibbs: k i32] then, 128-byte aligned, the staged lines D, AP (, S) of `ld` floats each when the row is kept in
 // shared memory
 __host__ __device__ inline uint32_t sweepRowOffset(uint32_t cap, uint32_t k)
@@ -417,8 +420,16 @@ __device__ __forceinline__ bool sweep_decide(const ModelView &mv, SweepCtl *ctl,
     return v.out.accepted != 0u;
 }
 
-template <int T, int NV, bool HAS_S, bool ROW_SMEM>
-__global__ void __launch_bounds__(T, (T <= 128 ? 5 : (T <= 256 ? 4 : 1))) sweep_kernel(const __grid_constant__ SweepArgs a)
+// STAGE: what a row keeps in shared memory for the length of the update — 1: its D and AP lines (and S), 2: its AP line only
+// (the one that changes; D, read-only, comes through L2 like the factor columns, and twice as many rows fit on an SM),
+// 0: nothing (rows beyond shared memory).  Same arithmetic, same bits in all three.
+__host__ __device__ constexpr int sweepMinBlocks(int T, int STAGE)
+{
+    return STAGE == 2 ? (T <= 128 ? 8 : (T <= 256 ? 4 : (T <= 512 ? 2 : 1))) : (T <= 128 ? 5 : (T <= 256 ? 4 : 1));
+}
+
+template <int T, int NV, bool HAS_S, int STAGE>
+__global__ void __launch_bounds__(T, sweepMinBlocks(T, STAGE)) sweep_kernel(const __grid_constant__ SweepArgs a)
 {
     extern __shared__ __align__(128) unsigned char smemRaw[];
     const ModelView &mv = a.mv;
@@ -431,7 +442,7 @@ __global__ void __launch_bounds__(T, (T <= 128 ? 5 : (T <= 256 ? 4 : 1))) sweep_
     const uint32_t rowPad = mv.ld; // floats per line, multiple of 32
     float *stage = reinterpret_cast<float*>(smemRaw + sweepRowOffset(a.cap, mv.k));
     const uint32_t tid = threadIdx.x;
-    const uint32_t row = blockIdx.x;
+    const uint32_t row = a.order != nullptr ? a.order[blockIdx.x] : blockIdx.x;
     const uint32_t L = mv.L;
     const size_t rowOff = static_cast<size_t>(row) * mv.ld;
 
@@ -449,7 +460,7 @@ __global__ void __launch_bounds__(T, (T <= 128 ? 5 : (T <= 256 ? 4 : 1))) sweep_
         hdr->steps = steps;
         hdr->count = cnt;
         hdr->dirty = 0u;
-        if (ROW_SMEM && steps > 0u)
+        if (STAGE != 0 && steps > 0u)
         {
             mbar_init(&hdr->bar, 1);
             fence_mbar_init();
@@ -464,7 +475,7 @@ __global__ void __launch_bounds__(T, (T <= 128 ? 5 : (T <= 256 ? 4 : 1))) sweep_
     //      draws of its first proposals ----
     const float *bufD, *bufS = nullptr;
     float *bufAP;
-    if (ROW_SMEM)
+    if (STAGE == 1)
     {
         bufD = stage;
         bufAP = stage + rowPad;
@@ -476,6 +487,18 @@ __global__ void __launch_bounds__(T, (T <= 128 ? 5 : (T <= 256 ? 4 : 1))) sweep_
             bulk_g2s(stage, mv.D + rowOff, bytes, &hdr->bar);
             bulk_g2s(stage + rowPad, mv.AP + rowOff, bytes, &hdr->bar);
             if (HAS_S) { bulk_g2s(stage + 2u * rowPad, mv.S + rowOff, bytes, &hdr->bar); }
+        }
+    }
+    else if (STAGE == 2)
+    {
+        bufD = mv.D + rowOff;
+        bufAP = stage;
+        if (HAS_S) { bufS = mv.S + rowOff; }
+        if (tid == 0)
+        {
+            const uint32_t bytes = ((L + 3u) & ~3u) * 4u;
+            mbar_expect_tx(&hdr->bar, bytes);
+            bulk_g2s(stage, mv.AP + rowOff, bytes, &hdr->bar);
         }
     }
     else
@@ -496,13 +519,30 @@ __global__ void __launch_bounds__(T, (T <= 128 ? 5 : (T <= 256 ? 4 : 1))) sweep_
         sCan[c] = mv.otherColNonzero[c];
     }
     __syncthreads();
-    if (ROW_SMEM) { mbar_wait(&hdr->bar, 0u); }
+    if (STAGE != 0) { mbar_wait(&hdr->bar, 0u); }
 
     unsigned long long nScan1 = 0ull, nScan2 = 0ull, nCommit = 0ull, nOverflow = 0ull;
     SweepPick pick;
     pick.idx = pick.idx2 = 0u;
     pick.newPos = 0ull;
     float4 keep1[NV > 0 ? NV : 1], keep2[NV > 0 ? NV : 1];
+    const bool prof = a.profile != 0u && tid == 0;
+    long long tPrev = 0;
+    if (prof)
+    {
+        for (int i = 0; i < 8; ++i) { hdr->phase[i] = 0ull; }
+        tPrev = clock64();
+    }
+    // phase p ends here: the cycles since the previous mark are its
+    auto mark = [&](int p)
+    {
+        if (prof)
+        {
+            const long long now = clock64();
+            hdr->phase[p] += static_cast<unsigned long long>(now - tPrev);
+            tPrev = now;
+        }
+    };
     if (tid == 0) { sweep_propose(a, row, draws[0], sPos, sMass, sCan, cnt, &hdr->ctl[0], &pick, &nOverflow); }
     for (uint32_t step = 0; step < steps; ++step)
     {
@@ -514,10 +554,12 @@ __global__ void __launch_bounds__(T, (T <= 128 ? 5 : (T <= 256 ? 4 : 1))) sweep_
             if (tid >= 32u && tid < 64u && base + (tid - 32u) < steps) { sweep_make_draw(a.key, row, base + (tid - 32u), 0u, &draws[(base + (tid - 32u)) % kSweepDrawRing]); }
         }
         __syncthreads(); // proposal `step` is published
+        mark(0);
         const uint32_t type = ctl->type;
         if (type == 0u)
         {
             if (tid == 0 && step + 1u < steps) { sweep_propose(a, row, draws[(step + 1u) % kSweepDrawRing], sPos, sMass, sCan, cnt, &hdr->ctl[(step + 1u) & 1u], &pick, &nOverflow); }
+            mark(6);
             continue;
         }
         const uint32_t c1 = ctl->c1, c2 = ctl->c2;
@@ -532,6 +574,7 @@ __global__ void __launch_bounds__(T, (T <= 128 ? 5 : (T <= 256 ? 4 : 1))) sweep_
             else { sweep_scan<T, NV, HAS_S, false, false>(bufD, bufS, bufAP, gV1, gV2, L, 0.f, accS, accMu, keep1, keep2); }
         }
         sweep_reduce<T>(hdr, accS, accMu);
+        mark(1);
         if (tid == 0)
         {
             // ---- decision and the atom bookkeeping of AsynchronousGibbsSampler::birth/death/move/exchange ----
@@ -568,7 +611,9 @@ __global__ void __launch_bounds__(T, (T <= 128 ? 5 : (T <= 256 ? 4 : 1))) sweep_
                 sMass[pick.idx2] = out.mass2;
             }
         }
+        mark(2);
         __syncthreads(); // the decision is published
+        mark(3);
         // ---- commit in place: AP[row,:] += d1 * other[:,c1] (+ d2 * other[:,c2]), updateAPMatrix
         //      (DenseNormalModel.cpp:243-258); a thread rewrites exactly the elements it scans, so no barrier follows ----
         const uint32_t flags = ctl->flags;
@@ -609,14 +654,21 @@ __global__ void __launch_bounds__(T, (T <= 128 ? 5 : (T <= 256 ? 4 : 1))) sweep_
                 if (flags & 2u) { sweep_axpy<T>(bufAP, gV2, d2, L); }
             }
         }
+        mark(4);
         if (tid == 0 && step + 1u < steps) { sweep_propose(a, row, draws[(step + 1u) % kSweepDrawRing], sPos, sMass, sCan, cnt, &hdr->ctl[(step + 1u) & 1u], &pick, &nOverflow); }
+        mark(5);
     }
     if (tid == 0) { hdr->count = cnt; }
     __syncthreads();
+    if (prof)
+    {
+        mark(7);
+        for (int i = 0; i < 8; ++i) { atomicAdd(&a.counters->phase[i], hdr->phase[i]); }
+    }
 
     // ---- write the row back: its AP line (if any proposal changed it) and its atoms ----
     const uint32_t cntEnd = hdr->count;
-    if (ROW_SMEM && hdr->dirty != 0u)
+    if (STAGE != 0 && hdr->dirty != 0u)
     {
         float *apRow = mv.AP + rowOff;
         const uint32_t nVec = (L + kVec - 1) / kVec;
@@ -652,7 +704,7 @@ __global__ void __launch_bounds__(T, (T <= 128 ? 5 : (T <= 256 ? 4 : 1))) sweep_
 // no AP line to stage: what stays in shared memory across the row's proposals is its factor row in both copies (the row
 // copy, and the column copy in which values below epsilon are stored as 0, data_structures/HybridMatrix.cpp:25-39);
 // the scan itself is the exact path's (sparse_scan_row: compact the common non-zeros, gather the other factor's rows).
-// dynamic shared memory: [SweepSmem | 640][draw ring][pos][mass][sRow: ldR f32][sCol: k f32][canUseGibbs: k i32], then
+// dynamic shared memory: [SweepSmem | 768][draw ring][pos][mass][sRow: ldR f32][sCol: k f32][canUseGibbs: k i32], then
 // 128-byte aligned [sIdx][sD][sV1][sV2], kSparseThreads * kSparseGroup entries each
 // ------------------------------------------------------------------------------------------------
 __host__ __device__ inline uint32_t sweepSparseScanOffset(uint32_t cap, uint32_t k, uint32_t ldR)
@@ -678,7 +730,7 @@ __global__ void __launch_bounds__(kSparseThreads, 4) sweep_sparse_kernel(const _
     float *sV1 = sD + kSparseThreads * kSparseGroup;
     float *sV2 = sV1 + kSparseThreads * kSparseGroup;
     const uint32_t tid = threadIdx.x;
-    const uint32_t row = blockIdx.x;
+    const uint32_t row = a.order != nullptr ? a.order[blockIdx.x] : blockIdx.x;
 
     uint32_t cnt = 0u;
     if (tid == 0)
@@ -1115,6 +1167,49 @@ __global__ void __launch_bounds__(T, (T <= 256 ? 4 : (T <= 512 ? 2 : 1))) sweep_
         if (nCommit) { atomicAdd(&c->commits, nCommit); }
         if (nOverflow) { atomicAdd(&c->overflow, nOverflow); }
     }
+}
+
+// Rows by decreasing atom count.  A row's chain is sequential and its length is proportional to its atom count, so a long
+// row that starts late is what the whole launch ends up waiting for; CTAs are handed out in blockIdx order, so the longest
+// chains go first.  Which CTA runs a row does not enter its result (the draws are countered by row, not by CTA).
+// One CTA: histogram of min(count, bins - 1), offsets from the top bin down, scatter.
+static const uint32_t kSweepOrderBins = 1024;
+
+__global__ void __launch_bounds__(1024) sweep_order_kernel(const uint32_t *count, uint32_t nRows, uint32_t *order)
+{
+    __shared__ uint32_t hist[kSweepOrderBins];
+    __shared__ uint32_t warpTot[32];
+    const uint32_t tid = threadIdx.x;
+    hist[tid] = 0u;
+    __syncthreads();
+    for (uint32_t r = tid; r < nRows; r += 1024u) { atomicAdd(&hist[min(count[r], kSweepOrderBins - 1u)], 1u); }
+    __syncthreads();
+    // thread t owns bin (bins - 1 - t): its rows start after those of all higher bins
+    const uint32_t mine = hist[kSweepOrderBins - 1u - tid];
+    uint32_t incl = mine;
+    for (int off = 1; off < 32; off <<= 1)
+    {
+        const uint32_t up = __shfl_up_sync(0xffffffffu, incl, off);
+        if ((tid & 31u) >= static_cast<uint32_t>(off)) { incl += up; }
+    }
+    if ((tid & 31u) == 31u) { warpTot[tid >> 5] = incl; }
+    __syncthreads();
+    if (tid < 32u)
+    {
+        uint32_t w = warpTot[tid];
+        for (int off = 1; off < 32; off <<= 1)
+        {
+            const uint32_t up = __shfl_up_sync(0xffffffffu, w, off);
+            if (tid >= static_cast<uint32_t>(off)) { w += up; }
+        }
+        warpTot[tid] = w;
+    }
+    __syncthreads();
+    const uint32_t before = (tid >= 32u ? warpTot[(tid >> 5) - 1u] : 0u) + incl - mine;
+    __syncthreads();
+    hist[kSweepOrderBins - 1u - tid] = before;
+    __syncthreads();
+    for (uint32_t r = tid; r < nRows; r += 1024u) { order[atomicAdd(&hist[min(count[r], kSweepOrderBins - 1u)], 1u)] = r; }
 }
 
 // largest per-row atom count (rows the sweep did not visit keep theirs): the host sizes the store from it

@@ -246,6 +246,10 @@ class GibbsSampler(object):
     def setPersistent(self, enabled):
         check(lib().cgb_sampler_set_persistent(self._h, int(bool(enabled))))
 
+    def setResidentShare(self, parts):
+        """this sampler's resident grid takes 1/parts of the device (before its first update)"""
+        check(lib().cgb_sampler_set_resident_share(self._h, int(parts)))
+
     def setUpdateMode(self, mode):
         """0: the reference's chain, proposal for proposal; 1: row-parallel sweep (cgb_sampler_set_update_mode)"""
         check(lib().cgb_sampler_set_update_mode(self._h, int(mode)))

@@ -63,6 +63,7 @@ int cgb_set_device(int device);
  * beside the others.  Call with the number of chains that will run at once BEFORE creating their samplers; each
  * resident grid then takes 1/parts of the device.  Default 1. */
 int cgb_set_resident_share(int32_t parts);
+/* (the per-handle form, cgb_sampler_set_resident_share below, needs no process-wide setting) */
 /* number of kernel launches issued by this library since process start (bench.py gpu_launches) */
 uint64_t cgb_kernel_launch_count(void);
 
@@ -288,6 +289,9 @@ int cgb_sampler_set_kernel_timing(cgb_sampler *s, int32_t enabled);
  * its batch is still being generated.  0: one eval-kernel launch per conflict-free batch.  Both run the same
  * device code and give bit-identical chains. */
 int cgb_sampler_set_persistent(cgb_sampler *s, int32_t enabled);
+/* This sampler's resident grid takes 1/parts of the device (several chains on one GPU, one host thread each).  Per
+ * handle, no process-wide state; call before the sampler's first update().  Default: cgb_set_resident_share's value. */
+int cgb_sampler_set_resident_share(cgb_sampler *s, int32_t parts);
 
 /* The device reduction order of the scan, so a checker can reproduce it bit-for-bit:
  * a row of length L is cut into `nSegments` contiguous segments of `segmentLength` floats;
