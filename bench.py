@@ -77,6 +77,16 @@ def load_peaks():
     return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
 
 
+def sweep_traffic(args):
+    """DRAM bytes per sweep_kernel launch (dram__bytes_read.sum + dram__bytes_write.sum, one ncu --set full capture,
+    profiles/sweep_kernel_traffic.json) — quoted only for the workload it was captured on"""
+    path = os.path.join(ROOT, "profiles", "sweep_kernel_traffic.json")
+    if (args.rows, args.cols, args.patterns) != (20000, 5000, 20) or not os.path.exists(path):
+        return None
+    with open(path) as f:
+        return json.load(f).get("dram_bytes_per_launch")
+
+
 class ClockSampler(object):
     """nvidia-smi clocks / throttle reasons, sampled every 100 ms from before the ramp; the JSON line reports the
     samples that fall inside the timed region (plus the nearest one on either side when the region is short)."""
@@ -255,8 +265,12 @@ def main():
               else "asynchronous, dense normal model, default uncertainty",
               "step": "one MCMC iteration: A.update(Poisson(atomsA)) + P.sync + P.update(Poisson(atomsP)) + A.sync",
               "ramp_iterations": args.ramp,
-              "device_mode": "resident grid per update(); each proposal streamed to its cluster through pinned host memory as it is generated; per-row commit versions instead of grid barriers"
-              if os.environ.get("COGAPS_PERSISTENT", "1") != "0" else "one eval-kernel launch per batch",
+              "device_mode": {"sweep": "one sweep_kernel launch per update(): one CTA per factor row, rows handed out longest chain first; "
+                                       "a row of up to 10240 floats keeps its D and AP lines in shared memory (4 rows per SM), a longer one "
+                                       "its AP line only (D through L2, 2 rows per SM); then one sweep_transport_kernel launch",
+                              "exact": "resident grid per update(); each proposal streamed to its cluster through pinned host memory as it "
+                                       "is generated; per-row commit versions instead of grid barriers"
+                                       if os.environ.get("COGAPS_PERSISTENT", "1") != "0" else "one eval-kernel launch per batch"},
               "l2": ("sparse model: per-proposal traffic is gathers of factor rows (k floats) at the row's non-zeros; "
                      "the CSR rows + both factors exceed L2 at 50000x30000, no flush needed") if args.sparse
               else "inputs larger than L2: 1.6 GB of resident D/AP streamed ~40 GB per step, no flush needed",
@@ -367,7 +381,7 @@ def main():
                               "frac": kbytes / max(ktime, 1e-12) / 1e9 / peak, "peak_source": peak_src,
                               "algorithmic_bytes_per_launch": kbytes / (2.0 * args.steps),
                               "avg_launch_us": ktime / (2.0 * args.steps) * 1e6, "launches": 2 * args.steps,
-                              "traffic": None,
+                              "traffic": sweep_traffic(args) if dense else None,
                               "A_side": {"GBps": cA.algorithmicBytes / max(cA.secondsKernel, 1e-12) / 1e9},
                               "P_side": {"GBps": cP.algorithmicBytes / max(cP.secondsKernel, 1e-12) / 1e9},
                               "how": "cudaEvent pair on the launching stream around the row sweep + transport launches of every "
@@ -383,7 +397,7 @@ def main():
           sweep["roofline"]["traffic_estimate"] = {
             "bytes_per_launch": (args.rows * L_A + args.cols * L_P) * 4.0 * (lines_in + 1.0) / 2.0,
             "how": "upper bound: (D + AP read, AP written) x every row of both samplers, per update() launch; measured per "
-                   "launch by ncu in profiles/r2_sweep_kernel_ncu.csv"}
+                   "launch by ncu in profiles/r2_sweep_kernel_ncu_final.csv (roofline.traffic)"}
           sweep["roofline"]["dram_frac_estimate"] = sweep["roofline"]["traffic_estimate"]["bytes_per_launch"] / \
             max(ktime / (2.0 * args.steps), 1e-12) / 1e9 / peak
 

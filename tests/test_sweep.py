@@ -251,15 +251,19 @@ def test_sweep_long_rows(oracle, spec, k, its):
 
 @pytest.mark.gpu
 def test_sweep_rows_in_shared_memory_or_not_give_the_same_chain(monkeypatch):
+    """what a row keeps in shared memory (D and AP lines / the AP line only / nothing) and the order rows are handed to
+    CTAs in (longest chain first / by index) are scheduling choices: every output bit is the same"""
     import cogaps_b200 as cg
     data = load_data("syn:203:117:5:11")
     kw = dict(seed=123, nPatterns=5, nIterations=60, outputFrequency=10, updateMode=SWEEP)
     a = cg.gaps_run(data, snapshots=True, snapshotFrequency=20, **kw)
-    monkeypatch.setenv("COGAPS_SWEEP_ROW_SMEM", "0")
-    b = cg.gaps_run(data, snapshots=True, snapshotFrequency=20, **kw)
-    assert np.array_equal(a.atomHistoryA, b.atomHistoryA) and np.array_equal(a.atomHistoryP, b.atomHistoryP)
-    assert np.array_equal(bits(a.snapshotsA), bits(b.snapshotsA)) and np.array_equal(bits(a.snapshotsP), bits(b.snapshotsP))
-    assert np.array_equal(bits(a.Amean), bits(b.Amean))
+    for knob, value in (("COGAPS_SWEEP_STAGE", "0"), ("COGAPS_SWEEP_STAGE", "1"), ("COGAPS_SWEEP_STAGE", "2"), ("COGAPS_SWEEP_ORDER", "0")):
+        monkeypatch.setenv(knob, value)
+        b = cg.gaps_run(data, snapshots=True, snapshotFrequency=20, **kw)
+        monkeypatch.delenv(knob)
+        assert np.array_equal(a.atomHistoryA, b.atomHistoryA) and np.array_equal(a.atomHistoryP, b.atomHistoryP), (knob, value)
+        assert np.array_equal(bits(a.snapshotsA), bits(b.snapshotsA)) and np.array_equal(bits(a.snapshotsP), bits(b.snapshotsP)), (knob, value)
+        assert np.array_equal(bits(a.Amean), bits(b.Amean)), (knob, value)
 
 
 @pytest.mark.gpu
