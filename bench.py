@@ -247,7 +247,8 @@ def main():
     ap.add_argument("--c5-genes", type=int, default=30000)
     ap.add_argument("--c5-cells", type=int, default=200000)
     ap.add_argument("--c5-patterns", type=int, default=50)
-    ap.add_argument("--c5-ramp", type=int, default=40)
+    ap.add_argument("--c5-ramp", type=int, default=150)
+    ap.add_argument("--c5-mode", default="sweep", choices=["sweep", "exact"])
     ap.add_argument("--c5-steps", type=int, default=5)
     ap.add_argument("--chains", type=int, default=0,
                     help="extra leg: this many independent chains on ONE GPU, one host thread each, every resident grid "
@@ -648,7 +649,7 @@ def run_c5(args, rank, world, local_rank, barrier, reduce_max_sum):
     cells = sizes[rank]
     t0 = time.time()
     data = make_data(genes, cells, k, DATA_SEED + 1000 + rank, 0.95)        # genes x this rank's cells (C4 recipe)
-    chain = Chain(data, k, CHAIN_SEED + rank, sparse=True)
+    chain = Chain(data, k, CHAIN_SEED + rank, sparse=True, updateMode=1 if args.c5_mode == "sweep" else 0)
     del data
     chain.ramp(args.c5_ramp)
     setup_s = time.time() - t0
@@ -664,6 +665,9 @@ def run_c5(args, rank, world, local_rank, barrier, reduce_max_sum):
     ev1.record()
     barrier()
     elapsed = ev0.elapsed_time(ev1) * 1e-3
+    if args.c5_mode == "sweep":
+        # the sweep rounds each row's share of the proposals stochastically: count the proposals actually made
+        asked = int(chain.A.counters().nProposalsTotal + chain.P.counters().nProposalsTotal)
     # the C ABI's communicator: rank 0 makes the id, the launcher's process group carries it to the others
     ids = [cg.Comm.unique_id() if rank == 0 else None]
     dist.broadcast_object_list(ids, src=0)
@@ -687,7 +691,7 @@ def run_c5(args, rank, world, local_rank, barrier, reduce_max_sum):
                         % (genes, cells_total, k, world, sizes),
             "value": updates / el, "unit": "atom-updates/s (sum over shards)", "ms_per_step": el / args.c5_steps * 1e3,
             "steps": args.c5_steps, "ramp_iterations": args.c5_ramp, "per_rank_updates_per_s": updates / el / world,
-            "sampler": "asynchronous, sparse normal model, exact mode", "atoms_rank0": atoms, "setup_s_rank0": setup_s,
+            "sampler": "asynchronous, sparse normal model, %s mode" % args.c5_mode, "atoms_rank0": atoms, "setup_s_rank0": setup_s,
             "allgather": {"what": "per-shard P rows (cells x nPatterns), pattern-major device blocks straight from the samplers",
                           "api": "cgb_comm_init + cgb_allgather_rows (ncclAllGather on the library's own stream)",
                           "allgather_us": gm * 1e3, "bytes_per_rank": int(k * ((max(sizes) + 31) // 32 * 32) * 4),

@@ -265,6 +265,84 @@ def test_consensus_recovers_shared_patterns():
     assert np.all(cor.max(axis=1) > 0.99) and sorted(cor.argmax(axis=1).tolist()) == [0, 1, 2]
 
 
+def _naive_complete_linkage(dist, k):
+    """agnes(diss, method="complete") + cutree(k), R/DistributedCogaps.R:206-207, restated the slow way: start from
+    singletons, merge the two clusters whose FARTHEST members are closest until k clusters are left; ids numbered by the
+    first member in column order (what cutree reports)."""
+    clusters = [[i] for i in range(dist.shape[0])]
+    while len(clusters) > k:
+        best = None
+        for a in range(len(clusters)):
+            for b in range(a + 1, len(clusters)):
+                d = max(dist[i, j] for i in clusters[a] for j in clusters[b])
+                if best is None or d < best[0]:
+                    best = (d, a, b)
+        _, a, b = best
+        clusters[a] = sorted(clusters[a] + clusters[b])
+        del clusters[b]
+    clusters.sort(key=lambda c: c[0])
+    ids = np.zeros(dist.shape[0], dtype=int)
+    for n, c in enumerate(clusters):
+        ids[c] = n + 1
+    return ids
+
+
+def test_corcut_against_a_naive_complete_linkage():
+    """corcut (scipy's linkage + fcluster standing in for R's agnes + cutree, R/DistributedCogaps.R:195-217) against the
+    definition of complete linkage written out: same partition of the patterns, clusters in order of first appearance,
+    clusters below minNS dropped — on 40 random pattern sets of 3 to 7 planted groups."""
+    from cogaps_b200.distributed import corcut
+    rng = np.random.default_rng(7)
+    for trial in range(40):
+        groups, per, length = int(rng.integers(3, 8)), int(rng.integers(2, 6)), 50
+        base = rng.random((length, groups))
+        cols = [base[:, g] * rng.uniform(0.5, 2.0) + 0.25 * rng.random(length) for g in range(groups) for _ in range(per)]
+        allPatterns = np.stack([cols[i] for i in rng.permutation(len(cols))], axis=1)
+        cut, minNS = groups, int(rng.integers(1, 4))
+        got = corcut(allPatterns, cut, minNS)
+        c = allPatterns - allPatterns.mean(axis=0, keepdims=True)
+        n = np.sqrt((c * c).sum(axis=0))
+        dist = 1.0 - (c.T @ c) / np.outer(n, n)
+        ids = _naive_complete_linkage(dist, cut)
+        want = [allPatterns[:, ids == i] for i in range(1, cut + 1) if (ids == i).sum() >= minNS]
+        assert len(got) == len(want), trial
+        for g, w in zip(got, want):
+            assert g.shape == w.shape and np.array_equal(g, w), trial
+
+
+def test_pattern_match_known_answer():
+    """patternMatch on a case small enough to follow by hand (R/DistributedCogaps.R:143-177): two clusters of two patterns
+    each; the consensus of a cluster is weighted.mean(row, round(cor(pattern, rowMeans), 3)^3) per row, scaled to a
+    maximum of 1 — written out here with plain Python sums."""
+    from cogaps_b200.distributed import patternMatch
+    a1 = np.array([1.0, 2.0, 3.0, 4.0, 0.5, 0.2])
+    a2 = np.array([1.2, 1.8, 3.3, 3.9, 0.4, 0.1])
+    b1 = np.array([4.0, 0.5, 3.0, 0.1, 2.0, 5.0])
+    b2 = np.array([3.6, 0.9, 2.8, 0.3, 2.4, 4.6])
+    allPatterns = np.stack([a1, b1, a2, b2], axis=1)
+    consensus, clusters = patternMatch(allPatterns, cut=2, minNS=2, maxNS=4)
+    assert len(clusters) == 2
+    assert np.array_equal(clusters[0], np.stack([a1, a2], axis=1)) and np.array_equal(clusters[1], np.stack([b1, b2], axis=1))
+
+    def pearson(x, y):
+        n = len(x)
+        mx, my = sum(x) / n, sum(y) / n
+        sxy = sum((p - mx) * (q - my) for p, q in zip(x, y))
+        return sxy / (sum((p - mx) ** 2 for p in x) * sum((q - my) ** 2 for q in y)) ** 0.5
+
+    for col, (u, v) in enumerate(((a1, a2), (b1, b2))):
+        mean = [(p + q) / 2 for p, q in zip(u, v)]
+        wu, wv = round(pearson(list(u), mean), 3) ** 3, round(pearson(list(v), mean), 3) ** 3
+        want = [(wu * p + wv * q) / (wu + wv) for p, q in zip(u, v)]
+        want = [x / max(want) for x in want]
+        assert np.allclose(consensus[:, col], want, rtol=1e-6), col
+    # a cluster beyond maxNS is cut in two (splitCluster); one that falls below minNS by the cut is dropped
+    six = np.stack([a1, a2, a1 * 1.1 + 0.01, b1, b2, b1 * 0.9 + 0.02], axis=1)
+    consensus2, clusters2 = patternMatch(six, cut=1, minNS=2, maxNS=3)
+    assert sorted(c.shape[1] for c in clusters2) == [3, 3]
+    assert consensus2.shape == (6, 2) and np.allclose(consensus2.max(axis=0), 1.0)
+
+
 class _FakeResult(object):
     def __init__(self, A, P):
         self.featureLoadings, self.sampleFactors = A, P
