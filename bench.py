@@ -532,6 +532,13 @@ def main():
         if dense:
             timings["sync_frac_of_hbm_peak"] = nbytes / (timings["sync_ms"] * 1e-3) / 1e9 / peak
             timings["extra_init_frac_of_hbm_peak"] = 4.0 * args.rows * args.cols / (timings["extra_init_ms"] * 1e-3) / 1e9 / peak
+        # GapsStatistics::meanChiSq (GapsStatistics.cpp:63-87): chi-square of the posterior-mean factors against D, every element
+        # of D read once, the k-term products formed on the fly
+        stats = cg.GapsStatistics(args.rows, args.cols, args.patterns)
+        stats.update(chain.A, chain.P)
+        timings["mean_chisq_ms"] = wall_ms(lambda: stats.meanChiSq(chain.P), 3)
+        timings["mean_chisq_frac_of_hbm_peak"] = 4.0 * args.rows * args.cols / (timings["mean_chisq_ms"] * 1e-3) / 1e9 / peak
+        del stats
     del chain
 
     # ---- several chains sharing the device (the generator of ONE exact-mode chain cannot keep a B200 busy) ----
@@ -692,10 +699,10 @@ def run_c5(args, rank, world, local_rank, barrier, reduce_max_sum):
             "value": updates / el, "unit": "atom-updates/s (sum over shards)", "ms_per_step": el / args.c5_steps * 1e3,
             "steps": args.c5_steps, "ramp_iterations": args.c5_ramp, "per_rank_updates_per_s": updates / el / world,
             "sampler": "asynchronous, sparse normal model, %s mode" % args.c5_mode, "atoms_rank0": atoms, "setup_s_rank0": setup_s,
-            "allgather": {"what": "per-shard P rows (cells x nPatterns), pattern-major device blocks straight from the samplers",
+            "allgather": {"what": "per-shard P rows (cells x nPatterns): the sparse model's row copy, straight from the samplers' device memory",
                           "api": "cgb_comm_init + cgb_allgather_rows (ncclAllGather on the library's own stream)",
-                          "allgather_us": gm * 1e3, "bytes_per_rank": int(k * ((max(sizes) + 31) // 32 * 32) * 4),
-                          "bytes_total": int(k * ((max(sizes) + 31) // 32 * 32) * 4 * world),
+                          "allgather_us": gm * 1e3, "bytes_per_rank": int(max(sizes) * ((k + 3) // 4 * 4) * 4),
+                          "bytes_total": int(max(sizes) * ((k + 3) // 4 * 4) * 4 * world),
                           "every_rank_found_its_own_rows_in_place": bool(oks == world),
                           "checksum_matches_sum_of_shards": bool(abs(checksum - own_sum) <= 1e-6 * max(1.0, abs(own_sum)))},
             "scaling": "strong (the matrix is fixed; each GPU owns cells_total / N cells)"}

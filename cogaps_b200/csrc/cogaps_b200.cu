@@ -3751,7 +3751,10 @@ extern "C" int cgb_comm_init(const uint8_t *id, int32_t rank, int32_t nRanks, cg
 
 // gathers pattern-major device blocks ([k][ld], element (row r, pattern p) at dev[p*ld + r]; rowsPerRank[rank] rows here)
 // of every rank into one row-major host matrix (sum of rows) x k, ranks in order
-static int allgatherRows(cgb_comm *c, const float *dev, uint64_t ld, uint32_t k, const uint32_t *rowsPerRank, float *out, double *deviceMs)
+// dev: this rank's factor block — pattern-major [k][ld] (the dense model's matrix), or, rowMajor, [rows][ld] with k values per
+// row (the sparse model's row copy, the one HybridMatrix -> Matrix conversions and cgb_sampler_get_matrix read)
+static int allgatherRows(cgb_comm *c, const float *dev, uint64_t ld, uint32_t k, const uint32_t *rowsPerRank, float *out, double *deviceMs,
+                         bool rowMajor = false)
 {
     CGB_CHECK(c && dev && rowsPerRank && out, "cgb_allgather_rows: NULL argument");
     CGB_CUDA(cudaSetDevice(c->device));
@@ -3759,9 +3762,10 @@ static int allgatherRows(cgb_comm *c, const float *dev, uint64_t ld, uint32_t k,
     uint64_t totalRows = 0;
     for (int r = 0; r < c->nRanks; ++r) { maxRows = std::max(maxRows, rowsPerRank[r]); totalRows += rowsPerRank[r]; }
     const uint32_t mine = rowsPerRank[c->rank];
-    CGB_CHECK(mine <= ld, "cgb_allgather_rows: rowsPerRank[rank] exceeds the block's stride");
-    const size_t ldMax = roundUp(std::max(maxRows, 1u), 32);
-    const size_t sendFloats = static_cast<size_t>(k) * ldMax, recvFloats = sendFloats * c->nRanks;
+    CGB_CHECK(rowMajor ? k <= ld : mine <= ld, "cgb_allgather_rows: rowsPerRank[rank] exceeds the block's stride");
+    const size_t ldMax = rowMajor ? static_cast<size_t>(ld) : roundUp(std::max(maxRows, 1u), 32);
+    const size_t sendFloats = rowMajor ? static_cast<size_t>(std::max(maxRows, 1u)) * ldMax : static_cast<size_t>(k) * ldMax;
+    const size_t recvFloats = sendFloats * c->nRanks;
     if (sendFloats > c->sendFloats)
     {
         cudaFree(c->dSend); c->dSend = nullptr; c->sendFloats = 0;
@@ -3776,8 +3780,12 @@ static int allgatherRows(cgb_comm *c, const float *dev, uint64_t ld, uint32_t k,
     }
     // equal-size blocks for the collective: this rank's k columns, each padded to the widest shard
     CGB_CUDA(cudaMemsetAsync(c->dSend, 0, sendFloats * sizeof(float), c->stream));
-    CGB_CUDA(cudaMemcpy2DAsync(c->dSend, ldMax * sizeof(float), dev, ld * sizeof(float), static_cast<size_t>(mine) * sizeof(float), k,
-                               cudaMemcpyDeviceToDevice, c->stream));
+    if (rowMajor) { CGB_CUDA(cudaMemcpyAsync(c->dSend, dev, static_cast<size_t>(mine) * ld * sizeof(float), cudaMemcpyDeviceToDevice, c->stream)); }
+    else
+    {
+        CGB_CUDA(cudaMemcpy2DAsync(c->dSend, ldMax * sizeof(float), dev, ld * sizeof(float), static_cast<size_t>(mine) * sizeof(float), k,
+                                   cudaMemcpyDeviceToDevice, c->stream));
+    }
     CGB_CUDA(cudaEventRecord(c->ev0, c->stream));
     const int nrc = g_nccl.allGather(c->dSend, c->dRecv, sendFloats, kNcclFloat32, c->comm, c->stream);
     if (nrc != 0) { return ncclFail("cgb_allgather_rows (ncclAllGather)", nrc); }
@@ -3797,7 +3805,7 @@ static int allgatherRows(cgb_comm *c, const float *dev, uint64_t ld, uint32_t k,
         const float *blk = host.data() + static_cast<size_t>(r) * sendFloats;
         for (uint32_t i = 0; i < rowsPerRank[r]; ++i)
         {
-            for (uint32_t p = 0; p < k; ++p) { out[(row0 + i) * k + p] = blk[static_cast<size_t>(p) * ldMax + i]; }
+            for (uint32_t p = 0; p < k; ++p) { out[(row0 + i) * k + p] = rowMajor ? blk[static_cast<size_t>(i) * ldMax + p] : blk[static_cast<size_t>(p) * ldMax + i]; }
         }
         row0 += rowsPerRank[r];
     }
@@ -3811,6 +3819,9 @@ static int cgb_allgather_rows_body(cgb_comm *c, const cgb_sampler *s, const uint
     CGB_CHECK(rowsPerRank[c->rank] == s->nRows, "cgb_allgather_rows: rowsPerRank[rank] is not this sampler's row count");
     CGB_CUDA(cudaSetDevice(s->device));
     CGB_CUDA(cudaStreamSynchronize(s->stream));
+    // the values cgb_sampler_get_matrix returns: the dense model's matrix, the sparse model's row copy (its column copy
+    // stores values below epsilon as 0, data_structures/HybridMatrix.cpp:25-39)
+    if (s->sparse) { return allgatherRows(c, s->dMrows, s->ldR, s->k, rowsPerRank, out, deviceMs, true); }
     return allgatherRows(c, s->dM, s->ldM, s->k, rowsPerRank, out, deviceMs);
 }
 

@@ -491,6 +491,29 @@ def test_distributed_modes_single_process():
     assert not np.isnan(res.sampleFactors).any()
 
 
+@pytest.mark.parametrize("sparse", [0, 1])
+def test_comm_allgather_returns_the_factor_rows(sparse):
+    """cgb_comm_init + cgb_allgather_rows (the C ABI's NCCL communicator) on a one-rank communicator: the rows
+    gathered from device memory are the values cgb_sampler_get_matrix returns — the dense model's matrix, the sparse model's
+    row copy (not its column copy, in which values below epsilon are stored as 0).  tools/dist_check.py and bench.py's c5
+    record cover 2 / 4 / 8 ranks (profiles/r2_dist_check_8gpu.log)."""
+    import bench
+    import cogaps_b200 as cg
+    data = load_data("gist")
+    chain = bench.Chain(data, 4, 17, sparse=bool(sparse), updateMode=1)
+    chain.ramp(60)
+    try:
+        comm = cg.Comm(cg.Comm.unique_id(), 0, 1)
+    except cg.CogapsError as e:
+        pytest.skip("NCCL is not loadable here: %s" % e)
+    for smp in (chain.P, chain.A):
+        want = smp.getMatrix()
+        got = comm.allgatherRows(smp, [want.shape[0]])
+        assert got.shape == want.shape and np.array_equal(got.view(np.uint32), want.view(np.uint32))
+        assert comm.last_ms >= 0.0
+    assert (chain.P.getMatrix() > 0).any()
+
+
 def test_full_size_invariants_20000x5000_k20():
     """BASELINE.json configs[2] at full size (the bench workload), through properties that need no oracle run:
     (1) the resident grid and one launch per batch give the same chain, bit for bit, with 3-CTA clusters on the
