@@ -674,6 +674,39 @@ def test_tier3_chains_agree_with_the_reference_over_seeds(name, k, its, mode):
         assert abs(mr - mg) <= max(tol * abs(mr), sd), what
 
 
+@pytest.mark.parametrize("mode", [0, 1])
+def test_tier3_midsize_chains_agree_with_the_reference(mode):
+    """The same comparison on a matrix between the reference's own data sets and the BASELINE shapes: 1200 x 500, 8
+    patterns, 300 + 300 iterations, six seeds.  The reference's trajectories (scalar build, 20 s per seed on a host core)
+    travel as tests/golden/tier3_midsize_ref.npz (generator: tests/golden/make_tier3_midsize.py); the free-running CUDA
+    chains — exact mode and the row-parallel sweep — are held to them from the end of the annealed transient on: chi-square
+    and meanChiSq inside the seed-to-seed spread (|difference of means| <= 3 standard errors, floor 3 %), atom counts
+    within 0.15 (sweep 0.2) or one seed-to-seed standard deviation."""
+    import cogaps_b200 as cg
+    fix = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "tier3_midsize_ref.npz"))
+    data = load_data(str(fix["spec"]))
+    k, its, freq = int(fix["k"]), int(fix["its"]), int(fix["freq"])
+    R = fix["rows"].astype(np.float64)
+    rows = []
+    for seed in fix["seeds"]:
+        b = cg.gaps_run(data, updateMode=mode, seed=int(seed), nPatterns=k, nIterations=its, outputFrequency=freq)
+        rows.append(np.concatenate([b.atomHistoryA, b.atomHistoryP, b.chisqHistory, [b.meanChiSq]]).astype(np.float64))
+    Gm = np.array(rows)
+    assert Gm.shape == R.shape
+    nh = (R.shape[1] - 1) // 3
+    for j in range(R.shape[1]):
+        if j % nh < 2 and j < 3 * nh:
+            continue                       # annealed transient (temperature < 1 until half of the equilibration phase)
+        mr, mg = R[:, j].mean(), Gm[:, j].mean()
+        sd = np.sqrt(0.5 * (R[:, j].var(ddof=1) + Gm[:, j].var(ddof=1)))
+        se = sd * np.sqrt(2.0 / R.shape[0])
+        tol = (0.2 if mode == 1 else 0.15) if j < 2 * nh else 0.1
+        what = "column %d (%s)" % (j, "atoms" if j < 2 * nh else "chi-square"), mr, mg, sd
+        if j >= 2 * nh:
+            assert abs(mr - mg) <= max(3.0 * se, 0.03 * abs(mr)), what
+        assert abs(mr - mg) <= max(tol * abs(mr), sd), what
+
+
 # ------------------------------------------------------------------------------------------------
 # the reference-side binding, compiled (oracle/cuda_adapter.cpp -> oracle/_ref/libcogaps_ref_adapter.so)
 # ------------------------------------------------------------------------------------------------

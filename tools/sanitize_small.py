@@ -14,6 +14,11 @@ for d, k in ((data, 3), (gist, 4)):
     for extra in (dict(updateMode=1), dict(updateMode=1, useSparseOptimization=1), dict(), dict(useSparseOptimization=1)):
         r = cg.gaps_run(d, seed=3, nPatterns=k, nIterations=its, outputFrequency=its, maxThreads=1, **extra)
         print(d.shape, extra, "updates", r.totalUpdates, "atoms", r.atomHistoryA[-1], r.atomHistoryP[-1], flush=True)
+# rows beyond 10240 floats: 512 threads, only the AP line in shared memory (STAGE 2); 200 rows: handed out longest chain first
+from tests.cases import load_data  # noqa: E402
+long_rows = load_data("syn:20:12000:3:5")
+r = cg.gaps_run(long_rows, seed=3, nPatterns=3, nIterations=max(its // 3, 2), outputFrequency=its, maxThreads=1, updateMode=1)
+print(long_rows.shape, "sweep, long rows", r.totalUpdates, flush=True)
 unc = np.maximum(0.15 * data, 0.2).astype(np.float32)
 r = cg.gaps_run(data, uncertainty=unc, seed=3, nPatterns=3, nIterations=its, outputFrequency=its, maxThreads=1, updateMode=1)
 print("explicit uncertainty", r.totalUpdates, flush=True)
