@@ -610,7 +610,9 @@ static int samplerCreateImpl(const float *data, uint32_t nrow, uint32_t ncol, in
             meanJob.nnz = static_cast<unsigned>(v.size());
             return;
         }
+        const double t0 = nowSeconds();
         runningSum(meanBase, s->nRows, s->L, meanStrideR, meanStrideL, sum, nnz);
+        if (envInt("COGAPS_HOST_PROFILE", 0)) { std::printf("[sampler create] lambda's running sum over %u x %u (%s): %.3f s\n", s->nRows, s->L, meanStrideL == 1 ? "along rows" : "down columns", nowSeconds() - t0); }
         meanJob.sum = sum;
         meanJob.nnz = nnz;
     });

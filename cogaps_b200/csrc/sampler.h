@@ -13,8 +13,15 @@
 #include "host_rng.h"
 
 #include <cuda_runtime.h>
+#include <atomic>
+#include <cstdlib>
+#include <cstring>
+#if defined(__SSE2__)
+#include <emmintrin.h>
+#endif
 #include <new>
 #include <string>
+#include <thread>
 #include <vector>
 
 namespace cgb {
@@ -126,6 +133,207 @@ private:
     bool mUseCachedRng;
 };
 
+// n contiguous elements added, in order, into an fp32 running sum — the bits of `for (i) sum += x[i]` without its chain of
+// dependent floating-point adds.  While the sum stays inside one binade [2^e, 2^(e+1)) it is an integer multiple m * u of
+// its ulp u = 2^(e-23), and RN(m*u + x) = (m + q + r) * u with q = floor(x / u) and r = 1 when the fraction of x / u is above
+// one half, 0 when below — neither depends on m.  Only an exact tie (fraction == 1/2) looks at the sum (round half to
+// even).  So a chunk is summed as integers: one pass without any loop-carried floating-point dependence (four elements at a
+// time) forms the increments and counts the ties, and with no tie the increments just add up.  A chunk with a tie, one
+// whose adds would leave the binade, or one that holds a negative, huge or NaN element is added the plain way — as are the
+// first elements, until the sum is a normal number; after a tie the next 64 chunks go the plain way untried (count data
+// lies on a grid where ties are everywhere).  gaps::nonZeroMean sums 10^8 elements twice per cgb_run at BASELINE configs[2].
+inline void accumulateRun(const float *x, size_t n, float &sum, unsigned &nnz)
+{
+    const size_t kChunk = 1024;
+    float s = sum;
+    unsigned count = nnz;
+    size_t i = 0;
+    uint32_t backoff = 0u; // chunks to add the plain way before the integer route is tried again
+    while (i < n)
+    {
+        const size_t len = (n - i < kChunk) ? n - i : kChunk;
+        const float *c = x + i;
+        bool done = false;
+        if (backoff > 0u) { --backoff; }
+        else if (s >= 1.0e-30f && s < 1.0e30f)
+        {
+            uint32_t bits;
+            std::memcpy(&bits, &s, sizeof(bits));
+            const uint32_t expField = bits >> 23;                       // s in [2^e, 2^(e+1)), e = expField - 127
+            const uint32_t m0 = (bits & 0x007fffffu) | 0x00800000u;     // s = m0 * 2^(e-23)
+            const uint32_t scaleBits = (127u + 23u + 127u - expField) << 23; // 2^(23-e); expField is within 27..227 here
+            float scale;
+            std::memcpy(&scale, &scaleBits, sizeof(scale));
+            uint32_t incSum = 0u, ties = 0u, bad = 0u, pos = 0u;
+            size_t j = 0;
+#if defined(__SSE2__)
+            {
+                // four elements at a time; compare masks are all-ones, so subtracting them counts
+                const __m128 vScale = _mm_set1_ps(scale), vHalf = _mm_set1_ps(0.5f), vTop = _mm_set1_ps(16384.f), vZero = _mm_setzero_ps();
+                __m128i vInc = _mm_setzero_si128(), vTies = _mm_setzero_si128(), vBad = _mm_setzero_si128(), vPos = _mm_setzero_si128();
+                for (; j + 4 <= len; j += 4)
+                {
+                    const __m128 xv = _mm_loadu_ps(c + j);
+                    const __m128 y = _mm_mul_ps(xv, vScale);
+                    const __m128 ok = _mm_and_ps(_mm_cmpge_ps(y, vZero), _mm_cmplt_ps(y, vTop));
+                    const __m128 yy = _mm_and_ps(y, ok);
+                    const __m128i q = _mm_cvttps_epi32(yy);
+                    const __m128 fr = _mm_sub_ps(yy, _mm_cvtepi32_ps(q));
+                    vInc = _mm_sub_epi32(_mm_add_epi32(vInc, q), _mm_castps_si128(_mm_cmpgt_ps(fr, vHalf)));
+                    vTies = _mm_sub_epi32(vTies, _mm_castps_si128(_mm_cmpeq_ps(fr, vHalf)));
+                    vBad = _mm_or_si128(vBad, _mm_castps_si128(_mm_cmpeq_ps(ok, vZero))); // lanes whose mask is all zeros
+                    vPos = _mm_sub_epi32(vPos, _mm_castps_si128(_mm_cmpgt_ps(xv, vZero)));
+                }
+                uint32_t lanes[4];
+                _mm_storeu_si128(reinterpret_cast<__m128i*>(lanes), vInc);
+                incSum = lanes[0] + lanes[1] + lanes[2] + lanes[3];
+                _mm_storeu_si128(reinterpret_cast<__m128i*>(lanes), vTies);
+                ties = lanes[0] + lanes[1] + lanes[2] + lanes[3];
+                _mm_storeu_si128(reinterpret_cast<__m128i*>(lanes), vBad);
+                bad = lanes[0] | lanes[1] | lanes[2] | lanes[3];
+                _mm_storeu_si128(reinterpret_cast<__m128i*>(lanes), vPos);
+                pos = lanes[0] + lanes[1] + lanes[2] + lanes[3];
+            }
+#endif
+            for (; j < len; ++j)
+            {
+                const float xv = c[j];
+                const float y = xv * scale;                             // exact (a power of two), or far below 1/2 if it underflows
+                const bool ok = (y >= 0.f) && (y < 16384.f);            // also false for NaN; 1024 * 16384 = 2^24: no overflow below
+                const float yy = ok ? y : 0.f;
+                const int32_t q = static_cast<int32_t>(yy);
+                const float fr = yy - static_cast<float>(q);
+                incSum += static_cast<uint32_t>(q) + (fr > 0.5f ? 1u : 0u);
+                ties += (fr == 0.5f) ? 1u : 0u;
+                bad |= ok ? 0u : 1u;
+                pos += (xv > 0.f) ? 1u : 0u;
+            }
+            if (bad == 0u && ties == 0u && m0 + incSum < 0x01000000u)
+            {
+                const uint32_t out = (expField << 23) | ((m0 + incSum) & 0x007fffffu);
+                std::memcpy(&s, &out, sizeof(s));
+                count += pos;
+                done = true;
+            }
+            else if (ties != 0u) { backoff = 64u; } // data on a coarse grid (counts): ties everywhere, the plain adds are the faster way
+        }
+        if (!done)
+        {
+            for (size_t j = 0; j < len; ++j)
+            {
+                s += c[j];
+                if (c[j] > 0.f) { ++count; }
+            }
+        }
+        i += len;
+    }
+    sum = s;
+    nnz = count;
+}
+
+// w sampler rows that run down columns r0 .. r0+w-1 of a row-major matrix, gathered into w contiguous rows of L floats:
+// 16 x 16 tiles, so that both the reads and the writes move whole cache lines; a wide strip (64 rows: 256 bytes of every
+// matrix row) keeps the page walks down — every matrix row lies on a page of its own
+inline void gatherStrip(const float *base, uint32_t L, size_t strideL, uint32_t r0, uint32_t w, float *dst)
+{
+    uint32_t j0 = 0;
+    for (; j0 + 16u <= w; j0 += 16u)
+    {
+        float tile[16][16];
+        uint32_t l0 = 0;
+        for (; l0 + 16u <= L; l0 += 16u)
+        {
+            for (uint32_t dl = 0; dl < 16u; ++dl)
+            {
+                const float *src = base + static_cast<size_t>(l0 + dl) * strideL + r0 + j0;
+                for (uint32_t j = 0; j < 16u; ++j) { tile[dl][j] = src[j]; }
+            }
+            for (uint32_t j = 0; j < 16u; ++j)
+            {
+                float *out = dst + static_cast<size_t>(j0 + j) * L + l0;
+                for (uint32_t dl = 0; dl < 16u; ++dl) { out[dl] = tile[dl][j]; }
+            }
+        }
+        for (; l0 < L; ++l0)
+        {
+            const float *src = base + static_cast<size_t>(l0) * strideL + r0 + j0;
+            for (uint32_t j = 0; j < 16u; ++j) { dst[static_cast<size_t>(j0 + j) * L + l0] = src[j]; }
+        }
+    }
+    for (uint32_t l0 = 0; j0 < w && l0 < L; ++l0)
+    {
+        const float *src = base + static_cast<size_t>(l0) * strideL + r0;
+        for (uint32_t j = j0; j < w; ++j) { dst[static_cast<size_t>(j) * L + l0] = src[j]; }
+    }
+}
+
+// The column-walking case of runningSum (below) with the memory side taken off the chain of adds: helper threads gather
+// strips of 16 sampler rows (one cache line's width of the row-major matrix) into contiguous buffers a few strips ahead,
+// the calling thread only adds — same elements, same order, same bits; on a large matrix the call then costs what the
+// dependent adds cost (about 1 ns each) instead of three to four times that.  Returns false (nothing summed) when the
+// matrix is small or threads / buffers cannot be had; the caller then walks the strips itself.
+inline bool runningSumPipelined(const float *base, uint32_t nRows, uint32_t L, size_t strideL, float &sum, unsigned &nnz)
+{
+    const uint32_t B = 16, kSlots = 6, kGatherers = 3;
+    if (static_cast<uint64_t>(nRows) * L < (1ull << 24)) { return false; }
+    {
+        const char *knob = std::getenv("COGAPS_SUM_PIPELINE"); // 0: the calling thread gathers the strips itself
+        if (knob && knob[0] == '0') { return false; }
+    }
+    const uint32_t nStrips = (nRows + B - 1) / B;
+    float *slots = new (std::nothrow) float[static_cast<size_t>(kSlots) * B * L];
+    if (slots == nullptr) { return false; }
+    std::atomic<uint32_t> ready[kSlots];      // strip number + 1 held by the slot
+    for (uint32_t i = 0; i < kSlots; ++i) { ready[i].store(0u); }
+    std::atomic<uint32_t> consumed(0u);       // strips the adder is done with
+    std::atomic<bool> stop(false);
+    auto gather = [&](uint32_t first)
+    {
+        for (uint32_t sIdx = first; sIdx < nStrips && !stop.load(std::memory_order_relaxed); sIdx += kGatherers)
+        {
+            while (sIdx >= consumed.load(std::memory_order_acquire) + kSlots)   // the slot still holds strip sIdx - kSlots
+            {
+                if (stop.load(std::memory_order_relaxed)) { return; }
+                std::this_thread::yield();
+            }
+            float *dst = slots + static_cast<size_t>(sIdx % kSlots) * B * L;
+            const uint32_t r0 = sIdx * B;
+            const uint32_t w = (nRows - r0 < B) ? nRows - r0 : B;
+            gatherStrip(base, L, strideL, r0, w, dst);
+            ready[sIdx % kSlots].store(sIdx + 1u, std::memory_order_release);
+        }
+    };
+    std::thread workers[kGatherers];
+    uint32_t started = 0;
+    try
+    {
+        for (; started < kGatherers; ++started) { workers[started] = std::thread(gather, started); }
+    }
+    catch (...)
+    {
+        stop.store(true);
+        for (uint32_t i = 0; i < started; ++i) { workers[i].join(); }
+        delete[] slots;
+        return false;
+    }
+    float acc = sum;
+    unsigned count = nnz;
+    for (uint32_t sIdx = 0; sIdx < nStrips; ++sIdx)
+    {
+        while (ready[sIdx % kSlots].load(std::memory_order_acquire) != sIdx + 1u) { std::this_thread::yield(); }
+        const float *src = slots + static_cast<size_t>(sIdx % kSlots) * B * L;
+        const uint32_t r0 = sIdx * B;
+        const uint32_t w = (nRows - r0 < B) ? nRows - r0 : B;
+        accumulateRun(src, static_cast<size_t>(w) * L, acc, count);          // the strip's rows lie one after the other
+        consumed.store(sIdx + 1u, std::memory_order_release);
+    }
+    for (uint32_t i = 0; i < kGatherers; ++i) { workers[i].join(); }
+    delete[] slots;
+    sum = acc;
+    nnz = count;
+    return true;
+}
+
 // gaps::nonZeroMean's numerator and denominator (MatrixMath.cpp:39-55): ONE fp32 running sum over the sampler's rows in
 // order, and the count of positive elements.  The order of the additions is the result, so the chain of dependent
 // adds cannot be split; what can be helped is the memory side.  Row r starts at base + r * strideR, its elements are
@@ -153,15 +361,11 @@ inline void runningSum(const float *base, uint32_t nRows, uint32_t L, size_t str
     unsigned nnz = 0;
     if (strideL == 1)
     {
-        for (uint32_t r = 0; r < nRows; ++r)
-        {
-            const float *row = base + static_cast<size_t>(r) * strideR;
-            for (uint32_t l = 0; l < L; ++l)
-            {
-                sum += row[l];
-                if (row[l] > 0.f) { ++nnz; }
-            }
-        }
+        for (uint32_t r = 0; r < nRows; ++r) { accumulateRun(base + static_cast<size_t>(r) * strideR, L, sum, nnz); }
+    }
+    else if (strideR == 1 && runningSumPipelined(base, nRows, L, strideL, sum, nnz))
+    {
+        // strips gathered by helper threads ahead of the chain of adds (below)
     }
     else if (strideR == 1 && strip.reserveFor(L))
     {
@@ -169,20 +373,8 @@ inline void runningSum(const float *base, uint32_t nRows, uint32_t L, size_t str
         for (uint32_t r0 = 0; r0 < nRows; r0 += B)
         {
             const uint32_t w = (nRows - r0 < B) ? nRows - r0 : B;
-            for (uint32_t l = 0; l < L; ++l)
-            {
-                const float *src = base + static_cast<size_t>(l) * strideL + r0;
-                for (uint32_t j = 0; j < w; ++j) { strip.data[static_cast<size_t>(j) * L + l] = src[j]; }
-            }
-            for (uint32_t j = 0; j < w; ++j)
-            {
-                const float *row = strip.data + static_cast<size_t>(j) * L;
-                for (uint32_t l = 0; l < L; ++l)
-                {
-                    sum += row[l];
-                    if (row[l] > 0.f) { ++nnz; }
-                }
-            }
+            gatherStrip(base, L, strideL, r0, w, strip.data);
+            accumulateRun(strip.data, static_cast<size_t>(w) * L, sum, nnz);
         }
     }
     else

@@ -532,6 +532,43 @@ def test_running_sum_behind_lambda_is_order_exact(shape):
         assert n.value == int((data > 0).sum())
 
 
+@pytest.mark.parametrize("family", ["gamma", "counts", "sparse_small", "wide_range", "rare_negative", "rare_huge", "tiny"])
+def test_running_sum_fast_routes_are_order_exact(family):
+    """The same, on matrices large enough for the fast routes (csrc/sampler.h): accumulateRun adds chunks as integer
+    multiples of the sum's ulp while the sum stays in one binade (any tie, binade change, negative, huge or NaN element
+    sends the chunk the plain way), and the column-walking sum has helper threads gather its strips ahead.  Every family
+    below must give the bits of the plain sequential fp32 sum: float data, counts (ties at every turn), mostly zeros, twelve
+    orders of magnitude, rare negatives, rare huge values, values so small the sum stays subnormal for a while."""
+    import ctypes as C
+    from cogaps_b200._lib import lib, check
+    from cogaps_b200._runhelp import fptr
+    rng = np.random.default_rng(len(family))
+    shape = (4200, 4099)                                             # 17.2 M elements: above the pipelining threshold
+    if family == "gamma":
+        data = rng.gamma(2.0, 3.0, shape)
+    elif family == "counts":
+        data = rng.poisson(1.3, shape).astype(np.float64)
+    elif family == "sparse_small":
+        data = rng.random(shape) * 0.004 * (rng.random(shape) < 0.05)
+    elif family == "wide_range":
+        data = np.exp(rng.uniform(-14.0, 14.0, shape))
+    elif family == "rare_negative":
+        data = rng.gamma(2.0, 3.0, shape)
+        data[rng.random(shape) < 1e-5] *= -1.0
+    elif family == "rare_huge":
+        data = rng.gamma(2.0, 3.0, shape)
+        data[rng.random(shape) < 1e-6] = 3.0e12
+    else:
+        data = rng.random(shape) * 1e-44
+    data = np.ascontiguousarray(data, dtype=np.float32)
+    for by_columns, order in ((0, data.ravel()), (1, data.T.ravel())):
+        want = np.add.accumulate(order, dtype=np.float32)[-1]
+        s, n = C.c_float(), C.c_uint32()
+        check(lib().cgb_debug_running_sum(fptr(data), shape[0], shape[1], by_columns, C.byref(s), C.byref(n)))
+        assert np.float32(s.value).view(np.uint32) == np.float32(want).view(np.uint32), (family, by_columns, s.value, want)
+        assert n.value == int((data > 0).sum())
+
+
 def test_distributed_driver_with_named_explicit_sets():
     """explicitSets given by sample name travel through distributedCogaps (R/SubsetData.R:15-29): each subset run sees
     exactly the named columns, and the stitched rows come back in the order of the sets."""
