@@ -33,7 +33,7 @@ EXPORTS = [
     "cgb_run_ex", "cgb_sampler_serialize", "cgb_sampler_deserialize", "cgb_sampler_set_atoms", "cgb_stats_serialize",
     "cgb_stats_deserialize", "cgb_randstate_get_state", "cgb_randstate_set_state", "cgb_rng_get_state", "cgb_rng_set_state",
     "cgb_checkpoint_info_read", "cgb_checkpoint_rewrite", "cgb_read_matrix_csr",
-    "cgb_debug_replay_generator", "cgb_debug_replay_message", "cgb_run_file_ex", "cgb_debug_running_sum", "cgb_write_matrix_csv", "cgb_result_write_files", "cgb_file_col_names", "cgb_debug_domain_fuzz",
+    "cgb_debug_replay_generator", "cgb_debug_replay_message", "cgb_run_file_ex", "cgb_debug_running_sum", "cgb_write_matrix_csv", "cgb_result_write_files", "cgb_file_col_names", "cgb_debug_domain_fuzz", "cgb_release_device_cache",
     "cgb_sampler_set_update_mode", "cgb_sweep_reduction_order_for_length",
     "cgb_sampler_set_resident_share", "cgb_comm_get_unique_id", "cgb_comm_init", "cgb_comm_destroy", "cgb_allgather_rows", "cgb_allgather_device_rows",
 ]

@@ -447,15 +447,106 @@ extern "C" int cgb_reduction_order_for_length(uint32_t rowLength, cgb_reduction_
 
 static int stopPersistent(cgb_sampler *s);
 
+// Matrix-sized device buffers (D, AP, S: 400 MB each at BASELINE configs[2]) are parked here when a sampler is destroyed and
+// handed to the next sampler that asks for the same size on the same device.  cudaFree of such a buffer hands the memory
+// back to the system and the next cudaMalloc maps it afresh: measured on the B200 box, a cgb_run's teardown took anything
+// from 5 ms to 0.9 s and its allocations from 3 to 95 ms, call to call — and callers like distributed CoGAPS run one
+// factorisation after the other.  At most COGAPS_DEVICE_CACHE_MB (default 16384, 0 disables) stay parked;
+// cgb_release_device_cache() frees them.
+struct ParkedBuffer { void *ptr; size_t bytes; int device; };
+static std::mutex g_parkLock;
+static std::vector<ParkedBuffer> g_parked;
+static size_t g_parkedBytes = 0;
+
+static cudaError_t matrixAlloc(void **out, size_t bytes, int device)
+{
+    {
+        std::lock_guard<std::mutex> hold(g_parkLock);
+        for (size_t i = 0; i < g_parked.size(); ++i)
+        {
+            if (g_parked[i].bytes == bytes && g_parked[i].device == device)
+            {
+                *out = g_parked[i].ptr;
+                g_parkedBytes -= bytes;
+                g_parked.erase(g_parked.begin() + static_cast<long>(i));
+                return cudaSuccess;
+            }
+        }
+    }
+    return cudaMalloc(out, bytes);
+}
+
+// the caller has synchronised every stream that touched the buffer
+static void matrixFree(void *ptr, size_t bytes, int device)
+{
+    if (ptr == nullptr) { return; }
+    const size_t limit = static_cast<size_t>(std::max(envInt("COGAPS_DEVICE_CACHE_MB", 16384), 0)) << 20;
+    {
+        std::lock_guard<std::mutex> hold(g_parkLock);
+        if (bytes >= (1u << 20) && g_parkedBytes + bytes <= limit)
+        {
+            try
+            {
+                g_parked.push_back(ParkedBuffer{ptr, bytes, device});
+                g_parkedBytes += bytes;
+                return;
+            }
+            catch (...) { }
+        }
+    }
+    cudaFree(ptr);
+}
+
+extern "C" int cgb_release_device_cache(void)
+{
+    std::vector<ParkedBuffer> drop;
+    {
+        std::lock_guard<std::mutex> hold(g_parkLock);
+        drop.swap(g_parked);
+        g_parkedBytes = 0;
+    }
+    int current = 0;
+    cudaGetDevice(&current);
+    for (size_t i = 0; i < drop.size(); ++i)
+    {
+        cudaSetDevice(drop[i].device);
+        cudaFree(drop[i].ptr);
+    }
+    cudaSetDevice(current);
+    return CGB_OK;
+}
+
 extern "C" void cgb_sampler_destroy(cgb_sampler *s)
 {
     if (!s) { return; }
     cudaSetDevice(s->device);
+    const bool lapOn = envInt("COGAPS_HOST_PROFILE", 0) != 0;
+    double lapT = nowSeconds();
+    auto lap = [&](const char *what)
+    {
+        if (lapOn)
+        {
+            const double now = nowSeconds();
+            if (now - lapT > 2.0e-3) { std::printf("[sampler destroy] %s %.1f ms\n", what, (now - lapT) * 1e3); }
+            lapT = now;
+        }
+    };
     if (s->persistentRunning) { stopPersistent(s); } // never free what a resident grid may still touch
-    cudaFree(s->dD); cudaFree(s->dS); cudaFree(s->dAP); cudaFree(s->dM); cudaFree(s->dColNonzero);
+    if (s->stream) { cudaStreamSynchronize(s->stream); }
+    cudaStreamSynchronize(cudaStreamLegacy);
+    lap("waiting for the streams");
+    {
+        const size_t matBytes = static_cast<size_t>(s->nRows) * s->ld * sizeof(float);
+        matrixFree(s->dD, matBytes, s->device);
+        matrixFree(s->dS, matBytes, s->device);
+        matrixFree(s->dAP, matBytes, s->device);
+    }
+    lap("matrix buffers");
+    cudaFree(s->dM); cudaFree(s->dColNonzero);
     cudaFree(s->dPartials); cudaFree(s->dTickets); cudaFree(s->dReducePartials); cudaFree(s->dPhaseClocks);
     cudaFree(s->dRowVersion); cudaFree(s->dStreamStats);
     cudaFree(s->dSwPos); cudaFree(s->dSwMass); cudaFree(s->dSwCount); cudaFree(s->dSwCounters); cudaFree(s->dSwOrder);
+    lap("small device buffers, sweep store");
     if (s->hSwCounters) { cudaFreeHost(s->hSwCounters); }
     cudaFree(s->dSpRowPtr); cudaFree(s->dSpIdx); cudaFree(s->dSpVal); cudaFree(s->dMrows); cudaFree(s->dZ1); cudaFree(s->dZ2);
     if (s->hCommitsMirror) { cudaFreeHost(const_cast<unsigned long long*>(s->hCommitsMirror)); }
@@ -464,10 +555,13 @@ extern "C" void cgb_sampler_destroy(cgb_sampler *s)
     if (s->hStreamOutcomes) { cudaFreeHost(s->hStreamOutcomes); }
     if (s->hOutcomes) { cudaFreeHost(s->hOutcomes); }
     if (s->hReducePartials) { cudaFreeHost(s->hReducePartials); }
+    lap("pinned host buffers");
     if (s->evStart) { cudaEventDestroy(s->evStart); }
     if (s->evStop) { cudaEventDestroy(s->evStop); }
     if (s->stream) { cudaStreamDestroy(s->stream); }
+    lap("events and stream");
     delete s;
+    lap("host object");
 }
 
 static const int kReduceBlocks = 592; // 148 SMs x 4
@@ -658,9 +752,20 @@ static int samplerCreateImpl(const float *data, uint32_t nrow, uint32_t ncol, in
         const size_t matBytes = static_cast<size_t>(s->nRows) * s->ld * sizeof(float);
         const size_t facBytes = static_cast<size_t>(s->k) * s->ldM * sizeof(float);
 #define CGB_CUDA_BREAK(call) { cudaError_t e__ = (call); if (e__ != cudaSuccess) { rc = fail(e__ == cudaErrorMemoryAllocation ? CGB_ENOMEM : CGB_ECUDA, std::string(#call) + ": " + cudaGetErrorString(e__)); break; } }
+        const bool lapOn = envInt("COGAPS_HOST_PROFILE", 0) != 0;
+        double lapT = nowSeconds();
+        auto lap = [&](const char *what)
+        {
+            if (lapOn)
+            {
+                const double now = nowSeconds();
+                std::printf("[sampler create %ux%u] %s %.1f ms\n", s->nRows, s->L, what, (now - lapT) * 1e3);
+                lapT = now;
+            }
+        };
         CGB_CUDA_BREAK(cudaStreamCreateWithFlags(&s->stream, cudaStreamNonBlocking));
-        CGB_CUDA_BREAK(cudaMalloc(&s->dD, matBytes));
-        if (!s->sparse) { CGB_CUDA_BREAK(cudaMalloc(&s->dAP, matBytes)); }
+        CGB_CUDA_BREAK(matrixAlloc(reinterpret_cast<void**>(&s->dD), matBytes, s->device));
+        if (!s->sparse) { CGB_CUDA_BREAK(matrixAlloc(reinterpret_cast<void**>(&s->dAP), matBytes, s->device)); }
         if (s->sparse)
         {
             const size_t nnz = spIdx.size();
@@ -702,6 +807,7 @@ static int samplerCreateImpl(const float *data, uint32_t nrow, uint32_t ncol, in
         }
         CGB_CUDA_BREAK(cudaEventCreate(&s->evStart));
         CGB_CUDA_BREAK(cudaEventCreate(&s->evStop));
+        lap("allocations (device, pinned host)");
         if (csr)
         {
             // the dense copy the chi-square kernels walk is rebuilt on the device from the rows just uploaded (pageable
@@ -744,6 +850,7 @@ static int samplerCreateImpl(const float *data, uint32_t nrow, uint32_t ncol, in
         // staged, the memset only queued) and the samplers' own streams are non-blocking, i.e. NOT ordered behind
         // the legacy stream these calls use: wait here, before anybody (the twin's transpose first of all) reads D
         CGB_CUDA_BREAK(cudaStreamSynchronize(cudaStreamLegacy));
+        lap("D on the device (upload or transpose of the twin's, incl. waiting for the twin)");
         if (publish)
         {
             publish->sampler = s;
@@ -768,8 +875,13 @@ static int samplerCreateImpl(const float *data, uint32_t nrow, uint32_t ncol, in
         rc = uploadTables(rs);
         // every memset / copy above went through the legacy stream (see the note at the upload of D)
         if (rc == CGB_OK) { CGB_CUDA_BREAK(cudaStreamSynchronize(cudaStreamLegacy)); }
+        lap("memsets, kernel attributes, tables");
     } while (0);
-    meanThread.join();
+    {
+        const double tj = nowSeconds();
+        meanThread.join();
+        if (envInt("COGAPS_HOST_PROFILE", 0)) { std::printf("[sampler create %ux%u] waited %.1f ms more for lambda's running sum\n", s->nRows, s->L, (nowSeconds() - tj) * 1e3); }
+    }
     if (rc != CGB_OK)
     {
         if (publish && publish->state.load() == 0) { publish->state.store(-1); }
@@ -818,7 +930,7 @@ static int cgb_sampler_set_uncertainty_body(cgb_sampler *s, const float *unc, ui
         params->nSubsetIndices, nRows, L, ld, host, 1.f);
     CGB_CHECK(nRows == s->nRows && L == s->L, "cgb_sampler_set_uncertainty: shape differs from the data");
     const size_t matBytes = static_cast<size_t>(s->nRows) * s->ld * sizeof(float);
-    if (!s->dS) { CGB_CUDA(cudaMalloc(&s->dS, matBytes)); }
+    if (!s->dS) { CGB_CUDA(matrixAlloc(reinterpret_cast<void**>(&s->dS), matBytes, s->device)); }
     CGB_CUDA(cudaMemcpy(s->dS, host.data(), matBytes, cudaMemcpyHostToDevice));
     CGB_CUDA(cudaStreamSynchronize(cudaStreamLegacy)); // pageable copy: staged, not necessarily landed
     s->hasS = true;
@@ -3268,11 +3380,13 @@ struct RunGuard
     RunGuard() : rs(nullptr), A(nullptr), P(nullptr), st(nullptr), rng(nullptr) {}
     ~RunGuard()
     {
+        const double t0 = nowSeconds();
         cgb_rng_destroy(rng);
         cgb_stats_destroy(st);
         cgb_sampler_destroy(A);
         cgb_sampler_destroy(P);
         cgb_randstate_destroy(rs);
+        if (envInt("COGAPS_HOST_PROFILE", 0)) { std::printf("[cgb_run] teardown %.3f s\n", nowSeconds() - t0); }
     }
 };
 

@@ -64,6 +64,10 @@ int cgb_set_device(int device);
  * resident grid then takes 1/parts of the device.  Default 1. */
 int cgb_set_resident_share(int32_t parts);
 /* (the per-handle form, cgb_sampler_set_resident_share below, needs no process-wide setting) */
+/* Matrix-sized device buffers of destroyed samplers are kept for the next sampler of the same shape (a cudaFree /
+ * cudaMalloc pair of 400 MB costs up to a second on some calls); this hands them back to the device.  The cache holds
+ * at most COGAPS_DEVICE_CACHE_MB (environment, default 16384; 0 disables it). */
+int cgb_release_device_cache(void);
 /* number of kernel launches issued by this library since process start (bench.py gpu_launches) */
 uint64_t cgb_kernel_launch_count(void);
 

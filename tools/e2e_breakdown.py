@@ -5,7 +5,7 @@ import bench
 import cogaps_b200 as cg
 data = bench.make_data()
 os.environ['COGAPS_HOST_PROFILE'] = '1'
-for it in (100, 100, 100):
+for it in (100, 100, 100, 100, 100):
     t0 = time.perf_counter()
     res = cg.gaps_run(data, seed=42, nPatterns=20, nIterations=it, outputFrequency=0, maxThreads=1, updateMode=1)
     wall = time.perf_counter() - t0
