@@ -603,7 +603,7 @@ def main():
                 "sampler_loop_s": loop_s, "sampler_loop_value": upd / max(loop_s, 1e-9)}
 
     if rank == 0 and not args.no_e2e:
-        sweep["e2e"] = e2e_of(1, 3)
+        sweep["e2e"] = e2e_of(1, 5)
         exact["e2e"] = e2e_of(0, 3)
 
     # ---- BASELINE.json configs[4] on N > 1 GPUs: every rank runs its 200000/N x 30000 k=50 sparse shard, then the NCCL
