@@ -95,9 +95,13 @@ class ClockSampler(object):
          "clocks_event_reasons.sw_power_cap")
 
     def __init__(self, index):
+        """index: a GPU index, a comma-separated list of them (one nvidia-smi process watches them all), or None: no sampling
+        (ranks other than 0 under torchrun — eight polling loops perturb the launches of all ranks)"""
         self.rows = []
         self.proc = None
         self.t_begin = self.t_end = None
+        if index is None:
+            return
         try:
             self.proc = subprocess.Popen(["nvidia-smi", "-i", str(index), "--query-gpu=" + self.Q,
                                           "--format=csv,noheader,nounits", "-lms", "100"],
@@ -353,7 +357,8 @@ def main():
                              "in the same run under exact_mode") if mode == "sweep" else \
                             "exact: the reference's chain proposal for proposal (host generator + resident evaluator grid)"
     data = make_data(args.rows, args.cols, args.patterns, DATA_SEED + rank, args.zeros if args.sparse else 0.0)
-    clocks = ClockSampler(local_rank)
+    # rank 0 watches every GPU of the job (local ranks 0 .. world-1) from one nvidia-smi process
+    clocks = ClockSampler(",".join(str(i) for i in range(world)) if world > 1 else local_rank) if rank == 0 else ClockSampler(None)
     t_setup = time.time()
     # the chain grows to its steady state in sweep mode (seconds instead of minutes), untimed
     chain = Chain(data, args.patterns, CHAIN_SEED + rank, sparse=args.sparse, updateMode=1)

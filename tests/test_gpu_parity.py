@@ -491,6 +491,32 @@ def test_distributed_modes_single_process():
     assert not np.isnan(res.sampleFactors).any()
 
 
+def test_distributed_result_fits_the_data():
+    """What the two-pass distributed driver returns is a factorisation of the WHOLE matrix (R/DistributedCogaps.R:48-119:
+    per-subset runs, consensus matrix, second pass with it held fixed, rows stitched back in place): its chi-square against
+    the data — with the default uncertainty max(0.1 D, 0.1) — must be of the order of a plain run's with the same number of
+    patterns, and far below that of the best rank-0 model (every gene at its mean)."""
+    import cogaps_b200 as cg
+    from tests.cases import synthetic
+    data = synthetic("syn:400:96:4:3")
+    sd = np.maximum(0.1 * data, 0.1)
+
+    def chisq(A, P):
+        return float((((data - A.astype(np.float64) @ P.astype(np.float64).T) / sd) ** 2).sum())
+
+    plain = cg.CoGAPS(data, cg.CogapsParams(nPatterns=4, nIterations=300, seed=7), messages=False, outputFrequency=150)
+    base = chisq(plain.featureLoadings, plain.sampleFactors)
+    null = float((((data - data.mean(axis=1, keepdims=True)) / sd) ** 2).sum())
+    assert base < 0.2 * null
+    for mode, nsets in (("genome-wide", 4), ("single-cell", 3)):
+        p = cg.CogapsParams(nPatterns=4, nIterations=300, seed=7, distributed=mode)
+        p.setParam("nSets", nsets)
+        res = cg.CoGAPS(data, p, messages=False, outputFrequency=150)
+        assert res.featureLoadings.shape == (400, res.sampleFactors.shape[1]) and res.sampleFactors.shape[0] == 96
+        got = chisq(res.featureLoadings, res.sampleFactors)
+        assert got < 3.0 * base and got < 0.3 * null, (mode, got, base, null)
+
+
 @pytest.mark.parametrize("sparse", [0, 1])
 def test_comm_allgather_returns_the_factor_rows(sparse):
     """cgb_comm_init + cgb_allgather_rows (the C ABI's NCCL communicator) on a one-rank communicator: the rows
