@@ -279,7 +279,7 @@ def main():
               "l2": ("sparse model: per-proposal traffic is gathers of factor rows (k floats) at the row's non-zeros; "
                      "the CSR rows + both factors exceed L2 at 50000x30000, no flush needed") if args.sparse
               else "inputs larger than L2: 1.6 GB of resident D/AP streamed ~40 GB per step, no flush needed",
-              "parallelism": "replicas x%d (one independent chain per GPU, no data-path collective)" % world
+              "parallelism": "replicas x%d (one chain per GPU on its own copy of the matrix, same seeds: per-GPU work identical; no data-path collective)" % world
               if world > 1 else "single chain"}
 
     if args.impl == "reference":
@@ -356,12 +356,15 @@ def main():
                              "statistically against it and bit for bit against oracle/; the reference's own chain is measured "
                              "in the same run under exact_mode") if mode == "sweep" else \
                             "exact: the reference's chain proposal for proposal (host generator + resident evaluator grid)"
-    data = make_data(args.rows, args.cols, args.patterns, DATA_SEED + rank, args.zeros if args.sparse else 0.0)
+    # every rank factorises the same synthetic matrix with the same chain seed: weak scaling with the per-GPU work exactly
+    # fixed (with per-rank seeds the replicas' atom counts, and with them the work per step, differed by several per cent
+    # and the max over ranks measured the busiest replica, not the hardware)
+    data = make_data(args.rows, args.cols, args.patterns, DATA_SEED, args.zeros if args.sparse else 0.0)
     # rank 0 watches every GPU of the job (local ranks 0 .. world-1) from one nvidia-smi process
     clocks = ClockSampler(",".join(str(i) for i in range(world)) if world > 1 else local_rank) if rank == 0 else ClockSampler(None)
     t_setup = time.time()
     # the chain grows to its steady state in sweep mode (seconds instead of minutes), untimed
-    chain = Chain(data, args.patterns, CHAIN_SEED + rank, sparse=args.sparse, updateMode=1)
+    chain = Chain(data, args.patterns, CHAIN_SEED, sparse=args.sparse, updateMode=1)
     chain.ramp(args.ramp)
     for _ in range(args.warmup):
         chain.step()
@@ -375,6 +378,15 @@ def main():
         r = timed_steps(chain, args.steps, clocks if mode == "sweep" else None)
         el, (made, launches) = reduce_max_sum(r["elapsed"], [r["made"], r["launches"]])
         cA, cP = r["cA"], r["cP"]
+        per_rank = None
+        if world > 1:
+            # every rank's own step time and kernel time: one straggler, or all of them slower than a lone GPU?
+            mine = torch.tensor([r["elapsed"] / args.steps * 1e3, (cA.secondsKernel + cP.secondsKernel) / args.steps * 1e3, r["host"] / args.steps * 1e3],
+                                dtype=torch.float64, device="cuda")
+            allr = [torch.zeros_like(mine) for _ in range(world)]
+            dist.all_gather(allr, mine)
+            per_rank = {"ms_per_step": [float(t[0]) for t in allr], "kernel_ms_per_step": [float(t[1]) for t in allr],
+                        "host_ms_per_step": [float(t[2]) for t in allr]}
         ktime = cA.secondsKernel + cP.secondsKernel
         kbytes = cA.algorithmicBytes + cP.algorithmicBytes
         sweep = {"value": made / el, "unit": "atom-updates/s", "ms_per_step": el / args.steps * 1e3, "steps": args.steps,
@@ -382,6 +394,7 @@ def main():
                  "atoms": {"A": int(chain.A.nAtoms()), "P": int(chain.P.nAtoms())},
                  "host_ms_per_step": r["host"] / args.steps * 1e3,
                  "kernel_ms_per_step": {"A": cA.secondsKernel / args.steps * 1e3, "P": cP.secondsKernel / args.steps * 1e3},
+                 "per_rank": per_rank,
                  "roofline": {"bound": "hbm", "kernel": ("sweep_kernel" if dense else "sweep_sparse_kernel") + " + sweep_transport_kernel (one update() = one launch of each)",
                               "achieved": kbytes / max(ktime, 1e-12) / 1e9, "peak": peak, "unit": "GB/s",
                               "frac": kbytes / max(ktime, 1e-12) / 1e9 / peak, "peak_source": peak_src,
