@@ -481,20 +481,34 @@ static void matrixFree(void *ptr, size_t bytes, int device)
 {
     if (ptr == nullptr) { return; }
     const size_t limit = static_cast<size_t>(std::max(envInt("COGAPS_DEVICE_CACHE_MB", 16384), 0)) << 20;
+    std::vector<ParkedBuffer> evicted; // the oldest parked buffers make room (freed outside the lock)
+    bool parked = false;
     {
         std::lock_guard<std::mutex> hold(g_parkLock);
-        if (bytes >= (1u << 20) && g_parkedBytes + bytes <= limit)
+        if (bytes >= (1u << 20) && bytes <= limit)
         {
             try
             {
+                while (g_parkedBytes + bytes > limit && !g_parked.empty())
+                {
+                    evicted.push_back(g_parked.front());
+                    g_parkedBytes -= g_parked.front().bytes;
+                    g_parked.erase(g_parked.begin());
+                }
                 g_parked.push_back(ParkedBuffer{ptr, bytes, device});
                 g_parkedBytes += bytes;
-                return;
+                parked = true;
             }
             catch (...) { }
         }
     }
-    cudaFree(ptr);
+    for (size_t i = 0; i < evicted.size(); ++i)
+    {
+        cudaSetDevice(evicted[i].device);
+        cudaFree(evicted[i].ptr);
+    }
+    if (!evicted.empty()) { cudaSetDevice(device); }
+    if (!parked) { cudaFree(ptr); }
 }
 
 extern "C" int cgb_release_device_cache(void)
