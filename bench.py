@@ -88,7 +88,7 @@ def sweep_traffic(args):
 
 
 class ClockSampler(object):
-    """nvidia-smi clocks / throttle reasons, sampled every 100 ms from before the ramp; the JSON line reports the
+    """nvidia-smi clocks / throttle reasons, sampled every 50 ms from before the ramp; the JSON line reports the
     samples that fall inside the timed region (plus the nearest one on either side when the region is short)."""
     Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
          "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
@@ -104,7 +104,7 @@ class ClockSampler(object):
             return
         try:
             self.proc = subprocess.Popen(["nvidia-smi", "-i", str(index), "--query-gpu=" + self.Q,
-                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                          "--format=csv,noheader,nounits", "-lms", "50"],
                                          stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             self.thread = threading.Thread(target=self._read, daemon=True)
             self.thread.start()
@@ -360,8 +360,8 @@ def main():
     # fixed (with per-rank seeds the replicas' atom counts, and with them the work per step, differed by several per cent
     # and the max over ranks measured the busiest replica, not the hardware)
     data = make_data(args.rows, args.cols, args.patterns, DATA_SEED, args.zeros if args.sparse else 0.0)
-    # rank 0 watches every GPU of the job (local ranks 0 .. world-1) from one nvidia-smi process
-    clocks = ClockSampler(",".join(str(i) for i in range(world)) if world > 1 else local_rank) if rank == 0 else ClockSampler(None)
+    # rank 0 watches its own GPU (one polling loop per job: a query over all eight GPUs takes longer than the timed region)
+    clocks = ClockSampler(local_rank) if rank == 0 else ClockSampler(None)
     t_setup = time.time()
     # the chain grows to its steady state in sweep mode (seconds instead of minutes), untimed
     chain = Chain(data, args.patterns, CHAIN_SEED, sparse=args.sparse, updateMode=1)
