@@ -854,7 +854,7 @@ static int samplerCreateImpl(const float *data, uint32_t nrow, uint32_t ncol, in
             }
             const cgb_sampler *t = twin->sampler;
             CGB_CUDA_BREAK(cudaMemsetAsync(s->dD, 0, matBytes, s->stream));
-            dim3 grid((s->L + 31) / 32, (s->nRows + 31) / 32);
+            dim3 grid((s->L + kTransposeTile - 1) / kTransposeTile, (s->nRows + kTransposeTile - 1) / kTransposeTile);
             transpose_kernel<<<grid, 256, 0, s->stream>>>(s->dD, t->dD, s->nRows, s->L, s->ld, t->ld);
             ++g_kernelLaunches;
             CGB_CUDA_BREAK(cudaGetLastError());
@@ -1030,7 +1030,7 @@ static int cgb_sampler_sync_body(cgb_sampler *s, const cgb_sampler *other)
     }
     else
     {
-        dim3 grid((s->L + 31) / 32, (s->nRows + 31) / 32);
+        dim3 grid((s->L + kTransposeTile - 1) / kTransposeTile, (s->nRows + kTransposeTile - 1) / kTransposeTile);
         transpose_kernel<<<grid, 256, 0, s->stream>>>(s->dAP, other->dAP, s->nRows, s->L, s->ld, other->ld);
     }
     ++g_kernelLaunches;

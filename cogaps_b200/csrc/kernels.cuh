@@ -1404,25 +1404,57 @@ __global__ void __launch_bounds__(256) csr_scatter_kernel(const uint32_t *__rest
 // ------------------------------------------------------------------------------------------------
 // sync: dst[r][l] = src[l][r]  (DenseNormalModel::sync, DenseNormalModel.cpp:20-36)
 // ------------------------------------------------------------------------------------------------
+// 64 x 64 tiles, 16-byte loads and stores on both sides (rows are padded to 32 floats, so every tile row starts on a
+// 16-byte boundary); tiles that reach over an edge of the matrix go element by element and never write a pad column.
+static const int kTransposeTile = 64;
+
 __global__ void __launch_bounds__(256) transpose_kernel(float *__restrict__ dst, const float *__restrict__ src,
                                                         uint32_t dstRows, uint32_t dstCols, uint32_t ldDst,
                                                         uint32_t ldSrc)
 {
-    __shared__ float tile[32][33];
-    const uint32_t bx = blockIdx.x * 32, by = blockIdx.y * 32; // bx: dst col block, by: dst row block
-    const uint32_t tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
-#pragma unroll
-    for (int i = 0; i < 32; i += 8)
+    __shared__ float tile[kTransposeTile][kTransposeTile + 1]; // [src row in tile][src col in tile]
+    const uint32_t bx = blockIdx.x * kTransposeTile, by = blockIdx.y * kTransposeTile; // bx: dst col block, by: dst row block
+    const uint32_t t = threadIdx.x;
+    const bool interior = (bx + kTransposeTile <= dstCols) && (by + kTransposeTile <= dstRows);
+    if (interior)
     {
-        const uint32_t srcRow = bx + ty + i, srcCol = by + tx; // src is [dstCols][dstRows]
-        tile[ty + i][tx] = (srcRow < dstCols && srcCol < dstRows) ? src[static_cast<size_t>(srcRow) * ldSrc + srcCol] : 0.f;
+        // src is [dstCols][dstRows]: tile row q = src row bx + q, 16 vectors of 4 along src columns by ..
+#pragma unroll
+        for (int i = 0; i < 4; ++i)
+        {
+            const uint32_t idx = t + 256u * i, q = idx >> 4, c4 = idx & 15u;
+            const float4 v = __ldcs(reinterpret_cast<const float4*>(src + static_cast<size_t>(bx + q) * ldSrc + by) + c4);
+            tile[q][c4 * 4u + 0u] = v.x;
+            tile[q][c4 * 4u + 1u] = v.y;
+            tile[q][c4 * 4u + 2u] = v.z;
+            tile[q][c4 * 4u + 3u] = v.w;
+        }
+        __syncthreads();
+#pragma unroll
+        for (int i = 0; i < 4; ++i)
+        {
+            const uint32_t idx = t + 256u * i, r = idx >> 4, c4 = idx & 15u; // dst row by + r, dst cols bx + 4 c4 ..
+            float4 v;
+            v.x = tile[c4 * 4u + 0u][r];
+            v.y = tile[c4 * 4u + 1u][r];
+            v.z = tile[c4 * 4u + 2u][r];
+            v.w = tile[c4 * 4u + 3u][r];
+            reinterpret_cast<float4*>(dst + static_cast<size_t>(by + r) * ldDst + bx)[c4] = v;
+        }
+        return;
+    }
+    for (uint32_t idx = t; idx < kTransposeTile * kTransposeTile; idx += 256u)
+    {
+        const uint32_t q = idx / kTransposeTile, c = idx % kTransposeTile;
+        const uint32_t srcRow = bx + q, srcCol = by + c;
+        tile[q][c] = (srcRow < dstCols && srcCol < dstRows) ? src[static_cast<size_t>(srcRow) * ldSrc + srcCol] : 0.f;
     }
     __syncthreads();
-#pragma unroll
-    for (int i = 0; i < 32; i += 8)
+    for (uint32_t idx = t; idx < kTransposeTile * kTransposeTile; idx += 256u)
     {
-        const uint32_t dRow = by + ty + i, dCol = bx + tx;
-        if (dRow < dstRows && dCol < dstCols) { dst[static_cast<size_t>(dRow) * ldDst + dCol] = tile[tx][ty + i]; }
+        const uint32_t r = idx / kTransposeTile, c = idx % kTransposeTile;
+        const uint32_t dRow = by + r, dCol = bx + c;
+        if (dRow < dstRows && dCol < dstCols) { dst[static_cast<size_t>(dRow) * ldDst + dCol] = tile[c][r]; }
     }
 }
 
