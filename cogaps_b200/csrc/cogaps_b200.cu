@@ -2100,9 +2100,11 @@ template <class Kernel>
 static int sweepGrowSmemLimit(Kernel kernel, size_t smem)
 {
     static std::mutex lock;
-    static std::map<const void*, size_t> configured; // per instance: every instantiation has the same pointer type
+    static std::map<std::pair<int, const void*>, size_t> configured; // per device and instance (every instantiation has the same pointer type)
+    int device = 0;
+    CGB_CUDA(cudaGetDevice(&device));
     std::lock_guard<std::mutex> hold(lock);
-    size_t &have = configured[reinterpret_cast<const void*>(kernel)];
+    size_t &have = configured[std::make_pair(device, reinterpret_cast<const void*>(kernel))];
     if (have == 0u) { have = 48u * 1024u; }
     if (smem > have)
     {
