@@ -88,8 +88,9 @@ def sweep_traffic(args):
 
 
 class ClockSampler(object):
-    """nvidia-smi clocks / throttle reasons, sampled every 50 ms from before the ramp; the JSON line reports the
-    samples that fall inside the timed region (plus the nearest one on either side when the region is short)."""
+    """SM clock and throttle reasons of the GPU, sampled from before the ramp (NVML every 10 ms; an nvidia-smi loop every
+    50 ms where NVML cannot be had); the JSON line reports the samples that fall inside the timed region (plus the nearest
+    one on either side when the region is short)."""
     Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
          "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
          "clocks_event_reasons.sw_power_cap")
@@ -99,9 +100,22 @@ class ClockSampler(object):
         (ranks other than 0 under torchrun — eight polling loops perturb the launches of all ranks)"""
         self.rows = []
         self.proc = None
+        self.nvml = None
         self.t_begin = self.t_end = None
         if index is None:
             return
+        # NVML in a thread of this process (what nvidia-smi itself reads), every 10 ms: the timed region is about a tenth
+        # of a second, an nvidia-smi loop delivers one sample in that time.  nvidia-smi stays as the fallback.
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            self.nvml = (pynvml, pynvml.nvmlDeviceGetHandleByIndex(int(index)))
+            self.nvml_stop = threading.Event()
+            self.thread = threading.Thread(target=self._poll_nvml, daemon=True)
+            self.thread.start()
+            return
+        except Exception:
+            self.nvml = None
         try:
             self.proc = subprocess.Popen(["nvidia-smi", "-i", str(index), "--query-gpu=" + self.Q,
                                           "--format=csv,noheader,nounits", "-lms", "50"],
@@ -115,6 +129,37 @@ class ClockSampler(object):
         for line in self.proc.stdout:
             self.rows.append((time.perf_counter(), line.strip()))
 
+    def _poll_nvml(self):
+        nv, h = self.nvml
+        try:
+            mx = nv.nvmlDeviceGetMaxClockInfo(h, nv.NVML_CLOCK_SM)
+        except Exception:
+            mx = 0
+        names = (("hw_slowdown", "HwSlowdown"), ("hw_thermal_slowdown", "HwThermalSlowdown"),
+                 ("sw_thermal_slowdown", "SwThermalSlowdown"), ("sw_power_cap", "SwPowerCap"))
+        while not self.nvml_stop.is_set():
+            try:
+                sm = nv.nvmlDeviceGetClockInfo(h, nv.NVML_CLOCK_SM)
+                try:
+                    mask = nv.nvmlDeviceGetCurrentClocksEventReasons(h)
+                except Exception:
+                    mask = nv.nvmlDeviceGetCurrentClocksThrottleReasons(h)
+                try:
+                    watts = nv.nvmlDeviceGetPowerUsage(h) / 1000.0
+                except Exception:
+                    watts = 0.0
+                flags = []
+                for _, suffix in names:
+                    bit = getattr(nv, "nvmlClocksEventReason" + suffix, None)
+                    if bit is None:
+                        bit = getattr(nv, "nvmlClocksThrottleReason" + suffix, 0)
+                    flags.append("Active" if (mask & bit) else "Not Active")
+                # the same row nvidia-smi would print for Q
+                self.rows.append((time.perf_counter(), "%d, %d, %.2f, %s" % (sm, mx, watts, ", ".join(flags))))
+            except Exception:
+                pass
+            self.nvml_stop.wait(0.01)
+
     def begin(self):
         self.t_begin = time.perf_counter()
 
@@ -122,14 +167,18 @@ class ClockSampler(object):
         self.t_end = time.perf_counter()
 
     def stop(self):
-        if self.proc is None:
+        if self.proc is None and self.nvml is None:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
         time.sleep(0.15)   # let the sample that covers the end of the region arrive
-        self.proc.terminate()
-        try:
-            self.proc.wait(timeout=5)
-        except subprocess.TimeoutExpired:
-            self.proc.kill()
+        if self.nvml is not None:
+            self.nvml_stop.set()
+            self.thread.join(timeout=2)
+        else:
+            self.proc.terminate()
+            try:
+                self.proc.wait(timeout=5)
+            except subprocess.TimeoutExpired:
+                self.proc.kill()
         t0 = self.t_begin if self.t_begin is not None else 0.0
         t1 = self.t_end if self.t_end is not None else float("inf")
         inside = [r for r in self.rows if t0 <= r[0] <= t1]
@@ -151,7 +200,8 @@ class ClockSampler(object):
                 if val.lower().startswith("active"):
                     reasons.add(name)
         return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
-                "reasons": sorted(reasons), "samples": len(sm), "samples_inside_timed_region": len(inside)}
+                "reasons": sorted(reasons), "samples": len(sm), "samples_inside_timed_region": len(inside),
+                "source": "NVML, every 10 ms" if self.nvml is not None else "nvidia-smi -lms 50"}
 
 
 class Chain(object):
