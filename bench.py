@@ -328,7 +328,9 @@ def main():
                                        if os.environ.get("COGAPS_PERSISTENT", "1") != "0" else "one eval-kernel launch per batch"},
               "l2": ("sparse model: per-proposal traffic is gathers of factor rows (k floats) at the row's non-zeros; "
                      "the CSR rows + both factors exceed L2 at 50000x30000, no flush needed") if args.sparse
-              else "inputs larger than L2: 1.6 GB of resident D/AP streamed ~40 GB per step, no flush needed",
+              else "inputs larger than L2 (126 MB): 1.6 GB of resident D / AP in two orientations; every update() walks all rows of one "
+                   "orientation (0.8 GB in, the rewritten AP lines out) and every sync rewrites the other's 0.4 GB — nothing a step reads "
+                   "is left in L2 from the step before, no flush needed",
               "parallelism": "replicas x%d (one chain per GPU on its own copy of the matrix, same seeds: per-GPU work identical; no data-path collective)" % world
               if world > 1 else "single chain"}
 
