@@ -154,7 +154,9 @@ __host__ __device__ inline uint32_t sweepRowOffset(uint32_t cap, uint32_t k)
 
 // One scan of the staged row against one or two factor columns read through L2 (DenseNormalModel.cpp:162-240); same
 // element arithmetic and lane order as scan_segment (kernels.cuh).  KEEP: the columns stay in registers for the commit.
-template <int T, int NV, bool HAS_S, bool USE_V2, bool WITH_CHANGE>
+// DG: the D (and S) line lies in global memory and is read past L1 (ld.global.cg) like the columns — the little L1 left beside
+// the staged rows holds the erf / erfinv tables and the one-lane code's stack, which a row streaming through would evict
+template <int T, int NV, bool HAS_S, bool USE_V2, bool WITH_CHANGE, bool DG = false>
 __device__ __forceinline__ void sweep_scan(const float *bufD, const float *bufS, const float *bufAP, const float *gV1,
                                            const float *gV2, uint32_t len, float ch, float &accS, float &accMu,
                                            float4 (&keep1)[NV > 0 ? NV : 1], float4 (&keep2)[NV > 0 ? NV : 1])
@@ -163,10 +165,10 @@ __device__ __forceinline__ void sweep_scan(const float *bufD, const float *bufS,
     const uint32_t nVec = (len + kVec - 1) / kVec;
     auto element = [&](uint32_t j, const float4 &v4, const float4 &w4)
     {
-        const float4 d4 = reinterpret_cast<const float4*>(bufD)[j];
+        const float4 d4 = DG ? __ldcg(reinterpret_cast<const float4*>(bufD) + j) : reinterpret_cast<const float4*>(bufD)[j];
         const float4 a4 = reinterpret_cast<const float4*>(bufAP)[j];
         float4 s4 = make_float4(1.f, 1.f, 1.f, 1.f);
-        if (HAS_S) { s4 = reinterpret_cast<const float4*>(bufS)[j]; }
+        if (HAS_S) { s4 = DG ? __ldcg(reinterpret_cast<const float4*>(bufS) + j) : reinterpret_cast<const float4*>(bufS)[j]; }
         const float d[4] = {d4.x, d4.y, d4.z, d4.w};
         const float a[4] = {a4.x, a4.y, a4.z, a4.w};
         const float v[4] = {v4.x, v4.y, v4.z, v4.w};
@@ -569,9 +571,9 @@ __global__ void __launch_bounds__(T, sweepMinBlocks(T, STAGE)) sweep_kernel(cons
         float accS = 0.f, accMu = 0.f;
         if (ctl->scan != 0u)
         {
-            if (pairType) { sweep_scan<T, NV, HAS_S, true, false>(bufD, bufS, bufAP, gV1, gV2, L, 0.f, accS, accMu, keep1, keep2); }
-            else if (type == 'D') { sweep_scan<T, NV, HAS_S, false, true>(bufD, bufS, bufAP, gV1, gV2, L, -ctl->m1, accS, accMu, keep1, keep2); }
-            else { sweep_scan<T, NV, HAS_S, false, false>(bufD, bufS, bufAP, gV1, gV2, L, 0.f, accS, accMu, keep1, keep2); }
+            if (pairType) { sweep_scan<T, NV, HAS_S, true, false, STAGE == 2>(bufD, bufS, bufAP, gV1, gV2, L, 0.f, accS, accMu, keep1, keep2); }
+            else if (type == 'D') { sweep_scan<T, NV, HAS_S, false, true, STAGE == 2>(bufD, bufS, bufAP, gV1, gV2, L, -ctl->m1, accS, accMu, keep1, keep2); }
+            else { sweep_scan<T, NV, HAS_S, false, false, STAGE == 2>(bufD, bufS, bufAP, gV1, gV2, L, 0.f, accS, accMu, keep1, keep2); }
         }
         sweep_reduce<T>(hdr, accS, accMu);
         mark(1);
