@@ -106,6 +106,12 @@ struct LookupTables
         }
         qgamma[CGB_QGAMMA_TABLE_SIZE - 1] = qGamma2(0.9998f);
     }
+    // the built-in tables, generated once per process (13 000 bisections: 15 ms, which a cgb_run used to pay on every call)
+    static const LookupTables &builtin()
+    {
+        static const LookupTables once = [] { LookupTables t; t.generate(); return t; }();
+        return once;
+    }
 };
 
 // GapsRng on the host: the PCG stream plus the draws the device never makes
@@ -201,7 +207,7 @@ struct HostRng : public Pcg
 // GapsRandomState (math/Random.h:79-98)
 struct cgb_randstate
 {
-    explicit cgb_randstate(uint32_t seed) : seeder(seed), dErf(nullptr), dErfinv(nullptr), dQgamma(nullptr), device(-1) { tables.generate(); }
+    explicit cgb_randstate(uint32_t seed) : seeder(seed), tables(cgb::LookupTables::builtin()), dErf(nullptr), dErfinv(nullptr), dQgamma(nullptr), device(-1) { }
     cgb::Xoroshiro128plus seeder;
     cgb::LookupTables tables;
     float *dErf;     // device copies, uploaded lazily by the first sampler
